@@ -1,0 +1,224 @@
+/* sibrar_b200 -- C ABI of the B200-native (sm_100a) SingleBranchNet hot path.
+ *
+ * The reference (Tigxy/SiBraR---Single-Branch-Recommender) is pure Python/PyTorch and has NO FFI for this path
+ * (SURVEY.md section 8b); its boundary is the Python class API of ``SingleBranchNet``
+ * (``algorithms/sgd_alg.py:2009-2144``, ``algorithms/base_classes.py:87-170``).  The entry points below are what a
+ * ctypes/cffi binding of that class would call; each one names the reference code whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in ``_host``;
+ *   - nothing here allocates, frees or synchronises; work is enqueued on ``stream`` (a ``cudaStream_t``);
+ *   - return value 0 = ok, otherwise an SBR_ERR_* code; ``sbr_last_error()`` gives a thread-local message;
+ *   - "bf16" pointers are ``void*`` (raw __nv_bfloat16); row pitches (``ld*``) are in ELEMENTS.
+ */
+#ifndef SIBRAR_B200_H
+#define SIBRAR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBR_OK 0
+#define SBR_ERR_ARG 1
+#define SBR_ERR_CUDA 2
+
+/* activation ids (reference modules/polylinear.py:5-10) */
+#define SBR_ACT_NONE 0
+#define SBR_ACT_RELU 1
+#define SBR_ACT_TANH 2
+#define SBR_ACT_SIGMOID 3
+#define SBR_ACT_SELU 4
+
+/* modality source kinds for the row gather (reference algorithms/sgd_alg.py:1327-1357, 1373-1389) */
+#define SBR_SRC_TABLE 0       /* fp32 table [n_rows, C] of projected features (Linear(+hidden)+act output)     */
+#define SBR_SRC_CATEGORICAL 1 /* nn.Embedding: weight[cat[row]]                                               */
+#define SBR_SRC_TAG 2         /* nn.EmbeddingBag(mode='mean', padding_idx=-1): mean of weight[tags[row, :]]   */
+
+/* rec losses (reference train/rec_losses.py:116-119) */
+#define SBR_LOSS_BPR 0
+#define SBR_LOSS_BCE 1
+#define SBR_LOSS_SSM 2
+
+const char* sbr_last_error(void);
+int sbr_version(void);
+
+/* ------------------------------------------------------------------------------------------------ GEMM (tcgen05)
+ * D[M,N] = alpha * A * B^T with bf16 operands and fp32 TMEM accumulation, fused epilogue.
+ *   A: K-major  -> memory [M, K] row-major, pitch lda;  MN-major -> memory [K, M] row-major, pitch lda.
+ *   B: K-major  -> memory [N, K] row-major, pitch ldb;  MN-major -> memory [K, N] row-major, pitch ldb.
+ * Replaces nn.Linear forward (modules/polylinear.py:50-76; algorithms/sgd_alg.py:1356,1380,1876) and the autograd
+ * dgrad / wgrad GEMMs of ``total_loss.backward()`` (train/trainer.py:221). */
+typedef struct {
+  const float* bias;      /* [N] added to alpha*acc before stats/activation, or NULL                             */
+  int act;                /* SBR_ACT_* applied after bias                                                         */
+  void* out_bf16;         /* optional bf16 output [M, N]                                                          */
+  int64_t ld_bf16;
+  float* out_f32;         /* optional fp32 output [M, N] ([N, M] if transpose_out)                                */
+  int64_t ld_f32;
+  float* colstats;        /* optional [2*N]: += column sum and sum of squares of (alpha*acc + bias), valid rows   */
+  const void* actgrad_y;  /* optional bf16 [M, N]: result *= act'(y) expressed through the saved output y         */
+  int64_t ld_actgrad;
+  int actgrad_act;
+  int transpose_out;      /* fp32 output written transposed                                                       */
+  int atomic_out;         /* fp32 output accumulated with atomicAdd (needed when split_k > 1)                     */
+  int split_k;            /* number of partitions of the K loop (>= 1)                                            */
+  float alpha;
+} sbr_gemm_epilogue_t;
+
+int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,
+                  int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ casts / fills */
+int sbr_cast_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                         void* stream); /* dst columns [cols, ld_dst) are zero-filled */
+int sbr_transpose_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                              void* stream); /* dst[c, r] = src[r, c] */
+int sbr_csr_to_dense_bf16(const int64_t* indptr, const int32_t* indices, int64_t rows, int64_t cols, void* dst,
+                          int64_t ld_dst, void* stream); /* multi-hot rows (data/Feature.py:147-150) */
+
+/* ------------------------------------------------------------------------------------------------ sparse 'interactions'
+ * out[r, :] = act(sum_{j in csr[r]} Wt[j, :] + bias)  -- Linear over a multi-hot row without densifying it
+ * (replaces data/Feature.py:147-150 + algorithms/sgd_alg.py:1380).  Wt is the TRANSPOSED weight [d, C] fp32.
+ * With bias == NULL and act == NONE the same kernel is the wgrad of that Linear through the transposed CSR:
+ * dWt[j, :] = sum_{r in csrT[j]} dPre[r, :]. */
+int sbr_spmm_csr(const int64_t* indptr, const int32_t* indices, int64_t rows, const float* dense, int64_t ld_dense,
+                 int64_t C, const float* bias, int act, float* out, int64_t ld_out, int transpose_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ modality sampling
+ * Per (row, slot) choose k distinct modalities out of n_mods (optionally slot 0 fixed to `central`), Philox keyed
+ * by (seed, step).  Replaces utilities/utils.py:60-90 + algorithms/sgd_alg.py:1904-1927 (distributional parity:
+ * the reference's own stream depends on PYTHONHASHSEED). */
+int sbr_sample_modalities(uint8_t* mods, int64_t n_rows, int k, int n_mods, int central, uint64_t seed,
+                          const int64_t* step_dev, void* stream);
+
+/* step counter kept on the DEVICE (so that CUDA-graph replays of a step see a fresh value): *counter += 1 */
+int sbr_tick(int64_t* counter_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ row gather
+ * One descriptor per modality of an entity. */
+typedef struct {
+  int kind;               /* SBR_SRC_*                                                                            */
+  const int32_t* remap;   /* [n_entities] entity index -> feature row (data/Feature.py:146), or NULL = identity  */
+  const float* table;     /* TABLE: [n_rows, C] fp32; CATEGORICAL/TAG: embedding weight [n_cat(+1), C] fp32       */
+  float* grad;            /* same shape as `table`: gradient accumulator (atomicAdd), or NULL in forward          */
+  const int32_t* codes;   /* CATEGORICAL: [n_rows] category id; TAG: [n_rows, max_tags] tag ids (pad = n_tags)    */
+  int32_t max_tags;       /* TAG only                                                                             */
+  int32_t pad_id;         /* TAG only                                                                             */
+} sbr_modality_src_t;
+
+/* X[r, :] = dropout(normalize(src_{mods[r]}(idx[r / k])))  written as bf16 (algorithms/sgd_alg.py:1934-1978,
+ * 1865-1876).  srcs_dev: device array [n_mods].  keep_mask (optional, uint8 [N, C]) overrides the Philox mask. */
+int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
+                       int64_t n_idx, int k, int C, int normalize, float p_drop, uint64_t seed,
+                       const int64_t* step_dev, const uint8_t* keep_mask, void* out_bf16, int64_t ld_out,
+                       int32_t* err_flag, void* stream);
+/* backward of the above: dX (fp32 [N, C], pitch ld_dx) -> atomicAdd into the sources' grad buffers */
+int sbr_row_gather_bwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
+                       int64_t n_idx, int k, int C, int normalize, float p_drop, uint64_t seed,
+                       const int64_t* step_dev, const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
+                       void* stream);
+
+/* table-level backward of the projection output activation: dpre = dT * act'(T) -> bf16 (+ column sums = dbias) */
+int sbr_actgrad_colsum(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y, int act,
+                       int64_t rows, int64_t cols, void* out_bf16, int64_t ld_out, float* out_f32, int64_t ld_out_f32,
+                       float* colsum, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ BatchNorm1d
+ * (torch.nn.BatchNorm1d used at modules/polylinear.py:58-61,68-69 and algorithms/sgd_alg.py:1834-1837)
+ * stats: [2*C] column sum / sum of squares accumulated by the GEMM epilogue.  finalize -> mean_invstd [2*C],
+ * updates running stats (momentum 0.1, unbiased var) and num_batches_tracked. */
+int sbr_bn_finalize(const float* stats, int64_t n_rows, int C, float eps, float momentum, float* mean_invstd,
+                    float* running_mean, float* running_var, int64_t* num_batches_tracked, void* stream);
+/* y = act(gamma * (z - mean) * invstd + beta); z fp32 [rows, C]; writes bf16 and/or fp32.
+ * eval mode: pass running stats through sbr_bn_eval_coeffs first. */
+int sbr_bn_apply(const float* z, int64_t ld_z, const float* mean_invstd, const float* gamma, const float* beta,
+                 int act, int64_t rows, int C, void* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32,
+                 void* stream);
+int sbr_bn_eval_coeffs(const float* running_mean, const float* running_var, int C, float eps, float* mean_invstd,
+                       void* stream);
+/* backward pass 1: dzb = dy * act'(y); sums[0:C] += dzb, sums[C:2C] += dzb * xhat (xhat from z, mean, invstd) */
+int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y, int act,
+                      const float* z, int64_t ld_z, const float* mean_invstd, int64_t rows, int C, float* sums,
+                      void* stream);
+/* backward pass 2: dz = gamma*invstd*(dzb - mean(dzb) - xhat*mean(dzb*xhat)) -> bf16 (+fp32); dgamma, dbeta from sums */
+int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y, int act,
+                     const float* z, int64_t ld_z, const float* mean_invstd, const float* gamma, const float* sums,
+                     int64_t rows, int C, void* dz_bf16, int64_t ld_dz, float* dz_f32, int64_t ld_dz_f32,
+                     float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ losses
+ * Fused modality aggregation (mean | max over k), user-item scoring, rec loss and their gradients
+ * (algorithms/sgd_alg.py:1861,2114 + train/rec_losses.py:40-113).
+ *   eu: fp32 [B, ku, D], ei: fp32 [B, n, ki, D]; logits out [B, n]; loss_acc[0] += rec loss (double);
+ *   deu / dei written (=) with the gradient of the rec loss (NULL = forward only).
+ *   ssm_shift = ln(n_items / n_neg) when the sampler is 'uniform' (rec_losses.py:104-105), else 0. */
+int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n, int ku, int ki, int D, int agg_max_user,
+                   int agg_max_item, int loss_kind, int aggregator_sum, float ssm_shift, float* logits,
+                   double* loss_acc, float* deu, float* dei, float* u_agg, float* i_agg, void* stream);
+/* Symmetric InfoNCE (train/regularization_losses.py:8-43) between slot 0 and slot 1 of e [G, n, 2, D]:
+ * contrast along n inside each of the G groups (item side: G = B, n = 1 + n_neg; user side: G = 1, n = B).
+ * loss_acc[0] += weight * loss; de (+)= weight * dloss/de (accumulate=1 adds to existing gradients). */
+int sbr_infonce(const float* e, int64_t G, int64_t n, int D, float temperature, float weight, double* loss_acc,
+                float* de, int accumulate, float* lse_ws, void* stream);
+
+/* aggregation only (eval path): out[r, :] = mean | max over k of e[r, k, :] */
+int sbr_aggregate(const float* e, int64_t rows, int k, int D, int agg_max, float* out_f32, void* out_bf16,
+                  int64_t ld_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ optimizer
+ * Multi-tensor Adam / AdamW (torch.optim at train/trainer.py:62-68,222-223), one launch for all parameters;
+ * grads are zeroed in the same pass (zero_grad) and an optional bf16 shadow of the weight is refreshed. */
+typedef struct {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* shadow_bf16;   /* optional: bf16 copy with row pitch shadow_ld (rows x cols view of the parameter) */
+  int64_t numel;
+  int64_t cols;        /* innermost extent (for the pitched shadow); numel % cols == 0 */
+  int64_t shadow_ld;
+} sbr_adam_tensor_t;
+int sbr_adam_step(const sbr_adam_tensor_t* tensors_dev, int n_tensors, int64_t total_chunks,
+                  const int32_t* chunk_to_tensor_dev, const int64_t* chunk_offset_dev, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int decoupled, const int64_t* step_dev,
+                  float grad_scale, void* stream); /* *step_dev = 1-based index of the step being applied */
+
+/* ------------------------------------------------------------------------------------------------ evaluation
+ * Fused  scores = U * I^T  (bf16 tcgen05 GEMM, fp32 accumulate)  ->  seen-item mask (-inf)  ->  per-user top-k.
+ * The [U, I] score matrix never reaches HBM.  Replaces eval/eval.py:216-220 + the topk inside rmet.calculate
+ * (eval/eval.py:99-102).  Items are split into `n_splits` contiguous ranges for SM fill; the per-split survivor
+ * lists are merged by sbr_topk_merge.  Ties are broken by the LOWEST item position.  Positions are
+ * indices into items_in_split (+ item_offset for item-sharded multi-GPU evaluation).
+ *   users bf16 [U, ldu], items bf16 [I, ldi]; seen CSR over item positions (sorted per user), may be NULL. */
+int sbr_topk_workspace_bytes(int64_t U, int64_t I, int D, int k, int n_splits, int64_t* bytes_out);
+/* part_keys: uint64 [n_splits, U, k], UNSORTED survivors per split as packed keys
+ * (order-preserving score bits << 32 | (0xFFFFFFFF - position)), 0 = empty slot. */
+int sbr_topk_scores_masked(const void* users, int64_t ldu, const void* items, int64_t ldi, int64_t U, int64_t I, int D,
+                           const int64_t* seen_indptr, const int32_t* seen_indices, int k, int n_splits,
+                           int32_t item_offset, uint64_t* part_keys, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+/* exact top-k of L key lists per user: keys [L, U, k] -> sorted (descending, ties -> lowest position) scores
+ * [U, k], positions [U, k] (-inf / -1 where fewer than k candidates exist) and/or packed keys [U, k].
+ * Also the merge step after the NVLink all-gather of item-sharded evaluation (L = number of ranks). */
+int sbr_topk_merge(const uint64_t* keys, int L, int64_t U, int k, float* out_vals, int32_t* out_idx,
+                   uint64_t* out_keys, void* stream);
+/* per-user metrics from ranked positions and a target CSR (sorted): ndcg, precision, recall, f_score, hitrate for
+ * each k in ks (rmet.calculate at eval/eval.py:99-102; definitions eval/metrics.py:4-105).
+ * out: fp32 [5, n_ks, U] in that metric order; item_hits (optional int32 [n_ks, I]) marks recommended items for
+ * coverage. */
+int sbr_metrics_at_k(const int32_t* topk_idx, int64_t U, int k, const int64_t* tgt_indptr, const int32_t* tgt_indices,
+                     const int32_t* ks_dev, int n_ks, float* out, int32_t* item_hits, int64_t n_items, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ negative sampling
+ * 'uniform_recbole' (data/dataloader.py:154-198): uniform with replacement over items_in_split, re-drawn while the
+ * draw is a train positive of the user (binary search in the sorted train CSR).  Also draws the positives:
+ * a uniformly random train interaction per slot.  out_u [B], out_i [B, 1+n_neg]. */
+int sbr_sample_batch(const int32_t* coo_user, const int32_t* coo_item, int64_t nnz, const int64_t* train_indptr,
+                     const int32_t* train_indices, const int32_t* items_in_split, int64_t n_items_in_split, int64_t B,
+                     int n_neg, uint64_t seed, const int64_t* step_dev, int64_t* out_u, int64_t* out_i, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIBRAR_B200_H */

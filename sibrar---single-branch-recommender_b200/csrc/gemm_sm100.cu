@@ -1,0 +1,345 @@
+// sibrar_b200 -- bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// D[M,N] = alpha * A * B^T, A/B each K-major or MN-major (see include/sibrar_b200.h).  One 128 x BN output tile per
+// CTA, optional split-K over blockIdx.z.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
+// (single elected thread), warps 2..5 = epilogue (TMEM -> registers -> fused bias / BN statistics / activation /
+// activation-gradient / store | transposed atomic accumulate).
+//
+// Replaces nn.Linear forward in the reference's PolyLinear (modules/polylinear.py:50-76) and the dgrad/wgrad
+// GEMMs autograd runs for it (train/trainer.py:221).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle-128B span
+constexpr int A_STAGE_BYTES = BM * 128;  // 16 KiB
+
+struct GemmParams {
+  int64_t M, N, K;
+  int a_mn, b_mn;
+  int kb_per_split, num_kb;
+  sbr_gemm_epilogue_t ep;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;  // + barriers + align slack
+};
+
+// butterfly transpose-reduce: on return lane l holds sum over the warp's 32 lanes of v[l]
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      float send = upper ? v[i] : v[i + n];
+      float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + C::STAGES * C::B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* accum_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
+        uint8_t* a_dst = sA + s * A_STAGE_BYTES;
+        uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
+        if (!p.a_mn) {
+          tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full_bar[s], m0 + j * 64, kb * BK);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+        }
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+        const uint32_t b_addr = smem_u32(sB + s * C::B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: +32 B per 16-element K step inside the 128 B swizzle span; MN-major: +2 K-groups of 1024 B
+          const uint64_t adesc = p.a_mn ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                        : umma_smem_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t bdesc = p.b_mn ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const int64_t row = (int64_t)m0 + row_in_tile;
+    const bool row_ok = row < p.M;
+    const sbr_gemm_epilogue_t& ep = p.ep;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int64_t col0 = (int64_t)n0 + c0;
+      if (col0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]) * ep.alpha;
+        if (ep.bias != nullptr && col0 + j < p.N) x += __ldg(ep.bias + col0 + j);
+        v[j] = x;
+      }
+      if (ep.colstats != nullptr) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = row_ok ? v[j] : 0.f;
+          s1[j] = x;
+          s2[j] = x * x;
+        }
+        float cs = warp_colsum32(s1, lane);
+        float cq = warp_colsum32(s2, lane);
+        if (col0 + lane < p.N) {
+          atomicAdd(ep.colstats + col0 + lane, cs);
+          atomicAdd(ep.colstats + p.N + col0 + lane, cq);
+        }
+      }
+      if (ep.act != SBR_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_fwd(ep.act, v[j]);
+      }
+      const bool full_cols = col0 + 32 <= p.N;
+      if (ep.actgrad_y != nullptr && row_ok) {
+        const bf16* y = reinterpret_cast<const bf16*>(ep.actgrad_y) + row * ep.ld_actgrad + col0;
+        if (full_cols && (ep.ld_actgrad % 8 == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u = __ldg(reinterpret_cast<const uint4*>(y + j));
+            const bf16* yb = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[j + t] *= act_grad_from_out(ep.actgrad_act, __bfloat162float(yb[t]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] *= act_grad_from_out(ep.actgrad_act, __bfloat162float(y[j]));
+        }
+      }
+      if (ep.transpose_out) {
+        // out_f32 is [N, M]: for a fixed column the 32 lanes hit 32 consecutive floats
+        if (ep.out_f32 != nullptr && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.N) {
+              float* dst = ep.out_f32 + (col0 + j) * ep.ld_f32 + row;
+              if (ep.atomic_out) atomicAdd(dst, v[j]);
+              else *dst = v[j];
+            }
+          }
+        }
+        continue;
+      }
+      if (ep.out_f32 != nullptr && row_ok) {
+        float* dst = ep.out_f32 + row * ep.ld_f32 + col0;
+        if (ep.atomic_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+        } else if (full_cols && (ep.ld_f32 % 4 == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) dst[j] = v[j];
+        }
+      }
+      if (ep.out_bf16 != nullptr && row_ok) {
+        bf16* dst = reinterpret_cast<bf16*>(ep.out_bf16) + row * ep.ld_bf16 + col0;
+        if (full_cols && (ep.ld_bf16 % 8 == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+            *reinterpret_cast<uint4*>(dst + j) = u;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    SBR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg<BN>::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN), (unsigned)splits);
+  gemm_bf16_kernel<BN><<<grid, 192, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int sbr_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                          uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  SBR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  SBR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand base must be 16-byte aligned");
+  SBR_REQUIRE((ld_elems * 2) % 16 == 0, "TMA operand row pitch must be a multiple of 8 bf16 elements (got %llu)",
+              (unsigned long long)ld_elems);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SBR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu)",
+              (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems);
+  return SBR_OK;
+}
+
+extern "C" int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                             int64_t M, int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream) {
+  SBR_REQUIRE(A && B && ep, "sbr_gemm_bf16: null operand");
+  SBR_REQUIRE(M > 0 && N > 0 && K > 0, "sbr_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)M,
+              (long long)N, (long long)K);
+  SBR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "sbr_gemm_bf16: dimension too large");
+  SBR_REQUIRE(ep->out_bf16 || ep->out_f32 || ep->colstats, "sbr_gemm_bf16: no output requested");
+  SBR_REQUIRE(!(ep->transpose_out && ep->out_bf16), "sbr_gemm_bf16: transposed output is fp32 only");
+  int splits = ep->split_k < 1 ? 1 : ep->split_k;
+  const int num_kb = (int)((K + BK - 1) / BK);
+  if (splits > num_kb) splits = num_kb;
+  SBR_REQUIRE(splits == 1 || (ep->atomic_out && !ep->out_bf16 && !ep->colstats && !ep->bias &&
+                              ep->act == SBR_ACT_NONE && !ep->actgrad_y),
+              "sbr_gemm_bf16: split_k > 1 needs a pure atomic fp32 epilogue");
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn_major) rc = sbr_make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  else rc = sbr_make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn_major) rc = sbr_make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)BN);
+  else rc = sbr_make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_mn_major ? 1 : 0;
+  p.b_mn = b_mn_major ? 1 : 0;
+  p.num_kb = num_kb;
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  p.ep = *ep;
+  if (p.ep.alpha == 0.f) p.ep.alpha = 1.f;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (BN) {
+    case 64: return launch_gemm<64>(tmA, tmB, p, splits, st);
+    case 128: return launch_gemm<128>(tmA, tmB, p, splits, st);
+    default: return launch_gemm<256>(tmA, tmB, p, splits, st);
+  }
+}

@@ -1,0 +1,205 @@
+// sibrar_b200 -- fused modality aggregation + user-item scoring + rec loss (+ gradients), InfoNCE.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace {
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// one-warp-per-row kernels keep NV values per lane in registers: supported widths D <= 64 / 128 / 512
+#define DISPATCH_NV(n_elems, per, ...)                                   \
+  do {                                                                   \
+    int _nv = (int)(((n_elems) + (per) - 1) / (per));                    \
+    if (_nv <= 2) { constexpr int NVv = 2; __VA_ARGS__; }                \
+    else if (_nv <= 4) { constexpr int NVv = 4; __VA_ARGS__; }           \
+    else { constexpr int NVv = 16; __VA_ARGS__; }                        \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ score + loss
+// one warp per interaction.  lane owns d = lane + 32*i.
+template <int NV>
+__device__ __forceinline__ void aggregate_slots(const float* __restrict__ e, int k, int D, int lane, int agg_max,
+                                                float (&out)[NV], uint32_t (&argmax)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int d = lane + 32 * i;
+    float a = 0.f;
+    uint32_t am = 0;
+    if (d < D) {
+      if (agg_max) {
+        a = e[d];
+        for (int s = 1; s < k; ++s) {
+          float v = e[(int64_t)s * D + d];
+          if (v > a) { a = v; am = s; }
+        }
+      } else {
+        for (int s = 0; s < k; ++s) a += e[(int64_t)s * D + d];
+        a /= (float)k;
+      }
+    }
+    out[i] = a;
+    argmax[i] = am;
+  }
+}
+
+template <int NV>
+__global__ void score_loss_kernel(const float* __restrict__ eu, const float* __restrict__ ei, int64_t B, int n, int ku,
+                                  int ki, int D, int agg_max_user, int agg_max_item, int loss_kind, float inv_cnt,
+                                  float ssm_shift, float* __restrict__ logits, double* __restrict__ loss_acc,
+                                  float* __restrict__ deu, float* __restrict__ dei, float* __restrict__ u_agg_out,
+                                  float* __restrict__ i_agg_out) {
+  extern __shared__ float sh[];  // per warp: n scores + n grads
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t b = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
+  if (b >= B) return;
+  float* sc = sh + (size_t)wib * 2 * n;
+  float* gr = sc + n;
+  float u[NV];
+  uint32_t uam[NV];
+  aggregate_slots<NV>(eu + b * ku * D, ku, D, lane, agg_max_user, u, uam);
+  if (u_agg_out) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < D) u_agg_out[b * D + lane + 32 * i] = u[i];
+  }
+  for (int j = 0; j < n; ++j) {
+    float it[NV];
+    uint32_t iam[NV];
+    aggregate_slots<NV>(ei + ((b * n + j) * ki) * D, ki, D, lane, agg_max_item, it, iam);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dot += u[i] * it[i];
+    dot = warp_sum(dot);
+    if (lane == 0) sc[j] = dot;
+    if (i_agg_out) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (lane + 32 * i < D) i_agg_out[(b * n + j) * D + lane + 32 * i] = it[i];
+    }
+  }
+  __syncwarp();
+  // ---- loss and d loss / d score (lanes stride over j)
+  float lsum = 0.f;
+  if (loss_kind == SBR_LOSS_BPR) {
+    float s0 = sc[0], g0 = 0.f;
+    for (int j = 1 + lane; j < n; j += 32) {
+      float d = s0 - sc[j];
+      lsum += (d > 0.f ? log1pf(__expf(-d)) : -d + log1pf(__expf(d)));
+      float sg = 1.f / (1.f + __expf(d));  // sigmoid(-d)
+      gr[j] = sg * inv_cnt;
+      g0 -= sg * inv_cnt;
+    }
+    g0 = warp_sum(g0);
+    if (lane == 0) gr[0] = g0;
+  } else if (loss_kind == SBR_LOSS_BCE) {
+    for (int j = lane; j < n; j += 32) {
+      float s = sc[j], y = (j == 0) ? 1.f : 0.f;
+      lsum += (s > 0.f ? s + log1pf(__expf(-s)) : log1pf(__expf(s))) - y * s;
+      gr[j] = (1.f / (1.f + __expf(-s)) - y) * inv_cnt;
+    }
+  } else {
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sc[j] + (j > 0 ? ssm_shift : 0.f));
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int j = lane; j < n; j += 32) se += __expf(sc[j] + (j > 0 ? ssm_shift : 0.f) - mx);
+    se = warp_sum(se);
+    float lse = mx + logf(se);
+    for (int j = lane; j < n; j += 32) {
+      float zj = sc[j] + (j > 0 ? ssm_shift : 0.f);
+      gr[j] = (__expf(zj - lse) - (j == 0 ? 1.f : 0.f)) * inv_cnt;
+    }
+    if (lane == 0) lsum = lse - sc[0];
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) {
+    if (loss_acc) atomicAdd(loss_acc, (double)lsum * (double)inv_cnt);
+  }
+  if (logits) {
+    for (int j = lane; j < n; j += 32) logits[b * n + j] = sc[j];
+  }
+  __syncwarp();
+  if (deu == nullptr || dei == nullptr) return;
+  // ---- gradients
+  float du[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) du[i] = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float g = gr[j];
+    float it[NV];
+    uint32_t iam[NV];
+    const float* ej = ei + ((b * n + j) * ki) * D;
+    aggregate_slots<NV>(ej, ki, D, lane, agg_max_item, it, iam);
+    float* dj = dei + ((b * n + j) * ki) * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int d = lane + 32 * i;
+      if (d < D) {
+        du[i] += g * it[i];
+        float gi = g * u[i];
+        for (int s = 0; s < ki; ++s)
+          dj[(int64_t)s * D + d] = agg_max_item ? ((uint32_t)s == iam[i] ? gi : 0.f) : gi / (float)ki;
+      }
+    }
+  }
+  float* dub = deu + b * ku * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int d = lane + 32 * i;
+    if (d < D)
+      for (int s = 0; s < ku; ++s)
+        dub[(int64_t)s * D + d] = agg_max_user ? ((uint32_t)s == uam[i] ? du[i] : 0.f) : du[i] / (float)ku;
+  }
+}
+
+__global__ void aggregate_kernel(const float* __restrict__ e, int64_t rows, int k, int D, int agg_max,
+                                 float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int64_t ld_bf16) {
+  int64_t total = rows * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / D;
+    int d = (int)(i - r * D);
+    const float* p = e + r * k * D + d;
+    float a = p[0];
+    for (int s = 1; s < k; ++s) {
+      float v = p[(int64_t)s * D];
+      a = agg_max ? fmaxf(a, v) : a + v;
+    }
+    if (!agg_max) a /= (float)k;
+    if (out_f32) out_f32[i] = a;
+    if (out_bf16) out_bf16[r * ld_bf16 + d] = __float2bfloat16(a);
+  }
+}
+
+}  // namespace
+
+extern "C" int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n, int ku, int ki, int D,
+                              int agg_max_user, int agg_max_item, int loss_kind, int aggregator_sum, float ssm_shift,
+                              float* logits, double* loss_acc, float* deu, float* dei, float* u_agg, float* i_agg,
+                              void* stream) {
+  SBR_REQUIRE(eu && ei && B > 0 && n >= 1 && ku >= 1 && ki >= 1, "sbr_score_loss: bad arguments");
+  SBR_REQUIRE(D > 0 && D <= 512, "sbr_score_loss: D=%d not in [1, 512]", D);
+  SBR_REQUIRE(n <= 1024, "sbr_score_loss: at most 1024 items per interaction (got %d)", n);
+  SBR_REQUIRE(loss_kind >= 0 && loss_kind <= 2, "sbr_score_loss: unknown loss kind %d", loss_kind);
+  SBR_REQUIRE(!(loss_kind == SBR_LOSS_BPR && n < 2), "sbr_score_loss: BPR needs at least one negative");
+  double cnt = 1.0;
+  if (!aggregator_sum)
+    cnt = loss_kind == SBR_LOSS_BPR ? (double)B * (n - 1) : (loss_kind == SBR_LOSS_BCE ? (double)B * n : (double)B);
+  const int wpb = 4;
+  size_t shmem = (size_t)wpb * 2 * n * sizeof(float);
+  DISPATCH_NV(D, 32, score_loss_kernel<NVv><<<cdiv(B, wpb), wpb * 32, shmem, S(stream)>>>(
+                         eu, ei, B, n, ku, ki, D, agg_max_user, agg_max_item, loss_kind, (float)(1.0 / cnt), ssm_shift,
+                         logits, loss_acc, deu, dei, u_agg, i_agg));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_aggregate(const float* e, int64_t rows, int k, int D, int agg_max, float* out_f32, void* out_bf16,
+                             int64_t ld_bf16, void* stream) {
+  SBR_REQUIRE(e && rows > 0 && k >= 1 && D > 0 && (out_f32 || out_bf16), "sbr_aggregate: bad arguments");
+  unsigned blocks = (unsigned)min((int64_t)sbr_num_sms() * 16, (rows * D + 255) / 256);
+  aggregate_kernel<<<blocks, 256, 0, S(stream)>>>(e, rows, k, D, agg_max, out_f32, reinterpret_cast<bf16*>(out_bf16),
+                                                  ld_bf16);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}

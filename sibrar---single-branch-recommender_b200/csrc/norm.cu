@@ -1,0 +1,219 @@
+// sibrar_b200 -- BatchNorm1d (train statistics finalize / apply / backward) and the table-level activation
+// gradient with column sums.  Thread block = 8 row-lanes x 32 consecutive columns; grid = row blocks x column chunks,
+// so every warp reads 128 contiguous bytes per row and column partial sums stay in one register per thread.
+// Replaces torch.nn.BatchNorm1d as used at modules/polylinear.py:58-61,68-69 and algorithms/sgd_alg.py:1834-1837,
+// and the autograd of the projection's output activation (algorithms/sgd_alg.py:1356).
+#include "common.cuh"
+
+namespace {
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+constexpr int RB = 256;  // rows per block
+
+__device__ __forceinline__ float load_y(const float* y_f32, const bf16* y_bf16, int64_t off) {
+  return y_f32 ? y_f32[off] : __bfloat162float(y_bf16[off]);
+}
+
+// reduce `v` over the 8 row-lanes of the block and atomically add to dst[c]
+__device__ __forceinline__ void block_col_flush(float v, float* dst, int c, int C) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  red[ty][tx] = v;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][tx];
+    atomicAdd(dst + c, t);
+  }
+  __syncthreads();
+}
+
+__global__ void actgrad_colsum_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
+                                      const bf16* __restrict__ y_bf16, int64_t ld_y, int act, int64_t rows, int C,
+                                      bf16* __restrict__ out_bf16, int64_t ld_out, float* __restrict__ out_f32,
+                                      int64_t ld_out_f32, float* __restrict__ colsum) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.x * RB;
+  float part = 0.f;
+  if (c < C) {
+    for (int rr = ty; rr < RB; rr += 8) {
+      int64_t r = r0 + rr;
+      if (r >= rows) break;
+      float v = dy[r * ld_dy + c];
+      if (act != SBR_ACT_NONE) v *= act_grad_from_out(act, load_y(y_f32, y_bf16, r * ld_y + c));
+      part += v;
+      if (out_bf16) out_bf16[r * ld_out + c] = __float2bfloat16(v);
+      if (out_f32) out_f32[r * ld_out_f32 + c] = v;
+    }
+  }
+  if (colsum) block_col_flush(part, colsum, c, C);
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int64_t n_rows, int C, float eps, float momentum,
+                                   float* __restrict__ mean_invstd, float* running_mean, float* running_var,
+                                   int64_t* num_batches_tracked) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (c >= C) return;
+  double n = (double)n_rows;
+  double mean = (double)stats[c] / n;
+  double var = (double)stats[C + c] / n - mean * mean;
+  if (var < 0.) var = 0.;
+  mean_invstd[c] = (float)mean;
+  mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    double unbiased = n > 1. ? var * n / (n - 1.) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
+                                      float* __restrict__ mean_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean_invstd[c] = rm[c];
+  mean_invstd[C + c] = rsqrtf(rv[c] + eps);
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                int64_t rows, int C, bf16* __restrict__ out_bf16, int64_t ld_bf16,
+                                float* __restrict__ out_f32, int64_t ld_f32) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + tx;
+  if (c >= C) return;
+  const int64_t r0 = (int64_t)blockIdx.x * RB;
+  const float mean = mean_invstd[c], sc = mean_invstd[C + c] * gamma[c], sh = beta[c];
+  for (int rr = ty; rr < RB; rr += 8) {
+    int64_t r = r0 + rr;
+    if (r >= rows) break;
+    float v = act_fwd(act, (z[r * ld_z + c] - mean) * sc + sh);
+    if (out_bf16) out_bf16[r * ld_bf16 + c] = __float2bfloat16(v);
+    if (out_f32) out_f32[r * ld_f32 + c] = v;
+  }
+}
+
+// sums[0:C] += dzb, sums[C:2C] += dzb * xhat   with dzb = dy * act'(y)
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
+                                     const bf16* __restrict__ y_bf16, int64_t ld_y, int act,
+                                     const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
+                                     int64_t rows, int C, float* __restrict__ sums) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.x * RB;
+  float p0 = 0.f, p1 = 0.f;
+  if (c < C) {
+    const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
+    for (int rr = ty; rr < RB; rr += 8) {
+      int64_t r = r0 + rr;
+      if (r >= rows) break;
+      float g = dy[r * ld_dy + c];
+      if (act != SBR_ACT_NONE) g *= act_grad_from_out(act, load_y(y_f32, y_bf16, r * ld_y + c));
+      p0 += g;
+      p1 += g * (z[r * ld_z + c] - mean) * invstd;
+    }
+  }
+  block_col_flush(p0, sums, c, C);
+  block_col_flush(p1, sums + C, c, C);
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
+                                    const bf16* __restrict__ y_bf16, int64_t ld_y, int act,
+                                    const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sums, int64_t rows,
+                                    int C, bf16* __restrict__ dz_bf16, int64_t ld_dz, float* __restrict__ dz_f32,
+                                    int64_t ld_dz_f32, float* dgamma, float* dbeta) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + tx;
+  if (c >= C) return;
+  const int64_t r0 = (int64_t)blockIdx.x * RB;
+  const float inv_n = 1.f / (float)rows;
+  const float s0 = sums[c], s1 = sums[C + c];
+  if (blockIdx.x == 0 && ty == 0) {
+    if (dbeta) dbeta[c] += s0;
+    if (dgamma) dgamma[c] += s1;
+  }
+  const float mean = mean_invstd[c], invstd = mean_invstd[C + c], gi = gamma[c] * invstd;
+  for (int rr = ty; rr < RB; rr += 8) {
+    int64_t r = r0 + rr;
+    if (r >= rows) break;
+    float g = dy[r * ld_dy + c];
+    if (act != SBR_ACT_NONE) g *= act_grad_from_out(act, load_y(y_f32, y_bf16, r * ld_y + c));
+    float xh = (z[r * ld_z + c] - mean) * invstd;
+    float v = gi * (g - s0 * inv_n - xh * s1 * inv_n);
+    if (dz_bf16) dz_bf16[r * ld_dz + c] = __float2bfloat16(v);
+    if (dz_f32) dz_f32[r * ld_dz_f32 + c] = v;
+  }
+}
+
+inline dim3 tile_grid(int64_t rows, int64_t cols) { return dim3(cdiv(rows, RB), cdiv(cols, 32)); }
+}  // namespace
+
+extern "C" int sbr_actgrad_colsum(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
+                                  int act, int64_t rows, int64_t cols, void* out_bf16, int64_t ld_out, float* out_f32,
+                                  int64_t ld_out_f32, float* colsum, void* stream) {
+  SBR_REQUIRE(dy && rows > 0 && cols > 0, "sbr_actgrad_colsum: bad arguments");
+  SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_actgrad_colsum: activation gradient needs the output y");
+  actgrad_colsum_kernel<<<tile_grid(rows, cols), 256, 0, S(stream)>>>(
+      dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, rows, (int)cols,
+      reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_bn_finalize(const float* stats, int64_t n_rows, int C, float eps, float momentum,
+                               float* mean_invstd, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, void* stream) {
+  SBR_REQUIRE(stats && mean_invstd && n_rows > 0 && C > 0, "sbr_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, S(stream)>>>(stats, n_rows, C, eps, momentum, mean_invstd, running_mean,
+                                                          running_var, num_batches_tracked);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_bn_eval_coeffs(const float* running_mean, const float* running_var, int C, float eps,
+                                  float* mean_invstd, void* stream) {
+  SBR_REQUIRE(running_mean && running_var && mean_invstd && C > 0, "sbr_bn_eval_coeffs: bad arguments");
+  bn_eval_coeffs_kernel<<<cdiv(C, 128), 128, 0, S(stream)>>>(running_mean, running_var, C, eps, mean_invstd);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_bn_apply(const float* z, int64_t ld_z, const float* mean_invstd, const float* gamma,
+                            const float* beta, int act, int64_t rows, int C, void* out_bf16, int64_t ld_bf16,
+                            float* out_f32, int64_t ld_f32, void* stream) {
+  SBR_REQUIRE(z && mean_invstd && gamma && beta && rows > 0 && C > 0, "sbr_bn_apply: bad arguments");
+  bn_apply_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(z, ld_z, mean_invstd, gamma, beta, act, rows, C,
+                                                             reinterpret_cast<bf16*>(out_bf16), ld_bf16, out_f32,
+                                                             ld_f32);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
+                                 int act, const float* z, int64_t ld_z, const float* mean_invstd, int64_t rows, int C,
+                                 float* sums, void* stream) {
+  SBR_REQUIRE(dy && z && mean_invstd && sums && rows > 0 && C > 0, "sbr_bn_bwd_reduce: bad arguments");
+  SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_reduce: activation gradient needs the output y");
+  bn_bwd_reduce_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(
+      dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, rows, C, sums);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
+                                int act, const float* z, int64_t ld_z, const float* mean_invstd, const float* gamma,
+                                const float* sums, int64_t rows, int C, void* dz_bf16, int64_t ld_dz, float* dz_f32,
+                                int64_t ld_dz_f32, float* dgamma, float* dbeta, void* stream) {
+  SBR_REQUIRE(dy && z && mean_invstd && gamma && sums && rows > 0 && C > 0, "sbr_bn_bwd_apply: bad arguments");
+  SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_apply: activation gradient needs the output y");
+  bn_bwd_apply_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(
+      dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, gamma, sums, rows, C,
+      reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}

@@ -1,0 +1,234 @@
+// sibrar_b200 -- casts, CSR densify, modality sampling, step counter, multi-tensor Adam(W), negative sampling.
+// Reference code replaced by each kernel is named in include/sibrar_b200.h.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ error plumbing
+static thread_local char g_err[1024] = "";
+void sbr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* sbr_last_error(void) { return g_err; }
+extern "C" int sbr_version(void) { return 100; }
+
+
+namespace {
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------ casts
+__global__ void cast_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst, int64_t ld_dst,
+                            int64_t rows, int64_t cols) {
+  int64_t total = rows * ld_dst;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / ld_dst, c = i - r * ld_dst;
+    dst[i] = __float2bfloat16(c < cols ? src[r * ld_src + c] : 0.f);
+  }
+}
+
+__global__ void transpose_cast_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst,
+                                      int64_t ld_dst, int64_t rows, int64_t cols) {
+  __shared__ float tile[32][33];
+  int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[c * ld_dst + r] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+
+__global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                    int64_t rows, int64_t cols, bf16* __restrict__ dst, int64_t ld_dst) {
+  int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int lane = threadIdx.x & 31;
+  bf16* d = dst + row * ld_dst;
+  const bf16 zero = __float2bfloat16(0.f), one = __float2bfloat16(1.f);
+  for (int64_t c = lane; c < ld_dst; c += 32) d[c] = zero;
+  __syncwarp();
+  for (int64_t p = indptr[row] + lane; p < indptr[row + 1]; p += 32) {
+    int32_t c = indices[p];
+    if (c >= 0 && c < cols) d[c] = one;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ modality sampling
+__global__ void sample_modalities_kernel(uint8_t* __restrict__ mods, int64_t n_rows, int k, int n_mods, int central,
+                                         uint64_t seed, const int64_t* __restrict__ step_dev) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  uint64_t step = (uint64_t)*step_dev;
+  uint4 rnd = philox4x32(make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)step, 0x6d6f6473u),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
+  if (k == 1) {
+    mods[r] = (uint8_t)min(n_mods - 1, (int)(u32_to_unit(rnd.x) * n_mods));
+  } else if (central >= 0) {
+    int o = min(n_mods - 2, (int)(u32_to_unit(rnd.x) * (n_mods - 1)));
+    if (o >= central) ++o;
+    mods[r * 2] = (uint8_t)central;
+    mods[r * 2 + 1] = (uint8_t)o;
+  } else {
+    int a = min(n_mods - 1, (int)(u32_to_unit(rnd.x) * n_mods));
+    int b = min(n_mods - 2, (int)(u32_to_unit(rnd.y) * (n_mods - 1)));
+    if (b >= a) ++b;
+    mods[r * 2] = (uint8_t)a;
+    mods[r * 2 + 1] = (uint8_t)b;
+  }
+}
+
+__global__ void tick_kernel(int64_t* c) { *c += 1; }
+
+// ------------------------------------------------------------------------------------------------ Adam / AdamW
+constexpr int ADAM_CHUNK = 4096;
+__global__ void adam_kernel(const sbr_adam_tensor_t* __restrict__ tensors, const int32_t* __restrict__ chunk_to_tensor,
+                            const int64_t* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps,
+                            float wd, int decoupled, const int64_t* __restrict__ step_dev, float grad_scale) {
+  const sbr_adam_tensor_t t = tensors[chunk_to_tensor[blockIdx.x]];
+  const int64_t off = chunk_offset[blockIdx.x];
+  const double step = (double)*step_dev;
+  const float bc1 = (float)(1.0 - pow((double)beta1, step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+  const float step_size = lr / bc1;
+  for (int64_t i = off + threadIdx.x; i < min(off + (int64_t)ADAM_CHUNK, t.numel); i += blockDim.x) {
+    float p = t.param[i], g = t.grad[i] * grad_scale, m = t.exp_avg[i], v = t.exp_avg_sq[i];
+    if (decoupled) p *= (1.f - lr * wd);
+    else g += wd * p;
+    m = beta1 * m + (1.f - beta1) * g;
+    v = beta2 * v + (1.f - beta2) * g * g;
+    p -= step_size * m / (sqrtf(v) / bc2_sqrt + eps);
+    t.param[i] = p;
+    t.exp_avg[i] = m;
+    t.exp_avg_sq[i] = v;
+    t.grad[i] = 0.f;
+    if (t.shadow_bf16) {
+      int64_t r = i / t.cols, c = i - r * t.cols;
+      reinterpret_cast<bf16*>(t.shadow_bf16)[r * t.shadow_ld + c] = __float2bfloat16(p);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ negative sampling
+__global__ void sample_batch_kernel(const int32_t* __restrict__ coo_user, const int32_t* __restrict__ coo_item,
+                                    int64_t nnz, const int64_t* __restrict__ indptr,
+                                    const int32_t* __restrict__ indices, const int32_t* __restrict__ items_in_split,
+                                    int64_t n_items_in_split, int64_t B, int n_neg, uint64_t seed,
+                                    const int64_t* __restrict__ step_dev, int64_t* __restrict__ out_u,
+                                    int64_t* __restrict__ out_i) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= B * (n_neg + 1)) return;
+  const int64_t b = t / (n_neg + 1);
+  const int j = (int)(t - b * (n_neg + 1));
+  const uint64_t step = (uint64_t)*step_dev;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x6e656773u);
+  // the positive (and thereby the user) of slot b: same draw for every j of the slot
+  uint4 r0 = philox4x32(make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+  uint64_t r64 = ((uint64_t)r0.x << 32) | r0.y;
+  int64_t e = (int64_t)__umul64hi(r64, (uint64_t)nnz);
+  const int32_t u = coo_user[e];
+  if (j == 0) {
+    out_u[b] = u;
+    out_i[b * (n_neg + 1)] = coo_item[e];
+    return;
+  }
+  const int64_t beg = indptr[u], end = indptr[u + 1];
+  int32_t cand = 0;
+  for (int attempt = 0; attempt < 64; ++attempt) {
+    uint4 r = philox4x32(make_uint4((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)step, 0x80000000u + attempt), key);
+    uint64_t q = ((uint64_t)r.x << 32) | r.y;
+    cand = items_in_split[(int64_t)__umul64hi(q, (uint64_t)n_items_in_split)];
+    int64_t lo = beg, hi = end;  // binary search in the sorted positives of u
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (indices[mid] < cand) lo = mid + 1;
+      else hi = mid;
+    }
+    if (!(lo < end && indices[lo] == cand)) break;
+  }
+  out_i[t] = cand;
+}
+
+}  // namespace
+
+extern "C" int sbr_cast_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
+                                    int64_t cols, void* stream) {
+  SBR_REQUIRE(src && dst && rows >= 0 && cols >= 0 && ld_dst >= cols, "sbr_cast_f32_to_bf16: bad arguments");
+  if (rows * ld_dst == 0) return SBR_OK;
+  unsigned blocks = (unsigned)min((int64_t)sbr_num_sms() * 16, (rows * ld_dst + 255) / 256);
+  cast_kernel<<<blocks, 256, 0, S(stream)>>>(src, ld_src, reinterpret_cast<bf16*>(dst), ld_dst, rows, cols);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_transpose_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
+                                         int64_t cols, void* stream) {
+  SBR_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_dst >= rows, "sbr_transpose_f32_to_bf16: bad arguments");
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+  transpose_cast_kernel<<<grid, dim3(32, 8), 0, S(stream)>>>(src, ld_src, reinterpret_cast<bf16*>(dst), ld_dst, rows,
+                                                             cols);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_csr_to_dense_bf16(const int64_t* indptr, const int32_t* indices, int64_t rows, int64_t cols,
+                                     void* dst, int64_t ld_dst, void* stream) {
+  SBR_REQUIRE(indptr && dst && rows > 0 && ld_dst >= cols, "sbr_csr_to_dense_bf16: bad arguments");
+  csr_to_dense_kernel<<<cdiv(rows, 8), 256, 0, S(stream)>>>(indptr, indices, rows, cols, reinterpret_cast<bf16*>(dst),
+                                                            ld_dst);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_sample_modalities(uint8_t* mods, int64_t n_rows, int k, int n_mods, int central, uint64_t seed,
+                                     const int64_t* step_dev, void* stream) {
+  SBR_REQUIRE(mods && step_dev && n_rows > 0, "sbr_sample_modalities: bad arguments");
+  SBR_REQUIRE(k == 1 || k == 2, "sbr_sample_modalities: k must be 1 or 2 (got %d)", k);
+  SBR_REQUIRE(n_mods >= k && n_mods <= 255, "sbr_sample_modalities: need k <= n_mods <= 255 (k=%d n_mods=%d)", k,
+              n_mods);
+  SBR_REQUIRE(central < n_mods, "sbr_sample_modalities: central modality out of range");
+  sample_modalities_kernel<<<cdiv(n_rows, 256), 256, 0, S(stream)>>>(mods, n_rows, k, n_mods, central, seed, step_dev);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_tick(int64_t* counter_dev, void* stream) {
+  SBR_REQUIRE(counter_dev, "sbr_tick: null counter");
+  tick_kernel<<<1, 1, 0, S(stream)>>>(counter_dev);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_adam_step(const sbr_adam_tensor_t* tensors_dev, int n_tensors, int64_t total_chunks,
+                             const int32_t* chunk_to_tensor_dev, const int64_t* chunk_offset_dev, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int decoupled, const int64_t* step_dev,
+                             float grad_scale, void* stream) {
+  SBR_REQUIRE(tensors_dev && chunk_to_tensor_dev && chunk_offset_dev && step_dev && n_tensors > 0 && total_chunks > 0,
+              "sbr_adam_step: bad arguments");
+  adam_kernel<<<(unsigned)total_chunks, 256, 0, S(stream)>>>(tensors_dev, chunk_to_tensor_dev, chunk_offset_dev, lr,
+                                                             beta1, beta2, eps, weight_decay, decoupled, step_dev,
+                                                             grad_scale);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_sample_batch(const int32_t* coo_user, const int32_t* coo_item, int64_t nnz,
+                                const int64_t* train_indptr, const int32_t* train_indices,
+                                const int32_t* items_in_split, int64_t n_items_in_split, int64_t B, int n_neg,
+                                uint64_t seed, const int64_t* step_dev, int64_t* out_u, int64_t* out_i, void* stream) {
+  SBR_REQUIRE(coo_user && coo_item && train_indptr && train_indices && items_in_split && out_u && out_i && step_dev,
+              "sbr_sample_batch: null argument");
+  SBR_REQUIRE(nnz > 0 && n_items_in_split > 0 && B > 0 && n_neg >= 0, "sbr_sample_batch: bad sizes");
+  sample_batch_kernel<<<cdiv(B * (n_neg + 1), 256), 256, 0, S(stream)>>>(coo_user, coo_item, nnz, train_indptr,
+                                                                        train_indices, items_in_split, n_items_in_split,
+                                                                        B, n_neg, seed, step_dev, out_u, out_i);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
