@@ -56,7 +56,7 @@ typedef struct {
   int64_t ld_bf16;
   float* out_f32;         /* optional fp32 output [M, N] ([N, M] if transpose_out)                                */
   int64_t ld_f32;
-  float* colstats;        /* optional [2*N]: += column sum and sum of squares of (alpha*acc + bias), valid rows   */
+  float* colstats;        /* optional [2*N]: += column sum / sum of squares of the FINAL epilogue value, valid rows */
   const void* actgrad_y;  /* optional bf16 [M, N]: result *= act'(y) expressed through the saved output y         */
   int64_t ld_actgrad;
   int actgrad_act;
@@ -74,6 +74,8 @@ int sbr_cast_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld
                          void* stream); /* dst columns [cols, ld_dst) are zero-filled */
 int sbr_transpose_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols,
                               void* stream); /* dst[c, r] = src[r, c] */
+int sbr_transpose_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                      void* stream);
 int sbr_csr_to_dense_bf16(const int64_t* indptr, const int32_t* indices, int64_t rows, int64_t cols, void* dst,
                           int64_t ld_dst, void* stream); /* multi-hot rows (data/Feature.py:147-150) */
 
@@ -108,11 +110,12 @@ typedef struct {
 } sbr_modality_src_t;
 
 /* X[r, :] = dropout(normalize(src_{mods[r]}(idx[r / k])))  written as bf16 (algorithms/sgd_alg.py:1934-1978,
- * 1865-1876).  srcs_dev: device array [n_mods].  keep_mask (optional, uint8 [N, C]) overrides the Philox mask. */
+ * 1865-1876) and/or fp32.  srcs_dev: device array [n_mods].  keep_mask (optional, uint8 [N, C]) overrides the
+ * Philox mask.  err_flag is set to 1 when an entity index has no feature row (KeyError at data/Feature.py:146). */
 int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
                        int64_t n_idx, int k, int C, int normalize, float p_drop, uint64_t seed,
                        const int64_t* step_dev, const uint8_t* keep_mask, void* out_bf16, int64_t ld_out,
-                       int32_t* err_flag, void* stream);
+                       float* out_f32, int64_t ld_f32, int32_t* err_flag, void* stream);
 /* backward of the above: dX (fp32 [N, C], pitch ld_dx) -> atomicAdd into the sources' grad buffers */
 int sbr_row_gather_bwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
                        int64_t n_idx, int k, int C, int normalize, float p_drop, uint64_t seed,

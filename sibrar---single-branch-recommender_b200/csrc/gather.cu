@@ -82,7 +82,8 @@ __global__ void row_gather_fwd_kernel(const sbr_modality_src_t* __restrict__ src
                                       const int64_t* __restrict__ idx, const uint8_t* __restrict__ mods, int64_t N,
                                       int k, int C, int normalize, float p_drop, uint64_t seed,
                                       const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
-                                      bf16* __restrict__ out, int64_t ld_out, int32_t* err_flag) {
+                                      bf16* __restrict__ out, int64_t ld_out, float* __restrict__ out_f32,
+                                      int64_t ld_f32, int32_t* err_flag) {
   int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= N) return;
   const int lane = threadIdx.x & 31;
@@ -112,7 +113,8 @@ __global__ void row_gather_fwd_kernel(const sbr_modality_src_t* __restrict__ src
       int c = 4 * lane + j + 128 * i;
       if (c < C) {
         float v = x[i * 4 + j] * keep_scale(keep_mask, r, C, c, p_drop, seed, step, cache, cache_c4);
-        out[r * ld_out + c] = __float2bfloat16(v);
+        if (out) out[r * ld_out + c] = __float2bfloat16(v);
+        if (out_f32) out_f32[r * ld_f32 + c] = v;
       }
     }
 }
@@ -195,16 +197,18 @@ __global__ void row_gather_bwd_kernel(const sbr_modality_src_t* __restrict__ src
 extern "C" int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx,
                                   const uint8_t* mods, int64_t n_idx, int k, int C, int normalize, float p_drop,
                                   uint64_t seed, const int64_t* step_dev, const uint8_t* keep_mask, void* out_bf16,
-                                  int64_t ld_out, int32_t* err_flag, void* stream) {
-  SBR_REQUIRE(srcs_dev && idx && out_bf16 && n_idx > 0 && k >= 1, "sbr_row_gather_fwd: bad arguments");
-  SBR_REQUIRE(C > 0 && C <= 1024 && ld_out >= C, "sbr_row_gather_fwd: C=%d not in [1, 1024] or ld_out < C", C);
+                                  int64_t ld_out, float* out_f32, int64_t ld_f32, int32_t* err_flag, void* stream) {
+  SBR_REQUIRE(srcs_dev && idx && (out_bf16 || out_f32) && n_idx > 0 && k >= 1, "sbr_row_gather_fwd: bad arguments");
+  SBR_REQUIRE(C > 0 && C <= 1024, "sbr_row_gather_fwd: C=%d not in [1, 1024]", C);
+  SBR_REQUIRE((!out_bf16 || ld_out >= C) && (!out_f32 || ld_f32 >= C), "sbr_row_gather_fwd: output pitch < C");
   SBR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "sbr_row_gather_fwd: dropout p must be in [0, 1)");
   const int64_t N = n_idx * k;
   DISPATCH_NV(C, 128, {
     constexpr int NV4 = NVv > 8 ? 8 : NVv;
     row_gather_fwd_kernel<NV4><<<cdiv(N, 8), 256, 0, S(stream)>>>(srcs_dev, n_mods, idx, mods, N, k, C, normalize,
                                                                   p_drop, seed, step_dev, keep_mask,
-                                                                  reinterpret_cast<bf16*>(out_bf16), ld_out, err_flag);
+                                                                  reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32,
+                                                                  ld_f32, err_flag);
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;

@@ -156,21 +156,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (ep.bias != nullptr && col0 + j < p.N) x += __ldg(ep.bias + col0 + j);
         v[j] = x;
       }
-      if (ep.colstats != nullptr) {
-        float s1[32], s2[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = row_ok ? v[j] : 0.f;
-          s1[j] = x;
-          s2[j] = x * x;
-        }
-        float cs = warp_colsum32(s1, lane);
-        float cq = warp_colsum32(s2, lane);
-        if (col0 + lane < p.N) {
-          atomicAdd(ep.colstats + col0 + lane, cs);
-          atomicAdd(ep.colstats + p.N + col0 + lane, cq);
-        }
-      }
       if (ep.act != SBR_ACT_NONE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = act_fwd(ep.act, v[j]);
@@ -190,6 +175,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < p.N) v[j] *= act_grad_from_out(ep.actgrad_act, __bfloat162float(y[j]));
+        }
+      }
+      if (ep.colstats != nullptr) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = row_ok ? v[j] : 0.f;
+          s1[j] = x;
+          s2[j] = x * x;
+        }
+        float cs = warp_colsum32(s1, lane);
+        float cq = warp_colsum32(s2, lane);
+        if (col0 + lane < p.N) {
+          atomicAdd(ep.colstats + col0 + lane, cs);
+          atomicAdd(ep.colstats + p.N + col0 + lane, cq);
         }
       }
       if (ep.transpose_out) {

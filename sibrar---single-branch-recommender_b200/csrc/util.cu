@@ -30,7 +30,11 @@ __global__ void cast_kernel(const float* __restrict__ src, int64_t ld_src, bf16*
   }
 }
 
-__global__ void transpose_cast_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst,
+__device__ __forceinline__ void store_as(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_as(bf16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename OutT>
+__global__ void transpose_cast_kernel(const float* __restrict__ src, int64_t ld_src, OutT* __restrict__ dst,
                                       int64_t ld_dst, int64_t rows, int64_t cols) {
   __shared__ float tile[32][33];
   int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
@@ -41,7 +45,7 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, int64_t ld_
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     int64_t c = c0 + j, r = r0 + threadIdx.x;
-    if (c < cols && r < rows) dst[c * ld_dst + r] = __float2bfloat16(tile[threadIdx.x][j]);
+    if (c < cols && r < rows) store_as(dst + c * ld_dst + r, tile[threadIdx.x][j]);
   }
 }
 
@@ -171,8 +175,17 @@ extern "C" int sbr_transpose_f32_to_bf16(const float* src, int64_t ld_src, void*
                                          int64_t cols, void* stream) {
   SBR_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_dst >= rows, "sbr_transpose_f32_to_bf16: bad arguments");
   dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
-  transpose_cast_kernel<<<grid, dim3(32, 8), 0, S(stream)>>>(src, ld_src, reinterpret_cast<bf16*>(dst), ld_dst, rows,
-                                                             cols);
+  transpose_cast_kernel<bf16><<<grid, dim3(32, 8), 0, S(stream)>>>(src, ld_src, reinterpret_cast<bf16*>(dst), ld_dst,
+                                                                   rows, cols);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_transpose_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows,
+                                 int64_t cols, void* stream) {
+  SBR_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_dst >= rows, "sbr_transpose_f32: bad arguments");
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+  transpose_cast_kernel<float><<<grid, dim3(32, 8), 0, S(stream)>>>(src, ld_src, dst, ld_dst, rows, cols);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

@@ -1,0 +1,264 @@
+"""Thin tensor-level wrappers over the C ABI (``include/sibrar_b200.h``).  torch is used for device memory and the
+current stream only; every function enqueues hand-written sm_100a kernels and returns immediately."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import ACT, LOSS, AdamTensor, GemmEpilogue, ModalitySrc, call, ptr, stream_ptr
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def pad8(n: int) -> int:
+    return (int(n) + 7) // 8 * 8
+
+
+def _act(a):
+    return a if isinstance(a, int) else ACT[a]
+
+
+def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, act=None, out_bf16=None,
+         out_f32=None, colstats=None, actgrad_y=None, actgrad_act=None, transpose_out=False, atomic_out=False,
+         split_k=1, alpha=1.0):
+    """D[M,N] = alpha * A @ B^T (bf16 in, fp32 accumulate) + fused epilogue.  A/B: 2-D bf16 tensors whose last
+    dimension is contiguous; K-major means [rows, K], MN-major means [K, rows]."""
+    assert A.dtype == BF16 and B.dtype == BF16 and A.stride(-1) == 1 and B.stride(-1) == 1
+    ep = GemmEpilogue()
+    ep.bias = ptr(bias)
+    ep.act = _act(act)
+    ep.out_bf16 = ptr(out_bf16)
+    ep.ld_bf16 = out_bf16.stride(0) if out_bf16 is not None else 0
+    ep.out_f32 = ptr(out_f32)
+    ep.ld_f32 = out_f32.stride(0) if out_f32 is not None else 0
+    ep.colstats = ptr(colstats)
+    ep.actgrad_y = ptr(actgrad_y)
+    ep.ld_actgrad = actgrad_y.stride(0) if actgrad_y is not None else 0
+    ep.actgrad_act = _act(actgrad_act)
+    ep.transpose_out = int(transpose_out)
+    ep.atomic_out = int(atomic_out)
+    ep.split_k = int(split_k)
+    ep.alpha = float(alpha)
+    call("sbr_gemm_bf16", ptr(A), lda if lda is not None else A.stride(0), int(a_mn), ptr(B),
+         ldb if ldb is not None else B.stride(0), int(b_mn), int(M), int(N), int(K), C.byref(ep), stream_ptr())
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, pad8(cols)] (pad columns zeroed)"""
+    rows, cols = src.shape
+    if dst is None:
+        dst = torch.empty((rows, pad8(cols)), dtype=BF16, device=src.device)
+    call("sbr_cast_f32_to_bf16", ptr(src), src.stride(0), ptr(dst), dst.stride(0), rows, cols, stream_ptr())
+    return dst
+
+
+def transpose_f32(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:
+    rows, cols = src.shape
+    if dst is None:
+        dst = torch.empty((cols, rows), dtype=F32, device=src.device)
+    call("sbr_transpose_f32", ptr(src), src.stride(0), ptr(dst), dst.stride(0), rows, cols, stream_ptr())
+    return dst
+
+
+def csr_to_dense_bf16(indptr, indices, rows, cols) -> torch.Tensor:
+    dst = torch.empty((rows, pad8(cols)), dtype=BF16, device=indptr.device)
+    call("sbr_csr_to_dense_bf16", ptr(indptr), ptr(indices), rows, cols, ptr(dst), dst.stride(0), stream_ptr())
+    return dst
+
+
+def spmm_csr(indptr, indices, rows, dense, C_, bias, act, out, transpose_out=False):
+    call("sbr_spmm_csr", ptr(indptr), ptr(indices), int(rows), ptr(dense), dense.stride(0), int(C_), ptr(bias),
+         _act(act), ptr(out), out.stride(0), int(transpose_out), stream_ptr())
+
+
+def sample_modalities(mods, n_rows, k, n_mods, central, seed, step_dev):
+    call("sbr_sample_modalities", ptr(mods), int(n_rows), int(k), int(n_mods), int(central), int(seed),
+         ptr(step_dev), stream_ptr())
+
+
+def tick(counter):
+    call("sbr_tick", ptr(counter), stream_ptr())
+
+
+def make_modality_srcs(entries, device) -> torch.Tensor:
+    """entries: list of dict(kind, remap, table, grad, codes, max_tags, pad_id) -> uint8 device blob of
+    ``sbr_modality_src_t[n]``"""
+    arr = (ModalitySrc * len(entries))()
+    for i, e in enumerate(entries):
+        arr[i].kind = e["kind"]
+        arr[i].remap = ptr(e.get("remap"))
+        arr[i].table = ptr(e.get("table"))
+        arr[i].grad = ptr(e.get("grad"))
+        arr[i].codes = ptr(e.get("codes"))
+        arr[i].max_tags = int(e.get("max_tags", 0))
+        arr[i].pad_id = int(e.get("pad_id", -1))
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device)
+
+
+def row_gather_fwd(srcs, n_mods, idx, mods, k, C_, normalize, p_drop, seed, step_dev, keep_mask, out_bf16=None,
+                   out_f32=None, err_flag=None):
+    call("sbr_row_gather_fwd", ptr(srcs), int(n_mods), ptr(idx), ptr(mods), idx.numel(), int(k), int(C_),
+         int(bool(normalize)), float(p_drop or 0.0), int(seed), ptr(step_dev), ptr(keep_mask), ptr(out_bf16),
+         out_bf16.stride(0) if out_bf16 is not None else 0, ptr(out_f32),
+         out_f32.stride(0) if out_f32 is not None else 0, ptr(err_flag), stream_ptr())
+
+
+def row_gather_bwd(srcs, n_mods, idx, mods, k, C_, normalize, p_drop, seed, step_dev, keep_mask, dx):
+    call("sbr_row_gather_bwd", ptr(srcs), int(n_mods), ptr(idx), ptr(mods), idx.numel(), int(k), int(C_),
+         int(bool(normalize)), float(p_drop or 0.0), int(seed), ptr(step_dev), ptr(keep_mask), ptr(dx), dx.stride(0),
+         stream_ptr())
+
+
+def _y_args(y):
+    if y is None:
+        return None, None, 0
+    return (ptr(y), None, y.stride(0)) if y.dtype == F32 else (None, ptr(y), y.stride(0))
+
+
+def actgrad_colsum(dy, y, act, rows, cols, out_bf16=None, out_f32=None, colsum=None):
+    yf, yb, ldy = _y_args(y)
+    call("sbr_actgrad_colsum", ptr(dy), dy.stride(0), yf, yb, ldy, _act(act), int(rows), int(cols), ptr(out_bf16),
+         out_bf16.stride(0) if out_bf16 is not None else 0, ptr(out_f32),
+         out_f32.stride(0) if out_f32 is not None else 0, ptr(colsum), stream_ptr())
+
+
+def bn_finalize(stats, n_rows, C_, mean_invstd, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):
+    call("sbr_bn_finalize", ptr(stats), int(n_rows), int(C_), float(eps), float(momentum), ptr(mean_invstd),
+         ptr(running_mean), ptr(running_var), ptr(nbt), stream_ptr())
+
+
+def bn_eval_coeffs(running_mean, running_var, C_, mean_invstd, eps=1e-5):
+    call("sbr_bn_eval_coeffs", ptr(running_mean), ptr(running_var), int(C_), float(eps), ptr(mean_invstd),
+         stream_ptr())
+
+
+def bn_apply(z, mean_invstd, gamma, beta, act, rows, C_, out_bf16=None, out_f32=None):
+    call("sbr_bn_apply", ptr(z), z.stride(0), ptr(mean_invstd), ptr(gamma), ptr(beta), _act(act), int(rows), int(C_),
+         ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(out_f32),
+         out_f32.stride(0) if out_f32 is not None else 0, stream_ptr())
+
+
+def bn_bwd_reduce(dy, y, act, z, mean_invstd, rows, C_, sums):
+    yf, yb, ldy = _y_args(y)
+    call("sbr_bn_bwd_reduce", ptr(dy), dy.stride(0), yf, yb, ldy, _act(act), ptr(z), z.stride(0), ptr(mean_invstd),
+         int(rows), int(C_), ptr(sums), stream_ptr())
+
+
+def bn_bwd_apply(dy, y, act, z, mean_invstd, gamma, sums, rows, C_, dz_bf16=None, dz_f32=None, dgamma=None,
+                 dbeta=None):
+    yf, yb, ldy = _y_args(y)
+    call("sbr_bn_bwd_apply", ptr(dy), dy.stride(0), yf, yb, ldy, _act(act), ptr(z), z.stride(0), ptr(mean_invstd),
+         ptr(gamma), ptr(sums), int(rows), int(C_), ptr(dz_bf16), dz_bf16.stride(0) if dz_bf16 is not None else 0,
+         ptr(dz_f32), dz_f32.stride(0) if dz_f32 is not None else 0, ptr(dgamma), ptr(dbeta), stream_ptr())
+
+
+def score_loss(eu, ei, B, n, ku, ki, D, agg_max_user, agg_max_item, loss_kind, aggregator_sum, ssm_shift, logits,
+               loss_acc, deu=None, dei=None, u_agg=None, i_agg=None):
+    lk = loss_kind if isinstance(loss_kind, int) else LOSS[loss_kind]
+    call("sbr_score_loss", ptr(eu), ptr(ei), int(B), int(n), int(ku), int(ki), int(D), int(agg_max_user),
+         int(agg_max_item), lk, int(aggregator_sum), float(ssm_shift), ptr(logits), ptr(loss_acc), ptr(deu), ptr(dei),
+         ptr(u_agg), ptr(i_agg), stream_ptr())
+
+
+def infonce(e, G, n, D, temperature, weight, loss_acc, de, accumulate, lse_ws=None):
+    if lse_ws is None:
+        lse_ws = torch.empty(2 * G * n, dtype=F32, device=e.device)
+    call("sbr_infonce", ptr(e), int(G), int(n), int(D), float(temperature), float(weight), ptr(loss_acc), ptr(de),
+         int(accumulate), ptr(lse_ws), stream_ptr())
+
+
+def aggregate(e, rows, k, D, agg_max, out_f32=None, out_bf16=None):
+    call("sbr_aggregate", ptr(e), int(rows), int(k), int(D), int(agg_max), ptr(out_f32), ptr(out_bf16),
+         out_bf16.stride(0) if out_bf16 is not None else 0, stream_ptr())
+
+
+ADAM_CHUNK = 4096
+
+
+class AdamPlan:
+    """device-side tables for the one-launch multi-tensor Adam(W)"""
+
+    def __init__(self, entries, device):
+        """entries: list of dict(param, grad, exp_avg, exp_avg_sq, shadow(optional bf16 [rows, ld]))"""
+        arr = (AdamTensor * len(entries))()
+        c2t, coff = [], []
+        for i, e in enumerate(entries):
+            p = e["param"]
+            arr[i].param, arr[i].grad = ptr(p), ptr(e["grad"])
+            arr[i].exp_avg, arr[i].exp_avg_sq = ptr(e["exp_avg"]), ptr(e["exp_avg_sq"])
+            sh = e.get("shadow")
+            arr[i].shadow_bf16 = ptr(sh)
+            arr[i].numel = p.numel()
+            arr[i].cols = p.shape[-1] if (sh is not None and p.dim() >= 1) else max(1, p.numel())
+            arr[i].shadow_ld = sh.stride(0) if sh is not None else 0
+            for off in range(0, p.numel(), ADAM_CHUNK):
+                c2t.append(i)
+                coff.append(off)
+        self.n_tensors = len(entries)
+        self.total_chunks = len(c2t)
+        self.tensors = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        self.chunk_to_tensor = torch.tensor(c2t, dtype=torch.int32, device=device)
+        self.chunk_offset = torch.tensor(coff, dtype=torch.int64, device=device)
+
+    def step(self, lr, beta1, beta2, eps, wd, decoupled, step_dev, grad_scale=1.0):
+        call("sbr_adam_step", ptr(self.tensors), self.n_tensors, self.total_chunks, ptr(self.chunk_to_tensor),
+             ptr(self.chunk_offset), float(lr), float(beta1), float(beta2), float(eps), float(wd), int(decoupled),
+             ptr(step_dev), float(grad_scale), stream_ptr())
+
+
+def topk_n_splits(U: int, I: int, D: int, k: int, n_sms: int = 148) -> int:
+    nu = 256 if D <= 256 else 128
+    user_tiles = (U + nu - 1) // nu
+    item_tiles = (I + 127) // 128
+    want = max(1, -(-n_sms // user_tiles))
+    splits = min(want, item_tiles, max(1, 1024 // k))
+    tps = -(-item_tiles // splits)
+    return -(-item_tiles // tps)  # no empty split
+
+
+def topk_scores_masked(users_bf16, items_bf16, U, I, D, seen_indptr, seen_indices, k, n_splits=None, item_offset=0,
+                       return_keys=False):
+    """exact masked top-k of users @ items^T.  Returns (vals [U,k] f32, idx [U,k] i32) or packed keys [U,k]."""
+    dev = users_bf16.device
+    if n_splits is None:
+        n_splits = topk_n_splits(U, I, D, k, torch.cuda.get_device_properties(dev).multi_processor_count)
+    nbytes = C.c_int64(0)
+    call("sbr_topk_workspace_bytes", int(U), int(I), int(D), int(k), int(n_splits), C.byref(nbytes))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    part = torch.empty((n_splits, U, k), dtype=torch.int64, device=dev)
+    call("sbr_topk_scores_masked", ptr(users_bf16), users_bf16.stride(0), ptr(items_bf16), items_bf16.stride(0), int(U),
+         int(I), int(D), ptr(seen_indptr), ptr(seen_indices), int(k), int(n_splits), int(item_offset), ptr(part),
+         ptr(ws), nbytes.value, stream_ptr())
+    return topk_merge(part, n_splits, U, k, return_keys=return_keys)
+
+
+def topk_merge(keys, L, U, k, return_keys=False):
+    dev = keys.device
+    if return_keys:
+        out = torch.empty((U, k), dtype=torch.int64, device=dev)
+        call("sbr_topk_merge", ptr(keys), int(L), int(U), int(k), None, None, ptr(out), stream_ptr())
+        return out
+    vals = torch.empty((U, k), dtype=F32, device=dev)
+    idx = torch.empty((U, k), dtype=torch.int32, device=dev)
+    call("sbr_topk_merge", ptr(keys), int(L), int(U), int(k), ptr(vals), ptr(idx), None, stream_ptr())
+    return vals, idx
+
+
+def metrics_at_k(topk_idx, tgt_indptr, tgt_indices, ks, n_items, want_item_hits=False):
+    U, k = topk_idx.shape
+    dev = topk_idx.device
+    ks_dev = torch.tensor(sorted(ks), dtype=torch.int32, device=dev)
+    out = torch.zeros((5, len(ks), U), dtype=F32, device=dev)
+    hits = torch.zeros((len(ks), n_items), dtype=torch.int32, device=dev) if want_item_hits else None
+    call("sbr_metrics_at_k", ptr(topk_idx), int(U), int(k), ptr(tgt_indptr), ptr(tgt_indices), ptr(ks_dev), len(ks),
+         ptr(out), ptr(hits), int(n_items), stream_ptr())
+    return out, hits
+
+
+def sample_batch(coo_user, coo_item, train_indptr, train_indices, items_in_split, B, n_neg, seed, step_dev, out_u,
+                 out_i):
+    call("sbr_sample_batch", ptr(coo_user), ptr(coo_item), coo_user.numel(), ptr(train_indptr), ptr(train_indices),
+         ptr(items_in_split), items_in_split.numel(), int(B), int(n_neg), int(seed), ptr(step_dev), ptr(out_u),
+         ptr(out_i), stream_ptr())

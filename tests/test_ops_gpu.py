@@ -1,0 +1,340 @@
+"""Kernel-level parity tests (GPU): every C-ABI entry point against a plain fp32/fp64 torch / numpy statement of the
+same arithmetic on the same seeded inputs.  Tolerances: bf16-operand GEMMs 2e-2 relative to the output scale (bf16 has
+8 mantissa bits; accumulation is fp32), fp32 kernels 1e-5..1e-4, integer / index results bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from sibrar_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def _rand_bf16(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
+
+
+def _padded(t, ld):
+    out = torch.full((t.shape[0], ld), float("nan"), dtype=t.dtype, device=t.device)
+    out[:, :t.shape[1]] = t
+    return out[:, :t.shape[1]]  # view with pitch ld; the pad holds NaN on purpose (must never be read)
+
+
+def _relerr(a, b):
+    return (a.double() - b.double()).abs().max().item() / max(1e-12, b.double().abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 64, 70), (1000, 100, 200), (257, 200, 1000), (4096, 512, 128),
+                                   (77, 16, 8), (513, 24, 3706)])
+def test_gemm_linear_forward(M, N, K):
+    A = _padded(_rand_bf16(M, K, seed=1), ops.pad8(K) + 8)
+    W = _padded(_rand_bf16(N, K, seed=2, scale=0.2), ops.pad8(K))
+    bias = torch.randn(N, device=DEV)
+    o16 = torch.zeros((M, ops.pad8(N)), dtype=torch.bfloat16, device=DEV)
+    o32 = torch.zeros((M, N), dtype=torch.float32, device=DEV)
+    stats = torch.zeros(2 * N, device=DEV)
+    ops.gemm(A, W, M, N, K, bias=bias, act="relu", out_bf16=o16, out_f32=o32, colstats=stats)
+    ref = torch.relu(A.float() @ W.float().T + bias)
+    torch.cuda.synchronize()
+    assert _relerr(o32, ref) < 2e-5 * math.sqrt(K) + 1e-6, _relerr(o32, ref)
+    assert _relerr(o16[:, :N].float(), ref) < 1e-2
+    assert _relerr(stats[:N], ref.sum(0)) < 1e-4 and _relerr(stats[N:], (ref * ref).sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("rows,din,dout,split", [(1000, 64, 64, 1), (5000, 70, 100, 7), (3000, 768, 64, 4),
+                                                 (700, 300, 300, 3), (129, 16, 24, 2)])
+def test_gemm_wgrad_mn_major(rows, din, dout, split):
+    """dW[out, in] += dY^T X with X [rows, in], dY [rows, out] both read MN-major (contraction over rows)."""
+    X = _padded(_rand_bf16(rows, din, seed=3), ops.pad8(din))
+    dY = _padded(_rand_bf16(rows, dout, seed=4), ops.pad8(dout) + 8)
+    dW = torch.ones((dout, din), dtype=torch.float32, device=DEV)
+    ops.gemm(X, dY, din, dout, rows, a_mn=True, b_mn=True, out_f32=dW, transpose_out=True, atomic_out=True,
+             split_k=split)
+    ref = 1.0 + dY.float().T @ X.float()
+    torch.cuda.synchronize()
+    assert _relerr(dW, ref) < 1e-4, _relerr(dW, ref)
+
+
+@pytest.mark.parametrize("rows,din,dout", [(1000, 64, 64), (333, 100, 70), (2048, 512, 256), (100, 24, 16)])
+def test_gemm_dgrad_b_mn_major_actgrad(rows, din, dout):
+    """dX = (dY W) * relu'(Y_prev), column sums of the result = bias gradient of the previous layer."""
+    dY = _padded(_rand_bf16(rows, dout, seed=5), ops.pad8(dout))
+    W = _padded(_rand_bf16(dout, din, seed=6, scale=0.3), ops.pad8(din))
+    Yp = _padded(torch.relu(_rand_bf16(rows, din, seed=7)), ops.pad8(din))
+    o16 = torch.zeros((rows, ops.pad8(din)), dtype=torch.bfloat16, device=DEV)
+    o32 = torch.zeros((rows, din), dtype=torch.float32, device=DEV)
+    stats = torch.zeros(2 * din, device=DEV)
+    ops.gemm(dY, W, rows, din, dout, b_mn=True, out_bf16=o16, out_f32=o32, actgrad_y=Yp, actgrad_act="relu",
+             colstats=stats)
+    ref = (dY.float() @ W.float()) * (Yp.float() > 0)
+    torch.cuda.synchronize()
+    assert _relerr(o32, ref) < 1e-4, _relerr(o32, ref)
+    assert _relerr(o16[:, :din].float(), ref) < 1e-2
+    assert _relerr(stats[:din], ref.sum(0)) < 1e-3
+
+
+def _ref_topk(u, it, seen, k):
+    s = u.double() @ it.double().T
+    s = s.cpu().numpy()
+    if seen is not None:
+        ip, ix = seen
+        for r in range(s.shape[0]):
+            s[r, ix[ip[r]:ip[r + 1]]] = -np.inf
+    order = np.lexsort((np.broadcast_to(np.arange(s.shape[1]), s.shape), -s), axis=-1)[:, :k]
+    return np.take_along_axis(s, order, 1), order
+
+
+def _seen_csr(U, I, per_user, seed):
+    rng = np.random.default_rng(seed)
+    rows = [np.sort(rng.choice(I, size=min(I, int(rng.integers(0, per_user + 1))), replace=False)) for _ in range(U)]
+    indptr = np.zeros(U + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum([len(r) for r in rows])
+    return indptr, (np.concatenate(rows) if indptr[-1] else np.zeros(0)).astype(np.int32)
+
+
+@pytest.mark.parametrize("U,I,D,k,n_splits,per_user", [
+    (300, 1000, 64, 10, 1, 20), (300, 1000, 64, 10, 3, 20), (1000, 5000, 128, 50, None, 100),
+    (257, 3706, 64, 100, None, 300), (130, 700, 512, 20, 2, 50), (64, 129, 72, 5, 2, 129), (5, 40, 8, 1, 1, 3),
+    (200, 20000, 256, 10, None, 0)])
+def test_topk_scores_masked_exact(U, I, D, k, n_splits, per_user):
+    """small-integer embeddings -> every score is exact in fp32 whatever the accumulation order -> the top-k
+    (values AND positions, ties -> lowest position) must be bit-exact."""
+    g = torch.Generator().manual_seed(U + I)
+    u = torch.randint(-3, 4, (U, D), generator=g).to(torch.bfloat16).to(DEV)
+    it = torch.randint(-3, 4, (I, D), generator=g).to(torch.bfloat16).to(DEV)
+    seen = _seen_csr(U, I, per_user, seed=I) if per_user else None
+    ip = torch.from_numpy(seen[0]).to(DEV) if seen else None
+    ix = torch.from_numpy(seen[1]).to(DEV) if seen else None
+    vals, idx = ops.topk_scores_masked(u, it, U, I, D, ip, ix, k, n_splits=n_splits)
+    rv, ri = _ref_topk(u.float(), it.float(), seen, k)
+    vals, idx = vals.cpu().numpy(), idx.cpu().numpy()
+    finite = np.isfinite(rv)
+    assert (idx[finite] == ri[finite]).all(), f"{(idx[finite] != ri[finite]).sum()} of {finite.sum()} positions differ"
+    assert (vals[finite] == rv[finite]).all()
+    assert (idx[~finite] == -1).all() and np.isneginf(vals[~finite]).all()
+
+
+def test_topk_float_scores_close():
+    U, I, D, k = 500, 8000, 64, 20
+    u = _rand_bf16(U, D, seed=11, scale=D ** -0.5)
+    it = _rand_bf16(I, D, seed=12)
+    vals, idx = ops.topk_scores_masked(u, it, U, I, D, None, None, k)
+    rv, ri = _ref_topk(u.float(), it.float(), None, k)
+    vals, idx = vals.cpu().numpy(), idx.cpu().numpy()
+    assert np.abs(vals - rv).max() < 1e-4
+    gap = np.abs(np.diff(np.concatenate([rv, rv[:, -1:] - 1], 1), axis=1))
+    safe = (gap > 1e-4) & (np.abs(np.diff(np.concatenate([rv[:, :1] + 1, rv], 1), axis=1)) > 1e-4)
+    assert (idx[safe] == ri[safe]).all()
+
+
+def test_topk_merge_and_metrics():
+    from oracle import sbnet_oracle as O
+    import scipy.sparse as sp
+    U, I, k = 400, 3000, 20
+    rng = np.random.default_rng(0)
+    top = np.stack([rng.choice(I, size=k, replace=False) for _ in range(U)]).astype(np.int32)
+    tgt = sp.random(U, I, density=0.01, format="csr", random_state=1)
+    tgt.sort_indices()
+    ks = [1, 5, 10, 20]
+    out, hits = ops.metrics_at_k(torch.from_numpy(top).to(DEV), torch.from_numpy(tgt.indptr.astype(np.int64)).to(DEV),
+                                 torch.from_numpy(tgt.indices.astype(np.int32)).to(DEV), ks, I, want_item_hits=True)
+    ref = O.metrics_at_k(top, tgt, ks, n_items=I)
+    out = out.cpu().numpy()
+    for mi, m in enumerate(["ndcg", "precision", "recall", "f_score", "hitrate"]):
+        for ki, kk in enumerate(ks):
+            assert np.abs(out[mi, ki] - ref[f"{m}@{kk}"]).max() < 2e-6, (m, kk)
+    for ki, kk in enumerate(ks):
+        assert hits[ki].sum().item() / I == pytest.approx(ref[f"coverage@{kk}"])
+
+
+def test_spmm_matches_dense():
+    import scipy.sparse as sp
+    rows, d, C_ = 700, 900, 64
+    m = sp.random(rows, d, density=0.03, format="csr", random_state=3)
+    m.data[:] = 1
+    m.sort_indices()
+    Wt = torch.randn(d, C_, device=DEV)
+    b = torch.randn(C_, device=DEV)
+    out = torch.empty(rows, C_, device=DEV)
+    ip = torch.from_numpy(m.indptr.astype(np.int64)).to(DEV)
+    ix = torch.from_numpy(m.indices.astype(np.int32)).to(DEV)
+    ops.spmm_csr(ip, ix, rows, Wt, C_, b, "relu", out)
+    ref = torch.relu(torch.from_numpy(m.toarray()).float().to(DEV) @ Wt + b)
+    assert _relerr(out, ref) < 1e-5
+    dense = ops.csr_to_dense_bf16(ip, ix, rows, d)
+    assert (dense[:, :d].float().cpu().numpy() == m.toarray()).all()
+    outT = torch.zeros(C_, rows, device=DEV)
+    ops.spmm_csr(ip, ix, rows, Wt, C_, None, None, outT, transpose_out=True)
+    assert _relerr(outT.T, torch.from_numpy(m.toarray()).float().to(DEV) @ Wt) < 1e-5
+
+
+def test_row_gather_fwd_bwd():
+    n_ent, C_, k = 50, 24, 2
+    g = torch.Generator().manual_seed(5)
+    table = torch.randn(n_ent, C_, generator=g).to(DEV)
+    emb = torch.randn(7, C_, generator=g).to(DEV)
+    bag = torch.randn(6, C_, generator=g).to(DEV)
+    cat = torch.randint(0, 7, (n_ent,), generator=g).int().to(DEV)
+    tags = torch.randint(0, 6, (n_ent, 4), generator=g).int().to(DEV)  # pad id = 5
+    remap = torch.randperm(n_ent, generator=g).int().to(DEV)
+    grads = [torch.zeros_like(table), torch.zeros_like(emb), torch.zeros_like(bag)]
+    srcs = ops.make_modality_srcs([
+        dict(kind=0, remap=remap, table=table, grad=grads[0]),
+        dict(kind=1, remap=None, table=emb, grad=grads[1], codes=cat),
+        dict(kind=2, remap=None, table=bag, grad=grads[2], codes=tags, max_tags=4, pad_id=5)], DEV)
+    idx = torch.randint(0, n_ent, (33,), generator=g).to(DEV)
+    mods = torch.randint(0, 3, (33 * k,), generator=g).to(torch.uint8).to(DEV)
+    keep = (torch.rand(33 * k, C_, generator=g) > 0.3).to(torch.uint8).to(DEV)
+    step = torch.zeros(1, dtype=torch.int64, device=DEV)
+    out = torch.zeros(33 * k, C_, device=DEV)
+    ops.row_gather_fwd(srcs, 3, idx, mods, k, C_, True, 0.3, 1, step, keep, out_f32=out)
+
+    t_table, t_emb, t_bag = (x.clone().requires_grad_() for x in (table, emb, bag))
+    fi = idx.repeat_interleave(k)
+    x0 = t_table[remap[fi].long()]
+    x1 = t_emb[cat[fi].long()]
+    valid = (tags[fi] != 5).float()
+    x2 = (t_bag[tags[fi].long()] * valid[..., None]).sum(1) / valid.sum(1).clamp(min=1)[:, None]
+    x = torch.where((mods == 0)[:, None], x0, torch.where((mods == 1)[:, None], x1, x2))
+    ref = torch.nn.functional.normalize(x, dim=-1) * keep.float() / 0.7
+    assert _relerr(out, ref) < 1e-5
+    dx = torch.randn(33 * k, C_, device=DEV)
+    ops.row_gather_bwd(srcs, 3, idx, mods, k, C_, True, 0.3, 1, step, keep, dx)
+    ref.backward(dx)
+    gb = t_bag.grad.clone()
+    gb[5] = 0
+    grads[2][5] = 0
+    for got, want in zip(grads, (t_table.grad, t_emb.grad, gb)):
+        assert _relerr(got, want) < 1e-4
+
+    # Philox dropout: deterministic for (seed, step), keeps ~ (1 - p)
+    big = torch.zeros(4000, C_, device=DEV)
+    idx2 = torch.randint(0, n_ent, (4000,), generator=g).to(DEV)
+    ops.row_gather_fwd(srcs, 1, idx2, None, 1, C_, False, 0.25, 7, step, None, out_f32=big)
+    big2 = torch.zeros_like(big)
+    ops.row_gather_fwd(srcs, 1, idx2, None, 1, C_, False, 0.25, 7, step, None, out_f32=big2)
+    assert torch.equal(big, big2)
+    assert abs((big != 0).float().mean().item() - 0.75) < 0.01
+
+
+@pytest.mark.parametrize("act", [None, "relu"])
+def test_batchnorm_fwd_bwd(act):
+    rows, C_ = 1000, 40
+    z = (torch.randn(rows, C_, device=DEV) * 2 + 1).requires_grad_()
+    gamma = torch.randn(C_, device=DEV).requires_grad_()
+    beta = torch.randn(C_, device=DEV).requires_grad_()
+    rm, rv = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
+    ref = torch.nn.functional.batch_norm(z, rm.clone(), rv.clone(), gamma, beta, True, 0.1, 1e-5)
+    ref = torch.relu(ref) if act else ref
+    stats = torch.stack([z.detach().sum(0), (z.detach() ** 2).sum(0)]).reshape(-1).contiguous()
+    mi = torch.empty(2 * C_, device=DEV)
+    nbt = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ops.bn_finalize(stats, rows, C_, mi, rm, rv, nbt)
+    y = torch.empty(rows, C_, device=DEV)
+    ops.bn_apply(z.detach(), mi, gamma.detach(), beta.detach(), act, rows, C_, out_f32=y)
+    assert _relerr(y, ref) < 1e-4
+    rm2, rv2 = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
+    torch.nn.functional.batch_norm(z.detach(), rm2, rv2, None, None, True, 0.1, 1e-5)
+    assert _relerr(rm, rm2) < 1e-4 and _relerr(rv, rv2) < 1e-4 and nbt.item() == 1
+    dy = torch.randn(rows, C_, device=DEV)
+    ref.backward(dy)
+    sums = torch.zeros(2 * C_, device=DEV)
+    ops.bn_bwd_reduce(dy, y, act, z.detach(), mi, rows, C_, sums)
+    dz = torch.empty(rows, C_, device=DEV)
+    dg, db = torch.zeros(C_, device=DEV), torch.zeros(C_, device=DEV)
+    ops.bn_bwd_apply(dy, y, act, z.detach(), mi, gamma.detach(), sums, rows, C_, dz_f32=dz, dgamma=dg, dbeta=db)
+    assert _relerr(dz, z.grad) < 2e-4 and _relerr(dg, gamma.grad) < 1e-4 and _relerr(db, beta.grad) < 1e-4
+
+
+@pytest.mark.parametrize("loss,agg_u,agg_i,ku,ki,sum_", [("bpr", 0, 0, 1, 1, 0), ("bpr", 0, 1, 2, 2, 0),
+                                                         ("bce", 1, 0, 2, 1, 1), ("sampled_softmax", 0, 0, 1, 2, 0)])
+def test_score_loss(loss, agg_u, agg_i, ku, ki, sum_):
+    from oracle import sbnet_oracle as O
+    B, n, D = 37, 6, 24
+    eu = torch.randn(B, ku, D, device=DEV).requires_grad_()
+    ei = torch.randn(B, n, ki, D, device=DEV).requires_grad_()
+    logits = torch.empty(B, n, device=DEV)
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    deu, dei = torch.empty_like(eu), torch.empty_like(ei)
+    shift = math.log(100 / (n - 1)) if loss == "sampled_softmax" else 0.0
+    ops.score_loss(eu.detach(), ei.detach(), B, n, ku, ki, D, agg_u, agg_i, loss, sum_, shift, logits, acc, deu, dei)
+    u = eu.max(1).values if agg_u else eu.mean(1)
+    it = ei.max(2).values if agg_i else ei.mean(2)
+    ref_logits = torch.einsum("be,bce->bc", u, it)
+    rl, dlog = O.rec_loss(loss, ref_logits.detach().cpu().numpy(), "sum" if sum_ else "mean", 100, n - 1,
+                          "uniform" if loss == "sampled_softmax" else "uniform_recbole")
+    ref_logits.backward(torch.from_numpy(dlog).float().to(DEV))
+    assert _relerr(logits, ref_logits) < 1e-5
+    assert abs(acc.item() - rl) < 1e-5 * max(1, abs(rl))
+    assert _relerr(deu, eu.grad) < 1e-4 and _relerr(dei, ei.grad) < 1e-4
+
+
+@pytest.mark.parametrize("G,n,D", [(9, 5, 24), (1, 70, 16), (300, 11, 64)])
+def test_infonce(G, n, D):
+    from oracle import sbnet_oracle as O
+    e = torch.randn(G, n, 2, D, device=DEV) * 0.5
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    de = torch.ones_like(e)
+    ops.infonce(e, G, n, D, 0.7, 0.3, acc, de, accumulate=1)
+    en = e.double().cpu().numpy()
+    loss, d0, d1 = O.info_nce(en[:, :, 0], en[:, :, 1], 0.7)
+    assert abs(acc.item() - 0.3 * loss) < 1e-5 * max(1, abs(loss))
+    ref = 1.0 + 0.3 * np.stack([d0, d1], axis=2)
+    assert np.abs(de.cpu().numpy() - ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("decoupled", [0, 1])
+def test_adam(decoupled):
+    shapes = [(70, 33), (5000,), (3, 4097), (1,)]
+    ps = [torch.randn(*s, device=DEV) for s in shapes]
+    ref = [p.clone().requires_grad_() for p in ps]
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)(ref, lr=1e-2, weight_decay=0.1)
+    grads = [torch.zeros_like(p) for p in ps]
+    shadows = [torch.zeros((70, 40), dtype=torch.bfloat16, device=DEV), None, None, None]
+    plan = ops.AdamPlan([dict(param=p, grad=g, exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p), shadow=s)
+                         for p, g, s in zip(ps, grads, shadows)], DEV)
+    step = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for it in range(3):
+        ops.tick(step)
+        for g, r in zip(grads, ref):
+            g.copy_(torch.randn_like(g))
+            r.grad = g.clone()
+        opt.step()
+        plan.step(1e-2, 0.9, 0.999, 1e-8, 0.1, decoupled, step)
+        for p, r, g in zip(ps, ref, grads):
+            assert _relerr(p, r.detach()) < 1e-5
+            assert g.abs().max().item() == 0
+    assert torch.equal(shadows[0][:, :33], ps[0].to(torch.bfloat16))
+
+
+def test_samplers():
+    import scipy.sparse as sp
+    U, I, B, n_neg = 200, 300, 5000, 6
+    m = sp.random(U, I, density=0.05, format="csr", random_state=2)
+    m.sort_indices()
+    coo = m.tocoo()
+    d = lambda a, t: torch.from_numpy(a.astype(t)).to(DEV)  # noqa: E731
+    items = np.arange(0, I, 2)
+    step = torch.ones(1, dtype=torch.int64, device=DEV)
+    out_u = torch.empty(B, dtype=torch.int64, device=DEV)
+    out_i = torch.empty(B, n_neg + 1, dtype=torch.int64, device=DEV)
+    ops.sample_batch(d(coo.row, np.int32), d(coo.col, np.int32), d(m.indptr, np.int64), d(m.indices, np.int32),
+                     d(items, np.int32), B, n_neg, 3, step, out_u, out_i)
+    u, i = out_u.cpu().numpy(), out_i.cpu().numpy()
+    dense = m.toarray() != 0
+    assert dense[u, i[:, 0]].all()
+    assert not dense[u[:, None], i[:, 1:]].any()
+    assert np.isin(i[:, 1:], items).all()
+    mods = torch.empty(20000 * 2, dtype=torch.uint8, device=DEV)
+    ops.sample_modalities(mods, 20000, 2, 4, -1, 5, step)
+    mm = mods.view(-1, 2).cpu().numpy()
+    assert (mm[:, 0] != mm[:, 1]).all() and mm.max() == 3
+    assert np.abs(np.bincount(mm[:, 0], minlength=4) / 20000 - 0.25).max() < 0.02
+    ops.sample_modalities(mods, 20000, 2, 4, 2, 5, step)
+    mm = mods.view(-1, 2).cpu().numpy()
+    assert (mm[:, 0] == 2).all() and (mm[:, 1] != 2).all()
