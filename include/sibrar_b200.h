@@ -57,6 +57,7 @@ typedef struct {
   float* out_f32;         /* optional fp32 output [M, N] ([N, M] if transpose_out)                                */
   int64_t ld_f32;
   float* colstats;        /* optional [2*N]: += column sum / sum of squares of the FINAL epilogue value, valid rows */
+  int colstats_sum_only;  /* 1: only the N column sums are accumulated (e.g. a bias gradient)                     */
   const void* actgrad_y;  /* optional bf16 [M, N]: result *= act'(y) expressed through the saved output y         */
   int64_t ld_actgrad;
   int actgrad_act;

@@ -22,7 +22,7 @@ c_i64, c_i32, c_f32, c_vp, c_u64 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, 
 
 class GemmEpilogue(C.Structure):
     _fields_ = [("bias", c_vp), ("act", C.c_int), ("out_bf16", c_vp), ("ld_bf16", c_i64), ("out_f32", c_vp),
-                ("ld_f32", c_i64), ("colstats", c_vp), ("actgrad_y", c_vp), ("ld_actgrad", c_i64),
+                ("ld_f32", c_i64), ("colstats", c_vp), ("colstats_sum_only", C.c_int), ("actgrad_y", c_vp), ("ld_actgrad", c_i64),
                 ("actgrad_act", C.c_int), ("transpose_out", C.c_int), ("atomic_out", C.c_int), ("split_k", C.c_int),
                 ("alpha", c_f32)]
 

@@ -186,10 +186,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s2[j] = x * x;
         }
         float cs = warp_colsum32(s1, lane);
-        float cq = warp_colsum32(s2, lane);
-        if (col0 + lane < p.N) {
-          atomicAdd(ep.colstats + col0 + lane, cs);
-          atomicAdd(ep.colstats + p.N + col0 + lane, cq);
+        if (col0 + lane < p.N) atomicAdd(ep.colstats + col0 + lane, cs);
+        if (!ep.colstats_sum_only) {
+          float cq = warp_colsum32(s2, lane);
+          if (col0 + lane < p.N) atomicAdd(ep.colstats + p.N + col0 + lane, cq);
         }
       }
       if (ep.transpose_out) {

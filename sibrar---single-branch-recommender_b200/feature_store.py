@@ -1,0 +1,101 @@
+"""Device-resident feature store: built ONCE from ``dataset.{user,item}_features`` and then read by the kernels.
+
+Replaces the per-batch host path of the reference (``data/Feature.py:140-162``: ``np.vectorize`` dict lookups,
+``csr.toarray()``, ``torch.tensor(values, device=...)`` with a D2H sync + an H2D copy per modality per step).
+
+HBM layout per feature (row = position in the feature's value table, NOT the entity index):
+  * ``remap``  int32 [n_entities]  entity index -> row (-1: entity has no row; identity maps are dropped)
+  * dense (VECTOR / CONTINUOUS / DISCRETE, and 'interactions' when dense enough):
+        ``x16`` bf16 [n_rows, pad8(d)]  row-major -- read K-major by the forward GEMM and MN-major by the wgrad GEMM
+  * csr ('interactions', sparse route): ``indptr`` int64 / ``indices`` int32 of the matrix and of its transpose
+  * CATEGORICAL: ``codes`` int32 [n_rows];  TAG: ``codes`` int32 [n_rows, max_tags] padded with ``pad_id``
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import ops
+
+
+def feature_type(feature) -> str:
+    t = feature.feature_definition.type
+    return str(getattr(t, "value", t)).lower()
+
+
+class DeviceFeature:
+    def __init__(self, name: str, feature, n_entities: int, device, dense_min_density: float = 0.004,
+                 dense_max_bytes: int = 48 << 30):
+        self.name = name
+        self.type = feature_type(feature)
+        self.device = device
+        values = feature.values
+        idx = np.asarray(feature._indices)
+        self.n_rows = int(values.shape[0])
+        self.remap = None
+        if not (len(idx) == n_entities and np.array_equal(idx, np.arange(n_entities))):
+            remap = np.full(n_entities, -1, dtype=np.int32)
+            remap[idx] = np.arange(len(idx), dtype=np.int32)
+            self.remap = torch.from_numpy(remap).to(device)
+        self.x16 = self.csr = self.csr_t = self.codes = None
+        self.max_tags, self.pad_id, self.n_cat = 0, -1, 0
+        if self.type == "categorical":
+            self.kind = "categorical"
+            self.n_cat = int(feature.n_unique_categories)
+            self.codes = torch.from_numpy(np.asarray(values).astype(np.int32)).to(device)
+            self.dim = 0
+        elif self.type == "tag":
+            self.kind = "tag"
+            v = np.asarray(values).astype(np.int32)
+            self.codes = torch.from_numpy(np.ascontiguousarray(v)).to(device)
+            self.max_tags = int(v.shape[1])
+            self.pad_id = int(feature.dim)  # padding index == number of tags (data/Feature.py:254-255)
+            self.n_cat = int(feature.dim) + 1
+            self.dim = int(feature.dim)
+        elif sp.issparse(values):
+            m = values.tocsr()
+            m.sort_indices()
+            self.dim = int(m.shape[1])
+            density = m.nnz / max(1, m.shape[0] * m.shape[1])
+            dense_bytes = m.shape[0] * ops.pad8(m.shape[1]) * 2
+            ip = torch.from_numpy(m.indptr.astype(np.int64)).to(device)
+            ix = torch.from_numpy(m.indices.astype(np.int32)).to(device)
+            if density >= dense_min_density and dense_bytes <= dense_max_bytes:
+                # dense bf16 multi-hot, resident in HBM: the projection becomes a tcgen05 GEMM
+                self.kind = "dense"
+                self.x16 = ops.csr_to_dense_bf16(ip, ix, m.shape[0], m.shape[1])
+            else:
+                self.kind = "csr"
+                mt = m.T.tocsr()
+                mt.sort_indices()
+                self.csr = (ip, ix)
+                self.csr_t = (torch.from_numpy(mt.indptr.astype(np.int64)).to(device),
+                              torch.from_numpy(mt.indices.astype(np.int32)).to(device))
+        else:
+            self.kind = "dense"
+            v = np.asarray(values, dtype=np.float32)
+            if v.ndim == 1:
+                v = v[:, None]
+            v = v.reshape(v.shape[0], -1)
+            self.dim = int(v.shape[1])
+            x = torch.zeros((v.shape[0], ops.pad8(self.dim)), dtype=torch.bfloat16, device=device)
+            x[:, :self.dim] = torch.from_numpy(v).to(device)  # one-off H2D + cast at build time
+            self.x16 = x
+
+    def nbytes(self) -> int:
+        n = 0
+        for t in (self.remap, self.x16, self.codes):
+            if t is not None:
+                n += t.numel() * t.element_size()
+        for pair in (self.csr, self.csr_t):
+            if pair is not None:
+                n += sum(t.numel() * t.element_size() for t in pair)
+        return n
+
+
+def csr_to_device(m, device):
+    m = m.tocsr()
+    m.sort_indices()
+    return (torch.from_numpy(m.indptr.astype(np.int64)).to(device),
+            torch.from_numpy(m.indices.astype(np.int32)).to(device))

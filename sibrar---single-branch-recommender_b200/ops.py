@@ -20,7 +20,7 @@ def _act(a):
 
 
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, act=None, out_bf16=None,
-         out_f32=None, colstats=None, actgrad_y=None, actgrad_act=None, transpose_out=False, atomic_out=False,
+         out_f32=None, colstats=None, colstats_sum_only=False, actgrad_y=None, actgrad_act=None, transpose_out=False, atomic_out=False,
          split_k=1, alpha=1.0):
     """D[M,N] = alpha * A @ B^T (bf16 in, fp32 accumulate) + fused epilogue.  A/B: 2-D bf16 tensors whose last
     dimension is contiguous; K-major means [rows, K], MN-major means [K, rows]."""
@@ -33,6 +33,7 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None
     ep.out_f32 = ptr(out_f32)
     ep.ld_f32 = out_f32.stride(0) if out_f32 is not None else 0
     ep.colstats = ptr(colstats)
+    ep.colstats_sum_only = int(colstats_sum_only)
     ep.actgrad_y = ptr(actgrad_y)
     ep.ld_actgrad = actgrad_y.stride(0) if actgrad_y is not None else 0
     ep.actgrad_act = _act(actgrad_act)
@@ -183,6 +184,7 @@ class AdamPlan:
     def __init__(self, entries, device):
         """entries: list of dict(param, grad, exp_avg, exp_avg_sq, shadow(optional bf16 [rows, ld]))"""
         arr = (AdamTensor * len(entries))()
+        self.entries = entries  # keeps every tensor whose raw pointer is stored below alive
         c2t, coff = [], []
         for i, e in enumerate(entries):
             p = e["param"]
