@@ -123,10 +123,11 @@ int sbr_row_gather_bwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int
                        const int64_t* step_dev, const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
                        void* stream);
 
-/* table-level backward of the projection output activation: dpre = dT * act'(T) -> bf16 (+ column sums = dbias) */
-int sbr_actgrad_colsum(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y, int act,
+/* table-level backward of the projection output activation: dpre = dT * act'(T) -> bf16 (+ column sums = dbias).
+ * zero_dy = 1 clears dy after reading it (the gradient table is an atomicAdd accumulator reused every step). */
+int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y, int act,
                        int64_t rows, int64_t cols, void* out_bf16, int64_t ld_out, float* out_f32, int64_t ld_out_f32,
-                       float* colsum, void* stream);
+                       float* colsum, int zero_dy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ BatchNorm1d
  * (torch.nn.BatchNorm1d used at modules/polylinear.py:58-61,68-69 and algorithms/sgd_alg.py:1834-1837)

@@ -30,10 +30,10 @@ __device__ __forceinline__ void block_col_flush(float v, float* dst, int c, int 
   __syncthreads();
 }
 
-__global__ void actgrad_colsum_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
+__global__ void actgrad_colsum_kernel(float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
                                       const bf16* __restrict__ y_bf16, int64_t ld_y, int act, int64_t rows, int C,
                                       bf16* __restrict__ out_bf16, int64_t ld_out, float* __restrict__ out_f32,
-                                      int64_t ld_out_f32, float* __restrict__ colsum) {
+                                      int64_t ld_out_f32, float* __restrict__ colsum, int zero_dy) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   const int64_t r0 = (int64_t)blockIdx.x * RB;
@@ -43,6 +43,7 @@ __global__ void actgrad_colsum_kernel(const float* __restrict__ dy, int64_t ld_d
       int64_t r = r0 + rr;
       if (r >= rows) break;
       float v = dy[r * ld_dy + c];
+      if (zero_dy) dy[r * ld_dy + c] = 0.f;
       if (act != SBR_ACT_NONE) v *= act_grad_from_out(act, load_y(y_f32, y_bf16, r * ld_y + c));
       part += v;
       if (out_bf16) out_bf16[r * ld_out + c] = __float2bfloat16(v);
@@ -153,14 +154,14 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy,
 inline dim3 tile_grid(int64_t rows, int64_t cols) { return dim3(cdiv(rows, RB), cdiv(cols, 32)); }
 }  // namespace
 
-extern "C" int sbr_actgrad_colsum(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
+extern "C" int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
                                   int act, int64_t rows, int64_t cols, void* out_bf16, int64_t ld_out, float* out_f32,
-                                  int64_t ld_out_f32, float* colsum, void* stream) {
+                                  int64_t ld_out_f32, float* colsum, int zero_dy, void* stream) {
   SBR_REQUIRE(dy && rows > 0 && cols > 0, "sbr_actgrad_colsum: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_actgrad_colsum: activation gradient needs the output y");
   actgrad_colsum_kernel<<<tile_grid(rows, cols), 256, 0, S(stream)>>>(
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, rows, (int)cols,
-      reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum);
+      reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum, zero_dy);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

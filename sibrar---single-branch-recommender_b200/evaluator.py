@@ -1,0 +1,121 @@
+"""Full-catalog evaluation on the device: replaces ``evaluate_recommender_algorithm`` + ``FullEvaluator``
+(``eval/eval.py:20-227``) for SGD-based algorithms.
+
+Item representations once (all ``items_in_split``, all eval modalities), user representations once, then ONE fused
+kernel does scores -> seen-item mask -> exact top-k (``csrc/eval_topk.cu``) followed by the metric kernel; the
+[U, I] score matrix, the dense label rows (``data/dataset.py:445-453``) and the dense host masks
+(``eval/eval.py:219``) of the reference never exist.  Result keys follow the reference: ``'{metric}@{k}'``
+(optionally ``'{name}/...'``), mean over the users of the split, ``_std`` when requested, ``coverage@k`` from all
+users' top-k.
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import EvalConfig
+from .feature_store import csr_to_device
+
+USER_METRICS = ["ndcg", "precision", "recall", "f_score", "hitrate"]  # order of sbr_metrics_at_k's output
+SUPPORTED = USER_METRICS + ["coverage"]
+
+
+def _natural_key(s: str):
+    return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", s)]
+
+
+class FullEvaluator:
+    def __init__(self, config, evaluator_name: Optional[str] = None, dataset=None):
+        if isinstance(config, dict):
+            config = EvalConfig.from_dict(config)
+        invalid = set(config.metrics) - set(SUPPORTED)
+        if invalid:
+            raise ValueError(f"Metric(s) {invalid} are not supported. Select metrics from {SUPPORTED}.")
+        self.config, self.name, self.dataset = config, evaluator_name, dataset
+        self._dev_cache = None
+
+    def _device_split(self, dataset, device):
+        if self._dev_cache is not None and self._dev_cache[0] is dataset and self._dev_cache[1] == device:
+            return self._dev_cache[2]
+        users = np.asarray(dataset.users_in_split)
+        items = np.asarray(dataset.items_in_split)
+        seen = dataset.exclude_data[users] if dataset.exclude_data is not None else None
+        tgt = dataset.user_sampling_matrix[users][:, items]
+        pack = dict(users=torch.from_numpy(users.astype(np.int64)).to(device),
+                    items=torch.from_numpy(items.astype(np.int64)).to(device),
+                    seen=csr_to_device(seen, device) if seen is not None and seen.nnz > 0 else (None, None),
+                    tgt=csr_to_device(tgt, device))
+        self._dev_cache = (dataset, device, pack)
+        return pack
+
+    @torch.no_grad()
+    def evaluate(self, model, dataset=None, return_topk: bool = False) -> Dict[str, float]:
+        dataset = dataset or self.dataset
+        dev = model.device
+        d = self._device_split(dataset, dev)
+        was_training = model.training
+        model.eval()
+        i_repr = model.get_item_representations(d["items"])
+        u_repr = model.get_user_representations(d["users"])
+        if was_training:
+            model.train()
+        res = self.evaluate_representations(u_repr, i_repr, d["seen"], d["tgt"], len(dataset.items_in_split),
+                                            return_topk=return_topk)
+        return res
+
+    @torch.no_grad()
+    def evaluate_representations(self, u_repr, i_repr, seen, tgt, n_items, return_topk=False, item_offset=0):
+        U, D = u_repr.shape
+        I = i_repr.shape[0]
+        ks = sorted(set(int(k) for k in self.config.top_k))
+        kmax = min(max(ks), I)
+        u16 = ops.cast_bf16(u_repr.contiguous())
+        i16 = ops.cast_bf16(i_repr.contiguous())
+        vals, idx = ops.topk_scores_masked(u16, i16, U, I, u16.shape[1], seen[0], seen[1], kmax,
+                                           item_offset=item_offset)
+        out = self.metrics_from_topk(idx, tgt, ks, n_items)
+        if return_topk:
+            return out, (vals, idx)
+        return out
+
+    def metrics_from_topk(self, idx, tgt, ks, n_items) -> Dict[str, float]:
+        kmax = idx.shape[1]
+        ks_eff = [k for k in ks if k <= kmax]
+        want_cov = "coverage" in self.config.metrics
+        m, hits = ops.metrics_at_k(idx, tgt[0], tgt[1], ks_eff, n_items, want_item_hits=want_cov)
+        mean = m.mean(dim=2).cpu().numpy()
+        std = m.std(dim=2, unbiased=False).cpu().numpy() if self.config.calculate_std else None
+        pre = f"{self.name}/" if self.name else ""
+        res = {}
+        for mi, name in enumerate(USER_METRICS):
+            if name not in self.config.metrics:
+                continue
+            for ki, k in enumerate(ks_eff):
+                res[f"{pre}{name}@{k}"] = float(mean[mi, ki])
+                if std is not None:
+                    res[f"{pre}{name}@{k}_std"] = float(std[mi, ki])
+        if want_cov:
+            cov = hits.sum(dim=1).cpu().numpy() / float(n_items)
+            for ki, k in enumerate(ks_eff):
+                res[f"{pre}coverage@{k}"] = float(cov[ki])
+        self.raw = m
+        return {k: res[k] for k in sorted(res, key=_natural_key)}
+
+
+def evaluate_recommender_algorithm(alg, eval_loader_or_dataset, evaluator: FullEvaluator, device="cuda",
+                                   return_raw=False, verbose=False):
+    """signature-compatible entry (``eval/eval.py:171``); ``eval_loader_or_dataset`` may be a DataLoader whose
+    ``.dataset`` is the eval split, or the split itself."""
+    dataset = getattr(eval_loader_or_dataset, "dataset", eval_loader_or_dataset)
+    results = evaluator.evaluate(alg, dataset)
+    if return_raw:
+        raw = {f"{name}@{k}": evaluator.raw[mi, ki].cpu().numpy()
+               for mi, name in enumerate(USER_METRICS)
+               for ki, k in enumerate(sorted(set(evaluator.config.top_k)))
+               if ki < evaluator.raw.shape[1]}
+        return results, raw
+    return results

@@ -118,11 +118,11 @@ def _y_args(y):
     return (ptr(y), None, y.stride(0)) if y.dtype == F32 else (None, ptr(y), y.stride(0))
 
 
-def actgrad_colsum(dy, y, act, rows, cols, out_bf16=None, out_f32=None, colsum=None):
+def actgrad_colsum(dy, y, act, rows, cols, out_bf16=None, out_f32=None, colsum=None, zero_dy=False):
     yf, yb, ldy = _y_args(y)
     call("sbr_actgrad_colsum", ptr(dy), dy.stride(0), yf, yb, ldy, _act(act), int(rows), int(cols), ptr(out_bf16),
          out_bf16.stride(0) if out_bf16 is not None else 0, ptr(out_f32),
-         out_f32.stride(0) if out_f32 is not None else 0, ptr(colsum), stream_ptr())
+         out_f32.stride(0) if out_f32 is not None else 0, ptr(colsum), int(zero_dy), stream_ptr())
 
 
 def bn_finalize(stats, n_rows, C_, mean_invstd, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):

@@ -1,0 +1,745 @@
+"""SingleBranchNet on B200: drop-in for the reference's algorithm API (``algorithms/sgd_alg.py:2009-2144``,
+``algorithms/base_classes.py:87-170``) with every arithmetic step executed by the hand-written sm_100a kernels.
+
+Same constructor ``(config, dataset)``, ``build_from_conf(conf: dict, dataset)``, ``forward / predict /
+get_user_representations / get_item_representations / combine_user_item_representations /
+get_and_reset_other_loss / save_model_to_path / load_model_from_path`` and the same ``state_dict()`` keys
+(the modules below only hold parameters under the reference's names; they never run torch arithmetic).
+
+B200-first design:
+  * feature store resident in HBM (``feature_store.py``); no host work per step;
+  * "entity-table projection": each step projects ALL rows of a dense/sparse modality once
+    (``T_m = act(X_m W^T + b)``, a tcgen05 GEMM or a CSR SpMM), batch rows then gather 1 row of ``T_m`` each
+    -- the reference re-projects every batch row (``sgd_alg.py:1960-1974``); results are identical;
+  * SB-net = chain of fused stages ``Linear -> [act] -> [BatchNorm -> [act]]``; BN statistics come out of the GEMM
+    epilogue; dgrad epilogues apply the previous activation's derivative and emit the bias gradient;
+  * gradients accumulate into persistent fp32 buffers; one multi-tensor Adam(W) launch updates fp32 masters and
+    their bf16 shadows.
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import SRC_CATEGORICAL, SRC_TABLE, SRC_TAG
+from .config import (EmbeddingRegularizationType, FeatureModuleConfig, SingleBranchNetConfig,
+                     SingleBranchNetEntityConfig)
+from .feature_store import DeviceFeature, feature_type
+
+BF16, F32 = torch.bfloat16, torch.float32
+ACTIVATIONS = ("relu", "tanh", "sigmoid", "selu")
+
+
+# ================================================================================================ parameter holders
+def _kaiming_relu_(linear: nn.Linear):
+    """``general_weight_init`` of the reference for nn.Linear (train/utils.py:5-10)"""
+    nn.init.kaiming_uniform_(linear.weight, nonlinearity="relu")
+    if linear.bias is not None:
+        nn.init.constant_(linear.bias, 0)
+
+
+class PolyLinear(nn.Module):
+    """Holds the parameters of the reference's PolyLinear under the same names (modules/polylinear.py:50-71):
+    ``layers.linear_{i}``, ``layers.batch_norm_{i}``, ``layers.batch_norm``.  ``spec`` lists the ops in order."""
+
+    def __init__(self, layer_config, activation_fn="relu", output_fn="relu", apply_batch_norm_every: int = 0):
+        super().__init__()
+        assert len(layer_config) > 1, "For a linear network, we at least need one input and one output dimension"
+        for a in (activation_fn, output_fn):
+            if a is not None and a not in ACTIVATIONS:
+                raise ValueError(f'activation "{a}" is not supported (choose from {ACTIVATIONS})')
+        self.layer_config = list(layer_config)
+        mods, spec = OrderedDict(), []
+        n_layers = len(layer_config) - 1
+        for i, (d1, d2) in enumerate(zip(layer_config[:-1], layer_config[1:])):
+            mods[f"linear_{i}"] = nn.Linear(d1, d2)
+            spec.append(("linear", f"linear_{i}"))
+            if apply_batch_norm_every > 0 and (i + 1) % apply_batch_norm_every == 0:
+                mods[f"batch_norm_{i}"] = nn.BatchNorm1d(d2)
+                spec.append(("bn", f"batch_norm_{i}"))
+            if i < n_layers - 1:
+                spec.append(("act", activation_fn))
+        if apply_batch_norm_every == -1:
+            mods["batch_norm"] = nn.BatchNorm1d(layer_config[-1])
+            spec.append(("bn", "batch_norm"))
+        if output_fn is not None:
+            spec.append(("act", output_fn))
+        self.layers = nn.ModuleDict(mods)
+        self.spec = spec
+
+    def forward(self, *a, **k):
+        raise RuntimeError("PolyLinear is a parameter container; arithmetic runs in the sibrar_b200 kernels")
+
+
+class _Identity(nn.Module):
+    """placeholder that keeps the reference's nn.Sequential numbering (a Dropout module shifts sb_net indices)"""
+
+    def forward(self, x):
+        return x
+
+
+# ================================================================================================ fused stages
+class LinearStage:
+    """Linear -> [act1] -> [BatchNorm -> [act2]]  run by kernels; holds bf16 shadows of the fp32 master weight."""
+
+    def __init__(self, linear: nn.Linear):
+        self.linear = linear
+        self.act1: Optional[str] = None
+        self.bn: Optional[nn.BatchNorm1d] = None
+        self.act2: Optional[str] = None
+        self.in_f, self.out_f = linear.in_features, linear.out_features
+        self.w16 = None     # bf16 [out, pad8(in)]: K-major B of the forward GEMM, MN-major B of the dgrad GEMM
+        self.wt32 = None    # fp32 [in, out] for the CSR route
+        self._ver = -1
+        # saved for backward
+        self.x = self.y16 = self.y32 = self.a32 = self.mi = None
+
+    def refresh(self, need_wt32: bool):
+        w = self.linear.weight
+        if self.w16 is None or self.w16.device != w.device:
+            self.w16 = torch.zeros((self.out_f, ops.pad8(self.in_f)), dtype=BF16, device=w.device)
+            self._ver = -1
+        if w._version != self._ver:
+            ops.cast_bf16(w.detach(), self.w16)
+            self._ver = w._version
+        if need_wt32:  # refreshed every forward: the fused optimizer only maintains the bf16 shadow
+            if self.wt32 is None or self.wt32.device != w.device:
+                self.wt32 = torch.empty((self.in_f, self.out_f), dtype=F32, device=w.device)
+            ops.transpose_f32(w.detach(), self.wt32)
+
+
+def build_stages(poly: PolyLinear, trailing_bn: Optional[nn.BatchNorm1d] = None):
+    stages = []
+    for kind, arg in poly.spec:
+        if kind == "linear":
+            stages.append(LinearStage(poly.layers[arg]))
+        elif kind == "bn":
+            assert stages[-1].bn is None
+            stages[-1].bn = poly.layers[arg]
+        else:
+            st = stages[-1]
+            if st.bn is None:
+                assert st.act1 is None
+                st.act1 = arg
+            else:
+                assert st.act2 is None
+                st.act2 = arg
+    if trailing_bn is not None:
+        assert stages[-1].bn is None
+        stages[-1].bn = trailing_bn
+    return stages
+
+
+class ZeroArena:
+    """small accumulators of one step (BN sums, loss sums, ...) carved out of one buffer cleared by one memset"""
+
+    def __init__(self, device, nbytes: int = 1 << 20):
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, n: int, dtype=F32) -> torch.Tensor:
+        size = torch.empty((), dtype=dtype).element_size() * n
+        start = (self.off + 15) // 16 * 16
+        if start + size > self.buf.numel():
+            raise RuntimeError("ZeroArena exhausted")
+        self.off = start + size
+        return self.buf[start:start + size].view(dtype)
+
+
+class Chain:
+    """A stack of LinearStages.  forward: bf16 rows (or a CSR feature) -> fp32 output; backward: hand-written."""
+
+    def __init__(self, stages, feature: Optional[DeviceFeature] = None):
+        self.stages = stages
+        self.feature = feature  # first-stage input when the chain projects a feature table
+        self.rows = 0
+
+    @property
+    def csr_input(self):
+        return self.feature is not None and self.feature.kind == "csr"
+
+    def forward(self, x16, rows, training, arena: ZeroArena, keep_for_backward=True, out32=None):
+        dev = self.stages[0].linear.weight.device
+        self.rows = rows
+        last = len(self.stages) - 1
+        for si, st in enumerate(self.stages):
+            final = si == last
+            first_csr = si == 0 and self.csr_input
+            st.refresh(first_csr)
+            bias = st.linear.bias.detach() if st.linear.bias is not None else None
+            out_pad = ops.pad8(st.out_f)
+            y16 = y32 = a32 = mi = None
+            if st.bn is None:
+                if final or first_csr:
+                    y32 = out32 if (final and out32 is not None) else torch.empty((rows, st.out_f), dtype=F32,
+                                                                                  device=dev)
+                if not final:
+                    y16 = torch.empty((rows, out_pad), dtype=BF16, device=dev)
+                if first_csr:
+                    ip, ix = self.feature.csr
+                    ops.spmm_csr(ip, ix, rows, st.wt32, st.out_f, bias, st.act1, y32)
+                    if y16 is not None:
+                        ops.cast_bf16(y32, y16)
+                else:
+                    ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_bf16=y16, out_f32=y32)
+            else:
+                bn = st.bn
+                a32 = torch.empty((rows, st.out_f), dtype=F32, device=dev)
+                mi = torch.empty(2 * st.out_f, dtype=F32, device=dev)
+                stats = arena.take(2 * st.out_f) if training else None
+                if first_csr:
+                    raise NotImplementedError("BatchNorm directly on a sparse feature projection")
+                ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_f32=a32, colstats=stats)
+                if training:
+                    ops.bn_finalize(stats, rows, st.out_f, mi, bn.running_mean, bn.running_var,
+                                    bn.num_batches_tracked, eps=bn.eps, momentum=bn.momentum)
+                else:
+                    ops.bn_eval_coeffs(bn.running_mean, bn.running_var, st.out_f, mi, eps=bn.eps)
+                if final:
+                    y32 = out32 if out32 is not None else torch.empty((rows, st.out_f), dtype=F32, device=dev)
+                else:
+                    y16 = torch.empty((rows, out_pad), dtype=BF16, device=dev)
+                ops.bn_apply(a32, mi, bn.weight.detach(), bn.bias.detach(), st.act2, rows, st.out_f, out_bf16=y16,
+                             out_f32=y32)
+            if keep_for_backward:
+                st.x, st.y16, st.y32, st.a32, st.mi = x16, y16, y32, a32, mi
+            x16 = y16
+        return y32
+
+    def backward(self, dy32, grads: Dict[int, torch.Tensor], need_dx: bool, arena: ZeroArena, zero_dy=False):
+        """dy32: fp32 [rows, out] gradient w.r.t. the chain output.  Accumulates parameter gradients into
+        ``grads[id(param)]``; returns fp32 [rows, in] gradient w.r.t. the chain input if ``need_dx``."""
+        rows = self.rows
+        dev = dy32.device
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        fused = None  # (dz16, dz32) of the current stage when the following stage's dgrad produced it
+        for si in reversed(range(len(self.stages))):
+            st = self.stages[si]
+            first_csr = si == 0 and self.csr_input
+            out_pad = ops.pad8(st.out_f)
+            g_w = grads[id(st.linear.weight)]
+            g_b = grads[id(st.linear.bias)] if st.linear.bias is not None else None
+            if fused is not None:
+                dz16, dz32 = fused
+                fused = None
+            else:
+                y = st.y32 if st.y32 is not None else st.y16
+                dz16 = None if first_csr else torch.empty((rows, out_pad), dtype=BF16, device=dev)
+                dz32 = torch.empty((rows, st.out_f), dtype=F32, device=dev) if first_csr else None
+                if st.bn is None:
+                    ops.actgrad_colsum(dy32, y, st.act1, rows, st.out_f, out_bf16=dz16, out_f32=dz32, colsum=g_b,
+                                       zero_dy=zero_dy)
+                else:
+                    bn = st.bn
+                    sums = arena.take(2 * st.out_f)
+                    ops.bn_bwd_reduce(dy32, y, st.act2, st.a32, st.mi, rows, st.out_f, sums)
+                    g_gamma, g_beta = grads[id(bn.weight)], grads[id(bn.bias)]
+                    if st.act1 is None:
+                        # the Linear bias in front of a BatchNorm has an exactly-zero gradient: not computed
+                        ops.bn_bwd_apply(dy32, y, st.act2, st.a32, st.mi, bn.weight.detach(), sums, rows, st.out_f,
+                                         dz_bf16=dz16, dgamma=g_gamma, dbeta=g_beta)
+                    else:
+                        da32 = torch.empty((rows, st.out_f), dtype=F32, device=dev)
+                        ops.bn_bwd_apply(dy32, y, st.act2, st.a32, st.mi, bn.weight.detach(), sums, rows, st.out_f,
+                                         dz_f32=da32, dgamma=g_gamma, dbeta=g_beta)
+                        ops.actgrad_colsum(da32, st.a32, st.act1, rows, st.out_f, out_bf16=dz16, colsum=g_b)
+            # ---- wgrad: dW[out, in] += dz^T x   (contraction over the rows)
+            if first_csr:
+                ip_t, ix_t = self.feature.csr_t
+                ops.spmm_csr(ip_t, ix_t, st.in_f, dz32, st.out_f, None, None, g_w, transpose_out=True)
+            else:
+                x16 = st.x if si > 0 or self.feature is None else self.feature.x16
+                tiles = -(-st.in_f // 128) * -(-st.out_f // (64 if st.out_f <= 64 else 128 if st.out_f <= 128 else 256))
+                split = max(1, min(-(-rows // 64), (2 * n_sms) // max(1, tiles)))
+                ops.gemm(x16, dz16, st.in_f, st.out_f, rows, a_mn=True, b_mn=True, out_f32=g_w, transpose_out=True,
+                         atomic_out=True, split_k=split)
+            # ---- dgrad
+            if si > 0:
+                prev = self.stages[si - 1]
+                if prev.bn is None:
+                    prev_csr = si - 1 == 0 and self.csr_input
+                    p16 = None if prev_csr else torch.empty((rows, ops.pad8(st.in_f)), dtype=BF16, device=dev)
+                    p32 = torch.empty((rows, st.in_f), dtype=F32, device=dev) if prev_csr else None
+                    g_pb = grads[id(prev.linear.bias)] if prev.linear.bias is not None else None
+                    ops.gemm(dz16, st.w16, rows, st.in_f, st.out_f, b_mn=True, out_bf16=p16, out_f32=p32,
+                             actgrad_y=prev.y16, actgrad_act=prev.act1, colstats=g_pb, colstats_sum_only=True)
+                    fused = (p16, p32)
+                else:
+                    dy32 = torch.empty((rows, st.in_f), dtype=F32, device=dev)
+                    ops.gemm(dz16, st.w16, rows, st.in_f, st.out_f, b_mn=True, out_f32=dy32)
+                    zero_dy = False
+            elif need_dx:
+                dx32 = torch.empty((rows, st.in_f), dtype=F32, device=dev)
+                ops.gemm(dz16, st.w16, rows, st.in_f, st.out_f, b_mn=True, out_f32=dx32)
+                return dx32
+        return None
+
+    def release(self):
+        for st in self.stages:
+            st.x = st.y16 = st.y32 = st.a32 = st.mi = None
+
+
+# ================================================================================================ FeatureEmbedding
+class FeatureEmbedding(nn.Module):
+    """Parameters of one modality (reference ``FeatureEmbedding``, sgd_alg.py:1279-1396): ``pre_embedding_layers``
+    (PolyLinear with the activation also on its output) for vector-like features, ``embedding_layer``
+    (nn.Embedding / nn.EmbeddingBag(mean, padding_idx=-1)) for categorical / tag features."""
+
+    def __init__(self, feature, embedding_dim: int = None, pre_embedding_layers=None, post_embedding_layers=None,
+                 activation_fn: str = "relu"):
+        super().__init__()
+        self._feature = feature
+        self._feature_type = feature_type(feature)
+        name = feature.feature_definition.name
+        if embedding_dim is None and self._feature_type in ("categorical", "tag"):
+            raise ValueError(f'For {self._feature_type} feature "{name}", the size of its embeddings have to be '
+                             f'specified with "embedding_dim"')
+        if pre_embedding_layers and self._feature_type in ("categorical", "tag"):
+            raise ValueError(f'For {self._feature_type} feature "{name}", using pre-embedding layers would not make '
+                             f'any sense (as the input are simple indices).')
+        self.pre_embedding_layers = None
+        self.embedding_layer = None
+        self.post_embedding_layers = None
+        self.output_dim = embedding_dim
+        if self._feature_type == "categorical":
+            self.embedding_layer = nn.Embedding(feature.n_unique_categories, embedding_dim)
+            nn.init.normal_(self.embedding_layer.weight, std=.1 / embedding_dim)  # train/utils.py:11-13
+        elif self._feature_type == "tag":
+            # default torch init (general_weight_init skips EmbeddingBag), last row = padding
+            self.embedding_layer = nn.EmbeddingBag(feature.dim + 1, embedding_dim, padding_idx=-1)
+        else:
+            dim = feature.dim if not isinstance(feature.dim, tuple) else int(np.prod(feature.dim))
+            cfg = [int(dim)] + list(pre_embedding_layers or []) + ([embedding_dim] if embedding_dim is not None else [])
+            self.output_dim = cfg[-1]
+            if len(cfg) > 1:
+                self.pre_embedding_layers = PolyLinear(cfg, activation_fn=activation_fn, output_fn=activation_fn)
+                for m in self.pre_embedding_layers.layers.values():
+                    _kaiming_relu_(m)
+        if post_embedding_layers:
+            cfg = [self.output_dim] + list(post_embedding_layers)
+            self.output_dim = cfg[-1]
+            self.post_embedding_layers = PolyLinear(cfg, activation_fn=activation_fn, output_fn=activation_fn)
+            for m in self.post_embedding_layers.layers.values():
+                _kaiming_relu_(m)
+
+    @classmethod
+    def build_from_conf(cls, config: FeatureModuleConfig, feature):
+        return cls(feature, embedding_dim=config.embedding_dim, pre_embedding_layers=config.pre_embedding_layers,
+                   post_embedding_layers=config.post_embedding_layers, activation_fn=config.activation_fn)
+
+    def forward(self, *a, **k):
+        raise RuntimeError("FeatureEmbedding is a parameter container; arithmetic runs in the sibrar_b200 kernels")
+
+
+# ================================================================================================ entity engines
+class _EntityBase(nn.Module):
+    """shared device-side plumbing of the two entity kinds"""
+
+    def _init_runtime(self, n_entities: int):
+        self.n_entities = n_entities
+        self._dev_ready = None
+        self._owner = None  # set by SingleBranchNet: access to step counter / arena / grads
+
+    def _device(self):
+        return next(iter(self.parameters())).device
+
+    def _rt(self):
+        if self._owner is None:
+            raise RuntimeError("entity module used outside of a SingleBranchNet")
+        return self._owner()
+
+
+class PlainEntity(_EntityBase):
+    """Entity that is a single FeatureEmbedding (reference: ``FeatureEmbedding`` used directly as
+    ``{user,item}_embedding_module`` when the config parses as FeatureModuleConfig, sgd_alg.py:2043-2046)."""
+
+    def __init__(self, feature, config: FeatureModuleConfig, n_entities: int):
+        nn.Module.__init__(self)
+        fe = FeatureEmbedding.build_from_conf(config, feature)
+        if fe._feature_type != "categorical" or fe.post_embedding_layers is not None:
+            raise NotImplementedError("plain (non single-branch) entities are supported for categorical features "
+                                      "(ID embeddings) only on the B200 path")
+        # flatten: the reference's state_dict keys are '<entity>_embedding_module.embedding_layer.weight'
+        self.embedding_layer = fe.embedding_layer
+        self.pre_embedding_layers = None
+        self.post_embedding_layers = None
+        self._feature = feature
+        self.output_dim = fe.output_dim
+        self.k_train = self.k_eval = 1
+        self.agg_max = 0
+        self.reg_enabled = False
+        self._init_runtime(n_entities)
+
+    def _materialize(self):
+        dev = self._device()
+        if self._dev_ready == dev:
+            return
+        self.df = DeviceFeature("plain", self._feature, self.n_entities, dev)
+        self._dev_ready = dev
+        self._srcs = self._srcs_grad = None
+
+    def _src_blob(self, grads):
+        w = self.embedding_layer.weight
+        g = grads[id(w)] if grads is not None else None
+        return ops.make_modality_srcs([dict(kind=SRC_CATEGORICAL, remap=self.df.remap, table=w.detach(), grad=g,
+                                            codes=self.df.codes)], w.device)
+
+    def embed(self, idx, training, mods=None, keep_mask=None):
+        self._materialize()
+        rt = self._rt()
+        flat = idx.reshape(-1).contiguous()
+        D = self.output_dim
+        out = torch.empty((flat.numel(), D), dtype=F32, device=flat.device)
+        if self._srcs is None:
+            self._srcs = self._src_blob(None)
+        ops.row_gather_fwd(self._srcs, 1, flat, None, 1, D, False, 0.0, 0, rt.step_dev, None, out_f32=out,
+                           err_flag=rt.err_flag)
+        self._ctx = (flat,)
+        return out
+
+    def backward(self, dE, grads):
+        rt = self._rt()
+        (flat,) = self._ctx
+        if self._srcs_grad is None or self._srcs_grad[0] is not grads:
+            self._srcs_grad = (grads, self._src_blob(grads))
+        ops.row_gather_bwd(self._srcs_grad[1], 1, flat, None, 1, self.output_dim, False, 0.0, 0, rt.step_dev, None, dE)
+
+
+class SingleBranchNetEntity(_EntityBase):
+    """reference ``SingleBranchNetEntity`` (sgd_alg.py:1764-2006)"""
+
+    def __init__(self, entity_name: str, features: dict, entity_config: SingleBranchNetEntityConfig,
+                 shared_common_dim: int, val_interactions_available: bool = True, n_entities: int = None):
+        nn.Module.__init__(self)
+        self.features = features
+        self.entity_name = entity_name
+        self.entity_config = entity_config
+        self.output_dim = shared_common_dim
+        self.val_interactions_available = val_interactions_available
+        cfg = entity_config
+        if len(cfg.features) == 0:
+            raise ValueError("SingleBranchEntity requires at least one feature.")
+        self.train_modalities = self._get_modalities(train=True)
+        self.eval_modalities = self._get_modalities(train=False)
+        missing = self.train_modalities - set(features.keys())
+        if missing:
+            raise ValueError(f"Features for modalities {missing} are not available!")
+        missing = self.train_modalities - {f.feature_name for f in cfg.features}
+        if missing:
+            raise ValueError(f"Network definitions for modalities {missing} are not available!")
+        if cfg.aggregation_fn not in ("mean", "max"):
+            raise ValueError(f'Aggregation function "{cfg.aggregation_fn}" is not supported.')
+        if not isinstance(cfg.embedding_regularization_type, EmbeddingRegularizationType):
+            raise ValueError(f'Embedding regularization "{cfg.embedding_regularization_type}" is not yet supported.')
+
+        self.modality_modules = nn.ModuleDict()
+        for f in cfg.features:
+            if f.feature_name not in self.train_modalities:
+                continue
+            self.modality_modules[f.feature_name] = FeatureEmbedding(
+                features[f.feature_name], embedding_dim=cfg.common_modality_dim,
+                pre_embedding_layers=f.feature_hidden_layers, activation_fn=cfg.activation_fn)
+        self.mod_names = list(self.modality_modules.keys())  # canonical modality ids of this entity
+
+        layers = []
+        if cfg.single_branch_input_dropout is not None:
+            layers.append(_Identity())  # nn.Dropout in the reference: no parameters, shifts the numbering
+        every = cfg.apply_batch_norm_every if cfg.apply_batch_normalization else 0
+        poly = PolyLinear([cfg.common_modality_dim] + list(cfg.single_branch_hidden_layers) + [self.output_dim],
+                          activation_fn=cfg.activation_fn,
+                          output_fn=cfg.activation_fn if cfg.apply_output_activation else None,
+                          apply_batch_norm_every=every)
+        layers.append(poly)
+        trailing_bn = None
+        if cfg.apply_batch_normalization and cfg.apply_batch_norm_every == 0:
+            trailing_bn = nn.BatchNorm1d(self.output_dim)
+            layers.append(trailing_bn)
+        self.sb_net = nn.Sequential(*layers)
+        # plain references (not registered a second time as sub-modules)
+        object.__setattr__(self, "_poly", poly)
+        object.__setattr__(self, "_trailing_bn", trailing_bn)
+
+        self.reg_type = cfg.embedding_regularization_type
+        self.reg_enabled = self.reg_type != EmbeddingRegularizationType.NoRegularization
+        if self.reg_type == EmbeddingRegularizationType.CentralModality and \
+                cfg.central_modality not in self.train_modalities:
+            raise ValueError(f'central item "{cfg.central_modality}" must be contained in "a"')
+        if self.reg_enabled and len(self.mod_names) < 2:
+            raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+        self.k_train = 2 if self.reg_enabled else 1
+        self.k_eval = len(self.eval_modalities)
+        self.agg_max = 1 if cfg.aggregation_fn == "max" else 0
+        self.regularization_loss = None
+        self._init_runtime(n_entities)
+
+    # ---- modality sets (sgd_alg.py:1879-1902)
+    def _get_modalities(self, train=True):
+        cfg = self.entity_config
+        available = {f.feature_name for f in cfg.features}
+        if train:
+            mods = set(cfg.train_modalities or available)
+        else:
+            train_mods = self._get_modalities(train=True)
+            if cfg.eval_modalities is not None:
+                for m in cfg.eval_modalities:
+                    if m not in train_mods:
+                        raise ValueError(f'Cannot use modality "{m}" during evaluation, if it is not used during '
+                                         f'training.')
+            mods = set(cfg.eval_modalities or train_mods)
+            if not self.val_interactions_available:
+                mods.discard("interactions")
+        if len(mods) == 0:
+            raise ValueError(f'No single modality is available during {"training" if train else "evaluation"}: '
+                             f'There are either no modalities specified or no interactions are available)')
+        return mods
+
+    # ---- device state
+    def _materialize(self):
+        dev = self._device()
+        if self._dev_ready == dev:
+            return
+        cfg = self.entity_config
+        self.dfeat, self.proj = {}, {}
+        for name, fe in self.modality_modules.items():
+            df = DeviceFeature(name, self.features[name], self.n_entities, dev,
+                               dense_min_density=float(os.environ.get("SBR_DENSE_MIN_DENSITY", 0.004)))
+            self.dfeat[name] = df
+            if fe.pre_embedding_layers is not None:
+                self.proj[name] = Chain(build_stages(fe.pre_embedding_layers), feature=df)
+        self.sb_chain = Chain(build_stages(self._poly, self._trailing_bn))
+        # fp32 [n_rows, C] projected modality tables at stable addresses (the gather descriptors point at them)
+        self.tables = {n: torch.zeros((self.dfeat[n].n_rows, cfg.common_modality_dim), dtype=F32, device=dev)
+                       for n in self.proj}
+        self.table_grads = {n: torch.zeros((self.dfeat[n].n_rows, cfg.common_modality_dim), dtype=F32, device=dev)
+                            for n in self.proj}
+        self._srcs_cache = {}
+        self._eval_ids = torch.tensor([self.mod_names.index(m) for m in sorted(self.eval_modalities)],
+                                      dtype=torch.uint8, device=dev)
+        self._dev_ready = dev
+
+    def _src_blob(self, grads):
+        key = id(grads) if grads is not None else 0
+        hit = self._srcs_cache.get(key)
+        if hit is not None and hit[0] is grads:
+            return hit[1]
+        entries = []
+        for name in self.mod_names:
+            df, fe = self.dfeat[name], self.modality_modules[name]
+            if name in self.proj:
+                entries.append(dict(kind=SRC_TABLE, remap=df.remap, table=self.tables[name],
+                                    grad=self.table_grads[name] if grads is not None else None))
+            else:
+                w = fe.embedding_layer.weight
+                g = grads[id(w)] if grads is not None else None
+                kind = SRC_CATEGORICAL if df.kind == "categorical" else SRC_TAG
+                entries.append(dict(kind=kind, remap=df.remap, table=w.detach(), grad=g, codes=df.codes,
+                                    max_tags=df.max_tags, pad_id=df.pad_id))
+        blob = ops.make_modality_srcs(entries, self._device())
+        self._srcs_cache[key] = (grads, blob, entries)
+        return blob
+
+    def _project_tables(self, names, training, arena):
+        """entity-table projection: T_m = PolyLinear_m(X_m) for ALL rows of every listed modality"""
+        for name in names:
+            if name not in self.proj:
+                continue
+            df, chain = self.dfeat[name], self.proj[name]
+            chain.forward(df.x16, df.n_rows, training, arena, keep_for_backward=training, out32=self.tables[name])
+
+    def sample_modalities(self, n_idx: int):
+        """device replacement of ``_sample_modalities`` (sgd_alg.py:1904-1927) for training"""
+        rt = self._rt()
+        k = self.k_train
+        mods = torch.empty(n_idx * k, dtype=torch.uint8, device=self._device())
+        central = -1
+        if self.reg_type == EmbeddingRegularizationType.CentralModality:
+            central = self.mod_names.index(self.entity_config.central_modality)
+        seed = (int(self.entity_config.sampling_seed) << 8) ^ (1 if self.entity_name == "user" else 2)
+        ops.sample_modalities(mods, n_idx, k, len(self.mod_names), central, seed, rt.step_dev)
+        return mods
+
+    def embed(self, idx, training, mods=None, keep_mask=None):
+        """indices [...] -> per-slot embeddings fp32 [N = numel * k, D] (``_embed``, sgd_alg.py:1865-1877)"""
+        self._materialize()
+        rt = self._rt()
+        cfg = self.entity_config
+        dev = self._device()
+        flat = idx.reshape(-1).contiguous()
+        n_idx = flat.numel()
+        if training:
+            k = self.k_train
+            if mods is None:
+                mods = self.sample_modalities(n_idx)
+            used = self.mod_names
+        else:
+            k = self.k_eval
+            mods = self._eval_ids.repeat(n_idx)
+            used = sorted(self.eval_modalities)
+        self._project_tables(used, training, rt.arena)
+        srcs = self._src_blob(None)
+        C_ = cfg.common_modality_dim
+        N = n_idx * k
+        x0 = torch.empty((N, ops.pad8(C_)), dtype=BF16, device=dev)
+        p_drop = cfg.single_branch_input_dropout if (training and cfg.single_branch_input_dropout) else 0.0
+        seed = (int(cfg.sampling_seed) << 8) ^ (0x11 if self.entity_name == "user" else 0x22)
+        ops.row_gather_fwd(srcs, len(self.mod_names), flat, mods, k, C_, cfg.normalize_single_branch_input, p_drop,
+                           seed, rt.step_dev, keep_mask, out_bf16=x0, err_flag=rt.err_flag)
+        E = self.sb_chain.forward(x0, N, training, rt.arena, keep_for_backward=training)
+        self._ctx = (flat, mods, keep_mask, k, p_drop, seed)
+        return E
+
+    def backward(self, dE, grads):
+        rt = self._rt()
+        cfg = self.entity_config
+        flat, mods, keep_mask, k, p_drop, seed = self._ctx
+        C_ = cfg.common_modality_dim
+        dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena)
+        srcs = self._src_blob(grads)
+        ops.row_gather_bwd(srcs, len(self.mod_names), flat, mods, k, C_, cfg.normalize_single_branch_input, p_drop,
+                           seed, rt.step_dev, keep_mask, dx0)
+        for name, chain in self.proj.items():
+            # table-level backward; the accumulator table is cleared by the kernel that consumes it
+            chain.backward(self.table_grads[name], grads, need_dx=False, arena=rt.arena, zero_dy=True)
+
+    def get_and_reset_other_loss(self) -> Dict:
+        loss = self.regularization_loss
+        if loss is None:
+            loss = torch.zeros(1, device=self._device())
+        self.regularization_loss = None
+        return {"reg_loss": loss * self.entity_config.regularization_weight}
+
+
+# ================================================================================================ the model
+class _Runtime:
+    def __init__(self, device):
+        self.device = device
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.arena = ZeroArena(device)
+
+
+class SingleBranchNet(nn.Module):
+    """drop-in for the reference ``SingleBranchNet``"""
+
+    def __init__(self, config: SingleBranchNetConfig, dataset):
+        super().__init__()
+        self.name = self.__class__
+        from .synthetic import SynFeature  # light Feature-like container (no arithmetic)
+        user_features = dataset.user_features
+        user_features["interactions"] = SynFeature("interactions", "vector", dataset.user_sampling_matrix_train)
+        user_features["user_embedding"] = SynFeature("user_embedding", "categorical", np.arange(dataset.n_users))
+        item_features = dataset.item_features
+        item_features["interactions"] = SynFeature("interactions", "vector", dataset.item_sampling_matrix_train)
+        item_features["item_embedding"] = SynFeature("item_embedding", "categorical", np.arange(dataset.n_items))
+        self.config = config
+        self.n_users, self.n_items = dataset.n_users, dataset.n_items
+        self.is_user_sb_module = config.is_user_sb_module
+        self.is_item_sb_module = config.is_item_sb_module
+        D = config.shared_common_dim
+        self.user_embedding_module = self._build_entity("user", config.user, user_features, D,
+                                                        not dataset.is_cold_start_user, dataset.n_users)
+        self.item_embedding_module = self._build_entity("item", config.item, item_features, D,
+                                                        not dataset.is_cold_start_item, dataset.n_items)
+        self._runtime = None
+        import weakref
+        ref = weakref.ref(self)
+        for ent in (self.user_embedding_module, self.item_embedding_module):
+            ent._owner = lambda r=ref: r()._rt()
+
+    @staticmethod
+    def _build_entity(name, conf, features, D, interactions_available, n_entities):
+        if isinstance(conf, SingleBranchNetEntityConfig):
+            return SingleBranchNetEntity(name, features, conf, D, interactions_available, n_entities)
+        if conf.embedding_dim == -1:
+            conf.embedding_dim = D
+        return PlainEntity(features[conf.feature_name], conf, n_entities)
+
+    @staticmethod
+    def build_from_conf(conf: dict, dataset):
+        return SingleBranchNet(SingleBranchNetConfig.from_dict(conf), dataset)
+
+    # ---- runtime
+    @property
+    def device(self):
+        return next(iter(self.parameters())).device
+
+    def _rt(self) -> _Runtime:
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("sibrar_b200.SingleBranchNet runs on a CUDA device (sm_100a) only -- there is no CPU "
+                               "fallback; move the model with .to('cuda')")
+        if self._runtime is None or self._runtime.device != dev:
+            self._runtime = _Runtime(dev)
+        return self._runtime
+
+    def check_errors(self):
+        """raises KeyError like ``Feature.__getitem__`` (data/Feature.py:146) if a kernel met an entity index
+        without a feature row (host sync: call outside the hot loop)"""
+        if self._runtime is not None and int(self._runtime.err_flag.item()) != 0:
+            self._runtime.err_flag.zero_()
+            raise KeyError("an entity index without a feature row was requested")
+
+    # ---- reference API (inference / no-grad use; training goes through sibrar_b200.trainer.FusedTrainer)
+    def _represent(self, ent, idx):
+        training = self.training
+        if training and torch.is_grad_enabled():
+            from .autograd import entity_forward_with_grad
+            return entity_forward_with_grad(self, ent, idx)
+        rt = self._rt()
+        rt.arena.reset()
+        E = ent.embed(idx, training)
+        k = ent.k_train if training else ent.k_eval
+        D = self.config.shared_common_dim
+        if k == 1:
+            return E.view(*idx.shape, D)
+        out = torch.empty((idx.numel(), D), dtype=F32, device=E.device)
+        ops.aggregate(E, idx.numel(), k, D, ent.agg_max, out_f32=out)
+        return out.view(*idx.shape, D)
+
+    def get_user_representations(self, u_idxs: torch.Tensor):
+        return self._represent(self.user_embedding_module, u_idxs)
+
+    def get_item_representations(self, i_idxs: torch.Tensor):
+        return self._represent(self.item_embedding_module, i_idxs)
+
+    def combine_user_item_representations(self, u_repr, i_repr):
+        from .autograd import combine
+        return combine(u_repr, i_repr)
+
+    def forward(self, u_idxs, i_idxs):
+        u_repr = self.get_user_representations(u_idxs)
+        i_repr = self.get_item_representations(i_idxs)
+        return self.combine_user_item_representations(u_repr, i_repr)
+
+    @torch.no_grad()
+    def predict(self, u_idxs, i_idxs):
+        self.eval()
+        return self(u_idxs, i_idxs)
+
+    def get_and_reset_other_loss(self) -> Dict:
+        losses = {"reg_loss": torch.zeros(1, device=self.device)}
+        for name, ent, sb in (("user", self.user_embedding_module, self.is_user_sb_module),
+                              ("item", self.item_embedding_module, self.is_item_sb_module)):
+            if sb:
+                r = ent.get_and_reset_other_loss()
+                losses["reg_loss"] = losses["reg_loss"] + r["reg_loss"]
+                losses.update({f"{name}_{k}": v for k, v in r.items()})
+        return losses
+
+    def save_model_to_path(self, path: str):
+        torch.save(self.state_dict(), os.path.join(path, "model.pth"))
+        print("Model Saved")
+
+    def load_model_from_path(self, path: str):
+        self.load_state_dict(torch.load(os.path.join(path, "model.pth"), map_location=self.device))
+        print("Model Loaded")

@@ -1,0 +1,118 @@
+"""Fused training step: the body of the reference's ``Trainer._train`` loop (``train/trainer.py:204-223``: forward,
+rec loss, reg losses, backward, optimizer step, zero_grad) as one stream of hand-written kernels with no host
+synchronisation -- the reference syncs >= 3 times per step through ``.item()`` (``train/trainer.py:217-219``).
+
+Losses are accumulated on the device (fp64) and read on demand; the optimizer is the multi-tensor Adam/AdamW kernel
+(``torch.optim.Adam`` / ``AdamW`` semantics, selected like ``train/trainer.py:62-68``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .config import LearningConfig
+from .sbnet import SingleBranchNet, SingleBranchNetEntity
+
+F32 = torch.float32
+
+
+class FusedTrainer:
+    def __init__(self, model: SingleBranchNet, learn, n_negative_samples: int,
+                 negative_sampling_strategy: str = "uniform_recbole", betas=(0.9, 0.999), eps: float = 1e-8,
+                 grad_scale: float = 1.0):
+        if isinstance(learn, dict):
+            learn = LearningConfig.from_dict(learn)
+        if learn.optimizer not in ("adam", "adamw"):
+            raise ValueError(f'optimizer "{learn.optimizer}" is not available on the B200 path (adam | adamw)')
+        if learn.rec_loss not in ("bpr", "bce", "sampled_softmax"):
+            raise KeyError(learn.rec_loss)
+        assert learn.loss_aggregator in ("mean", "sum"), "Type of Aggregator not yet defined"
+        assert negative_sampling_strategy in ("uniform", "uniform_recbole"), \
+            "Type of Negative Strategy not currently supported"
+        self.model, self.learn = model, learn
+        self.n_neg = n_negative_samples
+        self.betas, self.eps, self.grad_scale = betas, eps, grad_scale
+        self.ssm_shift = 0.0
+        if learn.rec_loss == "sampled_softmax" and negative_sampling_strategy == "uniform":
+            self.ssm_shift = math.log(model.n_items / n_negative_samples)  # train/rec_losses.py:104-105
+        self.rt = model._rt()
+        dev = model.device
+        self.user, self.item = model.user_embedding_module, model.item_embedding_module
+        for ent in (self.user, self.item):
+            ent._materialize()
+        # persistent fp32 gradient accumulators (= p.grad), Adam moments, bf16 shadows maintained by the optimizer
+        self.grads: Dict[int, torch.Tensor] = {}
+        shadows = {}
+        for ent in (self.user, self.item):
+            if isinstance(ent, SingleBranchNetEntity):
+                for chain in list(ent.proj.values()) + [ent.sb_chain]:
+                    for st in chain.stages:
+                        st.refresh(False)
+                        shadows[id(st.linear.weight)] = st.w16
+        entries = []
+        for p in model.parameters():
+            g = torch.zeros_like(p, dtype=F32)
+            p.grad = g
+            self.grads[id(p)] = g
+            entries.append(dict(param=p.data, grad=g, exp_avg=torch.zeros_like(g), exp_avg_sq=torch.zeros_like(g),
+                                shadow=shadows.get(id(p))))
+        self.adam = ops.AdamPlan(entries, dev)
+        # [rec, user_reg, item_reg] sums since the last reset (fp64), + number of accumulated steps on the host
+        self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.steps_accumulated = 0
+        self.logits = None
+
+    # ------------------------------------------------------------------------------------------------ one step
+    def step(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor, mods: Optional[dict] = None,
+             keep_masks: Optional[dict] = None, apply_optimizer: bool = True):
+        """u_idxs int64 [B], i_idxs int64 [B, 1 + n_neg] on the device (positive item in column 0)."""
+        m, rt = self.model, self.rt
+        mods, keep_masks = mods or {}, keep_masks or {}
+        B, n = i_idxs.shape
+        D = m.config.shared_common_dim
+        ops.tick(rt.step_dev)
+        rt.arena.reset()
+        Eu = self.user.embed(u_idxs, True, mods.get("user"), keep_masks.get("user"))
+        Ei = self.item.embed(i_idxs, True, mods.get("item"), keep_masks.get("item"))
+        ku, ki = self.user.k_train, self.item.k_train
+        dEu, dEi = torch.empty_like(Eu), torch.empty_like(Ei)
+        if self.logits is None or self.logits.shape != (B, n):
+            self.logits = torch.empty((B, n), dtype=F32, device=Eu.device)
+        ops.score_loss(Eu, Ei, B, n, ku, ki, D, self.user.agg_max, self.item.agg_max, self.learn.rec_loss,
+                       self.learn.loss_aggregator == "sum", self.ssm_shift, self.logits, self.loss_acc[0:1], dEu, dEi)
+        if self.user.reg_enabled:
+            c = self.user.entity_config
+            ops.infonce(Eu, 1, B, D, c.regularization_temperature, c.regularization_weight, self.loss_acc[1:2], dEu, 1)
+        if self.item.reg_enabled:
+            c = self.item.entity_config
+            ops.infonce(Ei, B, n, D, c.regularization_temperature, c.regularization_weight, self.loss_acc[2:3], dEi, 1)
+        self.item.backward(dEi, self.grads)
+        self.user.backward(dEu, self.grads)
+        if apply_optimizer:
+            self.optimizer_step()
+        self.steps_accumulated += 1
+
+    def optimizer_step(self):
+        b1, b2 = self.betas
+        self.adam.step(self.learn.lr, b1, b2, self.eps, self.learn.wd, self.learn.optimizer == "adamw",
+                       self.rt.step_dev, self.grad_scale)
+
+    # ------------------------------------------------------------------------------------------------ logging
+    def read_losses(self, reset: bool = True) -> Dict[str, float]:
+        """host sync.  Mean per-step losses since the last reset, keyed like the reference's epoch dict
+        (``train/trainer.py:217-219,233``)."""
+        acc = self.loss_acc.cpu().tolist()
+        n = max(1, self.steps_accumulated)
+        out = {"train/rec_loss": acc[0] / n, "train/reg_loss": (acc[1] + acc[2]) / n,
+               "train/loss": (acc[0] + acc[1] + acc[2]) / n}
+        if self.model.is_user_sb_module:
+            out["train/user_reg_loss"] = acc[1] / n
+        if self.model.is_item_sb_module:
+            out["train/item_reg_loss"] = acc[2] / n
+        if reset:
+            self.loss_acc.zero_()
+            self.steps_accumulated = 0
+        return out

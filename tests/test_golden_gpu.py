@@ -1,0 +1,181 @@
+"""GPU parity of the B200 path against the fixtures produced by the UNMODIFIED reference (tests/golden/*.npz) and the
+numpy oracle: one fused train step (logits, losses, every gradient, BatchNorm running statistics), multi-step training
+with the fused AdamW, and full-catalog evaluation (representations, top-k, metrics).
+
+Tolerances (bf16 GEMM operands, fp32 accumulation; BASELINE.json: losses <= 1e-2 relative, fp32 scores <= 1e-3):
+  logits / representations : 2e-2 of the tensor's max-abs
+  losses                   : 1e-2 relative
+  gradients                : 4e-2 of the tensor's max-abs (+ fp32 noise floor of the whole step)
+  top-k at FIXED scores    : bit-exact positions wherever the oracle's ranking gap exceeds the fp32 round-off
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import sbnet_oracle as O  # noqa: E402
+from sibrar_b200 import ops  # noqa: E402
+from sibrar_b200.evaluator import FullEvaluator  # noqa: E402
+from sibrar_b200.sbnet import SingleBranchNet, SingleBranchNetEntity  # noqa: E402
+from sibrar_b200.trainer import FusedTrainer  # noqa: E402
+from tests.golden_util import CASES, load_case, state_dict_of, step_inputs  # noqa: E402
+
+DEV = "cuda"
+
+
+def _build(name):
+    spec, g, corpus = load_case(name)
+    model = SingleBranchNet.build_from_conf(spec["model"], corpus.dataset("train"))
+    return spec, g, corpus, model
+
+
+def _load(model, sd):
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+
+
+def _translate(model, g, s):
+    """fixture modality ids / dropout masks -> device tensors in this model's modality numbering"""
+    u, i, mods, names, drop = step_inputs(g, s)
+    dmods, dkeep = {}, {}
+    for ent_name, ent in (("user", model.user_embedding_module), ("item", model.item_embedding_module)):
+        if ent_name in mods and isinstance(ent, SingleBranchNetEntity):
+            lut = np.array([ent.mod_names.index(n) if n in ent.mod_names else 255 for n in names[ent_name]],
+                           dtype=np.uint8)
+            dmods[ent_name] = torch.from_numpy(lut[mods[ent_name]].reshape(-1)).to(DEV)
+            if ent_name in drop:
+                C_ = ent.entity_config.common_modality_dim
+                dkeep[ent_name] = torch.from_numpy(drop[ent_name].reshape(-1, C_).astype(np.uint8)).to(DEV)
+    return torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), dmods, dkeep
+
+
+def _maxrel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want).max() / max(1e-12, np.abs(want).max())
+
+
+def _trainer(model, spec):
+    return FusedTrainer(model, dict(lr=spec["lr"], wd=spec["wd"], optimizer=spec["optimizer"],
+                                    rec_loss=spec["rec_loss"], loss_aggregator="mean"),
+                        n_negative_samples=spec["n_neg"])
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_single_steps_match_reference(name):
+    spec, g, corpus, model = _build(name)
+    model.to(DEV).train()
+    tr = _trainer(model, spec)
+    for s in range(spec["steps"]):
+        _load(model, state_dict_of(g, "sd0/") if s == 0 else state_dict_of(g, f"s{s - 1}/sd/"))
+        u, i, mods, keep = _translate(model, g, s)
+        for gr in tr.grads.values():
+            gr.zero_()
+        tr.read_losses()
+        tr.step(u, i, mods, keep, apply_optimizer=False)
+        torch.cuda.synchronize()
+        model.check_errors()
+        assert _maxrel(tr.logits.cpu().numpy(), g[f"s{s}/logits"]) < 2e-2, f"s{s} logits"
+        losses = tr.read_losses()
+        assert losses["train/rec_loss"] == pytest.approx(float(g[f"s{s}/rec_loss"]), rel=1e-2, abs=1e-4)
+        assert losses["train/reg_loss"] == pytest.approx(float(g[f"s{s}/reg_loss"]), rel=1e-2, abs=1e-4)
+        assert losses["train/loss"] == pytest.approx(float(g[f"s{s}/loss"]), rel=1e-2, abs=1e-4)
+        gold = state_dict_of(g, f"s{s}/grad/")
+        gscale = max(float(np.abs(v).max()) for v in gold.values())
+        params = dict(model.named_parameters())
+        worst = {}
+        for k, gg in gold.items():
+            got = tr.grads[id(params[k])].cpu().numpy()
+            err = np.abs(got - gg).max()
+            tol = 4e-2 * np.abs(gg).max() + 2e-3 * gscale
+            worst[k] = (err, tol)
+        bad = {k: v for k, v in worst.items() if v[0] > v[1]}
+        assert not bad, f"s{s} gradients out of tolerance: {bad}"
+        # BatchNorm running statistics of this step
+        sd = model.state_dict()
+        for k, v in state_dict_of(g, f"s{s}/sd/").items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                assert np.abs(sd[k].cpu().numpy() - v).max() < 2e-2 * max(1.0, np.abs(v).max()), k
+            if k.endswith("num_batches_tracked"):
+                assert int(sd[k].item()) == int(v), k
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_training_trajectory(name):
+    """fused multi-step training from the reference's initial weights on the reference's batches: the loss curve
+    stays within 1e-2 (relative) and no parameter drifts further than Adam's step bound lr * n_steps * 2.5."""
+    spec, g, corpus, model = _build(name)
+    _load(model, state_dict_of(g, "sd0/"))
+    model.to(DEV).train()
+    tr = _trainer(model, spec)
+    for s in range(spec["steps"]):
+        u, i, mods, keep = _translate(model, g, s)
+        tr.step(u, i, mods, keep)
+        loss = tr.read_losses()["train/loss"]
+        assert loss == pytest.approx(float(g[f"s{s}/loss"]), rel=2e-2, abs=1e-3), f"step {s}"
+    sd = model.state_dict()
+    last = state_dict_of(g, f"s{spec['steps'] - 1}/sd/")
+    bound = spec["lr"] * spec["steps"] * 2.5
+    for k, v in last.items():
+        if v.dtype.kind != "f" or k.endswith("running_mean") or k.endswith("running_var"):
+            continue
+        assert np.abs(sd[k].cpu().numpy() - v).max() <= bound + 1e-6, k
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_eval_matches_reference(name):
+    spec, g, corpus, model = _build(name)
+    _load(model, state_dict_of(g, f"s{spec['steps'] - 1}/sd/"))
+    model.to(DEV).eval()
+    val = corpus.dataset("val")
+    with torch.no_grad():
+        i_repr = model.get_item_representations(torch.from_numpy(val.items_in_split).to(DEV))
+        u_repr = model.get_user_representations(torch.from_numpy(val.users_in_split).to(DEV))
+    assert model.training is False
+    assert _maxrel(i_repr.cpu().numpy(), g["eval/i_repr"]) < 2e-2
+    assert _maxrel(u_repr.cpu().numpy(), g["eval/u_repr"]) < 2e-2
+    logits = model.predict(torch.from_numpy(val.users_in_split[:5]).to(DEV),
+                           torch.from_numpy(np.tile(val.items_in_split[:7], (5, 1))).to(DEV))
+    want = g["eval/u_repr"][:5] @ g["eval/i_repr"][:7].T
+    assert _maxrel(logits.cpu().numpy(), want) < 3e-2
+    # end to end: metrics close to the reference's (ranks may swap inside the bf16 score error)
+    ev = FullEvaluator(dict(top_k=[1, 3, 5], metrics=["ndcg", "precision", "recall", "f_score", "hitrate",
+                                                      "coverage"], calculate_std=False))
+    res = ev.evaluate(model, val)
+    for k, v in state_dict_of(g, "eval/metric/").items():
+        assert res[k] == pytest.approx(float(v), abs=0.03), k
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_topk_and_metrics_at_fixed_scores(name):
+    """fixed (reference) representations rounded to bf16: positions bit-exact vs the oracle wherever the ranking gap
+    is above fp32 round-off, integer hit counts and metrics identical."""
+    spec, g, corpus, model = _build(name)
+    val = corpus.dataset("val")
+    u = torch.from_numpy(g["eval/u_repr"]).to(DEV)
+    it = torch.from_numpy(g["eval/i_repr"]).to(DEV)
+    u16, i16 = ops.cast_bf16(u), ops.cast_bf16(it)
+    ex = val.exclude_data[val.users_in_split]
+    ex.sort_indices()
+    seen = (torch.from_numpy(ex.indptr.astype(np.int64)).to(DEV), torch.from_numpy(ex.indices.astype(np.int32)).to(DEV))
+    k = 5
+    vals, idx = ops.topk_scores_masked(u16, i16, u.shape[0], it.shape[0], u16.shape[1],
+                                       seen[0] if ex.nnz else None, seen[1] if ex.nnz else None, k)
+    D = u.shape[1]
+    ov, oi = O.masked_topk(u16[:, :D].float().cpu().numpy(), i16[:, :D].float().cpu().numpy(), ex, k + 1)
+    gaps = np.abs(np.diff(ov, axis=1))
+    clear = (np.minimum(gaps[:, :k], np.concatenate([np.full((len(ov), 1), np.inf), gaps[:, :k - 1]], 1)) > 1e-5)
+    idx = idx.cpu().numpy()
+    assert clear.mean() > 0.8
+    assert (idx[clear] == oi[:, :k][clear]).all()
+    assert np.abs(vals.cpu().numpy() - ov[:, :k]).max() < 1e-5
+    # metrics on the oracle's own top-k: the metric kernel must agree with the restated definitions to fp32
+    tgt = val.user_sampling_matrix[val.users_in_split][:, val.items_in_split].tocsr()
+    tgt.sort_indices()
+    m, hits = ops.metrics_at_k(torch.from_numpy(oi[:, :k].astype(np.int32)).to(DEV),
+                               torch.from_numpy(tgt.indptr.astype(np.int64)).to(DEV),
+                               torch.from_numpy(tgt.indices.astype(np.int32)).to(DEV), [1, 3, 5], it.shape[0], True)
+    ref = O.metrics_at_k(oi[:, :k], tgt, [1, 3, 5], n_items=it.shape[0])
+    m = m.cpu().numpy()
+    for mi, mn in enumerate(["ndcg", "precision", "recall", "f_score", "hitrate"]):
+        for ki, kk in enumerate([1, 3, 5]):
+            assert np.abs(m[mi, ki] - ref[f"{mn}@{kk}"]).max() < 2e-6
