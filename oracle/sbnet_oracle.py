@@ -59,6 +59,27 @@ def act_bwd(name, y, dy):
     raise ValueError(name)
 
 
+# ------------------------------------------------------------------------------------------------ bf16 emulation
+def bf16_round(x):
+    """round-to-nearest-even to bfloat16, returned as float64 (what the kernels' bf16 stores do)"""
+    x32 = np.ascontiguousarray(np.asarray(x, np.float32))
+    u = x32.view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32).astype(F64)
+
+
+class Bf16Emulation:
+    """Mirrors the ROUNDING POINTS of the B200 path ('precision'): GEMM operands (weights, activations
+    between fused stages, dz) are bf16; accumulation, BatchNorm, normalisation, losses and every reduction are
+    fp32/fp64; the CSR ('sparse interactions') route is fp32 end to end.  With it the oracle predicts the kernels'
+    results to ~1e-3 instead of the ~1e-2 that separates bf16 from the fp32 reference."""
+
+    def __init__(self, csr_route=()):
+        self.csr_route = set(csr_route)  # prefixes of FeatureProj modules whose first layer runs as SpMM
+
+    q = staticmethod(bf16_round)
+
+
 # ------------------------------------------------------------------------------------------------ PolyLinear
 def poly_spec(layer_config, bn_every, activation, output_fn):
     """List of ops exactly in the order of ``modules/polylinear.py:50-71``."""
@@ -101,11 +122,17 @@ def bn_backward(dy, cache, grads, prefix):
     return (g / std) * (dy - dy.mean(0) - xhat * (dy * xhat).mean(0))
 
 
-def poly_forward(x, p, prefix, ops, training, new_stats=None):
+def poly_forward(x, p, prefix, ops, training, new_stats=None, emu=None, exact_first=False):
+    """emu: Bf16Emulation or None.  With emulation the input of every Linear and its weight are bf16-rounded (the
+    kernels store inter-stage activations as bf16); ``exact_first`` keeps the first Linear in fp32 (CSR route)."""
     caches = []
+    n_lin = 0
     for kind, arg in ops:
         if kind == "linear":
             W, b = p[f"{prefix}.{arg}.weight"].astype(F64), p[f"{prefix}.{arg}.bias"].astype(F64)
+            if emu is not None and not (exact_first and n_lin == 0):
+                x, W = emu.q(x), emu.q(W)
+            n_lin += 1
             caches.append(x)
             x = x @ W.T + b
         elif kind == "bn":
@@ -117,13 +144,17 @@ def poly_forward(x, p, prefix, ops, training, new_stats=None):
     return x, caches
 
 
-def poly_backward(dy, p, prefix, ops, caches, grads, need_dx=True):
+def poly_backward(dy, p, prefix, ops, caches, grads, need_dx=True, emu=None, exact_first=False):
+    n_lin = sum(1 for k, _ in ops if k == "linear")
     for (kind, arg), c in zip(reversed(ops), reversed(caches)):
         if kind == "linear":
+            n_lin -= 1
             W = p[f"{prefix}.{arg}.weight"].astype(F64)
             kw, kb = f"{prefix}.{arg}.weight", f"{prefix}.{arg}.bias"
+            grads[kb] = grads.get(kb, 0) + dy.sum(0)  # bias gradient: fp32 column sums before the bf16 store
+            if emu is not None and not (exact_first and n_lin == 0):
+                dy, W = emu.q(dy), emu.q(W)
             grads[kw] = grads.get(kw, 0) + dy.T @ c
-            grads[kb] = grads.get(kb, 0) + dy.sum(0)
             dy = dy @ W
         elif kind == "bn":
             dy = bn_backward(dy, c, grads, f"{prefix}.{arg}")
@@ -192,6 +223,22 @@ class FeatureProj:
         if self.post_ops is not None:
             y, cache["post"] = poly_forward(y, p, self.prefix + ".post_embedding_layers.layers", self.post_ops, True)
         return y, cache
+
+    # -- table mode (what the B200 path does): project ALL rows once, gather afterwards; the backward sums the
+    #    row gradients per feature row BEFORE the activation derivative / bf16 rounding of the wgrad operand
+    def table_forward(self, p, emu):
+        n = self.f.values.shape[0]
+        x = self.raw(np.arange(n)).astype(F64)
+        csr = emu is not None and self.prefix in emu.csr_route
+        y, cache = poly_forward(x, p, self.prefix + ".pre_embedding_layers.layers", self.pre_ops, True, emu=emu,
+                                exact_first=csr)
+        self._table_cache = (cache, csr)
+        return y
+
+    def table_backward(self, dT, p, grads, emu):
+        cache, csr = self._table_cache
+        poly_backward(dT, p, self.prefix + ".pre_embedding_layers.layers", self.pre_ops, cache, grads, emu=emu,
+                      exact_first=csr)
 
     def backward(self, dy, cache, p, grads):
         if self.post_ops is not None:
@@ -313,7 +360,7 @@ class Entity:
         self.temperature = conf.get("regularization_temperature", 1.)
         self.reg_weight = conf.get("regularization_weight", 1.)
 
-    def forward(self, idx, mods, mod_names, p, training, drop_keep=None, new_stats=None):
+    def forward(self, idx, mods, mod_names, p, training, drop_keep=None, new_stats=None, emu=None):
         """idx: int array [...]; mods: int ids [..., k] into mod_names."""
         shape = idx.shape
         k = mods.shape[-1]
@@ -321,10 +368,16 @@ class Entity:
         flat_mod = mods.reshape(-1)
         N = flat_idx.size
         X = np.zeros((N, self.C), F64)
-        c = {"shape": shape, "k": k, "proj": {}}
+        c = {"shape": shape, "k": k, "proj": {}, "emu": emu}
         for mid in np.unique(flat_mod):
             sel = np.nonzero(flat_mod == mid)[0]
-            y, pc = self.proj[str(mod_names[mid])].forward(flat_idx[sel], p)
+            fp = self.proj[str(mod_names[mid])]
+            if emu is not None and fp.pre_ops is not None:
+                rows = fp.rows(flat_idx[sel])
+                X[sel] = fp.table_forward(p, emu)[rows]
+                c["proj"][int(mid)] = (sel, {"table_rows": rows})
+                continue
+            y, pc = fp.forward(flat_idx[sel], p)
             X[sel] = y
             c["proj"][int(mid)] = (sel, pc)
         if self.normalize:
@@ -336,7 +389,7 @@ class Entity:
             scale = keep / (1. - self.p_drop)
             c["drop"] = scale
             X = X * scale
-        Z, c["sb"] = poly_forward(X, p, self.sb_prefix, self.sb_ops, training, new_stats)
+        Z, c["sb"] = poly_forward(X, p, self.sb_prefix, self.sb_ops, training, new_stats, emu=emu)
         if self.trailing_bn:
             Z, c["tbn"] = bn_forward(Z, p, self.trailing_bn, training, new_stats)
         E = Z.reshape(shape + (k, self.D))
@@ -366,14 +419,21 @@ class Entity:
         dZ = dE.reshape(-1, self.D)
         if self.trailing_bn:
             dZ = bn_backward(dZ, c["tbn"], grads, self.trailing_bn)
-        dX = poly_backward(dZ, p, self.sb_prefix, self.sb_ops, c["sb"], grads)
+        emu = c.get("emu")
+        dX = poly_backward(dZ, p, self.sb_prefix, self.sb_ops, c["sb"], grads, emu=emu)
         if "drop" in c:
             dX = dX * c["drop"]
         if self.normalize:
             y, nrm = c["norm"]
             dX = (dX - y * (y * dX).sum(1, keepdims=True)) / nrm
         for mid, (sel, pc) in c["proj"].items():
-            self.proj[str(mod_names[mid])].backward(dX[sel], pc, p, grads)
+            fp = self.proj[str(mod_names[mid])]
+            if "table_rows" in pc:
+                dT = np.zeros((fp.f.values.shape[0], self.C), F64)
+                np.add.at(dT, pc["table_rows"], dX[sel])
+                fp.table_backward(dT, p, grads, emu)
+            else:
+                fp.backward(dX[sel], pc, p, grads)
 
 
 class OracleSBNet:
@@ -403,7 +463,7 @@ class OracleSBNet:
                                              c.get("post_embedding_layers"))
 
     # -- representations
-    def represent(self, name, idx, p, training, mods=None, mod_names=None, drop_keep=None, new_stats=None):
+    def represent(self, name, idx, p, training, mods=None, mod_names=None, drop_keep=None, new_stats=None, emu=None):
         e = self.ent[name]
         if isinstance(e, FeatureProj):
             y, cache = e.forward(idx.reshape(-1), p)
@@ -413,17 +473,17 @@ class OracleSBNet:
         if not training:
             mod_names = sorted(e.eval_mods)
             mods = np.broadcast_to(np.arange(len(mod_names)), idx.shape + (len(mod_names),))
-        return e.forward(idx, np.asarray(mods), mod_names, p, training, drop_keep, new_stats)
+        return e.forward(idx, np.asarray(mods), mod_names, p, training, drop_keep, new_stats, emu=emu)
 
     def train_step_fwd_bwd(self, p, u, i, mods, mod_names, drop, loss_kind="bpr", aggregator="mean", n_items=None,
-                           neg_train=None, neg_strategy="uniform_recbole"):
+                           neg_train=None, neg_strategy="uniform_recbole", emu=None):
         """mods/mod_names/drop: dicts keyed 'user'/'item'.  Returns dict(logits, rec_loss, reg losses, grads,
         new_stats)."""
         new_stats, grads = {}, {}
         ur, ureg = self.represent("user", u, p, True, mods.get("user"), mod_names.get("user"), drop.get("user"),
-                                  new_stats)
+                                  new_stats, emu)
         ir, ireg = self.represent("item", i, p, True, mods.get("item"), mod_names.get("item"), drop.get("item"),
-                                  new_stats)
+                                  new_stats, emu)
         logits = np.einsum("be,bce->bc", ur, ir)
         rl, dlog = rec_loss(loss_kind, logits, aggregator, n_items, neg_train, neg_strategy)
         d_ur = np.einsum("bc,bce->be", dlog, ir)

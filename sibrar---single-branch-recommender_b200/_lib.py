@@ -109,7 +109,21 @@ class SbrError(RuntimeError):
     pass
 
 
+# kernels launched per C-ABI call (for the "gpu_launches" figure of bench.py)
+KERNELS_PER_CALL = {"sbr_infonce": 2, "sbr_topk_workspace_bytes": 0}
+_launches = [0]
+
+
+def reset_launch_counter():
+    _launches[0] = 0
+
+
+def launch_counter() -> int:
+    return _launches[0]
+
+
 def call(name: str, *args):
+    _launches[0] += KERNELS_PER_CALL.get(name, 1)
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise SbrError(f"{name} failed ({rc}): {lib().sbr_last_error().decode()}")

@@ -1,0 +1,118 @@
+"""One-process-per-GPU scaling of the hot path over NCCL / NVLink (``torch.distributed`` is plumbing only).
+
+The reference is single-device (no collective anywhere); this is the B200 addition:
+  * training: data parallel.  Every rank runs the fused step on its own B interactions; the flat fp32 gradient buffer
+    is all-reduced in two buckets -- the item-entity bucket is launched as soon as the item backward has been
+    enqueued, so the collective overlaps the user-entity backward -- and the multi-tensor Adam kernel divides by the
+    world size.  BatchNorm statistics and the user-side in-batch InfoNCE stay rank-local.
+  * evaluation: the item catalogue is sharded; each rank computes its items' representations and an exact local
+    top-k (packed keys with GLOBAL positions), the [U, k] key lists are all-gathered and merged by
+    ``sbr_topk_merge`` -- the only exchange step of the path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .evaluator import FullEvaluator
+from .feature_store import csr_to_device
+from .trainer import FusedTrainer
+
+
+def shard_range(n: int, rank: int, world: int):
+    """contiguous shard [lo, hi) of n items; shards differ by at most one element"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_keys(scores: np.ndarray, positions: np.ndarray) -> np.ndarray:
+    """host statement of the kernels' candidate key: order-preserving fp32 bits << 32 | (0xFFFFFFFF - position)"""
+    u = np.asarray(scores, np.float32).view(np.uint32).astype(np.uint64)
+    u = np.where(u & np.uint64(0x80000000), ~u & np.uint64(0xFFFFFFFF), u | np.uint64(0x80000000))
+    return (u << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - np.asarray(positions).astype(np.uint64))
+
+
+def unpack_keys(keys: np.ndarray):
+    keys = np.asarray(keys).astype(np.uint64)
+    u = (keys >> np.uint64(32)).astype(np.uint32)
+    u = np.where(u & np.uint32(0x80000000), u & np.uint32(0x7FFFFFFF), ~u)
+    pos = (np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    return u.astype(np.uint32).view(np.float32), pos
+
+
+def merge_keys_host(all_keys: np.ndarray, k: int) -> np.ndarray:
+    """[L, U, k] packed keys -> [U, k] largest keys per user, descending (reference statement of sbr_topk_merge)"""
+    L, U, _ = all_keys.shape
+    cat = np.transpose(all_keys, (1, 0, 2)).reshape(U, -1)
+    return np.sort(cat.astype(np.uint64), axis=1)[:, ::-1][:, :k]
+
+
+def allreduce_mean_(flat: torch.Tensor, world: int):
+    """in-place mean over ranks (used by the CPU/gloo test of the protocol; the GPU path folds 1/world into Adam)"""
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    return flat
+
+
+class DataParallelTrainer(FusedTrainer):
+    def __init__(self, model, learn, n_negative_samples, **kw):
+        self.world = dist.get_world_size()
+        # identical initial weights on every rank
+        for p in model.parameters():
+            dist.broadcast(p.data, src=0)
+        for b in model.buffers():
+            dist.broadcast(b, src=0)
+        super().__init__(model, learn, n_negative_samples, grad_scale=1.0 / self.world, **kw)
+        self._work = []
+
+    def _after_item_backward(self):
+        lo, mid, _ = self.bucket_bounds
+        if mid > lo:
+            self._work.append(dist.all_reduce(self.flat_grads[lo:mid], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _after_user_backward(self):
+        _, mid, hi = self.bucket_bounds
+        if hi > mid:
+            self._work.append(dist.all_reduce(self.flat_grads[mid:hi], op=dist.ReduceOp.SUM, async_op=True))
+        for w in self._work:
+            w.wait()  # stream-level wait: no host synchronisation
+        self._work.clear()
+
+
+class ShardedEvaluator(FullEvaluator):
+    """item-sharded full-catalog evaluation with an all-gather top-k merge"""
+
+    @torch.no_grad()
+    def evaluate(self, model, dataset=None, return_topk: bool = False):
+        dataset = dataset or self.dataset
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = model.device
+        users = np.asarray(dataset.users_in_split)
+        items = np.asarray(dataset.items_in_split)
+        lo, hi = shard_range(len(items), rank, world)
+        seen = dataset.exclude_data[users][:, lo:hi].tocsr()
+        tgt = dataset.user_sampling_matrix[users][:, items]
+        was_training = model.training
+        model.eval()
+        i_repr = model.get_item_representations(torch.from_numpy(items[lo:hi].astype(np.int64)).to(dev))
+        u_repr = model.get_user_representations(torch.from_numpy(users.astype(np.int64)).to(dev))
+        if was_training:
+            model.train()
+        ks = sorted(set(int(k) for k in self.config.top_k))
+        kmax = min(max(ks), len(items))
+        u16, i16 = ops.cast_bf16(u_repr.contiguous()), ops.cast_bf16(i_repr.contiguous())
+        seen_dev = csr_to_device(seen, dev) if seen.nnz > 0 else (None, None)
+        local = ops.topk_scores_masked(u16, i16, len(users), hi - lo, u16.shape[1], seen_dev[0], seen_dev[1],
+                                       min(kmax, hi - lo) if hi - lo < kmax else kmax, item_offset=lo,
+                                       return_keys=True)
+        if local.shape[1] < kmax:  # tiny shard: pad with empty slots
+            pad = torch.zeros((local.shape[0], kmax - local.shape[1]), dtype=local.dtype, device=dev)
+            local = torch.cat([local, pad], dim=1)
+        gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, local.contiguous())
+        vals, idx = ops.topk_merge(gathered, world, len(users), kmax)
+        out = self.metrics_from_topk(idx, csr_to_device(tgt, dev), ks, len(items))
+        return (out, (vals, idx)) if return_topk else out

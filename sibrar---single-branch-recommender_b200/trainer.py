@@ -52,9 +52,20 @@ class FusedTrainer:
                     for st in chain.stages:
                         st.refresh(False)
                         shadows[id(st.linear.weight)] = st.w16
+        # one flat fp32 gradient buffer, item-entity parameters first (they finish first in the backward pass, so a
+        # data-parallel run can all-reduce that bucket while the user entity is still back-propagating)
+        ordered = list(self.item.parameters()) + list(self.user.parameters())
+        assert len(ordered) == len(list(model.parameters()))
+        offs, total = [], 0
+        for p in ordered:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
+        self.flat_grads = torch.zeros(total, dtype=F32, device=dev)
+        n_item = len(list(self.item.parameters()))
+        self.bucket_bounds = (0, offs[n_item] if n_item < len(offs) else total, total)  # [item | user]
         entries = []
-        for p in model.parameters():
-            g = torch.zeros_like(p, dtype=F32)
+        for p, o in zip(ordered, offs):
+            g = self.flat_grads[o:o + p.numel()].view(p.shape)
             p.grad = g
             self.grads[id(p)] = g
             entries.append(dict(param=p.data, grad=g, exp_avg=torch.zeros_like(g), exp_avg_sq=torch.zeros_like(g),
@@ -90,10 +101,19 @@ class FusedTrainer:
             c = self.item.entity_config
             ops.infonce(Ei, B, n, D, c.regularization_temperature, c.regularization_weight, self.loss_acc[2:3], dEi, 1)
         self.item.backward(dEi, self.grads)
+        self._after_item_backward()
         self.user.backward(dEu, self.grads)
+        self._after_user_backward()
         if apply_optimizer:
             self.optimizer_step()
         self.steps_accumulated += 1
+
+    # hooks for the data-parallel subclass (gradient all-reduce overlapped with the rest of the backward pass)
+    def _after_item_backward(self):
+        pass
+
+    def _after_user_backward(self):
+        pass
 
     def optimizer_step(self):
         b1, b2 = self.betas
