@@ -368,7 +368,7 @@ def main():
         with CallProfiler(ops, torch) as prof:
             for k in range(3):
                 flush.zero_()
-                tr.step(*batches[args.warmup + k])
+                tr.step(*batches[(args.warmup + k) % len(batches)])
         agg = prof.summary()
         step_ms = sum(v[0] for v in agg.values()) / 3
         top = sorted(agg.items(), key=lambda kv: -kv[1][0])

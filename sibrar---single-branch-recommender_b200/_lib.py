@@ -29,7 +29,7 @@ class GemmEpilogue(C.Structure):
 
 class ModalitySrc(C.Structure):
     _fields_ = [("kind", C.c_int), ("remap", c_vp), ("table", c_vp), ("grad", c_vp), ("codes", c_vp),
-                ("max_tags", c_i32), ("pad_id", c_i32)]
+                ("max_tags", c_i32), ("pad_id", c_i32), ("key_base", c_i64)]
 
 
 class AdamTensor(C.Structure):
@@ -50,6 +50,9 @@ _PROTOS = {
                            c_vp, c_i64, c_vp, c_i64, c_vp, c_vp],
     "sbr_row_gather_bwd": [c_vp, C.c_int, c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_f32, c_u64, c_vp, c_vp,
                            c_vp, c_i64, c_vp],
+    "sbr_gather_plan": [c_vp, C.c_int, c_vp, c_vp, c_i64, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "sbr_row_gather_bwd_segmented": [c_vp, C.c_int, c_i64, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_u64, c_vp, c_vp,
+                                     c_vp, c_i64, C.c_int, C.c_int, c_vp],
     "sbr_actgrad_colsum": [c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp,
                            C.c_int, c_vp],
     "sbr_bn_finalize": [c_vp, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp],
@@ -110,7 +113,7 @@ class SbrError(RuntimeError):
 
 
 # kernels launched per C-ABI call (for the "gpu_launches" figure of bench.py)
-KERNELS_PER_CALL = {"sbr_infonce": 2, "sbr_topk_workspace_bytes": 0}
+KERNELS_PER_CALL = {"sbr_infonce": 2, "sbr_topk_workspace_bytes": 0, "sbr_gather_plan": 3}
 _launches = [0]
 
 

@@ -192,6 +192,176 @@ __global__ void row_gather_bwd_kernel(const sbr_modality_src_t* __restrict__ src
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ segmented backward
+// Rows of a batch that hit the same (modality, table row | category) are reduced by ONE warp instead of contending
+// with atomics: plan = counting sort of the flat rows by key, then a segment reduce.  L2-normalise backward is linear
+// in the incoming gradient, so it is applied once per segment (chunk) to the summed gradient.
+__device__ __forceinline__ int64_t row_key(const sbr_modality_src_t& s, int64_t feat_row) {
+  if (feat_row < 0) return -1;
+  if (s.kind == SBR_SRC_CATEGORICAL) return s.key_base + (int64_t)__ldg(s.codes + feat_row);
+  return s.key_base + feat_row;
+}
+
+__global__ void plan_count_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
+                                  const int64_t* __restrict__ idx, const uint8_t* __restrict__ mods, int64_t N, int k,
+                                  int32_t* __restrict__ counts, int32_t* __restrict__ row_keys) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const sbr_modality_src_t& s = srcs[min(mods ? (int)mods[r] : 0, n_mods - 1)];
+  const int64_t e = idx[r / k];
+  const int64_t feat_row = s.remap ? (int64_t)__ldg(s.remap + e) : e;
+  const int64_t key = row_key(s, feat_row);
+  row_keys[r] = (int32_t)key;
+  if (key >= 0) atomicAdd(counts + key, 1);
+}
+
+// exclusive scan by one block (n up to a few million keys: n / 1024 iterations)
+__global__ void plan_scan_kernel(const int32_t* __restrict__ counts, int64_t n, int32_t* __restrict__ offsets) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const int32_t v = i < n ? counts[i] : 0;
+    int32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_sums[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const int32_t carry = carry_s;
+    const int32_t warp_off = warp > 0 ? warp_sums[warp - 1] : 0;
+    if (i < n) offsets[i] = carry + warp_off + x - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry_s;
+}
+
+__global__ void plan_fill_kernel(const int32_t* __restrict__ row_keys, int64_t N, const int32_t* __restrict__ offsets,
+                                 int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const int32_t key = row_keys[r];
+  if (key < 0) return;
+  perm[offsets[key] + atomicAdd(cursor + key, 1)] = (int32_t)r;
+}
+
+template <int NV4>
+__global__ void seg_reduce_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int64_t n_keys,
+                                  const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm, int C,
+                                  int normalize, float p_drop, uint64_t seed, const int64_t* __restrict__ step_dev,
+                                  const uint8_t* __restrict__ keep_mask, const float* __restrict__ dx, int64_t ld_dx,
+                                  int rows_per_chunk) {
+  const int64_t key = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (key >= n_keys) return;
+  const int lane = threadIdx.x & 31;
+  const int32_t seg_beg = offsets[key], seg_end = offsets[key + 1];
+  const int32_t beg = seg_beg + blockIdx.y * rows_per_chunk;
+  if (beg >= seg_end) return;
+  // the last chunk of the grid takes everything that is left
+  const int32_t end = (blockIdx.y == gridDim.y - 1) ? seg_end : min(seg_end, beg + rows_per_chunk);
+  const bool whole = (beg == seg_beg && end == seg_end);
+  int m = 0;
+  for (int t = 1; t < n_mods; ++t)
+    if (key >= srcs[t].key_base) m = t;
+  const sbr_modality_src_t s = srcs[m];
+  if (s.grad == nullptr) return;
+  const uint64_t step = step_dev ? (uint64_t)*step_dev : 0;
+  float g[NV4 * 4];
+#pragma unroll
+  for (int i = 0; i < NV4 * 4; ++i) g[i] = 0.f;
+  for (int32_t p = beg; p < end; ++p) {
+    const int64_t r = perm[p];
+    uint4 cache;
+    int cache_c4 = -1;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = 4 * lane + j + 128 * i;
+        if (c < C)
+          g[i * 4 + j] += dx[r * ld_dx + c] * keep_scale(keep_mask, r, C, c, p_drop, seed, step, cache, cache_c4);
+      }
+  }
+  const int64_t local = key - s.key_base;  // table row | category | entity row (TAG)
+  float inv_cnt = 1.f;
+  if (normalize || s.kind == SBR_SRC_TAG) {
+    // every row of the segment gathered the same source vector x
+    sbr_modality_src_t src = s;
+    float x[NV4 * 4];
+    if (s.kind == SBR_SRC_CATEGORICAL) {  // load_source_row indexes through codes: point it at the category row
+      const float* w = s.table + local * C;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 4 * lane + j + 128 * i;
+          x[i * 4 + j] = c < C ? __ldg(w + c) : 0.f;
+        }
+    } else {
+      load_source_row<NV4>(src, local, C, lane, x, inv_cnt);
+    }
+    if (normalize) {
+      float ss = 0.f, dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV4 * 4; ++i) ss += x[i] * x[i];
+      ss = warp_sum(ss);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < NV4 * 4; ++i) {
+        x[i] *= inv;
+        dot += x[i] * g[i];
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int i = 0; i < NV4 * 4; ++i) g[i] = (g[i] - x[i] * dot) * inv;
+    }
+  }
+  if (s.kind == SBR_SRC_TAG) {
+    for (int t = 0; t < s.max_tags; ++t) {
+      const int32_t tag = __ldg(s.codes + local * s.max_tags + t);
+      if (tag == s.pad_id) continue;
+      float* w = s.grad + (int64_t)tag * C;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 4 * lane + j + 128 * i;
+          if (c < C) atomicAdd(w + c, g[i * 4 + j] * inv_cnt);
+        }
+    }
+  } else {
+    float* w = s.grad + local * C;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = 4 * lane + j + 128 * i;
+        if (c < C) {
+          if (whole) w[c] += g[i * 4 + j];
+          else atomicAdd(w + c, g[i * 4 + j]);
+        }
+      }
+  }
+}
+
 }  // namespace
 
 extern "C" int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx,
@@ -230,3 +400,37 @@ extern "C" int sbr_row_gather_bwd(const sbr_modality_src_t* srcs_dev, int n_mods
   return SBR_OK;
 }
 
+
+extern "C" int sbr_gather_plan(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
+                               int64_t n_idx, int k, int64_t n_keys, int32_t* counts, int32_t* offsets,
+                               int32_t* cursor, int32_t* row_keys, int32_t* perm, void* stream) {
+  SBR_REQUIRE(srcs_dev && idx && counts && offsets && cursor && row_keys && perm, "sbr_gather_plan: null argument");
+  SBR_REQUIRE(n_idx > 0 && k >= 1 && n_keys > 0 && n_keys < (1ll << 31), "sbr_gather_plan: bad sizes");
+  const int64_t N = n_idx * k;
+  SBR_REQUIRE(N < (1ll << 31), "sbr_gather_plan: too many rows");
+  SBR_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_keys, S(stream)));
+  SBR_CHECK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n_keys, S(stream)));
+  plan_count_kernel<<<cdiv(N, 256), 256, 0, S(stream)>>>(srcs_dev, n_mods, idx, mods, N, k, counts, row_keys);
+  plan_scan_kernel<<<1, 1024, 0, S(stream)>>>(counts, n_keys, offsets);
+  plan_fill_kernel<<<cdiv(N, 256), 256, 0, S(stream)>>>(row_keys, N, offsets, cursor, perm);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, int n_mods, int64_t n_keys,
+                                            const int32_t* offsets, const int32_t* perm, int C, int normalize,
+                                            float p_drop, uint64_t seed, const int64_t* step_dev,
+                                            const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
+                                            int rows_per_chunk, int n_chunks, void* stream) {
+  SBR_REQUIRE(srcs_dev && offsets && perm && dx && n_keys > 0, "sbr_row_gather_bwd_segmented: bad arguments");
+  SBR_REQUIRE(C > 0 && C <= 1024 && ld_dx >= C, "sbr_row_gather_bwd_segmented: C=%d not in [1, 1024] or ld_dx < C", C);
+  SBR_REQUIRE(rows_per_chunk >= 1 && n_chunks >= 1 && n_chunks <= 65535, "sbr_row_gather_bwd_segmented: bad chunking");
+  dim3 grid(cdiv(n_keys, 8), (unsigned)n_chunks);
+  DISPATCH_NV(C, 128, {
+    constexpr int NV4 = NVv > 8 ? 8 : NVv;
+    seg_reduce_kernel<NV4><<<grid, 256, 0, S(stream)>>>(srcs_dev, n_mods, n_keys, offsets, perm, C, normalize, p_drop,
+                                                        seed, step_dev, keep_mask, dx, ld_dx, rows_per_chunk);
+  });
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
