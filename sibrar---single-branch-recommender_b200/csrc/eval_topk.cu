@@ -1,18 +1,23 @@
 // sibrar_b200 -- full-catalog evaluation: tiled user x item score GEMM (tcgen05, TMEM accumulators, TMA operand
 // staging) fused with seen-item masking and an exact streaming top-k, so the [U, I] score matrix never reaches HBM.
 //
-// Orientation: ITEMS are the UMMA M dimension (TMEM lanes), USERS the N dimension (TMEM columns).  A CTA keeps the
-// bf16 embeddings of NU users resident in shared memory (B operand) and streams 128-item tiles (A operand) through a
-// TMA ring; accumulators are double-buffered in TMEM so the MMA of tile t+1 overlaps the epilogue of tile t.
-// Epilogue warps (one TMEM lane quarter each): lane = item, register c = user.  A score is a candidate when it beats
-// the user's running k-th best (threshold in smem); candidates are found with warp ballots per user column, filtered
-// by the seen-item bitmap of the tile (built from the sorted seen CSR with one cursor per user), and appended as
-// packed 64-bit keys  (order-preserving score bits << 32 | ~position)  to a per-user list in global scratch.  When a
-// list may overflow it is pruned to its exact top-k by one warp (bitwise k-th-largest selection with warp reductions),
-// which also raises the threshold.  Larger key == better: higher score first, ties -> LOWEST item position.
+// Orientation: USERS are the UMMA M dimension (TMEM lanes), ITEMS the N dimension (TMEM columns).  A CTA keeps the
+// bf16 embeddings of 128 * UT users resident IN TENSOR MEMORY (the A operand of tcgen05.mma in TS form, so the MMA
+// reads only the item tile from shared memory -- the SS form is bound by the 128 B/clk shared-memory read port at
+// M = N = 128) and streams 128-item tiles (B operand) through a TMA ring.  One fp32 accumulator [128 users x 128 items]
+// per user tile (UT = 2; the MMA of one user tile overlaps the drain of the other) or two alternating ones (UT = 1).
+// Epilogue thread = (user, 64-column slice): it copies its 64 scores TMEM -> registers, hands the accumulator back,
+// and compares a 3-input max tree against the user's running threshold (one register) -- ~0.6 instructions per score
+// on the common path.  Scores that reach the threshold and are not in the user's seen set (a sorted-CSR cursor turned
+// into a 64-bit mask per tile) are appended to the thread's candidate list in global scratch; when a list may
+// overflow its warp prunes it to the exact top-k (bisection over the packed 64-bit keys) and raises the threshold.
+// A second small kernel merges the lists of a user; sbr_topk_merge merges item splits / ranks.
+// Larger key == better: higher score first, ties -> LOWEST item position.
 //
 // Replaces eval/eval.py:216-220 (scores, mask -> -inf) + the top-k inside rmet.calculate (eval/eval.py:99-102), and
 // provides the k-way merge for item-split / item-sharded evaluation and the per-user metrics (eval/metrics.py:4-105).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -20,38 +25,46 @@ namespace {
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
-constexpr int TI = 128;  // items per tile (UMMA M)
-constexpr int STAGES = 4;
-constexpr int ITEM_STAGE_BYTES = TI * 128;
-constexpr int MAX_R = 16;  // candidate keys per lane in a prune: cap <= 512
+constexpr int TI = 128;         // items per tile (UMMA N)
+constexpr int UM = 128;         // users per UMMA (M = TMEM lanes)
+constexpr int MAX_STAGES = 12;  // ring of item K-chunks (actual depth chosen from the free shared memory)
+constexpr int STAGE_BYTES = TI * 128;
+constexpr int W = 64;           // accumulator columns (items) one epilogue thread scans per tile
+constexpr int CS = TI / W;      // column slices per tile = candidate lists per user
+constexpr int A_COL0 = 256;     // first TMEM column of the user operand (accumulators live in [0, 256))
 
 struct TopkParams {
-  int64_t U, I;
-  int D, k, cap;
-  int tiles_per_split, num_item_tiles;
+  int64_t U, I, users_padded, ldu;
+  int D, k, cap, prune_at;
+  int tiles_per_split, num_item_tiles, stages;
   int32_t item_offset;
+  int debug;  // SBR_TOPK_DEBUG (measurement only): 1 = skip the scan, 2 = also skip the TMEM load, 3 = 2 + no TMA,
+              // 4 = 2 + no MMA, -1 = common path of the scan only
+  const bf16* users;
   const int64_t* seen_indptr;
   const int32_t* seen_indices;
   unsigned long long* part_keys;  // [n_splits, U, k]
-  unsigned long long* cand;       // [gridDim.y, gridDim.x * NU, cap]
+  uint2* cand;                    // [n_splits, users_padded, CS, cap]  (raw score bits, local item position)
+  int32_t* cand_cnt;              // [n_splits, users_padded, CS]
 };
 
+__device__ __forceinline__ uint32_t orderable(uint32_t fbits) {
+  return (fbits & 0x80000000u) ? ~fbits : (fbits | 0x80000000u);
+}
+__device__ __forceinline__ float orderable_to_float(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
 __device__ __forceinline__ unsigned long long make_key(float score, uint32_t pos) {
-  uint32_t u = __float_as_uint(score);
-  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - pos);
+  return ((unsigned long long)orderable(__float_as_uint(score)) << 32) | (unsigned long long)(0xFFFFFFFFu - pos);
 }
-__device__ __forceinline__ float key_score(unsigned long long key) {
-  uint32_t u = (uint32_t)(key >> 32);
-  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
-  return __uint_as_float(u);
-}
+__device__ __forceinline__ float key_score(unsigned long long key) { return orderable_to_float((uint32_t)(key >> 32)); }
 __device__ __forceinline__ int32_t key_pos(unsigned long long key) {
   return (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
 }
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 // k-th largest of the (distinct, non-zero) keys held by the warp, R per lane.  Returns 0 if fewer than k keys.
@@ -70,279 +83,428 @@ __device__ __forceinline__ unsigned long long warp_kth_largest(const unsigned lo
   return prefix;
 }
 
-// prune the candidate list of one user to its top-k (in place); returns the new count and k-th key
-__device__ __forceinline__ void prune_list(unsigned long long* list, int count, int k, int lane, int& new_count,
-                                           unsigned long long& kth) {
-  unsigned long long keys[MAX_R];
+// Lower bound `t` of the k-th largest key such that EXACTLY k keys are >= t.  Needs more than k valid (non-zero,
+// distinct) keys in the warp.  Bisection over the key bits, starting below the keys' common prefix and stopping as
+// soon as the count is exactly k (typically ~10 rounds instead of 64).
+template <int R>
+__device__ __forceinline__ unsigned long long warp_select_k(const unsigned long long (&keys)[R], int k) {
+  uint32_t or_hi = 0, or_lo = 0, and_hi = 0xFFFFFFFFu, and_lo = 0xFFFFFFFFu;
 #pragma unroll
-  for (int i = 0; i < MAX_R; ++i) {
-    int pos = lane + 32 * i;
-    keys[i] = pos < count ? __ldcg(list + pos) : 0ull;
+  for (int i = 0; i < R; ++i) {
+    if (keys[i] != 0ull) {
+      or_hi |= (uint32_t)(keys[i] >> 32); or_lo |= (uint32_t)keys[i];
+      and_hi &= (uint32_t)(keys[i] >> 32); and_lo &= (uint32_t)keys[i];
+    }
   }
-  kth = warp_kth_largest<MAX_R>(keys, k);  // 0 when count < k: everything survives
+  or_hi = __reduce_or_sync(0xffffffffu, or_hi);
+  or_lo = __reduce_or_sync(0xffffffffu, or_lo);
+  and_hi = __reduce_and_sync(0xffffffffu, and_hi);
+  and_lo = __reduce_and_sync(0xffffffffu, and_lo);
+  const unsigned long long orv = ((unsigned long long)or_hi << 32) | or_lo;
+  const unsigned long long andv = ((unsigned long long)and_hi << 32) | and_lo;
+  const unsigned long long diff = orv ^ andv;  // != 0: at least two distinct keys
+  const int top = 63 - __clzll((long long)diff);
+  unsigned long long prefix = (top == 63) ? 0ull : (andv & ~((2ull << top) - 1ull));
+#pragma unroll 1
+  for (int bit = top; bit >= 0; --bit) {
+    const unsigned long long trial = prefix | (1ull << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i) c += (keys[i] >= trial) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) {
+      prefix = trial;
+      if (c == k) break;
+    }
+  }
+  return prefix;
+}
+
+// one candidate list (count entries, all unseen) as packed keys, R per lane
+template <int R>
+__device__ __forceinline__ void load_list_keys(const uint2* __restrict__ list, int count, int lane,
+                                               unsigned long long (&keys)[R]) {
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int idx = lane + 32 * i;
+    unsigned long long key = 0ull;
+    if (idx < count) {
+      const uint2 e = __ldcg(list + idx);
+      key = ((unsigned long long)orderable(e.x) << 32) | (unsigned long long)(0xFFFFFFFFu - e.y);
+    }
+    keys[i] = key;
+  }
+}
+
+// Prunes one candidate list in place to its k best entries (all of them if there are at most k).
+// Warp-cooperative; returns the new length and the lower bound of the k-th key (0 = no bound yet).
+template <int R>
+__device__ __forceinline__ void prune_list(uint2* list, int count, int k, int lane, int& new_count,
+                                           unsigned long long& bound) {
+  unsigned long long keys[R];
+  load_list_keys<R>(list, count, lane, keys);
+  bound = 0ull;
+  if (count > k) bound = warp_select_k<R>(keys, k);
+  else if (count == k) {  // everything survives; the smallest key is the bound
+    unsigned long long mn = ~0ull;
+#pragma unroll
+    for (int i = 0; i < R; ++i) if (keys[i] != 0ull && keys[i] < mn) mn = keys[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, mn, o);
+      mn = other < mn ? other : mn;
+    }
+    bound = mn;
+  }
   __syncwarp();
   int offset = 0;
 #pragma unroll
-  for (int i = 0; i < MAX_R; ++i) {
-    const bool keep = keys[i] != 0ull && keys[i] >= kth;
+  for (int i = 0; i < R; ++i) {
+    const bool keep = keys[i] != 0ull && keys[i] >= bound;
     const unsigned bits = __ballot_sync(0xffffffffu, keep);
-    if (keep) __stcg(list + offset + __popc(bits & ((1u << lane) - 1u)), keys[i]);
+    if (keep) {
+      const uint32_t hi = (uint32_t)(keys[i] >> 32);
+      const uint32_t raw = (hi & 0x80000000u) ? (hi & 0x7FFFFFFFu) : ~hi;
+      __stcg(list + offset + __popc(bits & ((1u << lane) - 1u)),
+             make_uint2(raw, 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull)));
+    }
     offset += __popc(bits);
   }
   new_count = offset;
   __syncwarp();
 }
 
-template <int NU>
-__global__ void __launch_bounds__(192, 1)
-topk_scores_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI, TopkParams p) {
+// one 32-column block of the accumulator: lane = user, r[c] = score of item pos0 + c.  `skip` = columns that are
+// seen items of this lane's user or lie beyond the catalogue.
+__device__ __forceinline__ void scan32(const uint32_t (&r)[32], float thr, uint32_t pos0, uint32_t skip, uint2* list,
+                                       int& cnt) {
+  float m[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float a = fmax3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+    const float b = fmax3(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+    m[g] = fmaxf(fmax3(a, b, __uint_as_float(r[8 * g + 6])), __uint_as_float(r[8 * g + 7]));
+  }
+  const float mm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+  if (!__any_sync(0xffffffffu, mm >= thr)) return;
+  const bool any_skip = __any_sync(0xffffffffu, skip != 0u);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (__any_sync(0xffffffffu, m[g] >= thr)) {
+      if (!any_skip) {
+#pragma unroll
+        for (int c = 8 * g; c < 8 * g + 8; ++c) {
+          if (__uint_as_float(r[c]) >= thr) {
+            __stcg(list + cnt, make_uint2(r[c], pos0 + (uint32_t)c));
+            ++cnt;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 8 * g; c < 8 * g + 8; ++c) {
+          if (__uint_as_float(r[c]) >= thr && !((skip >> c) & 1u)) {
+            __stcg(list + cnt, make_uint2(r[c], pos0 + (uint32_t)c));
+            ++cnt;
+          }
+        }
+      }
+    }
+  }
+}
+
+// UT = user tiles of 128 per CTA, R = cap / 32.  Warps [0, 8*UT) = epilogue, then TMA producer, then MMA issuer.
+// "Job" j = one [128 users x 128 items] accumulator: UT == 2: tile j / 2, user tile j % 2;  UT == 1: tile j.
+// Job j uses accumulator j % 2.
+template <int UT, int R>
+__global__ void __launch_bounds__((8 * UT + 2) * 32, 1)
+topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
+  constexpr int NEW = 8 * UT;  // epilogue warps: 4 lane quarters x CS column slices per accumulator in flight
+  constexpr int NUSERS = UT * UM;
+  constexpr int CAP = 32 * R;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int KC = (p.D + 63) / 64;
-  uint8_t* sU = smem;                                  // KC chunks of [NU rows x 128 B]
-  uint8_t* sI = sU + (size_t)KC * NU * 128;            // STAGES x [128 rows x 128 B]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sI + STAGES * ITEM_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* ufull_bar = empty_bar + STAGES;
-  uint64_t* tfull_bar = ufull_bar + 1;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;  // [2]
+  const int KA = KC * 32;  // TMEM columns of one user tile (two bf16 per column, zero-padded to whole K chunks)
+  const int STAGES = p.stages;
+  uint8_t* sI = smem;  // STAGES x [128 items x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sI + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
-  float* s_thr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 128);  // [NU], 16-byte aligned
-  int* s_cnt = reinterpret_cast<int*>(s_thr + NU);                 // [NU]
-  uint32_t* s_bm = reinterpret_cast<uint32_t*>(s_cnt + NU);        // [NU][4]
+  uint32_t* s_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [NUSERS] orderable bits
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t u0 = (int64_t)blockIdx.x * NU;
+  const int64_t u0 = (int64_t)blockIdx.x * NUSERS;
   const int split = blockIdx.y;
   const int tile_begin = split * p.tiles_per_split;
   const int tile_end = min(p.num_item_tiles, tile_begin + p.tiles_per_split);
   const int n_tiles = tile_end - tile_begin;
+  const int n_jobs = n_tiles * UT;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmU);
+  if (warp == NEW && lane == 0) {
     tma_prefetch_desc(&tmI);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(ufull_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * NU);
-  for (int j = threadIdx.x; j < NU; j += blockDim.x) {
-    s_thr[j] = (u0 + j < p.U) ? -INFINITY : INFINITY;  // users past the end never collect candidates
-    s_cnt[j] = 0;
-  }
-  if (threadIdx.x == 0) *s_flag = 0;
+  if (warp == NEW + 1) tmem_alloc(tmem_slot, 512);
+  for (int j = threadIdx.x; j < NUSERS; j += blockDim.x) s_thr[j] = 0x007FFFFFu;  // orderable(-inf)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_arrive_expect_tx(ufull_bar, (uint32_t)(KC * NU * 128));
-      for (int kc = 0; kc < KC; ++kc) tma_load_2d(sU + (size_t)kc * NU * 128, &tmU, ufull_bar, kc * 64, (int)u0);
+  // ---- user operand: global bf16 rows -> TMEM (lane = user, column j = elements 2j, 2j+1)
+  if (warp < NEW) {
+    const int q = warp & 3;
+    const int grp = warp >> 2;  // UT == 2: user tile = grp % 2, slice = grp / 2;  UT == 1: slice = grp
+    const int ut = (UT == 2) ? (grp & 1) : 0;
+    const int cs = (UT == 2) ? (grp >> 1) : grp;
+    if (cs == 0) {
+      const int64_t u = u0 + ut * UM + q * 32 + lane;
+      const uint4* row = reinterpret_cast<const uint4*>(p.users + (u < p.U ? u : 0) * p.ldu);
+      for (int c32 = 0; c32 < KA / 32; ++c32) {
+        uint32_t w[32];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const int e0 = c32 * 64 + v * 8;  // first bf16 element of this 16-byte vector
+          uint4 x = make_uint4(0u, 0u, 0u, 0u);
+          if (u < p.U && e0 < p.D) x = __ldg(row + (e0 >> 3));
+          w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        }
+        tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_COL0 + ut * KA + c32 * 32), w);
+      }
+      tmem_st_wait();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == NEW) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
+    if (p.debug != 3) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int row0 = (tile_begin + t) * TI;
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], ITEM_STAGE_BYTES);
-          tma_load_2d(sI + s * ITEM_STAGE_BYTES, &tmI, &full_bar[s], kc * 64, row0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_2d(sI + s * STAGE_BYTES, &tmI, &full_bar[s], kc * 64, row0);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TI, NU, 0, 0);
-      mbar_wait(ufull_bar, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        const int acc = t & 1;
-        const uint32_t use = (uint32_t)(t >> 1);
-        mbar_wait(&tempty_bar[acc], (use & 1) ^ 1);
+  } else if (warp == NEW + 1) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected issue)
+    const uint32_t idesc = umma_idesc_bf16(UM, TI, 0, 0);
+    const int last_ksteps = (p.D - (KC - 1) * 64 + 15) / 16;
+    const uint32_t sI_addr = smem_u32(sI);
+    int s = 0;  // ring position of the current tile's first chunk
+    uint32_t ph = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      int ss = s;
+      uint32_t pp = ph;
+#pragma unroll
+      for (int ut = 0; ut < UT; ++ut) {
+        const int j = t * UT + ut;
+        const int a = j & 1;
+        mbar_wait(&tempty_bar[a], (uint32_t)(((j >> 1) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NU);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * TI);
+        ss = s;
+        pp = ph;
         for (int kc = 0; kc < KC; ++kc) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sI + s * ITEM_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sU + (size_t)kc * NU * 128);
-          const int ksteps = min(4, (p.D - kc * 64 + 15) / 16);
-          for (int k = 0; k < ksteps; ++k) {
-            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 16, 1024), umma_smem_desc(b_addr + k * 32, 16, 1024),
-                      idesc, (kc > 0 || k > 0) ? 1u : 0u);
+          if (ut == 0 && p.debug != 3) {  // the second user tile re-uses the chunk the first one waited for
+            mbar_wait(&full_bar[ss], pp);
+            tc_fence_after();
           }
-          umma_commit(&empty_bar[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          const uint32_t b_addr = sI_addr + (uint32_t)(ss * STAGE_BYTES);
+          const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + ut * KA + kc * 32);
+          const int ksteps = (kc == KC - 1) ? last_ksteps : 4;
+          if (elect_one()) {
+            if (p.debug != 4) {
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), umma_smem_desc(b_addr + k * 32, 16, 1024), idesc,
+                             (kc > 0 || k > 0) ? 1u : 0u);
+            }
+            if (ut == UT - 1) umma_commit(&empty_bar[ss]);
+          }
+          __syncwarp();
+          if (++ss == STAGES) { ss = 0; pp ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit(&tfull_bar[a]);
+        __syncwarp();
       }
+      s = ss;
+      ph = pp;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: 4 warps = 128 threads
-    const int q = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127
-    constexpr int UPT = NU / 128;     // users whose seen-cursor this thread owns
-    int64_t cur[UPT], cend[UPT];
-    const int64_t first_item = (int64_t)tile_begin * TI;
-#pragma unroll
-    for (int w = 0; w < UPT; ++w) {
-      const int64_t u = u0 + et + 128 * w;
-      cur[w] = cend[w] = 0;
-      if (p.seen_indptr != nullptr && u < p.U) {
-        int64_t lo = p.seen_indptr[u], hi = p.seen_indptr[u + 1];
-        cend[w] = hi;
-        while (lo < hi) {  // lower_bound(first item of this CTA's range)
-          int64_t mid = (lo + hi) >> 1;
-          if ((int64_t)p.seen_indices[mid] < first_item) lo = mid + 1;
-          else hi = mid;
-        }
-        cur[w] = lo;
+    // ------------------------------------------------------------------ epilogue: lane = user, columns = items
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int grp = warp >> 2;
+    const int ut = (UT == 2) ? (grp & 1) : 0;
+    const int cs = (UT == 2) ? (grp >> 1) : grp;
+    const int ul0 = ut * UM + q * 32;  // first user (CTA-local) of this warp
+    const int64_t u_warp = u0 + ul0;
+    const int64_t u = u_warp + lane;
+    uint2* warp_list = p.cand + (((size_t)split * p.users_padded + u_warp) * CS + cs) * (size_t)CAP;
+    constexpr size_t LANE_STRIDE = (size_t)CS * CAP;
+    uint2* my_list = warp_list + lane * LANE_STRIDE;
+    float thr = (u < p.U) ? -INFINITY : INFINITY;  // users past the end never collect candidates
+    int cnt = 0;
+    // cursor into the user's sorted seen row
+    int64_t cur = 0, cend = 0;
+    int32_t next_seen = 0x7FFFFFFF;
+    if (p.seen_indptr != nullptr && u < p.U) {
+      int64_t lo = __ldg(p.seen_indptr + u), hi = __ldg(p.seen_indptr + u + 1);
+      cend = hi;
+      const int32_t first_item = tile_begin * TI;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(p.seen_indices + mid) < first_item) lo = mid + 1;
+        else hi = mid;
       }
+      cur = lo;
+      if (cur < cend) next_seen = __ldg(p.seen_indices + cur);
     }
-    unsigned long long* my_cand = p.cand + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)NU * p.cap;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cs * W);
 
-    for (int t = 0; t < n_tiles; ++t) {
-      const int acc = t & 1;
-      const uint32_t use = (uint32_t)(t >> 1);
-      const int64_t item0 = (int64_t)(tile_begin + t) * TI;
-      // 1. seen bitmap of this tile: bit (item - item0) of user j lives in s_bm[j][(item - item0) / 32]
-#pragma unroll
-      for (int w = 0; w < UPT; ++w) {
-        const int j = et + 128 * w;
-        uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-        int64_t c = cur[w];
-        while (c < cend[w]) {
-          const int64_t it = (int64_t)__ldg(p.seen_indices + c) - item0;
-          if (it >= TI) break;
-          if (it >= 0) {
-            const uint32_t bit = 1u << (it & 31);
-            if (it < 32) b0 |= bit;
-            else if (it < 64) b1 |= bit;
-            else if (it < 96) b2 |= bit;
-            else b3 |= bit;
-          }
-          ++c;
+    for (int j = (UT == 2) ? ut : 0; j < n_jobs; j += UT) {
+      const int a = j & 1;
+      const uint32_t use = (uint32_t)(j >> 1);
+      const int t = (UT == 2) ? (j >> 1) : j;
+      const int64_t item0 = (int64_t)(tile_begin + t) * TI + cs * W;
+      // seen items / out-of-catalogue columns of this thread's 64-column slice
+      uint32_t skip0 = 0u, skip1 = 0u;
+      if (__any_sync(0xffffffffu, (int64_t)next_seen < item0 + W)) {
+        while ((int64_t)next_seen < item0 + W) {
+          const int rel = (int)((int64_t)next_seen - item0);
+          if (rel >= 32) skip1 |= 1u << (rel - 32);
+          else if (rel >= 0) skip0 |= 1u << rel;
+          ++cur;
+          next_seen = cur < cend ? __ldg(p.seen_indices + cur) : 0x7FFFFFFF;
         }
-        cur[w] = c;
-        *reinterpret_cast<uint4*>(s_bm + 4 * j) = make_uint4(b0, b1, b2, b3);
       }
-      named_bar_sync(1, 128);
-      // 2. scan the accumulator
-      mbar_wait(&tfull_bar[acc], use & 1);
+      if (item0 + W > p.I) {  // last tile: columns beyond the catalogue hold zeros
+        const int64_t nvalid = p.I - item0;
+        skip0 |= nvalid <= 0 ? 0xFFFFFFFFu : (nvalid >= 32 ? 0u : (0xFFFFFFFFu << nvalid));
+        skip1 |= nvalid <= 32 ? 0xFFFFFFFFu : (nvalid >= 64 ? 0u : (0xFFFFFFFFu << (nvalid - 32)));
+      }
+      thr = fmaxf(thr, orderable_to_float(s_thr[ul0 + lane]));
+      mbar_wait(&tfull_bar[a], use & 1);
       tc_fence_after();
-      const int64_t my_item = item0 + q * 32 + lane;
-      const unsigned valid_bits = __ballot_sync(0xffffffffu, my_item < p.I);
-      const uint32_t my_pos = (uint32_t)(my_item + p.item_offset);
-#pragma unroll 1
-      for (int c0 = 0; c0 < NU; c0 += 32) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NU + c0), r);
-        float thr[32];
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          float4 v = *reinterpret_cast<const float4*>(s_thr + c0 + c);
-          thr[c] = v.x; thr[c + 1] = v.y; thr[c + 2] = v.z; thr[c + 3] = v.w;
-        }
+      uint32_t r0[32], r1[32];
+      if (p.debug < 2) {
+        tmem_ld32(lane_taddr + (uint32_t)(a * TI), r0);
+        tmem_ld32(lane_taddr + (uint32_t)(a * TI + 32), r1);
         tmem_ld_wait();
-        bool any = false;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) any |= (__uint_as_float(r[c]) > thr[c]);
-        if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float sc = __uint_as_float(r[c]);
-            unsigned bits = __ballot_sync(0xffffffffu, sc > thr[c]) & valid_bits;
-            if (bits) {
-              const int j = c0 + c;
-              bits &= ~s_bm[4 * j + q];
-              if (bits) {
-                const int npass = __popc(bits);
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_cnt[j], npass);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if ((bits >> lane) & 1u) {
-                  const int pos = base + __popc(bits & ((1u << lane) - 1u));
-                  if (pos < p.cap) __stcg(my_cand + (size_t)j * p.cap + pos, make_key(sc, my_pos));
-                }
-                if (lane == 0) {
-                  const int nc = base + npass;
-                  if (nc > p.cap - TI || (thr[c] == -INFINITY && nc >= p.k)) *s_flag = 1;
-                }
-              }
-            }
-          }
-        }
       }
-      // 3. all reads of this accumulator and all appends of this tile are done
+      // the accumulator is in registers: hand it back to the MMA warp before the scan
       tc_fence_before();
-      named_bar_sync(1, 128);
-      if (et == 0) mbar_arrive(&tempty_bar[acc]);
-      const int flagged = *s_flag;
-      named_bar_sync(1, 128);
-      if (et == 0) *s_flag = 0;
-      // 4. prune the lists that could overflow during the next tile (or that can now define a threshold)
-      if (flagged) {
-        for (int j = q; j < NU; j += 4) {
-          const int c = s_cnt[j];
-          if (c > p.cap - TI || (s_thr[j] == -INFINITY && c >= p.k)) {
-            int nc;
-            unsigned long long kth;
-            prune_list(my_cand + (size_t)j * p.cap, min(c, p.cap), p.k, lane, nc, kth);
-            if (lane == 0) {
-              s_cnt[j] = nc;
-              if (kth != 0ull) s_thr[j] = key_score(kth);
-            }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      if (p.debug >= 1) {
+        if (p.debug < 2 && r0[0] == 0x7fc12345u && r1[31] == 0x7fc54321u) cnt = 1;  // keep the loads alive
+      } else {
+        if (p.debug == -1) thr = INFINITY;  // measurement only: common path of the scan alone
+        scan32(r0, thr, (uint32_t)item0, skip0, my_list, cnt);
+        scan32(r1, thr, (uint32_t)item0 + 32u, skip1, my_list, cnt);
+      }
+      // prune the lists that could overflow during the next tile
+      unsigned need = __ballot_sync(0xffffffffu, cnt > p.prune_at);
+      while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        const int cntL = __shfl_sync(0xffffffffu, cnt, L);
+        int nc;
+        unsigned long long bound;
+        prune_list<R>(warp_list + L * LANE_STRIDE, cntL, p.k, lane, nc, bound);
+        if (lane == L) {
+          cnt = nc;
+          if (bound != 0ull) {
+            const uint32_t hi = (uint32_t)(bound >> 32);
+            thr = fmaxf(thr, orderable_to_float(hi));
+            atomicMax(&s_thr[ul0 + lane], hi);
           }
         }
       }
-      // (the bitmap barrier of the next tile orders these smem updates before the next scan)
     }
-    // ------------------------------------------------------------------ final: <= k survivors per user -> part_keys
-    named_bar_sync(1, 128);
-    for (int j = q; j < NU; j += 4) {
-      const int64_t u = u0 + j;
-      if (u >= p.U) continue;
-      int c = min(s_cnt[j], p.cap);
-      unsigned long long* list = my_cand + (size_t)j * p.cap;
-      if (c > p.k) {
-        unsigned long long kth;
-        prune_list(list, c, p.k, lane, c, kth);
-      }
-      unsigned long long* dst = p.part_keys + ((size_t)split * p.U + u) * p.k;
-      for (int i = lane; i < p.k; i += 32) dst[i] = i < c ? __ldcg(list + i) : 0ull;
-    }
+    if (u < p.U) p.cand_cnt[((size_t)split * p.users_padded + u) * CS + cs] = cnt;
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == NEW + 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * NU);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
-inline size_t topk_smem_bytes(int NU, int D) {
-  const int KC = (D + 63) / 64;
-  return (size_t)KC * NU * 128 + STAGES * ITEM_STAGE_BYTES + 256 + (size_t)NU * (4 + 4 + 16) + 1024 + 64;
+// one warp per (split, user): the CS candidate lists of the user -> exact top-k -> part_keys (unsorted packed keys
+// with GLOBAL positions, 0 = empty slot)
+template <int R>
+__global__ void topk_finalize_kernel(TopkParams p, int n_splits) {
+  const int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)n_splits * p.U) return;
+  const int lane = threadIdx.x & 31;
+  const int split = (int)(w / p.U);
+  const int64_t u = w - (int64_t)split * p.U;
+  constexpr int CAP = 32 * R;
+  unsigned long long keys[CS * R];
+  int total = 0;
+#pragma unroll
+  for (int cs = 0; cs < CS; ++cs) {
+    const size_t li = ((size_t)split * p.users_padded + u) * CS + cs;
+    const int c = p.cand_cnt[li];
+    total += c;
+    unsigned long long part[R];
+    load_list_keys<R>(p.cand + li * CAP, c, lane, part);
+#pragma unroll
+    for (int i = 0; i < R; ++i) keys[cs * R + i] = part[i];
+  }
+  unsigned long long bound = 0ull;
+  if (total > p.k) bound = warp_select_k<CS * R>(keys, p.k);
+  unsigned long long* dst = p.part_keys + ((size_t)split * p.U + u) * p.k;
+  int offset = 0;
+#pragma unroll
+  for (int i = 0; i < CS * R; ++i) {
+    const bool keep = keys[i] != 0ull && keys[i] >= bound;
+    const unsigned bits = __ballot_sync(0xffffffffu, keep);
+    if (keep) dst[offset + __popc(bits & ((1u << lane) - 1u))] = keys[i] - (unsigned long long)(uint32_t)p.item_offset;
+    offset += __popc(bits);
+  }
+  for (int i = offset + lane; i < p.k; i += 32) dst[i] = 0ull;
 }
-inline int topk_nu(int D) { return D <= 256 ? 256 : 128; }
+
+inline int topk_ut(int D) { return D <= 256 ? 2 : 1; }
+inline int topk_stages(int UT, int D) {
+  const int KC = (D + 63) / 64;
+  int s = MAX_STAGES;
+  const char* e = getenv("SBR_TOPK_STAGES");  // measurement only
+  if (e) s = atoi(e);
+  const int lo = UT == 2 ? KC + 1 : 2;  // a chunk stays resident until both user tiles have consumed it
+  return s < lo ? lo : (s > MAX_STAGES ? MAX_STAGES : s);
+}
+inline size_t topk_smem_bytes(int UT, int stages) {
+  return (size_t)stages * STAGE_BYTES + 256 + (size_t)UT * UM * 4 + 1024 + 64;
+}
 inline int topk_cap(int k) {
-  int cap = ((k + 384 + 31) / 32) * 32;
-  return cap > 512 ? 512 : cap;
+  int cap = k <= 24 ? 128 : (k <= 96 ? 256 : 512);
+  const char* e = getenv("SBR_TOPK_CAP");  // measurement only
+  if (e && atoi(e) >= cap) cap = atoi(e);
+  return cap;
 }
 
 // ------------------------------------------------------------------------------------------------ merge
@@ -451,27 +613,39 @@ __global__ void metrics_kernel(const int32_t* __restrict__ topk_idx, int64_t U, 
   }
 }
 
-template <int NU>
-int launch_topk(const CUtensorMap& tmU, const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int n_splits,
-                cudaStream_t st) {
-  const size_t smem = topk_smem_bytes(NU, p.D);
+template <int UT, int R>
+int launch_topk(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int n_splits, cudaStream_t st) {
+  const size_t smem = topk_smem_bytes(UT, p.stages);
   static size_t configured = 0;
   if (smem > configured) {
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(topk_scores_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SBR_CHECK_CUDA(cudaFuncSetAttribute(topk_scores_kernel<UT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
     configured = smem;
   }
-  topk_scores_kernel<NU><<<dim3(user_tiles, n_splits), 192, smem, st>>>(tmU, tmI, p);
+  topk_scores_kernel<UT, R><<<dim3(user_tiles, n_splits), (8 * UT + 2) * 32, smem, st>>>(tmI, p);
+  SBR_LAUNCH_CHECK();
+  topk_finalize_kernel<R><<<cdiv((int64_t)n_splits * p.U, 4), 128, 0, st>>>(p, n_splits);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
+}
+
+template <int UT>
+int launch_topk_r(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int n_splits, cudaStream_t st) {
+  if (p.cap == 128) return launch_topk<UT, 4>(tmI, p, user_tiles, n_splits, st);
+  if (p.cap == 256) return launch_topk<UT, 8>(tmI, p, user_tiles, n_splits, st);
+  return launch_topk<UT, 16>(tmI, p, user_tiles, n_splits, st);
 }
 
 }  // namespace
 
 extern "C" int sbr_topk_workspace_bytes(int64_t U, int64_t I, int D, int k, int n_splits, int64_t* bytes_out) {
   SBR_REQUIRE(bytes_out && U > 0 && I > 0 && k > 0 && n_splits > 0, "sbr_topk_workspace_bytes: bad arguments");
-  const int NU = topk_nu(D);
-  const int64_t user_tiles = (U + NU - 1) / NU;
-  *bytes_out = user_tiles * NU * (int64_t)n_splits * topk_cap(k) * 8;
+  const int NU = topk_ut(D) * UM;
+  const int64_t users_padded = (U + NU - 1) / NU * NU;
+  const int64_t lists = users_padded * n_splits * CS;
+  int cap = topk_cap(k);
+  if (cap != 128 && cap != 256) cap = 512;
+  *bytes_out = lists * cap * 8 + lists * 4;
   return SBR_OK;
 }
 
@@ -482,8 +656,11 @@ extern "C" int sbr_topk_scores_masked(const void* users, int64_t ldu, const void
   SBR_REQUIRE(users && items && part_keys && workspace, "sbr_topk_scores_masked: null argument");
   SBR_REQUIRE(U > 0 && I > 0 && U < (1ll << 31) && I < (1ll << 31), "sbr_topk_scores_masked: bad U/I");
   SBR_REQUIRE(D >= 8 && D <= 512 && D % 8 == 0, "sbr_topk_scores_masked: D=%d must be a multiple of 8 in [8, 512]", D);
+  SBR_REQUIRE(ldu % 8 == 0 && ldu >= D && (reinterpret_cast<uintptr_t>(users) & 15) == 0,
+              "sbr_topk_scores_masked: user rows must be 16-byte aligned (ldu %% 8 == 0)");
   SBR_REQUIRE(k >= 1 && k <= 256, "sbr_topk_scores_masked: k=%d not in [1, 256]", k);
   SBR_REQUIRE((seen_indptr == nullptr) == (seen_indices == nullptr), "sbr_topk_scores_masked: half a CSR given");
+  SBR_REQUIRE(item_offset >= 0 && (int64_t)item_offset + I < (1ll << 32), "sbr_topk_scores_masked: bad item_offset");
   const int num_item_tiles = (int)((I + TI - 1) / TI);
   SBR_REQUIRE(n_splits >= 1 && n_splits <= num_item_tiles, "sbr_topk_scores_masked: n_splits=%d not in [1, %d]",
               n_splits, num_item_tiles);
@@ -491,26 +668,41 @@ extern "C" int sbr_topk_scores_masked(const void* users, int64_t ldu, const void
   sbr_topk_workspace_bytes(U, I, D, k, n_splits, &need);
   SBR_REQUIRE(workspace_bytes >= need, "sbr_topk_scores_masked: workspace too small (%lld < %lld)",
               (long long)workspace_bytes, (long long)need);
-  const int NU = topk_nu(D);
+  const int UT = topk_ut(D);
+  const int NU = UT * UM;
   const int user_tiles = (int)((U + NU - 1) / NU);
-  CUtensorMap tmU, tmI;
-  int rc = sbr_make_tmap_bf16_2d(&tmU, users, (uint64_t)D, (uint64_t)U, (uint64_t)ldu, 64, (uint32_t)NU);
-  if (rc) return rc;
-  rc = sbr_make_tmap_bf16_2d(&tmI, items, (uint64_t)D, (uint64_t)I, (uint64_t)ldi, 64, TI);
+  CUtensorMap tmI;
+  int rc = sbr_make_tmap_bf16_2d(&tmI, items, (uint64_t)D, (uint64_t)I, (uint64_t)ldi, 64, TI);
   if (rc) return rc;
   TopkParams p;
-  p.U = U; p.I = I; p.D = D; p.k = k; p.cap = topk_cap(k);
+  p.U = U; p.I = I; p.D = D; p.k = k; p.ldu = ldu;
+  p.cap = topk_cap(k);
+  if (p.cap != 128 && p.cap != 256) p.cap = 512;
+  p.prune_at = p.cap - W;
+  {
+    const char* e = getenv("SBR_TOPK_PRUNE_AT");  // measurement only
+    if (e && atoi(e) >= k && atoi(e) <= p.cap - W) p.prune_at = atoi(e);
+  }
+  p.users = reinterpret_cast<const bf16*>(users);
+  p.users_padded = (int64_t)user_tiles * NU;
   p.num_item_tiles = num_item_tiles;
   p.tiles_per_split = (num_item_tiles + n_splits - 1) / n_splits;
   SBR_REQUIRE((int64_t)(n_splits - 1) * p.tiles_per_split < num_item_tiles,
               "sbr_topk_scores_masked: n_splits=%d leaves an empty split for %d item tiles", n_splits, num_item_tiles);
   p.item_offset = item_offset;
+  p.stages = topk_stages(UT, D);
+  {
+    const char* dbg = getenv("SBR_TOPK_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   p.seen_indptr = seen_indptr;
   p.seen_indices = seen_indices;
   p.part_keys = reinterpret_cast<unsigned long long*>(part_keys);
-  p.cand = reinterpret_cast<unsigned long long*>(workspace);
-  if (NU == 256) return launch_topk<256>(tmU, tmI, p, user_tiles, n_splits, S(stream));
-  return launch_topk<128>(tmU, tmI, p, user_tiles, n_splits, S(stream));
+  p.cand = reinterpret_cast<uint2*>(workspace);
+  p.cand_cnt = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) +
+                                          p.users_padded * n_splits * CS * (int64_t)p.cap * 8);
+  if (UT == 2) return launch_topk_r<2>(tmI, p, user_tiles, n_splits, S(stream));
+  return launch_topk_r<1>(tmI, p, user_tiles, n_splits, S(stream));
 }
 
 extern "C" int sbr_topk_merge(const uint64_t* keys, int L, int64_t U, int k, float* out_vals, int32_t* out_idx,
