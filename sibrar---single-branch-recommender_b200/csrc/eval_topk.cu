@@ -31,7 +31,6 @@ constexpr int MAX_STAGES = 12;  // ring of item K-chunks (actual depth chosen fr
 constexpr int STAGE_BYTES = TI * 128;
 constexpr int W = 64;           // accumulator columns (items) one epilogue thread scans per tile
 constexpr int CS = TI / W;      // column slices per tile = candidate lists per user
-constexpr int A_COL0 = 256;     // first TMEM column of the user operand (accumulators live in [0, 256))
 
 struct TopkParams {
   int64_t U, I, users_padded, ldu;
@@ -165,8 +164,8 @@ __device__ __forceinline__ void prune_list(uint2* list, int count, int k, int la
     if (keep) {
       const uint32_t hi = (uint32_t)(keys[i] >> 32);
       const uint32_t raw = (hi & 0x80000000u) ? (hi & 0x7FFFFFFFu) : ~hi;
-      __stcg(list + offset + __popc(bits & ((1u << lane) - 1u)),
-             make_uint2(raw, 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull)));
+      const int dst = offset + __popc(bits & ((1u << lane) - 1u));
+      __stcg(list + dst, make_uint2(raw, 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull)));
     }
     offset += __popc(bits);
   }
@@ -174,53 +173,60 @@ __device__ __forceinline__ void prune_list(uint2* list, int count, int k, int la
   __syncwarp();
 }
 
-// one 32-column block of the accumulator: lane = user, r[c] = score of item pos0 + c.  `skip` = columns that are
-// seen items of this lane's user or lie beyond the catalogue.
-__device__ __forceinline__ void scan32(const uint32_t (&r)[32], float thr, uint32_t pos0, uint32_t skip, uint2* list,
-                                       int& cnt) {
-  float m[4];
+constexpr int ROW_PITCH = 36;  // floats per staged accumulator row (16-byte aligned, not a multiple of 32 banks)
+
+// One 32-column block of the accumulator: lane = user, r[c] = score of item pos0 + c.  `skip` = columns that are seen
+// items of this lane's user or lie beyond the catalogue.  Common path: 3-input max tree + one vote.  Otherwise the
+// lanes that hold a score >= their threshold stage their 32 scores in shared memory and the warp handles them one
+// user at a time with lane = column: one compare, one ballot and a coalesced append to that user's list.
+__device__ __forceinline__ void scan32(const uint32_t (&r)[32], float thr, uint32_t pos0, uint32_t skip,
+                                       uint2* warp_list, size_t lane_stride, float* srow, int lane, int& cnt) {
+  float m[11];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const float a = fmax3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
-    const float b = fmax3(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-    m[g] = fmaxf(fmax3(a, b, __uint_as_float(r[8 * g + 6])), __uint_as_float(r[8 * g + 7]));
+  for (int g = 0; g < 10; ++g)
+    m[g] = fmax3(__uint_as_float(r[3 * g]), __uint_as_float(r[3 * g + 1]), __uint_as_float(r[3 * g + 2]));
+  m[10] = fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+  const float a = fmax3(m[0], m[1], m[2]), b = fmax3(m[3], m[4], m[5]), c = fmax3(m[6], m[7], m[8]);
+  const float mm = fmax3(fmax3(a, b, c), m[9], m[10]);
+  const bool mine = mm >= thr;
+  unsigned flagged = __ballot_sync(0xffffffffu, mine);
+  if (flagged == 0u) return;
+  if (mine) {
+    float4* dst = reinterpret_cast<float4*>(srow + lane * ROW_PITCH);
+#pragma unroll
+    for (int v = 0; v < 8; ++v)
+      dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                           __uint_as_float(r[4 * v + 3]));
   }
-  const float mm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-  if (!__any_sync(0xffffffffu, mm >= thr)) return;
-  const bool any_skip = __any_sync(0xffffffffu, skip != 0u);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (__any_sync(0xffffffffu, m[g] >= thr)) {
-      if (!any_skip) {
-#pragma unroll
-        for (int c = 8 * g; c < 8 * g + 8; ++c) {
-          if (__uint_as_float(r[c]) >= thr) {
-            __stcg(list + cnt, make_uint2(r[c], pos0 + (uint32_t)c));
-            ++cnt;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int c = 8 * g; c < 8 * g + 8; ++c) {
-          if (__uint_as_float(r[c]) >= thr && !((skip >> c) & 1u)) {
-            __stcg(list + cnt, make_uint2(r[c], pos0 + (uint32_t)c));
-            ++cnt;
-          }
-        }
-      }
-    }
+  __syncwarp();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  while (flagged) {
+    const int L = __ffs(flagged) - 1;
+    flagged &= flagged - 1;
+    const float v = srow[L * ROW_PITCH + lane];
+    const float thrL = __shfl_sync(0xffffffffu, thr, L);
+    const uint32_t skipL = __shfl_sync(0xffffffffu, skip, L);
+    const int cntL = __shfl_sync(0xffffffffu, cnt, L);
+    const bool pass = v >= thrL && !((skipL >> lane) & 1u);
+    const unsigned bits = __ballot_sync(0xffffffffu, pass);
+    if (pass)
+      __stcg(warp_list + L * lane_stride + cntL + __popc(bits & lt_mask),
+             make_uint2(__float_as_uint(v), pos0 + (uint32_t)lane));
+    if (lane == L) cnt = cntL + __popc(bits);
   }
+  __syncwarp();
 }
 
 // UT = user tiles of 128 per CTA, R = cap / 32.  Warps [0, 8*UT) = epilogue, then TMA producer, then MMA issuer.
 // "Job" j = one [128 users x 128 items] accumulator: UT == 2: tile j / 2, user tile j % 2;  UT == 1: tile j.
-// Job j uses accumulator j % 2.
-template <int UT, int R>
+// Job j uses accumulator j % NACC (NACC = 3 when the user operand leaves room in the 512 TMEM columns).
+template <int UT, int R, int NACC>
 __global__ void __launch_bounds__((8 * UT + 2) * 32, 1)
 topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
   constexpr int NEW = 8 * UT;  // epilogue warps: 4 lane quarters x CS column slices per accumulator in flight
   constexpr int NUSERS = UT * UM;
   constexpr int CAP = 32 * R;
+  constexpr int A_COL0 = NACC * TI;  // first TMEM column of the user operand (accumulators live below it)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int KC = (p.D + 63) / 64;
@@ -229,10 +235,11 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
   uint8_t* sI = smem;  // STAGES x [128 items x 128 B]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sI + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [NACC]
+  uint64_t* tempty_bar = tfull_bar + 3;          // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 3);
   uint32_t* s_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [NUSERS] orderable bits
+  float* s_rows = reinterpret_cast<float*>(s_thr + NUSERS);  // [NEW warps][32 rows][ROW_PITCH] staged accumulator rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t u0 = (int64_t)blockIdx.x * NUSERS;
@@ -248,7 +255,7 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NACC; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 8);
     }
@@ -319,8 +326,8 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
 #pragma unroll
       for (int ut = 0; ut < UT; ++ut) {
         const int j = t * UT + ut;
-        const int a = j & 1;
-        mbar_wait(&tempty_bar[a], (uint32_t)(((j >> 1) & 1) ^ 1));
+        const int a = j % NACC;
+        mbar_wait(&tempty_bar[a], (uint32_t)(((j / NACC) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * TI);
         ss = s;
@@ -366,7 +373,8 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
     int cnt = 0;
     // cursor into the user's sorted seen row
     int64_t cur = 0, cend = 0;
-    int32_t next_seen = 0x7FFFFFFF;
+    int32_t next_seen = 0x7FFFFFFF, after_next = 0x7FFFFFFF;  // two entries ahead: the load latency stays hidden
+    float* srow = s_rows + (size_t)warp * 32 * ROW_PITCH;
     if (p.seen_indptr != nullptr && u < p.U) {
       int64_t lo = __ldg(p.seen_indptr + u), hi = __ldg(p.seen_indptr + u + 1);
       cend = hi;
@@ -378,30 +386,15 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
       }
       cur = lo;
       if (cur < cend) next_seen = __ldg(p.seen_indices + cur);
+      if (cur + 1 < cend) after_next = __ldg(p.seen_indices + cur + 1);
     }
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cs * W);
 
     for (int j = (UT == 2) ? ut : 0; j < n_jobs; j += UT) {
-      const int a = j & 1;
-      const uint32_t use = (uint32_t)(j >> 1);
+      const int a = j % NACC;
+      const uint32_t use = (uint32_t)(j / NACC);
       const int t = (UT == 2) ? (j >> 1) : j;
       const int64_t item0 = (int64_t)(tile_begin + t) * TI + cs * W;
-      // seen items / out-of-catalogue columns of this thread's 64-column slice
-      uint32_t skip0 = 0u, skip1 = 0u;
-      if (__any_sync(0xffffffffu, (int64_t)next_seen < item0 + W)) {
-        while ((int64_t)next_seen < item0 + W) {
-          const int rel = (int)((int64_t)next_seen - item0);
-          if (rel >= 32) skip1 |= 1u << (rel - 32);
-          else if (rel >= 0) skip0 |= 1u << rel;
-          ++cur;
-          next_seen = cur < cend ? __ldg(p.seen_indices + cur) : 0x7FFFFFFF;
-        }
-      }
-      if (item0 + W > p.I) {  // last tile: columns beyond the catalogue hold zeros
-        const int64_t nvalid = p.I - item0;
-        skip0 |= nvalid <= 0 ? 0xFFFFFFFFu : (nvalid >= 32 ? 0u : (0xFFFFFFFFu << nvalid));
-        skip1 |= nvalid <= 32 ? 0xFFFFFFFFu : (nvalid >= 64 ? 0u : (0xFFFFFFFFu << (nvalid - 32)));
-      }
       thr = fmaxf(thr, orderable_to_float(s_thr[ul0 + lane]));
       mbar_wait(&tfull_bar[a], use & 1);
       tc_fence_after();
@@ -411,16 +404,33 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
         tmem_ld32(lane_taddr + (uint32_t)(a * TI + 32), r1);
         tmem_ld_wait();
       }
-      // the accumulator is in registers: hand it back to the MMA warp before the scan
+      // the accumulator is in registers: hand it back to the MMA warp before anything else
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      // seen items / out-of-catalogue columns of this thread's 64-column slice
+      uint32_t skip0 = 0u, skip1 = 0u;
+      if (__any_sync(0xffffffffu, (int64_t)next_seen < item0 + W)) {
+        while ((int64_t)next_seen < item0 + W) {
+          const int rel = (int)((int64_t)next_seen - item0);
+          if (rel >= 32) skip1 |= 1u << (rel - 32);
+          else if (rel >= 0) skip0 |= 1u << rel;
+          ++cur;
+          next_seen = after_next;
+          after_next = cur + 1 < cend ? __ldg(p.seen_indices + cur + 1) : 0x7FFFFFFF;
+        }
+      }
+      if (item0 + W > p.I) {  // last tile: columns beyond the catalogue hold zeros
+        const int64_t nvalid = p.I - item0;
+        skip0 |= nvalid <= 0 ? 0xFFFFFFFFu : (nvalid >= 32 ? 0u : (0xFFFFFFFFu << nvalid));
+        skip1 |= nvalid <= 32 ? 0xFFFFFFFFu : (nvalid >= 64 ? 0u : (0xFFFFFFFFu << (nvalid - 32)));
+      }
       if (p.debug >= 1) {
         if (p.debug < 2 && r0[0] == 0x7fc12345u && r1[31] == 0x7fc54321u) cnt = 1;  // keep the loads alive
       } else {
         if (p.debug == -1) thr = INFINITY;  // measurement only: common path of the scan alone
-        scan32(r0, thr, (uint32_t)item0, skip0, my_list, cnt);
-        scan32(r1, thr, (uint32_t)item0 + 32u, skip1, my_list, cnt);
+        scan32(r0, thr, (uint32_t)item0, skip0, warp_list, LANE_STRIDE, srow, lane, cnt);
+        scan32(r1, thr, (uint32_t)item0 + 32u, skip1, warp_list, LANE_STRIDE, srow, lane, cnt);
       }
       // prune the lists that could overflow during the next tile
       unsigned need = __ballot_sync(0xffffffffu, cnt > p.prune_at);
@@ -491,14 +501,14 @@ __global__ void topk_finalize_kernel(TopkParams p, int n_splits) {
 inline int topk_ut(int D) { return D <= 256 ? 2 : 1; }
 inline int topk_stages(int UT, int D) {
   const int KC = (D + 63) / 64;
-  int s = MAX_STAGES;
+  int s = UT == 2 ? 8 : 10;
   const char* e = getenv("SBR_TOPK_STAGES");  // measurement only
   if (e) s = atoi(e);
   const int lo = UT == 2 ? KC + 1 : 2;  // a chunk stays resident until both user tiles have consumed it
   return s < lo ? lo : (s > MAX_STAGES ? MAX_STAGES : s);
 }
 inline size_t topk_smem_bytes(int UT, int stages) {
-  return (size_t)stages * STAGE_BYTES + 256 + (size_t)UT * UM * 4 + 1024 + 64;
+  return (size_t)stages * STAGE_BYTES + 256 + (size_t)UT * UM * 4 + (size_t)(8 * UT) * 32 * ROW_PITCH * 4 + 1024 + 64;
 }
 inline int topk_cap(int k) {
   int cap = k <= 24 ? 128 : (k <= 96 ? 256 : 512);
@@ -613,16 +623,28 @@ __global__ void metrics_kernel(const int32_t* __restrict__ topk_idx, int64_t U, 
   }
 }
 
-template <int UT, int R>
-int launch_topk(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int n_splits, cudaStream_t st) {
+template <int UT, int R, int NACC>
+int launch_topk_n(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int n_splits, cudaStream_t st) {
   const size_t smem = topk_smem_bytes(UT, p.stages);
   static size_t configured = 0;
   if (smem > configured) {
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(topk_scores_kernel<UT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+    SBR_CHECK_CUDA(cudaFuncSetAttribute(topk_scores_kernel<UT, R, NACC>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  topk_scores_kernel<UT, R><<<dim3(user_tiles, n_splits), (8 * UT + 2) * 32, smem, st>>>(tmI, p);
+  topk_scores_kernel<UT, R, NACC><<<dim3(user_tiles, n_splits), (8 * UT + 2) * 32, smem, st>>>(tmI, p);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+template <int UT, int R>
+int launch_topk(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int n_splits, cudaStream_t st) {
+  // a third accumulator fits next to the user operand when UT * ceil(D / 64) * 32 <= 128 TMEM columns
+  const bool three = UT == 2 && p.D <= 128 && !getenv("SBR_TOPK_NACC2");
+  int rc;
+  if (UT == 2 && three) rc = launch_topk_n<UT, R, (UT == 2 ? 3 : 2)>(tmI, p, user_tiles, n_splits, st);
+  else rc = launch_topk_n<UT, R, 2>(tmI, p, user_tiles, n_splits, st);
+  if (rc) return rc;
   SBR_LAUNCH_CHECK();
   topk_finalize_kernel<R><<<cdiv((int64_t)n_splits * p.U, 4), 128, 0, st>>>(p, n_splits);
   SBR_LAUNCH_CHECK();

@@ -4,7 +4,7 @@ with the fused AdamW, and full-catalog evaluation (representations, top-k, metri
 
 Two checkers per train step:
   (1) the numpy oracle run with ``Bf16Emulation`` -- the same arithmetic with the kernels' ROUNDING POINTS (bf16 GEMM
-      operands, fp32/fp64 everything else).  Tight: logits 1e-3, losses 1e-4 relative, every gradient within 1e-2 of
+      operands, fp32/fp64 everything else).  Tight: logits 5e-3 (one flipped bf16 rounding), losses 5e-4 relative, every gradient within 1e-2 of
       its max-abs.  This is the bug detector.
   (2) the fixture of the fp32 reference itself.  bf16 tolerances (BASELINE.json: losses <= 1e-2 relative):
       logits / representations 2e-2..3e-2 of max-abs, losses 1e-2 relative, gradient DIRECTION cosine >= 0.95 per tensor
@@ -93,8 +93,10 @@ def test_single_steps_match_reference(name):
         uu, ii, omods, onames, odrop = step_inputs(g, s)
         emu = net.train_step_fwd_bwd(p64, uu, ii, omods, onames, odrop, loss_kind=spec["rec_loss"],
                                      n_items=corpus.n_items, neg_train=spec["n_neg"], emu=O.Bf16Emulation())
-        assert _maxrel(tr.logits.cpu().numpy(), emu["logits"]) < 1e-3, f"s{s} logits vs emulated oracle"
-        assert losses["train/loss"] == pytest.approx(emu["loss"], rel=1e-4, abs=1e-6)
+        # one bf16 rounding of an activation that flips between the fp32-accumulating kernels and the fp64-accumulating
+        # emulation moves that activation by 2^-9 ~ 2e-3 relative; BatchNorm stacks pass it on to single logits
+        assert _maxrel(tr.logits.cpu().numpy(), emu["logits"]) < 5e-3, f"s{s} logits vs emulated oracle"
+        assert losses["train/loss"] == pytest.approx(emu["loss"], rel=5e-4, abs=1e-6)  # same flipped roundings
         bad = {}
         for k, gg in gold.items():
             got = tr.grads[id(params[k])].cpu().numpy()
