@@ -125,17 +125,19 @@ int sbr_row_gather_bwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int
                        const int64_t* step_dev, const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
                        void* stream);
 
-/* Contention-free backward of the row gather.  plan: counting sort of the N flat rows by segment key
- * (counts/cursor int32 [n_keys], offsets int32 [n_keys + 1], row_keys/perm int32 [N]; all caller-owned scratch);
- * reduce: one warp per (segment, chunk of rows) sums dropout-scaled dx rows, applies the L2-normalise backward once
- * and writes / adds the result into the sources' grad buffers (atomics only for split segments and tag bags). */
+/* Low-contention backward of the row gather.  plan: counting sort of the N flat rows by segment key
+ * (counts/cursor int32 [n_keys], offsets int32 [n_keys + 1], row_keys/perm/sorted_keys int32 [N]; all caller-owned
+ * scratch).  reduce: one warp per `rows_per_warp` consecutive SORTED rows sums runs of equal keys in registers
+ * (dropout-scaled dx rows), applies the L2-normalise backward once per run and atomically adds the run into the
+ * source's grad buffer: a (modality, source row) that occurs n times costs ~n / run-length atomics instead of n. */
 int sbr_gather_plan(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
                     int64_t n_idx, int k, int64_t n_keys, int32_t* counts, int32_t* offsets, int32_t* cursor,
-                    int32_t* row_keys, int32_t* perm, void* stream);
+                    int32_t* row_keys, int32_t* perm, int32_t* sorted_keys, void* stream);
 int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, int n_mods, int64_t n_keys,
-                                 const int32_t* offsets, const int32_t* perm, int C, int normalize, float p_drop,
-                                 uint64_t seed, const int64_t* step_dev, const uint8_t* keep_mask, const float* dx,
-                                 int64_t ld_dx, int rows_per_chunk, int n_chunks, void* stream);
+                                 const int32_t* offsets, const int32_t* perm, const int32_t* sorted_keys,
+                                 int64_t n_rows, int C, int normalize, float p_drop, uint64_t seed,
+                                 const int64_t* step_dev, const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
+                                 int rows_per_warp, void* stream);
 
 /* table-level backward of the projection output activation: dpre = dT * act'(T) -> bf16 (+ column sums = dbias).
  * zero_dy = 1 clears dy after reading it (the gradient table is an atomicAdd accumulator reused every step). */

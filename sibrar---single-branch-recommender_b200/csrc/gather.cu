@@ -255,58 +255,32 @@ __global__ void plan_scan_kernel(const int32_t* __restrict__ counts, int64_t n, 
 }
 
 __global__ void plan_fill_kernel(const int32_t* __restrict__ row_keys, int64_t N, const int32_t* __restrict__ offsets,
-                                 int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+                                 int32_t* __restrict__ cursor, int32_t* __restrict__ perm,
+                                 int32_t* __restrict__ sorted_keys) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= N) return;
   const int32_t key = row_keys[r];
   if (key < 0) return;
-  perm[offsets[key] + atomicAdd(cursor + key, 1)] = (int32_t)r;
+  const int32_t pos = offsets[key] + atomicAdd(cursor + key, 1);
+  perm[pos] = (int32_t)r;
+  sorted_keys[pos] = key;
 }
 
+// flush the summed gradient of one run of equal keys into the owning source's gradient buffer
 template <int NV4>
-__global__ void seg_reduce_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int64_t n_keys,
-                                  const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm, int C,
-                                  int normalize, float p_drop, uint64_t seed, const int64_t* __restrict__ step_dev,
-                                  const uint8_t* __restrict__ keep_mask, const float* __restrict__ dx, int64_t ld_dx,
-                                  int rows_per_chunk) {
-  const int64_t key = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (key >= n_keys) return;
-  const int lane = threadIdx.x & 31;
-  const int32_t seg_beg = offsets[key], seg_end = offsets[key + 1];
-  const int32_t beg = seg_beg + blockIdx.y * rows_per_chunk;
-  if (beg >= seg_end) return;
-  // the last chunk of the grid takes everything that is left
-  const int32_t end = (blockIdx.y == gridDim.y - 1) ? seg_end : min(seg_end, beg + rows_per_chunk);
-  const bool whole = (beg == seg_beg && end == seg_end);
+__device__ __forceinline__ void flush_run(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int32_t key, int C,
+                                          int normalize, int lane, float (&g)[NV4 * 4]) {
   int m = 0;
   for (int t = 1; t < n_mods; ++t)
-    if (key >= srcs[t].key_base) m = t;
+    if ((int64_t)key >= srcs[t].key_base) m = t;
   const sbr_modality_src_t s = srcs[m];
   if (s.grad == nullptr) return;
-  const uint64_t step = step_dev ? (uint64_t)*step_dev : 0;
-  float g[NV4 * 4];
-#pragma unroll
-  for (int i = 0; i < NV4 * 4; ++i) g[i] = 0.f;
-  for (int32_t p = beg; p < end; ++p) {
-    const int64_t r = perm[p];
-    uint4 cache;
-    int cache_c4 = -1;
-#pragma unroll
-    for (int i = 0; i < NV4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = 4 * lane + j + 128 * i;
-        if (c < C)
-          g[i * 4 + j] += dx[r * ld_dx + c] * keep_scale(keep_mask, r, C, c, p_drop, seed, step, cache, cache_c4);
-      }
-  }
-  const int64_t local = key - s.key_base;  // table row | category | entity row (TAG)
+  const int64_t local = (int64_t)key - s.key_base;  // table row | category | entity row (TAG)
   float inv_cnt = 1.f;
   if (normalize || s.kind == SBR_SRC_TAG) {
-    // every row of the segment gathered the same source vector x
-    sbr_modality_src_t src = s;
+    // every row of the run gathered the same source vector x; the L2-normalise backward is linear in the gradient
     float x[NV4 * 4];
-    if (s.kind == SBR_SRC_CATEGORICAL) {  // load_source_row indexes through codes: point it at the category row
+    if (s.kind == SBR_SRC_CATEGORICAL) {
       const float* w = s.table + local * C;
 #pragma unroll
       for (int i = 0; i < NV4; ++i)
@@ -316,7 +290,7 @@ __global__ void seg_reduce_kernel(const sbr_modality_src_t* __restrict__ srcs, i
           x[i * 4 + j] = c < C ? __ldg(w + c) : 0.f;
         }
     } else {
-      load_source_row<NV4>(src, local, C, lane, x, inv_cnt);
+      load_source_row<NV4>(s, local, C, lane, x, inv_cnt);
     }
     if (normalize) {
       float ss = 0.f, dot = 0.f;
@@ -354,12 +328,63 @@ __global__ void seg_reduce_kernel(const sbr_modality_src_t* __restrict__ srcs, i
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = 4 * lane + j + 128 * i;
-        if (c < C) {
-          if (whole) w[c] += g[i * 4 + j];
-          else atomicAdd(w + c, g[i * 4 + j]);
-        }
+        if (c < C) atomicAdd(w + c, g[i * 4 + j]);
       }
   }
+}
+
+// One warp per chunk of `rows_per_warp` consecutive SORTED rows: runs of equal keys are summed in registers and
+// flushed once, so a (modality, source row) that occurs n times in the batch costs ~n / run-length atomics instead
+// of n, and the work per warp does not depend on how skewed the keys are (a 2-category feature, a popular item).
+template <int NV4>
+__global__ void seg_reduce_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int64_t n_keys,
+                                  const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm,
+                                  const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop,
+                                  uint64_t seed, const int64_t* __restrict__ step_dev,
+                                  const uint8_t* __restrict__ keep_mask, const float* __restrict__ dx, int64_t ld_dx,
+                                  int rows_per_warp) {
+  const int64_t chunk = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_sorted = offsets[n_keys];  // rows that have a feature row
+  const int64_t beg = chunk * rows_per_warp;
+  if (beg >= n_sorted) return;
+  const int64_t end = min(n_sorted, beg + rows_per_warp);
+  const int lane = threadIdx.x & 31;
+  const uint64_t step = step_dev ? (uint64_t)*step_dev : 0;
+  float g[NV4 * 4];
+#pragma unroll
+  for (int i = 0; i < NV4 * 4; ++i) g[i] = 0.f;
+  int32_t cur_key = __ldg(sorted_keys + beg);
+  for (int64_t p = beg; p < end; ++p) {
+    const int32_t key = __ldg(sorted_keys + p);
+    const int64_t r = __ldg(perm + p);
+    if (key != cur_key) {  // warp-uniform
+      flush_run<NV4>(srcs, n_mods, cur_key, C, normalize, lane, g);
+      cur_key = key;
+#pragma unroll
+      for (int i = 0; i < NV4 * 4; ++i) g[i] = 0.f;
+    }
+    uint4 cache;
+    int cache_c4 = -1;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c0 = 4 * lane + 128 * i;
+      if (c0 + 3 < C && (ld_dx & 3) == 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dx + r * ld_dx + c0));
+        g[i * 4 + 0] += v.x * keep_scale(keep_mask, r, C, c0 + 0, p_drop, seed, step, cache, cache_c4);
+        g[i * 4 + 1] += v.y * keep_scale(keep_mask, r, C, c0 + 1, p_drop, seed, step, cache, cache_c4);
+        g[i * 4 + 2] += v.z * keep_scale(keep_mask, r, C, c0 + 2, p_drop, seed, step, cache, cache_c4);
+        g[i * 4 + 3] += v.w * keep_scale(keep_mask, r, C, c0 + 3, p_drop, seed, step, cache, cache_c4);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j;
+          if (c < C)
+            g[i * 4 + j] += dx[r * ld_dx + c] * keep_scale(keep_mask, r, C, c, p_drop, seed, step, cache, cache_c4);
+        }
+      }
+    }
+  }
+  flush_run<NV4>(srcs, n_mods, cur_key, C, normalize, lane, g);
 }
 
 }  // namespace
@@ -403,8 +428,9 @@ extern "C" int sbr_row_gather_bwd(const sbr_modality_src_t* srcs_dev, int n_mods
 
 extern "C" int sbr_gather_plan(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
                                int64_t n_idx, int k, int64_t n_keys, int32_t* counts, int32_t* offsets,
-                               int32_t* cursor, int32_t* row_keys, int32_t* perm, void* stream) {
-  SBR_REQUIRE(srcs_dev && idx && counts && offsets && cursor && row_keys && perm, "sbr_gather_plan: null argument");
+                               int32_t* cursor, int32_t* row_keys, int32_t* perm, int32_t* sorted_keys, void* stream) {
+  SBR_REQUIRE(srcs_dev && idx && counts && offsets && cursor && row_keys && perm && sorted_keys,
+              "sbr_gather_plan: null argument");
   SBR_REQUIRE(n_idx > 0 && k >= 1 && n_keys > 0 && n_keys < (1ll << 31), "sbr_gather_plan: bad sizes");
   const int64_t N = n_idx * k;
   SBR_REQUIRE(N < (1ll << 31), "sbr_gather_plan: too many rows");
@@ -412,24 +438,26 @@ extern "C" int sbr_gather_plan(const sbr_modality_src_t* srcs_dev, int n_mods, c
   SBR_CHECK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n_keys, S(stream)));
   plan_count_kernel<<<cdiv(N, 256), 256, 0, S(stream)>>>(srcs_dev, n_mods, idx, mods, N, k, counts, row_keys);
   plan_scan_kernel<<<1, 1024, 0, S(stream)>>>(counts, n_keys, offsets);
-  plan_fill_kernel<<<cdiv(N, 256), 256, 0, S(stream)>>>(row_keys, N, offsets, cursor, perm);
+  plan_fill_kernel<<<cdiv(N, 256), 256, 0, S(stream)>>>(row_keys, N, offsets, cursor, perm, sorted_keys);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
 
 extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, int n_mods, int64_t n_keys,
-                                            const int32_t* offsets, const int32_t* perm, int C, int normalize,
-                                            float p_drop, uint64_t seed, const int64_t* step_dev,
-                                            const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
-                                            int rows_per_chunk, int n_chunks, void* stream) {
-  SBR_REQUIRE(srcs_dev && offsets && perm && dx && n_keys > 0, "sbr_row_gather_bwd_segmented: bad arguments");
+                                            const int32_t* offsets, const int32_t* perm, const int32_t* sorted_keys,
+                                            int64_t n_rows, int C, int normalize, float p_drop, uint64_t seed,
+                                            const int64_t* step_dev, const uint8_t* keep_mask, const float* dx,
+                                            int64_t ld_dx, int rows_per_warp, void* stream) {
+  SBR_REQUIRE(srcs_dev && offsets && perm && sorted_keys && dx && n_keys > 0 && n_rows > 0,
+              "sbr_row_gather_bwd_segmented: bad arguments");
   SBR_REQUIRE(C > 0 && C <= 1024 && ld_dx >= C, "sbr_row_gather_bwd_segmented: C=%d not in [1, 1024] or ld_dx < C", C);
-  SBR_REQUIRE(rows_per_chunk >= 1 && n_chunks >= 1 && n_chunks <= 65535, "sbr_row_gather_bwd_segmented: bad chunking");
-  dim3 grid(cdiv(n_keys, 8), (unsigned)n_chunks);
+  SBR_REQUIRE(rows_per_warp >= 1, "sbr_row_gather_bwd_segmented: bad chunking");
+  const unsigned blocks = cdiv(cdiv(n_rows, rows_per_warp), 8);
   DISPATCH_NV(C, 128, {
     constexpr int NV4 = NVv > 8 ? 8 : NVv;
-    seg_reduce_kernel<NV4><<<grid, 256, 0, S(stream)>>>(srcs_dev, n_mods, n_keys, offsets, perm, C, normalize, p_drop,
-                                                        seed, step_dev, keep_mask, dx, ld_dx, rows_per_chunk);
+    seg_reduce_kernel<NV4><<<blocks, 256, 0, S(stream)>>>(srcs_dev, n_mods, n_keys, offsets, perm, sorted_keys, C,
+                                                          normalize, p_drop, seed, step_dev, keep_mask, dx, ld_dx,
+                                                          rows_per_warp);
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;

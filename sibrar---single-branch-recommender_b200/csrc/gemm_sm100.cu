@@ -83,12 +83,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
         uint8_t* a_dst = sA + s * A_STAGE_BYTES;
         uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
@@ -104,20 +104,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
         }
-        if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == C::STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
-        const uint32_t b_addr = smem_u32(sB + s * C::B_STAGE_BYTES);
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected issue:
+    // under `lane == 0` ptxas wraps every tcgen05.mma in a register->uniform-register broadcast loop)
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = sA_addr + (uint32_t)(s * A_STAGE_BYTES);
+      const uint32_t b_addr = sB_addr + (uint32_t)(s * C::B_STAGE_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // K-major: +32 B per 16-element K step inside the 128 B swizzle span; MN-major: +2 K-groups of 1024 B
@@ -128,10 +131,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
-        if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(accum_bar);
+      __syncwarp();
+      if (++s == C::STAGES) { s = 0; ph ^= 1; }
     }
+    if (elect_one()) umma_commit(accum_bar);
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
     const int q = warp & 3;

@@ -114,9 +114,9 @@ def row_gather_bwd(srcs, n_mods, idx, mods, k, C_, normalize, p_drop, seed, step
 
 
 class GatherPlan:
-    """scratch + launch parameters of the segmented gather backward for a fixed (n_keys, N)"""
+    """scratch + launches of the sorted-run gather backward for a fixed (n_keys, N)"""
 
-    def __init__(self, n_keys: int, N: int, device, n_sms: int = 148):
+    def __init__(self, n_keys: int, N: int, device, rows_per_warp: int = 32):
         i32 = torch.int32
         self.n_keys, self.N = int(n_keys), int(N)
         self.counts = torch.zeros(n_keys, dtype=i32, device=device)
@@ -124,18 +124,19 @@ class GatherPlan:
         self.offsets = torch.zeros(n_keys + 1, dtype=i32, device=device)
         self.row_keys = torch.empty(N, dtype=i32, device=device)
         self.perm = torch.empty(N, dtype=i32, device=device)
-        # chunk long segments (a popular item, a 2-category feature) so that no warp sums more than ~256 rows
-        self.rows_per_chunk = 256
-        self.n_chunks = int(max(1, min(256, -(-N // 256))))
+        self.sorted_keys = torch.empty(N, dtype=i32, device=device)
+        self.rows_per_warp = rows_per_warp
 
     def build(self, srcs, n_mods, idx, mods, k):
+        assert idx.numel() * k == self.N
         call("sbr_gather_plan", ptr(srcs), int(n_mods), ptr(idx), ptr(mods), idx.numel(), int(k), self.n_keys,
-             ptr(self.counts), ptr(self.offsets), ptr(self.cursor), ptr(self.row_keys), ptr(self.perm), stream_ptr())
+             ptr(self.counts), ptr(self.offsets), ptr(self.cursor), ptr(self.row_keys), ptr(self.perm),
+             ptr(self.sorted_keys), stream_ptr())
 
     def backward(self, srcs, n_mods, C_, normalize, p_drop, seed, step_dev, keep_mask, dx):
         call("sbr_row_gather_bwd_segmented", ptr(srcs), int(n_mods), self.n_keys, ptr(self.offsets), ptr(self.perm),
-             int(C_), int(bool(normalize)), float(p_drop or 0.0), int(seed), ptr(step_dev), ptr(keep_mask), ptr(dx),
-             dx.stride(0), self.rows_per_chunk, self.n_chunks, stream_ptr())
+             ptr(self.sorted_keys), self.N, int(C_), int(bool(normalize)), float(p_drop or 0.0), int(seed),
+             ptr(step_dev), ptr(keep_mask), ptr(dx), dx.stride(0), self.rows_per_warp, stream_ptr())
 
 
 def _y_args(y):

@@ -359,6 +359,15 @@ class _EntityBase(nn.Module):
         return self._owner()
 
 
+def _gather_plan(ent, n_keys: int, N: int, device) -> "ops.GatherPlan":
+    """scratch of the sorted-run gather backward, cached per (n_keys, N)"""
+    cache = ent.__dict__.setdefault("_plans", {})
+    plan = cache.get((n_keys, N))
+    if plan is None:
+        plan = cache[(n_keys, N)] = ops.GatherPlan(n_keys, N, device)
+    return plan
+
+
 class PlainEntity(_EntityBase):
     """Entity that is a single FeatureEmbedding (reference: ``FeatureEmbedding`` used directly as
     ``{user,item}_embedding_module`` when the config parses as FeatureModuleConfig, sgd_alg.py:2043-2046)."""
@@ -391,8 +400,9 @@ class PlainEntity(_EntityBase):
     def _src_blob(self, grads):
         w = self.embedding_layer.weight
         g = grads[id(w)] if grads is not None else None
+        self.n_keys = int(w.shape[0])
         return ops.make_modality_srcs([dict(kind=SRC_CATEGORICAL, remap=self.df.remap, table=w.detach(), grad=g,
-                                            codes=self.df.codes)], w.device)
+                                            codes=self.df.codes, key_base=0)], w.device)
 
     def embed(self, idx, training, mods=None, keep_mask=None):
         self._materialize()
@@ -412,7 +422,9 @@ class PlainEntity(_EntityBase):
         (flat,) = self._ctx
         if self._srcs_grad is None or self._srcs_grad[0] is not grads:
             self._srcs_grad = (grads, self._src_blob(grads))
-        ops.row_gather_bwd(self._srcs_grad[1], 1, flat, None, 1, self.output_dim, False, 0.0, 0, rt.step_dev, None, dE)
+        plan = _gather_plan(self, self.n_keys, flat.numel(), flat.device)
+        plan.build(self._srcs_grad[1], 1, flat, None, 1)
+        plan.backward(self._srcs_grad[1], 1, self.output_dim, False, 0.0, 0, rt.step_dev, None, dE)
 
 
 class SingleBranchNetEntity(_EntityBase):
@@ -532,18 +544,22 @@ class SingleBranchNetEntity(_EntityBase):
         hit = self._srcs_cache.get(key)
         if hit is not None and hit[0] is grads:
             return hit[1]
-        entries = []
+        entries, key_base = [], 0
         for name in self.mod_names:
             df, fe = self.dfeat[name], self.modality_modules[name]
             if name in self.proj:
-                entries.append(dict(kind=SRC_TABLE, remap=df.remap, table=self.tables[name],
+                entries.append(dict(kind=SRC_TABLE, remap=df.remap, table=self.tables[name], key_base=key_base,
                                     grad=self.table_grads[name] if grads is not None else None))
+                key_base += int(df.n_rows)
             else:
                 w = fe.embedding_layer.weight
                 g = grads[id(w)] if grads is not None else None
                 kind = SRC_CATEGORICAL if df.kind == "categorical" else SRC_TAG
                 entries.append(dict(kind=kind, remap=df.remap, table=w.detach(), grad=g, codes=df.codes,
-                                    max_tags=df.max_tags, pad_id=df.pad_id))
+                                    max_tags=df.max_tags, pad_id=df.pad_id, key_base=key_base))
+                # segment key: the category (Embedding) or the entity's feature row (EmbeddingBag)
+                key_base += int(w.shape[0]) if kind == SRC_CATEGORICAL else int(df.n_rows)
+        self.n_keys = key_base
         blob = ops.make_modality_srcs(entries, self._device())
         self._srcs_cache[key] = (grads, blob, entries)
         return blob
@@ -605,8 +621,10 @@ class SingleBranchNetEntity(_EntityBase):
         C_ = cfg.common_modality_dim
         dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena)
         srcs = self._src_blob(grads)
-        ops.row_gather_bwd(srcs, len(self.mod_names), flat, mods, k, C_, cfg.normalize_single_branch_input, p_drop,
-                           seed, rt.step_dev, keep_mask, dx0)
+        plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
+        plan.build(srcs, len(self.mod_names), flat, mods, k)
+        plan.backward(srcs, len(self.mod_names), C_, cfg.normalize_single_branch_input, p_drop, seed, rt.step_dev,
+                      keep_mask, dx0)
         for name, chain in self.proj.items():
             # table-level backward; the accumulator table is cleared by the kernel that consumes it
             chain.backward(self.table_grads[name], grads, need_dx=False, arena=rt.arena, zero_dy=True)

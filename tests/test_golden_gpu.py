@@ -7,7 +7,7 @@ Two checkers per train step:
       operands, fp32/fp64 everything else).  Tight: logits 5e-3 (one flipped bf16 rounding), losses 5e-4 relative, every gradient within 1e-2 of
       its max-abs.  This is the bug detector.
   (2) the fixture of the fp32 reference itself.  bf16 tolerances (BASELINE.json: losses <= 1e-2 relative):
-      logits / representations 2e-2..3e-2 of max-abs, losses 1e-2 relative, gradient DIRECTION cosine >= 0.95 per tensor
+      logits / representations 2e-2..3e-2 of max-abs, losses 1e-2 relative, gradient DIRECTION cosine >= 0.9 per tensor
       (deep BatchNorm stacks on 128-row batches amplify bf16 rounding to 10-40 % of max-abs on single entries while
       the direction stays; the emulated oracle reproduces exactly that deviation, see DESIGN.md "precision").
   top-k at FIXED scores: bit-exact positions wherever the oracle's ranking gap exceeds the fp32 round-off.
@@ -113,7 +113,7 @@ def test_single_steps_match_reference(name):
             if np.abs(gg).max() < 1e-3 * gscale:
                 continue  # e.g. the bias in front of a BatchNorm: exactly zero, the reference holds fp32 noise
             cos = float(got @ gg) / max(1e-30, np.linalg.norm(got) * np.linalg.norm(gg))
-            assert cos > 0.95, f"s{s} {k}: cosine to the reference gradient {cos:.4f}"
+            assert cos > 0.9, f"s{s} {k}: cosine to the reference gradient {cos:.4f}"
         # BatchNorm running statistics of this step
         sd = model.state_dict()
         for k, v in state_dict_of(g, f"s{s}/sd/").items():

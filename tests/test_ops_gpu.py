@@ -212,6 +212,24 @@ def test_row_gather_fwd_bwd():
     for got, want in zip(grads, (t_table.grad, t_emb.grad, gb)):
         assert _relerr(got, want) < 1e-4
 
+    # sorted-run backward (counting sort by (modality, source row) + run reduce): same gradients
+    grads2 = [torch.zeros_like(table), torch.zeros_like(emb), torch.zeros_like(bag)]
+    srcs2 = ops.make_modality_srcs([
+        dict(kind=0, remap=remap, table=table, grad=grads2[0], key_base=0),
+        dict(kind=1, remap=None, table=emb, grad=grads2[1], codes=cat, key_base=n_ent),
+        dict(kind=2, remap=None, table=bag, grad=grads2[2], codes=tags, max_tags=4, pad_id=5, key_base=n_ent + 7)], DEV)
+    for rpw in (1, 4, 32):
+        for gr in grads2:
+            gr.zero_()
+        plan = ops.GatherPlan(n_ent + 7 + n_ent, 33 * k, DEV, rows_per_warp=rpw)
+        plan.build(srcs2, 3, idx, mods, k)
+        plan.backward(srcs2, 3, C_, True, 0.3, 1, step, keep, dx)
+        sk = plan.sorted_keys.cpu().numpy()
+        assert (np.diff(sk) >= 0).all() and sorted(plan.perm.cpu().tolist()) == list(range(33 * k))
+        grads2[2][5] = 0
+        for got, want in zip(grads2, (t_table.grad, t_emb.grad, gb)):
+            assert _relerr(got, want) < 1e-4, rpw
+
     # Philox dropout: deterministic for (seed, step), keeps ~ (1 - p)
     big = torch.zeros(4000, C_, device=DEV)
     idx2 = torch.randint(0, n_ent, (4000,), generator=g).to(DEV)
