@@ -46,6 +46,53 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// activation with the (warp-uniform) switch hoisted out of the element loop
+__device__ __forceinline__ void apply_act32(int act, float (&v)[32]) {
+  switch (act) {
+    case SBR_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case SBR_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+      break;
+    case SBR_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+      break;
+    case SBR_ACT_SELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = 1.0507009873554805f * (v[j] > 0.f ? v[j] : 1.6732632423543772f * (__expf(v[j]) - 1.f));
+      break;
+    default: break;
+  }
+}
+// v[j] *= act'(y[j]) expressed through the saved output y
+__device__ __forceinline__ void apply_actgrad32(int act, float (&v)[32], const float (&y)[32]) {
+  switch (act) {
+    case SBR_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = y[j] > 0.f ? v[j] : 0.f;
+      break;
+    case SBR_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= 1.f - y[j] * y[j];
+      break;
+    case SBR_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= y[j] * (1.f - y[j]);
+      break;
+    case SBR_ACT_SELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] *= y[j] > 0.f ? 1.0507009873554805f : y[j] + 1.0507009873554805f * 1.6732632423543772f;
+      break;
+    default: break;
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(192)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
@@ -56,12 +103,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + C::STAGES * C::B_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* accum_bar = empty_bar + C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + C::STAGES;  // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
+  // persistent over the M tiles: CTA x handles tiles x, x + gridDim.x, ...; the two TMEM accumulators let the MMA of
+  // tile t+1 run while the epilogue warps drain tile t (skinny layers are bound by the epilogue's HBM traffic)
+  const int num_m_tiles = (int)((p.M + BM - 1) / BM);
   const int n0 = blockIdx.y * BN;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
@@ -73,10 +123,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -86,27 +139,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
     int s = 0;
     uint32_t ph = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
-        uint8_t* a_dst = sA + s * A_STAGE_BYTES;
-        uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
-        if (!p.a_mn) {
-          tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-        } else {
+    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
+      const int m0 = tile * BM;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
+          uint8_t* a_dst = sA + s * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
+          if (!p.a_mn) {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full_bar[s], m0 + j * 64, kb * BK);
-        }
-        if (!p.b_mn) {
-          tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
-        } else {
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full_bar[s], m0 + j * 64, kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+          }
         }
+        __syncwarp();
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == C::STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp, elected issue:
@@ -115,36 +171,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     int s = 0;
     uint32_t ph = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      mbar_wait(&full_bar[s], ph);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
       tc_fence_after();
-      const uint32_t a_addr = sA_addr + (uint32_t)(s * A_STAGE_BYTES);
-      const uint32_t b_addr = sB_addr + (uint32_t)(s * C::B_STAGE_BYTES);
-      if (elect_one()) {
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = sA_addr + (uint32_t)(s * A_STAGE_BYTES);
+        const uint32_t b_addr = sB_addr + (uint32_t)(s * C::B_STAGE_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: +32 B per 16-element K step inside the 128 B swizzle span; MN-major: +2 K-groups of 1024 B
-          const uint64_t adesc = p.a_mn ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
-                                        : umma_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bdesc = p.b_mn ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: +32 B per 16-element K step inside the 128 B swizzle span; MN-major: +2 K-groups of 1024 B
+            const uint64_t adesc = p.a_mn ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                          : umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = p.b_mn ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                          : umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        __syncwarp();
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull_bar[acc]);
       __syncwarp();
-      if (++s == C::STAGES) { s = 0; ph ^= 1; }
     }
-    if (elect_one()) umma_commit(accum_bar);
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
-    const int64_t row = (int64_t)m0 + row_in_tile;
-    const bool row_ok = row < p.M;
     const sbr_gemm_epilogue_t& ep = p.ep;
-    mbar_wait(accum_bar, 0);
+    float cs_acc[BN / 32], cq_acc[BN / 32];  // lane l: partial column statistics of column 32 * i + l
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) cs_acc[i] = cq_acc[i] = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+    const int acc = it & 1;
+    const int64_t row = (int64_t)tile * BM + row_in_tile;
+    const bool row_ok = row < p.M;
+    mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
     tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -152,35 +221,47 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (col0 >= p.N) break;  // warp-uniform
       uint32_t r[32];
       __syncwarp();
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
       tmem_ld_wait();
+      const bool full_cols = col0 + 32 <= p.N;
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * ep.alpha;
-        if (ep.bias != nullptr && col0 + j < p.N) x += __ldg(ep.bias + col0 + j);
-        v[j] = x;
-      }
-      if (ep.act != SBR_ACT_NONE) {
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+      if (ep.bias != nullptr) {
+        if (full_cols && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = act_fwd(ep.act, v[j]);
-      }
-      const bool full_cols = col0 + 32 <= p.N;
-      if (ep.actgrad_y != nullptr && row_ok) {
-        const bf16* y = reinterpret_cast<const bf16*>(ep.actgrad_y) + row * ep.ld_actgrad + col0;
-        if (full_cols && (ep.ld_actgrad % 8 == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u = __ldg(reinterpret_cast<const uint4*>(y + j));
-            const bf16* yb = reinterpret_cast<const bf16*>(&u);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[j + t] *= act_grad_from_out(ep.actgrad_act, __bfloat162float(yb[t]));
+          for (int j = 0; j < 32; j += 4) {  // same address in every lane: one broadcast transaction each
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] *= act_grad_from_out(ep.actgrad_act, __bfloat162float(y[j]));
+            if (col0 + j < p.N) v[j] += __ldg(ep.bias + col0 + j);
         }
+      }
+      if (ep.act != SBR_ACT_NONE) apply_act32(ep.act, v);
+      if (ep.actgrad_y != nullptr) {
+        float yv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) yv[j] = 1.f;  // rows / columns outside the matrix: derivative value irrelevant
+        if (row_ok) {
+          const bf16* y = reinterpret_cast<const bf16*>(ep.actgrad_y) + row * ep.ld_actgrad + col0;
+          if (full_cols && (ep.ld_actgrad % 8 == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u = __ldg(reinterpret_cast<const uint4*>(y + j));
+              const bf16* yb = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) yv[j + t] = __bfloat162float(yb[t]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) yv[j] = __bfloat162float(y[j]);
+          }
+        }
+        apply_actgrad32(ep.actgrad_act, v, yv);
       }
       if (ep.colstats != nullptr) {
         float s1[32], s2[32];
@@ -190,12 +271,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s1[j] = x;
           s2[j] = x * x;
         }
-        float cs = warp_colsum32(s1, lane);
-        if (col0 + lane < p.N) atomicAdd(ep.colstats + col0 + lane, cs);
-        if (!ep.colstats_sum_only) {
-          float cq = warp_colsum32(s2, lane);
-          if (col0 + lane < p.N) atomicAdd(ep.colstats + p.N + col0 + lane, cq);
-        }
+        // accumulated over all tiles of this CTA; flushed with one atomic per column after the tile loop
+        cs_acc[c0 / 32] += warp_colsum32(s1, lane);
+        if (!ep.colstats_sum_only) cq_acc[c0 / 32] += warp_colsum32(s2, lane);
       }
       if (ep.transpose_out) {
         // out_f32 is [N, M]: for a fixed column the 32 lanes hit 32 consecutive floats
@@ -245,13 +323,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+    // this warp is done with the accumulator
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }  // tile loop
+    if (ep.colstats != nullptr) {
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int64_t col = (int64_t)n0 + 32 * i + lane;
+        if (col < p.N) {
+          atomicAdd(ep.colstats + col, cs_acc[i]);
+          if (!ep.colstats_sum_only) atomicAdd(ep.colstats + p.N + col, cq_acc[i]);
+        }
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN < 32 ? 32 : 2 * BN);
   }
 }
 
@@ -263,7 +356,11 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
                                         Cfg<BN>::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN), (unsigned)splits);
+  const int64_t m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int64_t ctas_per_sm = BN == 256 ? 1 : 2;  // 2 x BN TMEM columns and the operand ring per CTA
+  int64_t gx = (sbr_num_sms() * ctas_per_sm) / (n_tiles * splits);
+  gx = gx < 1 ? 1 : (gx > m_tiles ? m_tiles : gx);
+  dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);
   gemm_bf16_kernel<BN><<<grid, 192, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
   SBR_LAUNCH_CHECK();
   return SBR_OK;

@@ -153,6 +153,105 @@ __global__ void score_loss_kernel(const float* __restrict__ eu, const float* __r
   }
 }
 
+// Fast path (one modality slot per entity, D in {16, 32, 64, 128}): LPR = D / 4 lanes hold one row as float4, so one
+// load instruction covers 32 / LPR item rows; the block's loss goes out with one atomic.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ ei, int64_t B, int n, int loss_kind,
+                       float inv_cnt, float ssm_shift, float* __restrict__ logits, double* __restrict__ loss_acc,
+                       float* __restrict__ deu, float* __restrict__ dei) {
+  constexpr int D = 4 * LPR;
+  constexpr int RPP = 32 / LPR;  // item rows per pass
+  extern __shared__ float sh[];  // per warp: n scores + n grads; then one loss slot per warp
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int64_t b = blockIdx.x * (int64_t)nw + wib;
+  float* sc = sh + (size_t)wib * 2 * n;
+  float* gr = sc + n;
+  float* s_loss = sh + (size_t)nw * 2 * n;
+  const int sub = lane / LPR, li = lane % LPR;
+  float lsum = 0.f;
+  if (b < B) {
+    const float4 u4 = __ldg(reinterpret_cast<const float4*>(eu + b * D) + li);
+    const float4* items = reinterpret_cast<const float4*>(ei + b * n * D);
+    for (int j0 = 0; j0 < n; j0 += RPP) {
+      const int j = j0 + sub;
+      float dot = 0.f;
+      if (j < n) {
+        const float4 v = __ldg(items + (size_t)j * LPR + li);
+        dot = u4.x * v.x + u4.y * v.y + u4.z * v.z + u4.w * v.w;
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (li == 0 && j < n) sc[j] = dot;
+    }
+    __syncwarp();
+    if (loss_kind == SBR_LOSS_BPR) {
+      float s0 = sc[0], g0 = 0.f;
+      for (int j = 1 + lane; j < n; j += 32) {
+        float d = s0 - sc[j];
+        lsum += (d > 0.f ? log1pf(__expf(-d)) : -d + log1pf(__expf(d)));
+        float sg = 1.f / (1.f + __expf(d));  // sigmoid(-d)
+        gr[j] = sg * inv_cnt;
+        g0 -= sg * inv_cnt;
+      }
+      g0 = warp_sum(g0);
+      if (lane == 0) gr[0] = g0;
+    } else if (loss_kind == SBR_LOSS_BCE) {
+      for (int j = lane; j < n; j += 32) {
+        float s = sc[j], y = (j == 0) ? 1.f : 0.f;
+        lsum += (s > 0.f ? s + log1pf(__expf(-s)) : log1pf(__expf(s))) - y * s;
+        gr[j] = (1.f / (1.f + __expf(-s)) - y) * inv_cnt;
+      }
+    } else {
+      float mx = -INFINITY;
+      for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sc[j] + (j > 0 ? ssm_shift : 0.f));
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int j = lane; j < n; j += 32) se += __expf(sc[j] + (j > 0 ? ssm_shift : 0.f) - mx);
+      se = warp_sum(se);
+      float lse = mx + logf(se);
+      for (int j = lane; j < n; j += 32) {
+        float zj = sc[j] + (j > 0 ? ssm_shift : 0.f);
+        gr[j] = (__expf(zj - lse) - (j == 0 ? 1.f : 0.f)) * inv_cnt;
+      }
+      if (lane == 0) lsum = lse - sc[0];
+    }
+    lsum = warp_sum(lsum);
+    if (logits) {
+      for (int j = lane; j < n; j += 32) logits[b * n + j] = sc[j];
+    }
+    __syncwarp();
+    if (deu != nullptr && dei != nullptr) {
+      float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4* dit = reinterpret_cast<float4*>(dei + b * n * D);
+      for (int j0 = 0; j0 < n; j0 += RPP) {
+        const int j = j0 + sub;
+        if (j < n) {
+          const float g = gr[j];
+          const float4 v = __ldg(items + (size_t)j * LPR + li);
+          du.x += g * v.x; du.y += g * v.y; du.z += g * v.z; du.w += g * v.w;
+          dit[(size_t)j * LPR + li] = make_float4(g * u4.x, g * u4.y, g * u4.z, g * u4.w);
+        }
+      }
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        du.x += __shfl_xor_sync(0xffffffffu, du.x, o);
+        du.y += __shfl_xor_sync(0xffffffffu, du.y, o);
+        du.z += __shfl_xor_sync(0xffffffffu, du.z, o);
+        du.w += __shfl_xor_sync(0xffffffffu, du.w, o);
+      }
+      if (sub == 0) reinterpret_cast<float4*>(deu + b * D)[li] = du;
+    }
+  }
+  if (lane == 0) s_loss[wib] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_acc) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += (double)s_loss[w];
+    atomicAdd(loss_acc, t * (double)inv_cnt);
+  }
+}
+
 __global__ void aggregate_kernel(const float* __restrict__ e, int64_t rows, int k, int D, int agg_max,
                                  float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int64_t ld_bf16) {
   int64_t total = rows * D;
@@ -185,6 +284,25 @@ extern "C" int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n
   double cnt = 1.0;
   if (!aggregator_sum)
     cnt = loss_kind == SBR_LOSS_BPR ? (double)B * (n - 1) : (loss_kind == SBR_LOSS_BCE ? (double)B * n : (double)B);
+  const float inv = (float)(1.0 / cnt);
+  if (ku == 1 && ki == 1 && u_agg == nullptr && i_agg == nullptr && (D == 16 || D == 32 || D == 64 || D == 128) &&
+      (reinterpret_cast<uintptr_t>(eu) & 15) == 0 && (reinterpret_cast<uintptr_t>(ei) & 15) == 0 &&
+      (deu == nullptr || (reinterpret_cast<uintptr_t>(deu) & 15) == 0) &&
+      (dei == nullptr || (reinterpret_cast<uintptr_t>(dei) & 15) == 0)) {
+    const int nw = 8;
+    const size_t sm = ((size_t)nw * 2 * n + nw) * sizeof(float);
+    const unsigned blocks = cdiv(B, nw);
+#define SBR_FAST(LPR_)                                                                                              \
+  score_loss_fast_kernel<LPR_><<<blocks, nw * 32, sm, S(stream)>>>(eu, ei, B, n, loss_kind, inv, ssm_shift, logits, \
+                                                                   loss_acc, deu, dei)
+    if (D == 16) SBR_FAST(4);
+    else if (D == 32) SBR_FAST(8);
+    else if (D == 64) SBR_FAST(16);
+    else SBR_FAST(32);
+#undef SBR_FAST
+    SBR_LAUNCH_CHECK();
+    return SBR_OK;
+  }
   const int wpb = 4;
   size_t shmem = (size_t)wpb * 2 * n * sizeof(float);
   DISPATCH_NV(D, 32, score_loss_kernel<NVv><<<cdiv(B, wpb), wpb * 32, shmem, S(stream)>>>(
