@@ -62,62 +62,314 @@ __device__ __forceinline__ void load_source_row(const sbr_modality_src_t& s, int
   }
 }
 
+// Dropout keep decision of element (row r, column c): explicit mask, or 16 random bits of the Philox block of the
+// 8-column group c / 8 (one Philox call serves 8 elements; keep iff bits >= p * 65536).
+__device__ __forceinline__ uint32_t drop_threshold(float p_drop) { return (uint32_t)ceilf(p_drop * 65536.f); }
+__device__ __forceinline__ uint4 philox_group(int64_t r, int c8, uint64_t seed, uint64_t step) {
+  return philox4x32(make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)c8, 0x64726f70u),
+                    make_uint2((uint32_t)seed ^ (uint32_t)step, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
+}
+__device__ __forceinline__ uint32_t philox_lane16(const uint4& blk, int j) {  // j in [0, 8)
+  const uint32_t w = (j >> 1) == 0 ? blk.x : ((j >> 1) == 1 ? blk.y : ((j >> 1) == 2 ? blk.z : blk.w));
+  return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
 __device__ __forceinline__ float keep_scale(const uint8_t* keep_mask, int64_t r, int C, int c, float p_drop,
-                                            uint64_t seed, uint64_t step, uint4& cache, int& cache_c4) {
+                                            uint64_t seed, uint64_t step, uint4& cache, int& cache_c8) {
   if (p_drop <= 0.f) return 1.f;
   const float sc = 1.f / (1.f - p_drop);
   if (keep_mask != nullptr) return keep_mask[r * C + c] ? sc : 0.f;
-  int c4 = c >> 2;
-  if (c4 != cache_c4) {
-    cache = philox4x32(make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)c4, 0x64726f70u),
-                       make_uint2((uint32_t)seed ^ (uint32_t)step, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
-    cache_c4 = c4;
+  const int c8 = c >> 3;
+  if (c8 != cache_c8) {
+    cache = philox_group(r, c8, seed, step);
+    cache_c8 = c8;
   }
-  uint32_t bits = (c & 3) == 0 ? cache.x : ((c & 3) == 1 ? cache.y : ((c & 3) == 2 ? cache.z : cache.w));
-  return u32_to_unit(bits) >= p_drop ? sc : 0.f;
+  return philox_lane16(cache, c & 7) >= drop_threshold(p_drop) ? sc : 0.f;
+}
+// 8-bit keep mask of columns c0 .. c0+7 (c0 % 8 == 0)
+__device__ __forceinline__ uint32_t keep8(const uint8_t* keep_mask, int64_t r, int C, int c0, float p_drop,
+                                          uint64_t seed, uint64_t step) {
+  if (p_drop <= 0.f) return 0xFFu;
+  uint32_t m = 0;
+  if (keep_mask != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < C && keep_mask[r * C + c0 + j]) m |= 1u << j;
+    return m;
+  }
+  const uint4 blk = philox_group(r, c0 >> 3, seed, step);
+  const uint32_t thr = drop_threshold(p_drop);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (philox_lane16(blk, j) >= thr) m |= 1u << j;
+  return m;
 }
 
-template <int NV4>
-__global__ void row_gather_fwd_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
-                                      const int64_t* __restrict__ idx, const uint8_t* __restrict__ mods, int64_t N,
-                                      int k, int C, int normalize, float p_drop, uint64_t seed,
-                                      const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
-                                      bf16* __restrict__ out, int64_t ld_out, float* __restrict__ out_f32,
-                                      int64_t ld_f32, int32_t* err_flag) {
-  int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= N) return;
-  const int lane = threadIdx.x & 31;
+// ------------------------------------------------------------------------------------------------ group kernels
+// A "group" of LPR lanes owns one row; lane li of the group owns the 8 contiguous elements c = 8*li + 8*LPR*i + j
+// (j < 8, i < NV): 32-byte loads, all lanes busy whatever C is (C = 64 -> 8 lanes per row, 4 rows per warp).
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int LPR>
+__device__ __forceinline__ float group_sum_masked(float v, unsigned mask) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void load8(const float* __restrict__ p, int c, int C, bool vec_ok, float (&x)[8]) {
+  if (vec_ok && c + 8 <= C) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + c + 4));
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (c + j < C) ? __ldg(p + c + j) : 0.f;
+  }
+}
+
+// x = source row of (modality src, feature row) in the group layout; inv_cnt = 1 / #tags for TAG sources
+template <int LPR, int NV>
+__device__ __forceinline__ void load_source_row_g(const sbr_modality_src_t& s, int64_t feat_row, int C, int li,
+                                                  float (&x)[NV * 8], float& inv_cnt) {
+#pragma unroll
+  for (int i = 0; i < NV * 8; ++i) x[i] = 0.f;
+  inv_cnt = 1.f;
+  if (feat_row < 0) return;
+  const bool vec_ok = (C & 3) == 0;
+  if (s.kind == SBR_SRC_TAG) {
+    int cnt = 0;
+    for (int t = 0; t < s.max_tags; ++t) {
+      const int32_t tag = __ldg(s.codes + feat_row * s.max_tags + t);
+      if (tag == s.pad_id) continue;
+      ++cnt;
+      const float* w = s.table + (int64_t)tag * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[8];
+        load8(w, 8 * li + 8 * LPR * i, C, vec_ok, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[i * 8 + j] += v[j];
+      }
+    }
+    inv_cnt = 1.f / (float)max(cnt, 1);
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) x[i] *= inv_cnt;
+  } else {
+    const int64_t src_row = (s.kind == SBR_SRC_CATEGORICAL) ? (int64_t)__ldg(s.codes + feat_row) : feat_row;
+    const float* w = s.table + src_row * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float v[8];
+      load8(w, 8 * li + 8 * LPR * i, C, vec_ok, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[i * 8 + j] = v[j];
+    }
+  }
+}
+
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256)
+row_gather_fwd_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, const int64_t* __restrict__ idx,
+                        const uint8_t* __restrict__ mods, int64_t N, int k, int C, int normalize, float p_drop,
+                        uint64_t seed, const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
+                        bf16* __restrict__ out, int64_t ld_out, float* __restrict__ out_f32, int64_t ld_f32,
+                        int32_t* err_flag) {
+  const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+  const int li = threadIdx.x % LPR;
+  const bool valid = gid < N;
+  const int64_t r = valid ? gid : N - 1;  // keep every lane alive for the group shuffles
   const int m = mods ? (int)mods[r] : 0;
   const sbr_modality_src_t s = srcs[min(m, n_mods - 1)];
   const int64_t e = idx[r / k];
-  int64_t feat_row = s.remap ? (int64_t)__ldg(s.remap + e) : e;
-  if (feat_row < 0 && lane == 0 && err_flag) atomicExch(err_flag, 1);
-  float x[NV4 * 4], inv_cnt;
-  load_source_row<NV4>(s, feat_row, C, lane, x, inv_cnt);
+  const int64_t feat_row = s.remap ? (int64_t)__ldg(s.remap + e) : e;
+  if (feat_row < 0 && li == 0 && valid && err_flag) atomicExch(err_flag, 1);
+  float x[NV * 8], inv_cnt;
+  load_source_row_g<LPR, NV>(s, feat_row, C, li, x, inv_cnt);
   if (normalize) {
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV4 * 4; ++i) ss += x[i] * x[i];
-    ss = warp_sum(ss);
-    float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int i = 0; i < NV * 8; ++i) ss += x[i] * x[i];
+    ss = group_sum<LPR>(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-    for (int i = 0; i < NV4 * 4; ++i) x[i] *= inv;
+    for (int i = 0; i < NV * 8; ++i) x[i] *= inv;
   }
+  if (!valid) return;
   const uint64_t step = step_dev ? (uint64_t)*step_dev : 0;
-  uint4 cache;
-  int cache_c4 = -1;
+  const float sc = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
 #pragma unroll
-  for (int i = 0; i < NV4; ++i)
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = 8 * li + 8 * LPR * i;
+    if (c0 >= C) continue;
+    const uint32_t km = keep8(keep_mask, r, C, c0, p_drop, seed, step);
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int c = 4 * lane + j + 128 * i;
-      if (c < C) {
-        float v = x[i * 4 + j] * keep_scale(keep_mask, r, C, c, p_drop, seed, step, cache, cache_c4);
-        if (out) out[r * ld_out + c] = __float2bfloat16(v);
-        if (out_f32) out_f32[r * ld_f32 + c] = v;
+    for (int j = 0; j < 8; ++j) v[j] = ((km >> j) & 1u) ? x[i * 8 + j] * sc : 0.f;
+    if (out) {
+      bf16* dst = out + r * ld_out + c0;
+      if (c0 + 8 <= C && (ld_out & 7) == 0) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+        *reinterpret_cast<uint4*>(dst) = u;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < C) dst[j] = __float2bfloat16(v[j]);
       }
     }
+    if (out_f32) {
+      float* dst = out_f32 + r * ld_f32 + c0;
+      if (c0 + 8 <= C && (ld_f32 & 3) == 0) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < C) dst[j] = v[j];
+      }
+    }
+  }
 }
+
+// flush the summed gradient of one run of equal keys (group layout) into the owning source's gradient buffer
+template <int LPR, int NV>
+__device__ __forceinline__ void flush_run_g(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int32_t key, int C,
+                                            int normalize, int li, unsigned gmask, float (&g)[NV * 8]) {
+  int m = 0;
+  for (int t = 1; t < n_mods; ++t)
+    if ((int64_t)key >= srcs[t].key_base) m = t;
+  const sbr_modality_src_t s = srcs[m];
+  if (s.grad == nullptr) return;
+  const int64_t local = (int64_t)key - s.key_base;  // table row | category | entity row (TAG)
+  float inv_cnt = 1.f;
+  if (normalize || s.kind == SBR_SRC_TAG) {
+    // every row of the run gathered the same source vector x; the L2-normalise backward is linear in the gradient
+    float x[NV * 8];
+    if (s.kind == SBR_SRC_CATEGORICAL) {
+      const float* w = s.table + local * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[8];
+        load8(w, 8 * li + 8 * LPR * i, C, (C & 3) == 0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[i * 8 + j] = v[j];
+      }
+    } else {
+      load_source_row_g<LPR, NV>(s, local, C, li, x, inv_cnt);
+    }
+    if (normalize) {
+      float ss = 0.f, dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV * 8; ++i) ss += x[i] * x[i];
+      ss = group_sum_masked<LPR>(ss, gmask);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < NV * 8; ++i) {
+        x[i] *= inv;
+        dot += x[i] * g[i];
+      }
+      dot = group_sum_masked<LPR>(dot, gmask);
+#pragma unroll
+      for (int i = 0; i < NV * 8; ++i) g[i] = (g[i] - x[i] * dot) * inv;
+    }
+  }
+  if (s.kind == SBR_SRC_TAG) {
+    for (int t = 0; t < s.max_tags; ++t) {
+      const int32_t tag = __ldg(s.codes + local * s.max_tags + t);
+      if (tag == s.pad_id) continue;
+      float* w = s.grad + (int64_t)tag * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = 8 * li + 8 * LPR * i + j;
+          if (c < C) atomicAdd(w + c, g[i * 8 + j] * inv_cnt);
+        }
+    }
+  } else {
+    float* w = s.grad + local * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = 8 * li + 8 * LPR * i + j;
+        if (c < C) atomicAdd(w + c, g[i * 8 + j]);
+      }
+  }
+}
+
+// One GROUP per chunk of `rows_per_group` consecutive SORTED rows: runs of equal keys are summed in registers and
+// flushed once, so a (modality, source row) that occurs n times in the batch costs ~n / run-length atomics instead
+// of n, and the work per group does not depend on how skewed the keys are (a 2-category feature, a popular item).
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256)
+seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int64_t n_keys,
+                    const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm,
+                    const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop, uint64_t seed,
+                    const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
+                    const float* __restrict__ dx, int64_t ld_dx, int rows_per_group) {
+  const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+  const int li = threadIdx.x % LPR;
+  const int lane = threadIdx.x & 31;
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (lane / LPR * LPR));
+  const int64_t n_sorted = offsets[n_keys];  // rows that have a feature row
+  const int64_t beg = chunk * rows_per_group;
+  if (beg >= n_sorted) return;
+  const int64_t end = min(n_sorted, beg + rows_per_group);
+  const uint64_t step = step_dev ? (uint64_t)*step_dev : 0;
+  const float sc = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const bool vec_ok = (ld_dx & 3) == 0;
+  float g[NV * 8];
+#pragma unroll
+  for (int i = 0; i < NV * 8; ++i) g[i] = 0.f;
+  int32_t cur_key = __ldg(sorted_keys + beg);
+  int32_t key_n = cur_key;
+  int64_t r_n = __ldg(perm + beg);
+  for (int64_t p = beg; p < end; ++p) {
+    const int32_t key = key_n;
+    const int64_t r = r_n;
+    if (p + 1 < end) {  // the next row's indices are in flight while this row is summed
+      key_n = __ldg(sorted_keys + p + 1);
+      r_n = __ldg(perm + p + 1);
+    }
+    if (key != cur_key) {  // group-uniform
+      flush_run_g<LPR, NV>(srcs, n_mods, cur_key, C, normalize, li, gmask, g);
+      cur_key = key;
+#pragma unroll
+      for (int i = 0; i < NV * 8; ++i) g[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = 8 * li + 8 * LPR * i;
+      if (c0 >= C) continue;
+      float v[8];
+      load8(dx + r * ld_dx, c0, C, vec_ok, v);
+      const uint32_t km = keep8(keep_mask, r, C, c0, p_drop, seed, step);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[i * 8 + j] += ((km >> j) & 1u) ? v[j] * sc : 0.f;
+    }
+  }
+  flush_run_g<LPR, NV>(srcs, n_mods, cur_key, C, normalize, li, gmask, g);
+}
+
+// lanes per row / 8-element vectors per lane for a row of C elements
+#define DISPATCH_GROUP(C_, ...)                                                        \
+  do {                                                                                 \
+    if ((C_) <= 8) { constexpr int LPRv = 1, NVg = 1; __VA_ARGS__; }                   \
+    else if ((C_) <= 16) { constexpr int LPRv = 2, NVg = 1; __VA_ARGS__; }             \
+    else if ((C_) <= 32) { constexpr int LPRv = 4, NVg = 1; __VA_ARGS__; }             \
+    else if ((C_) <= 64) { constexpr int LPRv = 8, NVg = 1; __VA_ARGS__; }             \
+    else if ((C_) <= 128) { constexpr int LPRv = 16, NVg = 1; __VA_ARGS__; }           \
+    else if ((C_) <= 256) { constexpr int LPRv = 32, NVg = 1; __VA_ARGS__; }           \
+    else if ((C_) <= 512) { constexpr int LPRv = 32, NVg = 2; __VA_ARGS__; }           \
+    else { constexpr int LPRv = 32, NVg = 4; __VA_ARGS__; }                            \
+  } while (0)
 
 template <int NV4>
 __global__ void row_gather_bwd_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
@@ -266,127 +518,6 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ row_keys, int64_t N
   sorted_keys[pos] = key;
 }
 
-// flush the summed gradient of one run of equal keys into the owning source's gradient buffer
-template <int NV4>
-__device__ __forceinline__ void flush_run(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int32_t key, int C,
-                                          int normalize, int lane, float (&g)[NV4 * 4]) {
-  int m = 0;
-  for (int t = 1; t < n_mods; ++t)
-    if ((int64_t)key >= srcs[t].key_base) m = t;
-  const sbr_modality_src_t s = srcs[m];
-  if (s.grad == nullptr) return;
-  const int64_t local = (int64_t)key - s.key_base;  // table row | category | entity row (TAG)
-  float inv_cnt = 1.f;
-  if (normalize || s.kind == SBR_SRC_TAG) {
-    // every row of the run gathered the same source vector x; the L2-normalise backward is linear in the gradient
-    float x[NV4 * 4];
-    if (s.kind == SBR_SRC_CATEGORICAL) {
-      const float* w = s.table + local * C;
-#pragma unroll
-      for (int i = 0; i < NV4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = 4 * lane + j + 128 * i;
-          x[i * 4 + j] = c < C ? __ldg(w + c) : 0.f;
-        }
-    } else {
-      load_source_row<NV4>(s, local, C, lane, x, inv_cnt);
-    }
-    if (normalize) {
-      float ss = 0.f, dot = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV4 * 4; ++i) ss += x[i] * x[i];
-      ss = warp_sum(ss);
-      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-      for (int i = 0; i < NV4 * 4; ++i) {
-        x[i] *= inv;
-        dot += x[i] * g[i];
-      }
-      dot = warp_sum(dot);
-#pragma unroll
-      for (int i = 0; i < NV4 * 4; ++i) g[i] = (g[i] - x[i] * dot) * inv;
-    }
-  }
-  if (s.kind == SBR_SRC_TAG) {
-    for (int t = 0; t < s.max_tags; ++t) {
-      const int32_t tag = __ldg(s.codes + local * s.max_tags + t);
-      if (tag == s.pad_id) continue;
-      float* w = s.grad + (int64_t)tag * C;
-#pragma unroll
-      for (int i = 0; i < NV4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = 4 * lane + j + 128 * i;
-          if (c < C) atomicAdd(w + c, g[i * 4 + j] * inv_cnt);
-        }
-    }
-  } else {
-    float* w = s.grad + local * C;
-#pragma unroll
-    for (int i = 0; i < NV4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = 4 * lane + j + 128 * i;
-        if (c < C) atomicAdd(w + c, g[i * 4 + j]);
-      }
-  }
-}
-
-// One warp per chunk of `rows_per_warp` consecutive SORTED rows: runs of equal keys are summed in registers and
-// flushed once, so a (modality, source row) that occurs n times in the batch costs ~n / run-length atomics instead
-// of n, and the work per warp does not depend on how skewed the keys are (a 2-category feature, a popular item).
-template <int NV4>
-__global__ void seg_reduce_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int64_t n_keys,
-                                  const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm,
-                                  const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop,
-                                  uint64_t seed, const int64_t* __restrict__ step_dev,
-                                  const uint8_t* __restrict__ keep_mask, const float* __restrict__ dx, int64_t ld_dx,
-                                  int rows_per_warp) {
-  const int64_t chunk = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t n_sorted = offsets[n_keys];  // rows that have a feature row
-  const int64_t beg = chunk * rows_per_warp;
-  if (beg >= n_sorted) return;
-  const int64_t end = min(n_sorted, beg + rows_per_warp);
-  const int lane = threadIdx.x & 31;
-  const uint64_t step = step_dev ? (uint64_t)*step_dev : 0;
-  float g[NV4 * 4];
-#pragma unroll
-  for (int i = 0; i < NV4 * 4; ++i) g[i] = 0.f;
-  int32_t cur_key = __ldg(sorted_keys + beg);
-  for (int64_t p = beg; p < end; ++p) {
-    const int32_t key = __ldg(sorted_keys + p);
-    const int64_t r = __ldg(perm + p);
-    if (key != cur_key) {  // warp-uniform
-      flush_run<NV4>(srcs, n_mods, cur_key, C, normalize, lane, g);
-      cur_key = key;
-#pragma unroll
-      for (int i = 0; i < NV4 * 4; ++i) g[i] = 0.f;
-    }
-    uint4 cache;
-    int cache_c4 = -1;
-#pragma unroll
-    for (int i = 0; i < NV4; ++i) {
-      const int c0 = 4 * lane + 128 * i;
-      if (c0 + 3 < C && (ld_dx & 3) == 0) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(dx + r * ld_dx + c0));
-        g[i * 4 + 0] += v.x * keep_scale(keep_mask, r, C, c0 + 0, p_drop, seed, step, cache, cache_c4);
-        g[i * 4 + 1] += v.y * keep_scale(keep_mask, r, C, c0 + 1, p_drop, seed, step, cache, cache_c4);
-        g[i * 4 + 2] += v.z * keep_scale(keep_mask, r, C, c0 + 2, p_drop, seed, step, cache, cache_c4);
-        g[i * 4 + 3] += v.w * keep_scale(keep_mask, r, C, c0 + 3, p_drop, seed, step, cache, cache_c4);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = c0 + j;
-          if (c < C)
-            g[i * 4 + j] += dx[r * ld_dx + c] * keep_scale(keep_mask, r, C, c, p_drop, seed, step, cache, cache_c4);
-        }
-      }
-    }
-  }
-  flush_run<NV4>(srcs, n_mods, cur_key, C, normalize, lane, g);
-}
-
 }  // namespace
 
 extern "C" int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx,
@@ -398,12 +529,11 @@ extern "C" int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods
   SBR_REQUIRE((!out_bf16 || ld_out >= C) && (!out_f32 || ld_f32 >= C), "sbr_row_gather_fwd: output pitch < C");
   SBR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "sbr_row_gather_fwd: dropout p must be in [0, 1)");
   const int64_t N = n_idx * k;
-  DISPATCH_NV(C, 128, {
-    constexpr int NV4 = NVv > 8 ? 8 : NVv;
-    row_gather_fwd_kernel<NV4><<<cdiv(N, 8), 256, 0, S(stream)>>>(srcs_dev, n_mods, idx, mods, N, k, C, normalize,
-                                                                  p_drop, seed, step_dev, keep_mask,
-                                                                  reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32,
-                                                                  ld_f32, err_flag);
+  DISPATCH_GROUP(C, {
+    const int64_t threads = N * LPRv;
+    row_gather_fwd_g_kernel<LPRv, NVg><<<cdiv(threads, 256), 256, 0, S(stream)>>>(
+        srcs_dev, n_mods, idx, mods, N, k, C, normalize, p_drop, seed, step_dev, keep_mask,
+        reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_f32, err_flag);
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;
@@ -452,12 +582,11 @@ extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, 
               "sbr_row_gather_bwd_segmented: bad arguments");
   SBR_REQUIRE(C > 0 && C <= 1024 && ld_dx >= C, "sbr_row_gather_bwd_segmented: C=%d not in [1, 1024] or ld_dx < C", C);
   SBR_REQUIRE(rows_per_warp >= 1, "sbr_row_gather_bwd_segmented: bad chunking");
-  const unsigned blocks = cdiv(cdiv(n_rows, rows_per_warp), 8);
-  DISPATCH_NV(C, 128, {
-    constexpr int NV4 = NVv > 8 ? 8 : NVv;
-    seg_reduce_kernel<NV4><<<blocks, 256, 0, S(stream)>>>(srcs_dev, n_mods, n_keys, offsets, perm, sorted_keys, C,
-                                                          normalize, p_drop, seed, step_dev, keep_mask, dx, ld_dx,
-                                                          rows_per_warp);
+  DISPATCH_GROUP(C, {
+    const int64_t threads = (int64_t)cdiv(n_rows, rows_per_warp) * LPRv;
+    seg_reduce_g_kernel<LPRv, NVg><<<cdiv(threads, 256), 256, 0, S(stream)>>>(
+        srcs_dev, n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed, step_dev, keep_mask, dx,
+        ld_dx, rows_per_warp);
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;

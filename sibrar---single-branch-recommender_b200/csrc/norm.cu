@@ -3,13 +3,21 @@
 // so every warp reads 128 contiguous bytes per row and column partial sums stay in one register per thread.
 // Replaces torch.nn.BatchNorm1d as used at modules/polylinear.py:58-61,68-69 and algorithms/sgd_alg.py:1834-1837,
 // and the autograd of the projection's output activation (algorithms/sgd_alg.py:1356).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
-constexpr int RB = 256;  // rows per block
+// rows per block: 256 for long tensors, 32 for short ones (a [3 706 x 64] table would otherwise run on 30 blocks
+// whose threads walk 32 rows one dependent load at a time)
+inline int rows_per_block(int64_t rows) {
+  static const char* e = getenv("SBR_NORM_RB");  // measurement only
+  if (e) return atoi(e);
+  return rows >= 65536 ? 256 : 32;
+}
 
 __device__ __forceinline__ float load_y(const float* y_f32, const bf16* y_bf16, int64_t off) {
   return y_f32 ? y_f32[off] : __bfloat162float(y_bf16[off]);
@@ -33,7 +41,7 @@ __device__ __forceinline__ void block_col_flush(float v, float* dst, int c, int 
 __global__ void actgrad_colsum_kernel(float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
                                       const bf16* __restrict__ y_bf16, int64_t ld_y, int act, int64_t rows, int C,
                                       bf16* __restrict__ out_bf16, int64_t ld_out, float* __restrict__ out_f32,
-                                      int64_t ld_out_f32, float* __restrict__ colsum, int zero_dy) {
+                                      int64_t ld_out_f32, float* __restrict__ colsum, int zero_dy, int RB) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   const int64_t r0 = (int64_t)blockIdx.x * RB;
@@ -83,7 +91,7 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ rm, const float*
 __global__ void bn_apply_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                 int64_t rows, int C, bf16* __restrict__ out_bf16, int64_t ld_bf16,
-                                float* __restrict__ out_f32, int64_t ld_f32) {
+                                float* __restrict__ out_f32, int64_t ld_f32, int RB) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   if (c >= C) return;
@@ -102,7 +110,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, int64_t ld_z, const
 __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
                                      const bf16* __restrict__ y_bf16, int64_t ld_y, int act,
                                      const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
-                                     int64_t rows, int C, float* __restrict__ sums) {
+                                     int64_t rows, int C, float* __restrict__ sums, int RB) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   const int64_t r0 = (int64_t)blockIdx.x * RB;
@@ -127,7 +135,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy,
                                     const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ sums, int64_t rows,
                                     int C, bf16* __restrict__ dz_bf16, int64_t ld_dz, float* __restrict__ dz_f32,
-                                    int64_t ld_dz_f32, float* dgamma, float* dbeta) {
+                                    int64_t ld_dz_f32, float* dgamma, float* dbeta, int RB) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   if (c >= C) return;
@@ -151,7 +159,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy,
   }
 }
 
-inline dim3 tile_grid(int64_t rows, int64_t cols) { return dim3(cdiv(rows, RB), cdiv(cols, 32)); }
+inline dim3 tile_grid(int64_t rows, int64_t cols) { return dim3(cdiv(rows, rows_per_block(rows)), cdiv(cols, 32)); }
 }  // namespace
 
 extern "C" int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
@@ -161,7 +169,7 @@ extern "C" int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, 
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_actgrad_colsum: activation gradient needs the output y");
   actgrad_colsum_kernel<<<tile_grid(rows, cols), 256, 0, S(stream)>>>(
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, rows, (int)cols,
-      reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum, zero_dy);
+      reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum, zero_dy, rows_per_block(rows));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -190,7 +198,7 @@ extern "C" int sbr_bn_apply(const float* z, int64_t ld_z, const float* mean_invs
   SBR_REQUIRE(z && mean_invstd && gamma && beta && rows > 0 && C > 0, "sbr_bn_apply: bad arguments");
   bn_apply_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(z, ld_z, mean_invstd, gamma, beta, act, rows, C,
                                                              reinterpret_cast<bf16*>(out_bf16), ld_bf16, out_f32,
-                                                             ld_f32);
+                                                             ld_f32, rows_per_block(rows));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -201,7 +209,8 @@ extern "C" int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_
   SBR_REQUIRE(dy && z && mean_invstd && sums && rows > 0 && C > 0, "sbr_bn_bwd_reduce: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_reduce: activation gradient needs the output y");
   bn_bwd_reduce_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(
-      dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, rows, C, sums);
+      dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, rows, C, sums,
+      rows_per_block(rows));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -214,7 +223,7 @@ extern "C" int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_apply: activation gradient needs the output y");
   bn_bwd_apply_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, gamma, sums, rows, C,
-      reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta);
+      reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta, rows_per_block(rows));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

@@ -116,7 +116,7 @@ def row_gather_bwd(srcs, n_mods, idx, mods, k, C_, normalize, p_drop, seed, step
 class GatherPlan:
     """scratch + launches of the sorted-run gather backward for a fixed (n_keys, N)"""
 
-    def __init__(self, n_keys: int, N: int, device, rows_per_warp: int = 32):
+    def __init__(self, n_keys: int, N: int, device, rows_per_warp: int = 8):
         i32 = torch.int32
         self.n_keys, self.N = int(n_keys), int(N)
         self.counts = torch.zeros(n_keys, dtype=i32, device=device)

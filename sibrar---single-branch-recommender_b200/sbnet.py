@@ -94,6 +94,7 @@ class LinearStage:
         self.bn: Optional[nn.BatchNorm1d] = None
         self.act2: Optional[str] = None
         self.in_f, self.out_f = linear.in_features, linear.out_features
+        self.unit_mi = self.ones = self.zero_bias = None  # constants of the split-K forward's bias/activation pass
         self.w16 = None     # bf16 [out, pad8(in)]: K-major B of the forward GEMM, MN-major B of the dgrad GEMM
         self.wt32 = None    # fp32 [in, out] for the CSR route
         self._ver = -1
@@ -168,6 +169,15 @@ class Chain:
     def csr_input(self):
         return self.feature is not None and self.feature.kind == "csr"
 
+    @staticmethod
+    def _fwd_split_k(rows, st, n_sms: int = 148) -> int:
+        bn = 64 if st.out_f <= 64 else (128 if st.out_f <= 128 else 256)
+        tiles = -(-rows // 128) * -(-st.out_f // bn)
+        num_kb = -(-st.in_f // 64)
+        if tiles * 2 > n_sms or num_kb < 16:
+            return 1
+        return max(1, min(num_kb // 4, (2 * n_sms) // tiles))
+
     def forward(self, x16, rows, training, arena: ZeroArena, keep_for_backward=True, out32=None):
         dev = self.stages[0].linear.weight.device
         self.rows = rows
@@ -191,7 +201,21 @@ class Chain:
                     if y16 is not None:
                         ops.cast_bf16(y32, y16)
                 else:
-                    ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_bf16=y16, out_f32=y32)
+                    split = self._fwd_split_k(rows, st)
+                    if split > 1:
+                        # few output tiles, long contraction (an 'interactions' table): split K over the SMs into a
+                        # zeroed fp32 buffer, then one pass applies bias + activation (y = act(1 * (z - 0) * 1 + bias))
+                        z32 = torch.zeros((rows, st.out_f), dtype=F32, device=dev)
+                        ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, out_f32=z32, atomic_out=True, split_k=split)
+                        if st.unit_mi is None or st.unit_mi.device != dev:
+                            st.unit_mi = torch.cat([torch.zeros(st.out_f, device=dev), torch.ones(st.out_f, device=dev)])
+                            st.ones = torch.ones(st.out_f, device=dev)
+                            st.zero_bias = torch.zeros(st.out_f, device=dev)
+                        ops.bn_apply(z32, st.unit_mi, st.ones, bias if bias is not None else st.zero_bias, st.act1,
+                                     rows, st.out_f, out_bf16=y16, out_f32=y32)
+                    else:
+                        ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_bf16=y16,
+                                 out_f32=y32)
             else:
                 bn = st.bn
                 a32 = torch.empty((rows, st.out_f), dtype=F32, device=dev)
