@@ -187,6 +187,18 @@ class CallProfiler:
                     bool(ep.out_bf16), bool(ep.out_f32), int(ep.transpose_out))
         if name in ("sbr_row_gather_fwd", "sbr_row_gather_bwd"):
             return (name, int(args[4]) * int(args[5]), int(args[6]))
+        if name == "sbr_row_gather_bwd_segmented":
+            return (name, int(args[6]), int(args[7]))
+        if name == "sbr_bn_apply":
+            return (name, int(args[6]), int(args[7]), bool(args[8]), bool(args[10]))
+        if name == "sbr_bn_bwd_reduce":
+            return (name, int(args[9]), int(args[10]))
+        if name == "sbr_bn_bwd_apply":
+            return (name, int(args[11]), int(args[12]))
+        if name == "sbr_actgrad_colsum":
+            return (name, int(args[6]), int(args[7]))
+        if name == "sbr_score_loss":
+            return (name, int(args[2]), int(args[3]), int(args[4]), int(args[5]), int(args[6]))
         return (name,)
 
     def summary(self):
@@ -212,6 +224,24 @@ def algorithmic_work(key):
     if key[0] == "sbr_row_gather_bwd":
         _, rows, C = key
         return 0.0, rows * C * (4 + 4 + 4) + rows * 9
+    if key[0] == "sbr_row_gather_bwd_segmented":  # dx rows (fp32) + (sorted key, permutation) per row
+        _, rows, C = key
+        return 0.0, rows * C * 4 + rows * 8
+    if key[0] == "sbr_bn_apply":  # z fp32 in, bf16 and/or fp32 out
+        _, rows, C, o16, o32 = key
+        return 0.0, rows * C * (4 + (2 if o16 else 0) + (4 if o32 else 0))
+    if key[0] == "sbr_bn_bwd_reduce":  # dy, z
+        _, rows, C = key
+        return 0.0, rows * C * 8
+    if key[0] == "sbr_bn_bwd_apply":  # dy, z in; dz bf16 out
+        _, rows, C = key
+        return 0.0, rows * C * 10
+    if key[0] == "sbr_actgrad_colsum":  # dT fp32 in (+ cleared), T in, bf16 out
+        _, rows, C = key
+        return 0.0, rows * C * (4 + 4 + 4 + 2)
+    if key[0] == "sbr_score_loss":  # embeddings in, gradients out (fp32)
+        _, B, n, ku, ki, D = key
+        return 0.0, 2.0 * B * D * 4 * (ku + n * ki)
     return 0.0, 0.0
 
 
@@ -225,6 +255,7 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("SBR_BENCH_BATCH", 16384)),
                     help="interactions per GPU per step")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel (no CUDA graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -273,7 +304,7 @@ def main():
     model = SingleBranchNet.build_from_conf(ml1m_model_conf(), train).to(dev).train()
     from sibrar_b200.parallel import DataParallelTrainer
     tr = DataParallelTrainer(model, LEARN, n_negative_samples=N_NEG) if world > 1 else \
-        FusedTrainer(model, LEARN, n_negative_samples=N_NEG)
+        FusedTrainer(model, LEARN, n_negative_samples=N_NEG, cuda_graph=not args.no_graph)
 
     # ---- synthetic batches, sampled on the device by the GPU sampler (resident in HBM before the timed region)
     B, n = args.batch, 1 + N_NEG
@@ -366,6 +397,7 @@ def main():
             which = "measured"
         except Exception:
             peaks, which = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), "fallback"
+        tr.cuda_graph = False  # the per-call pass launches kernel by kernel
         with CallProfiler(ops, torch) as prof:
             for k in range(3):
                 flush.zero_()

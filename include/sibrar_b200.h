@@ -108,6 +108,7 @@ typedef struct {
   const int32_t* codes;   /* CATEGORICAL: [n_rows] category id; TAG: [n_rows, max_tags] tag ids (pad = n_tags)    */
   int32_t max_tags;       /* TAG only                                                                             */
   int32_t pad_id;         /* TAG only                                                                             */
+  int64_t n_table_rows;   /* rows of `table` / `grad` (small tables are accumulated in shared memory by the backward)  */
   int64_t key_base;       /* first segment key of this modality (sbr_gather_plan); keys = key_base + table row |
                              category | entity row (TAG)                                                          */
 } sbr_modality_src_t;

@@ -29,7 +29,7 @@ class GemmEpilogue(C.Structure):
 
 class ModalitySrc(C.Structure):
     _fields_ = [("kind", C.c_int), ("remap", c_vp), ("table", c_vp), ("grad", c_vp), ("codes", c_vp),
-                ("max_tags", c_i32), ("pad_id", c_i32), ("key_base", c_i64)]
+                ("max_tags", c_i32), ("pad_id", c_i32), ("n_table_rows", c_i64), ("key_base", c_i64)]
 
 
 class AdamTensor(C.Structure):

@@ -237,14 +237,23 @@ row_gather_fwd_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
   }
 }
 
+constexpr int SEG_MAX_MODS = 16;
+constexpr int SEG_SMEM_FLOATS = 10240;  // 40 KB of block-private gradient rows for small Embedding / EmbeddingBag tables
+
+struct SegShared {
+  sbr_modality_src_t src[SEG_MAX_MODS];
+  int smem_off[SEG_MAX_MODS];  // offset of the modality's private gradient table in `priv`, or -1
+  float priv[SEG_SMEM_FLOATS];
+};
+
 // flush the summed gradient of one run of equal keys (group layout) into the owning source's gradient buffer
 template <int LPR, int NV>
-__device__ __forceinline__ void flush_run_g(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int32_t key, int C,
-                                            int normalize, int li, unsigned gmask, float (&g)[NV * 8]) {
+__device__ __forceinline__ void flush_run_g(SegShared& sh, int n_mods, int32_t key, int C, int normalize, int li,
+                                            unsigned gmask, float (&g)[NV * 8]) {
   int m = 0;
   for (int t = 1; t < n_mods; ++t)
-    if ((int64_t)key >= srcs[t].key_base) m = t;
-  const sbr_modality_src_t s = srcs[m];
+    if ((int64_t)key >= sh.src[t].key_base) m = t;
+  const sbr_modality_src_t& s = sh.src[m];
   if (s.grad == nullptr) return;
   const int64_t local = (int64_t)key - s.key_base;  // table row | category | entity row (TAG)
   float inv_cnt = 1.f;
@@ -260,8 +269,12 @@ __device__ __forceinline__ void flush_run_g(const sbr_modality_src_t* __restrict
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[i * 8 + j] = v[j];
       }
-    } else {
+    } else if (normalize) {
       load_source_row_g<LPR, NV>(s, local, C, li, x, inv_cnt);
+    } else {  // TAG without normalisation: only the tag count is needed
+      int cnt = 0;
+      for (int t = 0; t < s.max_tags; ++t) cnt += __ldg(s.codes + local * s.max_tags + t) != s.pad_id ? 1 : 0;
+      inv_cnt = 1.f / (float)max(cnt, 1);
     }
     if (normalize) {
       float ss = 0.f, dot = 0.f;
@@ -279,11 +292,12 @@ __device__ __forceinline__ void flush_run_g(const sbr_modality_src_t* __restrict
       for (int i = 0; i < NV * 8; ++i) g[i] = (g[i] - x[i] * dot) * inv;
     }
   }
+  const int off = sh.smem_off[m];
   if (s.kind == SBR_SRC_TAG) {
     for (int t = 0; t < s.max_tags; ++t) {
       const int32_t tag = __ldg(s.codes + local * s.max_tags + t);
       if (tag == s.pad_id) continue;
-      float* w = s.grad + (int64_t)tag * C;
+      float* w = off >= 0 ? sh.priv + off + (int64_t)tag * C : s.grad + (int64_t)tag * C;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
 #pragma unroll
@@ -293,7 +307,7 @@ __device__ __forceinline__ void flush_run_g(const sbr_modality_src_t* __restrict
         }
     }
   } else {
-    float* w = s.grad + local * C;
+    float* w = off >= 0 ? sh.priv + off + local * C : s.grad + local * C;
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
@@ -304,9 +318,11 @@ __device__ __forceinline__ void flush_run_g(const sbr_modality_src_t* __restrict
   }
 }
 
-// One GROUP per chunk of `rows_per_group` consecutive SORTED rows: runs of equal keys are summed in registers and
-// flushed once, so a (modality, source row) that occurs n times in the batch costs ~n / run-length atomics instead
-// of n, and the work per group does not depend on how skewed the keys are (a 2-category feature, a popular item).
+// Persistent blocks; one GROUP per chunk of `rows_per_group` consecutive SORTED rows (grid-stride over the chunks):
+// runs of equal keys are summed in registers and flushed once, so a (modality, source row) that occurs n times in the
+// batch costs ~n / run-length atomics instead of n, and the work per group does not depend on how skewed the keys
+// are.  Small Embedding / EmbeddingBag tables (a 2-category feature, 18 genre tags) are accumulated in a block-private
+// shared-memory copy first: thousands of same-address global atomics serialise at ~100 cycles each in one L2 slice.
 template <int LPR, int NV>
 __global__ void __launch_bounds__(256)
 seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int64_t n_keys,
@@ -314,48 +330,77 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
                     const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop, uint64_t seed,
                     const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
                     const float* __restrict__ dx, int64_t ld_dx, int rows_per_group) {
-  const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+  __shared__ SegShared sh;
+  if (threadIdx.x == 0) {
+    int used = 0;
+    for (int m = 0; m < n_mods; ++m) {
+      sh.src[m] = srcs[m];
+      const int64_t need = sh.src[m].n_table_rows * C;
+      const bool small = sh.src[m].grad != nullptr && sh.src[m].kind != SBR_SRC_TABLE && need > 0 &&
+                         used + need <= SEG_SMEM_FLOATS;
+      sh.smem_off[m] = small ? used : -1;
+      if (small) used += (int)need;
+    }
+  }
+  for (int i = threadIdx.x; i < SEG_SMEM_FLOATS; i += blockDim.x) sh.priv[i] = 0.f;
+  __syncthreads();
+
   const int li = threadIdx.x % LPR;
   const int lane = threadIdx.x & 31;
   const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (lane / LPR * LPR));
   const int64_t n_sorted = offsets[n_keys];  // rows that have a feature row
-  const int64_t beg = chunk * rows_per_group;
-  if (beg >= n_sorted) return;
-  const int64_t end = min(n_sorted, beg + rows_per_group);
   const uint64_t step = step_dev ? (uint64_t)*step_dev : 0;
   const float sc = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   const bool vec_ok = (ld_dx & 3) == 0;
-  float g[NV * 8];
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / LPR);
+  for (int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;; chunk += groups_total) {
+    const int64_t beg = chunk * rows_per_group;
+    if (beg >= n_sorted) break;
+    const int64_t end = min(n_sorted, beg + rows_per_group);
+    float g[NV * 8];
 #pragma unroll
-  for (int i = 0; i < NV * 8; ++i) g[i] = 0.f;
-  int32_t cur_key = __ldg(sorted_keys + beg);
-  int32_t key_n = cur_key;
-  int64_t r_n = __ldg(perm + beg);
-  for (int64_t p = beg; p < end; ++p) {
-    const int32_t key = key_n;
-    const int64_t r = r_n;
-    if (p + 1 < end) {  // the next row's indices are in flight while this row is summed
-      key_n = __ldg(sorted_keys + p + 1);
-      r_n = __ldg(perm + p + 1);
+    for (int i = 0; i < NV * 8; ++i) g[i] = 0.f;
+    int32_t cur_key = __ldg(sorted_keys + beg);
+    int32_t key_n = cur_key;
+    int64_t r_n = __ldg(perm + beg);
+    for (int64_t p = beg; p < end; ++p) {
+      const int32_t key = key_n;
+      const int64_t r = r_n;
+      if (p + 1 < end) {  // the next row's indices are in flight while this row is summed
+        key_n = __ldg(sorted_keys + p + 1);
+        r_n = __ldg(perm + p + 1);
+      }
+      if (key != cur_key) {  // group-uniform
+        flush_run_g<LPR, NV>(sh, n_mods, cur_key, C, normalize, li, gmask, g);
+        cur_key = key;
+#pragma unroll
+        for (int i = 0; i < NV * 8; ++i) g[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = 8 * li + 8 * LPR * i;
+        if (c0 >= C) continue;
+        float v[8];
+        load8(dx + r * ld_dx, c0, C, vec_ok, v);
+        const uint32_t km = keep8(keep_mask, r, C, c0, p_drop, seed, step);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[i * 8 + j] += ((km >> j) & 1u) ? v[j] * sc : 0.f;
+      }
     }
-    if (key != cur_key) {  // group-uniform
-      flush_run_g<LPR, NV>(srcs, n_mods, cur_key, C, normalize, li, gmask, g);
-      cur_key = key;
-#pragma unroll
-      for (int i = 0; i < NV * 8; ++i) g[i] = 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c0 = 8 * li + 8 * LPR * i;
-      if (c0 >= C) continue;
-      float v[8];
-      load8(dx + r * ld_dx, c0, C, vec_ok, v);
-      const uint32_t km = keep8(keep_mask, r, C, c0, p_drop, seed, step);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[i * 8 + j] += ((km >> j) & 1u) ? v[j] * sc : 0.f;
+    flush_run_g<LPR, NV>(sh, n_mods, cur_key, C, normalize, li, gmask, g);
+  }
+  __syncthreads();
+  // block-private small tables -> global gradient buffers
+  for (int m = 0; m < n_mods; ++m) {
+    const int off = sh.smem_off[m];
+    if (off < 0) continue;
+    const int n = (int)(sh.src[m].n_table_rows * C);
+    float* dst = sh.src[m].grad;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = sh.priv[off + i];
+      if (v != 0.f) atomicAdd(dst + i, v);
     }
   }
-  flush_run_g<LPR, NV>(srcs, n_mods, cur_key, C, normalize, li, gmask, g);
 }
 
 // lanes per row / 8-element vectors per lane for a row of C elements
@@ -582,9 +627,13 @@ extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, 
               "sbr_row_gather_bwd_segmented: bad arguments");
   SBR_REQUIRE(C > 0 && C <= 1024 && ld_dx >= C, "sbr_row_gather_bwd_segmented: C=%d not in [1, 1024] or ld_dx < C", C);
   SBR_REQUIRE(rows_per_warp >= 1, "sbr_row_gather_bwd_segmented: bad chunking");
+  SBR_REQUIRE(n_mods <= SEG_MAX_MODS, "sbr_row_gather_bwd_segmented: at most %d modalities", SEG_MAX_MODS);
   DISPATCH_GROUP(C, {
     const int64_t threads = (int64_t)cdiv(n_rows, rows_per_warp) * LPRv;
-    seg_reduce_g_kernel<LPRv, NVg><<<cdiv(threads, 256), 256, 0, S(stream)>>>(
+    int64_t blocks = cdiv(threads, 256);
+    const int64_t cap = (int64_t)sbr_num_sms() * 4;  // persistent: 4 blocks (45 KB of shared memory each) per SM
+    if (blocks > cap) blocks = cap;
+    seg_reduce_g_kernel<LPRv, NVg><<<(unsigned)blocks, 256, 0, S(stream)>>>(
         srcs_dev, n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed, step_dev, keep_mask, dx,
         ld_dx, rows_per_warp);
   });

@@ -94,6 +94,7 @@ def make_modality_srcs(entries, device) -> torch.Tensor:
         arr[i].codes = ptr(e.get("codes"))
         arr[i].max_tags = int(e.get("max_tags", 0))
         arr[i].pad_id = int(e.get("pad_id", -1))
+        arr[i].n_table_rows = int(e["table"].shape[0]) if e.get("table") is not None else 0
         arr[i].key_base = int(e.get("key_base", 0))
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
     return host.to(device)

@@ -65,6 +65,7 @@ class DataParallelTrainer(FusedTrainer):
             dist.broadcast(p.data, src=0)
         for b in model.buffers():
             dist.broadcast(b, src=0)
+        kw.pop("cuda_graph", None)  # the NCCL all-reduce hooks run outside graphs
         super().__init__(model, learn, n_negative_samples, grad_scale=1.0 / self.world, **kw)
         self._work = []
 

@@ -22,7 +22,7 @@ F32 = torch.float32
 class FusedTrainer:
     def __init__(self, model: SingleBranchNet, learn, n_negative_samples: int,
                  negative_sampling_strategy: str = "uniform_recbole", betas=(0.9, 0.999), eps: float = 1e-8,
-                 grad_scale: float = 1.0):
+                 grad_scale: float = 1.0, cuda_graph: bool = False):
         if isinstance(learn, dict):
             learn = LearningConfig.from_dict(learn)
         if learn.optimizer not in ("adam", "adamw"):
@@ -75,11 +75,46 @@ class FusedTrainer:
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
         self.steps_accumulated = 0
         self.logits = None
+        # CUDA-graph replay of the whole step (the ~40 launches of a step cost more host time than GPU time at
+        # paper-sized batches).  Per batch shape: two eager steps first (lazy caches, function attributes), then the
+        # step is captured once and replayed; the step counter, the Philox streams and the loss sums live on the device.
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------------ one step
     def step(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor, mods: Optional[dict] = None,
              keep_masks: Optional[dict] = None, apply_optimizer: bool = True):
         """u_idxs int64 [B], i_idxs int64 [B, 1 + n_neg] on the device (positive item in column 0)."""
+        if self.cuda_graph and not mods and not keep_masks and apply_optimizer:
+            return self._graph_step(u_idxs, i_idxs)
+        return self._eager_step(u_idxs, i_idxs, mods, keep_masks, apply_optimizer)
+
+    def _graph_step(self, u_idxs, i_idxs):
+        key = (tuple(u_idxs.shape), tuple(i_idxs.shape))
+        st = self._graphs.setdefault(key, {"eager": 0})
+        if "graph" not in st:
+            if st["eager"] < 2:
+                st["eager"] += 1
+                return self._eager_step(u_idxs, i_idxs, None, None, True)
+            st["u"], st["i"] = u_idxs.clone(), i_idxs.clone()
+            torch.cuda.synchronize()
+            from . import _lib
+            before = _lib.launch_counter()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._eager_step(st["u"], st["i"], None, None, True)
+            self.steps_accumulated -= 1  # the capture only records
+            st["launches"] = _lib.launch_counter() - before
+            _lib._launches[0] = before
+            st["graph"] = g
+        st["u"].copy_(u_idxs, non_blocking=True)
+        st["i"].copy_(i_idxs, non_blocking=True)
+        st["graph"].replay()
+        from . import _lib
+        _lib._launches[0] += st["launches"]  # kernels of ours inside the replayed graph
+        self.steps_accumulated += 1
+
+    def _eager_step(self, u_idxs, i_idxs, mods, keep_masks, apply_optimizer):
         m, rt = self.model, self.rt
         mods, keep_masks = mods or {}, keep_masks or {}
         B, n = i_idxs.shape
