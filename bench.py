@@ -295,7 +295,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     _lib.lib()  # fail loudly here if the CUDA extension is missing
 
     corpus = SynCorpus("ml1m", "cold_start_item", seed=42)
@@ -303,7 +304,7 @@ def main():
     torch.manual_seed(1234)
     model = SingleBranchNet.build_from_conf(ml1m_model_conf(), train).to(dev).train()
     from sibrar_b200.parallel import DataParallelTrainer
-    tr = DataParallelTrainer(model, LEARN, n_negative_samples=N_NEG) if world > 1 else \
+    tr = DataParallelTrainer(model, LEARN, n_negative_samples=N_NEG, cuda_graph=not args.no_graph) if world > 1 else \
         FusedTrainer(model, LEARN, n_negative_samples=N_NEG, cuda_graph=not args.no_graph)
 
     # ---- synthetic batches, sampled on the device by the GPU sampler (resident in HBM before the timed region)
@@ -390,14 +391,39 @@ def main():
                             "(256 MiB write)", wall_ms_per_step_incl_flush=t_wall / args.steps * 1e3),
                 clocks=clk, e2e=e2e, gpu_launches=launches, train_loss=losses.get("train/loss"))
 
+    # ---- item-sharded evaluation (all ranks): local exact top-k per shard -> all-gather of [U, k] keys -> merge
+    sharded = None
+    if world > 1 and not args.no_eval:
+        from sibrar_b200.parallel import ShardedEvaluator
+        sev = ShardedEvaluator(dict(top_k=[1, 10, 20], metrics=["ndcg", "recall", "precision", "coverage"],
+                                    calculate_std=False))
+        val = corpus.dataset("val")
+        res = sev.evaluate(model, val)
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            res = sev.evaluate(model, val)
+        b.record()
+        sync_all()
+        t = torch.tensor([a.elapsed_time(b) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sharded = dict(metric="eval_users_per_sec", value=val.n_users_in_split / (float(t.item()) * 1e-3),
+                       unit="users/s", ms=float(t.item()), shards=world, ndcg10=res.get("ndcg@10"))
+
+    # ---- roofline of the dominant kernel (separate profiled pass, CUDA events around every C-ABI call); every rank
+    # runs these steps (they contain the gradient all-reduce), rank 0 records them
+    tr.cuda_graph = False  # the per-call pass launches kernel by kernel
+    if rank != 0:
+        for k in range(3):
+            flush.zero_()
+            tr.step(*batches[(args.warmup + k) % len(batches)])
     if rank == 0:
-        # ---- roofline of the dominant kernel (separate profiled pass, CUDA events around every C-ABI call)
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             which = "measured"
         except Exception:
             peaks, which = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), "fallback"
-        tr.cuda_graph = False  # the per-call pass launches kernel by kernel
         with CallProfiler(ops, torch) as prof:
             for k in range(3):
                 flush.zero_()
@@ -427,6 +453,8 @@ def main():
         if not args.no_eval:
             try:
                 line["eval"] = bench_eval(torch, ops, model, corpus, FullEvaluator, dev)
+                if sharded is not None:
+                    line["eval"]["item_sharded_val_split"] = sharded
             except Exception as e:  # keep the headline line
                 line["eval"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
@@ -436,8 +464,15 @@ def main():
                 line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
+        # graphs that captured NCCL kernels must go before the communicator does; then leave without running the
+        # interpreter's teardown of NCCL (a captured collective can make destroy_process_group wait forever)
+        tr._graphs.clear()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def bench_eval(torch, ops, model, corpus, FullEvaluator, dev):
