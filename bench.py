@@ -194,7 +194,7 @@ class CallProfiler:
         if name == "sbr_bn_bwd_reduce":
             return (name, int(args[9]), int(args[10]))
         if name == "sbr_bn_bwd_apply":
-            return (name, int(args[11]), int(args[12]))
+            return (name, int(args[12]), int(args[13]))
         if name == "sbr_actgrad_colsum":
             return (name, int(args[6]), int(args[7]))
         if name == "sbr_score_loss":

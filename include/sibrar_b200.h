@@ -163,11 +163,12 @@ int sbr_bn_eval_coeffs(const float* running_mean, const float* running_var, int 
 int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y, int act,
                       const float* z, int64_t ld_z, const float* mean_invstd, int64_t rows, int C, float* sums,
                       void* stream);
-/* backward pass 2: dz = gamma*invstd*(dzb - mean(dzb) - xhat*mean(dzb*xhat)) -> bf16 (+fp32); dgamma, dbeta from sums */
+/* backward pass 2: dz = gamma*invstd*(dzb - mean(dzb) - xhat*mean(dzb*xhat)) -> bf16 (+fp32); dgamma, dbeta from sums.
+ * sums: [n_replicas, 2*C] partial sums that are added up first (1 replica from sbr_bn_bwd_reduce). */
 int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y, int act,
                      const float* z, int64_t ld_z, const float* mean_invstd, const float* gamma, const float* sums,
-                     int64_t rows, int C, void* dz_bf16, int64_t ld_dz, float* dz_f32, int64_t ld_dz_f32,
-                     float* dgamma, float* dbeta, void* stream);
+                     int n_replicas, int64_t rows, int C, void* dz_bf16, int64_t ld_dz, float* dz_f32,
+                     int64_t ld_dz_f32, float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ losses
  * Fused modality aggregation (mean | max over k), user-item scoring, rec loss and their gradients
@@ -178,6 +179,22 @@ int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f32, const v
 int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n, int ku, int ki, int D, int agg_max_user,
                    int agg_max_item, int loss_kind, int aggregator_sum, float ssm_shift, float* logits,
                    double* loss_acc, float* deu, float* dei, float* u_agg, float* i_agg, void* stream);
+/* The same for entities whose single-branch net ends in a BatchNorm1d (algorithms/sgd_alg.py:1834-1837): the
+ * kernel reads the PRE-BatchNorm values z and applies e = gamma * (z - mean) * invstd + beta on the fly, and it
+ * accumulates the BatchNorm-backward column sums of the gradients it produces (sums[r][0:D] += de,
+ * sums[r][D:2D] += de * xhat, r = one of n_replicas copies) -- replaces sbr_bn_apply + sbr_bn_bwd_reduce at the
+ * end of the chain.  One modality slot per entity (no regularisation), D in {16, 32, 64, 128}.  bn_u / bn_i may be
+ * NULL (or have z == NULL): then eu / ei hold the embeddings themselves. */
+typedef struct {
+  const float* z;            /* [rows, D] pre-BatchNorm values                  */
+  const float* mean_invstd;  /* [2 * D] from sbr_bn_finalize                    */
+  const float* gamma;        /* [D]                                             */
+  const float* beta;         /* [D]                                             */
+  float* sums;               /* [n_replicas, 2 * D], zeroed by the caller       */
+} sbr_bn_inline_t;
+int sbr_score_loss_bn(const float* eu, const sbr_bn_inline_t* bn_u, const float* ei, const sbr_bn_inline_t* bn_i,
+                      int64_t B, int n, int D, int loss_kind, int aggregator_sum, float ssm_shift, float* logits,
+                      double* loss_acc, float* deu, float* dei, int n_replicas, void* stream);
 /* Symmetric InfoNCE (train/regularization_losses.py:8-43) between slot 0 and slot 1 of e [G, n, 2, D]:
  * contrast along n inside each of the G groups (item side: G = B, n = 1 + n_neg; user side: G = 1, n = B).
  * loss_acc[0] += weight * loss; de (+)= weight * dloss/de (accumulate=1 adds to existing gradients). */

@@ -32,6 +32,10 @@ class ModalitySrc(C.Structure):
                 ("max_tags", c_i32), ("pad_id", c_i32), ("n_table_rows", c_i64), ("key_base", c_i64)]
 
 
+class BnInline(C.Structure):
+    _fields_ = [("z", c_vp), ("mean_invstd", c_vp), ("gamma", c_vp), ("beta", c_vp), ("sums", c_vp)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", c_vp), ("grad", c_vp), ("exp_avg", c_vp), ("exp_avg_sq", c_vp), ("shadow_bf16", c_vp),
                 ("numel", c_i64), ("cols", c_i64), ("shadow_ld", c_i64)]
@@ -59,10 +63,12 @@ _PROTOS = {
     "sbr_bn_apply": [c_vp, c_i64, c_vp, c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, c_vp],
     "sbr_bn_eval_coeffs": [c_vp, c_vp, C.c_int, c_f32, c_vp, c_vp],
     "sbr_bn_bwd_reduce": [c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, C.c_int, c_vp, c_vp],
-    "sbr_bn_bwd_apply": [c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, C.c_int,
+    "sbr_bn_bwd_apply": [c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_int, c_i64, C.c_int,
                          c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp],
     "sbr_score_loss": [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                        c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "sbr_score_loss_bn": [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp,
+                          c_vp, C.c_int, c_vp],
     "sbr_infonce": [c_vp, c_i64, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, C.c_int, c_vp, c_vp],
     "sbr_aggregate": [c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp],
     "sbr_adam_step": [c_vp, C.c_int, c_i64, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, C.c_int, c_vp, c_f32,

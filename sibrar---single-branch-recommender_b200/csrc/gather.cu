@@ -329,7 +329,7 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
                     const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm,
                     const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop, uint64_t seed,
                     const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
-                    const float* __restrict__ dx, int64_t ld_dx, int rows_per_group) {
+                    const float* __restrict__ dx, int64_t ld_dx) {
   __shared__ SegShared sh;
   if (threadIdx.x == 0) {
     int used = 0;
@@ -353,22 +353,49 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
   const float sc = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   const bool vec_ok = (ld_dx & 3) == 0;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / LPR);
+  constexpr int RPG = 8;  // sorted rows per chunk
   for (int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;; chunk += groups_total) {
-    const int64_t beg = chunk * rows_per_group;
+    const int64_t beg = chunk * RPG;
     if (beg >= n_sorted) break;
-    const int64_t end = min(n_sorted, beg + rows_per_group);
+    const int64_t end = min(n_sorted, beg + RPG);
     float g[NV * 8];
 #pragma unroll
     for (int i = 0; i < NV * 8; ++i) g[i] = 0.f;
     int32_t cur_key = __ldg(sorted_keys + beg);
-    int32_t key_n = cur_key;
-    int64_t r_n = __ldg(perm + beg);
+    // software pipeline: indices two rows ahead, the dx row one row ahead of the row being summed
+    int32_t key_c = cur_key, key_n = cur_key;
+    int64_t r_c = __ldg(perm + beg), r_n = r_c;
+    if (beg + 1 < end) {
+      key_n = __ldg(sorted_keys + beg + 1);
+      r_n = __ldg(perm + beg + 1);
+    }
+    float vn[NV][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = 8 * li + 8 * LPR * i;
+      if (c0 < C) load8(dx + r_c * ld_dx, c0, C, vec_ok, vn[i]);
+    }
+#pragma unroll 1
     for (int64_t p = beg; p < end; ++p) {
-      const int32_t key = key_n;
-      const int64_t r = r_n;
-      if (p + 1 < end) {  // the next row's indices are in flight while this row is summed
-        key_n = __ldg(sorted_keys + p + 1);
-        r_n = __ldg(perm + p + 1);
+      const int32_t key = key_c;
+      const int64_t r = r_c;
+      float v[NV][8];
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = vn[i][j];
+      key_c = key_n;
+      r_c = r_n;
+      if (p + 1 < end) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c0 = 8 * li + 8 * LPR * i;
+          if (c0 < C) load8(dx + r_c * ld_dx, c0, C, vec_ok, vn[i]);
+        }
+        if (p + 2 < end) {
+          key_n = __ldg(sorted_keys + p + 2);
+          r_n = __ldg(perm + p + 2);
+        }
       }
       if (key != cur_key) {  // group-uniform
         flush_run_g<LPR, NV>(sh, n_mods, cur_key, C, normalize, li, gmask, g);
@@ -380,11 +407,9 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
       for (int i = 0; i < NV; ++i) {
         const int c0 = 8 * li + 8 * LPR * i;
         if (c0 >= C) continue;
-        float v[8];
-        load8(dx + r * ld_dx, c0, C, vec_ok, v);
         const uint32_t km = keep8(keep_mask, r, C, c0, p_drop, seed, step);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[i * 8 + j] += ((km >> j) & 1u) ? v[j] * sc : 0.f;
+        for (int j = 0; j < 8; ++j) g[i * 8 + j] += ((km >> j) & 1u) ? v[i][j] * sc : 0.f;
       }
     }
     flush_run_g<LPR, NV>(sh, n_mods, cur_key, C, normalize, li, gmask, g);
@@ -513,42 +538,40 @@ __global__ void plan_count_kernel(const sbr_modality_src_t* __restrict__ srcs, i
   if (key >= 0) atomicAdd(counts + key, 1);
 }
 
-// exclusive scan by one block (n up to a few million keys: n / 1024 iterations)
-__global__ void plan_scan_kernel(const int32_t* __restrict__ counts, int64_t n, int32_t* __restrict__ offsets) {
+// exclusive scan by one block of 1024 threads: thread t owns the contiguous slice [t * per, (t + 1) * per) -- one
+// serial pass for the slice sums, one block scan of the 1024 sums, one serial pass to write the offsets
+__global__ void __launch_bounds__(1024)
+plan_scan_kernel(const int32_t* __restrict__ counts, int64_t n, int32_t* __restrict__ offsets) {
   __shared__ int32_t warp_sums[32];
-  __shared__ int32_t carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+  const int64_t beg = min(n, (int64_t)threadIdx.x * per), end = min(n, beg + per);
+  int32_t local = 0;
+  for (int64_t i = beg; i < end; ++i) local += counts[i];
+  int32_t x = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
   __syncthreads();
-  for (int64_t base = 0; base < n; base += blockDim.x) {
-    const int64_t i = base + threadIdx.x;
-    const int32_t v = i < n ? counts[i] : 0;
-    int32_t x = v;
+  if (warp == 0) {
+    int32_t w = warp_sums[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+      const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
     }
-    if (lane == 31) warp_sums[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int32_t y = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += y;
-      }
-      warp_sums[lane] = w;  // inclusive
-    }
-    __syncthreads();
-    const int32_t carry = carry_s;
-    const int32_t warp_off = warp > 0 ? warp_sums[warp - 1] : 0;
-    if (i < n) offsets[i] = carry + warp_off + x - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_off + x;
-    __syncthreads();
+    warp_sums[lane] = w;  // inclusive
   }
-  if (threadIdx.x == 0) offsets[n] = carry_s;
+  __syncthreads();
+  int32_t run = (warp > 0 ? warp_sums[warp - 1] : 0) + x - local;  // exclusive prefix of this thread's slice
+  for (int64_t i = beg; i < end; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+  if (threadIdx.x == blockDim.x - 1) offsets[n] = warp_sums[31];
 }
 
 __global__ void plan_fill_kernel(const int32_t* __restrict__ row_keys, int64_t N, const int32_t* __restrict__ offsets,
@@ -629,13 +652,13 @@ extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, 
   SBR_REQUIRE(rows_per_warp >= 1, "sbr_row_gather_bwd_segmented: bad chunking");
   SBR_REQUIRE(n_mods <= SEG_MAX_MODS, "sbr_row_gather_bwd_segmented: at most %d modalities", SEG_MAX_MODS);
   DISPATCH_GROUP(C, {
-    const int64_t threads = (int64_t)cdiv(n_rows, rows_per_warp) * LPRv;
+    const int64_t threads = (int64_t)cdiv(n_rows, 8) * LPRv;  // 8 sorted rows per lane group
     int64_t blocks = cdiv(threads, 256);
     const int64_t cap = (int64_t)sbr_num_sms() * 4;  // persistent: 4 blocks (45 KB of shared memory each) per SM
     if (blocks > cap) blocks = cap;
     seg_reduce_g_kernel<LPRv, NVg><<<(unsigned)blocks, 256, 0, S(stream)>>>(
         srcs_dev, n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed, step_dev, keep_mask, dx,
-        ld_dx, rows_per_warp);
+        ld_dx);
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;

@@ -252,6 +252,169 @@ score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ e
   }
 }
 
+// Fused variant for entities whose single-branch net ends in a BatchNorm (the default configuration): the kernel
+// reads the PRE-BatchNorm values z and applies  e = gamma * (z - mean) * invstd + beta  on the fly (the normalised
+// embeddings are never written), and it accumulates the two BatchNorm-backward column sums  sum(de), sum(de * xhat)
+// of the gradients it produces -- bn_apply and bn_bwd_reduce disappear from the step.  Persistent blocks; the sums
+// go out once per block into one of `n_replicas` copies (same-address atomics serialise in one L2 slice).
+struct BnInline {
+  const float* z;            // [rows, D] pre-BatchNorm values, or nullptr: `e` holds the embeddings themselves
+  const float* mean_invstd;  // [2 * D]
+  const float* gamma;
+  const float* beta;
+  float* sums;               // [n_replicas, 2 * D], zeroed by the caller
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+score_loss_bn_kernel(const float* __restrict__ eu, BnInline bu, const float* __restrict__ ei, BnInline bi, int64_t B,
+                     int n, int loss_kind, float inv_cnt, float ssm_shift, float* __restrict__ logits,
+                     double* __restrict__ loss_acc, float* __restrict__ deu, float* __restrict__ dei, int n_replicas) {
+  constexpr int D = 4 * LPR;
+  constexpr int RPP = 32 / LPR;  // item rows per pass
+  extern __shared__ float sh[];  // per warp: n scores + n grads; then nw loss slots; then nw x 4 x D column sums
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float* sc = sh + (size_t)wib * 2 * n;
+  float* gr = sc + n;
+  float* s_loss = sh + (size_t)nw * 2 * n;
+  float* s_sums = s_loss + nw;
+  const int sub = lane / LPR, li = lane % LPR;
+  const float4* usrc = reinterpret_cast<const float4*>(bu.z ? bu.z : eu);
+  const float4* isrc = reinterpret_cast<const float4*>(bi.z ? bi.z : ei);
+  // per-lane BatchNorm coefficients of its 4 columns: e = z * a + c,  xhat = (z - mean) * invstd
+  float4 ua = make_float4(1.f, 1.f, 1.f, 1.f), uc = make_float4(0.f, 0.f, 0.f, 0.f), um = uc, uis = ua;
+  float4 ia = ua, ic = uc, im = uc, iis = ua;
+  if (bu.z) {
+    um = reinterpret_cast<const float4*>(bu.mean_invstd)[li];
+    uis = reinterpret_cast<const float4*>(bu.mean_invstd + D)[li];
+    const float4 g = reinterpret_cast<const float4*>(bu.gamma)[li], b = reinterpret_cast<const float4*>(bu.beta)[li];
+    ua = make_float4(g.x * uis.x, g.y * uis.y, g.z * uis.z, g.w * uis.w);
+    uc = make_float4(b.x - um.x * ua.x, b.y - um.y * ua.y, b.z - um.z * ua.z, b.w - um.w * ua.w);
+  }
+  if (bi.z) {
+    im = reinterpret_cast<const float4*>(bi.mean_invstd)[li];
+    iis = reinterpret_cast<const float4*>(bi.mean_invstd + D)[li];
+    const float4 g = reinterpret_cast<const float4*>(bi.gamma)[li], b = reinterpret_cast<const float4*>(bi.beta)[li];
+    ia = make_float4(g.x * iis.x, g.y * iis.y, g.z * iis.z, g.w * iis.w);
+    ic = make_float4(b.x - im.x * ia.x, b.y - im.y * ia.y, b.z - im.z * ia.z, b.w - im.w * ia.w);
+  }
+  float4 su0 = make_float4(0.f, 0.f, 0.f, 0.f), su1 = su0, si0 = su0, si1 = su0;  // sum(de), sum(de * xhat)
+  float lsum_total = 0.f;
+  for (int64_t b = blockIdx.x * (int64_t)nw + wib; b < B; b += (int64_t)gridDim.x * nw) {
+    const float4 zu = __ldg(usrc + b * LPR + li);
+    const float4 u4 = make_float4(zu.x * ua.x + uc.x, zu.y * ua.y + uc.y, zu.z * ua.z + uc.z, zu.w * ua.w + uc.w);
+    const float4* items = isrc + b * n * LPR;
+    for (int j0 = 0; j0 < n; j0 += RPP) {
+      const int j = j0 + sub;
+      float dot = 0.f;
+      if (j < n) {
+        const float4 z = __ldg(items + (size_t)j * LPR + li);
+        dot = u4.x * (z.x * ia.x + ic.x) + u4.y * (z.y * ia.y + ic.y) + u4.z * (z.z * ia.z + ic.z) +
+              u4.w * (z.w * ia.w + ic.w);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (li == 0 && j < n) sc[j] = dot;
+    }
+    __syncwarp();
+    float lsum = 0.f;
+    if (loss_kind == SBR_LOSS_BPR) {
+      float s0 = sc[0], g0 = 0.f;
+      for (int j = 1 + lane; j < n; j += 32) {
+        float d = s0 - sc[j];
+        lsum += (d > 0.f ? log1pf(__expf(-d)) : -d + log1pf(__expf(d)));
+        float sg = 1.f / (1.f + __expf(d));  // sigmoid(-d)
+        gr[j] = sg * inv_cnt;
+        g0 -= sg * inv_cnt;
+      }
+      g0 = warp_sum(g0);
+      if (lane == 0) gr[0] = g0;
+    } else if (loss_kind == SBR_LOSS_BCE) {
+      for (int j = lane; j < n; j += 32) {
+        float s = sc[j], y = (j == 0) ? 1.f : 0.f;
+        lsum += (s > 0.f ? s + log1pf(__expf(-s)) : log1pf(__expf(s))) - y * s;
+        gr[j] = (1.f / (1.f + __expf(-s)) - y) * inv_cnt;
+      }
+    } else {
+      float mx = -INFINITY;
+      for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sc[j] + (j > 0 ? ssm_shift : 0.f));
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int j = lane; j < n; j += 32) se += __expf(sc[j] + (j > 0 ? ssm_shift : 0.f) - mx);
+      se = warp_sum(se);
+      float lse = mx + logf(se);
+      for (int j = lane; j < n; j += 32) {
+        float zj = sc[j] + (j > 0 ? ssm_shift : 0.f);
+        gr[j] = (__expf(zj - lse) - (j == 0 ? 1.f : 0.f)) * inv_cnt;
+      }
+      if (lane == 0) lsum = lse - sc[0];
+    }
+    lsum_total += lsum;  // (lane-partial; reduced once at the end)
+    if (logits) {
+      for (int j = lane; j < n; j += 32) logits[b * n + j] = sc[j];
+    }
+    __syncwarp();
+    float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* dit = reinterpret_cast<float4*>(dei + b * n * D);
+    for (int j0 = 0; j0 < n; j0 += RPP) {
+      const int j = j0 + sub;
+      if (j < n) {
+        const float g = gr[j];
+        const float4 z = __ldg(items + (size_t)j * LPR + li);
+        du.x += g * (z.x * ia.x + ic.x); du.y += g * (z.y * ia.y + ic.y);
+        du.z += g * (z.z * ia.z + ic.z); du.w += g * (z.w * ia.w + ic.w);
+        const float4 d = make_float4(g * u4.x, g * u4.y, g * u4.z, g * u4.w);
+        dit[(size_t)j * LPR + li] = d;
+        si0.x += d.x; si0.y += d.y; si0.z += d.z; si0.w += d.w;
+        si1.x += d.x * (z.x - im.x) * iis.x; si1.y += d.y * (z.y - im.y) * iis.y;
+        si1.z += d.z * (z.z - im.z) * iis.z; si1.w += d.w * (z.w - im.w) * iis.w;
+      }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      du.x += __shfl_xor_sync(0xffffffffu, du.x, o);
+      du.y += __shfl_xor_sync(0xffffffffu, du.y, o);
+      du.z += __shfl_xor_sync(0xffffffffu, du.z, o);
+      du.w += __shfl_xor_sync(0xffffffffu, du.w, o);
+    }
+    if (sub == 0) {
+      reinterpret_cast<float4*>(deu + b * D)[li] = du;
+      su0.x += du.x; su0.y += du.y; su0.z += du.z; su0.w += du.w;
+      su1.x += du.x * (zu.x - um.x) * uis.x; su1.y += du.y * (zu.y - um.y) * uis.y;
+      su1.z += du.z * (zu.z - um.z) * uis.z; su1.w += du.w * (zu.w - um.w) * uis.w;
+    }
+    __syncwarp();
+  }
+  // ---- block reductions: loss, BatchNorm-backward column sums
+  lsum_total = warp_sum(lsum_total);
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) {  // item sums live in every sub-group
+    si0.x += __shfl_xor_sync(0xffffffffu, si0.x, o); si0.y += __shfl_xor_sync(0xffffffffu, si0.y, o);
+    si0.z += __shfl_xor_sync(0xffffffffu, si0.z, o); si0.w += __shfl_xor_sync(0xffffffffu, si0.w, o);
+    si1.x += __shfl_xor_sync(0xffffffffu, si1.x, o); si1.y += __shfl_xor_sync(0xffffffffu, si1.y, o);
+    si1.z += __shfl_xor_sync(0xffffffffu, si1.z, o); si1.w += __shfl_xor_sync(0xffffffffu, si1.w, o);
+  }
+  if (lane == 0) s_loss[wib] = lsum_total;
+  if (sub == 0) {
+    float4* row = reinterpret_cast<float4*>(s_sums + (size_t)wib * 4 * D);
+    row[li] = su0; row[LPR + li] = su1; row[2 * LPR + li] = si0; row[3 * LPR + li] = si1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_acc) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += (double)s_loss[w];
+    atomicAdd(loss_acc, t * (double)inv_cnt);
+  }
+  const int rep = blockIdx.x % n_replicas;
+  for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += s_sums[(size_t)w * 4 * D + i];
+    const int which = i / (2 * D), c = i % (2 * D);  // 0: user (sum, sum*xhat), 1: item
+    float* dst = which == 0 ? bu.sums : bi.sums;
+    if (dst != nullptr && t != 0.f) atomicAdd(dst + (size_t)rep * 2 * D + c, t);
+  }
+}
+
 __global__ void aggregate_kernel(const float* __restrict__ e, int64_t rows, int k, int D, int agg_max,
                                  float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int64_t ld_bf16) {
   int64_t total = rows * D;
@@ -308,6 +471,41 @@ extern "C" int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n
   DISPATCH_NV(D, 32, score_loss_kernel<NVv><<<cdiv(B, wpb), wpb * 32, shmem, S(stream)>>>(
                          eu, ei, B, n, ku, ki, D, agg_max_user, agg_max_item, loss_kind, (float)(1.0 / cnt), ssm_shift,
                          logits, loss_acc, deu, dei, u_agg, i_agg));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_score_loss_bn(const float* eu, const sbr_bn_inline_t* bn_u, const float* ei,
+                                 const sbr_bn_inline_t* bn_i, int64_t B, int n, int D, int loss_kind,
+                                 int aggregator_sum, float ssm_shift, float* logits, double* loss_acc, float* deu,
+                                 float* dei, int n_replicas, void* stream) {
+  SBR_REQUIRE((eu || (bn_u && bn_u->z)) && (ei || (bn_i && bn_i->z)) && deu && dei && B > 0 && n >= 1,
+              "sbr_score_loss_bn: bad arguments");
+  SBR_REQUIRE(D == 16 || D == 32 || D == 64 || D == 128, "sbr_score_loss_bn: D=%d not in {16, 32, 64, 128}", D);
+  SBR_REQUIRE(n <= 1024 && n_replicas >= 1, "sbr_score_loss_bn: bad n / n_replicas");
+  SBR_REQUIRE(loss_kind >= 0 && loss_kind <= 2, "sbr_score_loss_bn: unknown loss kind %d", loss_kind);
+  SBR_REQUIRE(!(loss_kind == SBR_LOSS_BPR && n < 2), "sbr_score_loss_bn: BPR needs at least one negative");
+  double cnt = 1.0;
+  if (!aggregator_sum)
+    cnt = loss_kind == SBR_LOSS_BPR ? (double)B * (n - 1) : (loss_kind == SBR_LOSS_BCE ? (double)B * n : (double)B);
+  BnInline bu{nullptr, nullptr, nullptr, nullptr, nullptr}, bi = bu;
+  if (bn_u && bn_u->z) bu = BnInline{bn_u->z, bn_u->mean_invstd, bn_u->gamma, bn_u->beta, bn_u->sums};
+  if (bn_i && bn_i->z) bi = BnInline{bn_i->z, bn_i->mean_invstd, bn_i->gamma, bn_i->beta, bn_i->sums};
+  const int nw = 8;
+  const size_t sm = ((size_t)nw * 2 * n + nw + (size_t)nw * 4 * D) * sizeof(float);
+  int64_t blocks = (B + nw - 1) / nw;
+  const int64_t cap = (int64_t)sbr_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  const float inv = (float)(1.0 / cnt);
+#define SBR_FUSED(LPR_)                                                                                          \
+  score_loss_bn_kernel<LPR_><<<(unsigned)blocks, nw * 32, sm, S(stream)>>>(eu, bu, ei, bi, B, n, loss_kind, inv, \
+                                                                           ssm_shift, logits, loss_acc, deu, dei, \
+                                                                           n_replicas)
+  if (D == 16) SBR_FUSED(4);
+  else if (D == 32) SBR_FUSED(8);
+  else if (D == 64) SBR_FUSED(16);
+  else SBR_FUSED(32);
+#undef SBR_FUSED
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

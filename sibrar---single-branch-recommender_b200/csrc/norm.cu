@@ -133,15 +133,19 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t ld_dy
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
                                     const bf16* __restrict__ y_bf16, int64_t ld_y, int act,
                                     const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ sums, int64_t rows,
-                                    int C, bf16* __restrict__ dz_bf16, int64_t ld_dz, float* __restrict__ dz_f32,
+                                    const float* __restrict__ gamma, const float* __restrict__ sums, int n_replicas,
+                                    int64_t rows, int C, bf16* __restrict__ dz_bf16, int64_t ld_dz, float* __restrict__ dz_f32,
                                     int64_t ld_dz_f32, float* dgamma, float* dbeta, int RB) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   if (c >= C) return;
   const int64_t r0 = (int64_t)blockIdx.x * RB;
   const float inv_n = 1.f / (float)rows;
-  const float s0 = sums[c], s1 = sums[C + c];
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = 0; r < n_replicas; ++r) {
+    s0 += sums[(size_t)r * 2 * C + c];
+    s1 += sums[(size_t)r * 2 * C + C + c];
+  }
   if (blockIdx.x == 0 && ty == 0) {
     if (dbeta) dbeta[c] += s0;
     if (dgamma) dgamma[c] += s1;
@@ -217,13 +221,14 @@ extern "C" int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_
 
 extern "C" int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
                                 int act, const float* z, int64_t ld_z, const float* mean_invstd, const float* gamma,
-                                const float* sums, int64_t rows, int C, void* dz_bf16, int64_t ld_dz, float* dz_f32,
-                                int64_t ld_dz_f32, float* dgamma, float* dbeta, void* stream) {
-  SBR_REQUIRE(dy && z && mean_invstd && gamma && sums && rows > 0 && C > 0, "sbr_bn_bwd_apply: bad arguments");
+                                const float* sums, int n_replicas, int64_t rows, int C, void* dz_bf16, int64_t ld_dz,
+                                float* dz_f32, int64_t ld_dz_f32, float* dgamma, float* dbeta, void* stream) {
+  SBR_REQUIRE(dy && z && mean_invstd && gamma && sums && rows > 0 && C > 0 && n_replicas >= 1,
+              "sbr_bn_bwd_apply: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_apply: activation gradient needs the output y");
   bn_bwd_apply_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(
-      dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, gamma, sums, rows, C,
-      reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta, rows_per_block(rows));
+      dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, gamma, sums, n_replicas,
+      rows, C, reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta, rows_per_block(rows));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

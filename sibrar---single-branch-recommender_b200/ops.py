@@ -6,7 +6,7 @@ import ctypes as C
 
 import torch
 
-from ._lib import ACT, LOSS, AdamTensor, GemmEpilogue, ModalitySrc, call, ptr, stream_ptr
+from ._lib import ACT, LOSS, AdamTensor, BnInline, GemmEpilogue, ModalitySrc, call, ptr, stream_ptr
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -176,10 +176,10 @@ def bn_bwd_reduce(dy, y, act, z, mean_invstd, rows, C_, sums):
 
 
 def bn_bwd_apply(dy, y, act, z, mean_invstd, gamma, sums, rows, C_, dz_bf16=None, dz_f32=None, dgamma=None,
-                 dbeta=None):
+                 dbeta=None, n_replicas=1):
     yf, yb, ldy = _y_args(y)
     call("sbr_bn_bwd_apply", ptr(dy), dy.stride(0), yf, yb, ldy, _act(act), ptr(z), z.stride(0), ptr(mean_invstd),
-         ptr(gamma), ptr(sums), int(rows), int(C_), ptr(dz_bf16), dz_bf16.stride(0) if dz_bf16 is not None else 0,
+         ptr(gamma), ptr(sums), int(n_replicas), int(rows), int(C_), ptr(dz_bf16), dz_bf16.stride(0) if dz_bf16 is not None else 0,
          ptr(dz_f32), dz_f32.stride(0) if dz_f32 is not None else 0, ptr(dgamma), ptr(dbeta), stream_ptr())
 
 
@@ -189,6 +189,24 @@ def score_loss(eu, ei, B, n, ku, ki, D, agg_max_user, agg_max_item, loss_kind, a
     call("sbr_score_loss", ptr(eu), ptr(ei), int(B), int(n), int(ku), int(ki), int(D), int(agg_max_user),
          int(agg_max_item), lk, int(aggregator_sum), float(ssm_shift), ptr(logits), ptr(loss_acc), ptr(deu), ptr(dei),
          ptr(u_agg), ptr(i_agg), stream_ptr())
+
+
+BN_SUM_REPLICAS = 8
+
+
+def score_loss_bn(eu, bn_u, ei, bn_i, B, n, D, loss_kind, aggregator_sum, ssm_shift, logits, loss_acc, deu, dei):
+    """bn_u / bn_i: None or dict(z, mean_invstd, gamma, beta, sums [BN_SUM_REPLICAS, 2 D] zeroed)"""
+    lk = loss_kind if isinstance(loss_kind, int) else LOSS[loss_kind]
+
+    def pack(d):
+        if d is None:
+            return None
+        b = BnInline()
+        b.z, b.mean_invstd, b.gamma, b.beta, b.sums = (ptr(d[k]) for k in ("z", "mean_invstd", "gamma", "beta", "sums"))
+        return C.byref(b)
+    call("sbr_score_loss_bn", ptr(eu), pack(bn_u), ptr(ei), pack(bn_i), int(B), int(n), int(D), lk,
+         int(aggregator_sum), float(ssm_shift), ptr(logits), ptr(loss_acc), ptr(deu), ptr(dei), BN_SUM_REPLICAS,
+         stream_ptr())
 
 
 def infonce(e, G, n, D, temperature, weight, loss_acc, de, accumulate, lse_ws=None):

@@ -178,9 +178,13 @@ class Chain:
             return 1
         return max(1, min(num_kb // 4, (2 * n_sms) // tiles))
 
-    def forward(self, x16, rows, training, arena: ZeroArena, keep_for_backward=True, out32=None):
+    def forward(self, x16, rows, training, arena: ZeroArena, keep_for_backward=True, out32=None,
+                defer_final_bn=False):
+        """``defer_final_bn``: when the chain ends in BatchNorm (no activation after it) the normalised output is not
+        written; ``self.deferred`` = dict(z, mean_invstd, gamma, beta) lets the score/loss kernel apply it inline."""
         dev = self.stages[0].linear.weight.device
         self.rows = rows
+        self.deferred = None
         last = len(self.stages) - 1
         for si, st in enumerate(self.stages):
             final = si == last
@@ -229,18 +233,22 @@ class Chain:
                                     bn.num_batches_tracked, eps=bn.eps, momentum=bn.momentum)
                 else:
                     ops.bn_eval_coeffs(bn.running_mean, bn.running_var, st.out_f, mi, eps=bn.eps)
-                if final:
-                    y32 = out32 if out32 is not None else torch.empty((rows, st.out_f), dtype=F32, device=dev)
+                if final and defer_final_bn and training and st.act2 is None:
+                    self.deferred = dict(z=a32, mean_invstd=mi, gamma=bn.weight.detach(), beta=bn.bias.detach())
                 else:
-                    y16 = torch.empty((rows, out_pad), dtype=BF16, device=dev)
-                ops.bn_apply(a32, mi, bn.weight.detach(), bn.bias.detach(), st.act2, rows, st.out_f, out_bf16=y16,
-                             out_f32=y32)
+                    if final:
+                        y32 = out32 if out32 is not None else torch.empty((rows, st.out_f), dtype=F32, device=dev)
+                    else:
+                        y16 = torch.empty((rows, out_pad), dtype=BF16, device=dev)
+                    ops.bn_apply(a32, mi, bn.weight.detach(), bn.bias.detach(), st.act2, rows, st.out_f, out_bf16=y16,
+                                 out_f32=y32)
             if keep_for_backward:
                 st.x, st.y16, st.y32, st.a32, st.mi = x16, y16, y32, a32, mi
             x16 = y16
         return y32
 
-    def backward(self, dy32, grads: Dict[int, torch.Tensor], need_dx: bool, arena: ZeroArena, zero_dy=False):
+    def backward(self, dy32, grads: Dict[int, torch.Tensor], need_dx: bool, arena: ZeroArena, zero_dy=False,
+                 final_bn_sums=None):
         """dy32: fp32 [rows, out] gradient w.r.t. the chain output.  Accumulates parameter gradients into
         ``grads[id(param)]``; returns fp32 [rows, in] gradient w.r.t. the chain input if ``need_dx``."""
         rows = self.rows
@@ -265,17 +273,20 @@ class Chain:
                                        zero_dy=zero_dy)
                 else:
                     bn = st.bn
-                    sums = arena.take(2 * st.out_f)
-                    ops.bn_bwd_reduce(dy32, y, st.act2, st.a32, st.mi, rows, st.out_f, sums)
+                    if final_bn_sums is not None and si == len(self.stages) - 1:
+                        sums, reps = final_bn_sums, ops.BN_SUM_REPLICAS  # produced by the fused score/loss kernel
+                    else:
+                        sums, reps = arena.take(2 * st.out_f), 1
+                        ops.bn_bwd_reduce(dy32, y, st.act2, st.a32, st.mi, rows, st.out_f, sums)
                     g_gamma, g_beta = grads[id(bn.weight)], grads[id(bn.bias)]
                     if st.act1 is None:
                         # the Linear bias in front of a BatchNorm has an exactly-zero gradient: not computed
                         ops.bn_bwd_apply(dy32, y, st.act2, st.a32, st.mi, bn.weight.detach(), sums, rows, st.out_f,
-                                         dz_bf16=dz16, dgamma=g_gamma, dbeta=g_beta)
+                                         dz_bf16=dz16, dgamma=g_gamma, dbeta=g_beta, n_replicas=reps)
                     else:
                         da32 = torch.empty((rows, st.out_f), dtype=F32, device=dev)
                         ops.bn_bwd_apply(dy32, y, st.act2, st.a32, st.mi, bn.weight.detach(), sums, rows, st.out_f,
-                                         dz_f32=da32, dgamma=g_gamma, dbeta=g_beta)
+                                         dz_f32=da32, dgamma=g_gamma, dbeta=g_beta, n_replicas=reps)
                         ops.actgrad_colsum(da32, st.a32, st.act1, rows, st.out_f, out_bf16=dz16, colsum=g_b)
             # ---- wgrad: dW[out, in] += dz^T x   (contraction over the rows)
             if first_csr:
@@ -428,7 +439,7 @@ class PlainEntity(_EntityBase):
         return ops.make_modality_srcs([dict(kind=SRC_CATEGORICAL, remap=self.df.remap, table=w.detach(), grad=g,
                                             codes=self.df.codes, key_base=0)], w.device)
 
-    def embed(self, idx, training, mods=None, keep_mask=None):
+    def embed(self, idx, training, mods=None, keep_mask=None, defer_final_bn=False):
         self._materialize()
         rt = self._rt()
         flat = idx.reshape(-1).contiguous()
@@ -441,7 +452,7 @@ class PlainEntity(_EntityBase):
         self._ctx = (flat,)
         return out
 
-    def backward(self, dE, grads):
+    def backward(self, dE, grads, final_bn_sums=None):
         rt = self._rt()
         (flat,) = self._ctx
         if self._srcs_grad is None or self._srcs_grad[0] is not grads:
@@ -608,8 +619,10 @@ class SingleBranchNetEntity(_EntityBase):
         ops.sample_modalities(mods, n_idx, k, len(self.mod_names), central, seed, rt.step_dev)
         return mods
 
-    def embed(self, idx, training, mods=None, keep_mask=None):
-        """indices [...] -> per-slot embeddings fp32 [N = numel * k, D] (``_embed``, sgd_alg.py:1865-1877)"""
+    def embed(self, idx, training, mods=None, keep_mask=None, defer_final_bn=False):
+        """indices [...] -> per-slot embeddings fp32 [N = numel * k, D] (``_embed``, sgd_alg.py:1865-1877).
+        With ``defer_final_bn`` (fused trainer) the trailing BatchNorm is left to the score/loss kernel: returns None
+        and ``self.sb_chain.deferred`` describes it."""
         self._materialize()
         rt = self._rt()
         cfg = self.entity_config
@@ -634,16 +647,17 @@ class SingleBranchNetEntity(_EntityBase):
         seed = (int(cfg.sampling_seed) << 8) ^ (0x11 if self.entity_name == "user" else 0x22)
         ops.row_gather_fwd(srcs, len(self.mod_names), flat, mods, k, C_, cfg.normalize_single_branch_input, p_drop,
                            seed, rt.step_dev, keep_mask, out_bf16=x0, err_flag=rt.err_flag)
-        E = self.sb_chain.forward(x0, N, training, rt.arena, keep_for_backward=training)
+        E = self.sb_chain.forward(x0, N, training, rt.arena, keep_for_backward=training,
+                                  defer_final_bn=defer_final_bn and k == 1)
         self._ctx = (flat, mods, keep_mask, k, p_drop, seed)
         return E
 
-    def backward(self, dE, grads):
+    def backward(self, dE, grads, final_bn_sums=None):
         rt = self._rt()
         cfg = self.entity_config
         flat, mods, keep_mask, k, p_drop, seed = self._ctx
         C_ = cfg.common_modality_dim
-        dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena)
+        dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena, final_bn_sums=final_bn_sums)
         srcs = self._src_blob(grads)
         plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
         plan.build(srcs, len(self.mod_names), flat, mods, k)

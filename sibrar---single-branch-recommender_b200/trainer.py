@@ -121,23 +121,40 @@ class FusedTrainer:
         D = m.config.shared_common_dim
         ops.tick(rt.step_dev)
         rt.arena.reset()
-        Eu = self.user.embed(u_idxs, True, mods.get("user"), keep_masks.get("user"))
-        Ei = self.item.embed(i_idxs, True, mods.get("item"), keep_masks.get("item"))
         ku, ki = self.user.k_train, self.item.k_train
-        dEu, dEi = torch.empty_like(Eu), torch.empty_like(Ei)
+        # entities that end in a BatchNorm leave it to the score/loss kernel (no normalised copy, no separate
+        # BatchNorm-backward reduction) when there is one modality slot per entity and D fits the fused kernel
+        fuse = ku == 1 and ki == 1 and D in (16, 32, 64, 128) and not self.user.reg_enabled and not self.item.reg_enabled
+        Eu = self.user.embed(u_idxs, True, mods.get("user"), keep_masks.get("user"), defer_final_bn=fuse)
+        Ei = self.item.embed(i_idxs, True, mods.get("item"), keep_masks.get("item"), defer_final_bn=fuse)
         if self.logits is None or self.logits.shape != (B, n):
-            self.logits = torch.empty((B, n), dtype=F32, device=Eu.device)
-        ops.score_loss(Eu, Ei, B, n, ku, ki, D, self.user.agg_max, self.item.agg_max, self.learn.rec_loss,
-                       self.learn.loss_aggregator == "sum", self.ssm_shift, self.logits, self.loss_acc[0:1], dEu, dEi)
+            self.logits = torch.empty((B, n), dtype=F32, device=u_idxs.device)
+        bn_u = bn_i = None
+        if Eu is None or Ei is None:
+            def inline(ent):
+                d = dict(ent.sb_chain.deferred)
+                d["sums"] = rt.arena.take(ops.BN_SUM_REPLICAS * 2 * D)
+                return d
+            bn_u = inline(self.user) if Eu is None else None
+            bn_i = inline(self.item) if Ei is None else None
+            dEu = torch.empty((B, D), dtype=F32, device=u_idxs.device)
+            dEi = torch.empty((B * n, D), dtype=F32, device=u_idxs.device)
+            ops.score_loss_bn(Eu, bn_u, Ei, bn_i, B, n, D, self.learn.rec_loss, self.learn.loss_aggregator == "sum",
+                              self.ssm_shift, self.logits, self.loss_acc[0:1], dEu, dEi)
+        else:
+            dEu, dEi = torch.empty_like(Eu), torch.empty_like(Ei)
+            ops.score_loss(Eu, Ei, B, n, ku, ki, D, self.user.agg_max, self.item.agg_max, self.learn.rec_loss,
+                           self.learn.loss_aggregator == "sum", self.ssm_shift, self.logits, self.loss_acc[0:1], dEu,
+                           dEi)
         if self.user.reg_enabled:
             c = self.user.entity_config
             ops.infonce(Eu, 1, B, D, c.regularization_temperature, c.regularization_weight, self.loss_acc[1:2], dEu, 1)
         if self.item.reg_enabled:
             c = self.item.entity_config
             ops.infonce(Ei, B, n, D, c.regularization_temperature, c.regularization_weight, self.loss_acc[2:3], dEi, 1)
-        self.item.backward(dEi, self.grads)
+        self.item.backward(dEi, self.grads, final_bn_sums=bn_i["sums"] if bn_i else None)
         self._after_item_backward()
-        self.user.backward(dEu, self.grads)
+        self.user.backward(dEu, self.grads, final_bn_sums=bn_u["sums"] if bn_u else None)
         self._after_user_backward()
         if apply_optimizer:
             self.optimizer_step()

@@ -103,11 +103,12 @@ def test_fused_step_and_eval_call_sequence(name, monkeypatch):
     tr.step(torch.from_numpy(u), torch.from_numpy(i))
     seq = stub.calls
     assert seq[0] == "sbr_tick" and seq[-1] == "sbr_adam_step"
-    assert "sbr_score_loss" in seq and "sbr_row_gather_fwd" in seq and "sbr_row_gather_bwd_segmented" in seq
+    score = "sbr_score_loss_bn" if "sbr_score_loss_bn" in seq else "sbr_score_loss"
+    assert score in seq and "sbr_row_gather_fwd" in seq and "sbr_row_gather_bwd_segmented" in seq
     assert seq.index("sbr_gather_plan") < seq.index("sbr_row_gather_bwd_segmented")
     assert seq.count("sbr_gemm_bf16") >= 3  # forward, wgrad, dgrad GEMMs on the tensor cores
     assert ("sbr_infonce" in seq) == (model.user_embedding_module.reg_enabled or model.item_embedding_module.reg_enabled)
-    assert seq.index("sbr_score_loss") < seq.index("sbr_row_gather_bwd_segmented") < seq.index("sbr_adam_step")
+    assert seq.index(score) < seq.index("sbr_row_gather_bwd_segmented") < seq.index("sbr_adam_step")
     assert set(tr.read_losses()) >= {"train/loss", "train/rec_loss", "train/reg_loss"}
     stub.calls.clear()
     res = FullEvaluator(dict(top_k=[1, 3, 5], metrics=["ndcg", "recall", "coverage"], calculate_std=True)).evaluate(

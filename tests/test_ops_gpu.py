@@ -292,6 +292,42 @@ def test_score_loss(loss, agg_u, agg_i, ku, ki, sum_):
     assert _relerr(deu, eu.grad) < 1e-4 and _relerr(dei, ei.grad) < 1e-4
 
 
+@pytest.mark.parametrize("loss,D,n,bn_user,bn_item", [("bpr", 64, 11, True, True), ("bce", 32, 4, False, True),
+                                                     ("sampled_softmax", 128, 7, True, False), ("bpr", 16, 3, True, True)])
+def test_score_loss_bn_matches_unfused(loss, D, n, bn_user, bn_item):
+    """fused (inline BatchNorm + BatchNorm-backward sums) == bn_apply -> score_loss -> bn_bwd_reduce"""
+    B = 1000
+    g = torch.Generator().manual_seed(D + n)
+    zu, zi = torch.randn(B, D, generator=g).to(DEV), (torch.randn(B * n, D, generator=g) * 1.5 + 0.3).to(DEV)
+
+    def side(z, use_bn, seed):
+        gg = torch.Generator().manual_seed(seed)
+        if not use_bn:
+            return z, None
+        mi = torch.cat([z.mean(0), 1.0 / torch.sqrt(z.var(0, unbiased=False) + 1e-5)]).contiguous()
+        gamma, beta = (torch.rand(D, generator=gg) + 0.5).to(DEV), torch.randn(D, generator=gg).to(DEV)
+        e = torch.empty_like(z)
+        ops.bn_apply(z, mi, gamma, beta, None, z.shape[0], D, out_f32=e)
+        return e, dict(z=z, mean_invstd=mi, gamma=gamma, beta=beta,
+                       sums=torch.zeros(ops.BN_SUM_REPLICAS * 2 * D, device=DEV))
+    eu, bu = side(zu, bn_user, 1)
+    ei, bi = side(zi, bn_item, 2)
+    lg0, lg1 = torch.empty(B, n, device=DEV), torch.empty(B, n, device=DEV)
+    acc0, acc1 = torch.zeros(1, dtype=torch.float64, device=DEV), torch.zeros(1, dtype=torch.float64, device=DEV)
+    du0, di0, du1, di1 = (torch.empty_like(t) for t in (eu, ei, eu, ei))
+    ops.score_loss(eu, ei, B, n, 1, 1, D, 0, 0, loss, 0, 0.3, lg0, acc0, du0, di0)
+    ops.score_loss_bn(None if bu else eu, bu, None if bi else ei, bi, B, n, D, loss, 0, 0.3, lg1, acc1, du1, di1)
+    assert _relerr(lg1, lg0) < 1e-5 and abs(acc1.item() - acc0.item()) < 1e-6 * max(1.0, abs(acc0.item()))
+    assert _relerr(du1, du0) < 1e-5 and _relerr(di1, di0) < 1e-5
+    for z, b, d in ((zu, bu, du0), (zi, bi, di0)):
+        if b is None:
+            continue
+        ref = torch.zeros(2 * D, device=DEV)
+        ops.bn_bwd_reduce(d, None, None, z, b["mean_invstd"], z.shape[0], D, ref)
+        got = b["sums"].view(ops.BN_SUM_REPLICAS, 2 * D).sum(0)
+        assert _relerr(got, ref) < 1e-4
+
+
 @pytest.mark.parametrize("G,n,D", [(9, 5, 24), (1, 70, 16), (300, 11, 64)])
 def test_infonce(G, n, D):
     from oracle import sbnet_oracle as O
