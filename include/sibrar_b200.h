@@ -70,6 +70,14 @@ typedef struct {
 int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,
                   int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream);
 
+/* Same GEMM with a BIT-PACKED 0/1 A operand (K-major): bit k of row m = A_bits[m * ld_words + k / 32] >> (k % 32).
+ * The multi-hot 'interactions' rows (data/Feature.py:147-150: csr.toarray() per batch in the reference) stay packed in
+ * HBM (1 bit per element) and are expanded to bf16 in shared memory inside the kernel.  ld_words is even and covers
+ * whole 64-bit K blocks; bits at k >= K are zero.  Used for the forward projection (A = the entity's interaction
+ * matrix) and for its wgrad (A = the transposed matrix, output written transposed). */
+int sbr_gemm_bits_bf16(const uint32_t* A_bits, int64_t ld_words, const void* B, int64_t ldb, int b_mn_major, int64_t M,
+                       int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ casts / fills */
 int sbr_cast_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols,
                          void* stream); /* dst columns [cols, ld_dst) are zero-filled */
@@ -115,7 +123,7 @@ typedef struct {
 
 /* X[r, :] = dropout(normalize(src_{mods[r]}(idx[r / k])))  written as bf16 (algorithms/sgd_alg.py:1934-1978,
  * 1865-1876) and/or fp32.  srcs_dev: device array [n_mods].  keep_mask (optional, uint8 [N, C]) overrides the
- * Philox mask.  err_flag is set to 1 when an entity index has no feature row (KeyError at data/Feature.py:146). */
+ * counter-based hash mask keyed by (row, column group, seed, step).  err_flag is set to 1 when an entity index has no feature row (KeyError at data/Feature.py:146). */
 int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
                        int64_t n_idx, int k, int C, int normalize, float p_drop, uint64_t seed,
                        const int64_t* step_dev, const uint8_t* keep_mask, void* out_bf16, int64_t ld_out,

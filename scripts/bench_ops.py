@@ -36,3 +36,18 @@ for split in (1, 37, 148, 296):
     timeit(f"gemm wgrad 64x64xM split_k={split}", lambda: ops.gemm(x, y16, 64, 64, M, a_mn=True, b_mn=True, out_f32=gw, transpose_out=True, atomic_out=True, split_k=split), M * 64 * 4)
 timeit("torch copy bf16->bf16 (reference point)", lambda: y16.copy_(x), M * 64 * 4)
 timeit("torch matmul bf16", lambda: torch.matmul(x, w.t(), out=y16), M * 64 * 4)
+
+# ---- small table-level kernels
+rows = 3706
+dy = torch.randn(rows, 64, device=dev)
+yt = torch.randn(rows, 64, device=dev)
+o16 = torch.empty(rows, 64, dtype=BF16, device=dev)
+cs = torch.zeros(64, device=dev)
+timeit("actgrad_colsum [3706 x 64] (+zero_dy, bf16 out, colsum)", lambda: ops.actgrad_colsum(dy, yt, "relu", rows, 64, out_bf16=o16, colsum=cs, zero_dy=True), rows * 64 * 14)
+big = torch.randn(M, 64, device=dev)
+mi = torch.cat([torch.zeros(64, device=dev), torch.ones(64, device=dev)])
+g1 = torch.ones(64, device=dev)
+sums = torch.zeros(128, device=dev)
+timeit("bn_apply [M x 64] f32 -> f32", lambda: ops.bn_apply(big, mi, g1, g1, None, M, 64, out_f32=y32), M * 64 * 8)
+timeit("bn_bwd_reduce [M x 64]", lambda: ops.bn_bwd_reduce(big, None, None, y32, mi, M, 64, sums), M * 64 * 8)
+timeit("bn_bwd_apply [M x 64] -> bf16", lambda: ops.bn_bwd_apply(big, None, None, y32, mi, g1, sums, M, 64, dz_bf16=y16), M * 64 * 10)

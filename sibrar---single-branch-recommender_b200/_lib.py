@@ -43,6 +43,7 @@ class AdamTensor(C.Structure):
 
 _PROTOS = {
     "sbr_gemm_bf16": [c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, c_i64, c_i64, c_i64, C.POINTER(GemmEpilogue), c_vp],
+    "sbr_gemm_bits_bf16": [c_vp, c_i64, c_vp, c_i64, C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp],
     "sbr_cast_f32_to_bf16": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "sbr_transpose_f32_to_bf16": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "sbr_transpose_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],

@@ -65,9 +65,17 @@ __device__ __forceinline__ void load_source_row(const sbr_modality_src_t& s, int
 // Dropout keep decision of element (row r, column c): explicit mask, or 16 random bits of the Philox block of the
 // 8-column group c / 8 (one Philox call serves 8 elements; keep iff bits >= p * 65536).
 __device__ __forceinline__ uint32_t drop_threshold(float p_drop) { return (uint32_t)ceilf(p_drop * 65536.f); }
+// 128 random bits of the dropout block (row r, 8-column group c8): four murmur3-finalised words of a counter that
+// mixes (r, c8, seed, step) -- a counter-based generator like Philox4x32-10 at a quarter of its instruction count
+// (the mask only has to be reproducible between forward and backward and statistically flat).
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
 __device__ __forceinline__ uint4 philox_group(int64_t r, int c8, uint64_t seed, uint64_t step) {
-  return philox4x32(make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)c8, 0x64726f70u),
-                    make_uint2((uint32_t)seed ^ (uint32_t)step, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
+  const uint32_t k0 = fmix32((uint32_t)seed ^ ((uint32_t)step * 0x9E3779B1u)) ^ (uint32_t)(seed >> 32);
+  const uint32_t x = ((uint32_t)r * 0x9E3779B1u) ^ ((uint32_t)(r >> 32) * 0x7FEB352Du) ^ ((uint32_t)c8 * 0x846CA68Bu) ^ k0;
+  return make_uint4(fmix32(x), fmix32(x + 0x68E31DA4u), fmix32(x + 0xB5297A4Du), fmix32(x + 0x1B56C4E9u));
 }
 __device__ __forceinline__ uint32_t philox_lane16(const uint4& blk, int j) {  // j in [0, 8)
   const uint32_t w = (j >> 1) == 0 ? blk.x : ((j >> 1) == 1 ? blk.y : ((j >> 1) == 2 ? blk.z : blk.w));

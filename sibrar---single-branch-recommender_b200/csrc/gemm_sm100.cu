@@ -19,6 +19,8 @@ constexpr int A_STAGE_BYTES = BM * 128;  // 16 KiB
 
 struct GemmParams {
   int64_t M, N, K;
+  const uint32_t* a_bits;  // A_BITS kernels: A is a 0/1 matrix, bit k of row m = a_bits[m * ld_words + k / 32] >> (k % 32)
+  int64_t ld_words;
   int a_mn, b_mn;
   int kb_per_split, num_kb;
   sbr_gemm_epilogue_t ep;
@@ -93,8 +95,12 @@ __device__ __forceinline__ void apply_actgrad32(int act, float (&v)[32], const f
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(192)
+// A_BITS: the A operand is a bit-packed 0/1 matrix (multi-hot 'interactions' rows, data/Feature.py:147-150).  Four extra
+// warps expand it into the bf16 SWIZZLE_128B K-major stage in shared memory (thread = tile row, 64 bits -> eight
+// 16-byte chunks per K block through a 16-entry nibble table), so HBM sees 1 bit per element instead of 16 and the
+// tensor cores see ordinary bf16 operands; the TMA producer then only loads B.
+template <int BN, bool A_BITS>
+__global__ void __launch_bounds__(A_BITS ? 320 : 192)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -106,9 +112,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + C::STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint2* s_lut = reinterpret_cast<uint2*>(tmem_slot + 2);  // A_BITS: nibble -> four bf16 (0.0 | 1.0)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (A_BITS && threadIdx.x < 16) {
+    const uint32_t t = threadIdx.x;
+    s_lut[t] = make_uint2(((t & 1u) ? 0x3F80u : 0u) | ((t & 2u) ? 0x3F800000u : 0u),
+                          ((t & 4u) ? 0x3F80u : 0u) | ((t & 8u) ? 0x3F800000u : 0u));
+  }
   // persistent over the M tiles: CTA x handles tiles x, x + gridDim.x, ...; the two TMEM accumulators let the MMA of
   // tile t+1 run while the epilogue warps drain tile t (skinny layers are bound by the epilogue's HBM traffic)
   const int num_m_tiles = (int)((p.M + BM - 1) / BM);
@@ -120,7 +132,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], A_BITS ? 5 : 1);  // TMA (+ the four converter warps)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -144,10 +156,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[s], (A_BITS ? 0 : A_STAGE_BYTES) + C::B_STAGE_BYTES);
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
-          if (!p.a_mn) {
+          if (A_BITS) {
+            // A is written by the converter warps
+          } else if (!p.a_mn) {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
           } else {
 #pragma unroll
@@ -199,6 +213,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (elect_one()) umma_commit(&tfull_bar[acc]);
       __syncwarp();
+    }
+  } else if (A_BITS && warp >= 6) {
+    // ------------------------------------------------------------------ bit -> bf16 converters (thread = tile row)
+    const int row_in_tile = threadIdx.x - 192;
+    const uint32_t sw = (uint32_t)(row_in_tile & 7);
+    const uint32_t row_off = (uint32_t)((row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
+      const int64_t row = (int64_t)tile * BM + row_in_tile;
+      const uint2* bits = reinterpret_cast<const uint2*>(p.a_bits + (row < p.M ? row : 0) * p.ld_words);
+      uint2 w_next = make_uint2(0u, 0u);
+      if (row < p.M && kb_begin < kb_end) w_next = __ldg(bits + kb_begin);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const uint2 w = w_next;
+        if (row < p.M && kb + 1 < kb_end) w_next = __ldg(bits + kb + 1);  // 64 bits = one K block of this row
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* dst = sA + s * A_STAGE_BYTES + row_off;
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {  // chunk c = K elements 8c .. 8c+7 -> 16 bytes at the swizzled position
+          const uint32_t byte = ((c < 4 ? w.x : w.y) >> ((c & 3) * 8)) & 0xFFu;
+          const uint2 lo = s_lut[byte & 15u], hi = s_lut[byte >> 4];
+          *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
@@ -348,11 +391,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN>
+template <int BN, bool A_BITS>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SBR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg<BN>::SMEM_BYTES));
     configured = true;
   }
@@ -361,7 +404,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   int64_t gx = (sbr_num_sms() * ctas_per_sm) / (n_tiles * splits);
   gx = gx < 1 ? 1 : (gx > m_tiles ? m_tiles : gx);
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);
-  gemm_bf16_kernel<BN><<<grid, 192, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN, A_BITS><<<grid, A_BITS ? 320 : 192, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -439,9 +482,53 @@ extern "C" int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
   p.ep = *ep;
   if (p.ep.alpha == 0.f) p.ep.alpha = 1.f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  p.a_bits = nullptr;
+  p.ld_words = 0;
   switch (BN) {
-    case 64: return launch_gemm<64>(tmA, tmB, p, splits, st);
-    case 128: return launch_gemm<128>(tmA, tmB, p, splits, st);
-    default: return launch_gemm<256>(tmA, tmB, p, splits, st);
+    case 64: return launch_gemm<64, false>(tmA, tmB, p, splits, st);
+    case 128: return launch_gemm<128, false>(tmA, tmB, p, splits, st);
+    default: return launch_gemm<256, false>(tmA, tmB, p, splits, st);
+  }
+}
+
+extern "C" int sbr_gemm_bits_bf16(const uint32_t* A_bits, int64_t ld_words, const void* B, int64_t ldb, int b_mn_major,
+                                  int64_t M, int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream) {
+  SBR_REQUIRE(A_bits && B && ep, "sbr_gemm_bits_bf16: null operand");
+  SBR_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31),
+              "sbr_gemm_bits_bf16: bad problem M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  const int num_kb = (int)((K + BK - 1) / BK);
+  SBR_REQUIRE(ld_words % 2 == 0 && ld_words >= 2 * (int64_t)num_kb &&
+                  (reinterpret_cast<uintptr_t>(A_bits) & 7) == 0,
+              "sbr_gemm_bits_bf16: rows must be 8-byte aligned and padded to whole 64-bit K blocks (ld_words=%lld)",
+              (long long)ld_words);
+  SBR_REQUIRE(ep->out_bf16 || ep->out_f32 || ep->colstats, "sbr_gemm_bits_bf16: no output requested");
+  SBR_REQUIRE(!(ep->transpose_out && ep->out_bf16), "sbr_gemm_bits_bf16: transposed output is fp32 only");
+  int splits = ep->split_k < 1 ? 1 : ep->split_k;
+  if (splits > num_kb) splits = num_kb;
+  SBR_REQUIRE(splits == 1 || (ep->atomic_out && !ep->out_bf16 && !ep->colstats && !ep->bias &&
+                              ep->act == SBR_ACT_NONE && !ep->actgrad_y),
+              "sbr_gemm_bits_bf16: split_k > 1 needs a pure atomic fp32 epilogue");
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap tmB;
+  int rc;
+  if (!b_mn_major) rc = sbr_make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)BN);
+  else rc = sbr_make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_bits = A_bits;
+  p.ld_words = ld_words;
+  p.a_mn = 0;
+  p.b_mn = b_mn_major ? 1 : 0;
+  p.num_kb = num_kb;
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.ep = *ep;
+  if (p.ep.alpha == 0.f) p.ep.alpha = 1.f;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (BN) {
+    case 64: return launch_gemm<64, true>(tmB, tmB, p, splits, st);
+    case 128: return launch_gemm<128, true>(tmB, tmB, p, splits, st);
+    default: return launch_gemm<256, true>(tmB, tmB, p, splits, st);
   }
 }

@@ -7,6 +7,8 @@ HBM layout per feature (row = position in the feature's value table, NOT the ent
   * ``remap``  int32 [n_entities]  entity index -> row (-1: entity has no row; identity maps are dropped)
   * dense (VECTOR / CONTINUOUS / DISCRETE, and 'interactions' when dense enough):
         ``x16`` bf16 [n_rows, pad8(d)]  row-major -- read K-major by the forward GEMM and MN-major by the wgrad GEMM
+  * bits ('interactions', density >= 0.4 %): ``bits`` int32 [n_rows, 2*ceil(d/64)] and ``bits_t`` of the transposed
+        matrix -- 1 bit per element; expanded to bf16 in shared memory by the GEMM (sbr_gemm_bits_bf16)
   * csr ('interactions', sparse route): ``indptr`` int64 / ``indices`` int32 of the matrix and of its transpose
   * CATEGORICAL: ``codes`` int32 [n_rows];  TAG: ``codes`` int32 [n_rows, max_tags] padded with ``pad_id``
 """
@@ -38,7 +40,7 @@ class DeviceFeature:
             remap = np.full(n_entities, -1, dtype=np.int32)
             remap[idx] = np.arange(len(idx), dtype=np.int32)
             self.remap = torch.from_numpy(remap).to(device)
-        self.x16 = self.csr = self.csr_t = self.codes = None
+        self.x16 = self.csr = self.csr_t = self.codes = self.bits = self.bits_t = None
         self.max_tags, self.pad_id, self.n_cat = 0, -1, 0
         if self.type == "categorical":
             self.kind = "categorical"
@@ -61,7 +63,14 @@ class DeviceFeature:
             dense_bytes = m.shape[0] * ops.pad8(m.shape[1]) * 2
             ip = torch.from_numpy(m.indptr.astype(np.int64)).to(device)
             ix = torch.from_numpy(m.indices.astype(np.int32)).to(device)
-            if density >= dense_min_density and dense_bytes <= dense_max_bytes:
+            binary = m.nnz == 0 or bool(np.all(m.data == 1))
+            if density >= dense_min_density and binary and m.shape[0] * m.shape[1] // 4 <= dense_max_bytes:
+                # bit-packed multi-hot rows (and the transposed matrix for the wgrad), 1 bit per element in HBM:
+                # the projection is a tcgen05 GEMM whose A operand is expanded to bf16 in shared memory
+                self.kind = "bits"
+                self.bits = ops.pack_bits(m, device)
+                self.bits_t = ops.pack_bits(m.T.tocsr(), device)
+            elif density >= dense_min_density and dense_bytes <= dense_max_bytes:
                 # dense bf16 multi-hot, resident in HBM: the projection becomes a tcgen05 GEMM
                 self.kind = "dense"
                 self.x16 = ops.csr_to_dense_bf16(ip, ix, m.shape[0], m.shape[1])
@@ -85,7 +94,7 @@ class DeviceFeature:
 
     def nbytes(self) -> int:
         n = 0
-        for t in (self.remap, self.x16, self.codes):
+        for t in (self.remap, self.x16, self.codes, self.bits, self.bits_t):
             if t is not None:
                 n += t.numel() * t.element_size()
         for pair in (self.csr, self.csr_t):

@@ -19,12 +19,8 @@ def _act(a):
     return a if isinstance(a, int) else ACT[a]
 
 
-def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, act=None, out_bf16=None,
-         out_f32=None, colstats=None, colstats_sum_only=False, actgrad_y=None, actgrad_act=None, transpose_out=False, atomic_out=False,
-         split_k=1, alpha=1.0):
-    """D[M,N] = alpha * A @ B^T (bf16 in, fp32 accumulate) + fused epilogue.  A/B: 2-D bf16 tensors whose last
-    dimension is contiguous; K-major means [rows, K], MN-major means [K, rows]."""
-    assert A.dtype == BF16 and B.dtype == BF16 and A.stride(-1) == 1 and B.stride(-1) == 1
+def _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad_y, actgrad_act, transpose_out,
+              atomic_out, split_k, alpha):
     ep = GemmEpilogue()
     ep.bias = ptr(bias)
     ep.act = _act(act)
@@ -41,8 +37,40 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None
     ep.atomic_out = int(atomic_out)
     ep.split_k = int(split_k)
     ep.alpha = float(alpha)
+    return ep
+
+
+def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, act=None, out_bf16=None,
+         out_f32=None, colstats=None, colstats_sum_only=False, actgrad_y=None, actgrad_act=None, transpose_out=False, atomic_out=False,
+         split_k=1, alpha=1.0):
+    """D[M,N] = alpha * A @ B^T (bf16 in, fp32 accumulate) + fused epilogue.  A/B: 2-D bf16 tensors whose last
+    dimension is contiguous; K-major means [rows, K], MN-major means [K, rows]."""
+    assert A.dtype == BF16 and B.dtype == BF16 and A.stride(-1) == 1 and B.stride(-1) == 1
+    ep = _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad_y, actgrad_act, transpose_out,
+                   atomic_out, split_k, alpha)
     call("sbr_gemm_bf16", ptr(A), lda if lda is not None else A.stride(0), int(a_mn), ptr(B),
          ldb if ldb is not None else B.stride(0), int(b_mn), int(M), int(N), int(K), C.byref(ep), stream_ptr())
+
+
+def gemm_bits(A_bits, B, M, N, K, *, b_mn=False, bias=None, act=None, out_bf16=None, out_f32=None, colstats=None,
+              colstats_sum_only=False, transpose_out=False, atomic_out=False, split_k=1, alpha=1.0):
+    """the same with a bit-packed 0/1 A operand: int32 [M, ld_words], bit k of row m = word k // 32, bit k % 32"""
+    assert A_bits.dtype == torch.int32 and A_bits.stride(-1) == 1 and B.dtype == BF16 and B.stride(-1) == 1
+    ep = _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, None, None, transpose_out, atomic_out,
+                   split_k, alpha)
+    call("sbr_gemm_bits_bf16", ptr(A_bits), A_bits.stride(0), ptr(B), B.stride(0), int(b_mn), int(M), int(N), int(K),
+         C.byref(ep), stream_ptr())
+
+
+def pack_bits(csr, device) -> torch.Tensor:
+    """scipy CSR 0/1 matrix -> int32 [rows, ld_words] bit matrix (ld_words even, whole 64-bit K blocks, zero padded)"""
+    import numpy as np
+    rows, cols = csr.shape
+    ld_words = 2 * ((cols + 63) // 64)
+    out = np.zeros((rows, ld_words), dtype=np.uint32)
+    coo = csr.tocoo()
+    np.bitwise_or.at(out, (coo.row, coo.col // 32), (np.uint32(1) << (coo.col % 32).astype(np.uint32)))
+    return torch.from_numpy(out.view(np.int32)).to(device)
 
 
 def cast_bf16(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:

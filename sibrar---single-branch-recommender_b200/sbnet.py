@@ -169,6 +169,10 @@ class Chain:
     def csr_input(self):
         return self.feature is not None and self.feature.kind == "csr"
 
+    @property
+    def bits_input(self):
+        return self.feature is not None and self.feature.kind == "bits"
+
     @staticmethod
     def _fwd_split_k(rows, st, n_sms: int = 148) -> int:
         bn = 64 if st.out_f <= 64 else (128 if st.out_f <= 128 else 256)
@@ -205,12 +209,14 @@ class Chain:
                     if y16 is not None:
                         ops.cast_bf16(y32, y16)
                 else:
+                    first_bits = si == 0 and self.bits_input
+                    mm = (lambda *a, **k: ops.gemm_bits(self.feature.bits, *a[1:], **k)) if first_bits else ops.gemm
                     split = self._fwd_split_k(rows, st)
                     if split > 1:
                         # few output tiles, long contraction (an 'interactions' table): split K over the SMs into a
                         # zeroed fp32 buffer, then one pass applies bias + activation (y = act(1 * (z - 0) * 1 + bias))
                         z32 = torch.zeros((rows, st.out_f), dtype=F32, device=dev)
-                        ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, out_f32=z32, atomic_out=True, split_k=split)
+                        mm(x16, st.w16, rows, st.out_f, st.in_f, out_f32=z32, atomic_out=True, split_k=split)
                         if st.unit_mi is None or st.unit_mi.device != dev:
                             st.unit_mi = torch.cat([torch.zeros(st.out_f, device=dev), torch.ones(st.out_f, device=dev)])
                             st.ones = torch.ones(st.out_f, device=dev)
@@ -218,8 +224,7 @@ class Chain:
                         ops.bn_apply(z32, st.unit_mi, st.ones, bias if bias is not None else st.zero_bias, st.act1,
                                      rows, st.out_f, out_bf16=y16, out_f32=y32)
                     else:
-                        ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_bf16=y16,
-                                 out_f32=y32)
+                        mm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_bf16=y16, out_f32=y32)
             else:
                 bn = st.bn
                 a32 = torch.empty((rows, st.out_f), dtype=F32, device=dev)
@@ -227,7 +232,12 @@ class Chain:
                 stats = arena.take(2 * st.out_f) if training else None
                 if first_csr:
                     raise NotImplementedError("BatchNorm directly on a sparse feature projection")
-                ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_f32=a32, colstats=stats)
+                if si == 0 and self.bits_input:
+                    ops.gemm_bits(self.feature.bits, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1,
+                                  out_f32=a32, colstats=stats)
+                else:
+                    ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_f32=a32,
+                             colstats=stats)
                 if training:
                     ops.bn_finalize(stats, rows, st.out_f, mi, bn.running_mean, bn.running_var,
                                     bn.num_batches_tracked, eps=bn.eps, momentum=bn.momentum)
@@ -296,8 +306,13 @@ class Chain:
                 x16 = st.x if si > 0 or self.feature is None else self.feature.x16
                 tiles = -(-st.in_f // 128) * -(-st.out_f // (64 if st.out_f <= 64 else 128 if st.out_f <= 128 else 256))
                 split = max(1, min(-(-rows // 64), (2 * n_sms) // max(1, tiles)))
-                ops.gemm(x16, dz16, st.in_f, st.out_f, rows, a_mn=True, b_mn=True, out_f32=g_w, transpose_out=True,
-                         atomic_out=True, split_k=split)
+                if si == 0 and self.bits_input:
+                    # dW^T [in, out] = X^T dZ with X^T = the transposed bit matrix as the K-major A operand
+                    ops.gemm_bits(self.feature.bits_t, dz16, st.in_f, st.out_f, rows, b_mn=True, out_f32=g_w,
+                                  transpose_out=True, atomic_out=True, split_k=split)
+                else:
+                    ops.gemm(x16, dz16, st.in_f, st.out_f, rows, a_mn=True, b_mn=True, out_f32=g_w,
+                             transpose_out=True, atomic_out=True, split_k=split)
             # ---- dgrad
             if si > 0:
                 prev = self.stages[si - 1]

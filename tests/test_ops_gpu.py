@@ -78,6 +78,34 @@ def test_gemm_dgrad_b_mn_major_actgrad(rows, din, dout):
     assert _relerr(stats[:din], ref.sum(0)) < 1e-3
 
 
+@pytest.mark.parametrize("rows,d,out,density", [(300, 200, 64, 0.05), (1000, 6040, 64, 0.04), (257, 130, 24, 0.3),
+                                                  (3706, 777, 128, 0.02)])
+def test_gemm_bits_matches_dense(rows, d, out, density):
+    """bit-packed multi-hot A operand == the same GEMM on the dense bf16 matrix (forward and wgrad forms)"""
+    import scipy.sparse as sp
+    m = sp.random(rows, d, density=density, format="csr", random_state=rows + d)
+    m.data[:] = 1
+    dense = torch.from_numpy(m.toarray().astype(np.float32)).to(DEV)
+    x16 = ops.cast_bf16(dense)
+    bits, bits_t = ops.pack_bits(m, DEV), ops.pack_bits(m.T.tocsr(), DEV)
+    w = _rand_bf16(out, ops.pad8(d), seed=3)[:, :d]
+    bias = torch.randn(out, device=DEV)
+    y_ref, y = torch.empty(rows, out, device=DEV), torch.empty(rows, out, device=DEV)
+    ops.gemm(x16, w, rows, out, d, bias=bias, act="relu", out_f32=y_ref)
+    ops.gemm_bits(bits, w, rows, out, d, bias=bias, act="relu", out_f32=y)
+    assert torch.equal(y, y_ref)
+    # split-K forward (atomic fp32): same sum, different order
+    z = torch.zeros(rows, out, device=DEV)
+    ops.gemm_bits(bits, w, rows, out, d, out_f32=z, atomic_out=True, split_k=3)
+    assert _relerr(torch.relu(z + bias), y_ref) < 1e-5
+    # wgrad form: dW [out, d] = dZ^T X  computed as (X^T dZ)^T with the transposed bit matrix as A
+    dz = _rand_bf16(rows, ops.pad8(out), seed=4)[:, :out]
+    g_ref, g = torch.zeros(out, d, device=DEV), torch.zeros(out, d, device=DEV)
+    ops.gemm(x16, dz, d, out, rows, a_mn=True, b_mn=True, out_f32=g_ref, transpose_out=True, atomic_out=True, split_k=1)
+    ops.gemm_bits(bits_t, dz, d, out, rows, b_mn=True, out_f32=g, transpose_out=True, atomic_out=True, split_k=2)
+    assert _relerr(g, g_ref) < 1e-5
+
+
 def _ref_topk(u, it, seen, k):
     s = u.double() @ it.double().T
     s = s.cpu().numpy()
