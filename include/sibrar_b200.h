@@ -64,11 +64,18 @@ typedef struct {
   int transpose_out;      /* fp32 output written transposed                                                       */
   int atomic_out;         /* fp32 output accumulated with atomicAdd (needed when split_k > 1)                     */
   int split_k;            /* number of partitions of the K loop (>= 1)                                            */
+  int64_t split_stride;   /* > 0: partition z writes (no atomics) to out_f32 + z * split_stride; sbr_splitk_reduce  */
   float alpha;
 } sbr_gemm_epilogue_t;
 
 int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,
                   int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream);
+
+/* out[r, c] (+)= act(sum_s partials[s * split_stride + r * ld_part + c] + bias[c]) -- the deterministic second half of
+ * a split-K GEMM (split_stride > 0 above).  accumulate = 1 adds into out_f32 (gradient buffers). */
+int sbr_splitk_reduce(const float* partials, int n_splits, int64_t split_stride, int64_t ld_part, int64_t rows,
+                      int64_t cols, const float* bias, int act, float* out_f32, int64_t ld_f32, int accumulate,
+                      void* out_bf16, int64_t ld_bf16, void* stream);
 
 /* Same GEMM with a BIT-PACKED 0/1 A operand (K-major): bit k of row m = A_bits[m * ld_words + k / 32] >> (k % 32).
  * The multi-hot 'interactions' rows (data/Feature.py:147-150: csr.toarray() per batch in the reference) stay packed in

@@ -24,7 +24,7 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("bias", c_vp), ("act", C.c_int), ("out_bf16", c_vp), ("ld_bf16", c_i64), ("out_f32", c_vp),
                 ("ld_f32", c_i64), ("colstats", c_vp), ("colstats_sum_only", C.c_int), ("actgrad_y", c_vp), ("ld_actgrad", c_i64),
                 ("actgrad_act", C.c_int), ("transpose_out", C.c_int), ("atomic_out", C.c_int), ("split_k", C.c_int),
-                ("alpha", c_f32)]
+                ("split_stride", c_i64), ("alpha", c_f32)]
 
 
 class ModalitySrc(C.Structure):
@@ -44,6 +44,8 @@ class AdamTensor(C.Structure):
 _PROTOS = {
     "sbr_gemm_bf16": [c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, c_i64, c_i64, c_i64, C.POINTER(GemmEpilogue), c_vp],
     "sbr_gemm_bits_bf16": [c_vp, c_i64, c_vp, c_i64, C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp],
+    "sbr_splitk_reduce": [c_vp, C.c_int, c_i64, c_i64, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, c_vp, c_i64,
+                          c_vp],
     "sbr_cast_f32_to_bf16": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "sbr_transpose_f32_to_bf16": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "sbr_transpose_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],

@@ -248,6 +248,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
     const sbr_gemm_epilogue_t& ep = p.ep;
+    // split-K without atomics: every K partition writes its own fp32 slice (reduced by sbr_splitk_reduce)
+    float* out32 = ep.out_f32 != nullptr ? ep.out_f32 + (int64_t)blockIdx.z * ep.split_stride : nullptr;
     float cs_acc[BN / 32], cq_acc[BN / 32];  // lane l: partial column statistics of column 32 * i + l
 #pragma unroll
     for (int i = 0; i < BN / 32; ++i) cs_acc[i] = cq_acc[i] = 0.f;
@@ -320,11 +322,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (ep.transpose_out) {
         // out_f32 is [N, M]: for a fixed column the 32 lanes hit 32 consecutive floats
-        if (ep.out_f32 != nullptr && row_ok) {
+        if (out32 != nullptr && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (col0 + j < p.N) {
-              float* dst = ep.out_f32 + (col0 + j) * ep.ld_f32 + row;
+              float* dst = out32 + (col0 + j) * ep.ld_f32 + row;
               if (ep.atomic_out) atomicAdd(dst, v[j]);
               else *dst = v[j];
             }
@@ -332,8 +334,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         continue;
       }
-      if (ep.out_f32 != nullptr && row_ok) {
-        float* dst = ep.out_f32 + row * ep.ld_f32 + col0;
+      if (out32 != nullptr && row_ok) {
+        float* dst = out32 + row * ep.ld_f32 + col0;
         if (ep.atomic_out) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -458,9 +460,9 @@ extern "C" int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
   int splits = ep->split_k < 1 ? 1 : ep->split_k;
   const int num_kb = (int)((K + BK - 1) / BK);
   if (splits > num_kb) splits = num_kb;
-  SBR_REQUIRE(splits == 1 || (ep->atomic_out && !ep->out_bf16 && !ep->colstats && !ep->bias &&
-                              ep->act == SBR_ACT_NONE && !ep->actgrad_y),
-              "sbr_gemm_bf16: split_k > 1 needs a pure atomic fp32 epilogue");
+  SBR_REQUIRE(splits == 1 || ((ep->atomic_out || ep->split_stride > 0) && !ep->out_bf16 && !ep->colstats &&
+                              !ep->bias && ep->act == SBR_ACT_NONE && !ep->actgrad_y),
+              "sbr_gemm_bf16: split_k > 1 needs a pure fp32 epilogue (atomic, or one slice per partition)");
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
 
   CUtensorMap tmA, tmB;
@@ -505,9 +507,9 @@ extern "C" int sbr_gemm_bits_bf16(const uint32_t* A_bits, int64_t ld_words, cons
   SBR_REQUIRE(!(ep->transpose_out && ep->out_bf16), "sbr_gemm_bits_bf16: transposed output is fp32 only");
   int splits = ep->split_k < 1 ? 1 : ep->split_k;
   if (splits > num_kb) splits = num_kb;
-  SBR_REQUIRE(splits == 1 || (ep->atomic_out && !ep->out_bf16 && !ep->colstats && !ep->bias &&
-                              ep->act == SBR_ACT_NONE && !ep->actgrad_y),
-              "sbr_gemm_bits_bf16: split_k > 1 needs a pure atomic fp32 epilogue");
+  SBR_REQUIRE(splits == 1 || ((ep->atomic_out || ep->split_stride > 0) && !ep->out_bf16 && !ep->colstats &&
+                              !ep->bias && ep->act == SBR_ACT_NONE && !ep->actgrad_y),
+              "sbr_gemm_bits_bf16: split_k > 1 needs a pure fp32 epilogue (atomic, or one slice per partition)");
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   CUtensorMap tmB;
   int rc;

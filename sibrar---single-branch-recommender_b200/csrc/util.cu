@@ -159,7 +159,61 @@ __global__ void sample_batch_kernel(const int32_t* __restrict__ coo_user, const 
   out_i[t] = cand;
 }
 
+// out[r, c] (+)= act(sum_s part[s][r, c] + bias[c]).  Block = 32 consecutive elements x 8 partition lanes: every
+// load instruction of a warp reads 128 contiguous bytes of one slice, lane group ty sums slices ty, ty + 8, ...
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, int64_t ld_part, int64_t rows,
+                     int64_t cols, const float* __restrict__ bias, int act, float* __restrict__ out_f32,
+                     int64_t ld_f32, int accumulate, bf16* __restrict__ out_bf16, int64_t ld_bf16) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t total = rows * cols;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + tx;
+    const int64_t r = i < total ? i / cols : 0, c = i < total ? i - r * cols : 0;
+    float a0 = 0.f, a1 = 0.f;
+    if (i < total) {
+      const float* p = part + r * ld_part + c;
+      int s = ty;
+      for (; s + 8 < n_splits; s += 16) {
+        a0 += p[(int64_t)s * split_stride];
+        a1 += p[(int64_t)(s + 8) * split_stride];
+      }
+      if (s < n_splits) a0 += p[(int64_t)s * split_stride];
+    }
+    red[ty][tx] = a0 + a1;
+    __syncthreads();
+    if (ty == 0 && i < total) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v += red[q][tx];
+      if (bias) v += bias[c];
+      v = act_fwd(act, v);
+      if (out_f32) {
+        float* d = out_f32 + r * ld_f32 + c;
+        *d = accumulate ? *d + v : v;
+      }
+      if (out_bf16) out_bf16[r * ld_bf16 + c] = __float2bfloat16(v);
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
+
+extern "C" int sbr_splitk_reduce(const float* partials, int n_splits, int64_t split_stride, int64_t ld_part,
+                                 int64_t rows, int64_t cols, const float* bias, int act, float* out_f32,
+                                 int64_t ld_f32, int accumulate, void* out_bf16, int64_t ld_bf16, void* stream) {
+  SBR_REQUIRE(partials && n_splits >= 1 && rows > 0 && cols > 0 && (out_f32 || out_bf16),
+              "sbr_splitk_reduce: bad arguments");
+  const int64_t total = rows * cols;
+  const unsigned blocks = (unsigned)min((int64_t)sbr_num_sms() * 16, (total + 31) / 32);
+  splitk_reduce_kernel<<<blocks, 256, 0, S(stream)>>>(partials, n_splits, split_stride, ld_part, rows, cols, bias, act,
+                                                      out_f32, ld_f32, accumulate,
+                                                      reinterpret_cast<bf16*>(out_bf16), ld_bf16);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
 
 extern "C" int sbr_cast_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
                                     int64_t cols, void* stream) {

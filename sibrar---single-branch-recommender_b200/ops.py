@@ -20,7 +20,7 @@ def _act(a):
 
 
 def _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad_y, actgrad_act, transpose_out,
-              atomic_out, split_k, alpha):
+              atomic_out, split_k, alpha, split_stride=0):
     ep = GemmEpilogue()
     ep.bias = ptr(bias)
     ep.act = _act(act)
@@ -36,30 +36,49 @@ def _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad
     ep.transpose_out = int(transpose_out)
     ep.atomic_out = int(atomic_out)
     ep.split_k = int(split_k)
+    ep.split_stride = int(split_stride)
     ep.alpha = float(alpha)
     return ep
 
 
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, act=None, out_bf16=None,
          out_f32=None, colstats=None, colstats_sum_only=False, actgrad_y=None, actgrad_act=None, transpose_out=False, atomic_out=False,
-         split_k=1, alpha=1.0):
+         split_k=1, alpha=1.0, split_stride=0):
     """D[M,N] = alpha * A @ B^T (bf16 in, fp32 accumulate) + fused epilogue.  A/B: 2-D bf16 tensors whose last
     dimension is contiguous; K-major means [rows, K], MN-major means [K, rows]."""
     assert A.dtype == BF16 and B.dtype == BF16 and A.stride(-1) == 1 and B.stride(-1) == 1
     ep = _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad_y, actgrad_act, transpose_out,
-                   atomic_out, split_k, alpha)
+                   atomic_out, split_k, alpha, split_stride)
     call("sbr_gemm_bf16", ptr(A), lda if lda is not None else A.stride(0), int(a_mn), ptr(B),
          ldb if ldb is not None else B.stride(0), int(b_mn), int(M), int(N), int(K), C.byref(ep), stream_ptr())
 
 
 def gemm_bits(A_bits, B, M, N, K, *, b_mn=False, bias=None, act=None, out_bf16=None, out_f32=None, colstats=None,
-              colstats_sum_only=False, transpose_out=False, atomic_out=False, split_k=1, alpha=1.0):
+              colstats_sum_only=False, transpose_out=False, atomic_out=False, split_k=1, alpha=1.0, split_stride=0):
     """the same with a bit-packed 0/1 A operand: int32 [M, ld_words], bit k of row m = word k // 32, bit k % 32"""
     assert A_bits.dtype == torch.int32 and A_bits.stride(-1) == 1 and B.dtype == BF16 and B.stride(-1) == 1
     ep = _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, None, None, transpose_out, atomic_out,
-                   split_k, alpha)
+                   split_k, alpha, split_stride)
     call("sbr_gemm_bits_bf16", ptr(A_bits), A_bits.stride(0), ptr(B), B.stride(0), int(b_mn), int(M), int(N), int(K),
          C.byref(ep), stream_ptr())
+
+
+def splitk_reduce(partials, n_splits, rows, cols, bias=None, act=None, out_f32=None, out_bf16=None, accumulate=False):
+    """partials: fp32 [n_splits, rows, cols] written by a split-K GEMM with ``split_stride = rows * cols``"""
+    call("sbr_splitk_reduce", ptr(partials), int(n_splits), int(rows) * int(cols), int(cols), int(rows), int(cols),
+         ptr(bias), _act(act), ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0, int(bool(accumulate)),
+         ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, stream_ptr())
+
+
+SPLITK_MAX_PARTIAL_BYTES = 256 << 20
+
+
+def effective_splits(K: int, split_k: int) -> int:
+    """number of K partitions the GEMM really uses (no empty partition): mirrors sbr_gemm_bf16"""
+    num_kb = -(-int(K) // 64)
+    split_k = max(1, min(int(split_k), num_kb))
+    per = -(-num_kb // split_k)
+    return -(-num_kb // per)
 
 
 def pack_bits(csr, device) -> torch.Tensor:

@@ -94,7 +94,6 @@ class LinearStage:
         self.bn: Optional[nn.BatchNorm1d] = None
         self.act2: Optional[str] = None
         self.in_f, self.out_f = linear.in_features, linear.out_features
-        self.unit_mi = self.ones = self.zero_bias = None  # constants of the split-K forward's bias/activation pass
         self.w16 = None     # bf16 [out, pad8(in)]: K-major B of the forward GEMM, MN-major B of the dgrad GEMM
         self.wt32 = None    # fp32 [in, out] for the CSR route
         self._ver = -1
@@ -211,18 +210,15 @@ class Chain:
                 else:
                     first_bits = si == 0 and self.bits_input
                     mm = (lambda *a, **k: ops.gemm_bits(self.feature.bits, *a[1:], **k)) if first_bits else ops.gemm
-                    split = self._fwd_split_k(rows, st)
+                    split = ops.effective_splits(st.in_f, self._fwd_split_k(rows, st))
                     if split > 1:
-                        # few output tiles, long contraction (an 'interactions' table): split K over the SMs into a
-                        # zeroed fp32 buffer, then one pass applies bias + activation (y = act(1 * (z - 0) * 1 + bias))
-                        z32 = torch.zeros((rows, st.out_f), dtype=F32, device=dev)
-                        mm(x16, st.w16, rows, st.out_f, st.in_f, out_f32=z32, atomic_out=True, split_k=split)
-                        if st.unit_mi is None or st.unit_mi.device != dev:
-                            st.unit_mi = torch.cat([torch.zeros(st.out_f, device=dev), torch.ones(st.out_f, device=dev)])
-                            st.ones = torch.ones(st.out_f, device=dev)
-                            st.zero_bias = torch.zeros(st.out_f, device=dev)
-                        ops.bn_apply(z32, st.unit_mi, st.ones, bias if bias is not None else st.zero_bias, st.act1,
-                                     rows, st.out_f, out_bf16=y16, out_f32=y32)
+                        # few output tiles, long contraction (an 'interactions' table): every K partition writes its
+                        # own fp32 slice (no atomics, deterministic), one pass sums them and applies bias + activation
+                        part = torch.empty((split, rows, st.out_f), dtype=F32, device=dev)
+                        mm(x16, st.w16, rows, st.out_f, st.in_f, out_f32=part.view(split * rows, st.out_f),
+                           split_k=split, split_stride=rows * st.out_f)
+                        ops.splitk_reduce(part, split, rows, st.out_f, bias=bias, act=st.act1, out_f32=y32,
+                                          out_bf16=y16)
                     else:
                         mm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_bf16=y16, out_f32=y32)
             else:
@@ -305,14 +301,24 @@ class Chain:
             else:
                 x16 = st.x if si > 0 or self.feature is None else self.feature.x16
                 tiles = -(-st.in_f // 128) * -(-st.out_f // (64 if st.out_f <= 64 else 128 if st.out_f <= 128 else 256))
-                split = max(1, min(-(-rows // 64), (2 * n_sms) // max(1, tiles)))
+                split = ops.effective_splits(rows, max(1, min(-(-rows // 64), (2 * n_sms) // max(1, tiles))))
+                # wgrad partitions accumulate with fp32 atomics (measured faster than private slices + a reduce pass at
+                # every shape of the ML-1M step; SBR_SLICED_MIN_SPLIT selects the deterministic sliced variant)
+                sliced = split >= int(os.environ.get("SBR_SLICED_MIN_SPLIT", 1 << 30)) and \
+                    split * st.out_f * st.in_f * 4 <= ops.SPLITK_MAX_PARTIAL_BYTES
+                if sliced:
+                    part = torch.empty((split, st.out_f, st.in_f), dtype=F32, device=dev)
+                    kw = dict(out_f32=part.view(split * st.out_f, st.in_f), transpose_out=True, split_k=split,
+                              split_stride=st.out_f * st.in_f)
+                else:
+                    kw = dict(out_f32=g_w, transpose_out=True, atomic_out=True, split_k=split)
                 if si == 0 and self.bits_input:
                     # dW^T [in, out] = X^T dZ with X^T = the transposed bit matrix as the K-major A operand
-                    ops.gemm_bits(self.feature.bits_t, dz16, st.in_f, st.out_f, rows, b_mn=True, out_f32=g_w,
-                                  transpose_out=True, atomic_out=True, split_k=split)
+                    ops.gemm_bits(self.feature.bits_t, dz16, st.in_f, st.out_f, rows, b_mn=True, **kw)
                 else:
-                    ops.gemm(x16, dz16, st.in_f, st.out_f, rows, a_mn=True, b_mn=True, out_f32=g_w,
-                             transpose_out=True, atomic_out=True, split_k=split)
+                    ops.gemm(x16, dz16, st.in_f, st.out_f, rows, a_mn=True, b_mn=True, **kw)
+                if sliced:
+                    ops.splitk_reduce(part, split, st.out_f, st.in_f, out_f32=g_w, accumulate=True)
             # ---- dgrad
             if si > 0:
                 prev = self.stages[si - 1]

@@ -98,12 +98,26 @@ def test_gemm_bits_matches_dense(rows, d, out, density):
     z = torch.zeros(rows, out, device=DEV)
     ops.gemm_bits(bits, w, rows, out, d, out_f32=z, atomic_out=True, split_k=3)
     assert _relerr(torch.relu(z + bias), y_ref) < 1e-5
+    # sliced split-K (one fp32 slice per partition, no atomics) + the reduce pass with bias / activation
+    ns = ops.effective_splits(d, 3)
+    part = torch.full((ns, rows, out), float("nan"), device=DEV)
+    ops.gemm_bits(bits, w, rows, out, d, out_f32=part.view(ns * rows, out), split_k=ns, split_stride=rows * out)
+    y2, y2h = torch.empty(rows, out, device=DEV), torch.empty(rows, ops.pad8(out), dtype=torch.bfloat16, device=DEV)
+    ops.splitk_reduce(part, ns, rows, out, bias=bias, act="relu", out_f32=y2, out_bf16=y2h)
+    assert _relerr(y2, y_ref) < 1e-5 and _relerr(y2h[:, :out].float(), y_ref) < 1e-2
     # wgrad form: dW [out, d] = dZ^T X  computed as (X^T dZ)^T with the transposed bit matrix as A
     dz = _rand_bf16(rows, ops.pad8(out), seed=4)[:, :out]
     g_ref, g = torch.zeros(out, d, device=DEV), torch.zeros(out, d, device=DEV)
     ops.gemm(x16, dz, d, out, rows, a_mn=True, b_mn=True, out_f32=g_ref, transpose_out=True, atomic_out=True, split_k=1)
     ops.gemm_bits(bits_t, dz, d, out, rows, b_mn=True, out_f32=g, transpose_out=True, atomic_out=True, split_k=2)
     assert _relerr(g, g_ref) < 1e-5
+    ns = ops.effective_splits(rows, 2)
+    part = torch.full((ns, out, d), float("nan"), device=DEV)
+    ops.gemm(x16, dz, d, out, rows, a_mn=True, b_mn=True, out_f32=part.view(ns * out, d), transpose_out=True,
+             split_k=ns, split_stride=out * d)
+    g2 = g_ref.clone()
+    ops.splitk_reduce(part, ns, out, d, out_f32=g2, accumulate=True)
+    assert _relerr(g2, 2 * g_ref) < 1e-5
 
 
 def _ref_topk(u, it, seen, k):
