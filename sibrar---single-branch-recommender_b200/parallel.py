@@ -94,34 +94,49 @@ class DataParallelTrainer(FusedTrainer):
 class ShardedEvaluator(FullEvaluator):
     """item-sharded full-catalog evaluation with an all-gather top-k merge"""
 
-    @torch.no_grad()
-    def evaluate(self, model, dataset=None, return_topk: bool = False):
-        dataset = dataset or self.dataset
-        rank, world = dist.get_rank(), dist.get_world_size()
-        dev = model.device
+    def _shard(self, dataset, dev, rank, world):
+        """device-resident inputs of this rank's item shard (built once per dataset)"""
+        key = (id(dataset), str(dev), rank, world)
+        hit = getattr(self, "_shard_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
         users = np.asarray(dataset.users_in_split)
         items = np.asarray(dataset.items_in_split)
         lo, hi = shard_range(len(items), rank, world)
         seen = dataset.exclude_data[users][:, lo:hi].tocsr()
         tgt = dataset.user_sampling_matrix[users][:, items]
+        pack = dict(lo=lo, hi=hi, n_users=len(users), n_items=len(items),
+                    users=torch.from_numpy(users.astype(np.int64)).to(dev),
+                    items=torch.from_numpy(items[lo:hi].astype(np.int64)).to(dev),
+                    seen=csr_to_device(seen, dev) if seen.nnz > 0 else (None, None),
+                    tgt=csr_to_device(tgt, dev))
+        self._shard_cache = (key, pack)
+        return pack
+
+    @torch.no_grad()
+    def evaluate(self, model, dataset=None, return_topk: bool = False):
+        dataset = dataset or self.dataset
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = model.device
+        d = self._shard(dataset, dev, rank, world)
+        lo, hi, n_users, n_items = d["lo"], d["hi"], d["n_users"], d["n_items"]
         was_training = model.training
         model.eval()
-        i_repr = model.get_item_representations(torch.from_numpy(items[lo:hi].astype(np.int64)).to(dev))
-        u_repr = model.get_user_representations(torch.from_numpy(users.astype(np.int64)).to(dev))
+        i_repr = model.get_item_representations(d["items"])
+        u_repr = model.get_user_representations(d["users"])
         if was_training:
             model.train()
         ks = sorted(set(int(k) for k in self.config.top_k))
-        kmax = min(max(ks), len(items))
+        kmax = min(max(ks), n_items)
         u16, i16 = ops.cast_bf16(u_repr.contiguous()), ops.cast_bf16(i_repr.contiguous())
-        seen_dev = csr_to_device(seen, dev) if seen.nnz > 0 else (None, None)
-        local = ops.topk_scores_masked(u16, i16, len(users), hi - lo, u16.shape[1], seen_dev[0], seen_dev[1],
-                                       min(kmax, hi - lo) if hi - lo < kmax else kmax, item_offset=lo,
-                                       return_keys=True)
+        k_local = min(kmax, hi - lo)
+        local = ops.topk_scores_masked(u16, i16, n_users, hi - lo, u16.shape[1], d["seen"][0], d["seen"][1], k_local,
+                                       item_offset=lo, return_keys=True)
         if local.shape[1] < kmax:  # tiny shard: pad with empty slots
             pad = torch.zeros((local.shape[0], kmax - local.shape[1]), dtype=local.dtype, device=dev)
             local = torch.cat([local, pad], dim=1)
         gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=dev)
         dist.all_gather_into_tensor(gathered, local.contiguous())
-        vals, idx = ops.topk_merge(gathered, world, len(users), kmax)
-        out = self.metrics_from_topk(idx, csr_to_device(tgt, dev), ks, len(items))
+        vals, idx = ops.topk_merge(gathered, world, n_users, kmax)
+        out = self.metrics_from_topk(idx, d["tgt"], ks, n_items)
         return (out, (vals, idx)) if return_topk else out
