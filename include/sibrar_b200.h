@@ -194,6 +194,11 @@ int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f32, const v
 int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n, int ku, int ki, int D, int agg_max_user,
                    int agg_max_item, int loss_kind, int aggregator_sum, float ssm_shift, float* logits,
                    double* loss_acc, float* deu, float* dei, float* u_agg, float* i_agg, void* stream);
+/* Backward of the scoring alone for a loss computed OUTSIDE (the reference's own loop: logits -> rec loss ->
+ * loss.backward(), train/trainer.py:209-221): given d loss / d logits [B, n], writes deu / dei like sbr_score_loss. */
+int sbr_score_bwd(const float* eu, const float* ei, int64_t B, int n, int ku, int ki, int D, int agg_max_user,
+                  int agg_max_item, const float* dlogits, float* deu, float* dei, void* stream);
+
 /* The same for entities whose single-branch net ends in a BatchNorm1d (algorithms/sgd_alg.py:1834-1837): the
  * kernel reads the PRE-BatchNorm values z and applies e = gamma * (z - mean) * invstd + beta on the fly, and it
  * accumulates the BatchNorm-backward column sums of the gradients it produces (sums[r][0:D] += de,

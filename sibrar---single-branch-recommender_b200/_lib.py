@@ -70,6 +70,7 @@ _PROTOS = {
                          c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp],
     "sbr_score_loss": [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                        c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "sbr_score_bwd": [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp],
     "sbr_score_loss_bn": [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp,
                           c_vp, C.c_int, c_vp],
     "sbr_infonce": [c_vp, c_i64, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, C.c_int, c_vp, c_vp],

@@ -48,7 +48,7 @@ __global__ void score_loss_kernel(const float* __restrict__ eu, const float* __r
                                   int ki, int D, int agg_max_user, int agg_max_item, int loss_kind, float inv_cnt,
                                   float ssm_shift, float* __restrict__ logits, double* __restrict__ loss_acc,
                                   float* __restrict__ deu, float* __restrict__ dei, float* __restrict__ u_agg_out,
-                                  float* __restrict__ i_agg_out) {
+                                  float* __restrict__ i_agg_out, const float* __restrict__ dlogits_in) {
   extern __shared__ float sh[];  // per warp: n scores + n grads
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t b = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
@@ -81,7 +81,9 @@ __global__ void score_loss_kernel(const float* __restrict__ eu, const float* __r
   __syncwarp();
   // ---- loss and d loss / d score (lanes stride over j)
   float lsum = 0.f;
-  if (loss_kind == SBR_LOSS_BPR) {
+  if (dlogits_in != nullptr) {  // gradients of an externally computed loss (autograd path): d loss / d score given
+    for (int j = lane; j < n; j += 32) gr[j] = dlogits_in[b * n + j];
+  } else if (loss_kind == SBR_LOSS_BPR) {
     float s0 = sc[0], g0 = 0.f;
     for (int j = 1 + lane; j < n; j += 32) {
       float d = s0 - sc[j];
@@ -470,7 +472,22 @@ extern "C" int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n
   size_t shmem = (size_t)wpb * 2 * n * sizeof(float);
   DISPATCH_NV(D, 32, score_loss_kernel<NVv><<<cdiv(B, wpb), wpb * 32, shmem, S(stream)>>>(
                          eu, ei, B, n, ku, ki, D, agg_max_user, agg_max_item, loss_kind, (float)(1.0 / cnt), ssm_shift,
-                         logits, loss_acc, deu, dei, u_agg, i_agg));
+                         logits, loss_acc, deu, dei, u_agg, i_agg, nullptr));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_score_bwd(const float* eu, const float* ei, int64_t B, int n, int ku, int ki, int D,
+                             int agg_max_user, int agg_max_item, const float* dlogits, float* deu, float* dei,
+                             void* stream) {
+  SBR_REQUIRE(eu && ei && dlogits && deu && dei && B > 0 && n >= 1 && ku >= 1 && ki >= 1,
+              "sbr_score_bwd: bad arguments");
+  SBR_REQUIRE(D > 0 && D <= 512 && n <= 1024, "sbr_score_bwd: D=%d / n=%d out of range", D, n);
+  const int wpb = 4;
+  size_t shmem = (size_t)wpb * 2 * n * sizeof(float);
+  DISPATCH_NV(D, 32, score_loss_kernel<NVv><<<cdiv(B, wpb), wpb * 32, shmem, S(stream)>>>(
+                         eu, ei, B, n, ku, ki, D, agg_max_user, agg_max_item, SBR_LOSS_BCE, 1.f, 0.f, nullptr, nullptr,
+                         deu, dei, nullptr, nullptr, dlogits));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

@@ -238,6 +238,11 @@ def score_loss(eu, ei, B, n, ku, ki, D, agg_max_user, agg_max_item, loss_kind, a
          ptr(u_agg), ptr(i_agg), stream_ptr())
 
 
+def score_bwd(eu, ei, B, n, ku, ki, D, agg_max_user, agg_max_item, dlogits, deu, dei):
+    call("sbr_score_bwd", ptr(eu), ptr(ei), int(B), int(n), int(ku), int(ki), int(D), int(agg_max_user),
+         int(agg_max_item), ptr(dlogits), ptr(deu), ptr(dei), stream_ptr())
+
+
 BN_SUM_REPLICAS = 8
 
 

@@ -766,12 +766,11 @@ class SingleBranchNet(nn.Module):
             self._runtime.err_flag.zero_()
             raise KeyError("an entity index without a feature row was requested")
 
-    # ---- reference API (inference / no-grad use; training goes through sibrar_b200.trainer.FusedTrainer)
+    # ---- reference API (model(u, i) is differentiable in training mode; FusedTrainer is the fast path)
     def _represent(self, ent, idx):
+        """representations WITHOUT an autograd graph (evaluation, analysis); gradients flow through ``forward`` (the
+        reference loop) or ``FusedTrainer.step``"""
         training = self.training
-        if training and torch.is_grad_enabled():
-            from .autograd import entity_forward_with_grad
-            return entity_forward_with_grad(self, ent, idx)
         rt = self._rt()
         rt.arena.reset()
         E = ent.embed(idx, training)
@@ -794,6 +793,9 @@ class SingleBranchNet(nn.Module):
         return combine(u_repr, i_repr)
 
     def forward(self, u_idxs, i_idxs):
+        if self.training and torch.is_grad_enabled():
+            from .autograd import train_forward
+            return train_forward(self, u_idxs, i_idxs)  # differentiable: loss.backward() fills param.grad
         u_repr = self.get_user_representations(u_idxs)
         i_repr = self.get_item_representations(i_idxs)
         return self.combine_user_item_representations(u_repr, i_repr)

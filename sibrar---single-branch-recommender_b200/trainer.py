@@ -71,6 +71,7 @@ class FusedTrainer:
             entries.append(dict(param=p.data, grad=g, exp_avg=torch.zeros_like(g), exp_avg_sq=torch.zeros_like(g),
                                 shadow=shadows.get(id(p))))
         self.adam = ops.AdamPlan(entries, dev)
+        self.opt_step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         # [rec, user_reg, item_reg] sums since the last reset (fp64), + number of accumulated steps on the host
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
         self.steps_accumulated = 0
@@ -169,8 +170,9 @@ class FusedTrainer:
 
     def optimizer_step(self):
         b1, b2 = self.betas
+        ops.tick(self.opt_step_dev)  # Adam's t counts the updates of THIS optimizer state (device-side: graph-safe)
         self.adam.step(self.learn.lr, b1, b2, self.eps, self.learn.wd, self.learn.optimizer == "adamw",
-                       self.rt.step_dev, self.grad_scale)
+                       self.opt_step_dev, self.grad_scale)
 
     # ------------------------------------------------------------------------------------------------ logging
     def read_losses(self, reset: bool = True) -> Dict[str, float]:

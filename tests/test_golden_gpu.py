@@ -138,6 +138,62 @@ def test_single_steps_match_reference(name):
 
 
 @pytest.mark.parametrize("name", list(CASES))
+def test_reference_style_loop_matches_fused_step(name):
+    """the reference's own loop -- logits = model(u, i); loss (torch, fp64) + reg; loss.backward(); torch.optim --
+    driven through the autograd glue gives the gradients / parameters of the fused step (same kernels underneath)"""
+    spec, g, corpus, model = _build(name)
+    if spec["rec_loss"] != "bpr":
+        pytest.skip("the torch-side loss of this test is BPR")
+    model.to(DEV).train()
+    sd0 = state_dict_of(g, "sd0/")
+    u, i, mods, keep = _translate(model, g, 0)
+    # (a) fused step, gradients only
+    _load(model, sd0)
+    tr = _trainer(model, spec)
+    tr.step(u, i, mods, keep, apply_optimizer=False)
+    params = dict(model.named_parameters())
+    fused = {k: tr.grads[id(p)].clone() for k, p in params.items()}
+    fused_loss = tr.read_losses()["train/loss"]
+    fused_logits = tr.logits.clone()
+    for p in model.parameters():
+        p.grad = None
+    # (b) the reference loop
+    _load(model, sd0)
+    model._injected_inputs = (mods, keep)
+    logits = model(u, i)
+    assert logits.requires_grad and _maxrel(logits.detach().cpu().numpy(), fused_logits.cpu().numpy()) < 1e-5
+    pos, neg = logits[:, :1].double(), logits[:, 1:].double()
+    rec = torch.nn.functional.softplus(-(pos - neg)).mean()
+    total = rec + model.get_and_reset_other_loss()["reg_loss"].double().sum()
+    assert float(total) == pytest.approx(fused_loss, rel=1e-5)
+    total.backward()
+    gscale = max(float(v.abs().max()) for v in fused.values())
+    for k, p in params.items():
+        assert p.grad is not None, k
+        err = float((p.grad - fused[k]).abs().max())
+        assert err <= 2e-3 * float(fused[k].abs().max()) + 1e-5 * gscale, (k, err)
+    # torch.optim on the accumulated .grad moves the parameters like the fused AdamW
+    opt = torch.optim.AdamW(model.parameters(), lr=spec["lr"], weight_decay=spec["wd"]) if spec["optimizer"] == "adamw" \
+        else torch.optim.Adam(model.parameters(), lr=spec["lr"], weight_decay=spec["wd"])
+    opt.step()
+    after = {k: p.detach().clone() for k, p in params.items()}
+    model._injected_inputs = None
+    _load(model, sd0)
+    for p in model.parameters():
+        p.grad = None
+    tr2 = _trainer(model, spec)
+    tr2.step(u, i, mods, keep)
+    # (Adam's first step moves every element by ~lr * g / (|g| + eps): compared where the gradient is well above eps
+    # and rounding noise; elsewhere only the bound 2 * lr holds)
+    for k, p in dict(model.named_parameters()).items():
+        diff = (p.detach() - after[k]).abs()
+        assert float(diff.max()) <= 2.1 * spec["lr"], k
+        solid = fused[k].abs() > max(1e-3 * float(fused[k].abs().max()), 1e-5)
+        if bool(solid.any()):
+            assert float(diff[solid].max()) <= 0.02 * spec["lr"], k
+
+
+@pytest.mark.parametrize("name", list(CASES))
 def test_training_trajectory(name):
     """fused multi-step training from the reference's initial weights on the reference's batches: the loss curve
     stays within 1e-2 (relative) and no parameter drifts further than Adam's step bound lr * n_steps * 2.5."""

@@ -161,6 +161,38 @@ def test_topk_scores_masked_exact(U, I, D, k, n_splits, per_user):
     assert (idx[~finite] == -1).all() and np.isneginf(vals[~finite]).all()
 
 
+def test_topk_full_size_properties():
+    """BASELINE configs[4] scale (1e6 items): size-independent properties of the fused kernel -- descending scores,
+    unique unseen positions, invariance to the item split, and agreement with torch on a sample of users"""
+    U, I, D, k = 20000, 1_000_000, 64, 50
+    g = torch.Generator().manual_seed(3)
+    u = (torch.randn(U, D, generator=g) / math.sqrt(D)).to(torch.bfloat16).to(DEV)
+    it = torch.randn(I, D, generator=g).to(torch.bfloat16).to(DEV)
+    per = 64
+    seen_ix = torch.sort(torch.randint(0, I, (U, per), device=DEV, dtype=torch.int32), dim=1).values
+    ip = torch.arange(0, (U + 1) * per, per, dtype=torch.int64, device=DEV)
+    v1, i1 = ops.topk_scores_masked(u, it, U, I, D, ip, seen_ix.reshape(-1).contiguous(), k, n_splits=1)
+    v4, i4 = ops.topk_scores_masked(u, it, U, I, D, ip, seen_ix.reshape(-1).contiguous(), k, n_splits=4)
+    assert torch.equal(i1, i4) and torch.equal(v1, v4)                       # split invariance (exact merge)
+    assert bool((v1[:, :-1] >= v1[:, 1:]).all())                             # sorted
+    assert bool((i1 >= 0).all()) and bool((i1 < I).all())
+    srt = torch.sort(i1, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                           # unique positions
+    hit = (i1.unsqueeze(2) == seen_ix.unsqueeze(1)).any(dim=2)
+    assert not bool(hit.any())                                               # no seen item is recommended
+    sample = torch.arange(0, U, U // 32, device=DEV)[:32]
+    sc = u[sample].float() @ it.float().T
+    sc.scatter_(1, seen_ix[sample].long(), float("-inf"))
+    rv, ri = torch.topk(sc, k, dim=1)
+    assert float((v1[sample] - rv).abs().max()) < 1e-4
+    same = (i1[sample] == ri)
+    gap_ok = (rv[:, :-1] - rv[:, 1:]) > 1e-5                                 # positions must agree where scores are apart
+    safe = torch.ones_like(same)
+    safe[:, 1:] &= gap_ok
+    safe[:, :-1] &= gap_ok
+    assert bool(same[safe].all())
+
+
 def test_topk_float_scores_close():
     U, I, D, k = 500, 8000, 64, 20
     u = _rand_bf16(U, D, seed=11, scale=D ** -0.5)
