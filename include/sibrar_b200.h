@@ -262,9 +262,9 @@ int sbr_topk_scores_masked(const void* users, int64_t ldu, const void* items, in
  * Also the merge step after the NVLink all-gather of item-sharded evaluation (L = number of ranks). */
 int sbr_topk_merge(const uint64_t* keys, int L, int64_t U, int k, float* out_vals, int32_t* out_idx,
                    uint64_t* out_keys, void* stream);
-/* per-user metrics from ranked positions and a target CSR (sorted): ndcg, precision, recall, f_score, hitrate for
- * each k in ks (rmet.calculate at eval/eval.py:99-102; definitions eval/metrics.py:4-105).
- * out: fp32 [5, n_ks, U] in that metric order; item_hits (optional int32 [n_ks, I]) marks recommended items for
+/* per-user metrics from ranked positions and a target CSR (sorted): ndcg, precision, recall, f_score, hitrate, ap, rr
+ * for each k in ks (rmet.calculate at eval/eval.py:99-102; definitions eval/metrics.py:4-105).
+ * out: fp32 [7, n_ks, U] in that metric order; item_hits (optional int32 [n_ks, I]) marks recommended items for
  * coverage. */
 int sbr_metrics_at_k(const int32_t* topk_idx, int64_t U, int k, const int64_t* tgt_indptr, const int32_t* tgt_indices,
                      const int32_t* ks_dev, int n_ks, float* out, int32_t* item_hits, int64_t n_items, void* stream);

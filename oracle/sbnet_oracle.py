@@ -559,6 +559,13 @@ def metrics_at_k(topk_idx, target_csr, ks, n_items=None):
             out[f"recall@{k}"] = rec
             out[f"f_score@{k}"] = np.where(prec + rec > 0, 2 * prec * rec / (prec + rec), 0.)
             out[f"hitrate@{k}"] = np.minimum(hits, 1.)
+            # rmet (restated, oracle/rmet_restated.py): ap = sum_r rel_r * precision@r / min(k, n_targets),
+            # rr = 1 / rank of the first hit
+            prec_at = np.cumsum(rel[:, :k], 1) / np.arange(1, k + 1, dtype=F64)
+            denom = np.minimum(nt, k)
+            out[f"ap@{k}"] = np.where(denom > 0, (prec_at * rel[:, :k]).sum(1) / np.maximum(denom, 1.), 0.)
+            first = np.where(rel[:, :k].sum(1) > 0, rel[:, :k].argmax(1) + 1, 0)
+            out[f"rr@{k}"] = np.where(first > 0, 1. / np.maximum(first, 1), 0.)
         if n_items:
             out[f"coverage@{k}"] = len(np.unique(topk_idx[:, :k])) / float(n_items)
     return out

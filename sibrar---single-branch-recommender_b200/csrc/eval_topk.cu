@@ -576,7 +576,8 @@ __global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys_in
 }
 
 // ------------------------------------------------------------------------------------------------ metrics
-// one thread per user; ks ascending.  out[m][ki][u], m: 0 ndcg, 1 precision, 2 recall, 3 f_score, 4 hitrate
+// one thread per user; ks ascending.  out[m][ki][u], m: 0 ndcg, 1 precision, 2 recall, 3 f_score, 4 hitrate, 5 ap, 6 rr
+// (ap = sum over hits of precision@rank / min(k, n_targets); rr = 1 / rank of the first hit)
 __global__ void metrics_kernel(const int32_t* __restrict__ topk_idx, int64_t U, int k,
                                const int64_t* __restrict__ tgt_indptr, const int32_t* __restrict__ tgt_indices,
                                const int32_t* __restrict__ ks, int n_ks, float* __restrict__ out,
@@ -585,7 +586,7 @@ __global__ void metrics_kernel(const int32_t* __restrict__ topk_idx, int64_t U, 
   if (u >= U) return;
   const int64_t beg = tgt_indptr[u], end = tgt_indptr[u + 1];
   const float nt = (float)(end - beg);
-  float hits = 0.f, dcg = 0.f, idcg = 0.f;
+  float hits = 0.f, dcg = 0.f, idcg = 0.f, ap_sum = 0.f, rr = 0.f;
   int ki = 0;
   for (int r = 0; r < k && ki < n_ks; ++r) {
     const int32_t it = topk_idx[u * k + r];
@@ -600,6 +601,8 @@ __global__ void metrics_kernel(const int32_t* __restrict__ topk_idx, int64_t U, 
       if (lo < end && tgt_indices[lo] == it) {
         hits += 1.f;
         dcg += disc;
+        ap_sum += hits / (float)(r + 1);
+        if (rr == 0.f) rr = 1.f / (float)(r + 1);
       }
       if (item_hits != nullptr && it < n_items) {
         for (int kk = ki; kk < n_ks; ++kk) item_hits[(int64_t)kk * n_items + it] = 1;
@@ -612,12 +615,16 @@ __global__ void metrics_kernel(const int32_t* __restrict__ topk_idx, int64_t U, 
       const float rec = nt > 0.f ? hits / nt : 0.f;
       const float ndcg = idcg > 0.f ? fminf(dcg / idcg, 1.f) : 0.f;
       const float fs = (prec + rec) > 0.f ? 2.f * prec * rec / (prec + rec) : 0.f;
+      const float denom = fminf(nt, kf);
       const size_t o = (size_t)ki * U + u;
-      out[0 * (size_t)n_ks * U + o] = ndcg;
-      out[1 * (size_t)n_ks * U + o] = prec;
-      out[2 * (size_t)n_ks * U + o] = rec;
-      out[3 * (size_t)n_ks * U + o] = fs;
-      out[4 * (size_t)n_ks * U + o] = fminf(hits, 1.f);
+      const size_t plane = (size_t)n_ks * U;
+      out[0 * plane + o] = ndcg;
+      out[1 * plane + o] = prec;
+      out[2 * plane + o] = rec;
+      out[3 * plane + o] = fs;
+      out[4 * plane + o] = fminf(hits, 1.f);
+      out[5 * plane + o] = denom > 0.f ? ap_sum / denom : 0.f;
+      out[6 * plane + o] = rr;
       ++ki;
     }
   }

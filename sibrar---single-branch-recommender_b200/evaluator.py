@@ -20,12 +20,29 @@ from . import ops
 from .config import EvalConfig
 from .feature_store import csr_to_device
 
-USER_METRICS = ["ndcg", "precision", "recall", "f_score", "hitrate"]  # order of sbr_metrics_at_k's output
+USER_METRICS = ["ndcg", "precision", "recall", "f_score", "hitrate", "ap", "rr"]  # order of sbr_metrics_at_k's output
 SUPPORTED = USER_METRICS + ["coverage"]
 
 
 def _natural_key(s: str):
     return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", s)]
+
+
+def _user_labels(feat, users) -> np.ndarray:
+    """group label of every user for a categorical user feature (``Feature.__getitem__`` + ``get_labels``,
+    data/Feature.py:126-128, 140-162), lower-cased like eval/eval.py:111-112"""
+    if hasattr(type(feat), "__getitem__"):
+        values = np.asarray(feat[users]).reshape(-1)
+    else:
+        row_of = {int(e): r for r, e in enumerate(np.asarray(feat._indices).tolist())}
+        values = np.asarray(feat.values)[[row_of[int(u)] for u in users]].reshape(-1)
+    if hasattr(feat, "get_labels"):
+        labels = np.asarray(feat.get_labels(values)).tolist()
+    elif getattr(feat, "_unique_values", None) is not None:
+        labels = [feat._unique_values[int(v)] for v in values]
+    else:
+        labels = values.tolist()
+    return np.array([lbl.lower() if isinstance(lbl, str) else lbl for lbl in labels])
 
 
 class FullEvaluator:
@@ -64,7 +81,38 @@ class FullEvaluator:
         if was_training:
             model.train()
         res = self.evaluate_representations(u_repr, i_repr, d["seen"], d["tgt"], len(dataset.items_in_split),
-                                            return_topk=return_topk)
+                                            return_topk=True)
+        out, topk = res
+        out.update(self.group_metrics(dataset, sorted(set(int(k) for k in self.config.top_k))))
+        out = {k: out[k] for k in sorted(out, key=_natural_key)}
+        return (out, topk) if return_topk else out
+
+    def group_metrics(self, dataset, ks) -> Dict[str, float]:
+        """per-group means (+ std) of the user metrics for every categorical user feature in
+        ``eval.user_group_features`` (``FullEvaluator._calculate_group_metrics``, eval/eval.py:106-119): keys
+        ``'[{name}/]{feature}_{label}/{metric}@{k}'``.  Uses the per-user metric vectors of the last evaluation."""
+        if not self.config.calculate_group_metrics or not self.config.user_group_features:
+            return {}
+        m = self.raw  # [7, n_ks, U]
+        ks_eff = [k for k in ks if k <= self._kmax]
+        users = np.asarray(dataset.users_in_split)
+        pre = f"{self.name}/" if self.name else ""
+        res = {}
+        for fname in self.config.user_group_features:
+            labels = _user_labels(dataset.user_features[fname], users)
+            for lbl in np.unique(labels):
+                sel = torch.from_numpy(np.nonzero(labels == lbl)[0]).to(m.device)
+                sub = m.index_select(2, sel)
+                mean = sub.mean(dim=2).cpu().numpy()
+                std = sub.std(dim=2, unbiased=False).cpu().numpy() if self.config.calculate_std else None
+                for mi, name in enumerate(USER_METRICS):
+                    if name not in self.config.metrics:
+                        continue
+                    for ki, k in enumerate(ks_eff):
+                        key = f"{pre}{fname}_{lbl}/{name}@{k}"
+                        res[key] = float(mean[mi, ki])
+                        if std is not None:
+                            res[f"{key}_std"] = float(std[mi, ki])
         return res
 
     @torch.no_grad()
@@ -102,7 +150,7 @@ class FullEvaluator:
             cov = hits.sum(dim=1).cpu().numpy() / float(n_items)
             for ki, k in enumerate(ks_eff):
                 res[f"{pre}coverage@{k}"] = float(cov[ki])
-        self.raw = m
+        self.raw, self._kmax = m, kmax
         return {k: res[k] for k in sorted(res, key=_natural_key)}
 
 

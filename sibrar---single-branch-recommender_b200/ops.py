@@ -350,7 +350,7 @@ def metrics_at_k(topk_idx, tgt_indptr, tgt_indices, ks, n_items, want_item_hits=
     U, k = topk_idx.shape
     dev = topk_idx.device
     ks_dev = torch.tensor(sorted(ks), dtype=torch.int32, device=dev)
-    out = torch.zeros((5, len(ks), U), dtype=F32, device=dev)
+    out = torch.zeros((7, len(ks), U), dtype=F32, device=dev)
     hits = torch.zeros((len(ks), n_items), dtype=torch.int32, device=dev) if want_item_hits else None
     call("sbr_metrics_at_k", ptr(topk_idx), int(U), int(k), ptr(tgt_indptr), ptr(tgt_indices), ptr(ks_dev), len(ks),
          ptr(out), ptr(hits), int(n_items), stream_ptr())

@@ -242,6 +242,32 @@ def test_eval_matches_reference(name):
         assert res[k] == pytest.approx(float(v), abs=tol), k
 
 
+def test_group_metrics_keys_and_values():
+    """eval.calculate_group_metrics / user_group_features (eval/eval.py:106-119): per-group means of the per-user
+    metric vectors, keys '{feature}_{label}/{metric}@{k}'"""
+    spec, g, corpus, model = _build("ml1m_small")
+    model.to(DEV).eval()
+    val = corpus.dataset("val")
+    feat = next(n for n, f in val.user_features.items()
+                if str(getattr(f.feature_definition.type, "value", f.feature_definition.type)).lower() == "categorical"
+                and n != "user_embedding")
+    ev = FullEvaluator(dict(top_k=[1, 5], metrics=["ndcg", "recall", "ap", "rr"], calculate_std=True,
+                            calculate_group_metrics=True, user_group_features=[feat]))
+    res = ev.evaluate(model, val)
+    from sibrar_b200.evaluator import USER_METRICS, _user_labels
+    labels = _user_labels(val.user_features[feat], np.asarray(val.users_in_split))
+    raw = ev.raw.cpu().numpy()
+    assert len(np.unique(labels)) >= 2
+    for lbl in np.unique(labels):
+        sel = labels == lbl
+        for name in ("ndcg", "recall", "ap", "rr"):
+            for ki, k in enumerate([1, 5]):
+                want = raw[USER_METRICS.index(name), ki][sel]
+                assert res[f"{feat}_{lbl}/{name}@{k}"] == pytest.approx(float(want.mean()), abs=1e-6)
+                assert res[f"{feat}_{lbl}/{name}@{k}_std"] == pytest.approx(float(want.std()), abs=1e-6)
+    assert "ndcg@5" in res and "rr@1" in res
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_topk_and_metrics_at_fixed_scores(name):
     """fixed (reference) representations rounded to bf16: positions bit-exact vs the oracle wherever the ranking gap

@@ -219,7 +219,7 @@ def test_topk_merge_and_metrics():
                                  torch.from_numpy(tgt.indices.astype(np.int32)).to(DEV), ks, I, want_item_hits=True)
     ref = O.metrics_at_k(top, tgt, ks, n_items=I)
     out = out.cpu().numpy()
-    for mi, m in enumerate(["ndcg", "precision", "recall", "f_score", "hitrate"]):
+    for mi, m in enumerate(["ndcg", "precision", "recall", "f_score", "hitrate", "ap", "rr"]):
         for ki, kk in enumerate(ks):
             assert np.abs(out[mi, ki] - ref[f"{m}@{kk}"]).max() < 2e-6, (m, kk)
     for ki, kk in enumerate(ks):
