@@ -29,8 +29,9 @@ constexpr int TI = 128;         // items per tile (UMMA N)
 constexpr int UM = 128;         // users per UMMA (M = TMEM lanes)
 constexpr int MAX_STAGES = 12;  // ring of item K-chunks (actual depth chosen from the free shared memory)
 constexpr int STAGE_BYTES = TI * 128;
-constexpr int W = 64;           // accumulator columns (items) one epilogue thread scans per tile
-constexpr int CS = TI / W;      // column slices per tile = candidate lists per user
+constexpr int W = TI;           // accumulator columns (items) one epilogue thread scans per tile: the whole tile
+constexpr int CS = TI / W;      // candidate lists per user (1)
+constexpr int NBLK = W / 32;    // 32-column blocks per thread and tile
 
 struct TopkParams {
   int64_t U, I, users_padded, ldu;
@@ -175,12 +176,10 @@ __device__ __forceinline__ void prune_list(uint2* list, int count, int k, int la
 
 constexpr int ROW_PITCH = 36;  // floats per staged accumulator row (16-byte aligned, not a multiple of 32 banks)
 
-// One 32-column block of the accumulator: lane = user, r[c] = score of item pos0 + c.  `skip` = columns that are seen
-// items of this lane's user or lie beyond the catalogue.  Common path: 3-input max tree + one vote.  Otherwise the
-// lanes that hold a score >= their threshold stage their 32 scores in shared memory and the warp handles them one
-// user at a time with lane = column: one compare, one ballot and a coalesced append to that user's list.
-__device__ __forceinline__ void scan32(const uint32_t (&r)[32], float thr, uint32_t pos0, uint32_t skip,
-                                       uint2* warp_list, size_t lane_stride, float* srow, int lane, int& cnt) {
+// One 32-column block of the accumulator: lane = user, r[c] = score of item pos0 + c.  Common path: 3-input max tree
+// + one vote.  Lanes that hold a score >= their threshold stage their 32 scores in shared memory (the registers
+// are then free for the next TMEM load); returns the ballot of those lanes.
+__device__ __forceinline__ unsigned fast_and_stage(const uint32_t (&r)[32], float thr, float* srow, int lane) {
   float m[11];
 #pragma unroll
   for (int g = 0; g < 10; ++g)
@@ -189,16 +188,22 @@ __device__ __forceinline__ void scan32(const uint32_t (&r)[32], float thr, uint3
   const float a = fmax3(m[0], m[1], m[2]), b = fmax3(m[3], m[4], m[5]), c = fmax3(m[6], m[7], m[8]);
   const float mm = fmax3(fmax3(a, b, c), m[9], m[10]);
   const bool mine = mm >= thr;
-  unsigned flagged = __ballot_sync(0xffffffffu, mine);
-  if (flagged == 0u) return;
-  if (mine) {
+  const unsigned flagged = __ballot_sync(0xffffffffu, mine);
+  if (flagged != 0u && mine) {
     float4* dst = reinterpret_cast<float4*>(srow + lane * ROW_PITCH);
 #pragma unroll
     for (int v = 0; v < 8; ++v)
       dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
                            __uint_as_float(r[4 * v + 3]));
   }
-  __syncwarp();
+  return flagged;
+}
+
+// The staged rows of one block, one user at a time with lane = column: one compare against that user's threshold and
+// seen mask, one ballot, one coalesced append to that user's candidate list.
+__device__ __forceinline__ void handle_events(unsigned flagged, float thr, uint32_t pos0, uint32_t skip,
+                                              uint2* warp_list, size_t lane_stride, const float* srow, int lane,
+                                              int& cnt) {
   const unsigned lt_mask = (1u << lane) - 1u;
   while (flagged) {
     const int L = __ffs(flagged) - 1;
@@ -214,16 +219,16 @@ __device__ __forceinline__ void scan32(const uint32_t (&r)[32], float thr, uint3
              make_uint2(__float_as_uint(v), pos0 + (uint32_t)lane));
     if (lane == L) cnt = cntL + __popc(bits);
   }
-  __syncwarp();
 }
 
-// UT = user tiles of 128 per CTA, R = cap / 32.  Warps [0, 8*UT) = epilogue, then TMA producer, then MMA issuer.
+// UT = user tiles of 128 per CTA, R = cap / 32.  Warps [0, 4*UT) = epilogue (thread = one user, all 128 columns of
+// the tile), then TMA producer, then MMA issuer.
 // "Job" j = one [128 users x 128 items] accumulator: UT == 2: tile j / 2, user tile j % 2;  UT == 1: tile j.
 // Job j uses accumulator j % NACC (NACC = 3 when the user operand leaves room in the 512 TMEM columns).
 template <int UT, int R, int NACC>
-__global__ void __launch_bounds__((8 * UT + 2) * 32, 1)
+__global__ void __launch_bounds__((4 * UT + 2) * 32, 1)
 topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
-  constexpr int NEW = 8 * UT;  // epilogue warps: 4 lane quarters x CS column slices per accumulator in flight
+  constexpr int NEW = 4 * UT;  // epilogue warps: 4 TMEM lane quarters per user tile
   constexpr int NUSERS = UT * UM;
   constexpr int CAP = 32 * R;
   constexpr int A_COL0 = NACC * TI;  // first TMEM column of the user operand (accumulators live below it)
@@ -239,7 +244,7 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
   uint64_t* tempty_bar = tfull_bar + 3;          // [NACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 3);
   uint32_t* s_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [NUSERS] orderable bits
-  float* s_rows = reinterpret_cast<float*>(s_thr + NUSERS);  // [NEW warps][32 rows][ROW_PITCH] staged accumulator rows
+  float* s_rows = reinterpret_cast<float*>(s_thr + NUSERS);  // [NEW warps][NBLK blocks][32 rows][ROW_PITCH] staged rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t u0 = (int64_t)blockIdx.x * NUSERS;
@@ -257,7 +262,7 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
     }
     for (int a = 0; a < NACC; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);
+      mbar_init(&tempty_bar[a], 4);
     }
     fence_barrier_init();
   }
@@ -271,10 +276,8 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
   // ---- user operand: global bf16 rows -> TMEM (lane = user, column j = elements 2j, 2j+1)
   if (warp < NEW) {
     const int q = warp & 3;
-    const int grp = warp >> 2;  // UT == 2: user tile = grp % 2, slice = grp / 2;  UT == 1: slice = grp
-    const int ut = (UT == 2) ? (grp & 1) : 0;
-    const int cs = (UT == 2) ? (grp >> 1) : grp;
-    if (cs == 0) {
+    const int ut = warp >> 2;
+    {
       const int64_t u = u0 + ut * UM + q * 32 + lane;
       const uint4* row = reinterpret_cast<const uint4*>(p.users + (u < p.U ? u : 0) * p.ldu);
       for (int c32 = 0; c32 < KA / 32; ++c32) {
@@ -360,21 +363,18 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
   } else {
     // ------------------------------------------------------------------ epilogue: lane = user, columns = items
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int grp = warp >> 2;
-    const int ut = (UT == 2) ? (grp & 1) : 0;
-    const int cs = (UT == 2) ? (grp >> 1) : grp;
+    const int ut = warp >> 2;
     const int ul0 = ut * UM + q * 32;  // first user (CTA-local) of this warp
     const int64_t u_warp = u0 + ul0;
     const int64_t u = u_warp + lane;
-    uint2* warp_list = p.cand + (((size_t)split * p.users_padded + u_warp) * CS + cs) * (size_t)CAP;
-    constexpr size_t LANE_STRIDE = (size_t)CS * CAP;
-    uint2* my_list = warp_list + lane * LANE_STRIDE;
+    uint2* warp_list = p.cand + ((size_t)split * p.users_padded + u_warp) * (size_t)CAP;
+    constexpr size_t LANE_STRIDE = (size_t)CAP;
     float thr = (u < p.U) ? -INFINITY : INFINITY;  // users past the end never collect candidates
     int cnt = 0;
     // cursor into the user's sorted seen row
     int64_t cur = 0, cend = 0;
     int32_t next_seen = 0x7FFFFFFF, after_next = 0x7FFFFFFF;  // two entries ahead: the load latency stays hidden
-    float* srow = s_rows + (size_t)warp * 32 * ROW_PITCH;
+    float* srow = s_rows + (size_t)warp * NBLK * 32 * ROW_PITCH;
     if (p.seen_indptr != nullptr && u < p.U) {
       int64_t lo = __ldg(p.seen_indptr + u), hi = __ldg(p.seen_indptr + u + 1);
       cend = hi;
@@ -388,70 +388,90 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
       if (cur < cend) next_seen = __ldg(p.seen_indices + cur);
       if (cur + 1 < cend) after_next = __ldg(p.seen_indices + cur + 1);
     }
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cs * W);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int32_t n_items32 = (int32_t)p.I;
 
     for (int j = (UT == 2) ? ut : 0; j < n_jobs; j += UT) {
       const int a = j % NACC;
       const uint32_t use = (uint32_t)(j / NACC);
       const int t = (UT == 2) ? (j >> 1) : j;
-      const int64_t item0 = (int64_t)(tile_begin + t) * TI + cs * W;
-      thr = fmaxf(thr, orderable_to_float(s_thr[ul0 + lane]));
+      const int32_t item0 = (tile_begin + t) * TI;
+      const float thr_scan = p.debug == -1 ? INFINITY : thr;  // (-1: measurement of the common path alone)
       mbar_wait(&tfull_bar[a], use & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      if (p.debug < 2) {
-        tmem_ld32(lane_taddr + (uint32_t)(a * TI), r0);
-        tmem_ld32(lane_taddr + (uint32_t)(a * TI + 32), r1);
-        tmem_ld_wait();
+      unsigned flagged[NBLK];
+#pragma unroll
+      for (int h = 0; h < NBLK / 2; ++h) {
+        uint32_t r0[32], r1[32];
+        if (p.debug < 2) {
+          tmem_ld32(lane_taddr + (uint32_t)(a * TI + 64 * h), r0);
+          tmem_ld32(lane_taddr + (uint32_t)(a * TI + 64 * h + 32), r1);
+          tmem_ld_wait();
+        }
+        if (p.debug >= 1) {
+          flagged[2 * h] = flagged[2 * h + 1] = 0u;
+          if (p.debug < 2 && r0[0] == 0x7fc12345u && r1[31] == 0x7fc54321u) cnt = 1;  // keep the loads alive
+        } else {
+          flagged[2 * h] = fast_and_stage(r0, thr_scan, srow + (2 * h) * 32 * ROW_PITCH, lane);
+          flagged[2 * h + 1] = fast_and_stage(r1, thr_scan, srow + (2 * h + 1) * 32 * ROW_PITCH, lane);
+        }
       }
-      // the accumulator is in registers: hand it back to the MMA warp before anything else
+      // every score of the tile has been compared (candidate rows are staged): hand the accumulator back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
-      // seen items / out-of-catalogue columns of this thread's 64-column slice
-      uint32_t skip0 = 0u, skip1 = 0u;
-      if (__any_sync(0xffffffffu, (int64_t)next_seen < item0 + W)) {
-        while ((int64_t)next_seen < item0 + W) {
-          const int rel = (int)((int64_t)next_seen - item0);
-          if (rel >= 32) skip1 |= 1u << (rel - 32);
-          else if (rel >= 0) skip0 |= 1u << rel;
+      unsigned any_flag = 0u;
+#pragma unroll
+      for (int bq = 0; bq < NBLK; ++bq) any_flag |= flagged[bq];
+      // seen items of this user inside the tile (the cursor only ever moves forward)
+      uint32_t skip[NBLK];
+#pragma unroll
+      for (int bq = 0; bq < NBLK; ++bq) skip[bq] = 0u;
+      if (__any_sync(0xffffffffu, next_seen < item0 + W)) {
+        while (next_seen < item0 + W) {
+          const int rel = next_seen - item0;
+          if (rel >= 0) {
+#pragma unroll
+            for (int bq = 0; bq < NBLK; ++bq)
+              if ((rel >> 5) == bq) skip[bq] |= 1u << (rel & 31);
+          }
           ++cur;
           next_seen = after_next;
           after_next = cur + 1 < cend ? __ldg(p.seen_indices + cur + 1) : 0x7FFFFFFF;
         }
       }
-      if (item0 + W > p.I) {  // last tile: columns beyond the catalogue hold zeros
-        const int64_t nvalid = p.I - item0;
-        skip0 |= nvalid <= 0 ? 0xFFFFFFFFu : (nvalid >= 32 ? 0u : (0xFFFFFFFFu << nvalid));
-        skip1 |= nvalid <= 32 ? 0xFFFFFFFFu : (nvalid >= 64 ? 0u : (0xFFFFFFFFu << (nvalid - 32)));
-      }
-      if (p.debug >= 1) {
-        if (p.debug < 2 && r0[0] == 0x7fc12345u && r1[31] == 0x7fc54321u) cnt = 1;  // keep the loads alive
-      } else {
-        if (p.debug == -1) thr = INFINITY;  // measurement only: common path of the scan alone
-        scan32(r0, thr, (uint32_t)item0, skip0, warp_list, LANE_STRIDE, srow, lane, cnt);
-        scan32(r1, thr, (uint32_t)item0 + 32u, skip1, warp_list, LANE_STRIDE, srow, lane, cnt);
-      }
-      // prune the lists that could overflow during the next tile
-      unsigned need = __ballot_sync(0xffffffffu, cnt > p.prune_at);
-      while (need) {
-        const int L = __ffs(need) - 1;
-        need &= need - 1;
-        const int cntL = __shfl_sync(0xffffffffu, cnt, L);
-        int nc;
-        unsigned long long bound;
-        prune_list<R>(warp_list + L * LANE_STRIDE, cntL, p.k, lane, nc, bound);
-        if (lane == L) {
-          cnt = nc;
-          if (bound != 0ull) {
-            const uint32_t hi = (uint32_t)(bound >> 32);
-            thr = fmaxf(thr, orderable_to_float(hi));
-            atomicMax(&s_thr[ul0 + lane], hi);
+      if (any_flag) {
+        if (item0 + W > n_items32) {  // last tile: columns beyond the catalogue hold zeros
+          const int nvalid = n_items32 - item0;
+#pragma unroll
+          for (int bq = 0; bq < NBLK; ++bq) {
+            const int nv = nvalid - 32 * bq;
+            skip[bq] |= nv <= 0 ? 0xFFFFFFFFu : (nv >= 32 ? 0u : (0xFFFFFFFFu << nv));
+          }
+        }
+#pragma unroll
+        for (int bq = 0; bq < NBLK; ++bq)
+          if (flagged[bq])
+            handle_events(flagged[bq], thr_scan, (uint32_t)(item0 + 32 * bq), skip[bq], warp_list, LANE_STRIDE,
+                          srow + bq * 32 * ROW_PITCH, lane, cnt);
+        __syncwarp();  // the staged rows are free again
+        // prune the lists that could overflow during the next tile
+        unsigned need = __ballot_sync(0xffffffffu, cnt > p.prune_at);
+        while (need) {
+          const int L = __ffs(need) - 1;
+          need &= need - 1;
+          const int cntL = __shfl_sync(0xffffffffu, cnt, L);
+          int nc;
+          unsigned long long bound;
+          prune_list<R>(warp_list + L * LANE_STRIDE, cntL, p.k, lane, nc, bound);
+          if (lane == L) {
+            cnt = nc;
+            if (bound != 0ull) thr = fmaxf(thr, orderable_to_float((uint32_t)(bound >> 32)));
           }
         }
       }
     }
-    if (u < p.U) p.cand_cnt[((size_t)split * p.users_padded + u) * CS + cs] = cnt;
+    if (u < p.U) p.cand_cnt[(size_t)split * p.users_padded + u] = cnt;
   }
 
   tc_fence_before();
@@ -501,17 +521,17 @@ __global__ void topk_finalize_kernel(TopkParams p, int n_splits) {
 inline int topk_ut(int D) { return D <= 256 ? 2 : 1; }
 inline int topk_stages(int UT, int D) {
   const int KC = (D + 63) / 64;
-  int s = UT == 2 ? 8 : 10;
+  int s = UT == 2 ? 4 : 8;
   const char* e = getenv("SBR_TOPK_STAGES");  // measurement only
   if (e) s = atoi(e);
   const int lo = UT == 2 ? KC + 1 : 2;  // a chunk stays resident until both user tiles have consumed it
   return s < lo ? lo : (s > MAX_STAGES ? MAX_STAGES : s);
 }
 inline size_t topk_smem_bytes(int UT, int stages) {
-  return (size_t)stages * STAGE_BYTES + 256 + (size_t)UT * UM * 4 + (size_t)(8 * UT) * 32 * ROW_PITCH * 4 + 1024 + 64;
+  return (size_t)stages * STAGE_BYTES + 256 + (size_t)UT * UM * 4 + (size_t)(4 * UT) * NBLK * 32 * ROW_PITCH * 4 + 1024 + 64;
 }
 inline int topk_cap(int k) {
-  int cap = k <= 24 ? 128 : (k <= 96 ? 256 : 512);
+  int cap = k <= 48 ? 256 : 512;  // room for the 128 candidates one tile can add, plus several times k
   const char* e = getenv("SBR_TOPK_CAP");  // measurement only
   if (e && atoi(e) >= cap) cap = atoi(e);
   return cap;
@@ -639,7 +659,7 @@ int launch_topk_n(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, i
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  topk_scores_kernel<UT, R, NACC><<<dim3(user_tiles, n_splits), (8 * UT + 2) * 32, smem, st>>>(tmI, p);
+  topk_scores_kernel<UT, R, NACC><<<dim3(user_tiles, n_splits), (4 * UT + 2) * 32, smem, st>>>(tmI, p);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -660,7 +680,6 @@ int launch_topk(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int
 
 template <int UT>
 int launch_topk_r(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int n_splits, cudaStream_t st) {
-  if (p.cap == 128) return launch_topk<UT, 4>(tmI, p, user_tiles, n_splits, st);
   if (p.cap == 256) return launch_topk<UT, 8>(tmI, p, user_tiles, n_splits, st);
   return launch_topk<UT, 16>(tmI, p, user_tiles, n_splits, st);
 }
@@ -673,7 +692,7 @@ extern "C" int sbr_topk_workspace_bytes(int64_t U, int64_t I, int D, int k, int 
   const int64_t users_padded = (U + NU - 1) / NU * NU;
   const int64_t lists = users_padded * n_splits * CS;
   int cap = topk_cap(k);
-  if (cap != 128 && cap != 256) cap = 512;
+  if (cap != 256) cap = 512;
   *bytes_out = lists * cap * 8 + lists * 4;
   return SBR_OK;
 }
@@ -706,8 +725,12 @@ extern "C" int sbr_topk_scores_masked(const void* users, int64_t ldu, const void
   TopkParams p;
   p.U = U; p.I = I; p.D = D; p.k = k; p.ldu = ldu;
   p.cap = topk_cap(k);
-  if (p.cap != 128 && p.cap != 256) p.cap = 512;
-  p.prune_at = p.cap - W;
+  if (p.cap != 256) p.cap = 512;
+  // prune trigger: early enough that the thresholds stay tight (every candidate costs ~30 warp instructions), late
+  // enough that a prune (~2 us of one warp) stays rare -- measured optimum ~2k + 28 entries (gpurun_out/topk_v10)
+  p.prune_at = 2 * k + 28;
+  if (p.prune_at < 48) p.prune_at = 48;
+  if (p.prune_at > p.cap - W) p.prune_at = p.cap - W;
   {
     const char* e = getenv("SBR_TOPK_PRUNE_AT");  // measurement only
     if (e && atoi(e) >= k && atoi(e) <= p.cap - W) p.prune_at = atoi(e);
