@@ -35,7 +35,7 @@ constexpr int NBLK = W / 32;    // 32-column blocks per thread and tile
 
 struct TopkParams {
   int64_t U, I, users_padded, ldu;
-  int D, k, cap, prune_at;
+  int D, k, cap, prune_at, sbuf_trigger;
   int tiles_per_split, num_item_tiles, stages;
   int32_t item_offset;
   int debug;  // SBR_TOPK_DEBUG (measurement only): 1 = skip the scan, 2 = also skip the TMEM load, 3 = 2 + no TMA,
@@ -176,56 +176,106 @@ __device__ __forceinline__ void prune_list(uint2* list, int count, int k, int la
 
 constexpr int ROW_PITCH = 36;  // floats per staged accumulator row (16-byte aligned, not a multiple of 32 banks)
 
-// One 32-column block of the accumulator: lane = user, r[c] = score of item pos0 + c.  Common path: 3-input max tree
-// + one vote.  Lanes that hold a score >= their threshold stage their 32 scores in shared memory (the registers
-// are then free for the next TMEM load); returns the ballot of those lanes.
-__device__ __forceinline__ unsigned fast_and_stage(const uint32_t (&r)[32], float thr, float* srow, int lane) {
+constexpr int POOL = 64;   // staged candidate rows per warp (compact pool shared by the blocks of a tile)
+constexpr int SBUF_N = 64; // per-user score buffer in shared memory (threshold maintenance without global memory)
+
+// max of one 32-column block of the accumulator (lane = user): 3-input max tree, ~0.5 instructions per score
+__device__ __forceinline__ float block_max(const uint32_t (&r)[32]) {
   float m[11];
 #pragma unroll
   for (int g = 0; g < 10; ++g)
     m[g] = fmax3(__uint_as_float(r[3 * g]), __uint_as_float(r[3 * g + 1]), __uint_as_float(r[3 * g + 2]));
   m[10] = fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31]));
   const float a = fmax3(m[0], m[1], m[2]), b = fmax3(m[3], m[4], m[5]), c = fmax3(m[6], m[7], m[8]);
-  const float mm = fmax3(fmax3(a, b, c), m[9], m[10]);
-  const bool mine = mm >= thr;
-  const unsigned flagged = __ballot_sync(0xffffffffu, mine);
-  if (flagged != 0u && mine) {
-    float4* dst = reinterpret_cast<float4*>(srow + lane * ROW_PITCH);
+  return fmax3(fmax3(a, b, c), m[9], m[10]);
+}
+
+// lanes that hold a candidate copy their 32 scores into consecutive pool slots starting at `base`
+__device__ __forceinline__ void stage_rows(const uint32_t (&r)[32], unsigned flagged, bool mine, float* pool, int base,
+                                           int lane) {
+  if (mine) {
+    const int slot = base + __popc(flagged & ((1u << lane) - 1u));
+    float4* dst = reinterpret_cast<float4*>(pool + slot * ROW_PITCH);
 #pragma unroll
     for (int v = 0; v < 8; ++v)
       dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
                            __uint_as_float(r[4 * v + 3]));
   }
-  return flagged;
 }
 
 // The staged rows of one block, one user at a time with lane = column: one compare against that user's threshold and
-// seen mask, one ballot, one coalesced append to that user's candidate list.
-__device__ __forceinline__ void handle_events(unsigned flagged, float thr, uint32_t pos0, uint32_t skip,
-                                              uint2* warp_list, size_t lane_stride, const float* srow, int lane,
-                                              int& cnt) {
+// seen mask, one ballot, one coalesced append to that user's candidate list (and, SBUF, of the scores alone to the
+// user's shared-memory buffer that the threshold is refreshed from).
+template <bool SBUF>
+__device__ __forceinline__ void handle_events(unsigned flagged, int base, float thr, uint32_t pos0, uint32_t skip,
+                                              uint2* warp_list, size_t lane_stride, const float* pool,
+                                              float* warp_sbuf, int lane, int& cnt, int& scnt) {
   const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned all = flagged;
   while (flagged) {
     const int L = __ffs(flagged) - 1;
     flagged &= flagged - 1;
-    const float v = srow[L * ROW_PITCH + lane];
+    const float v = pool[(base + __popc(all & ((1u << L) - 1u))) * ROW_PITCH + lane];
     const float thrL = __shfl_sync(0xffffffffu, thr, L);
     const uint32_t skipL = __shfl_sync(0xffffffffu, skip, L);
     const int cntL = __shfl_sync(0xffffffffu, cnt, L);
     const bool pass = v >= thrL && !((skipL >> lane) & 1u);
     const unsigned bits = __ballot_sync(0xffffffffu, pass);
-    if (pass)
-      __stcg(warp_list + L * lane_stride + cntL + __popc(bits & lt_mask),
-             make_uint2(__float_as_uint(v), pos0 + (uint32_t)lane));
-    if (lane == L) cnt = cntL + __popc(bits);
+    const int rank = __popc(bits & lt_mask), n = __popc(bits);
+    if (pass) __stcg(warp_list + L * lane_stride + cntL + rank, make_uint2(__float_as_uint(v), pos0 + (uint32_t)lane));
+    if (SBUF) {
+      const int scL = __shfl_sync(0xffffffffu, scnt, L);
+      if (pass && scL + rank < SBUF_N) warp_sbuf[L * SBUF_N + scL + rank] = v;  // dropping is safe: bound of a subset
+      if (lane == L) scnt = min(SBUF_N, scL + n);
+    }
+    if (lane == L) cnt = cntL + n;
   }
+}
+
+// Threshold refresh from one user's score buffer (n <= 64 scores in shared memory, two per lane): bisection for a
+// value t with at least k scores >= t (exactly k unless scores tie), survivors compacted to the front.
+__device__ __forceinline__ void refresh_threshold(float* sbuf, int n, int k, int lane, int& new_n, uint32_t& bound) {
+  const uint32_t x0 = lane < n ? orderable(__float_as_uint(sbuf[lane])) : 0u;
+  const uint32_t x1 = lane + 32 < n ? orderable(__float_as_uint(sbuf[lane + 32])) : 0u;
+  bound = 0u;
+  new_n = n;
+  if (n <= k) return;
+  const uint32_t orv = __reduce_or_sync(0xffffffffu, x0 | x1);
+  const uint32_t andv = __reduce_and_sync(0xffffffffu, (x0 ? x0 : 0xFFFFFFFFu) & (x1 ? x1 : 0xFFFFFFFFu));
+  const uint32_t diff = orv ^ andv;
+  uint32_t prefix = andv;  // all scores equal: everything survives
+  if (diff != 0u) {
+    const int top = 31 - __clz((int)diff);
+    prefix = top == 31 ? 0u : (andv & ~((2u << top) - 1u));
+#pragma unroll 1
+    for (int bit = top; bit >= 0; --bit) {
+      const uint32_t trial = prefix | (1u << bit);
+      const int c = __reduce_add_sync(0xffffffffu, (x0 >= trial ? 1 : 0) + (x1 >= trial ? 1 : 0));
+      if (c >= k) {
+        prefix = trial;
+        if (c == k) break;
+      }
+    }
+  }
+  bound = prefix;
+  __syncwarp();
+  const bool k0 = x0 != 0u && x0 >= prefix, k1 = x1 != 0u && x1 >= prefix;
+  const unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+  const float v0 = orderable_to_float(x0), v1 = orderable_to_float(x1);
+  __syncwarp();
+  if (k0) sbuf[__popc(b0 & ((1u << lane) - 1u))] = v0;
+  if (k1) sbuf[__popc(b0) + __popc(b1 & ((1u << lane) - 1u))] = v1;
+  new_n = __popc(b0) + __popc(b1);
+  __syncwarp();
 }
 
 // UT = user tiles of 128 per CTA, R = cap / 32.  Warps [0, 4*UT) = epilogue (thread = one user, all 128 columns of
 // the tile), then TMA producer, then MMA issuer.
 // "Job" j = one [128 users x 128 items] accumulator: UT == 2: tile j / 2, user tile j % 2;  UT == 1: tile j.
 // Job j uses accumulator j % NACC (NACC = 3 when the user operand leaves room in the 512 TMEM columns).
-template <int UT, int R, int NACC>
+// SBUF (k <= 40): thresholds are refreshed from per-user score buffers in shared memory; the global lists are then
+// append-only until they are nearly full.
+template <int UT, int R, int NACC, bool SBUF>
 __global__ void __launch_bounds__((4 * UT + 2) * 32, 1)
 topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
   constexpr int NEW = 4 * UT;  // epilogue warps: 4 TMEM lane quarters per user tile
@@ -244,7 +294,8 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
   uint64_t* tempty_bar = tfull_bar + 3;          // [NACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 3);
   uint32_t* s_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [NUSERS] orderable bits
-  float* s_rows = reinterpret_cast<float*>(s_thr + NUSERS);  // [NEW warps][NBLK blocks][32 rows][ROW_PITCH] staged rows
+  float* s_rows = reinterpret_cast<float*>(s_thr + NUSERS);  // [NEW warps][POOL slots][ROW_PITCH] staged candidate rows
+  float* s_sbuf = s_rows + NEW * POOL * ROW_PITCH;            // SBUF: [NUSERS][SBUF_N] candidate scores per user
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t u0 = (int64_t)blockIdx.x * NUSERS;
@@ -374,7 +425,9 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
     // cursor into the user's sorted seen row
     int64_t cur = 0, cend = 0;
     int32_t next_seen = 0x7FFFFFFF, after_next = 0x7FFFFFFF;  // two entries ahead: the load latency stays hidden
-    float* srow = s_rows + (size_t)warp * NBLK * 32 * ROW_PITCH;
+    float* pool = s_rows + (size_t)warp * POOL * ROW_PITCH;
+    float* warp_sbuf = s_sbuf + (size_t)ul0 * SBUF_N;
+    int scnt = 0;
     if (p.seen_indptr != nullptr && u < p.U) {
       int64_t lo = __ldg(p.seen_indptr + u), hi = __ldg(p.seen_indptr + u + 1);
       cend = hi;
@@ -390,6 +443,7 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
     }
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int32_t n_items32 = (int32_t)p.I;
+    const int hard_limit = SBUF ? CAP - W : p.prune_at;  // global-list length that forces an exact prune
 
     for (int j = (UT == 2) ? ut : 0; j < n_jobs; j += UT) {
       const int a = j % NACC;
@@ -397,33 +451,7 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
       const int t = (UT == 2) ? (j >> 1) : j;
       const int32_t item0 = (tile_begin + t) * TI;
       const float thr_scan = p.debug == -1 ? INFINITY : thr;  // (-1: measurement of the common path alone)
-      mbar_wait(&tfull_bar[a], use & 1);
-      tc_fence_after();
-      unsigned flagged[NBLK];
-#pragma unroll
-      for (int h = 0; h < NBLK / 2; ++h) {
-        uint32_t r0[32], r1[32];
-        if (p.debug < 2) {
-          tmem_ld32(lane_taddr + (uint32_t)(a * TI + 64 * h), r0);
-          tmem_ld32(lane_taddr + (uint32_t)(a * TI + 64 * h + 32), r1);
-          tmem_ld_wait();
-        }
-        if (p.debug >= 1) {
-          flagged[2 * h] = flagged[2 * h + 1] = 0u;
-          if (p.debug < 2 && r0[0] == 0x7fc12345u && r1[31] == 0x7fc54321u) cnt = 1;  // keep the loads alive
-        } else {
-          flagged[2 * h] = fast_and_stage(r0, thr_scan, srow + (2 * h) * 32 * ROW_PITCH, lane);
-          flagged[2 * h + 1] = fast_and_stage(r1, thr_scan, srow + (2 * h + 1) * 32 * ROW_PITCH, lane);
-        }
-      }
-      // every score of the tile has been compared (candidate rows are staged): hand the accumulator back
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[a]);
-      unsigned any_flag = 0u;
-#pragma unroll
-      for (int bq = 0; bq < NBLK; ++bq) any_flag |= flagged[bq];
-      // seen items of this user inside the tile (the cursor only ever moves forward)
+      // seen items of this user inside the tile (the cursor only ever moves forward) + columns beyond the catalogue
       uint32_t skip[NBLK];
 #pragma unroll
       for (int bq = 0; bq < NBLK; ++bq) skip[bq] = 0u;
@@ -440,23 +468,91 @@ topk_scores_kernel(const __grid_constant__ CUtensorMap tmI, TopkParams p) {
           after_next = cur + 1 < cend ? __ldg(p.seen_indices + cur + 1) : 0x7FFFFFFF;
         }
       }
-      if (any_flag) {
-        if (item0 + W > n_items32) {  // last tile: columns beyond the catalogue hold zeros
-          const int nvalid = n_items32 - item0;
+      if (item0 + W > n_items32) {
+        const int nvalid = n_items32 - item0;
 #pragma unroll
-          for (int bq = 0; bq < NBLK; ++bq) {
-            const int nv = nvalid - 32 * bq;
-            skip[bq] |= nv <= 0 ? 0xFFFFFFFFu : (nv >= 32 ? 0u : (0xFFFFFFFFu << nv));
+        for (int bq = 0; bq < NBLK; ++bq) {
+          const int nv = nvalid - 32 * bq;
+          skip[bq] |= nv <= 0 ? 0xFFFFFFFFu : (nv >= 32 ? 0u : (0xFFFFFFFFu << nv));
+        }
+      }
+      mbar_wait(&tfull_bar[a], use & 1);
+      tc_fence_after();
+      unsigned flg[NBLK];
+      int base[NBLK];
+#pragma unroll
+      for (int bq = 0; bq < NBLK; ++bq) flg[bq] = 0u, base[bq] = 0;
+      int pool_used = 0;
+      // candidate rows wait in the pool until the whole tile has been compared (then TMEM is released first); if the
+      // pool cannot take a block's rows (first tiles of a pass: every score is a candidate) the pending blocks are
+      // handled on the spot
+      auto flush = [&]() {
+        __syncwarp();
+#pragma unroll
+        for (int bq = 0; bq < NBLK; ++bq) {
+          if (flg[bq]) {
+            handle_events<SBUF>(flg[bq], base[bq], thr_scan, (uint32_t)(item0 + 32 * bq), skip[bq], warp_list,
+                                LANE_STRIDE, pool, warp_sbuf, lane, cnt, scnt);
+            flg[bq] = 0u;
           }
         }
+        pool_used = 0;
+        __syncwarp();
+      };
 #pragma unroll
-        for (int bq = 0; bq < NBLK; ++bq)
-          if (flagged[bq])
-            handle_events(flagged[bq], thr_scan, (uint32_t)(item0 + 32 * bq), skip[bq], warp_list, LANE_STRIDE,
-                          srow + bq * 32 * ROW_PITCH, lane, cnt);
-        __syncwarp();  // the staged rows are free again
-        // prune the lists that could overflow during the next tile
-        unsigned need = __ballot_sync(0xffffffffu, cnt > p.prune_at);
+      for (int h = 0; h < NBLK / 2; ++h) {
+        uint32_t r0[32], r1[32];
+        if (p.debug < 2) {
+          tmem_ld32(lane_taddr + (uint32_t)(a * TI + 64 * h), r0);
+          tmem_ld32(lane_taddr + (uint32_t)(a * TI + 64 * h + 32), r1);
+          tmem_ld_wait();
+        }
+        if (p.debug >= 1) {
+          if (p.debug < 2 && r0[0] == 0x7fc12345u && r1[31] == 0x7fc54321u) cnt = 1;  // keep the loads alive
+        } else {
+          {
+            const bool mine = block_max(r0) >= thr_scan;
+            const unsigned f = __ballot_sync(0xffffffffu, mine);
+            if (f) {
+              if (pool_used + __popc(f) > POOL) flush();
+              stage_rows(r0, f, mine, pool, pool_used, lane);
+              flg[2 * h] = f; base[2 * h] = pool_used; pool_used += __popc(f);
+            }
+          }
+          {
+            const bool mine = block_max(r1) >= thr_scan;
+            const unsigned f = __ballot_sync(0xffffffffu, mine);
+            if (f) {
+              if (pool_used + __popc(f) > POOL) flush();
+              stage_rows(r1, f, mine, pool, pool_used, lane);
+              flg[2 * h + 1] = f; base[2 * h + 1] = pool_used; pool_used += __popc(f);
+            }
+          }
+        }
+      }
+      // every score of the tile has been compared (candidate rows are staged): hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      if (pool_used > 0) {
+        flush();
+        if (SBUF) {  // cheap threshold refresh from the shared-memory score buffers
+          unsigned need = __ballot_sync(0xffffffffu, scnt >= p.sbuf_trigger);
+          while (need) {
+            const int L = __ffs(need) - 1;
+            need &= need - 1;
+            const int nL = __shfl_sync(0xffffffffu, scnt, L);
+            int nn;
+            uint32_t bound;
+            refresh_threshold(warp_sbuf + L * SBUF_N, nL, p.k, lane, nn, bound);
+            if (lane == L) {
+              scnt = nn;
+              if (bound != 0u) thr = fmaxf(thr, orderable_to_float(bound));
+            }
+          }
+        }
+        // exact prune of the global lists that could overflow during the next tile
+        unsigned need = __ballot_sync(0xffffffffu, cnt > hard_limit);
         while (need) {
           const int L = __ffs(need) - 1;
           need &= need - 1;
@@ -528,10 +624,13 @@ inline int topk_stages(int UT, int D) {
   return s < lo ? lo : (s > MAX_STAGES ? MAX_STAGES : s);
 }
 inline size_t topk_smem_bytes(int UT, int stages) {
-  return (size_t)stages * STAGE_BYTES + 256 + (size_t)UT * UM * 4 + (size_t)(4 * UT) * NBLK * 32 * ROW_PITCH * 4 + 1024 + 64;
+  return (size_t)stages * STAGE_BYTES + 256 + (size_t)UT * UM * 4 + (size_t)(4 * UT) * POOL * ROW_PITCH * 4 +
+         (size_t)UT * UM * SBUF_N * 4 + 1024 + 64;
 }
 inline int topk_cap(int k) {
-  int cap = k <= 48 ? 256 : 512;  // room for the 128 candidates one tile can add, plus several times k
+  // k <= 40: thresholds come from shared-memory score buffers and the global list is append-only -> roomy list;
+  // larger k: the list itself is pruned at 2k + 28 entries
+  int cap = ((k <= 40 && getenv("SBR_TOPK_SBUF")) || k > 48) ? 512 : 256;
   const char* e = getenv("SBR_TOPK_CAP");  // measurement only
   if (e && atoi(e) >= cap) cap = atoi(e);
   return cap;
@@ -650,16 +749,16 @@ __global__ void metrics_kernel(const int32_t* __restrict__ topk_idx, int64_t U, 
   }
 }
 
-template <int UT, int R, int NACC>
+template <int UT, int R, int NACC, bool SBUF>
 int launch_topk_n(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int n_splits, cudaStream_t st) {
   const size_t smem = topk_smem_bytes(UT, p.stages);
   static size_t configured = 0;
   if (smem > configured) {
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(topk_scores_kernel<UT, R, NACC>,
+    SBR_CHECK_CUDA(cudaFuncSetAttribute(topk_scores_kernel<UT, R, NACC, SBUF>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  topk_scores_kernel<UT, R, NACC><<<dim3(user_tiles, n_splits), (4 * UT + 2) * 32, smem, st>>>(tmI, p);
+  topk_scores_kernel<UT, R, NACC, SBUF><<<dim3(user_tiles, n_splits), (4 * UT + 2) * 32, smem, st>>>(tmI, p);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -669,8 +768,13 @@ int launch_topk(const CUtensorMap& tmI, const TopkParams& p, int user_tiles, int
   // a third accumulator fits next to the user operand when UT * ceil(D / 64) * 32 <= 128 TMEM columns
   const bool three = UT == 2 && p.D <= 128 && !getenv("SBR_TOPK_NACC2");
   int rc;
-  if (UT == 2 && three) rc = launch_topk_n<UT, R, (UT == 2 ? 3 : 2)>(tmI, p, user_tiles, n_splits, st);
-  else rc = launch_topk_n<UT, R, 2>(tmI, p, user_tiles, n_splits, st);
+  const bool sbuf = p.sbuf_trigger > 0;
+  if (UT == 2 && three)
+    rc = sbuf ? launch_topk_n<UT, R, (UT == 2 ? 3 : 2), true>(tmI, p, user_tiles, n_splits, st)
+              : launch_topk_n<UT, R, (UT == 2 ? 3 : 2), false>(tmI, p, user_tiles, n_splits, st);
+  else
+    rc = sbuf ? launch_topk_n<UT, R, 2, true>(tmI, p, user_tiles, n_splits, st)
+              : launch_topk_n<UT, R, 2, false>(tmI, p, user_tiles, n_splits, st);
   if (rc) return rc;
   SBR_LAUNCH_CHECK();
   topk_finalize_kernel<R><<<cdiv((int64_t)n_splits * p.U, 4), 128, 0, st>>>(p, n_splits);
@@ -731,6 +835,13 @@ extern "C" int sbr_topk_scores_masked(const void* users, int64_t ldu, const void
   p.prune_at = 2 * k + 28;
   if (p.prune_at < 48) p.prune_at = 48;
   if (p.prune_at > p.cap - W) p.prune_at = p.cap - W;
+  p.sbuf_trigger = 0;
+  // (measured: no faster than pruning the list itself at 2k + 28 entries -> off unless SBR_TOPK_SBUF is set)
+  if (k <= 40 && getenv("SBR_TOPK_SBUF")) {
+    p.sbuf_trigger = k + 16;  // refresh when the buffer holds k survivors + 16 new scores
+    const char* e = getenv("SBR_TOPK_TRIG");  // measurement only
+    if (e && atoi(e) > k && atoi(e) <= SBUF_N) p.sbuf_trigger = atoi(e);
+  }
   {
     const char* e = getenv("SBR_TOPK_PRUNE_AT");  // measurement only
     if (e && atoi(e) >= k && atoi(e) <= p.cap - W) p.prune_at = atoi(e);
