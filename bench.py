@@ -361,19 +361,38 @@ def main():
     value = world * B * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: host buffers in, loss out, through the public trainer API
+    # (double-buffered: the pinned-memory fill and the H2D copy of batch k+1 run on a copy stream while step k
+    # computes; every step still ends with a device -> host read of its losses)
     hu = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(2)]
     hi = [torch.empty((B, n), dtype=torch.int64).pin_memory() for _ in range(2)]
     host_batches = [(b[0].cpu(), b[1].cpu()) for b in batches[:4]]
-    du, di = torch.empty_like(batches[0][0]), torch.empty_like(batches[0][1])
-    sync_all()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
+    dbuf = [(torch.empty_like(batches[0][0]), torch.empty_like(batches[0][1])) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(k):
+        s_ = k % 2
         src = host_batches[k % len(host_batches)]
-        hu[k % 2].copy_(src[0])
-        hi[k % 2].copy_(src[1])
-        du.copy_(hu[k % 2], non_blocking=True)
-        di.copy_(hi[k % 2], non_blocking=True)
-        tr.step(du, di)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s_])  # the step that last read this device buffer has finished
+            hu[s_].copy_(src[0])
+            hi[s_].copy_(src[1])
+            dbuf[s_][0].copy_(hu[s_], non_blocking=True)
+            dbuf[s_][1].copy_(hi[s_], non_blocking=True)
+            ready[s_].record(copy_stream)
+
+    sync_all()
+    for e in consumed:
+        e.record()
+    t0 = time.perf_counter()
+    stage(0)
+    for k in range(args.steps):
+        torch.cuda.current_stream().wait_event(ready[k % 2])
+        tr.step(*dbuf[k % 2])
+        consumed[k % 2].record()
+        if k + 1 < args.steps:
+            stage(k + 1)
         _ = tr.loss_acc.cpu()  # device -> host read of the step's losses (sync)
     sync_all()
     e2e_s = time.perf_counter() - t0

@@ -186,6 +186,7 @@ row_gather_fwd_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
                         uint64_t seed, const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
                         bf16* __restrict__ out, int64_t ld_out, float* __restrict__ out_f32, int64_t ld_f32,
                         int32_t* err_flag) {
+  SBR_PDL_ENTRY();
   const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   const int li = threadIdx.x % LPR;
   const bool valid = gid < N;
@@ -338,6 +339,7 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
                     const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop, uint64_t seed,
                     const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
                     const float* __restrict__ dx, int64_t ld_dx) {
+  SBR_PDL_ENTRY();
   __shared__ SegShared sh;
   if (threadIdx.x == 0) {
     int used = 0;
@@ -536,6 +538,7 @@ __device__ __forceinline__ int64_t row_key(const sbr_modality_src_t& s, int64_t 
 __global__ void plan_count_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
                                   const int64_t* __restrict__ idx, const uint8_t* __restrict__ mods, int64_t N, int k,
                                   int32_t* __restrict__ counts, int32_t* __restrict__ row_keys) {
+  SBR_PDL_ENTRY();
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= N) return;
   const sbr_modality_src_t& s = srcs[min(mods ? (int)mods[r] : 0, n_mods - 1)];
@@ -550,6 +553,7 @@ __global__ void plan_count_kernel(const sbr_modality_src_t* __restrict__ srcs, i
 // serial pass for the slice sums, one block scan of the 1024 sums, one serial pass to write the offsets
 __global__ void __launch_bounds__(1024)
 plan_scan_kernel(const int32_t* __restrict__ counts, int64_t n, int32_t* __restrict__ offsets) {
+  SBR_PDL_ENTRY();
   __shared__ int32_t warp_sums[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t per = (n + blockDim.x - 1) / blockDim.x;
@@ -585,6 +589,7 @@ plan_scan_kernel(const int32_t* __restrict__ counts, int64_t n, int32_t* __restr
 __global__ void plan_fill_kernel(const int32_t* __restrict__ row_keys, int64_t N, const int32_t* __restrict__ offsets,
                                  int32_t* __restrict__ cursor, int32_t* __restrict__ perm,
                                  int32_t* __restrict__ sorted_keys) {
+  SBR_PDL_ENTRY();
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= N) return;
   const int32_t key = row_keys[r];
@@ -607,9 +612,9 @@ extern "C" int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods
   const int64_t N = n_idx * k;
   DISPATCH_GROUP(C, {
     const int64_t threads = N * LPRv;
-    row_gather_fwd_g_kernel<LPRv, NVg><<<cdiv(threads, 256), 256, 0, S(stream)>>>(
-        srcs_dev, n_mods, idx, mods, N, k, C, normalize, p_drop, seed, step_dev, keep_mask,
-        reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_f32, err_flag);
+    SBR_CHECK_CUDA(sbr_launch(row_gather_fwd_g_kernel<LPRv, NVg>, dim3(cdiv(threads, 256)), dim3(256), 0, S(stream),
+                              srcs_dev, n_mods, idx, mods, N, k, C, normalize, p_drop, seed, step_dev, keep_mask,
+                              reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_f32, err_flag));
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;
@@ -642,9 +647,11 @@ extern "C" int sbr_gather_plan(const sbr_modality_src_t* srcs_dev, int n_mods, c
   SBR_REQUIRE(N < (1ll << 31), "sbr_gather_plan: too many rows");
   SBR_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_keys, S(stream)));
   SBR_CHECK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n_keys, S(stream)));
-  plan_count_kernel<<<cdiv(N, 256), 256, 0, S(stream)>>>(srcs_dev, n_mods, idx, mods, N, k, counts, row_keys);
-  plan_scan_kernel<<<1, 1024, 0, S(stream)>>>(counts, n_keys, offsets);
-  plan_fill_kernel<<<cdiv(N, 256), 256, 0, S(stream)>>>(row_keys, N, offsets, cursor, perm, sorted_keys);
+  SBR_CHECK_CUDA(sbr_launch(plan_count_kernel, dim3(cdiv(N, 256)), dim3(256), 0, S(stream), srcs_dev, n_mods, idx, mods,
+                            N, k, counts, row_keys));
+  SBR_CHECK_CUDA(sbr_launch(plan_scan_kernel, dim3(1), dim3(1024), 0, S(stream), (const int32_t*)counts, n_keys, offsets));
+  SBR_CHECK_CUDA(sbr_launch(plan_fill_kernel, dim3(cdiv(N, 256)), dim3(256), 0, S(stream), (const int32_t*)row_keys, N,
+                            (const int32_t*)offsets, cursor, perm, sorted_keys));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -664,9 +671,9 @@ extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, 
     int64_t blocks = cdiv(threads, 256);
     const int64_t cap = (int64_t)sbr_num_sms() * 4;  // persistent: 4 blocks (45 KB of shared memory each) per SM
     if (blocks > cap) blocks = cap;
-    seg_reduce_g_kernel<LPRv, NVg><<<(unsigned)blocks, 256, 0, S(stream)>>>(
-        srcs_dev, n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed, step_dev, keep_mask, dx,
-        ld_dx);
+    SBR_CHECK_CUDA(sbr_launch(seg_reduce_g_kernel<LPRv, NVg>, dim3((unsigned)blocks), dim3(256), 0, S(stream), srcs_dev,
+                              n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed, step_dev,
+                              keep_mask, dx, ld_dx));
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;

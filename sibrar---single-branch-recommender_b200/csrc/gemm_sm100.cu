@@ -102,6 +102,7 @@ __device__ __forceinline__ void apply_actgrad32(int act, float (&v)[32], const f
 template <int BN, bool A_BITS>
 __global__ void __launch_bounds__(A_BITS ? 320 : 192)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  SBR_PDL_ENTRY();
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -224,23 +225,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
       const int64_t row = (int64_t)tile * BM + row_in_tile;
       const uint2* bits = reinterpret_cast<const uint2*>(p.a_bits + (row < p.M ? row : 0) * p.ld_words);
-      uint2 w_next = make_uint2(0u, 0u);
-      if (row < p.M && kb_begin < kb_end) w_next = __ldg(bits + kb_begin);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const uint2 w = w_next;
-        if (row < p.M && kb + 1 < kb_end) w_next = __ldg(bits + kb + 1);  // 64 bits = one K block of this row
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* dst = sA + s * A_STAGE_BYTES + row_off;
+      // the row's bit words are fetched 8 K blocks at a time, one batch ahead of the batch being expanded: a thread's
+      // 8-byte loads are strided by the row pitch (one 32-byte sector per row), so their latency has to be overlapped
+      constexpr int NB = 8;
+      uint2 nxt[NB];
 #pragma unroll
-        for (uint32_t c = 0; c < 8; ++c) {  // chunk c = K elements 8c .. 8c+7 -> 16 bytes at the swizzled position
-          const uint32_t byte = ((c < 4 ? w.x : w.y) >> ((c & 3) * 8)) & 0xFFu;
-          const uint2 lo = s_lut[byte & 15u], hi = s_lut[byte >> 4];
-          *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+      for (int q = 0; q < NB; ++q)
+        nxt[q] = (row < p.M && kb_begin + q < kb_end) ? __ldg(bits + kb_begin + q) : make_uint2(0u, 0u);
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += NB) {
+        uint2 curw[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) curw[q] = nxt[q];
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+          nxt[q] = (row < p.M && kb0 + NB + q < kb_end) ? __ldg(bits + kb0 + NB + q) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          if (kb0 + q < kb_end) {  // 64 bits = one K block of this row
+            const uint2 w = curw[q];
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* dst = sA + s * A_STAGE_BYTES + row_off;
+#pragma unroll
+            for (uint32_t c = 0; c < 8; ++c) {  // chunk c = K elements 8c .. 8c+7 -> 16 bytes at the swizzled position
+              const uint32_t byte = ((c < 4 ? w.x : w.y) >> ((c & 3) * 8)) & 0xFFu;
+              const uint2 lo = s_lut[byte & 15u], hi = s_lut[byte >> 4];
+              *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+            if (++s == C::STAGES) { s = 0; ph ^= 1; }
+          }
         }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
-        if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -406,8 +422,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   int64_t gx = (sbr_num_sms() * ctas_per_sm) / (n_tiles * splits);
   gx = gx < 1 ? 1 : (gx > m_tiles ? m_tiles : gx);
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);
-  gemm_bf16_kernel<BN, A_BITS><<<grid, A_BITS ? 320 : 192, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
-  SBR_LAUNCH_CHECK();
+  SBR_CHECK_CUDA(sbr_launch(gemm_bf16_kernel<BN, A_BITS>, grid, dim3(A_BITS ? 320 : 192), (size_t)Cfg<BN>::SMEM_BYTES, st,
+                            tmA, tmB, p));
   return SBR_OK;
 }
 

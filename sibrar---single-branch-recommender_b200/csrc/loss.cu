@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256)
 score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ ei, int64_t B, int n, int loss_kind,
                        float inv_cnt, float ssm_shift, float* __restrict__ logits, double* __restrict__ loss_acc,
                        float* __restrict__ deu, float* __restrict__ dei) {
+  SBR_PDL_ENTRY();
   constexpr int D = 4 * LPR;
   constexpr int RPP = 32 / LPR;  // item rows per pass
   extern __shared__ float sh[];  // per warp: n scores + n grads; then one loss slot per warp
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(256)
 score_loss_bn_kernel(const float* __restrict__ eu, BnInline bu, const float* __restrict__ ei, BnInline bi, int64_t B,
                      int n, int loss_kind, float inv_cnt, float ssm_shift, float* __restrict__ logits,
                      double* __restrict__ loss_acc, float* __restrict__ deu, float* __restrict__ dei, int n_replicas) {
+  SBR_PDL_ENTRY();
   constexpr int D = 4 * LPR;
   constexpr int RPP = 32 / LPR;  // item rows per pass
   extern __shared__ float sh[];  // per warp: n scores + n grads; then nw loss slots; then nw x 4 x D column sums
@@ -458,8 +460,8 @@ extern "C" int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n
     const size_t sm = ((size_t)nw * 2 * n + nw) * sizeof(float);
     const unsigned blocks = cdiv(B, nw);
 #define SBR_FAST(LPR_)                                                                                              \
-  score_loss_fast_kernel<LPR_><<<blocks, nw * 32, sm, S(stream)>>>(eu, ei, B, n, loss_kind, inv, ssm_shift, logits, \
-                                                                   loss_acc, deu, dei)
+  SBR_CHECK_CUDA(sbr_launch(score_loss_fast_kernel<LPR_>, dim3(blocks), dim3(nw * 32), sm, S(stream), eu, ei, B, n,  \
+                            loss_kind, inv, ssm_shift, logits, loss_acc, deu, dei))
     if (D == 16) SBR_FAST(4);
     else if (D == 32) SBR_FAST(8);
     else if (D == 64) SBR_FAST(16);
@@ -515,9 +517,8 @@ extern "C" int sbr_score_loss_bn(const float* eu, const sbr_bn_inline_t* bn_u, c
   if (blocks > cap) blocks = cap;
   const float inv = (float)(1.0 / cnt);
 #define SBR_FUSED(LPR_)                                                                                          \
-  score_loss_bn_kernel<LPR_><<<(unsigned)blocks, nw * 32, sm, S(stream)>>>(eu, bu, ei, bi, B, n, loss_kind, inv, \
-                                                                           ssm_shift, logits, loss_acc, deu, dei, \
-                                                                           n_replicas)
+  SBR_CHECK_CUDA(sbr_launch(score_loss_bn_kernel<LPR_>, dim3((unsigned)blocks), dim3(nw * 32), sm, S(stream), eu, bu, \
+                            ei, bi, B, n, loss_kind, inv, ssm_shift, logits, loss_acc, deu, dei, n_replicas))
   if (D == 16) SBR_FUSED(4);
   else if (D == 32) SBR_FUSED(8);
   else if (D == 64) SBR_FUSED(16);

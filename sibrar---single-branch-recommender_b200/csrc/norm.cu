@@ -42,6 +42,7 @@ __global__ void actgrad_colsum_kernel(float* __restrict__ dy, int64_t ld_dy, con
                                       const bf16* __restrict__ y_bf16, int64_t ld_y, int act, int64_t rows, int C,
                                       bf16* __restrict__ out_bf16, int64_t ld_out, float* __restrict__ out_f32,
                                       int64_t ld_out_f32, float* __restrict__ colsum, int zero_dy, int RB) {
+  SBR_PDL_ENTRY();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   const int64_t r0 = (int64_t)blockIdx.x * RB;
@@ -64,6 +65,7 @@ __global__ void actgrad_colsum_kernel(float* __restrict__ dy, int64_t ld_dy, con
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int64_t n_rows, int C, float eps, float momentum,
                                    float* __restrict__ mean_invstd, float* running_mean, float* running_var,
                                    int64_t* num_batches_tracked) {
+  SBR_PDL_ENTRY();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
   if (c >= C) return;
@@ -92,6 +94,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, int64_t ld_z, const
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                 int64_t rows, int C, bf16* __restrict__ out_bf16, int64_t ld_bf16,
                                 float* __restrict__ out_f32, int64_t ld_f32, int RB) {
+  SBR_PDL_ENTRY();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   if (c >= C) return;
@@ -111,6 +114,7 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t ld_dy
                                      const bf16* __restrict__ y_bf16, int64_t ld_y, int act,
                                      const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
                                      int64_t rows, int C, float* __restrict__ sums, int RB) {
+  SBR_PDL_ENTRY();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   const int64_t r0 = (int64_t)blockIdx.x * RB;
@@ -136,6 +140,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy,
                                     const float* __restrict__ gamma, const float* __restrict__ sums, int n_replicas,
                                     int64_t rows, int C, bf16* __restrict__ dz_bf16, int64_t ld_dz, float* __restrict__ dz_f32,
                                     int64_t ld_dz_f32, float* dgamma, float* dbeta, int RB) {
+  SBR_PDL_ENTRY();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
   if (c >= C) return;
@@ -171,9 +176,9 @@ extern "C" int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, 
                                   int64_t ld_out_f32, float* colsum, int zero_dy, void* stream) {
   SBR_REQUIRE(dy && rows > 0 && cols > 0, "sbr_actgrad_colsum: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_actgrad_colsum: activation gradient needs the output y");
-  actgrad_colsum_kernel<<<tile_grid(rows, cols), 256, 0, S(stream)>>>(
+  SBR_CHECK_CUDA(sbr_launch(actgrad_colsum_kernel, dim3(tile_grid(rows, cols)), dim3(256), (size_t)(0), S(stream), 
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, rows, (int)cols,
-      reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum, zero_dy, rows_per_block(rows));
+      reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum, zero_dy, rows_per_block(rows)));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -182,8 +187,8 @@ extern "C" int sbr_bn_finalize(const float* stats, int64_t n_rows, int C, float 
                                float* mean_invstd, float* running_mean, float* running_var,
                                int64_t* num_batches_tracked, void* stream) {
   SBR_REQUIRE(stats && mean_invstd && n_rows > 0 && C > 0, "sbr_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, S(stream)>>>(stats, n_rows, C, eps, momentum, mean_invstd, running_mean,
-                                                          running_var, num_batches_tracked);
+  SBR_CHECK_CUDA(sbr_launch(bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), (size_t)(0), S(stream), stats, n_rows, C, eps, momentum, mean_invstd, running_mean,
+                                                          running_var, num_batches_tracked));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -200,9 +205,9 @@ extern "C" int sbr_bn_apply(const float* z, int64_t ld_z, const float* mean_invs
                             const float* beta, int act, int64_t rows, int C, void* out_bf16, int64_t ld_bf16,
                             float* out_f32, int64_t ld_f32, void* stream) {
   SBR_REQUIRE(z && mean_invstd && gamma && beta && rows > 0 && C > 0, "sbr_bn_apply: bad arguments");
-  bn_apply_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(z, ld_z, mean_invstd, gamma, beta, act, rows, C,
+  SBR_CHECK_CUDA(sbr_launch(bn_apply_kernel, dim3(tile_grid(rows, C)), dim3(256), (size_t)(0), S(stream), z, ld_z, mean_invstd, gamma, beta, act, rows, C,
                                                              reinterpret_cast<bf16*>(out_bf16), ld_bf16, out_f32,
-                                                             ld_f32, rows_per_block(rows));
+                                                             ld_f32, rows_per_block(rows)));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -212,9 +217,9 @@ extern "C" int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_
                                  float* sums, void* stream) {
   SBR_REQUIRE(dy && z && mean_invstd && sums && rows > 0 && C > 0, "sbr_bn_bwd_reduce: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_reduce: activation gradient needs the output y");
-  bn_bwd_reduce_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(
+  SBR_CHECK_CUDA(sbr_launch(bn_bwd_reduce_kernel, dim3(tile_grid(rows, C)), dim3(256), (size_t)(0), S(stream), 
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, rows, C, sums,
-      rows_per_block(rows));
+      rows_per_block(rows)));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -226,9 +231,9 @@ extern "C" int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f
   SBR_REQUIRE(dy && z && mean_invstd && gamma && sums && rows > 0 && C > 0 && n_replicas >= 1,
               "sbr_bn_bwd_apply: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_apply: activation gradient needs the output y");
-  bn_bwd_apply_kernel<<<tile_grid(rows, C), 256, 0, S(stream)>>>(
+  SBR_CHECK_CUDA(sbr_launch(bn_bwd_apply_kernel, dim3(tile_grid(rows, C)), dim3(256), (size_t)(0), S(stream), 
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, gamma, sums, n_replicas,
-      rows, C, reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta, rows_per_block(rows));
+      rows, C, reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta, rows_per_block(rows)));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

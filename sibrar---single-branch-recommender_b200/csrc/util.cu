@@ -67,6 +67,7 @@ __global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr, const in
 // ------------------------------------------------------------------------------------------------ modality sampling
 __global__ void sample_modalities_kernel(uint8_t* __restrict__ mods, int64_t n_rows, int k, int n_mods, int central,
                                          uint64_t seed, const int64_t* __restrict__ step_dev) {
+  SBR_PDL_ENTRY();
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   uint64_t step = (uint64_t)*step_dev;
@@ -95,6 +96,8 @@ constexpr int ADAM_CHUNK = 4096;
 __global__ void adam_kernel(const sbr_adam_tensor_t* __restrict__ tensors, const int32_t* __restrict__ chunk_to_tensor,
                             const int64_t* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps,
                             float wd, int decoupled, const int64_t* __restrict__ step_dev, float grad_scale) {
+  SBR_PDL_ENTRY();
+  SBR_PDL_ENTRY();
   const sbr_adam_tensor_t t = tensors[chunk_to_tensor[blockIdx.x]];
   const int64_t off = chunk_offset[blockIdx.x];
   const double step = (double)*step_dev;
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, int64_t ld_part, int64_t rows,
                      int64_t cols, const float* __restrict__ bias, int act, float* __restrict__ out_f32,
                      int64_t ld_f32, int accumulate, bf16* __restrict__ out_bf16, int64_t ld_bf16) {
+  SBR_PDL_ENTRY();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t total = rows * cols;
@@ -208,9 +212,9 @@ extern "C" int sbr_splitk_reduce(const float* partials, int n_splits, int64_t sp
               "sbr_splitk_reduce: bad arguments");
   const int64_t total = rows * cols;
   const unsigned blocks = (unsigned)min((int64_t)sbr_num_sms() * 16, (total + 31) / 32);
-  splitk_reduce_kernel<<<blocks, 256, 0, S(stream)>>>(partials, n_splits, split_stride, ld_part, rows, cols, bias, act,
+  SBR_CHECK_CUDA(sbr_launch(splitk_reduce_kernel, dim3(blocks), dim3(256), (size_t)(0), S(stream), partials, n_splits, split_stride, ld_part, rows, cols, bias, act,
                                                       out_f32, ld_f32, accumulate,
-                                                      reinterpret_cast<bf16*>(out_bf16), ld_bf16);
+                                                      reinterpret_cast<bf16*>(out_bf16), ld_bf16));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -260,14 +264,14 @@ extern "C" int sbr_sample_modalities(uint8_t* mods, int64_t n_rows, int k, int n
   SBR_REQUIRE(n_mods >= k && n_mods <= 255, "sbr_sample_modalities: need k <= n_mods <= 255 (k=%d n_mods=%d)", k,
               n_mods);
   SBR_REQUIRE(central < n_mods, "sbr_sample_modalities: central modality out of range");
-  sample_modalities_kernel<<<cdiv(n_rows, 256), 256, 0, S(stream)>>>(mods, n_rows, k, n_mods, central, seed, step_dev);
+  SBR_CHECK_CUDA(sbr_launch(sample_modalities_kernel, dim3(cdiv(n_rows, 256)), dim3(256), (size_t)(0), S(stream), mods, n_rows, k, n_mods, central, seed, step_dev));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
 
 extern "C" int sbr_tick(int64_t* counter_dev, void* stream) {
   SBR_REQUIRE(counter_dev, "sbr_tick: null counter");
-  tick_kernel<<<1, 1, 0, S(stream)>>>(counter_dev);
+  SBR_CHECK_CUDA(sbr_launch(tick_kernel, dim3(1), dim3(1), (size_t)(0), S(stream), counter_dev));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -278,9 +282,9 @@ extern "C" int sbr_adam_step(const sbr_adam_tensor_t* tensors_dev, int n_tensors
                              float grad_scale, void* stream) {
   SBR_REQUIRE(tensors_dev && chunk_to_tensor_dev && chunk_offset_dev && step_dev && n_tensors > 0 && total_chunks > 0,
               "sbr_adam_step: bad arguments");
-  adam_kernel<<<(unsigned)total_chunks, 256, 0, S(stream)>>>(tensors_dev, chunk_to_tensor_dev, chunk_offset_dev, lr,
+  SBR_CHECK_CUDA(sbr_launch(adam_kernel, dim3((unsigned)total_chunks), dim3(256), (size_t)(0), S(stream), tensors_dev, chunk_to_tensor_dev, chunk_offset_dev, lr,
                                                              beta1, beta2, eps, weight_decay, decoupled, step_dev,
-                                                             grad_scale);
+                                                             grad_scale));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
