@@ -41,6 +41,9 @@ def ml1m_model_conf(D=64):
 
 
 LEARN = dict(lr=1e-3, wd=1e-6, optimizer="adamw", rec_loss="bpr", loss_aggregator="mean")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of this workload's kernels
+# (profiles/r01_segreduce_ncu_raw.txt); keyed like CallProfiler._key
+NCU_DRAM_TRAFFIC = {("sbr_row_gather_bwd_segmented", 180224, 64): 49.25e6}
 N_NEG = 10
 
 
@@ -462,7 +465,8 @@ def main():
                 ach, peak, unit, bound = flops / dur / 1e12, peaks["bf16_tflops"], "TFLOP/s", "tensor"
             else:
                 ach, peak, unit, bound = nbytes / dur / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
-            line["roofline"] = dict(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+            line["roofline"] = dict(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak,
+                                    traffic=NCU_DRAM_TRAFFIC.get(key),
                                     kernel=str(key), peak_source=which + (" burst" if bound == "tensor" else ""),
                                     share_of_step=ms / 3 / step_ms)
             break

@@ -134,7 +134,9 @@ typedef struct {
 int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
                        int64_t n_idx, int k, int C, int normalize, float p_drop, uint64_t seed,
                        const int64_t* step_dev, const uint8_t* keep_mask, void* out_bf16, int64_t ld_out,
-                       float* out_f32, int64_t ld_f32, int32_t* err_flag, void* stream);
+                       float* out_f32, int64_t ld_f32, int32_t* err_flag, uint8_t* keep_bits_out, void* stream);
+/* keep_bits_out (optional, uint8 [N, ceil(C / 8)]): the dropout keep decisions of this call, bit j of byte c / 8 =
+ * column c -- handed to sbr_row_gather_bwd_segmented so that the backward does not regenerate the mask. */
 /* backward of the above: dX (fp32 [N, C], pitch ld_dx) -> atomicAdd into the sources' grad buffers */
 int sbr_row_gather_bwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
                        int64_t n_idx, int k, int C, int normalize, float p_drop, uint64_t seed,
@@ -153,7 +155,7 @@ int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, int n_mods,
                                  const int32_t* offsets, const int32_t* perm, const int32_t* sorted_keys,
                                  int64_t n_rows, int C, int normalize, float p_drop, uint64_t seed,
                                  const int64_t* step_dev, const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
-                                 int rows_per_warp, void* stream);
+                                 int rows_per_warp, const uint8_t* keep_bits, void* stream);
 
 /* table-level backward of the projection output activation: dpre = dT * act'(T) -> bf16 (+ column sums = dbias).
  * zero_dy = 1 clears dy after reading it (the gradient table is an atomicAdd accumulator reused every step). */

@@ -185,7 +185,7 @@ row_gather_fwd_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
                         const uint8_t* __restrict__ mods, int64_t N, int k, int C, int normalize, float p_drop,
                         uint64_t seed, const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
                         bf16* __restrict__ out, int64_t ld_out, float* __restrict__ out_f32, int64_t ld_f32,
-                        int32_t* err_flag) {
+                        int32_t* err_flag, uint8_t* __restrict__ keep_bits_out) {
   SBR_PDL_ENTRY();
   const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   const int li = threadIdx.x % LPR;
@@ -215,6 +215,7 @@ row_gather_fwd_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
     const int c0 = 8 * li + 8 * LPR * i;
     if (c0 >= C) continue;
     const uint32_t km = keep8(keep_mask, r, C, c0, p_drop, seed, step);
+    if (keep_bits_out != nullptr) keep_bits_out[r * ((C + 7) >> 3) + (c0 >> 3)] = (uint8_t)km;  // for the backward
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = ((km >> j) & 1u) ? x[i * 8 + j] * sc : 0.f;
@@ -338,7 +339,7 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
                     const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm,
                     const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop, uint64_t seed,
                     const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
-                    const float* __restrict__ dx, int64_t ld_dx) {
+                    const float* __restrict__ dx, int64_t ld_dx, const uint8_t* __restrict__ keep_bits) {
   SBR_PDL_ENTRY();
   __shared__ SegShared sh;
   if (threadIdx.x == 0) {
@@ -417,7 +418,9 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
       for (int i = 0; i < NV; ++i) {
         const int c0 = 8 * li + 8 * LPR * i;
         if (c0 >= C) continue;
-        const uint32_t km = keep8(keep_mask, r, C, c0, p_drop, seed, step);
+        // the forward's keep bits (1 byte per lane and row) when it stored them, else the mask is regenerated
+        const uint32_t km = keep_bits != nullptr ? (uint32_t)__ldg(keep_bits + r * ((C + 7) >> 3) + (c0 >> 3))
+                                                 : keep8(keep_mask, r, C, c0, p_drop, seed, step);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[i * 8 + j] += ((km >> j) & 1u) ? v[i][j] * sc : 0.f;
       }
@@ -604,7 +607,8 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ row_keys, int64_t N
 extern "C" int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx,
                                   const uint8_t* mods, int64_t n_idx, int k, int C, int normalize, float p_drop,
                                   uint64_t seed, const int64_t* step_dev, const uint8_t* keep_mask, void* out_bf16,
-                                  int64_t ld_out, float* out_f32, int64_t ld_f32, int32_t* err_flag, void* stream) {
+                                  int64_t ld_out, float* out_f32, int64_t ld_f32, int32_t* err_flag,
+                                  uint8_t* keep_bits_out, void* stream) {
   SBR_REQUIRE(srcs_dev && idx && (out_bf16 || out_f32) && n_idx > 0 && k >= 1, "sbr_row_gather_fwd: bad arguments");
   SBR_REQUIRE(C > 0 && C <= 1024, "sbr_row_gather_fwd: C=%d not in [1, 1024]", C);
   SBR_REQUIRE((!out_bf16 || ld_out >= C) && (!out_f32 || ld_f32 >= C), "sbr_row_gather_fwd: output pitch < C");
@@ -614,7 +618,8 @@ extern "C" int sbr_row_gather_fwd(const sbr_modality_src_t* srcs_dev, int n_mods
     const int64_t threads = N * LPRv;
     SBR_CHECK_CUDA(sbr_launch(row_gather_fwd_g_kernel<LPRv, NVg>, dim3(cdiv(threads, 256)), dim3(256), 0, S(stream),
                               srcs_dev, n_mods, idx, mods, N, k, C, normalize, p_drop, seed, step_dev, keep_mask,
-                              reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_f32, err_flag));
+                              reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_f32, err_flag,
+                              p_drop > 0.f ? keep_bits_out : (uint8_t*)nullptr));
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;
@@ -660,7 +665,7 @@ extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, 
                                             const int32_t* offsets, const int32_t* perm, const int32_t* sorted_keys,
                                             int64_t n_rows, int C, int normalize, float p_drop, uint64_t seed,
                                             const int64_t* step_dev, const uint8_t* keep_mask, const float* dx,
-                                            int64_t ld_dx, int rows_per_warp, void* stream) {
+                                            int64_t ld_dx, int rows_per_warp, const uint8_t* keep_bits, void* stream) {
   SBR_REQUIRE(srcs_dev && offsets && perm && sorted_keys && dx && n_keys > 0 && n_rows > 0,
               "sbr_row_gather_bwd_segmented: bad arguments");
   SBR_REQUIRE(C > 0 && C <= 1024 && ld_dx >= C, "sbr_row_gather_bwd_segmented: C=%d not in [1, 1024] or ld_dx < C", C);
@@ -673,7 +678,7 @@ extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, 
     if (blocks > cap) blocks = cap;
     SBR_CHECK_CUDA(sbr_launch(seg_reduce_g_kernel<LPRv, NVg>, dim3((unsigned)blocks), dim3(256), 0, S(stream), srcs_dev,
                               n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed, step_dev,
-                              keep_mask, dx, ld_dx));
+                              keep_mask, dx, ld_dx, p_drop > 0.f ? keep_bits : (const uint8_t*)nullptr));
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;

@@ -148,11 +148,11 @@ def make_modality_srcs(entries, device) -> torch.Tensor:
 
 
 def row_gather_fwd(srcs, n_mods, idx, mods, k, C_, normalize, p_drop, seed, step_dev, keep_mask, out_bf16=None,
-                   out_f32=None, err_flag=None):
+                   out_f32=None, err_flag=None, keep_bits_out=None):
     call("sbr_row_gather_fwd", ptr(srcs), int(n_mods), ptr(idx), ptr(mods), idx.numel(), int(k), int(C_),
          int(bool(normalize)), float(p_drop or 0.0), int(seed), ptr(step_dev), ptr(keep_mask), ptr(out_bf16),
          out_bf16.stride(0) if out_bf16 is not None else 0, ptr(out_f32),
-         out_f32.stride(0) if out_f32 is not None else 0, ptr(err_flag), stream_ptr())
+         out_f32.stride(0) if out_f32 is not None else 0, ptr(err_flag), ptr(keep_bits_out), stream_ptr())
 
 
 def row_gather_bwd(srcs, n_mods, idx, mods, k, C_, normalize, p_drop, seed, step_dev, keep_mask, dx):
@@ -181,10 +181,10 @@ class GatherPlan:
              ptr(self.counts), ptr(self.offsets), ptr(self.cursor), ptr(self.row_keys), ptr(self.perm),
              ptr(self.sorted_keys), stream_ptr())
 
-    def backward(self, srcs, n_mods, C_, normalize, p_drop, seed, step_dev, keep_mask, dx):
+    def backward(self, srcs, n_mods, C_, normalize, p_drop, seed, step_dev, keep_mask, dx, keep_bits=None):
         call("sbr_row_gather_bwd_segmented", ptr(srcs), int(n_mods), self.n_keys, ptr(self.offsets), ptr(self.perm),
              ptr(self.sorted_keys), self.N, int(C_), int(bool(normalize)), float(p_drop or 0.0), int(seed),
-             ptr(step_dev), ptr(keep_mask), ptr(dx), dx.stride(0), self.rows_per_warp, stream_ptr())
+             ptr(step_dev), ptr(keep_mask), ptr(dx), dx.stride(0), self.rows_per_warp, ptr(keep_bits), stream_ptr())
 
 
 def _y_args(y):

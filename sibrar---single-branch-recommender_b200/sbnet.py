@@ -666,24 +666,25 @@ class SingleBranchNetEntity(_EntityBase):
         x0 = torch.empty((N, ops.pad8(C_)), dtype=BF16, device=dev)
         p_drop = cfg.single_branch_input_dropout if (training and cfg.single_branch_input_dropout) else 0.0
         seed = (int(cfg.sampling_seed) << 8) ^ (0x11 if self.entity_name == "user" else 0x22)
+        keep_bits = torch.empty((N, (C_ + 7) // 8), dtype=torch.uint8, device=dev) if (training and p_drop) else None
         ops.row_gather_fwd(srcs, len(self.mod_names), flat, mods, k, C_, cfg.normalize_single_branch_input, p_drop,
-                           seed, rt.step_dev, keep_mask, out_bf16=x0, err_flag=rt.err_flag)
+                           seed, rt.step_dev, keep_mask, out_bf16=x0, err_flag=rt.err_flag, keep_bits_out=keep_bits)
         E = self.sb_chain.forward(x0, N, training, rt.arena, keep_for_backward=training,
                                   defer_final_bn=defer_final_bn and k == 1)
-        self._ctx = (flat, mods, keep_mask, k, p_drop, seed)
+        self._ctx = (flat, mods, keep_mask, k, p_drop, seed, keep_bits)
         return E
 
     def backward(self, dE, grads, final_bn_sums=None):
         rt = self._rt()
         cfg = self.entity_config
-        flat, mods, keep_mask, k, p_drop, seed = self._ctx
+        flat, mods, keep_mask, k, p_drop, seed, keep_bits = self._ctx
         C_ = cfg.common_modality_dim
         dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena, final_bn_sums=final_bn_sums)
         srcs = self._src_blob(grads)
         plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
         plan.build(srcs, len(self.mod_names), flat, mods, k)
         plan.backward(srcs, len(self.mod_names), C_, cfg.normalize_single_branch_input, p_drop, seed, rt.step_dev,
-                      keep_mask, dx0)
+                      keep_mask, dx0, keep_bits=keep_bits)
         for name, chain in self.proj.items():
             # table-level backward; the accumulator table is cleared by the kernel that consumes it
             chain.backward(self.table_grads[name], grads, need_dx=False, arena=rt.arena, zero_dy=True)

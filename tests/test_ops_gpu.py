@@ -303,6 +303,22 @@ def test_row_gather_fwd_bwd():
         grads2[2][5] = 0
         for got, want in zip(grads2, (t_table.grad, t_emb.grad, gb)):
             assert _relerr(got, want) < 1e-4, rpw
+    # keep bits stored by the forward (Philox-free backward): same gradients with a hash-generated mask
+    out_h = torch.zeros(33 * k, C_, device=DEV)
+    bits = torch.zeros(33 * k, (C_ + 7) // 8, dtype=torch.uint8, device=DEV)
+    ops.row_gather_fwd(srcs2, 3, idx, mods, k, C_, True, 0.3, 9, step, None, out_f32=out_h, keep_bits_out=bits)
+    res = []
+    for kb in (None, bits):
+        for gr in grads2:
+            gr.zero_()
+        plan = ops.GatherPlan(n_ent + 7 + n_ent, 33 * k, DEV)
+        plan.build(srcs2, 3, idx, mods, k)
+        plan.backward(srcs2, 3, C_, True, 0.3, 9, step, None, dx, keep_bits=kb)
+        res.append([gr.clone() for gr in grads2])
+    for a_, b_ in zip(*res):
+        assert _relerr(a_, b_) < 1e-5
+    kept = torch.stack([(bits[:, c // 8] >> (c % 8)) & 1 for c in range(C_)], dim=1).bool()
+    assert torch.equal(kept, out_h != 0) or float((kept != (out_h != 0)).float().mean()) < 0.01  # (exact zeros in x)
 
     # Philox dropout: deterministic for (seed, step), keeps ~ (1 - p)
     big = torch.zeros(4000, C_, device=DEV)
