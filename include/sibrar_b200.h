@@ -58,6 +58,9 @@ typedef struct {
   int64_t ld_f32;
   float* colstats;        /* optional [2*N]: += column sum / sum of squares of the FINAL epilogue value, valid rows */
   int colstats_sum_only;  /* 1: only the N column sums are accumulated (e.g. a bias gradient)                     */
+  int colstats_rows;      /* > 0: deterministic mode -- colstats is [colstats_rows, 2*N]; every epilogue warp writes
+                             its own row of partial sums (rows = sbr_gemm_colstats_rows(M, N)), summed in a fixed order
+                             by sbr_bn_finalize; 0: fp32 atomics into colstats[2*N]                                */
   const void* actgrad_y;  /* optional bf16 [M, N]: result *= act'(y) expressed through the saved output y         */
   int64_t ld_actgrad;
   int actgrad_act;
@@ -70,6 +73,7 @@ typedef struct {
 
 int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,
                   int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream);
+int sbr_gemm_colstats_rows(int64_t M, int64_t N); /* partial-statistics rows a [M, N] GEMM writes (no split-K) */
 
 /* out[r, c] (+)= act(sum_s partials[s * split_stride + r * ld_part + c] + bias[c]) -- the deterministic second half of
  * a split-K GEMM (split_stride > 0 above).  accumulate = 1 adds into out_f32 (gradient buffers). */
@@ -163,12 +167,12 @@ int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, const void*
                        int64_t rows, int64_t cols, void* out_bf16, int64_t ld_out, float* out_f32, int64_t ld_out_f32,
                        float* colsum, int zero_dy, void* stream);
 
-/* ------------------------------------------------------------------------------------------------ BatchNorm1d
- * (torch.nn.BatchNorm1d used at modules/polylinear.py:58-61,68-69 and algorithms/sgd_alg.py:1834-1837)
- * stats: [2*C] column sum / sum of squares accumulated by the GEMM epilogue.  finalize -> mean_invstd [2*C],
- * updates running stats (momentum 0.1, unbiased var) and num_batches_tracked. */
-int sbr_bn_finalize(const float* stats, int64_t n_rows, int C, float eps, float momentum, float* mean_invstd,
-                    float* running_mean, float* running_var, int64_t* num_batches_tracked, void* stream);
+/* stats: [n_partials, 2*C] column sums / sums of squares written by the GEMM epilogue (n_partials = 1: accumulated
+ * with atomics).  finalize adds the partial rows in a fixed order -> mean_invstd [2*C], updates running stats
+ * (momentum 0.1, unbiased var) and num_batches_tracked. */
+int sbr_bn_finalize(const float* stats, int n_partials, int64_t n_rows, int C, float eps, float momentum,
+                    float* mean_invstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                    void* stream);
 /* y = act(gamma * (z - mean) * invstd + beta); z fp32 [rows, C]; writes bf16 and/or fp32.
  * eval mode: pass running stats through sbr_bn_eval_coeffs first. */
 int sbr_bn_apply(const float* z, int64_t ld_z, const float* mean_invstd, const float* gamma, const float* beta,

@@ -22,7 +22,7 @@ c_i64, c_i32, c_f32, c_vp, c_u64 = C.c_int64, C.c_int32, C.c_float, C.c_void_p, 
 
 class GemmEpilogue(C.Structure):
     _fields_ = [("bias", c_vp), ("act", C.c_int), ("out_bf16", c_vp), ("ld_bf16", c_i64), ("out_f32", c_vp),
-                ("ld_f32", c_i64), ("colstats", c_vp), ("colstats_sum_only", C.c_int), ("actgrad_y", c_vp), ("ld_actgrad", c_i64),
+                ("ld_f32", c_i64), ("colstats", c_vp), ("colstats_sum_only", C.c_int), ("colstats_rows", C.c_int), ("actgrad_y", c_vp), ("ld_actgrad", c_i64),
                 ("actgrad_act", C.c_int), ("transpose_out", C.c_int), ("atomic_out", C.c_int), ("split_k", C.c_int),
                 ("split_stride", c_i64), ("alpha", c_f32)]
 
@@ -62,7 +62,8 @@ _PROTOS = {
                                      c_vp, c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp],
     "sbr_actgrad_colsum": [c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp,
                            C.c_int, c_vp],
-    "sbr_bn_finalize": [c_vp, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "sbr_bn_finalize": [c_vp, C.c_int, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "sbr_gemm_colstats_rows": [c_i64, c_i64],
     "sbr_bn_apply": [c_vp, c_i64, c_vp, c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, c_vp],
     "sbr_bn_eval_coeffs": [c_vp, c_vp, C.c_int, c_f32, c_vp, c_vp],
     "sbr_bn_bwd_reduce": [c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, C.c_int, c_vp, c_vp],

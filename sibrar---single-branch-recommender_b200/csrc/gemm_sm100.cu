@@ -394,8 +394,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = 0; i < BN / 32; ++i) {
         const int64_t col = (int64_t)n0 + 32 * i + lane;
         if (col < p.N) {
-          atomicAdd(ep.colstats + col, cs_acc[i]);
-          if (!ep.colstats_sum_only) atomicAdd(ep.colstats + p.N + col, cq_acc[i]);
+          if (ep.colstats_rows > 0) {
+            // deterministic statistics: this warp's private row of partial sums, added up in a fixed order by
+            // sbr_bn_finalize (fp32 atomics would make the batch statistics -- and through bf16 roundings the whole
+            // forward -- depend on the arrival order)
+            float* rowp = ep.colstats + (size_t)(blockIdx.x * 4 + q) * 2 * p.N;
+            rowp[col] = cs_acc[i];
+            if (!ep.colstats_sum_only) rowp[p.N + col] = cq_acc[i];
+          } else {
+            atomicAdd(ep.colstats + col, cs_acc[i]);
+            if (!ep.colstats_sum_only) atomicAdd(ep.colstats + p.N + col, cq_acc[i]);
+          }
         }
       }
     }
@@ -409,6 +418,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+inline int64_t gemm_grid_x(int64_t M, int64_t N, int splits) {
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int64_t ctas_per_sm = BN == 256 ? 1 : 2;  // 2 x BN TMEM columns and the operand ring per CTA
+  int64_t gx = (sbr_num_sms() * ctas_per_sm) / (n_tiles * splits);
+  return gx < 1 ? 1 : (gx > m_tiles ? m_tiles : gx);
+}
+
 template <int BN, bool A_BITS>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits, cudaStream_t st) {
   static bool configured = false;
@@ -417,10 +434,10 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
                                         Cfg<BN>::SMEM_BYTES));
     configured = true;
   }
-  const int64_t m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-  const int64_t ctas_per_sm = BN == 256 ? 1 : 2;  // 2 x BN TMEM columns and the operand ring per CTA
-  int64_t gx = (sbr_num_sms() * ctas_per_sm) / (n_tiles * splits);
-  gx = gx < 1 ? 1 : (gx > m_tiles ? m_tiles : gx);
+  const int64_t n_tiles = (p.N + BN - 1) / BN;
+  const int64_t gx = gemm_grid_x(p.M, p.N, splits);
+  SBR_REQUIRE(p.ep.colstats == nullptr || p.ep.colstats_rows == 0 || p.ep.colstats_rows >= 4 * gx,
+              "sbr_gemm: colstats_rows=%d < %lld partial rows", p.ep.colstats_rows, (long long)(4 * gx));
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);
   SBR_CHECK_CUDA(sbr_launch(gemm_bf16_kernel<BN, A_BITS>, grid, dim3(A_BITS ? 320 : 192), (size_t)Cfg<BN>::SMEM_BYTES, st,
                             tmA, tmB, p));
@@ -508,6 +525,8 @@ extern "C" int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
     default: return launch_gemm<256, false>(tmA, tmB, p, splits, st);
   }
 }
+
+extern "C" int sbr_gemm_colstats_rows(int64_t M, int64_t N) { return (int)(4 * gemm_grid_x(M, N, 1)); }
 
 extern "C" int sbr_gemm_bits_bf16(const uint32_t* A_bits, int64_t ld_words, const void* B, int64_t ldb, int b_mn_major,
                                   int64_t M, int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream) {

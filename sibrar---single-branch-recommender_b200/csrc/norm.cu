@@ -62,16 +62,45 @@ __global__ void actgrad_colsum_kernel(float* __restrict__ dy, int64_t ld_dy, con
   if (colsum) block_col_flush(part, colsum, c, C);
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int64_t n_rows, int C, float eps, float momentum,
-                                   float* __restrict__ mean_invstd, float* running_mean, float* running_var,
-                                   int64_t* num_batches_tracked) {
+// block = 32 columns x 32 partial-row lanes; partial rows are added in a fixed order (deterministic statistics):
+// lane ty sums rows ty, ty + 32, ... with four independent accumulators, then the 32 lane sums are added in order
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float* __restrict__ stats, int n_partials, int64_t n_rows, int C, float eps, float momentum,
+                   float* __restrict__ mean_invstd, float* running_mean, float* running_var,
+                   int64_t* num_batches_tracked) {
   SBR_PDL_ENTRY();
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= C) return;
+  __shared__ float red[2][32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    int r = ty;
+    for (; r + 96 < n_partials; r += 128) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[q] += stats[(size_t)(r + 32 * q) * 2 * C + c];
+        b[q] += stats[(size_t)(r + 32 * q) * 2 * C + C + c];
+      }
+    }
+    for (int q = 0; r < n_partials; r += 32, ++q) {
+      a[q] += stats[(size_t)r * 2 * C + c];
+      b[q] += stats[(size_t)r * 2 * C + C + c];
+    }
+  }
+  red[0][ty][tx] = (a[0] + a[1]) + (a[2] + a[3]);
+  red[1][ty][tx] = (b[0] + b[1]) + (b[2] + b[3]);
+  __syncthreads();
+  if (ty != 0 || c >= C) return;
+  double s1 = 0., s2 = 0.;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    s1 += (double)red[0][q][tx];
+    s2 += (double)red[1][q][tx];
+  }
   double n = (double)n_rows;
-  double mean = (double)stats[c] / n;
-  double var = (double)stats[C + c] / n - mean * mean;
+  double mean = s1 / n;
+  double var = s2 / n - mean * mean;
   if (var < 0.) var = 0.;
   mean_invstd[c] = (float)mean;
   mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -183,13 +212,12 @@ extern "C" int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, 
   return SBR_OK;
 }
 
-extern "C" int sbr_bn_finalize(const float* stats, int64_t n_rows, int C, float eps, float momentum,
+extern "C" int sbr_bn_finalize(const float* stats, int n_partials, int64_t n_rows, int C, float eps, float momentum,
                                float* mean_invstd, float* running_mean, float* running_var,
                                int64_t* num_batches_tracked, void* stream) {
-  SBR_REQUIRE(stats && mean_invstd && n_rows > 0 && C > 0, "sbr_bn_finalize: bad arguments");
-  SBR_CHECK_CUDA(sbr_launch(bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), (size_t)(0), S(stream), stats, n_rows, C, eps, momentum, mean_invstd, running_mean,
-                                                          running_var, num_batches_tracked));
-  SBR_LAUNCH_CHECK();
+  SBR_REQUIRE(stats && mean_invstd && n_rows > 0 && C > 0 && n_partials >= 1, "sbr_bn_finalize: bad arguments");
+  SBR_CHECK_CUDA(sbr_launch(bn_finalize_kernel, dim3(cdiv(C, 32)), dim3(1024), (size_t)0, S(stream), stats, n_partials,
+                            n_rows, C, eps, momentum, mean_invstd, running_mean, running_var, num_batches_tracked));
   return SBR_OK;
 }
 

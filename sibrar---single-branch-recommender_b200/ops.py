@@ -20,7 +20,7 @@ def _act(a):
 
 
 def _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad_y, actgrad_act, transpose_out,
-              atomic_out, split_k, alpha, split_stride=0):
+              atomic_out, split_k, alpha, split_stride=0, colstats_rows=0):
     ep = GemmEpilogue()
     ep.bias = ptr(bias)
     ep.act = _act(act)
@@ -30,6 +30,7 @@ def _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad
     ep.ld_f32 = out_f32.stride(0) if out_f32 is not None else 0
     ep.colstats = ptr(colstats)
     ep.colstats_sum_only = int(colstats_sum_only)
+    ep.colstats_rows = int(colstats_rows)
     ep.actgrad_y = ptr(actgrad_y)
     ep.ld_actgrad = actgrad_y.stride(0) if actgrad_y is not None else 0
     ep.actgrad_act = _act(actgrad_act)
@@ -43,24 +44,31 @@ def _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad
 
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, act=None, out_bf16=None,
          out_f32=None, colstats=None, colstats_sum_only=False, actgrad_y=None, actgrad_act=None, transpose_out=False, atomic_out=False,
-         split_k=1, alpha=1.0, split_stride=0):
+         split_k=1, alpha=1.0, split_stride=0, colstats_rows=0):
     """D[M,N] = alpha * A @ B^T (bf16 in, fp32 accumulate) + fused epilogue.  A/B: 2-D bf16 tensors whose last
     dimension is contiguous; K-major means [rows, K], MN-major means [K, rows]."""
     assert A.dtype == BF16 and B.dtype == BF16 and A.stride(-1) == 1 and B.stride(-1) == 1
     ep = _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, actgrad_y, actgrad_act, transpose_out,
-                   atomic_out, split_k, alpha, split_stride)
+                   atomic_out, split_k, alpha, split_stride, colstats_rows)
     call("sbr_gemm_bf16", ptr(A), lda if lda is not None else A.stride(0), int(a_mn), ptr(B),
          ldb if ldb is not None else B.stride(0), int(b_mn), int(M), int(N), int(K), C.byref(ep), stream_ptr())
 
 
 def gemm_bits(A_bits, B, M, N, K, *, b_mn=False, bias=None, act=None, out_bf16=None, out_f32=None, colstats=None,
-              colstats_sum_only=False, transpose_out=False, atomic_out=False, split_k=1, alpha=1.0, split_stride=0):
+              colstats_sum_only=False, transpose_out=False, atomic_out=False, split_k=1, alpha=1.0, split_stride=0,
+              colstats_rows=0):
     """the same with a bit-packed 0/1 A operand: int32 [M, ld_words], bit k of row m = word k // 32, bit k % 32"""
     assert A_bits.dtype == torch.int32 and A_bits.stride(-1) == 1 and B.dtype == BF16 and B.stride(-1) == 1
     ep = _epilogue(bias, act, out_bf16, out_f32, colstats, colstats_sum_only, None, None, transpose_out, atomic_out,
-                   split_k, alpha, split_stride)
+                   split_k, alpha, split_stride, colstats_rows)
     call("sbr_gemm_bits_bf16", ptr(A_bits), A_bits.stride(0), ptr(B), B.stride(0), int(b_mn), int(M), int(N), int(K),
          C.byref(ep), stream_ptr())
+
+
+def gemm_colstats_rows(M: int, N: int) -> int:
+    """rows of partial column statistics a [M, N] GEMM writes in deterministic mode (4 epilogue warps x CTAs)"""
+    from ._lib import lib
+    return int(lib().sbr_gemm_colstats_rows(int(M), int(N)))
 
 
 def splitk_reduce(partials, n_splits, rows, cols, bias=None, act=None, out_f32=None, out_bf16=None, accumulate=False):
@@ -200,8 +208,9 @@ def actgrad_colsum(dy, y, act, rows, cols, out_bf16=None, out_f32=None, colsum=N
          out_f32.stride(0) if out_f32 is not None else 0, ptr(colsum), int(zero_dy), stream_ptr())
 
 
-def bn_finalize(stats, n_rows, C_, mean_invstd, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):
-    call("sbr_bn_finalize", ptr(stats), int(n_rows), int(C_), float(eps), float(momentum), ptr(mean_invstd),
+def bn_finalize(stats, n_rows, C_, mean_invstd, running_mean, running_var, nbt, eps=1e-5, momentum=0.1, n_partials=1):
+    call("sbr_bn_finalize", ptr(stats), int(n_partials), int(n_rows), int(C_), float(eps), float(momentum),
+         ptr(mean_invstd),
          ptr(running_mean), ptr(running_var), ptr(nbt), stream_ptr())
 
 

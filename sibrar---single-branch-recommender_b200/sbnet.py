@@ -225,18 +225,20 @@ class Chain:
                 bn = st.bn
                 a32 = torch.empty((rows, st.out_f), dtype=F32, device=dev)
                 mi = torch.empty(2 * st.out_f, dtype=F32, device=dev)
-                stats = arena.take(2 * st.out_f) if training else None
+                # deterministic batch statistics: one row of partial sums per epilogue warp, added in a fixed order
+                n_part = ops.gemm_colstats_rows(rows, st.out_f) if training else 0
+                stats = torch.empty((n_part, 2 * st.out_f), dtype=F32, device=dev) if training else None
                 if first_csr:
                     raise NotImplementedError("BatchNorm directly on a sparse feature projection")
                 if si == 0 and self.bits_input:
                     ops.gemm_bits(self.feature.bits, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1,
-                                  out_f32=a32, colstats=stats)
+                                  out_f32=a32, colstats=stats, colstats_rows=n_part)
                 else:
                     ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_f32=a32,
-                             colstats=stats)
+                             colstats=stats, colstats_rows=n_part)
                 if training:
                     ops.bn_finalize(stats, rows, st.out_f, mi, bn.running_mean, bn.running_var,
-                                    bn.num_batches_tracked, eps=bn.eps, momentum=bn.momentum)
+                                    bn.num_batches_tracked, eps=bn.eps, momentum=bn.momentum, n_partials=n_part)
                 else:
                     ops.bn_eval_coeffs(bn.running_mean, bn.running_var, st.out_f, mi, eps=bn.eps)
                 if final and defer_final_bn and training and st.act2 is None:

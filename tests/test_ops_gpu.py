@@ -330,6 +330,26 @@ def test_row_gather_fwd_bwd():
     assert abs((big != 0).float().mean().item() - 0.75) < 0.01
 
 
+def test_gemm_partial_colstats_are_deterministic():
+    """BatchNorm statistics from the GEMM epilogue: per-warp partial rows + ordered finalize give bit-identical
+    mean / invstd on every run (the atomic variant depends on the arrival order) and agree with torch"""
+    M, N, K = 50000, 64, 64
+    x, w = _rand_bf16(M, K, seed=1), _rand_bf16(N, K, seed=2, scale=0.2)
+    rows = ops.gemm_colstats_rows(M, N)
+    outs = []
+    for _ in range(3):
+        a32 = torch.empty(M, N, device=DEV)
+        part = torch.full((rows, 2 * N), float("nan"), device=DEV)
+        ops.gemm(x, w, M, N, K, out_f32=a32, colstats=part, colstats_rows=rows)
+        mi = torch.empty(2 * N, device=DEV)
+        ops.bn_finalize(part, M, N, mi, None, None, None, n_partials=rows)
+        outs.append(mi.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = x.float() @ w.float().T
+    assert _relerr(outs[0][:N], ref.mean(0)) < 1e-4
+    assert _relerr(outs[0][N:], 1.0 / torch.sqrt(ref.var(0, unbiased=False) + 1e-5)) < 1e-4
+
+
 @pytest.mark.parametrize("act", [None, "relu"])
 def test_batchnorm_fwd_bwd(act):
     rows, C_ = 1000, 40
