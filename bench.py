@@ -516,6 +516,20 @@ def bench_eval(torch, ops, model, corpus, FullEvaluator, dev):
                                      unit="users/s", users=int(val.n_users_in_split), items=int(val.n_items_in_split),
                                      ms=ms, includes="item+user representations, scores, mask, top-20, metrics",
                                      ndcg10=res.get("ndcg@10"))
+    evg = FullEvaluator(dict(top_k=[1, 10, 20], metrics=["ndcg", "recall", "precision", "coverage"],
+                             calculate_std=False), cuda_graph=True)
+    for _ in range(3):  # eager, capture, first replay
+        resg = evg.evaluate(model, val)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        resg = evg.evaluate(model, val)
+    b.record()
+    torch.cuda.synchronize()
+    msg = a.elapsed_time(b) / reps
+    out["workload_val_split_graph"] = dict(metric="eval_users_per_sec", value=val.n_users_in_split / (msg * 1e-3),
+                                           unit="users/s", ms=msg, same_result=bool(resg == res),
+                                           includes="the same evaluation replayed as one CUDA graph + one D2H copy")
     g = torch.Generator(device="cpu").manual_seed(7)
     sweep = []
     for U, I, D, k in ((100_000, 100_000, 64, 10), (100_000, 1_000_000, 64, 10), (100_000, 1_000_000, 128, 50)):

@@ -46,7 +46,7 @@ def _user_labels(feat, users) -> np.ndarray:
 
 
 class FullEvaluator:
-    def __init__(self, config, evaluator_name: Optional[str] = None, dataset=None):
+    def __init__(self, config, evaluator_name: Optional[str] = None, dataset=None, cuda_graph: bool = False):
         if isinstance(config, dict):
             config = EvalConfig.from_dict(config)
         invalid = set(config.metrics) - set(SUPPORTED)
@@ -54,6 +54,10 @@ class FullEvaluator:
             raise ValueError(f"Metric(s) {invalid} are not supported. Select metrics from {SUPPORTED}.")
         self.config, self.name, self.dataset = config, evaluator_name, dataset
         self._dev_cache = None
+        # cuda_graph: the whole evaluation (representations, scores + mask + top-k, metrics, their reductions) of one
+        # (model, split) is captured on its second call and replayed afterwards; one D2H copy per evaluation
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
 
     def _device_split(self, dataset, device):
         if self._dev_cache is not None and self._dev_cache[0] is dataset and self._dev_cache[1] == device:
@@ -74,18 +78,77 @@ class FullEvaluator:
         dataset = dataset or self.dataset
         dev = model.device
         d = self._device_split(dataset, dev)
-        was_training = model.training
-        model.eval()
-        i_repr = model.get_item_representations(d["items"])
-        u_repr = model.get_user_representations(d["users"])
-        if was_training:
-            model.train()
-        res = self.evaluate_representations(u_repr, i_repr, d["seen"], d["tgt"], len(dataset.items_in_split),
-                                            return_topk=True)
-        out, topk = res
-        out.update(self.group_metrics(dataset, sorted(set(int(k) for k in self.config.top_k))))
+        n_items = len(dataset.items_in_split)
+        ks = sorted(set(int(k) for k in self.config.top_k))
+        st = self._graphs.setdefault((id(model), id(dataset)), {"calls": 0}) if self.cuda_graph else None
+
+        def device_part():
+            was_training = model.training
+            model.eval()
+            i_repr = model.get_item_representations(d["items"])
+            u_repr = model.get_user_representations(d["users"])
+            if was_training:
+                model.train()
+            return self._device_eval(u_repr, i_repr, d["seen"], d["tgt"], ks, n_items)
+
+        if st is None or st["calls"] < 1:
+            packed, topk = device_part()
+            if st is not None:
+                st["calls"] += 1
+        else:
+            model.refresh_shadows()
+            if "graph" not in st:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["out"] = device_part()
+                st["graph"] = g
+            st["graph"].replay()
+            packed, topk = st["out"]
+        out = self._host_results(packed, ks, n_items)
+        out.update(self.group_metrics(dataset, ks))
         out = {k: out[k] for k in sorted(out, key=_natural_key)}
         return (out, topk) if return_topk else out
+
+    def _device_eval(self, u_repr, i_repr, seen, tgt, ks, n_items, item_offset=0):
+        """everything that runs on the device: returns (packed [mean | std | coverage counts] tensor, (vals, idx))"""
+        U, D = u_repr.shape
+        I = i_repr.shape[0]
+        kmax = min(max(ks), I)
+        u16 = ops.cast_bf16(u_repr.contiguous())
+        i16 = ops.cast_bf16(i_repr.contiguous())
+        vals, idx = ops.topk_scores_masked(u16, i16, U, I, u16.shape[1], seen[0], seen[1], kmax,
+                                           item_offset=item_offset)
+        return self._device_metrics(idx, tgt, ks, n_items), (vals, idx)
+
+    def _device_metrics(self, idx, tgt, ks, n_items):
+        kmax = idx.shape[1]
+        ks_eff = [k for k in ks if k <= kmax]
+        want_cov = "coverage" in self.config.metrics
+        m, hits = ops.metrics_at_k(idx, tgt[0], tgt[1], ks_eff, n_items, want_item_hits=want_cov)
+        parts = [m.mean(dim=2).reshape(-1), m.std(dim=2, unbiased=False).reshape(-1)]
+        parts.append(hits.sum(dim=1).to(torch.float32) if want_cov else torch.zeros(len(ks_eff), device=m.device))
+        self.raw, self._kmax = m, kmax
+        return torch.cat(parts)
+
+    def _host_results(self, packed, ks, n_items) -> Dict[str, float]:
+        ks_eff = [k for k in ks if k <= self._kmax]
+        nk = len(ks_eff)
+        host = packed.cpu().numpy()  # the one device -> host copy of an evaluation
+        mean, std, cov = host[:7 * nk].reshape(7, nk), host[7 * nk:14 * nk].reshape(7, nk), host[14 * nk:]
+        pre = f"{self.name}/" if self.name else ""
+        res = {}
+        for mi, name in enumerate(USER_METRICS):
+            if name not in self.config.metrics:
+                continue
+            for ki, k in enumerate(ks_eff):
+                res[f"{pre}{name}@{k}"] = float(mean[mi, ki])
+                if self.config.calculate_std:
+                    res[f"{pre}{name}@{k}_std"] = float(std[mi, ki])
+        if "coverage" in self.config.metrics:
+            for ki, k in enumerate(ks_eff):
+                res[f"{pre}coverage@{k}"] = float(cov[ki]) / float(n_items)
+        return {k: res[k] for k in sorted(res, key=_natural_key)}
 
     def group_metrics(self, dataset, ks) -> Dict[str, float]:
         """per-group means (+ std) of the user metrics for every categorical user feature in
@@ -117,41 +180,13 @@ class FullEvaluator:
 
     @torch.no_grad()
     def evaluate_representations(self, u_repr, i_repr, seen, tgt, n_items, return_topk=False, item_offset=0):
-        U, D = u_repr.shape
-        I = i_repr.shape[0]
         ks = sorted(set(int(k) for k in self.config.top_k))
-        kmax = min(max(ks), I)
-        u16 = ops.cast_bf16(u_repr.contiguous())
-        i16 = ops.cast_bf16(i_repr.contiguous())
-        vals, idx = ops.topk_scores_masked(u16, i16, U, I, u16.shape[1], seen[0], seen[1], kmax,
-                                           item_offset=item_offset)
-        out = self.metrics_from_topk(idx, tgt, ks, n_items)
-        if return_topk:
-            return out, (vals, idx)
-        return out
+        packed, topk = self._device_eval(u_repr, i_repr, seen, tgt, ks, n_items, item_offset=item_offset)
+        out = self._host_results(packed, ks, n_items)
+        return (out, topk) if return_topk else out
 
     def metrics_from_topk(self, idx, tgt, ks, n_items) -> Dict[str, float]:
-        kmax = idx.shape[1]
-        ks_eff = [k for k in ks if k <= kmax]
-        want_cov = "coverage" in self.config.metrics
-        m, hits = ops.metrics_at_k(idx, tgt[0], tgt[1], ks_eff, n_items, want_item_hits=want_cov)
-        mean = m.mean(dim=2).cpu().numpy()
-        std = m.std(dim=2, unbiased=False).cpu().numpy() if self.config.calculate_std else None
-        pre = f"{self.name}/" if self.name else ""
-        res = {}
-        for mi, name in enumerate(USER_METRICS):
-            if name not in self.config.metrics:
-                continue
-            for ki, k in enumerate(ks_eff):
-                res[f"{pre}{name}@{k}"] = float(mean[mi, ki])
-                if std is not None:
-                    res[f"{pre}{name}@{k}_std"] = float(std[mi, ki])
-        if want_cov:
-            cov = hits.sum(dim=1).cpu().numpy() / float(n_items)
-            for ki, k in enumerate(ks_eff):
-                res[f"{pre}coverage@{k}"] = float(cov[ki])
-        self.raw, self._kmax = m, kmax
-        return {k: res[k] for k in sorted(res, key=_natural_key)}
+        return self._host_results(self._device_metrics(idx, tgt, ks, n_items), ks, n_items)
 
 
 def evaluate_recommender_algorithm(alg, eval_loader_or_dataset, evaluator: FullEvaluator, device="cuda",

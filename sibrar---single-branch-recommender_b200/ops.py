@@ -355,10 +355,16 @@ def topk_merge(keys, L, U, k, return_keys=False):
     return vals, idx
 
 
+_KS_CACHE = {}
+
+
 def metrics_at_k(topk_idx, tgt_indptr, tgt_indices, ks, n_items, want_item_hits=False):
     U, k = topk_idx.shape
     dev = topk_idx.device
-    ks_dev = torch.tensor(sorted(ks), dtype=torch.int32, device=dev)
+    key = (tuple(sorted(ks)), str(dev))
+    ks_dev = _KS_CACHE.get(key)
+    if ks_dev is None:  # (cached: a host list -> device copy is a synchronising H2D, not capturable in a CUDA graph)
+        ks_dev = _KS_CACHE[key] = torch.tensor(sorted(ks), dtype=torch.int32, device=dev)
     out = torch.zeros((7, len(ks), U), dtype=F32, device=dev)
     hits = torch.zeros((len(ks), n_items), dtype=torch.int32, device=dev) if want_item_hits else None
     call("sbr_metrics_at_k", ptr(topk_idx), int(U), int(k), ptr(tgt_indptr), ptr(tgt_indices), ptr(ks_dev), len(ks),

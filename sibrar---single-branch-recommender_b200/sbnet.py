@@ -762,6 +762,16 @@ class SingleBranchNet(nn.Module):
             self._runtime = _Runtime(dev)
         return self._runtime
 
+    def refresh_shadows(self):
+        """bring the bf16 weight shadows up to date with the fp32 masters (host-side version check, cast kernels only
+        for weights that changed); CUDA-graph replays of the evaluation call this first"""
+        for ent in (self.user_embedding_module, self.item_embedding_module):
+            if isinstance(ent, SingleBranchNetEntity):
+                ent._materialize()
+                for chain in list(ent.proj.values()) + [ent.sb_chain]:
+                    for st in chain.stages:
+                        st.refresh(False)
+
     def check_errors(self):
         """raises KeyError like ``Feature.__getitem__`` (data/Feature.py:146) if a kernel met an entity index
         without a feature row (host sync: call outside the hot loop)"""

@@ -247,6 +247,33 @@ def test_eval_matches_reference(name):
         assert res[k] == pytest.approx(float(v), abs=tol), k
 
 
+@pytest.mark.parametrize("name", list(CASES)[:2])
+def test_graph_evaluator_equals_eager_across_weight_updates(name):
+    """FullEvaluator(cuda_graph=True): call 1 eager, call 2 captures, later calls replay -- every call must return
+    exactly what the eager evaluator returns for the CURRENT weights (train steps in between)"""
+    spec, g, corpus, model = _build(name)
+    _load(model, state_dict_of(g, "s0/sd/"))
+    model.to(DEV).train()
+    tr = _trainer(model, spec)
+    val = corpus.dataset("val")
+    conf = dict(top_k=[1, 3, 5], metrics=["ndcg", "precision", "recall", "hitrate", "ap", "rr", "coverage"],
+                calculate_std=True)
+    eager, graphed = FullEvaluator(conf), FullEvaluator(conf, cuda_graph=True)
+    seen = []
+    for it in range(5):
+        want = eager.evaluate(model, val)
+        got = graphed.evaluate(model, val)
+        assert model.training is True
+        assert got.keys() == want.keys()
+        for k in want:
+            assert got[k] == want[k], (it, k)
+        seen.append(want["ndcg@5"])
+        u, i, dmods, dkeep = _translate(model, g, it % spec["steps"])
+        tr.step(u, i)
+    torch.cuda.synchronize()
+    assert len(set(seen)) > 1  # the weights (and the metrics) did move between evaluations
+
+
 def test_group_metrics_keys_and_values():
     """eval.calculate_group_metrics / user_group_features (eval/eval.py:106-119): per-group means of the per-user
     metric vectors, keys '{feature}_{label}/{metric}@{k}'"""
