@@ -676,6 +676,16 @@ class SingleBranchNetEntity(_EntityBase):
         self._ctx = (flat, mods, keep_mask, k, p_drop, seed, keep_bits)
         return E
 
+    def build_plan(self, idx, mods, k, grads):
+        """sorted-run plan of the gather backward; depends only on (indices, sampled modalities), so the trainer
+        builds it on its side stream while the forward GEMMs run"""
+        flat = idx.reshape(-1)
+        srcs = self._src_blob(grads)
+        plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
+        plan.build(srcs, len(self.mod_names), flat, mods, k)
+        self._plan_built = True
+        return plan
+
     def backward(self, dE, grads, final_bn_sums=None):
         rt = self._rt()
         cfg = self.entity_config
@@ -683,8 +693,11 @@ class SingleBranchNetEntity(_EntityBase):
         C_ = cfg.common_modality_dim
         dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena, final_bn_sums=final_bn_sums)
         srcs = self._src_blob(grads)
-        plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
-        plan.build(srcs, len(self.mod_names), flat, mods, k)
+        if getattr(self, "_plan_built", False):
+            plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
+        else:
+            plan = self.build_plan(flat, mods, k, grads)
+        self._plan_built = False
         plan.backward(srcs, len(self.mod_names), C_, cfg.normalize_single_branch_input, p_drop, seed, rt.step_dev,
                       keep_mask, dx0, keep_bits=keep_bits)
         for name, chain in self.proj.items():

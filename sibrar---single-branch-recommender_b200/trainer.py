@@ -8,6 +8,7 @@ Losses are accumulated on the device (fp64) and read on demand; the optimizer is
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -81,6 +82,9 @@ class FusedTrainer:
         # step is captured once and replayed; the step counter, the Philox streams and the loss sums live on the device.
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
+        # user side / item side of the step on two streams (SBR_BRANCHES=0: one stream)
+        self.branches = os.environ.get("SBR_BRANCHES", "1") != "0"
+        self._side = None
 
     # ------------------------------------------------------------------------------------------------ one step
     def step(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor, mods: Optional[dict] = None,
@@ -126,8 +130,30 @@ class FusedTrainer:
         # entities that end in a BatchNorm leave it to the score/loss kernel (no normalised copy, no separate
         # BatchNorm-backward reduction) when there is one modality slot per entity and D fits the fused kernel
         fuse = ku == 1 and ki == 1 and D in (16, 32, 64, 128) and not self.user.reg_enabled and not self.item.reg_enabled
-        Eu = self.user.embed(u_idxs, True, mods.get("user"), keep_masks.get("user"), defer_final_bn=fuse)
-        Ei = self.item.embed(i_idxs, True, mods.get("item"), keep_masks.get("item"), defer_final_bn=fuse)
+        # The user and the item side of a step only meet in the score/loss kernel and in Adam.  Their kernels are small
+        # (tens of CTAs for the table projections, one CTA for the BatchNorm finalisers), so the user side runs on a
+        # side stream -- a parallel branch of the captured graph -- next to the (longer) item side.
+        side = self._side_stream(u_idxs.device) if (self.branches and u_idxs.is_cuda) else None
+        main = torch.cuda.current_stream() if side is not None else None
+        sb_u, sb_i = isinstance(self.user, SingleBranchNetEntity), isinstance(self.item, SingleBranchNetEntity)
+        if side is not None:
+            imods = mods.get("item")
+            if imods is None and sb_i:
+                imods = self.item.sample_modalities(i_idxs.numel())
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                Eu = self.user.embed(u_idxs, True, mods.get("user"), keep_masks.get("user"), defer_final_bn=fuse)
+                if sb_u:
+                    self.user.build_plan(u_idxs, self.user._ctx[1], ku, self.grads)
+                if sb_i:
+                    self.item._materialize()
+                    self.item.build_plan(i_idxs, imods, ki, self.grads)
+                fwd_done = side.record_event()
+            Ei = self.item.embed(i_idxs, True, imods, keep_masks.get("item"), defer_final_bn=fuse)
+            main.wait_event(fwd_done)
+        else:
+            Eu = self.user.embed(u_idxs, True, mods.get("user"), keep_masks.get("user"), defer_final_bn=fuse)
+            Ei = self.item.embed(i_idxs, True, mods.get("item"), keep_masks.get("item"), defer_final_bn=fuse)
         if self.logits is None or self.logits.shape != (B, n):
             self.logits = torch.empty((B, n), dtype=F32, device=u_idxs.device)
         bn_u = bn_i = None
@@ -153,13 +179,27 @@ class FusedTrainer:
         if self.item.reg_enabled:
             c = self.item.entity_config
             ops.infonce(Ei, B, n, D, c.regularization_temperature, c.regularization_weight, self.loss_acc[2:3], dEi, 1)
-        self.item.backward(dEi, self.grads, final_bn_sums=bn_i["sums"] if bn_i else None)
-        self._after_item_backward()
-        self.user.backward(dEu, self.grads, final_bn_sums=bn_u["sums"] if bn_u else None)
-        self._after_user_backward()
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.user.backward(dEu, self.grads, final_bn_sums=bn_u["sums"] if bn_u else None)
+            self.item.backward(dEi, self.grads, final_bn_sums=bn_i["sums"] if bn_i else None)
+            self._after_item_backward()
+            main.wait_stream(side)
+            self._after_user_backward()
+        else:
+            self.item.backward(dEi, self.grads, final_bn_sums=bn_i["sums"] if bn_i else None)
+            self._after_item_backward()
+            self.user.backward(dEu, self.grads, final_bn_sums=bn_u["sums"] if bn_u else None)
+            self._after_user_backward()
         if apply_optimizer:
             self.optimizer_step()
         self.steps_accumulated += 1
+
+    def _side_stream(self, device):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
 
     # hooks for the data-parallel subclass (gradient all-reduce overlapped with the rest of the backward pass)
     def _after_item_backward(self):
