@@ -156,6 +156,24 @@ class ZeroArena:
         return self.buf[start:start + size].view(dtype)
 
 
+def run_branches(thunks, streams):
+    """fork/join: ``thunks[0]`` runs on the current stream, ``thunks[j]`` on ``streams[j - 1]``, all of them after
+    what the current stream holds so far; the current stream continues after all of them.  Under CUDA-graph capture
+    these become parallel branches of the graph.  ``streams`` None / too short: plain sequential execution."""
+    if len(thunks) <= 1 or not streams or len(streams) < len(thunks) - 1:
+        for t in thunks:
+            t()
+        return
+    cur = torch.cuda.current_stream()
+    for t, s in zip(thunks[1:], streams):
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            t()
+    thunks[0]()
+    for s in streams[:len(thunks) - 1]:
+        cur.wait_stream(s)
+
+
 class Chain:
     """A stack of LinearStages.  forward: bf16 rows (or a CSR feature) -> fp32 output; backward: hand-written."""
 
@@ -256,9 +274,21 @@ class Chain:
         return y32
 
     def backward(self, dy32, grads: Dict[int, torch.Tensor], need_dx: bool, arena: ZeroArena, zero_dy=False,
-                 final_bn_sums=None):
+                 final_bn_sums=None, wgrad_stream=None):
         """dy32: fp32 [rows, out] gradient w.r.t. the chain output.  Accumulates parameter gradients into
-        ``grads[id(param)]``; returns fp32 [rows, in] gradient w.r.t. the chain input if ``need_dx``."""
+        ``grads[id(param)]``; returns fp32 [rows, in] gradient w.r.t. the chain input if ``need_dx``.
+        ``wgrad_stream``: the weight-gradient GEMMs (needed by the optimizer only) run there, next to the dz -> dx
+        chain on the current stream; joined before returning."""
+        if wgrad_stream is None or len(self.stages) < 2:
+            return self._backward(dy32, grads, need_dx, arena, zero_dy, final_bn_sums, None, None)
+        keep = []  # operands of the side-stream GEMMs stay allocated until the join
+        try:
+            return self._backward(dy32, grads, need_dx, arena, zero_dy, final_bn_sums, wgrad_stream, keep)
+        finally:
+            torch.cuda.current_stream().wait_stream(wgrad_stream)
+            keep.clear()
+
+    def _backward(self, dy32, grads, need_dx, arena, zero_dy, final_bn_sums, wstream, keep):
         rows = self.rows
         dev = dy32.device
         n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -314,13 +344,22 @@ class Chain:
                               split_stride=st.out_f * st.in_f)
                 else:
                     kw = dict(out_f32=g_w, transpose_out=True, atomic_out=True, split_k=split)
-                if si == 0 and self.bits_input:
-                    # dW^T [in, out] = X^T dZ with X^T = the transposed bit matrix as the K-major A operand
-                    ops.gemm_bits(self.feature.bits_t, dz16, st.in_f, st.out_f, rows, b_mn=True, **kw)
+                def wgrad(st=st, si=si, x16=x16, dz16=dz16, kw=kw, sliced=sliced, split=split, g_w=g_w,
+                          part=part if sliced else None):
+                    if si == 0 and self.bits_input:
+                        # dW^T [in, out] = X^T dZ with X^T = the transposed bit matrix as the K-major A operand
+                        ops.gemm_bits(self.feature.bits_t, dz16, st.in_f, st.out_f, rows, b_mn=True, **kw)
+                    else:
+                        ops.gemm(x16, dz16, st.in_f, st.out_f, rows, a_mn=True, b_mn=True, **kw)
+                    if sliced:
+                        ops.splitk_reduce(part, split, st.out_f, st.in_f, out_f32=g_w, accumulate=True)
+                if wstream is not None and (si > 0 or need_dx):  # (the last GEMM of the chain has nothing to overlap)
+                    keep.extend((dz16, x16, part if sliced else None))
+                    wstream.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(wstream):
+                        wgrad()
                 else:
-                    ops.gemm(x16, dz16, st.in_f, st.out_f, rows, a_mn=True, b_mn=True, **kw)
-                if sliced:
-                    ops.splitk_reduce(part, split, st.out_f, st.in_f, out_f32=g_w, accumulate=True)
+                    wgrad()
             # ---- dgrad
             if si > 0:
                 prev = self.stages[si - 1]
@@ -622,13 +661,23 @@ class SingleBranchNetEntity(_EntityBase):
         self._srcs_cache[key] = (grads, blob, entries)
         return blob
 
+    def _aux_streams(self, n):
+        """side streams of this entity (None unless the trainer enabled branch parallelism on the runtime)"""
+        if not getattr(self._rt(), "branches", False):
+            return None
+        pool = self.__dict__.setdefault("_aux_pool", [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=self._device()))
+        return pool[:n]
+
     def _project_tables(self, names, training, arena):
-        """entity-table projection: T_m = PolyLinear_m(X_m) for ALL rows of every listed modality"""
-        for name in names:
-            if name not in self.proj:
-                continue
+        """entity-table projection: T_m = PolyLinear_m(X_m) for ALL rows of every listed modality (independent of
+        each other: parallel branches)"""
+        def one(name):
             df, chain = self.dfeat[name], self.proj[name]
             chain.forward(df.x16, df.n_rows, training, arena, keep_for_backward=training, out32=self.tables[name])
+        todo = [n for n in names if n in self.proj]
+        run_branches([lambda n=n: one(n) for n in todo], self._aux_streams(len(todo) - 1) if training else None)
 
     def sample_modalities(self, n_idx: int):
         """device replacement of ``_sample_modalities`` (sgd_alg.py:1904-1927) for training"""
@@ -691,7 +740,9 @@ class SingleBranchNetEntity(_EntityBase):
         cfg = self.entity_config
         flat, mods, keep_mask, k, p_drop, seed, keep_bits = self._ctx
         C_ = cfg.common_modality_dim
-        dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena, final_bn_sums=final_bn_sums)
+        aux = self._aux_streams(max(1, len(self.proj) - 1))
+        dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena, final_bn_sums=final_bn_sums,
+                                     wgrad_stream=aux[0] if aux else None)
         srcs = self._src_blob(grads)
         if getattr(self, "_plan_built", False):
             plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
@@ -700,9 +751,10 @@ class SingleBranchNetEntity(_EntityBase):
         self._plan_built = False
         plan.backward(srcs, len(self.mod_names), C_, cfg.normalize_single_branch_input, p_drop, seed, rt.step_dev,
                       keep_mask, dx0, keep_bits=keep_bits)
-        for name, chain in self.proj.items():
-            # table-level backward; the accumulator table is cleared by the kernel that consumes it
-            chain.backward(self.table_grads[name], grads, need_dx=False, arena=rt.arena, zero_dy=True)
+        # table-level backward, one independent branch per modality; the accumulator table is cleared by the kernel
+        # that consumes it
+        run_branches([lambda n=n, c=c: c.backward(self.table_grads[n], grads, need_dx=False, arena=rt.arena,
+                                                  zero_dy=True) for n, c in self.proj.items()], aux)
 
     def get_and_reset_other_loss(self) -> Dict:
         loss = self.regularization_loss
@@ -719,6 +771,7 @@ class _Runtime:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=device)
         self.arena = ZeroArena(device)
+        self.branches = False  # FusedTrainer: independent kernel chains of a step on parallel streams
 
 
 class SingleBranchNet(nn.Module):

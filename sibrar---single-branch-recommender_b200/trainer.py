@@ -83,7 +83,8 @@ class FusedTrainer:
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
         # user side / item side of the step on two streams (SBR_BRANCHES=0: one stream)
-        self.branches = os.environ.get("SBR_BRANCHES", "1") != "0"
+        # 2 (default): + weight-gradient GEMMs and per-modality table chains on further streams
+        self.branches = int(os.environ.get("SBR_BRANCHES", "2"))
         self._side = None
 
     # ------------------------------------------------------------------------------------------------ one step
@@ -134,6 +135,7 @@ class FusedTrainer:
         # (tens of CTAs for the table projections, one CTA for the BatchNorm finalisers), so the user side runs on a
         # side stream -- a parallel branch of the captured graph -- next to the (longer) item side.
         side = self._side_stream(u_idxs.device) if (self.branches and u_idxs.is_cuda) else None
+        rt.branches = side is not None and self.branches >= 2
         main = torch.cuda.current_stream() if side is not None else None
         sb_u, sb_i = isinstance(self.user, SingleBranchNetEntity), isinstance(self.item, SingleBranchNetEntity)
         if side is not None:
