@@ -161,6 +161,16 @@ int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, int n_mods,
                                  const int64_t* step_dev, const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
                                  int rows_per_warp, const uint8_t* keep_bits, void* stream);
 
+/* nn.EmbeddingBag(mode="mean", padding_idx=pad_id) of EVERY feature row as a dense fp32 table [n_rows, C]
+ * (reference FeatureEmbedding for tag features, algorithms/sgd_alg.py:1279-1396; codes int32 [n_rows, max_tags]):
+ * the model gathers from it as a SBR_SRC_TABLE source (one row per lookup, no tag loop inside the batch-sized gathers).
+ * bwd: grad_weight[tag] += bag_grad[r] / #tags(r) for every tag of every row; bag_grad is cleared as it is read
+ * (it is an atomic accumulator reused every step). */
+int sbr_tag_bag_fwd(const int32_t* codes, int max_tags, int32_t pad_id, const float* weight, int64_t n_rows, int C,
+                    float* out, void* stream);
+int sbr_tag_bag_bwd(const int32_t* codes, int max_tags, int32_t pad_id, float* bag_grad, int64_t n_rows, int C,
+                    float* grad_weight, int64_t n_weight_rows, void* stream);
+
 /* table-level backward of the projection output activation: dpre = dT * act'(T) -> bf16 (+ column sums = dbias).
  * zero_dy = 1 clears dy after reading it (the gradient table is an atomicAdd accumulator reused every step). */
 int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y, int act,

@@ -60,6 +60,8 @@ _PROTOS = {
     "sbr_gather_plan": [c_vp, C.c_int, c_vp, c_vp, c_i64, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "sbr_row_gather_bwd_segmented": [c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, c_f32, c_u64,
                                      c_vp, c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp],
+    "sbr_tag_bag_fwd": [c_vp, C.c_int, C.c_int32, c_vp, c_i64, C.c_int, c_vp, c_vp],
+    "sbr_tag_bag_bwd": [c_vp, C.c_int, C.c_int32, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp],
     "sbr_actgrad_colsum": [c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp,
                            C.c_int, c_vp],
     "sbr_bn_finalize": [c_vp, C.c_int, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -253,8 +253,33 @@ constexpr int SEG_SMEM_FLOATS = 10240;  // 40 KB of block-private gradient rows 
 struct SegShared {
   sbr_modality_src_t src[SEG_MAX_MODS];
   int smem_off[SEG_MAX_MODS];  // offset of the modality's private gradient table in `priv`, or -1
+  int n_rep, rep_stride;       // replicas of the private tables (warp w adds into replica w % n_rep)
   float priv[SEG_SMEM_FLOATS];
 };
+
+// 8 consecutive floats added to shared memory (float atomics in shared memory are CAS loops: keep the volume low)
+__device__ __forceinline__ void smem_add8(float* w, int c, int C, const float* g, float scale) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (c + j < C) atomicAdd(w + c + j, g[j] * scale);
+}
+
+// 8 consecutive floats added to global memory: two 16-byte vector reductions (REDG.E.ADD.F32x4) when aligned
+__device__ __forceinline__ void red_add8(float* w, int c, int C, const float* g, float scale) {
+  if (c + 8 <= C && ((reinterpret_cast<uintptr_t>(w + c) & 15) == 0)) {
+    const size_t a = __cvta_generic_to_global(w + c);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(g[0] * scale), "f"(g[1] * scale),
+                 "f"(g[2] * scale), "f"(g[3] * scale)
+                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a + 16), "f"(g[4] * scale), "f"(g[5] * scale),
+                 "f"(g[6] * scale), "f"(g[7] * scale)
+                 : "memory");
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c + j < C) atomicAdd(w + c + j, g[j] * scale);
+  }
+}
 
 // flush the summed gradient of one run of equal keys (group layout) into the owning source's gradient buffer
 template <int LPR, int NV>
@@ -303,28 +328,26 @@ __device__ __forceinline__ void flush_run_g(SegShared& sh, int n_mods, int32_t k
     }
   }
   const int off = sh.smem_off[m];
+  // shared-memory float atomics are compare-and-swap loops: the replicas keep the groups of different warps apart
+  float* priv = off >= 0 ? sh.priv + ((threadIdx.x >> 5) % sh.n_rep) * sh.rep_stride + off : nullptr;
   if (s.kind == SBR_SRC_TAG) {
     for (int t = 0; t < s.max_tags; ++t) {
       const int32_t tag = __ldg(s.codes + local * s.max_tags + t);
       if (tag == s.pad_id) continue;
-      float* w = off >= 0 ? sh.priv + off + (int64_t)tag * C : s.grad + (int64_t)tag * C;
+      if (priv != nullptr) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
+        for (int i = 0; i < NV; ++i) smem_add8(priv + (int64_t)tag * C, 8 * li + 8 * LPR * i, C, g + i * 8, inv_cnt);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = 8 * li + 8 * LPR * i + j;
-          if (c < C) atomicAdd(w + c, g[i * 8 + j] * inv_cnt);
-        }
-    }
-  } else {
-    float* w = off >= 0 ? sh.priv + off + local * C : s.grad + local * C;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = 8 * li + 8 * LPR * i + j;
-        if (c < C) atomicAdd(w + c, g[i * 8 + j]);
+        for (int i = 0; i < NV; ++i) red_add8(s.grad + (int64_t)tag * C, 8 * li + 8 * LPR * i, C, g + i * 8, inv_cnt);
       }
+    }
+  } else if (priv != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem_add8(priv + local * C, 8 * li + 8 * LPR * i, C, g + i * 8, 1.f);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red_add8(s.grad + local * C, 8 * li + 8 * LPR * i, C, g + i * 8, 1.f);
   }
 }
 
@@ -333,13 +356,13 @@ __device__ __forceinline__ void flush_run_g(SegShared& sh, int n_mods, int32_t k
 // batch costs ~n / run-length atomics instead of n, and the work per group does not depend on how skewed the keys
 // are.  Small Embedding / EmbeddingBag tables (a 2-category feature, 18 genre tags) are accumulated in a block-private
 // shared-memory copy first: thousands of same-address global atomics serialise at ~100 cycles each in one L2 slice.
-template <int LPR, int NV>
-__global__ void __launch_bounds__(256)
+template <int LPR, int NV, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int64_t n_keys,
                     const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm,
                     const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop, uint64_t seed,
                     const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
-                    const float* __restrict__ dx, int64_t ld_dx, const uint8_t* __restrict__ keep_bits) {
+                    const float* __restrict__ dx, int64_t ld_dx, const uint8_t* __restrict__ keep_bits, int rpg) {
   SBR_PDL_ENTRY();
   __shared__ SegShared sh;
   if (threadIdx.x == 0) {
@@ -352,6 +375,8 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
       sh.smem_off[m] = small ? used : -1;
       if (small) used += (int)need;
     }
+    sh.rep_stride = used;
+    sh.n_rep = used > 0 ? max(1, min((int)(blockDim.x >> 5), SEG_SMEM_FLOATS / used)) : 1;
   }
   for (int i = threadIdx.x; i < SEG_SMEM_FLOATS; i += blockDim.x) sh.priv[i] = 0.f;
   __syncthreads();
@@ -364,7 +389,7 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
   const float sc = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   const bool vec_ok = (ld_dx & 3) == 0;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / LPR);
-  constexpr int RPG = 8;  // sorted rows per chunk
+  const int RPG = rpg;  // sorted rows per chunk
   for (int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;; chunk += groups_total) {
     const int64_t beg = chunk * RPG;
     if (beg >= n_sorted) break;
@@ -435,9 +460,87 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
     const int n = (int)(sh.src[m].n_table_rows * C);
     float* dst = sh.src[m].grad;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float v = sh.priv[off + i];
+      float v = 0.f;
+      for (int rep = 0; rep < sh.n_rep; ++rep) v += sh.priv[rep * sh.rep_stride + off + i];
       if (v != 0.f) atomicAdd(dst + i, v);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ EmbeddingBag tables
+// nn.EmbeddingBag(mode="mean", padding_idx=pad) of EVERY feature row as a dense table (reference FeatureEmbedding for
+// tag features, sgd_alg.py:1279-1396): bag[r] = mean over the non-pad tags t of weight[codes[r, t]].  The model
+// gathers from this table like from a projected one (one row per lookup, no tag loop in the big gathers) and
+// scatters the table gradient back onto the tag embeddings with the kernel below.
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256)
+tag_bag_fwd_kernel(const int32_t* __restrict__ codes, int max_tags, int32_t pad_id, const float* __restrict__ weight,
+                   int64_t n_rows, int C, float* __restrict__ out) {
+  SBR_PDL_ENTRY();
+  const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+  const int li = threadIdx.x % LPR;
+  if (gid >= n_rows) return;
+  sbr_modality_src_t s;
+  s.kind = SBR_SRC_TAG;
+  s.table = weight;
+  s.codes = codes;
+  s.max_tags = max_tags;
+  s.pad_id = pad_id;
+  float x[NV * 8], inv_cnt;
+  load_source_row_g<LPR, NV>(s, gid, C, li, x, inv_cnt);  // the arithmetic of the direct TAG gather, bit for bit
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * li + 8 * LPR * i + j;
+      if (c < C) out[gid * C + c] = x[i * 8 + j];
+    }
+}
+
+// grad_weight[tag] += bag_grad[r] / #tags(r) for every tag of every feature row; bag_grad is cleared as it is read.
+// Block-private shared-memory copy of the (small) tag table first, one global atomic per touched element and block.
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256)
+tag_bag_bwd_kernel(const int32_t* __restrict__ codes, int max_tags, int32_t pad_id, float* __restrict__ bag_grad,
+                   int64_t n_rows, int C, float* __restrict__ grad_weight, int64_t n_weight_rows) {
+  SBR_PDL_ENTRY();
+  __shared__ float priv[SEG_SMEM_FLOATS];
+  const bool use_smem = n_weight_rows * C <= SEG_SMEM_FLOATS;
+  const int n_priv = use_smem ? (int)(n_weight_rows * C) : 0;
+  for (int i = threadIdx.x; i < n_priv; i += blockDim.x) priv[i] = 0.f;
+  __syncthreads();
+  const int li = threadIdx.x % LPR;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / LPR);
+  for (int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR; r < n_rows; r += groups_total) {
+    float g[NV * 8];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = 8 * li + 8 * LPR * i + j;
+        g[i * 8 + j] = c < C ? bag_grad[r * C + c] : 0.f;
+        any |= g[i * 8 + j] != 0.f;
+        if (c < C) bag_grad[r * C + c] = 0.f;
+      }
+    if (!any) continue;  // (per lane: a lane whose 8 elements are zero has nothing to add)
+    int cnt = 0;
+    for (int t = 0; t < max_tags; ++t) cnt += __ldg(codes + r * max_tags + t) != pad_id ? 1 : 0;
+    const float inv_cnt = 1.f / (float)max(cnt, 1);
+    for (int t = 0; t < max_tags; ++t) {
+      const int32_t tag = __ldg(codes + r * max_tags + t);
+      if (tag == pad_id) continue;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (use_smem) smem_add8(priv + (int64_t)tag * C, 8 * li + 8 * LPR * i, C, g + i * 8, inv_cnt);
+        else red_add8(grad_weight + (int64_t)tag * C, 8 * li + 8 * LPR * i, C, g + i * 8, inv_cnt);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_priv; i += blockDim.x) {
+    const float v = priv[i];
+    if (v != 0.f) atomicAdd(grad_weight + i, v);
   }
 }
 
@@ -672,13 +775,54 @@ extern "C" int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, 
   SBR_REQUIRE(rows_per_warp >= 1, "sbr_row_gather_bwd_segmented: bad chunking");
   SBR_REQUIRE(n_mods <= SEG_MAX_MODS, "sbr_row_gather_bwd_segmented: at most %d modalities", SEG_MAX_MODS);
   DISPATCH_GROUP(C, {
-    const int64_t threads = (int64_t)cdiv(n_rows, 8) * LPRv;  // 8 sorted rows per lane group
+    const int64_t threads = (int64_t)cdiv(n_rows, 8) * LPRv;  // >= 8 sorted rows per lane group
     int64_t blocks = cdiv(threads, 256);
-    const int64_t cap = (int64_t)sbr_num_sms() * 4;  // persistent: 4 blocks (45 KB of shared memory each) per SM
+    int bps = 3, rpg = 8, minb = 3;
+    if (const char* e = getenv("SBR_SEG_BPS")) bps = atoi(e);
+    if (const char* e = getenv("SBR_SEG_MINB")) minb = atoi(e);
+    const int64_t cap = (int64_t)sbr_num_sms() * bps;  // persistent: every block resident
     if (blocks > cap) blocks = cap;
-    SBR_CHECK_CUDA(sbr_launch(seg_reduce_g_kernel<LPRv, NVg>, dim3((unsigned)blocks), dim3(256), 0, S(stream), srcs_dev,
-                              n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed, step_dev,
-                              keep_mask, dx, ld_dx, p_drop > 0.f ? keep_bits : (const uint8_t*)nullptr));
+    if (const char* e = getenv("SBR_SEG_RPG")) rpg = atoi(e);
+    if (rpg <= 0) rpg = (int)std::max<int64_t>(8, cdiv(n_rows, blocks * (256 / LPRv)));  // one chunk per group
+    if (minb == 4) {
+      SBR_CHECK_CUDA(sbr_launch(seg_reduce_g_kernel<LPRv, NVg, 4>, dim3((unsigned)blocks), dim3(256), 0, S(stream),
+                                srcs_dev, n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed,
+                                step_dev, keep_mask, dx, ld_dx,
+                                p_drop > 0.f ? keep_bits : (const uint8_t*)nullptr, rpg));
+    } else {
+      SBR_CHECK_CUDA(sbr_launch(seg_reduce_g_kernel<LPRv, NVg, 3>, dim3((unsigned)blocks), dim3(256), 0, S(stream),
+                                srcs_dev, n_mods, n_keys, offsets, perm, sorted_keys, C, normalize, p_drop, seed,
+                                step_dev, keep_mask, dx, ld_dx,
+                                p_drop > 0.f ? keep_bits : (const uint8_t*)nullptr, rpg));
+    }
+  });
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_tag_bag_fwd(const int32_t* codes, int max_tags, int32_t pad_id, const float* weight, int64_t n_rows,
+                               int C, float* out, void* stream) {
+  SBR_REQUIRE(codes && weight && out && n_rows > 0 && max_tags >= 1, "sbr_tag_bag_fwd: bad arguments");
+  SBR_REQUIRE(C > 0 && C <= 1024, "sbr_tag_bag_fwd: C=%d not in [1, 1024]", C);
+  DISPATCH_GROUP(C, {
+    const int64_t threads = n_rows * LPRv;
+    SBR_CHECK_CUDA(sbr_launch(tag_bag_fwd_kernel<LPRv, NVg>, dim3(cdiv(threads, 256)), dim3(256), 0, S(stream), codes,
+                              max_tags, pad_id, weight, n_rows, C, out));
+  });
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_tag_bag_bwd(const int32_t* codes, int max_tags, int32_t pad_id, float* bag_grad, int64_t n_rows,
+                               int C, float* grad_weight, int64_t n_weight_rows, void* stream) {
+  SBR_REQUIRE(codes && bag_grad && grad_weight && n_rows > 0 && max_tags >= 1 && n_weight_rows > 0,
+              "sbr_tag_bag_bwd: bad arguments");
+  SBR_REQUIRE(C > 0 && C <= 1024, "sbr_tag_bag_bwd: C=%d not in [1, 1024]", C);
+  DISPATCH_GROUP(C, {
+    int64_t blocks = cdiv(n_rows * LPRv, 256);
+    if (blocks > sbr_num_sms()) blocks = sbr_num_sms();
+    SBR_CHECK_CUDA(sbr_launch(tag_bag_bwd_kernel<LPRv, NVg>, dim3((unsigned)blocks), dim3(256), 0, S(stream), codes,
+                              max_tags, pad_id, bag_grad, n_rows, C, grad_weight, n_weight_rows));
   });
   SBR_LAUNCH_CHECK();
   return SBR_OK;

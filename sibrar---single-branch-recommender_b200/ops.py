@@ -195,6 +195,18 @@ class GatherPlan:
              ptr(step_dev), ptr(keep_mask), ptr(dx), dx.stride(0), self.rows_per_warp, ptr(keep_bits), stream_ptr())
 
 
+def tag_bag_fwd(codes, max_tags, pad_id, weight, out):
+    """EmbeddingBag(mean, padding_idx) of every feature row -> fp32 table [n_rows, C]"""
+    call("sbr_tag_bag_fwd", ptr(codes), int(max_tags), int(pad_id), ptr(weight), int(out.shape[0]), int(out.shape[1]),
+         ptr(out), stream_ptr())
+
+
+def tag_bag_bwd(codes, max_tags, pad_id, bag_grad, grad_weight):
+    """table gradient [n_rows, C] (cleared) -> += gradient of the tag embedding matrix"""
+    call("sbr_tag_bag_bwd", ptr(codes), int(max_tags), int(pad_id), ptr(bag_grad), int(bag_grad.shape[0]),
+         int(bag_grad.shape[1]), ptr(grad_weight), int(grad_weight.shape[0]), stream_ptr())
+
+
 def _y_args(y):
     if y is None:
         return None, None, 0

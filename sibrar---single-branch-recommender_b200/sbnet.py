@@ -626,11 +626,14 @@ class SingleBranchNetEntity(_EntityBase):
             if fe.pre_embedding_layers is not None:
                 self.proj[name] = Chain(build_stages(fe.pre_embedding_layers), feature=df)
         self.sb_chain = Chain(build_stages(self._poly, self._trailing_bn))
+        # tag features: the EmbeddingBag means of all feature rows are a per-step table as well (sbr_tag_bag_fwd/bwd),
+        # so the batch-sized gathers see one source row per lookup
+        self.bags = [n for n in self.mod_names if self.dfeat[n].kind == "tag"]
         # fp32 [n_rows, C] projected modality tables at stable addresses (the gather descriptors point at them)
         self.tables = {n: torch.zeros((self.dfeat[n].n_rows, cfg.common_modality_dim), dtype=F32, device=dev)
-                       for n in self.proj}
+                       for n in list(self.proj) + self.bags}
         self.table_grads = {n: torch.zeros((self.dfeat[n].n_rows, cfg.common_modality_dim), dtype=F32, device=dev)
-                            for n in self.proj}
+                            for n in list(self.proj) + self.bags}
         self._srcs_cache = {}
         self._eval_ids = torch.tensor([self.mod_names.index(m) for m in sorted(self.eval_modalities)],
                                       dtype=torch.uint8, device=dev)
@@ -644,7 +647,7 @@ class SingleBranchNetEntity(_EntityBase):
         entries, key_base = [], 0
         for name in self.mod_names:
             df, fe = self.dfeat[name], self.modality_modules[name]
-            if name in self.proj:
+            if name in self.tables:
                 entries.append(dict(kind=SRC_TABLE, remap=df.remap, table=self.tables[name], key_base=key_base,
                                     grad=self.table_grads[name] if grads is not None else None))
                 key_base += int(df.n_rows)
@@ -674,9 +677,14 @@ class SingleBranchNetEntity(_EntityBase):
         """entity-table projection: T_m = PolyLinear_m(X_m) for ALL rows of every listed modality (independent of
         each other: parallel branches)"""
         def one(name):
-            df, chain = self.dfeat[name], self.proj[name]
+            df = self.dfeat[name]
+            if name in self.bags:
+                w = self.modality_modules[name].embedding_layer.weight.detach()
+                ops.tag_bag_fwd(df.codes, df.max_tags, df.pad_id, w, self.tables[name])
+                return
+            chain = self.proj[name]
             chain.forward(df.x16, df.n_rows, training, arena, keep_for_backward=training, out32=self.tables[name])
-        todo = [n for n in names if n in self.proj]
+        todo = [n for n in names if n in self.tables]
         run_branches([lambda n=n: one(n) for n in todo], self._aux_streams(len(todo) - 1) if training else None)
 
     def sample_modalities(self, n_idx: int):
@@ -740,7 +748,7 @@ class SingleBranchNetEntity(_EntityBase):
         cfg = self.entity_config
         flat, mods, keep_mask, k, p_drop, seed, keep_bits = self._ctx
         C_ = cfg.common_modality_dim
-        aux = self._aux_streams(max(1, len(self.proj) - 1))
+        aux = self._aux_streams(max(1, len(self.tables) - 1))
         dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena, final_bn_sums=final_bn_sums,
                                      wgrad_stream=aux[0] if aux else None)
         srcs = self._src_blob(grads)
@@ -753,8 +761,13 @@ class SingleBranchNetEntity(_EntityBase):
                       keep_mask, dx0, keep_bits=keep_bits)
         # table-level backward, one independent branch per modality; the accumulator table is cleared by the kernel
         # that consumes it
-        run_branches([lambda n=n, c=c: c.backward(self.table_grads[n], grads, need_dx=False, arena=rt.arena,
-                                                  zero_dy=True) for n, c in self.proj.items()], aux)
+        thunks = [lambda n=n, c=c: c.backward(self.table_grads[n], grads, need_dx=False, arena=rt.arena, zero_dy=True)
+                  for n, c in self.proj.items()]
+        for n in self.bags:
+            df, w = self.dfeat[n], self.modality_modules[n].embedding_layer.weight
+            thunks.append(lambda n=n, df=df, w=w: ops.tag_bag_bwd(df.codes, df.max_tags, df.pad_id,
+                                                                  self.table_grads[n], grads[id(w)]))
+        run_branches(thunks, aux)
 
     def get_and_reset_other_loss(self) -> Dict:
         loss = self.regularization_loss

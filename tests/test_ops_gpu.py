@@ -330,6 +330,35 @@ def test_row_gather_fwd_bwd():
     assert abs((big != 0).float().mean().item() - 0.75) < 0.01
 
 
+@pytest.mark.parametrize("n_rows,n_tags,max_tags,C", [(3706, 18, 6, 64), (50, 7, 3, 24), (1000, 300, 9, 128),
+                                                      (200, 40, 5, 600)])
+def test_tag_bag_table_matches_embedding_bag(n_rows, n_tags, max_tags, C):
+    """sbr_tag_bag_fwd/bwd == nn.EmbeddingBag(mode='mean', padding_idx=-1) forward / weight gradient; rows without
+    tags give zeros; the gradient table is cleared by the backward"""
+    g = torch.Generator(device="cpu").manual_seed(n_rows + C)
+    codes = torch.full((n_rows, max_tags), n_tags, dtype=torch.int32)
+    for r in range(n_rows):
+        n = int(torch.randint(0, max_tags + 1, (1,), generator=g))
+        codes[r, :n] = torch.randperm(n_tags, generator=g)[:n].to(torch.int32)
+    bag = torch.nn.EmbeddingBag(n_tags + 1, C, mode="mean", padding_idx=n_tags).double()
+    with torch.no_grad():
+        bag.weight.copy_(torch.randn(n_tags + 1, C, generator=g))
+    want = bag(codes.long())
+    dy = torch.randn(n_rows, C, generator=g)
+    want.backward(dy.double())
+    w = bag.weight.detach().float().to(DEV)
+    out = torch.full((n_rows, C), float("nan"), device=DEV)
+    ops.tag_bag_fwd(codes.to(DEV), max_tags, n_tags, w, out)
+    assert _relerr(out.cpu(), want.detach()) < 1e-6
+    empty = (codes == n_tags).all(dim=1)
+    assert empty.any() and (out.cpu()[empty] == 0).all()
+    gw = torch.zeros(n_tags + 1, C, device=DEV)
+    dyd = dy.to(DEV).clone()
+    ops.tag_bag_bwd(codes.to(DEV), max_tags, n_tags, dyd, gw)
+    assert _relerr(gw.cpu(), bag.weight.grad) < 1e-5
+    assert (gw[n_tags] == 0).all() and (dyd == 0).all()
+
+
 def test_gemm_partial_colstats_are_deterministic():
     """BatchNorm statistics from the GEMM epilogue: per-warp partial rows + ordered finalize give bit-identical
     mean / invstd on every run (the atomic variant depends on the arrival order) and agree with torch"""
