@@ -451,7 +451,8 @@ def main():
 
     # ---- roofline of the dominant kernel (separate profiled pass, CUDA events around every C-ABI call); every rank
     # runs these steps (they contain the gradient all-reduce), rank 0 records them
-    tr.cuda_graph = False  # the per-call pass launches kernel by kernel
+    tr.cuda_graph = False  # the per-call pass launches kernel by kernel ...
+    tr.branches = 0        # ... on one stream: concurrent branches would stretch each other's bracketed durations
     if rank != 0:
         for k in range(3):
             flush.zero_()

@@ -2,7 +2,7 @@
 //
 // D[M,N] = alpha * A * B^T, A/B each K-major or MN-major (see include/sibrar_b200.h).  One 128 x BN output tile per
 // CTA, optional split-K over blockIdx.z.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
-// (single elected thread), warps 2..5 = epilogue (TMEM -> registers -> fused bias / BN statistics / activation /
+// (single elected thread), warps 2..9 (2..5 next to the bit converters) = epilogue (TMEM -> registers -> fused bias / BN statistics / activation /
 // activation-gradient / store | transposed atomic accumulate).
 //
 // Replaces nn.Linear forward in the reference's PolyLinear (modules/polylinear.py:50-76) and the dgrad/wgrad
@@ -99,8 +99,16 @@ __device__ __forceinline__ void apply_actgrad32(int act, float (&v)[32], const f
 // warps expand it into the bf16 SWIZZLE_128B K-major stage in shared memory (thread = tile row, 64 bits -> eight
 // 16-byte chunks per K block through a 16-entry nibble table), so HBM sees 1 bit per element instead of 16 and the
 // tensor cores see ordinary bf16 operands; the TMA producer then only loads B.
+// epilogue warps: 4 (one per TMEM lane quarter) next to the bit converters, else 8 -- two warps per lane quarter, each
+// draining every other 32-column chunk: skinny layers (K = N = 64) are bound by the epilogue's instruction stream
+template <bool A_BITS>
+struct Warps {
+  static constexpr int EPI = A_BITS ? 4 : 8;
+  static constexpr int THREADS = (2 + EPI + (A_BITS ? 4 : 0)) * 32;
+};
+
 template <int BN, bool A_BITS>
-__global__ void __launch_bounds__(A_BITS ? 320 : 192)
+__global__ void __launch_bounds__(Warps<A_BITS>::THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   SBR_PDL_ENTRY();
   using C = Cfg<BN>;
@@ -138,7 +146,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], Warps<A_BITS>::EPI);
     }
     fence_barrier_init();
   }
@@ -262,6 +270,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
     const int q = warp & 3;
+    constexpr int NH = Warps<A_BITS>::EPI / 4;  // warps per lane quarter
+    const int half = (warp - 2) >> 2;           // this warp drains the chunks c0 = 32 * (half + NH * i)
     const int row_in_tile = q * 32 + lane;
     const sbr_gemm_epilogue_t& ep = p.ep;
     // split-K without atomics: every K partition writes its own fp32 slice (reduced by sbr_splitk_reduce)
@@ -277,7 +287,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 32 * half; c0 < BN; c0 += 32 * NH) {
       const int64_t col0 = (int64_t)n0 + c0;
       if (col0 >= p.N) break;  // warp-uniform
       uint32_t r[32];
@@ -393,7 +403,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
         const int64_t col = (int64_t)n0 + 32 * i + lane;
-        if (col < p.N) {
+        if (i % NH == half && col < p.N) {
           if (ep.colstats_rows > 0) {
             // deterministic statistics: this warp's private row of partial sums, added up in a fixed order by
             // sbr_bn_finalize (fp32 atomics would make the batch statistics -- and through bf16 roundings the whole
@@ -439,7 +449,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   SBR_REQUIRE(p.ep.colstats == nullptr || p.ep.colstats_rows == 0 || p.ep.colstats_rows >= 4 * gx,
               "sbr_gemm: colstats_rows=%d < %lld partial rows", p.ep.colstats_rows, (long long)(4 * gx));
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);
-  SBR_CHECK_CUDA(sbr_launch(gemm_bf16_kernel<BN, A_BITS>, grid, dim3(A_BITS ? 320 : 192), (size_t)Cfg<BN>::SMEM_BYTES, st,
+  SBR_CHECK_CUDA(sbr_launch(gemm_bf16_kernel<BN, A_BITS>, grid, dim3(Warps<A_BITS>::THREADS), (size_t)Cfg<BN>::SMEM_BYTES, st,
                             tmA, tmB, p));
   return SBR_OK;
 }

@@ -268,7 +268,7 @@ struct BnInline {
   float* sums;               // [n_replicas, 2 * D], zeroed by the caller
 };
 
-template <int LPR>
+template <int LPR, int MAXP>
 __global__ void __launch_bounds__(256)
 score_loss_bn_kernel(const float* __restrict__ eu, BnInline bu, const float* __restrict__ ei, BnInline bi, int64_t B,
                      int n, int loss_kind, float inv_cnt, float ssm_shift, float* __restrict__ logits,
@@ -308,17 +308,39 @@ score_loss_bn_kernel(const float* __restrict__ eu, BnInline bu, const float* __r
     const float4 zu = __ldg(usrc + b * LPR + li);
     const float4 u4 = make_float4(zu.x * ua.x + uc.x, zu.y * ua.y + uc.y, zu.z * ua.z + uc.z, zu.w * ua.w + uc.w);
     const float4* items = isrc + b * n * LPR;
-    for (int j0 = 0; j0 < n; j0 += RPP) {
-      const int j = j0 + sub;
-      float dot = 0.f;
-      if (j < n) {
-        const float4 z = __ldg(items + (size_t)j * LPR + li);
-        dot = u4.x * (z.x * ia.x + ic.x) + u4.y * (z.y * ia.y + ic.y) + u4.z * (z.z * ia.z + ic.z) +
-              u4.w * (z.w * ia.w + ic.w);
+    // MAXP > 0 (n <= MAXP * RPP): all item rows of the user are loaded at once and stay in registers for the
+    // gradient phase -- one 512-byte load in flight per warp (the loop below) caps the kernel at ~2.4 TB/s
+    float4 zr[MAXP > 0 ? MAXP : 1];
+    if (MAXP > 0) {
+#pragma unroll
+      for (int p = 0; p < MAXP; ++p) {
+        const int j = p * RPP + sub;
+        zr[p] = (p * RPP < n && j < n) ? __ldg(items + (size_t)j * LPR + li) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      if (li == 0 && j < n) sc[j] = dot;
+      for (int p = 0; p < MAXP; ++p) {
+        if (p * RPP >= n) break;  // warp-uniform
+        const int j = p * RPP + sub;
+        const float4 z = zr[p];
+        float dot = u4.x * (z.x * ia.x + ic.x) + u4.y * (z.y * ia.y + ic.y) + u4.z * (z.z * ia.z + ic.z) +
+                    u4.w * (z.w * ia.w + ic.w);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (li == 0 && j < n) sc[j] = dot;
+      }
+    } else {
+      for (int j0 = 0; j0 < n; j0 += RPP) {
+        const int j = j0 + sub;
+        float dot = 0.f;
+        if (j < n) {
+          const float4 z = __ldg(items + (size_t)j * LPR + li);
+          dot = u4.x * (z.x * ia.x + ic.x) + u4.y * (z.y * ia.y + ic.y) + u4.z * (z.z * ia.z + ic.z) +
+                u4.w * (z.w * ia.w + ic.w);
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (li == 0 && j < n) sc[j] = dot;
+      }
     }
     __syncwarp();
     float lsum = 0.f;
@@ -360,18 +382,26 @@ score_loss_bn_kernel(const float* __restrict__ eu, BnInline bu, const float* __r
     __syncwarp();
     float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
     float4* dit = reinterpret_cast<float4*>(dei + b * n * D);
-    for (int j0 = 0; j0 < n; j0 += RPP) {
-      const int j = j0 + sub;
-      if (j < n) {
-        const float g = gr[j];
-        const float4 z = __ldg(items + (size_t)j * LPR + li);
-        du.x += g * (z.x * ia.x + ic.x); du.y += g * (z.y * ia.y + ic.y);
-        du.z += g * (z.z * ia.z + ic.z); du.w += g * (z.w * ia.w + ic.w);
-        const float4 d = make_float4(g * u4.x, g * u4.y, g * u4.z, g * u4.w);
-        dit[(size_t)j * LPR + li] = d;
-        si0.x += d.x; si0.y += d.y; si0.z += d.z; si0.w += d.w;
-        si1.x += d.x * (z.x - im.x) * iis.x; si1.y += d.y * (z.y - im.y) * iis.y;
-        si1.z += d.z * (z.z - im.z) * iis.z; si1.w += d.w * (z.w - im.w) * iis.w;
+    auto grad_row = [&](int j, const float4 z) {
+      const float g = gr[j];
+      du.x += g * (z.x * ia.x + ic.x); du.y += g * (z.y * ia.y + ic.y);
+      du.z += g * (z.z * ia.z + ic.z); du.w += g * (z.w * ia.w + ic.w);
+      const float4 d = make_float4(g * u4.x, g * u4.y, g * u4.z, g * u4.w);
+      dit[(size_t)j * LPR + li] = d;
+      si0.x += d.x; si0.y += d.y; si0.z += d.z; si0.w += d.w;
+      si1.x += d.x * (z.x - im.x) * iis.x; si1.y += d.y * (z.y - im.y) * iis.y;
+      si1.z += d.z * (z.z - im.z) * iis.z; si1.w += d.w * (z.w - im.w) * iis.w;
+    };
+    if (MAXP > 0) {
+#pragma unroll
+      for (int p = 0; p < MAXP; ++p) {
+        const int j = p * RPP + sub;
+        if (p * RPP < n && j < n) grad_row(j, zr[p]);
+      }
+    } else {
+      for (int j0 = 0; j0 < n; j0 += RPP) {
+        const int j = j0 + sub;
+        if (j < n) grad_row(j, __ldg(items + (size_t)j * LPR + li));
       }
     }
 #pragma unroll
@@ -516,14 +546,30 @@ extern "C" int sbr_score_loss_bn(const float* eu, const sbr_bn_inline_t* bn_u, c
   const int64_t cap = (int64_t)sbr_num_sms() * 4;
   if (blocks > cap) blocks = cap;
   const float inv = (float)(1.0 / cnt);
-#define SBR_FUSED(LPR_)                                                                                          \
-  SBR_CHECK_CUDA(sbr_launch(score_loss_bn_kernel<LPR_>, dim3((unsigned)blocks), dim3(nw * 32), sm, S(stream), eu, bu, \
-                            ei, bi, B, n, loss_kind, inv, ssm_shift, logits, loss_acc, deu, dei, n_replicas))
+  const bool generic = getenv("SBR_SCORE_GENERIC") != nullptr;
+#define SBR_FUSED_P(LPR_, MAXP_)                                                                                  \
+  do {                                                                                                            \
+    int occ = 0; /* persistent grid = exactly the resident blocks (no second wave) */                             \
+    SBR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_loss_bn_kernel<LPR_, MAXP_>, nw * 32, sm)); \
+    int64_t grid = (B + nw - 1) / nw;                                                                             \
+    if (grid > (int64_t)sbr_num_sms() * (occ > 0 ? occ : 1)) grid = (int64_t)sbr_num_sms() * (occ > 0 ? occ : 1); \
+    SBR_CHECK_CUDA(sbr_launch(score_loss_bn_kernel<LPR_, MAXP_>, dim3((unsigned)grid), dim3(nw * 32), sm, S(stream), \
+                              eu, bu, ei, bi, B, n, loss_kind, inv, ssm_shift, logits, loss_acc, deu, dei,        \
+                              n_replicas));                                                                       \
+  } while (0)
+#define SBR_FUSED(LPR_)                                            \
+  do {                                                             \
+    const int passes = (n + 32 / LPR_ - 1) / (32 / LPR_);          \
+    if (!generic && passes <= 6) SBR_FUSED_P(LPR_, 6);             \
+    else if (!generic && passes <= 12) SBR_FUSED_P(LPR_, 12);      \
+    else SBR_FUSED_P(LPR_, 0);                                     \
+  } while (0)
   if (D == 16) SBR_FUSED(4);
   else if (D == 32) SBR_FUSED(8);
   else if (D == 64) SBR_FUSED(16);
   else SBR_FUSED(32);
 #undef SBR_FUSED
+#undef SBR_FUSED_P
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

@@ -200,11 +200,103 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy,
 inline dim3 tile_grid(int64_t rows, int64_t cols) { return dim3(cdiv(rows, rows_per_block(rows)), cdiv(cols, 32)); }
 }  // namespace
 
+// Vector path of actgrad_colsum (C % 4 == 0, 256 % (C / 4) == 0, 16-byte aligned rows): 4 columns per thread, the loads
+// of 4 rows in flight, one atomic per column and BLOCK (a [3 706 x 64] table: 58 blocks instead of 232 whose
+// same-address atomics queue up in one L2 slice).
+__global__ void __launch_bounds__(256)
+actgrad_colsum_vec_kernel(float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
+                          const bf16* __restrict__ y_bf16, int64_t ld_y, int act, int64_t rows, int C,
+                          bf16* __restrict__ out_bf16, int64_t ld_out, float* __restrict__ out_f32,
+                          int64_t ld_out_f32, float* __restrict__ colsum, int zero_dy) {
+  SBR_PDL_ENTRY();
+  constexpr int UNR = 4;
+  const int c4n = C >> 2;
+  const int c = (threadIdx.x % c4n) * 4;
+  const int rpb = 256 / c4n;
+  const int64_t stride = (int64_t)gridDim.x * rpb;
+  float part[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t r0 = (int64_t)blockIdx.x * rpb + threadIdx.x / c4n; r0 < rows; r0 += stride * UNR) {
+    float4 g[UNR], yv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= rows) continue;
+      g[u] = *reinterpret_cast<const float4*>(dy + r * ld_dy + c);
+      if (act != SBR_ACT_NONE) {
+        if (y_f32) {
+          yv[u] = *reinterpret_cast<const float4*>(y_f32 + r * ld_y + c);
+        } else {
+          const uint2 raw = *reinterpret_cast<const uint2*>(y_bf16 + r * ld_y + c);
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          yv[u] = make_float4(a.x, a.y, b.x, b.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= rows) break;
+      float v[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      if (act != SBR_ACT_NONE) {
+        v[0] *= act_grad_from_out(act, yv[u].x);
+        v[1] *= act_grad_from_out(act, yv[u].y);
+        v[2] *= act_grad_from_out(act, yv[u].z);
+        v[3] *= act_grad_from_out(act, yv[u].w);
+      }
+      if (zero_dy) *reinterpret_cast<float4*>(dy + r * ld_dy + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[j] += v[j];
+      if (out_bf16) {
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(out_bf16 + r * ld_out + c) = o;
+      }
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * ld_out_f32 + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  if (colsum == nullptr) return;
+  __shared__ float4 red[256];
+  red[threadIdx.x] = make_float4(part[0], part[1], part[2], part[3]);
+  __syncthreads();
+  if (threadIdx.x < c4n) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < rpb; ++k) {
+      const float4 a = red[k * c4n + threadIdx.x];
+      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    }
+    atomicAdd(colsum + c, t.x);
+    atomicAdd(colsum + c + 1, t.y);
+    atomicAdd(colsum + c + 2, t.z);
+    atomicAdd(colsum + c + 3, t.w);
+  }
+}
+
 extern "C" int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
                                   int act, int64_t rows, int64_t cols, void* out_bf16, int64_t ld_out, float* out_f32,
                                   int64_t ld_out_f32, float* colsum, int zero_dy, void* stream) {
   SBR_REQUIRE(dy && rows > 0 && cols > 0, "sbr_actgrad_colsum: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_actgrad_colsum: activation gradient needs the output y");
+  {
+    const auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+    const int C = (int)cols;
+    const bool vec = (C & 3) == 0 && C <= 1024 && 256 % (C >> 2) == 0 && (ld_dy & 3) == 0 && al(dy, 16) &&
+                     (act == SBR_ACT_NONE || (y_f32 ? ((ld_y & 3) == 0 && al(y_f32, 16)) : ((ld_y & 3) == 0 && al(y_bf16, 8)))) &&
+                     (!out_bf16 || ((ld_out & 3) == 0 && al(out_bf16, 8))) &&
+                     (!out_f32 || ((ld_out_f32 & 3) == 0 && al(out_f32, 16))) && getenv("SBR_NORM_SCALAR") == nullptr;
+    if (vec) {
+      const int rpb = 256 / (C >> 2);
+      int64_t blocks = cdiv(rows, (int64_t)rpb * 4);
+      const int64_t cap = (int64_t)sbr_num_sms() * 8;
+      if (blocks > cap) blocks = cap;
+      SBR_CHECK_CUDA(sbr_launch(actgrad_colsum_vec_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), S(stream), dy,
+                                ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, rows, C,
+                                reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum, zero_dy));
+      SBR_LAUNCH_CHECK();
+      return SBR_OK;
+    }
+  }
   SBR_CHECK_CUDA(sbr_launch(actgrad_colsum_kernel, dim3(tile_grid(rows, cols)), dim3(256), (size_t)(0), S(stream), 
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, rows, (int)cols,
       reinterpret_cast<bf16*>(out_bf16), ld_out, out_f32, ld_out_f32, colsum, zero_dy, rows_per_block(rows)));
@@ -252,6 +344,80 @@ extern "C" int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_
   return SBR_OK;
 }
 
+// Vector path of the above for the shapes of the train step (no activation in front, C % 4 == 0, 16-byte aligned
+// rows, 256 % (C / 4) == 0): a thread owns 4 columns (its BatchNorm coefficients live in registers), grid-strides over
+// the rows and keeps the loads of UNR rows in flight -- the scalar kernel (one 4-byte load per thread and row, no
+// unrolling) ran at 2.4 TB/s.
+constexpr int BNV_UNR = 4;
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ z, int64_t ld_z,
+                        const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                        const float* __restrict__ sums, int n_replicas, int64_t rows, int C,
+                        bf16* __restrict__ dz_bf16, int64_t ld_dz, float* __restrict__ dz_f32, int64_t ld_dz_f32,
+                        float* dgamma, float* dbeta) {
+  SBR_PDL_ENTRY();
+  const int c4n = C >> 2;                 // float4 columns per row
+  const int c = (threadIdx.x % c4n) * 4;  // this thread's first column (256 % c4n == 0)
+  const int rpb = 256 / c4n;              // rows per block pass
+  const float inv_n = 1.f / (float)rows;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < n_replicas; ++r) {
+    const float4 a = *reinterpret_cast<const float4*>(sums + (size_t)r * 2 * C + c);
+    const float4 b = *reinterpret_cast<const float4*>(sums + (size_t)r * 2 * C + C + c);
+    s0[0] += a.x; s0[1] += a.y; s0[2] += a.z; s0[3] += a.w;
+    s1[0] += b.x; s1[1] += b.y; s1[2] += b.z; s1[3] += b.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < c4n) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (dbeta) dbeta[c + j] += s0[j];
+      if (dgamma) dgamma[c + j] += s1[j];
+    }
+  }
+  const float4 mean = *reinterpret_cast<const float4*>(mean_invstd + c);
+  const float4 invstd = *reinterpret_cast<const float4*>(mean_invstd + C + c);
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+  const float m[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
+  const float gi[4] = {gm.x * invstd.x, gm.y * invstd.y, gm.z * invstd.z, gm.w * invstd.w};
+  float k0[4], k1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    k0[j] = s0[j] * inv_n;
+    k1[j] = s1[j] * inv_n;
+  }
+  const int64_t stride = (int64_t)gridDim.x * rpb;
+  for (int64_t r0 = (int64_t)blockIdx.x * rpb + threadIdx.x / c4n; r0 < rows; r0 += stride * BNV_UNR) {
+    float4 g[BNV_UNR], zz[BNV_UNR];
+#pragma unroll
+    for (int u = 0; u < BNV_UNR; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < rows) {
+        g[u] = __ldcs(reinterpret_cast<const float4*>(dy + r * ld_dy + c));  // read once: streaming
+        zz[u] = __ldcs(reinterpret_cast<const float4*>(z + r * ld_z + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BNV_UNR; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= rows) break;
+      const float gv[4] = {g[u].x, g[u].y, g[u].z, g[u].w}, zv[4] = {zz[u].x, zz[u].y, zz[u].z, zz[u].w};
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (zv[j] - m[j]) * is[j];
+        v[j] = gi[j] * (gv[j] - k0[j] - xh * k1[j]);
+      }
+      if (dz_bf16) {
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(dz_bf16 + r * ld_dz + c) = o;
+      }
+      if (dz_f32) *reinterpret_cast<float4*>(dz_f32 + r * ld_dz_f32 + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
 extern "C" int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
                                 int act, const float* z, int64_t ld_z, const float* mean_invstd, const float* gamma,
                                 const float* sums, int n_replicas, int64_t rows, int C, void* dz_bf16, int64_t ld_dz,
@@ -259,6 +425,22 @@ extern "C" int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f
   SBR_REQUIRE(dy && z && mean_invstd && gamma && sums && rows > 0 && C > 0 && n_replicas >= 1,
               "sbr_bn_bwd_apply: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_apply: activation gradient needs the output y");
+  const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = act == SBR_ACT_NONE && (C & 3) == 0 && C <= 1024 && 256 % (C >> 2) == 0 && (ld_dy & 3) == 0 &&
+                   (ld_z & 3) == 0 && al16(dy) && al16(z) && al16(mean_invstd) && al16(gamma) && al16(sums) &&
+                   (!dz_bf16 || ((ld_dz & 3) == 0 && (reinterpret_cast<uintptr_t>(dz_bf16) & 7) == 0)) &&
+                   (!dz_f32 || ((ld_dz_f32 & 3) == 0 && al16(dz_f32))) && getenv("SBR_NORM_SCALAR") == nullptr;
+  if (vec) {
+    const int rpb = 256 / (C >> 2);
+    int64_t blocks = cdiv(rows, (int64_t)rpb * BNV_UNR);
+    const int64_t cap = (int64_t)sbr_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    SBR_CHECK_CUDA(sbr_launch(bn_bwd_apply_vec_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), S(stream), dy,
+                              ld_dy, z, ld_z, mean_invstd, gamma, sums, n_replicas, rows, C,
+                              reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta));
+    SBR_LAUNCH_CHECK();
+    return SBR_OK;
+  }
   SBR_CHECK_CUDA(sbr_launch(bn_bwd_apply_kernel, dim3(tile_grid(rows, C)), dim3(256), (size_t)(0), S(stream), 
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, gamma, sums, n_replicas,
       rows, C, reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta, rows_per_block(rows)));
