@@ -116,6 +116,9 @@ int sbr_sample_modalities(uint8_t* mods, int64_t n_rows, int k, int n_mods, int 
 
 /* step counter kept on the DEVICE (so that CUDA-graph replays of a step see a fresh value): *counter += 1 */
 int sbr_tick(int64_t* counter_dev, void* stream);
+/* start of a fused train step in ONE launch: counter0 / counter1 (nullable) += 1 and `zero_bytes` (multiple of 16) of the
+ * step's accumulator arena cleared (replaces two sbr_tick launches and a memset on the step's critical path) */
+int sbr_step_begin(int64_t* counter0, int64_t* counter1, void* zero, int64_t zero_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ row gather
  * One descriptor per modality of an entity. */

@@ -69,35 +69,32 @@ bn_finalize_kernel(const float* __restrict__ stats, int n_partials, int64_t n_ro
                    float* __restrict__ mean_invstd, float* running_mean, float* running_var,
                    int64_t* num_batches_tracked) {
   SBR_PDL_ENTRY();
-  __shared__ float red[2][32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
+  // block = 8 columns x 128 row lanes (C = 64: 8 blocks, ~9 partial rows per lane), then a fixed pairwise tree in shared
+  // memory: the result depends on n_partials only, never on the arrival order of the producers
+  __shared__ float red[2][128][9];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + tx;
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  float a = 0.f, b = 0.f;
   if (c < C) {
-    int r = ty;
-    for (; r + 96 < n_partials; r += 128) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        a[q] += stats[(size_t)(r + 32 * q) * 2 * C + c];
-        b[q] += stats[(size_t)(r + 32 * q) * 2 * C + C + c];
-      }
-    }
-    for (int q = 0; r < n_partials; r += 32, ++q) {
-      a[q] += stats[(size_t)r * 2 * C + c];
-      b[q] += stats[(size_t)r * 2 * C + C + c];
+    for (int r = ty; r < n_partials; r += 128) {
+      a += stats[(size_t)r * 2 * C + c];
+      b += stats[(size_t)r * 2 * C + C + c];
     }
   }
-  red[0][ty][tx] = (a[0] + a[1]) + (a[2] + a[3]);
-  red[1][ty][tx] = (b[0] + b[1]) + (b[2] + b[3]);
+  red[0][ty][tx] = a;
+  red[1][ty][tx] = b;
   __syncthreads();
-  if (ty != 0 || c >= C) return;
-  double s1 = 0., s2 = 0.;
 #pragma unroll
-  for (int q = 0; q < 32; ++q) {
-    s1 += (double)red[0][q][tx];
-    s2 += (double)red[1][q][tx];
+  for (int s = 64; s > 0; s >>= 1) {
+    if (ty < s) {
+      red[0][ty][tx] += red[0][ty + s][tx];
+      red[1][ty][tx] += red[1][ty + s][tx];
+    }
+    __syncthreads();
   }
+  if (ty != 0 || c >= C) return;
+  const double s1 = (double)red[0][0][tx], s2 = (double)red[1][0][tx];
   double n = (double)n_rows;
   double mean = s1 / n;
   double var = s2 / n - mean * mean;
@@ -308,7 +305,7 @@ extern "C" int sbr_bn_finalize(const float* stats, int n_partials, int64_t n_row
                                float* mean_invstd, float* running_mean, float* running_var,
                                int64_t* num_batches_tracked, void* stream) {
   SBR_REQUIRE(stats && mean_invstd && n_rows > 0 && C > 0 && n_partials >= 1, "sbr_bn_finalize: bad arguments");
-  SBR_CHECK_CUDA(sbr_launch(bn_finalize_kernel, dim3(cdiv(C, 32)), dim3(1024), (size_t)0, S(stream), stats, n_partials,
+  SBR_CHECK_CUDA(sbr_launch(bn_finalize_kernel, dim3(cdiv(C, 8)), dim3(1024), (size_t)0, S(stream), stats, n_partials,
                             n_rows, C, eps, momentum, mean_invstd, running_mean, running_var, num_batches_tracked));
   return SBR_OK;
 }

@@ -91,26 +91,77 @@ __global__ void sample_modalities_kernel(uint8_t* __restrict__ mods, int64_t n_r
 
 __global__ void tick_kernel(int64_t* c) { *c += 1; }
 
+// start of a train step in one launch: bump the step counters and clear the step's accumulator arena
+__global__ void step_begin_kernel(int64_t* c0, int64_t* c1, uint4* zero, int64_t n16) {
+  SBR_PDL_ENTRY();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (c0) *c0 += 1;
+    if (c1) *c1 += 1;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+    zero[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ------------------------------------------------------------------------------------------------ Adam / AdamW
 constexpr int ADAM_CHUNK = 4096;
-__global__ void adam_kernel(const sbr_adam_tensor_t* __restrict__ tensors, const int32_t* __restrict__ chunk_to_tensor,
-                            const int64_t* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps,
-                            float wd, int decoupled, const int64_t* __restrict__ step_dev, float grad_scale) {
+__device__ __forceinline__ void adam_update(float& p, float& g, float& m, float& v, float grad_scale, float lr, float wd,
+                                            int decoupled, float beta1, float beta2, float step_size, float bc2_sqrt,
+                                            float eps) {
+  g *= grad_scale;
+  if (decoupled) p *= (1.f - lr * wd);
+  else g += wd * p;
+  m = beta1 * m + (1.f - beta1) * g;
+  v = beta2 * v + (1.f - beta2) * g * g;
+  p -= step_size * m / (sqrtf(v) / bc2_sqrt + eps);
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(const sbr_adam_tensor_t* __restrict__ tensors, const int32_t* __restrict__ chunk_to_tensor,
+            const int64_t* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps, float wd,
+            int decoupled, const int64_t* __restrict__ step_dev, float grad_scale) {
   SBR_PDL_ENTRY();
-  SBR_PDL_ENTRY();
+  // bias corrections: double-precision pow once per block (every thread doing it cost more than the update itself)
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double step = (double)*step_dev;
+    s_bc[0] = (float)(1.0 - pow((double)beta1, step));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, step));
+  }
   const sbr_adam_tensor_t t = tensors[chunk_to_tensor[blockIdx.x]];
   const int64_t off = chunk_offset[blockIdx.x];
-  const double step = (double)*step_dev;
-  const float bc1 = (float)(1.0 - pow((double)beta1, step));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
-  const float step_size = lr / bc1;
-  for (int64_t i = off + threadIdx.x; i < min(off + (int64_t)ADAM_CHUNK, t.numel); i += blockDim.x) {
-    float p = t.param[i], g = t.grad[i] * grad_scale, m = t.exp_avg[i], v = t.exp_avg_sq[i];
-    if (decoupled) p *= (1.f - lr * wd);
-    else g += wd * p;
-    m = beta1 * m + (1.f - beta1) * g;
-    v = beta2 * v + (1.f - beta2) * g * g;
-    p -= step_size * m / (sqrtf(v) / bc2_sqrt + eps);
+  const int64_t end = min(off + (int64_t)ADAM_CHUNK, t.numel);
+  __syncthreads();
+  const float bc2_sqrt = s_bc[1];
+  const float step_size = lr / s_bc[0];
+  const auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+  const bool vec = (t.numel & 3) == 0 && (off & 3) == 0 && al(t.param, 16) && al(t.grad, 16) && al(t.exp_avg, 16) &&
+                   al(t.exp_avg_sq, 16) &&
+                   (t.shadow_bf16 == nullptr || ((t.cols & 3) == 0 && (t.shadow_ld & 3) == 0 && al(t.shadow_bf16, 8)));
+  if (vec) {
+    for (int64_t i = off + 4 * (int64_t)threadIdx.x; i < end; i += 4 * (int64_t)blockDim.x) {
+      float4 p4 = *reinterpret_cast<const float4*>(t.param + i), g4 = *reinterpret_cast<const float4*>(t.grad + i);
+      float4 m4 = *reinterpret_cast<const float4*>(t.exp_avg + i), v4 = *reinterpret_cast<const float4*>(t.exp_avg_sq + i);
+      adam_update(p4.x, g4.x, m4.x, v4.x, grad_scale, lr, wd, decoupled, beta1, beta2, step_size, bc2_sqrt, eps);
+      adam_update(p4.y, g4.y, m4.y, v4.y, grad_scale, lr, wd, decoupled, beta1, beta2, step_size, bc2_sqrt, eps);
+      adam_update(p4.z, g4.z, m4.z, v4.z, grad_scale, lr, wd, decoupled, beta1, beta2, step_size, bc2_sqrt, eps);
+      adam_update(p4.w, g4.w, m4.w, v4.w, grad_scale, lr, wd, decoupled, beta1, beta2, step_size, bc2_sqrt, eps);
+      *reinterpret_cast<float4*>(t.param + i) = p4;
+      *reinterpret_cast<float4*>(t.exp_avg + i) = m4;
+      *reinterpret_cast<float4*>(t.exp_avg_sq + i) = v4;
+      *reinterpret_cast<float4*>(t.grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t.shadow_bf16) {
+        const int64_t r = i / t.cols, c = i - r * t.cols;  // 4 consecutive elements stay inside one row (cols % 4 == 0)
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(p4.x, p4.y);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(p4.z, p4.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(t.shadow_bf16) + r * t.shadow_ld + c) = o;
+      }
+    }
+    return;
+  }
+  for (int64_t i = off + threadIdx.x; i < end; i += blockDim.x) {
+    float p = t.param[i], g = t.grad[i], m = t.exp_avg[i], v = t.exp_avg_sq[i];
+    adam_update(p, g, m, v, grad_scale, lr, wd, decoupled, beta1, beta2, step_size, bc2_sqrt, eps);
     t.param[i] = p;
     t.exp_avg[i] = m;
     t.exp_avg_sq[i] = v;
@@ -265,6 +316,20 @@ extern "C" int sbr_sample_modalities(uint8_t* mods, int64_t n_rows, int k, int n
               n_mods);
   SBR_REQUIRE(central < n_mods, "sbr_sample_modalities: central modality out of range");
   SBR_CHECK_CUDA(sbr_launch(sample_modalities_kernel, dim3(cdiv(n_rows, 256)), dim3(256), (size_t)(0), S(stream), mods, n_rows, k, n_mods, central, seed, step_dev));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_step_begin(int64_t* counter0, int64_t* counter1, void* zero, int64_t zero_bytes, void* stream) {
+  SBR_REQUIRE(zero_bytes >= 0 && (zero_bytes & 15) == 0 && (zero_bytes == 0 || zero != nullptr) &&
+                  (reinterpret_cast<uintptr_t>(zero) & 15) == 0,
+              "sbr_step_begin: the cleared range must be 16-byte aligned and sized");
+  const int64_t n16 = zero_bytes / 16;
+  int64_t blocks = (n16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > sbr_num_sms()) blocks = sbr_num_sms();
+  SBR_CHECK_CUDA(sbr_launch(step_begin_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, S(stream), counter0, counter1,
+                            reinterpret_cast<uint4*>(zero), n16));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

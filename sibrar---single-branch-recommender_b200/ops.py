@@ -137,6 +137,11 @@ def tick(counter):
     call("sbr_tick", ptr(counter), stream_ptr())
 
 
+def step_begin(counter0, counter1, zero_buf, zero_bytes):
+    """counters += 1 and the first ``zero_bytes`` of ``zero_buf`` cleared, in one launch"""
+    call("sbr_step_begin", ptr(counter0), ptr(counter1), ptr(zero_buf), int(zero_bytes), stream_ptr())
+
+
 def make_modality_srcs(entries, device) -> torch.Tensor:
     """entries: list of dict(kind, remap, table, grad, codes, max_tags, pad_id) -> uint8 device blob of
     ``sbr_modality_src_t[n]``"""

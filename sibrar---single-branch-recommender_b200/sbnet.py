@@ -142,9 +142,16 @@ class ZeroArena:
     def __init__(self, device, nbytes: int = 1 << 20):
         self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         self.off = 0
+        self.high = 0  # everything ever handed out (= everything that can be non-zero) lies in [0, high)
 
     def reset(self):
         self.buf.zero_()
+        self.off = 0
+
+    def begin_step(self, counter0=None, counter1=None):
+        """``reset`` of the used part fused with the step-counter increments (one launch, sbr_step_begin)"""
+        nbytes = min(self.buf.numel(), max(4096, (self.high + 255) // 256 * 256))
+        ops.step_begin(counter0, counter1, self.buf, nbytes)
         self.off = 0
 
     def take(self, n: int, dtype=F32) -> torch.Tensor:
@@ -153,6 +160,7 @@ class ZeroArena:
         if start + size > self.buf.numel():
             raise RuntimeError("ZeroArena exhausted")
         self.off = start + size
+        self.high = max(self.high, self.off)
         return self.buf[start:start + size].view(dtype)
 
 

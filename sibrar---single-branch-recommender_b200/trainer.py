@@ -125,8 +125,8 @@ class FusedTrainer:
         mods, keep_masks = mods or {}, keep_masks or {}
         B, n = i_idxs.shape
         D = m.config.shared_common_dim
-        ops.tick(rt.step_dev)
-        rt.arena.reset()
+        # one launch: model step counter (+ Adam's t when this step updates) += 1, accumulator arena cleared
+        rt.arena.begin_step(rt.step_dev, self.opt_step_dev if apply_optimizer else None)
         ku, ki = self.user.k_train, self.item.k_train
         # entities that end in a BatchNorm leave it to the score/loss kernel (no normalised copy, no separate
         # BatchNorm-backward reduction) when there is one modality slot per entity and D fits the fused kernel
@@ -195,7 +195,7 @@ class FusedTrainer:
             self.user.backward(dEu, self.grads, final_bn_sums=bn_u["sums"] if bn_u else None)
             self._after_user_backward()
         if apply_optimizer:
-            self.optimizer_step()
+            self.optimizer_step(ticked=True)
         self.steps_accumulated += 1
 
     def _side_stream(self, device):
@@ -210,9 +210,10 @@ class FusedTrainer:
     def _after_user_backward(self):
         pass
 
-    def optimizer_step(self):
+    def optimizer_step(self, ticked: bool = False):
         b1, b2 = self.betas
-        ops.tick(self.opt_step_dev)  # Adam's t counts the updates of THIS optimizer state (device-side: graph-safe)
+        if not ticked:
+            ops.tick(self.opt_step_dev)  # Adam's t counts the updates of THIS optimizer state (device-side: graph-safe)
         self.adam.step(self.learn.lr, b1, b2, self.eps, self.learn.wd, self.learn.optimizer == "adamw",
                        self.opt_step_dev, self.grad_scale)
 

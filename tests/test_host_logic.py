@@ -102,7 +102,7 @@ def test_fused_step_and_eval_call_sequence(name, monkeypatch):
     stub.calls.clear()  # construction builds the feature store and the bf16 weight shadows
     tr.step(torch.from_numpy(u), torch.from_numpy(i))
     seq = stub.calls
-    assert seq[0] == "sbr_tick" and seq[-1] == "sbr_adam_step"
+    assert seq[0] == "sbr_step_begin" and seq[-1] == "sbr_adam_step" and "sbr_tick" not in seq
     score = "sbr_score_loss_bn" if "sbr_score_loss_bn" in seq else "sbr_score_loss"
     assert score in seq and "sbr_row_gather_fwd" in seq and "sbr_row_gather_bwd_segmented" in seq
     assert seq.index("sbr_gather_plan") < seq.index("sbr_row_gather_bwd_segmented")
