@@ -103,7 +103,7 @@ __global__ void step_begin_kernel(int64_t* c0, int64_t* c1, uint4* zero, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------ Adam / AdamW
-constexpr int ADAM_CHUNK = 4096;
+constexpr int ADAM_CHUNK = 1024;  // (ops.ADAM_CHUNK builds the chunk table)
 __device__ __forceinline__ void adam_update(float& p, float& g, float& m, float& v, float grad_scale, float lr, float wd,
                                             int decoupled, float beta1, float beta2, float step_size, float bc2_sqrt,
                                             float eps) {
@@ -254,6 +254,54 @@ splitk_reduce_kernel(const float* __restrict__ part, int n_splits, int64_t split
   }
 }
 
+// few partitions (the forward split-K of an 'interactions' table: 6-10 slices): a thread owns 4 consecutive elements
+// and walks the slices with independent 16-byte loads -- no shared memory, no barriers
+__global__ void __launch_bounds__(256)
+splitk_reduce_vec_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, int64_t ld_part,
+                         int64_t rows, int64_t cols, const float* __restrict__ bias, int act,
+                         float* __restrict__ out_f32, int64_t ld_f32, int accumulate, bf16* __restrict__ out_bf16,
+                         int64_t ld_bf16) {
+  SBR_PDL_ENTRY();
+  const int64_t c4n = cols >> 2, total4 = rows * c4n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4n, c = (i - r * c4n) * 4;
+    const float* p = part + r * ld_part + c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    int s = 0;
+    for (; s + 1 < n_splits; s += 2) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)s * split_stride));
+      const float4 y = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)(s + 1) * split_stride));
+      a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+      b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+    }
+    if (s < n_splits) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)s * split_stride));
+      a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+    }
+    float v[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+    if (bias) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias + c);
+      v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = act_fwd(act, v[j]);
+    if (out_f32) {
+      float4* d = reinterpret_cast<float4*>(out_f32 + r * ld_f32 + c);
+      if (accumulate) {
+        const float4 o = *d;
+        v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+      }
+      *d = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (out_bf16) {
+      uint2 o;
+      *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[0], v[1]);
+      *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[2], v[3]);
+      *reinterpret_cast<uint2*>(out_bf16 + r * ld_bf16 + c) = o;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int sbr_splitk_reduce(const float* partials, int n_splits, int64_t split_stride, int64_t ld_part,
@@ -262,6 +310,17 @@ extern "C" int sbr_splitk_reduce(const float* partials, int n_splits, int64_t sp
   SBR_REQUIRE(partials && n_splits >= 1 && rows > 0 && cols > 0 && (out_f32 || out_bf16),
               "sbr_splitk_reduce: bad arguments");
   const int64_t total = rows * cols;
+  const auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+  if (n_splits <= 32 && (cols & 3) == 0 && (ld_part & 3) == 0 && (split_stride & 3) == 0 && al(partials, 16) &&
+      (!bias || al(bias, 16)) && (!out_f32 || ((ld_f32 & 3) == 0 && al(out_f32, 16))) &&
+      (!out_bf16 || ((ld_bf16 & 3) == 0 && al(out_bf16, 8)))) {
+    const unsigned blocks = (unsigned)min((int64_t)sbr_num_sms() * 8, (total / 4 + 255) / 256);
+    SBR_CHECK_CUDA(sbr_launch(splitk_reduce_vec_kernel, dim3(blocks), dim3(256), (size_t)(0), S(stream), partials,
+                              n_splits, split_stride, ld_part, rows, cols, bias, act, out_f32, ld_f32, accumulate,
+                              reinterpret_cast<bf16*>(out_bf16), ld_bf16));
+    SBR_LAUNCH_CHECK();
+    return SBR_OK;
+  }
   const unsigned blocks = (unsigned)min((int64_t)sbr_num_sms() * 16, (total + 31) / 32);
   SBR_CHECK_CUDA(sbr_launch(splitk_reduce_kernel, dim3(blocks), dim3(256), (size_t)(0), S(stream), partials, n_splits, split_stride, ld_part, rows, cols, bias, act,
                                                       out_f32, ld_f32, accumulate,

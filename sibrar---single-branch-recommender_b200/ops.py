@@ -299,7 +299,7 @@ def aggregate(e, rows, k, D, agg_max, out_f32=None, out_bf16=None):
          out_bf16.stride(0) if out_bf16 is not None else 0, stream_ptr())
 
 
-ADAM_CHUNK = 4096
+ADAM_CHUNK = 1024  # elements per block of the Adam kernel (csrc/util.cu)
 
 
 class AdamPlan:
