@@ -42,8 +42,10 @@ def ml1m_model_conf(D=64):
 
 LEARN = dict(lr=1e-3, wd=1e-6, optimizer="adamw", rec_loss="bpr", loss_aggregator="mean")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of this workload's kernels
-# (profiles/r01_segreduce_ncu_raw.txt); keyed like CallProfiler._key
-NCU_DRAM_TRAFFIC = {("sbr_row_gather_bwd_segmented", 180224, 64): 49.25e6}
+# (profiles/r01_segreduce_ncu_raw.txt, profiles/r01_gemm_bits_ncu_raw.txt); keyed like CallProfiler._key
+NCU_DRAM_TRAFFIC = {("sbr_row_gather_bwd_segmented", 180224, 64): 49.25e6,
+                    # bit matrix + weights from DRAM; the fp32 K-partition slices stay in L2 for the reduce pass
+                    ("sbr_gemm_bits_bf16", 3706, 64, 6040, 10): 3.668e6}
 N_NEG = 10
 
 

@@ -46,7 +46,7 @@ static inline int sbr_num_sms() {
 typedef __nv_bfloat16 bf16;
 
 // ------------------------------------------------------------------------------------------------ launches
-// Programmatic dependent launch (opt-in, SBR_PDL=1): every kernel of the train step starts with SBR_PDL_ENTRY() -- it lets the NEXT kernel
+// Programmatic dependent launch (default on, SBR_PDL=0 disables): every kernel of the train step starts with SBR_PDL_ENTRY() -- it lets the NEXT kernel
 // of the stream be scheduled as soon as all CTAs of this one are running (its prologue / block dispatch overlaps our
 // tail) and then waits until the PREVIOUS kernel has completed and flushed its memory.  Nothing before the wait may
 // touch global memory.  Without the launch attribute (plain <<<>>> launches) both instructions are no-ops.
@@ -60,7 +60,9 @@ static inline int sbr_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SBR_PDL");
-    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;  // off by default: measured 3 % SLOWER under CUDA-graph replay
+    // on by default (SBR_PDL=0 disables): 3.6 % faster on the multi-branch step graph (0.339 -> 0.327 ms); it was 3 %
+    // slower on the earlier single-stream graph
+    v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
   return v;
 }

@@ -89,7 +89,10 @@ __global__ void sample_modalities_kernel(uint8_t* __restrict__ mods, int64_t n_r
   }
 }
 
-__global__ void tick_kernel(int64_t* c) { *c += 1; }
+__global__ void tick_kernel(int64_t* c) {
+  SBR_PDL_ENTRY();
+  *c += 1;
+}
 
 // start of a train step in one launch: bump the step counters and clear the step's accumulator arena
 __global__ void step_begin_kernel(int64_t* c0, int64_t* c1, uint4* zero, int64_t n16) {
