@@ -392,6 +392,9 @@ def main():
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
+    loss_host = torch.empty(tr.loss_acc.shape, dtype=tr.loss_acc.dtype).pin_memory()
+    loss_read = torch.cuda.Event()
+
     def stage(k):
         s_ = k % 2
         src = host_batches[k % len(host_batches)]
@@ -414,7 +417,9 @@ def main():
         consumed[k % 2].record()
         if k + 1 < args.steps:
             stage(k + 1)
-        _ = tr.loss_acc.cpu()  # device -> host read of the step's losses (sync)
+        loss_host.copy_(tr.loss_acc, non_blocking=True)  # device -> host read of the step's losses ...
+        loss_read.record()
+        loss_read.synchronize()                           # ... waited for before the next step is issued
     sync_all()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -478,7 +483,13 @@ def main():
         top = sorted(agg.items(), key=lambda kv: -kv[1][0])
         line["kernel_shares"] = [dict(kernel=str(k), share=round(v[0] / 3 / step_ms, 4), launches_per_step=v[1] / 3,
                                       avg_us=round(v[0] / v[1] * 1e3, 2)) for k, v in top[:8]]
-        for key, (ms, cnt) in top:
+        # dominant kernel = largest share among the calls with a roofline model; of two calls within 10 % of each other
+        # (the user- and the item-side projection GEMM trade places from run to run) the one with an ncu DRAM capture
+        modelled = [(k, v) for k, v in top if algorithmic_work(k) != (0.0, 0.0)]
+        if modelled:
+            near = [kv for kv in modelled if kv[1][0] >= 0.9 * modelled[0][1][0] and kv[0] in NCU_DRAM_TRAFFIC]
+            modelled = (near or modelled)[:1]
+        for key, (ms, cnt) in modelled:
             flops, nbytes = algorithmic_work(key)
             if flops == 0 and nbytes == 0:
                 continue
