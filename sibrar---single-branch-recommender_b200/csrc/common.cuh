@@ -56,6 +56,11 @@ typedef __nv_bfloat16 bf16;
     asm volatile("griddepcontrol.wait;" ::: "memory");                    \
   } while (0)
 
+// the two halves, for kernels with a real prologue (barrier / TMEM set-up, shared-memory clears): the prologue runs
+// while the previous kernel drains; only what follows SBR_PDL_WAIT() may touch memory the previous kernel wrote
+#define SBR_PDL_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define SBR_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
 static inline int sbr_pdl_enabled() {
   static int v = -1;
   if (v < 0) {

@@ -363,7 +363,7 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
                     const int32_t* __restrict__ sorted_keys, int C, int normalize, float p_drop, uint64_t seed,
                     const int64_t* __restrict__ step_dev, const uint8_t* __restrict__ keep_mask,
                     const float* __restrict__ dx, int64_t ld_dx, const uint8_t* __restrict__ keep_bits, int rpg) {
-  SBR_PDL_ENTRY();
+  SBR_PDL_LAUNCH();  // the shared-memory set-up below overlaps the previous kernel (srcs is a set-up-time constant)
   __shared__ SegShared sh;
   if (threadIdx.x == 0) {
     int used = 0;
@@ -380,6 +380,7 @@ seg_reduce_g_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, int
   }
   for (int i = threadIdx.x; i < SEG_SMEM_FLOATS; i += blockDim.x) sh.priv[i] = 0.f;
   __syncthreads();
+  SBR_PDL_WAIT();
 
   const int li = threadIdx.x % LPR;
   const int lane = threadIdx.x & 31;
@@ -503,12 +504,13 @@ template <int LPR, int NV>
 __global__ void __launch_bounds__(256)
 tag_bag_bwd_kernel(const int32_t* __restrict__ codes, int max_tags, int32_t pad_id, float* __restrict__ bag_grad,
                    int64_t n_rows, int C, float* __restrict__ grad_weight, int64_t n_weight_rows) {
-  SBR_PDL_ENTRY();
+  SBR_PDL_LAUNCH();
   __shared__ float priv[SEG_SMEM_FLOATS];
   const bool use_smem = n_weight_rows * C <= SEG_SMEM_FLOATS;
   const int n_priv = use_smem ? (int)(n_weight_rows * C) : 0;
   for (int i = threadIdx.x; i < n_priv; i += blockDim.x) priv[i] = 0.f;
   __syncthreads();
+  SBR_PDL_WAIT();
   const int li = threadIdx.x % LPR;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / LPR);
   for (int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR; r < n_rows; r += groups_total) {

@@ -110,7 +110,7 @@ struct Warps {
 template <int BN, bool A_BITS>
 __global__ void __launch_bounds__(Warps<A_BITS>::THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-  SBR_PDL_ENTRY();
+  SBR_PDL_LAUNCH();  // (the wait follows the barrier / TMEM set-up: the prologue overlaps the previous kernel's tail)
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -155,6 +155,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  SBR_PDL_WAIT();  // nothing above reads or writes global memory
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
