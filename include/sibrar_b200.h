@@ -296,6 +296,14 @@ int sbr_sample_batch(const int32_t* coo_user, const int32_t* coo_item, int64_t n
                      const int32_t* train_indices, const int32_t* items_in_split, int64_t n_items_in_split, int64_t B,
                      int n_neg, uint64_t seed, const int64_t* step_dev, int64_t* out_u, int64_t* out_i, void* stream);
 
+/* the same for ONE batch of a shuffled epoch (DataLoader(shuffle=True) over TrainRecDataset, data/dataset.py:380-396,
+ * train/trainer.py:204): slot b is interaction order[offset + b] (order: a permutation of [0, nnz) on the device), its
+ * n_neg negatives are drawn as above. */
+int sbr_sample_epoch_batch(const int32_t* coo_user, const int32_t* coo_item, int64_t nnz, const int64_t* order,
+                           int64_t offset, const int64_t* train_indptr, const int32_t* train_indices,
+                           const int32_t* items_in_split, int64_t n_items_in_split, int64_t B, int n_neg, uint64_t seed,
+                           const int64_t* step_dev, int64_t* out_u, int64_t* out_i, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,8 @@ _PROTOS = {
     "sbr_topk_merge": [c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp],
     "sbr_metrics_at_k": [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_i64, c_vp],
     "sbr_sample_batch": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_u64, c_vp, c_vp, c_vp, c_vp],
+    "sbr_sample_epoch_batch": [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_u64, c_vp,
+                               c_vp, c_vp, c_vp],
 }
 
 EXPORTS = sorted(list(_PROTOS) + ["sbr_last_error", "sbr_version"])

@@ -182,17 +182,22 @@ __global__ void sample_batch_kernel(const int32_t* __restrict__ coo_user, const 
                                     const int32_t* __restrict__ indices, const int32_t* __restrict__ items_in_split,
                                     int64_t n_items_in_split, int64_t B, int n_neg, uint64_t seed,
                                     const int64_t* __restrict__ step_dev, int64_t* __restrict__ out_u,
-                                    int64_t* __restrict__ out_i) {
+                                    int64_t* __restrict__ out_i, const int64_t* __restrict__ order, int64_t offset) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= B * (n_neg + 1)) return;
   const int64_t b = t / (n_neg + 1);
   const int j = (int)(t - b * (n_neg + 1));
   const uint64_t step = (uint64_t)*step_dev;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x6e656773u);
-  // the positive (and thereby the user) of slot b: same draw for every j of the slot
-  uint4 r0 = philox4x32(make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
-  uint64_t r64 = ((uint64_t)r0.x << 32) | r0.y;
-  int64_t e = (int64_t)__umul64hi(r64, (uint64_t)nnz);
+  int64_t e;
+  if (order != nullptr) {
+    e = order[offset + b];  // epoch order: slot b is the (offset + b)-th interaction of the shuffled epoch
+  } else {
+    // the positive (and thereby the user) of slot b: same draw for every j of the slot
+    uint4 r0 = philox4x32(make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)step, (uint32_t)(step >> 32)), key);
+    uint64_t r64 = ((uint64_t)r0.x << 32) | r0.y;
+    e = (int64_t)__umul64hi(r64, (uint64_t)nnz);
+  }
   const int32_t u = coo_user[e];
   if (j == 0) {
     out_u[b] = u;
@@ -425,7 +430,27 @@ extern "C" int sbr_sample_batch(const int32_t* coo_user, const int32_t* coo_item
   SBR_REQUIRE(nnz > 0 && n_items_in_split > 0 && B > 0 && n_neg >= 0, "sbr_sample_batch: bad sizes");
   sample_batch_kernel<<<cdiv(B * (n_neg + 1), 256), 256, 0, S(stream)>>>(coo_user, coo_item, nnz, train_indptr,
                                                                         train_indices, items_in_split, n_items_in_split,
-                                                                        B, n_neg, seed, step_dev, out_u, out_i);
+                                                                        B, n_neg, seed, step_dev, out_u, out_i,
+                                                                        (const int64_t*)nullptr, 0);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_sample_epoch_batch(const int32_t* coo_user, const int32_t* coo_item, int64_t nnz,
+                                      const int64_t* order, int64_t offset, const int64_t* train_indptr,
+                                      const int32_t* train_indices, const int32_t* items_in_split,
+                                      int64_t n_items_in_split, int64_t B, int n_neg, uint64_t seed,
+                                      const int64_t* step_dev, int64_t* out_u, int64_t* out_i, void* stream) {
+  SBR_REQUIRE(coo_user && coo_item && order && train_indptr && train_indices && items_in_split && out_u && out_i &&
+                  step_dev,
+              "sbr_sample_epoch_batch: null argument");
+  SBR_REQUIRE(nnz > 0 && n_items_in_split > 0 && B > 0 && n_neg >= 0 && offset >= 0 && offset + B <= nnz,
+              "sbr_sample_epoch_batch: bad sizes (offset=%lld B=%lld nnz=%lld)", (long long)offset, (long long)B,
+              (long long)nnz);
+  sample_batch_kernel<<<cdiv(B * (n_neg + 1), 256), 256, 0, S(stream)>>>(coo_user, coo_item, nnz, train_indptr,
+                                                                        train_indices, items_in_split, n_items_in_split,
+                                                                        B, n_neg, seed, step_dev, out_u, out_i, order,
+                                                                        offset);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

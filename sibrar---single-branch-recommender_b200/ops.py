@@ -394,3 +394,11 @@ def sample_batch(coo_user, coo_item, train_indptr, train_indices, items_in_split
     call("sbr_sample_batch", ptr(coo_user), ptr(coo_item), coo_user.numel(), ptr(train_indptr), ptr(train_indices),
          ptr(items_in_split), items_in_split.numel(), int(B), int(n_neg), int(seed), ptr(step_dev), ptr(out_u),
          ptr(out_i), stream_ptr())
+
+
+def sample_epoch_batch(coo_user, coo_item, order, offset, train_indptr, train_indices, items_in_split, B, n_neg, seed,
+                       step_dev, out_u, out_i):
+    """batch ``order[offset : offset + B]`` of a shuffled epoch + ``n_neg`` 'uniform_recbole' negatives per slot"""
+    call("sbr_sample_epoch_batch", ptr(coo_user), ptr(coo_item), coo_user.numel(), ptr(order), int(offset),
+         ptr(train_indptr), ptr(train_indices), ptr(items_in_split), items_in_split.numel(), int(B), int(n_neg),
+         int(seed), ptr(step_dev), ptr(out_u), ptr(out_i), stream_ptr())

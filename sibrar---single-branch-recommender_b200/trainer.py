@@ -233,3 +233,57 @@ class FusedTrainer:
             self.loss_acc.zero_()
             self.steps_accumulated = 0
         return out
+
+
+class DeviceBatchFeeder:
+    """Device-side replacement of ``NegativeSamplingDataLoader`` over ``TrainRecDataset`` (``data/dataloader.py:128-198``,
+    ``data/dataset.py:380-396``): every epoch visits each train interaction exactly once, in a fresh random order when
+    ``shuffle`` (the reference's ``DataLoader(shuffle=True)``), in batches of ``batch_size`` (the last one shorter);
+    each slot gets ``n_negative_samples`` 'uniform_recbole' negatives drawn by ``sbr_sample_epoch_batch``.  No host work
+    per batch: the COO arrays, the sorted train CSR and the epoch permutation live on the device.
+
+        feeder = DeviceBatchFeeder(train_dataset, batch_size=16384, device="cuda")
+        for epoch in range(n_epochs):
+            for u_idxs, i_idxs in feeder.epoch():        # int64 [b], int64 [b, 1 + n_neg], positive in column 0
+                trainer.step(u_idxs, i_idxs)
+    """
+
+    def __init__(self, dataset, batch_size: int, device, shuffle: bool = True, seed: int = 0,
+                 n_negative_samples: Optional[int] = None):
+        import numpy as np
+        strategy = getattr(dataset, "negative_sampling_strategy", "uniform_recbole")
+        if strategy not in {"uniform_recbole"}:
+            raise ValueError(f"sampling strategy {strategy} not supported for dataloader sampling!")
+        self.device = torch.device(device)
+        self.batch_size, self.shuffle, self.seed = int(batch_size), shuffle, int(seed)
+        self.n_neg = int(dataset.n_negative_samples if n_negative_samples is None else n_negative_samples)
+        coo = dataset.interaction_matrix
+        csr = dataset.user_sampling_matrix.tocsr()
+        csr.sort_indices()
+        n_choices, row_len = len(dataset.items_in_split), np.diff(csr.indptr)
+        if n_choices - int(row_len.max(initial=0)) < self.n_neg:
+            raise ValueError(f'Not enough values in the range to sample "{self.n_neg}" unique values.')
+        dev = lambda a, t: torch.from_numpy(np.ascontiguousarray(a).astype(t)).to(self.device)  # noqa: E731
+        self.coo_u, self.coo_i = dev(coo.row, np.int32), dev(coo.col, np.int32)
+        self.indptr, self.indices = dev(csr.indptr, np.int64), dev(csr.indices, np.int32)
+        self.items = dev(dataset.items_in_split, np.int32)
+        self.nnz = int(coo.nnz)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.gen = torch.Generator(device=self.device).manual_seed(self.seed)
+        self.epochs_done = 0
+
+    def __len__(self):
+        return -(-self.nnz // self.batch_size)
+
+    def epoch(self):
+        order = torch.randperm(self.nnz, device=self.device, generator=self.gen) if self.shuffle else \
+            torch.arange(self.nnz, device=self.device)
+        for off in range(0, self.nnz, self.batch_size):
+            b = min(self.batch_size, self.nnz - off)
+            u = torch.empty(b, dtype=torch.int64, device=self.device)
+            i = torch.empty((b, 1 + self.n_neg), dtype=torch.int64, device=self.device)
+            ops.tick(self.step_dev)
+            ops.sample_epoch_batch(self.coo_u, self.coo_i, order, off, self.indptr, self.indices, self.items, b,
+                                   self.n_neg, self.seed, self.step_dev, u, i)
+            yield u, i
+        self.epochs_done += 1

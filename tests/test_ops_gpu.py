@@ -531,3 +531,39 @@ def test_samplers():
     ops.sample_modalities(mods, 20000, 2, 4, 2, 5, step)
     mm = mods.view(-1, 2).cpu().numpy()
     assert (mm[:, 0] == 2).all() and (mm[:, 1] != 2).all()
+
+
+def test_device_batch_feeder_epoch_semantics():
+    """DeviceBatchFeeder: an epoch visits every train interaction exactly once (shuffled), the last batch is short,
+    negatives are items of the split that are not train positives of the slot's user, two epochs differ in order"""
+    from sibrar_b200.synthetic import SynCorpus
+    from sibrar_b200.trainer import DeviceBatchFeeder
+    train = SynCorpus("ml1m", "cold_start_item", seed=4, scale=0.05).dataset("train")
+    feeder = DeviceBatchFeeder(train, batch_size=1000, device=DEV, seed=3, n_negative_samples=5)
+    coo = train.interaction_matrix
+    csr = train.user_sampling_matrix.tocsr()
+    want_pairs = np.sort(coo.row.astype(np.int64) * train.n_items + coo.col.astype(np.int64))
+    in_split = np.zeros(train.n_items, dtype=bool)
+    in_split[train.items_in_split] = True
+    orders = []
+    for _ in range(2):
+        got_u, got_i, sizes = [], [], []
+        for u, i in feeder.epoch():
+            got_u.append(u.cpu().numpy())
+            got_i.append(i.cpu().numpy())
+            sizes.append(len(u))
+        assert len(sizes) == len(feeder) and all(s == 1000 for s in sizes[:-1]) and sizes[-1] == coo.nnz - 1000 * (len(sizes) - 1)
+        u, i = np.concatenate(got_u), np.concatenate(got_i)
+        assert np.array_equal(np.sort(u * train.n_items + i[:, 0]), want_pairs)  # each interaction exactly once
+        neg = i[:, 1:]
+        assert in_split[neg].all()
+        assert not np.asarray(csr[np.repeat(u, neg.shape[1]), neg.reshape(-1)]).any()  # never a train positive
+        # roughly uniform over the split's items: no item takes more than 5x its fair share
+        counts = np.bincount(neg.reshape(-1), minlength=train.n_items)[train.items_in_split]
+        assert counts.max() < 5 * neg.size / len(train.items_in_split) + 20
+        orders.append(u * train.n_items + i[:, 0])
+    assert not np.array_equal(orders[0], orders[1])
+    assert feeder.epochs_done == 2
+    with pytest.raises(ValueError):
+        train.negative_sampling_strategy = "popular"
+        DeviceBatchFeeder(train, batch_size=10, device=DEV)
