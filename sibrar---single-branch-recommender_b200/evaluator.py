@@ -196,9 +196,39 @@ def evaluate_recommender_algorithm(alg, eval_loader_or_dataset, evaluator: FullE
     dataset = getattr(eval_loader_or_dataset, "dataset", eval_loader_or_dataset)
     results = evaluator.evaluate(alg, dataset)
     if return_raw:
-        raw = {f"{name}@{k}": evaluator.raw[mi, ki].cpu().numpy()
-               for mi, name in enumerate(USER_METRICS)
-               for ki, k in enumerate(sorted(set(evaluator.config.top_k)))
-               if ki < evaluator.raw.shape[1]}
-        return results, raw
+        return results, _raw_metrics(evaluator)
     return results
+
+
+def _raw_metrics(evaluator: FullEvaluator) -> Dict[str, np.ndarray]:
+    return {f"{name}@{k}": evaluator.raw[mi, ki].cpu().numpy()
+            for mi, name in enumerate(USER_METRICS)
+            for ki, k in enumerate(sorted(set(evaluator.config.top_k)))
+            if ki < evaluator.raw.shape[1]}
+
+
+def gather_recommender_algorithm_results(alg, eval_loader_or_dataset, evaluator: FullEvaluator,
+                                         results_path: Optional[str] = None, device="cuda", verbose=False):
+    """``run_gather`` entry (``eval/eval.py:258-333``): the top-``max(top_k)`` logits and item positions of every user
+    of the split, the user indices, the targets and the (raw) metrics in one dict, optionally pickled.
+
+    Keys as in the reference: ``n_users, n_items, k, topk_item_indices [U, k]`` (column positions inside
+    ``items_in_split``, best first), ``topk_logits [U, k]``, ``user_indices [U]``, ``targets [nnz, 2]``, ``metrics``,
+    ``raw_metrics``.  Deviations: the logits are those of the bf16 scoring kernel; the first column of ``targets`` is
+    the user's position in ``users_in_split`` (the reference concatenates per-batch ``argwhere`` rows, i.e. positions
+    inside each evaluation batch); users with fewer than k unmasked items get ``(-inf, -1)`` in the tail."""
+    import pickle
+    dataset = getattr(eval_loader_or_dataset, "dataset", eval_loader_or_dataset)
+    metrics, (vals, idx) = evaluator.evaluate(alg, dataset, return_topk=True)
+    users = np.asarray(dataset.users_in_split)
+    labels = dataset.user_sampling_matrix[users][:, np.asarray(dataset.items_in_split)].tocoo()
+    order = np.lexsort((labels.col, labels.row))
+    out = dict(n_users=dataset.n_users_in_split, n_items=dataset.n_items_in_split, k=int(idx.shape[1]),
+               topk_item_indices=idx.cpu().numpy().astype(np.int64), topk_logits=vals.cpu().numpy(),
+               user_indices=users.astype(np.int64),
+               targets=np.stack([labels.row[order], labels.col[order]], axis=1).astype(np.int64),
+               metrics=metrics, raw_metrics=_raw_metrics(evaluator))
+    if results_path is not None:
+        with open(results_path, "wb") as fh:
+            pickle.dump(out, fh)
+    return out

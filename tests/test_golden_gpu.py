@@ -274,6 +274,42 @@ def test_graph_evaluator_equals_eager_across_weight_updates(name):
     assert len(set(seen)) > 1  # the weights (and the metrics) did move between evaluations
 
 
+def test_gather_results_are_consistent(tmp_path):
+    """``gather_recommender_algorithm_results`` (eval/eval.py:258-333): keys, shapes, top-k rows sorted best first,
+    no seen item among them, and the metrics recomputed on the host from (top-k, targets) equal the reported ones"""
+    import pickle
+    from sibrar_b200.evaluator import gather_recommender_algorithm_results
+    spec, g, corpus, model = _build("ml1m_small")
+    _load(model, state_dict_of(g, f"s{spec['steps'] - 1}/sd/"))
+    model.to(DEV).eval()
+    val = corpus.dataset("val")
+    ev = FullEvaluator(dict(top_k=[1, 3, 5], metrics=["ndcg", "recall", "hitrate"], calculate_std=False))
+    path = str(tmp_path / "gather.pkl")
+    res = gather_recommender_algorithm_results(model, val, ev, results_path=path)
+    assert set(res) == {"n_users", "n_items", "k", "topk_item_indices", "topk_logits", "user_indices", "targets",
+                        "metrics", "raw_metrics"}
+    U, k = val.n_users_in_split, 5
+    assert res["n_users"] == U and res["n_items"] == val.n_items_in_split and res["k"] == k
+    assert res["topk_item_indices"].shape == (U, k) and res["topk_logits"].shape == (U, k)
+    assert np.array_equal(res["user_indices"], val.users_in_split)
+    logits = res["topk_logits"]
+    assert np.all(logits[:, :-1] >= logits[:, 1:])
+    seen = val.exclude_data[val.users_in_split].toarray()
+    idx = res["topk_item_indices"]
+    valid = idx >= 0
+    assert not seen[np.repeat(np.arange(U), k)[valid.reshape(-1)], idx[valid]].any()
+    rel = np.zeros((U, val.n_items_in_split), dtype=bool)
+    rel[res["targets"][:, 0], res["targets"][:, 1]] = True
+    hits = np.where(valid, rel[np.arange(U)[:, None], np.maximum(idx, 0)], False)
+    recall3 = hits[:, :3].sum(1) / np.maximum(1, rel.sum(1))
+    assert np.allclose(res["raw_metrics"]["recall@3"], recall3, atol=1e-6)
+    assert res["metrics"]["recall@3"] == pytest.approx(recall3.mean(), abs=1e-6)
+    assert res["metrics"]["hitrate@5"] == pytest.approx(hits.any(1).mean(), abs=1e-6)
+    with open(path, "rb") as fh:
+        back = pickle.load(fh)
+    assert np.array_equal(back["topk_item_indices"], idx) and back["metrics"] == res["metrics"]
+
+
 def test_group_metrics_keys_and_values():
     """eval.calculate_group_metrics / user_group_features (eval/eval.py:106-119): per-group means of the per-user
     metric vectors, keys '{feature}_{label}/{metric}@{k}'"""
