@@ -59,6 +59,8 @@ def timeit(name, label, reps=10):
     print(f"{label:50s} median {t[len(t) // 2]:7.1f} us  min {t[0]:7.1f} us", flush=True)
 
 timeit("sbr_row_gather_fwd", "forward gather")
-for dbg in (0, 1, 8, 16):
-    os.environ.update(SBR_SEG_DEBUG=str(dbg))
-    timeit("sbr_row_gather_bwd_segmented", f"seg_reduce debug={dbg} (1: no flush, 8: no TAG flush, 16: no non-TAG flush)")
+for minb, bps in ((3, 3), (3, 4), (4, 4)):
+    for rpg in (8, 12, 0):
+        os.environ.update(SBR_SEG_MINB=str(minb), SBR_SEG_BPS=str(bps), SBR_SEG_RPG=str(rpg))
+        timeit("sbr_row_gather_bwd_segmented",
+               f"seg_reduce min blocks/SM={minb} blocks/SM={bps} rows/chunk={rpg or 'balanced'}")
