@@ -81,6 +81,18 @@ CASES = {
                                eval_modalities=["title_mpnet", "image_resnet"],
                                embedding_regularization_type="pairwise_single", regularization_weight=0.1)),
         rec_loss="sampled_softmax", optimizer="adamw", lr=1e-3, wd=1e-2, batch=12, n_neg=5, steps=2),
+    # tanh everywhere (activation + activation-gradient epilogues other than ReLU), input dropout AND L2 normalisation on
+    # both entities, a hidden layer inside a modality projection, an Embedding modality next to tags, Adam without decay
+    "tanh_dropout_norm": dict(
+        corpus=dict(shape="ml1m", split_type="cold_start_item", seed=13, scale=0.03, vector_dim_cap=16),
+        model=dict(shared_common_dim=16,
+                   user=entity([("interactions", [12]), ("gender", []), ("occupation", [])], [16], 16,
+                               activation_fn="tanh", single_branch_input_dropout=0.3,
+                               normalize_single_branch_input=True),
+                   item=entity([("interactions", []), ("genres", []), ("plot_mpnet", []), ("item_embedding", [])],
+                               [16, 16], 16, activation_fn="tanh", single_branch_input_dropout=0.1,
+                               normalize_single_branch_input=True)),
+        rec_loss="bce", optimizer="adam", lr=3e-3, wd=0.0, batch=24, n_neg=3, steps=3),
 }
 
 
