@@ -2,7 +2,7 @@
 
 Run in the build container (needs ``/root/reference``):  ``python -m oracle.make_disk_golden``.
 
-Writes two tiny preprocessed datasets in the reference's on-disk format (``data/data_preprocessing_utils.py:391-416``:
+Writes three tiny preprocessed datasets (item cold start, random split, user cold start) in the reference's on-disk format (``data/data_preprocessing_utils.py:391-416``:
 ``user_idxs.csv``, ``item_idxs.csv``, ``listening_history_{split}.csv``, ``{entity}_features_{split}.csv``,
 ``{entity}_{feature}_{split}.npz``, ``used_config.yaml``) under ``tests/golden/disk_<case>/`` and loads every split
 with the UNMODIFIED reference classes (``data/dataset.py``: ``TrainRecDataset`` for train, ``FullEvalDataset`` for
@@ -32,7 +32,8 @@ USER_FEATURES = [dict(name="gender", type="categorical"), dict(name="age", type=
 ITEM_FEATURES = [dict(name="genres", type="tag", tag_split_sep="|"), dict(name="year", type="continuous"),
                  dict(name="studio", type="categorical"), dict(name="plot", type="vector")]
 CASES = {"cs_item": dict(cold_start="item", seed=11, n_users=37, n_items=29),
-         "random": dict(cold_start=None, seed=12, n_users=23, n_items=31)}
+         "random": dict(cold_start=None, seed=12, n_users=23, n_items=31),
+         "cs_user": dict(cold_start="user", seed=14, n_users=41, n_items=19)}
 
 
 def write_case(name: str, spec: dict) -> str:
@@ -48,13 +49,14 @@ def write_case(name: str, spec: dict) -> str:
     # interactions: every user 4..9 distinct items (plus one DUPLICATED train row: the reference sums duplicates)
     pairs = [(u, int(i)) for u in range(U) for i in rng.choice(I, size=int(rng.integers(4, 10)), replace=False)]
     pairs = np.array(pairs)
-    if spec["cold_start"] == "item":
-        perm = rng.permutation(I)
-        owner = np.empty(I, dtype=int)
-        owner[perm[:int(0.6 * I)]] = 0
-        owner[perm[int(0.6 * I):int(0.8 * I)]] = 1
-        owner[perm[int(0.8 * I):]] = 2
-        part = owner[pairs[:, 1]]
+    if spec["cold_start"] in ("item", "user"):
+        n_ent, col = (I, 1) if spec["cold_start"] == "item" else (U, 0)
+        perm = rng.permutation(n_ent)
+        owner = np.empty(n_ent, dtype=int)
+        owner[perm[:int(0.6 * n_ent)]] = 0
+        owner[perm[int(0.6 * n_ent):int(0.8 * n_ent)]] = 1
+        owner[perm[int(0.8 * n_ent):]] = 2
+        part = owner[pairs[:, col]]
     else:
         part = rng.choice(3, size=len(pairs), p=[0.7, 0.15, 0.15])
     splits = {s: pairs[part == k] for k, s in enumerate(("train", "val", "test"))}

@@ -24,7 +24,7 @@ def _csr_equal(m, g, prefix):
     assert np.array_equal(np.asarray(m.data).astype(np.int64), g[prefix + "data"])
 
 
-@pytest.mark.parametrize("case", ["cs_item", "random"])
+@pytest.mark.parametrize("case", ["cs_item", "random", "cs_user"])
 @pytest.mark.parametrize("split", ["train", "val", "test"])
 def test_loader_matches_reference_dataset(case, split):
     g = np.load(os.path.join(GOLDEN, f"disk_{case}_expected.npz"))
