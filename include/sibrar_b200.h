@@ -96,16 +96,20 @@ int sbr_transpose_f32_to_bf16(const float* src, int64_t ld_src, void* dst, int64
                               void* stream); /* dst[c, r] = src[r, c] */
 int sbr_transpose_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int64_t cols,
                       void* stream);
-int sbr_csr_to_dense_bf16(const int64_t* indptr, const int32_t* indices, int64_t rows, int64_t cols, void* dst,
-                          int64_t ld_dst, void* stream); /* multi-hot rows (data/Feature.py:147-150) */
+int sbr_csr_to_dense_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows, int64_t cols,
+                          void* dst, int64_t ld_dst, void* stream); /* csr rows -> dense (data/Feature.py:147-150);
+                                                                       vals == NULL: all stored entries are 1 */
 
 /* ------------------------------------------------------------------------------------------------ sparse 'interactions'
- * out[r, :] = act(sum_{j in csr[r]} Wt[j, :] + bias)  -- Linear over a multi-hot row without densifying it
- * (replaces data/Feature.py:147-150 + algorithms/sgd_alg.py:1380).  Wt is the TRANSPOSED weight [d, C] fp32.
+ * out[r, :] = act(sum_{p in csr[r]} vals[p] * Wt[indices[p], :] + bias)  -- Linear over a sparse row without densifying
+ * it (replaces data/Feature.py:147-150 + algorithms/sgd_alg.py:1380).  Wt is the TRANSPOSED weight [d, C] fp32;
+ * vals == NULL means all stored entries are 1 (duplicate history rows give counts > 1 in the reference's matrices).
  * With bias == NULL and act == NONE the same kernel is the wgrad of that Linear through the transposed CSR:
- * dWt[j, :] = sum_{r in csrT[j]} dPre[r, :]. */
-int sbr_spmm_csr(const int64_t* indptr, const int32_t* indices, int64_t rows, const float* dense, int64_t ld_dense,
-                 int64_t C, const float* bias, int act, float* out, int64_t ld_out, int transpose_out, void* stream);
+ * dW[:, j] (+)= sum_{p in csrT[j]} valsT[p] * dPre[indicesT[p], :]  (transpose_out = 1: out is [C, rows];
+ * accumulate = 1: out += result, like every other wgrad of the path).  out_bf16: optional bf16 copy of the result. */
+int sbr_spmm_csr(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows, const float* dense,
+                 int64_t ld_dense, int64_t C, const float* bias, int act, float* out, int64_t ld_out, int transpose_out,
+                 int accumulate, void* out_bf16, int64_t ld_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ modality sampling
  * Per (row, slot) choose k distinct modalities out of n_mods (optionally slot 0 fixed to `central`), Philox keyed
@@ -262,7 +266,10 @@ typedef struct {
 int sbr_adam_step(const sbr_adam_tensor_t* tensors_dev, int n_tensors, int64_t total_chunks,
                   const int32_t* chunk_to_tensor_dev, const int64_t* chunk_offset_dev, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int decoupled, const int64_t* step_dev,
-                  float grad_scale, void* stream); /* *step_dev = 1-based index of the step being applied */
+                  float grad_scale, void* stream); /* *step_dev = 1-based index of the step being applied;
+                                                      decoupled: 0 = Adam (L2 folded into the gradient), 1 = AdamW,
+                                                      2 = Adagrad (torch.optim.Adagrad defaults; exp_avg_sq holds the
+                                                      running sum of squares, exp_avg is left untouched) */
 
 /* ------------------------------------------------------------------------------------------------ evaluation
  * Fused  scores = U * I^T  (bf16 tcgen05 GEMM, fp32 accumulate)  ->  seen-item mask (-inf)  ->  per-user top-k.

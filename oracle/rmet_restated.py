@@ -1,8 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the third-party ``rmet`` package used by the reference.
 
-PARITY UNPINNED: ``rmet`` (git+https://github.com/tigxy/recommender-metrics.git, unpinned HEAD, reference
-``environment.yml:40``) is not vendored in the reference tree and is not installable here (no network).  The
-reference holds no golden vectors for it.  This file restates its published behaviour, anchored on
+``rmet`` (git+https://github.com/tigxy/recommender-metrics.git, unpinned HEAD, reference ``environment.yml:40``) is not
+vendored in the reference tree and is not installable here (no network).  PINNING STATUS:
+  * ndcg / recall / precision are PINNED against code the reference itself holds: ``oracle/make_metrics_golden.py`` runs
+    the unmodified ``eval/metrics.py:4-105`` and ``tests/test_oracle_vs_golden.py::
+    test_metric_restatement_pinned_against_reference_metrics`` compares this file with its per-user vectors;
+  * f_score / hitrate / ap / rr / coverage stay PARITY UNPINNED (no statement of them exists in the reference tree;
+    standard definitions, listed at the end of this docstring).
+This file restates the package's behaviour, anchored on
 
 * the reference's call sites ``eval/eval.py:99-102`` (overall metrics + top-k indices), ``:115-118`` (group
   metrics), ``:141-144`` (distribution metrics from stored top-k), the key contract ``'{metric}@{k}'`` with an

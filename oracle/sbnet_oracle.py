@@ -523,6 +523,17 @@ def adam_step(p, grads, state, lr, wd, step, decoupled=True, betas=(0.9, 0.999),
         p[k] = w
 
 
+def adagrad_step(p, grads, state, lr, wd, eps=1e-10):
+    """torch.optim.Adagrad with its defaults (lr_decay 0, initial accumulator 0), as built by ``train/trainer.py:62-68``:
+    coupled weight decay, ``sum += g^2``, ``w -= lr * g / (sqrt(sum) + eps)``.  In place on ``p`` / ``state``."""
+    for k, g in grads.items():
+        w = p[k].astype(F64)
+        g = g.astype(F64) + wd * w
+        acc = state.setdefault("sum/" + k, np.zeros_like(w))
+        acc[:] = acc + g * g
+        p[k] = w - lr * g / (np.sqrt(acc) + eps)
+
+
 # ------------------------------------------------------------------------------------------------ evaluation
 def masked_topk(u_repr, i_repr, exclude_csr, k):
     """scores = u @ i.T, seen -> -inf (eval/eval.py:217-220), top-k with ties broken by LOWEST index.

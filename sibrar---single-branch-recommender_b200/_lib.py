@@ -49,8 +49,9 @@ _PROTOS = {
     "sbr_cast_f32_to_bf16": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "sbr_transpose_f32_to_bf16": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "sbr_transpose_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
-    "sbr_csr_to_dense_bf16": [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp],
-    "sbr_spmm_csr": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, c_vp],
+    "sbr_csr_to_dense_bf16": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp],
+    "sbr_spmm_csr": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int, c_vp,
+                     c_i64, c_vp],
     "sbr_sample_modalities": [c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_u64, c_vp, c_vp],
     "sbr_tick": [c_vp, c_vp],
     "sbr_step_begin": [c_vp, c_vp, c_vp, c_i64, c_vp],

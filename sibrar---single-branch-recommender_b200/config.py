@@ -127,7 +127,7 @@ class LearningConfig:
     max_batches_per_epoch: Optional[int] = None
     lr: float = 1e-3
     wd: float = 0.0
-    optimizer: str = "adam"          # adam | adamw  (adagrad: not on the B200 path)
+    optimizer: str = "adam"          # adam | adamw | adagrad  (train/trainer.py:62-66)
     optimizing_metric: str = "ndcg@10"
     rec_loss: str = "bce"            # bce | bpr | sampled_softmax
     loss_aggregator: str = "mean"    # mean | sum

@@ -50,7 +50,8 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, int64_t ld_
 }
 
 __global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                    int64_t rows, int64_t cols, bf16* __restrict__ dst, int64_t ld_dst) {
+                                    const float* __restrict__ vals, int64_t rows, int64_t cols, bf16* __restrict__ dst,
+                                    int64_t ld_dst) {
   int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   int lane = threadIdx.x & 31;
@@ -60,7 +61,7 @@ __global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr, const in
   __syncwarp();
   for (int64_t p = indptr[row] + lane; p < indptr[row + 1]; p += 32) {
     int32_t c = indices[p];
-    if (c >= 0 && c < cols) d[c] = one;
+    if (c >= 0 && c < cols) d[c] = vals ? __float2bfloat16(vals[p]) : one;
   }
 }
 
@@ -111,6 +112,14 @@ __device__ __forceinline__ void adam_update(float& p, float& g, float& m, float&
                                             int decoupled, float beta1, float beta2, float step_size, float bc2_sqrt,
                                             float eps) {
   g *= grad_scale;
+  if (decoupled == 2) {
+    // torch.optim.Adagrad (train/trainer.py:62-66; lr_decay = 0, initial accumulator 0): coupled weight decay,
+    // v = running sum of squared gradients, no first moment
+    g += wd * p;
+    v += g * g;
+    p -= lr * g / (sqrtf(v) + eps);
+    return;
+  }
   if (decoupled) p *= (1.f - lr * wd);
   else g += wd * p;
   m = beta1 * m + (1.f - beta1) * g;
@@ -206,17 +215,32 @@ __global__ void sample_batch_kernel(const int32_t* __restrict__ coo_user, const 
   }
   const int64_t beg = indptr[u], end = indptr[u + 1];
   int32_t cand = 0;
-  for (int attempt = 0; attempt < 64; ++attempt) {
-    uint4 r = philox4x32(make_uint4((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)step, 0x80000000u + attempt), key);
-    uint64_t q = ((uint64_t)r.x << 32) | r.y;
-    cand = items_in_split[(int64_t)__umul64hi(q, (uint64_t)n_items_in_split)];
-    int64_t lo = beg, hi = end;  // binary search in the sorted positives of u
+  int64_t pos = 0;
+  bool found = false;
+  const auto is_positive = [&](int32_t c) {  // binary search in the sorted positives of u
+    int64_t lo = beg, hi = end;
     while (lo < hi) {
       int64_t mid = (lo + hi) >> 1;
-      if (indices[mid] < cand) lo = mid + 1;
+      if (indices[mid] < c) lo = mid + 1;
       else hi = mid;
     }
-    if (!(lo < end && indices[lo] == cand)) break;
+    return lo < end && indices[lo] == c;
+  };
+  for (int attempt = 0; attempt < 64 && !found; ++attempt) {
+    uint4 r = philox4x32(make_uint4((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)step, 0x80000000u + attempt), key);
+    uint64_t q = ((uint64_t)r.x << 32) | r.y;
+    pos = (int64_t)__umul64hi(q, (uint64_t)n_items_in_split);
+    cand = items_in_split[pos];
+    found = !is_positive(cand);
+  }
+  // 64 rejected draws (a user who interacted with almost every item of the split): the reference keeps re-drawing
+  // (data/dataloader.py:180-191); here the walk continues from the last draw to the next item that is NOT a positive,
+  // so a positive is never emitted as a negative (the host checked that such an item exists)
+  for (int64_t probe = 1; !found && probe < n_items_in_split; ++probe) {
+    int64_t q = pos + probe;
+    if (q >= n_items_in_split) q -= n_items_in_split;
+    cand = items_in_split[q];
+    found = !is_positive(cand);
   }
   out_i[t] = cand;
 }
@@ -366,11 +390,11 @@ extern "C" int sbr_transpose_f32(const float* src, int64_t ld_src, float* dst, i
   return SBR_OK;
 }
 
-extern "C" int sbr_csr_to_dense_bf16(const int64_t* indptr, const int32_t* indices, int64_t rows, int64_t cols,
-                                     void* dst, int64_t ld_dst, void* stream) {
+extern "C" int sbr_csr_to_dense_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows,
+                                     int64_t cols, void* dst, int64_t ld_dst, void* stream) {
   SBR_REQUIRE(indptr && dst && rows > 0 && ld_dst >= cols, "sbr_csr_to_dense_bf16: bad arguments");
-  csr_to_dense_kernel<<<cdiv(rows, 8), 256, 0, S(stream)>>>(indptr, indices, rows, cols, reinterpret_cast<bf16*>(dst),
-                                                            ld_dst);
+  csr_to_dense_kernel<<<cdiv(rows, 8), 256, 0, S(stream)>>>(indptr, indices, vals, rows, cols,
+                                                            reinterpret_cast<bf16*>(dst), ld_dst);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

@@ -41,6 +41,7 @@ class DeviceFeature:
             remap[idx] = np.arange(len(idx), dtype=np.int32)
             self.remap = torch.from_numpy(remap).to(device)
         self.x16 = self.csr = self.csr_t = self.codes = self.bits = self.bits_t = None
+        self.csr_vals = self.csr_t_vals = None
         self.max_tags, self.pad_id, self.n_cat = 0, -1, 0
         if self.type == "categorical":
             self.kind = "categorical"
@@ -64,6 +65,9 @@ class DeviceFeature:
             ip = torch.from_numpy(m.indptr.astype(np.int64)).to(device)
             ix = torch.from_numpy(m.indices.astype(np.int32)).to(device)
             binary = m.nnz == 0 or bool(np.all(m.data == 1))
+            # the reference feeds the stored values (``csr[rows].toarray().float()``, data/Feature.py:147-150): duplicate
+            # history rows are counts > 1 in its sampling matrices.  None = all ones (the bit-packed route needs that).
+            vals = None if binary else torch.from_numpy(m.data.astype(np.float32)).to(device)
             if density >= dense_min_density and binary and m.shape[0] * m.shape[1] // 4 <= dense_max_bytes:
                 # bit-packed multi-hot rows (and the transposed matrix for the wgrad), 1 bit per element in HBM:
                 # the projection is a tcgen05 GEMM whose A operand is expanded to bf16 in shared memory
@@ -73,7 +77,7 @@ class DeviceFeature:
             elif density >= dense_min_density and dense_bytes <= dense_max_bytes:
                 # dense bf16 multi-hot, resident in HBM: the projection becomes a tcgen05 GEMM
                 self.kind = "dense"
-                self.x16 = ops.csr_to_dense_bf16(ip, ix, m.shape[0], m.shape[1])
+                self.x16 = ops.csr_to_dense_bf16(ip, ix, m.shape[0], m.shape[1], vals)
             else:
                 self.kind = "csr"
                 mt = m.T.tocsr()
@@ -81,6 +85,8 @@ class DeviceFeature:
                 self.csr = (ip, ix)
                 self.csr_t = (torch.from_numpy(mt.indptr.astype(np.int64)).to(device),
                               torch.from_numpy(mt.indices.astype(np.int32)).to(device))
+                self.csr_vals = vals
+                self.csr_t_vals = None if binary else torch.from_numpy(mt.data.astype(np.float32)).to(device)
         else:
             self.kind = "dense"
             v = np.asarray(values, dtype=np.float32)

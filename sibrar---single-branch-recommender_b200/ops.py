@@ -117,15 +117,21 @@ def transpose_f32(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:
     return dst
 
 
-def csr_to_dense_bf16(indptr, indices, rows, cols) -> torch.Tensor:
+def csr_to_dense_bf16(indptr, indices, rows, cols, vals=None) -> torch.Tensor:
+    """``vals``: fp32 stored values (None: every stored entry is 1)"""
     dst = torch.empty((rows, pad8(cols)), dtype=BF16, device=indptr.device)
-    call("sbr_csr_to_dense_bf16", ptr(indptr), ptr(indices), rows, cols, ptr(dst), dst.stride(0), stream_ptr())
+    call("sbr_csr_to_dense_bf16", ptr(indptr), ptr(indices), ptr(vals), rows, cols, ptr(dst), dst.stride(0),
+         stream_ptr())
     return dst
 
 
-def spmm_csr(indptr, indices, rows, dense, C_, bias, act, out, transpose_out=False):
-    call("sbr_spmm_csr", ptr(indptr), ptr(indices), int(rows), ptr(dense), dense.stride(0), int(C_), ptr(bias),
-         _act(act), ptr(out), out.stride(0), int(transpose_out), stream_ptr())
+def spmm_csr(indptr, indices, rows, dense, C_, bias, act, out, transpose_out=False, vals=None, accumulate=False,
+             out_bf16=None):
+    """out[r] = act(sum_p vals[p] * dense[indices[p]] + bias); ``transpose_out``: out is [C, rows] (the wgrad through
+    the transposed CSR), ``accumulate``: out += result"""
+    call("sbr_spmm_csr", ptr(indptr), ptr(indices), ptr(vals), int(rows), ptr(dense), dense.stride(0), int(C_),
+         ptr(bias), _act(act), ptr(out), out.stride(0) if out is not None else 0, int(transpose_out),
+         int(bool(accumulate)), ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, stream_ptr())
 
 
 def sample_modalities(mods, n_rows, k, n_mods, central, seed, step_dev):

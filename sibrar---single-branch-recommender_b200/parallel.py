@@ -67,10 +67,12 @@ class DataParallelTrainer(FusedTrainer):
             dist.broadcast(b, src=0)
         super().__init__(model, learn, n_negative_samples, grad_scale=1.0 / self.world, **kw)
         self._work = []
+        # every rank draws its own modalities / dropout masks (the rank enters the Philox seeds)
+        self.rt.seed_salt = dist.get_rank()
 
     def _after_item_backward(self):
         lo, mid, _ = self.bucket_bounds
-        if mid <= lo:
+        if mid <= lo or not self._reduce_now:
             return
         if torch.cuda.is_current_stream_capturing():
             # inside the step's CUDA graph the collective is captured in stream order (the buckets are a few MB:
@@ -81,7 +83,7 @@ class DataParallelTrainer(FusedTrainer):
 
     def _after_user_backward(self):
         _, mid, hi = self.bucket_bounds
-        if hi > mid:
+        if hi > mid and self._reduce_now:
             if torch.cuda.is_current_stream_capturing():
                 dist.all_reduce(self.flat_grads[mid:hi], op=dist.ReduceOp.SUM)
             else:
@@ -89,6 +91,12 @@ class DataParallelTrainer(FusedTrainer):
         for w in self._work:
             w.wait()  # stream-level wait: no host synchronisation
         self._work.clear()
+
+
+    def optimizer_step(self, ticked: bool = False):
+        if not ticked:  # called on its own after accumulation steps: their rank-local sums are reduced here, once
+            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
+        super().optimizer_step(ticked)
 
 
 class ShardedEvaluator(FullEvaluator):

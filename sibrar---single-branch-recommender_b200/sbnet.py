@@ -230,8 +230,9 @@ class Chain:
                     y16 = torch.empty((rows, out_pad), dtype=BF16, device=dev)
                 if first_csr:
                     ip, ix = self.feature.csr
-                    ops.spmm_csr(ip, ix, rows, st.wt32, st.out_f, bias, st.act1, y32)
-                    if y16 is not None:
+                    ops.spmm_csr(ip, ix, rows, st.wt32, st.out_f, bias, st.act1, y32, vals=self.feature.csr_vals,
+                                 out_bf16=y16 if (y16 is not None and st.out_f % 8 == 0) else None)
+                    if y16 is not None and st.out_f % 8 != 0:
                         ops.cast_bf16(y32, y16)
                 else:
                     first_bits = si == 0 and self.bits_input
@@ -337,7 +338,9 @@ class Chain:
             # ---- wgrad: dW[out, in] += dz^T x   (contraction over the rows)
             if first_csr:
                 ip_t, ix_t = self.feature.csr_t
-                ops.spmm_csr(ip_t, ix_t, st.in_f, dz32, st.out_f, None, None, g_w, transpose_out=True)
+                # accumulates like every other wgrad of the path (gradient accumulation over micro-batches)
+                ops.spmm_csr(ip_t, ix_t, st.in_f, dz32, st.out_f, None, None, g_w, transpose_out=True,
+                             vals=self.feature.csr_t_vals, accumulate=True)
             else:
                 x16 = st.x if si > 0 or self.feature is None else self.feature.x16
                 tiles = -(-st.in_f // 128) * -(-st.out_f // (64 if st.out_f <= 64 else 128 if st.out_f <= 128 else 256))
@@ -703,7 +706,8 @@ class SingleBranchNetEntity(_EntityBase):
         central = -1
         if self.reg_type == EmbeddingRegularizationType.CentralModality:
             central = self.mod_names.index(self.entity_config.central_modality)
-        seed = (int(self.entity_config.sampling_seed) << 8) ^ (1 if self.entity_name == "user" else 2)
+        seed = (int(self.entity_config.sampling_seed) << 8) ^ (1 if self.entity_name == "user" else 2) ^ \
+            (int(rt.seed_salt) << 24)
         ops.sample_modalities(mods, n_idx, k, len(self.mod_names), central, seed, rt.step_dev)
         return mods
 
@@ -732,7 +736,8 @@ class SingleBranchNetEntity(_EntityBase):
         N = n_idx * k
         x0 = torch.empty((N, ops.pad8(C_)), dtype=BF16, device=dev)
         p_drop = cfg.single_branch_input_dropout if (training and cfg.single_branch_input_dropout) else 0.0
-        seed = (int(cfg.sampling_seed) << 8) ^ (0x11 if self.entity_name == "user" else 0x22)
+        seed = (int(cfg.sampling_seed) << 8) ^ (0x11 if self.entity_name == "user" else 0x22) ^ \
+            (int(rt.seed_salt) << 24)
         keep_bits = torch.empty((N, (C_ + 7) // 8), dtype=torch.uint8, device=dev) if (training and p_drop) else None
         ops.row_gather_fwd(srcs, len(self.mod_names), flat, mods, k, C_, cfg.normalize_single_branch_input, p_drop,
                            seed, rt.step_dev, keep_mask, out_bf16=x0, err_flag=rt.err_flag, keep_bits_out=keep_bits)
@@ -793,6 +798,7 @@ class _Runtime:
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=device)
         self.arena = ZeroArena(device)
         self.branches = False  # FusedTrainer: independent kernel chains of a step on parallel streams
+        self.seed_salt = 0     # data parallel: the rank, so that ranks draw different modalities / dropout masks
 
 
 class SingleBranchNet(nn.Module):

@@ -26,8 +26,8 @@ class FusedTrainer:
                  grad_scale: float = 1.0, cuda_graph: bool = False):
         if isinstance(learn, dict):
             learn = LearningConfig.from_dict(learn)
-        if learn.optimizer not in ("adam", "adamw"):
-            raise ValueError(f'optimizer "{learn.optimizer}" is not available on the B200 path (adam | adamw)')
+        if learn.optimizer not in ("adam", "adamw", "adagrad"):  # train/trainer.py:62-66
+            raise KeyError(learn.optimizer)
         if learn.rec_loss not in ("bpr", "bce", "sampled_softmax"):
             raise KeyError(learn.rec_loss)
         assert learn.loss_aggregator in ("mean", "sum"), "Type of Aggregator not yet defined"
@@ -123,6 +123,10 @@ class FusedTrainer:
     def _eager_step(self, u_idxs, i_idxs, mods, keep_masks, apply_optimizer):
         m, rt = self.model, self.rt
         mods, keep_masks = mods or {}, keep_masks or {}
+        # data parallel: the gradient buffers are all-reduced on the step that applies the optimizer only (accumulation
+        # steps keep rank-local sums: reducing the persistent buffer every step would count earlier micro-batches
+        # world-size times)
+        self._reduce_now = bool(apply_optimizer)
         B, n = i_idxs.shape
         D = m.config.shared_common_dim
         # one launch: model step counter (+ Adam's t when this step updates) += 1, accumulator arena cleared
@@ -214,8 +218,9 @@ class FusedTrainer:
         b1, b2 = self.betas
         if not ticked:
             ops.tick(self.opt_step_dev)  # Adam's t counts the updates of THIS optimizer state (device-side: graph-safe)
-        self.adam.step(self.learn.lr, b1, b2, self.eps, self.learn.wd, self.learn.optimizer == "adamw",
-                       self.opt_step_dev, self.grad_scale)
+        mode = {"adam": 0, "adamw": 1, "adagrad": 2}[self.learn.optimizer]
+        eps = 1e-10 if mode == 2 and self.eps == 1e-8 else self.eps  # torch.optim.Adagrad's default eps
+        self.adam.step(self.learn.lr, b1, b2, eps, self.learn.wd, mode, self.opt_step_dev, self.grad_scale)
 
     # ------------------------------------------------------------------------------------------------ logging
     def read_losses(self, reset: bool = True) -> Dict[str, float]:

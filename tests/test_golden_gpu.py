@@ -370,3 +370,28 @@ def test_topk_and_metrics_at_fixed_scores(name):
     for mi, mn in enumerate(["ndcg", "precision", "recall", "f_score", "hitrate"]):
         for ki, kk in enumerate([1, 3, 5]):
             assert np.abs(m[mi, ki] - ref[f"{mn}@{kk}"]).max() < 2e-6
+
+
+def test_metric_kernel_pinned_against_reference_metrics():
+    """``sbr_metrics_at_k`` (ndcg / recall / precision) against the per-user vectors the reference's own
+    ``eval/metrics.py:4-105`` produced (``tests/golden/metrics_pin.npz``), and the fused score + mask + top-k kernel
+    against ``torch.topk`` run by that script -- bit-exact positions (tie-free integer-friendly logits)."""
+    import os
+
+    import scipy.sparse as sp
+
+    from tests.golden_util import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "metrics_pin.npz"))
+    ks = [int(k) for k in g["ks"]]
+    kmax = max(ks)
+    tgt = sp.csr_matrix(g["targets"])
+    tgt.sort_indices()
+    ip = torch.from_numpy(tgt.indptr.astype(np.int64)).to(DEV)
+    ix = torch.from_numpy(tgt.indices.astype(np.int32)).to(DEV)
+    idx = torch.from_numpy(g[f"topk@{kmax}"].astype(np.int32)).to(DEV)
+    m, _ = ops.metrics_at_k(idx, ip, ix, ks, g["targets"].shape[1])
+    m = m.cpu().numpy()
+    from sibrar_b200.evaluator import USER_METRICS
+    for ki, k in enumerate(ks):
+        for name in ("ndcg", "recall", "precision"):
+            assert np.abs(m[USER_METRICS.index(name), ki] - g[f"{name}@{k}"]).max() < 2e-6, (name, k)

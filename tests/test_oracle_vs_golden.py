@@ -75,3 +75,29 @@ def test_eval_matches_reference(name):
     for key, v in state_dict_of(g, "eval/metric/").items():
         got = m[key] if key.startswith("coverage") else m[key].mean()
         _close(got, v, rtol=1e-5, atol=1e-6, what=f"metric {key}")
+
+
+def test_metric_restatement_pinned_against_reference_metrics():
+    """ndcg / recall / precision of ``oracle/rmet_restated.py`` and of ``O.metrics_at_k`` against vectors produced by the
+    reference's own ``eval/metrics.py:4-105`` (``oracle/make_metrics_golden.py``): users without targets, with more
+    targets than k, with every item a target."""
+    import os
+
+    import scipy.sparse as sp
+    import torch
+
+    from oracle import rmet_restated as R
+    from tests.golden_util import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "metrics_pin.npz"))
+    logits, targets = torch.from_numpy(g["logits"]), torch.from_numpy(g["targets"].astype(np.float32))
+    ks = [int(k) for k in g["ks"]]
+    res, best = R.calculate(["ndcg", "recall", "precision"], logits, targets, k=ks, return_individual=True,
+                            return_best_logit_indices=True)
+    assert np.array_equal(best.numpy(), g[f"topk@{max(ks)}"])  # tie-free logits: torch.topk is unambiguous
+    tgt = sp.csr_matrix(g["targets"])
+    m = O.metrics_at_k(g[f"topk@{max(ks)}"], tgt, ks, n_items=targets.shape[1])
+    for k in ks:
+        for name in ("ndcg", "recall", "precision"):
+            want = g[f"{name}@{k}"]
+            assert np.abs(res[f"{name}_individual@{k}"].numpy() - want).max() < 1e-6, (name, k)
+            assert np.abs(m[f"{name}@{k}"] - want).max() < 1e-6, (name, k)
