@@ -36,6 +36,20 @@ def entity(features, hidden, C, **kw):
     return d
 
 
+def _fixture_shapes():
+    from sibrar_b200.synthetic import CATEGORICAL, CONTINUOUS, TAG, VECTOR, Shape
+    onion = Shape(150, 320, 6000,
+                  {"gender": (CATEGORICAL, 3), "country": (CATEGORICAL, 12), "age": (CONTINUOUS, None),
+                   "mpnet": (VECTOR, 96)},
+                  {"genres": (TAG, 24), "jukebox": (VECTOR, 1200), "musicnn": (VECTOR, 50),
+                   "lyrics_mpnet": (VECTOR, 96)})
+    amazon = Shape(137, 260, 3000, {},
+                   {"title_mpnet": (VECTOR, 768), "description_mpnet": (VECTOR, 64), "image_resnet": (VECTOR, 64)})
+    return onion, amazon
+
+
+ONION_FIXTURE_SHAPE, AMAZON_FIXTURE_SHAPE = _fixture_shapes()
+
 # name -> dict(corpus kwargs, model conf, loss, optimizer, ...)
 CASES = {
     # conf/single/algorithms/sbnet_ml1m_conf.yml model block (C = D = small), trailing BN, item dropout
@@ -93,7 +107,83 @@ CASES = {
                                [16, 16], 16, activation_fn="tanh", single_branch_input_dropout=0.1,
                                normalize_single_branch_input=True)),
         rec_loss="bce", optimizer="adam", lr=3e-3, wd=0.0, batch=24, n_neg=3, steps=3),
+    # ---- REAL LAYER WIDTHS (catalogue scaled down, widths not): conf/single/algorithms/sbnet_onion18_huge_conf.yml:31-66
+    # item C = 512, MLP [512, 512, 512, 256, 256] -> D = 128, BatchNorm after every 2nd Linear, output activation, input
+    # dropout 0.02, L2 normalisation, pairwise InfoNCE (k = 2); user: train_modalities = [interactions], C = 128,
+    # normalised, output activation + trailing BatchNorm.  Weights come from ``seeded_state`` (regenerated by the tests),
+    # gradients are stored as scaled fp16 (see ``pack_f16``) to keep the fixture small.
+    "onion_huge_widths": dict(
+        corpus=dict(shape=ONION_FIXTURE_SHAPE, split_type="random", seed=21, scale=1.0),
+        model=dict(shared_common_dim=128,
+                   user=entity([("interactions", []), ("age", []), ("gender", []), ("country", []), ("mpnet", [128])],
+                               [], 128, single_branch_input_dropout=None, normalize_single_branch_input=True,
+                               train_modalities=["interactions"], aggregation_fn="mean",
+                               embedding_regularization_type="no_regularization", apply_output_activation=True,
+                               apply_batch_normalization=True),
+                   item=entity([("interactions", []), ("musicnn", []), ("lyrics_mpnet", []), ("jukebox", []),
+                                ("genres", [])],
+                               [512, 512, 512, 256, 256], 512, single_branch_input_dropout=2e-2,
+                               normalize_single_branch_input=True, aggregation_fn="mean",
+                               embedding_regularization_type="pairwise_single", central_modality="interactions",
+                               train_modalities=["interactions", "genres", "jukebox"], apply_output_activation=True,
+                               apply_batch_normalization=True, apply_batch_norm_every=2)),
+        rec_loss="bpr", optimizer="adamw", lr=5e-5, wd=1e-3, batch=64, n_neg=3, steps=1, seeded_init=7),
+    # conf/single/algorithms/sbnet_amazonvid2024_huge_no-user_conf.yml:30-63: plain user embedding (embedding_dim -1 -> D),
+    # the same huge item branch on [interactions, title], missing-modality evaluation (eval_modalities = [title])
+    "amazon_nouser_widths": dict(
+        corpus=dict(shape=AMAZON_FIXTURE_SHAPE, split_type="random", seed=23, scale=1.0),
+        model=dict(shared_common_dim=128,
+                   user=dict(feature_name="user_embedding", embedding_dim=-1, activation_fn="relu"),
+                   item=entity([("interactions", []), ("title_mpnet", []), ("description_mpnet", []),
+                                ("image_resnet", [])],
+                               [512, 512, 512, 256, 256], 512, single_branch_input_dropout=2e-2,
+                               normalize_single_branch_input=True, aggregation_fn="mean",
+                               embedding_regularization_type="pairwise_single", central_modality="interactions",
+                               train_modalities=["interactions", "title_mpnet"], eval_modalities=["title_mpnet"],
+                               apply_output_activation=True, apply_batch_normalization=True,
+                               apply_batch_norm_every=2)),
+        rec_loss="bpr", optimizer="adamw", lr=5e-5, wd=1e-3, batch=48, n_neg=4, steps=1, seeded_init=11),
 }
+
+
+def seeded_state(shapes: dict, seed: int) -> dict:
+    """deterministic fp32 ``state_dict`` values from names + shapes alone (numpy only, so the tests regenerate it
+    instead of the fixture storing ~2 M floats): 2-D weights uniform with variance 1/fan_in, embedding tables N(0, 0.1),
+    biases N(0, 0.05), BatchNorm gamma 1 + N(0, 0.1), running mean N(0, 0.05), running var 1 + U(0, 0.2)."""
+    import zlib
+    out = {}
+    for name in sorted(shapes):
+        shp = tuple(int(x) for x in shapes[name])
+        rng = np.random.default_rng([int(seed), zlib.crc32(name.encode())])
+        if name.endswith("num_batches_tracked"):
+            v = np.zeros(shp, dtype=np.int64)
+        elif name.endswith("running_var"):
+            v = 1.0 + 0.2 * rng.random(shp)
+        elif name.endswith("running_mean"):
+            v = 0.05 * rng.standard_normal(shp)
+        elif "embedding_layer" in name:
+            v = 0.1 * rng.standard_normal(shp)
+        elif len(shp) == 2:
+            v = (rng.random(shp) * 2.0 - 1.0) * np.sqrt(3.0 / shp[1])
+        elif "batch_norm" in name and name.endswith(".weight") or (len(shp) == 1 and name.endswith(".weight")):
+            v = 1.0 + 0.1 * rng.standard_normal(shp)
+        else:
+            v = 0.05 * rng.standard_normal(shp)
+        out[name] = v if v.dtype == np.int64 else v.astype(np.float32)
+    return out
+
+
+def pack_f16(a):
+    """fp32 array -> (fp16 mantissas, fp32 scale): |a| / scale <= 1024, so entries down to 6e-8 of the largest one keep
+    11 significant bits"""
+    a = np.asarray(a, np.float32)
+    m = float(np.abs(a).max())
+    scale = np.float32(m / 1024.0 if m > 0 else 1.0)
+    return (a / scale).astype(np.float16), scale
+
+
+def unpack_f16(q, scale):
+    return q.astype(np.float32) * np.float32(scale)
 
 
 def build_reference_datasets(corpus):
@@ -151,9 +241,16 @@ def run_case(name, spec):
     train_ds = dss["train"]
     model = SingleBranchNet.build_from_conf(copy.deepcopy(spec["model"]), train_ds)
     out = {}
+    seeded = spec.get("seeded_init")
+    if seeded is not None:
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in seeded_state(shapes, seeded).items()})
+        for k, shp in shapes.items():
+            out[f"shape/{k}"] = np.asarray(shp, dtype=np.int64)
     sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    for k, v in sd0.items():
-        out[f"sd0/{k}"] = v.numpy()
+    if seeded is None:
+        for k, v in sd0.items():
+            out[f"sd0/{k}"] = v.numpy()
 
     # ---- hooks: record modalities and dropout masks
     rec = {"mods": {}, "drop": {}}
@@ -214,11 +311,19 @@ def run_case(name, spec):
             if ent_name in rec["drop"]:
                 out[f"s{step}/drop_{ent_name}"] = rec["drop"][ent_name].astype(np.uint8)
         for k, p in model.named_parameters():
-            out[f"s{step}/grad/{k}"] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
-        opt.step()
+            gnp = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
+            if seeded is None:
+                out[f"s{step}/grad/{k}"] = gnp
+            else:
+                out[f"s{step}/grad16/{k}"], out[f"s{step}/gscale/{k}"] = pack_f16(gnp)
+        if seeded is None:
+            opt.step()
         opt.zero_grad()
         for k, v in model.state_dict().items():
-            out[f"s{step}/sd/{k}"] = v.detach().numpy().copy()
+            # seeded cases: the optimizer is not applied (Adam is pinned by the small cases); only what the step itself
+            # changed -- the BatchNorm running statistics -- is stored, the tests overlay it on the seeded weights
+            if seeded is None or k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+                out[f"s{step}/sd/{k}"] = v.detach().numpy().copy()
         rec["mods"].clear()
         rec["drop"].clear()
 

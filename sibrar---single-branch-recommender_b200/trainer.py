@@ -65,6 +65,7 @@ class FusedTrainer:
         n_item = len(list(self.item.parameters()))
         self.bucket_bounds = (0, offs[n_item] if n_item < len(offs) else total, total)  # [item | user]
         entries = []
+        self.grad_offsets = {id(p): (o, p.numel(), tuple(p.shape)) for p, o in zip(ordered, offs)}
         for p, o in zip(ordered, offs):
             g = self.flat_grads[o:o + p.numel()].view(p.shape)
             p.grad = g
@@ -86,6 +87,10 @@ class FusedTrainer:
         # 2 (default): + weight-gradient GEMMs and per-modality table chains on further streams
         self.branches = int(os.environ.get("SBR_BRANCHES", "2"))
         self._side = None
+        # debugging / parity tests: a copy of the flat gradient buffer taken inside the step right before the optimizer
+        # consumes (and clears) it -- also inside the captured graph
+        self.snapshot_grads = False
+        self.grads_snapshot = None
 
     # ------------------------------------------------------------------------------------------------ one step
     def step(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor, mods: Optional[dict] = None,
@@ -198,6 +203,10 @@ class FusedTrainer:
             self._after_item_backward()
             self.user.backward(dEu, self.grads, final_bn_sums=bn_u["sums"] if bn_u else None)
             self._after_user_backward()
+        if self.snapshot_grads:
+            if self.grads_snapshot is None:
+                self.grads_snapshot = torch.empty_like(self.flat_grads)
+            self.grads_snapshot.copy_(self.flat_grads)
         if apply_optimizer:
             self.optimizer_step(ticked=True)
         self.steps_accumulated += 1

@@ -3,13 +3,25 @@ import os
 
 import numpy as np
 
-from oracle.make_golden import CASES, GOLDEN_DIR  # noqa: F401  (CASES only; nothing of the reference is imported)
+from oracle.make_golden import CASES, GOLDEN_DIR, seeded_state, unpack_f16  # noqa: F401  (nothing of the reference)
 
 
 def load_case(name):
     from sibrar_b200.synthetic import SynCorpus
     spec = CASES[name]
     g = dict(np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"), allow_pickle=False))
+    if spec.get("seeded_init") is not None:
+        # compact fixture: weights regenerated from (name, shape, seed), gradients stored as scaled fp16, and of the
+        # post-step state only the BatchNorm running statistics (the optimizer is pinned by the small cases)
+        shapes = {k[len("shape/"):]: v for k, v in g.items() if k.startswith("shape/")}
+        sd0 = seeded_state(shapes, spec["seeded_init"])
+        g.update({f"sd0/{k}": v for k, v in sd0.items()})
+        for s in range(spec["steps"]):
+            for k in [k for k in g if k.startswith(f"s{s}/grad16/")]:
+                pname = k[len(f"s{s}/grad16/"):]
+                g[f"s{s}/grad/{pname}"] = unpack_f16(g[k], g[f"s{s}/gscale/{pname}"])
+            for k, v in sd0.items():
+                g.setdefault(f"s{s}/sd/{k}", v)
     corpus = SynCorpus(**spec["corpus"])
     return spec, g, corpus
 

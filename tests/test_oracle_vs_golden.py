@@ -8,17 +8,23 @@ from oracle import sbnet_oracle as O
 from tests.golden_util import CASES, load_case, state_dict_of, step_inputs
 
 
+WIDE = {"fp32_noise": 0.0}  # set per case: fp32 round-off of the reference relative to max-abs (wide layers)
+
+
 def _close(a, b, rtol=2e-4, atol=2e-6, what=""):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     assert a.shape == b.shape, (what, a.shape, b.shape)
     err = np.abs(a - b)
-    tol = atol + rtol * np.abs(b)
+    # the reference accumulates K = 512 .. 1200 products in fp32: entries near zero carry round-off proportional to
+    # the tensor's scale, not to their own value
+    tol = atol + rtol * np.abs(b) + WIDE["fp32_noise"] * (np.abs(b).max() if b.size else 0.0)
     assert (err <= tol).all(), f"{what}: max err {err.max():.3e} (ref max {np.abs(b).max():.3e})"
 
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_train_steps_match_reference(name):
     spec, g, corpus = load_case(name)
+    WIDE["fp32_noise"] = 2e-5 if spec.get("seeded_init") is not None else 0.0
     ds = corpus.dataset("train")
     net = O.OracleSBNet(spec["model"], ds)
     p = {k: v.astype(np.float64) if v.dtype.kind == "f" else v for k, v in state_dict_of(g, "sd0/").items()}
@@ -37,11 +43,14 @@ def test_train_steps_match_reference(name):
             got = r["grads"].get(k, np.zeros_like(gg))
             # atol: fp32 round-off of the reference (e.g. a bias in front of a BatchNorm has an exactly-zero
             # gradient; the reference holds ~1e-6 noise there)
-            _close(got, gg, rtol=1e-3, atol=3e-5 * gscale, what=f"s{s} grad {k}")
+            # (real-width fixtures store the gradients as scaled fp16: 2^-12 of each value, + the reference's fp32 noise)
+            extra = 1.5e-3 * float(np.abs(gg).max()) if spec.get("seeded_init") is not None else 0.0
+            _close(got, gg, rtol=1e-3, atol=3e-5 * gscale + extra, what=f"s{s} grad {k}")
         # the optimizer restatement is checked on the reference's own gradients: Adam turns the fp32 noise of
         # exactly-zero gradients into +-lr updates, which no independent implementation can reproduce
         grads = {k: v.astype(np.float64) for k, v in gold_grads.items()}
-        O.adam_step(p, grads, state, spec["lr"], spec["wd"], s + 1, decoupled=spec["optimizer"] == "adamw")
+        if spec.get("seeded_init") is None:  # (the real-width fixtures do not apply the optimizer, see make_golden.py)
+            O.adam_step(p, grads, state, spec["lr"], spec["wd"], s + 1, decoupled=spec["optimizer"] == "adamw")
         p.update(r["new_stats"])
         for k, v in state_dict_of(g, f"s{s}/sd/").items():
             _close(p[k], v, rtol=1e-3, atol=2e-5, what=f"s{s} param {k}")
@@ -50,6 +59,7 @@ def test_train_steps_match_reference(name):
 @pytest.mark.parametrize("name", list(CASES))
 def test_eval_matches_reference(name):
     spec, g, corpus = load_case(name)
+    WIDE["fp32_noise"] = 2e-5 if spec.get("seeded_init") is not None else 0.0
     net = O.OracleSBNet(spec["model"], corpus.dataset("train"))
     val = corpus.dataset("val")
     p = state_dict_of(g, f"s{spec['steps'] - 1}/sd/")
