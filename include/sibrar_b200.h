@@ -109,7 +109,19 @@ int sbr_csr_to_dense_bf16(const int64_t* indptr, const int32_t* indices, const f
  * accumulate = 1: out += result, like every other wgrad of the path).  out_bf16: optional bf16 copy of the result. */
 int sbr_spmm_csr(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows, const float* dense,
                  int64_t ld_dense, int64_t C, const float* bias, int act, float* out, int64_t ld_out, int transpose_out,
-                 int accumulate, void* out_bf16, int64_t ld_bf16, void* stream);
+                 int accumulate, void* out_bf16, int64_t ld_bf16, const int32_t* row_map, int atomic, void* stream);
+/* row_map / atomic (row-major fp32 output only): CSR row s adds its result into out[row_map[s]] with vector reductions
+ * -- the EmbeddingBag(mean) backward of a large tag vocabulary (algorithms/sgd_alg.py:1331-1340): CSR rows are
+ * <= 128-entry segments of "feature rows carrying tag t", vals = 1 / #tags of the row, dense = the bag-table gradient.
+ *
+ * The same with a bf16 dense operand (fp32 accumulation): W^T as the transposed bf16 shadow [d, pad8(C)] in the forward,
+ * the bf16 dz table in the wgrad -- the rounding points of the tensor-core routes at half the bytes.  row_list
+ * (optional): the CSR rows to compute, n_rows_dev (optional): device-side number of valid entries of row_list (the
+ * "referenced rows" of a step); outputs go to the listed rows. */
+int sbr_spmm_csr_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows,
+                      const void* dense_bf16, int64_t ld_dense, int64_t C, const float* bias, int act, float* out,
+                      int64_t ld_out, int transpose_out, int accumulate, void* out_bf16, int64_t ld_bf16,
+                      const int32_t* row_list, const int32_t* n_rows_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ modality sampling
  * Per (row, slot) choose k distinct modalities out of n_mods (optionally slot 0 fixed to `central`), Philox keyed
@@ -169,6 +181,59 @@ int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, int n_mods,
                                  int64_t n_rows, int C, int normalize, float p_drop, uint64_t seed,
                                  const int64_t* step_dev, const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
                                  int rows_per_warp, const uint8_t* keep_bits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ fused single-branch MLP
+ * One persistent kernel per direction for an entity whose single-branch network is 1 or 2 Linear layers of width <= 64
+ * (conf/single/algorithms/sbnet_ml1m_conf.yml, sbnet_onion18_conf.yml, ...):
+ *   fwd: z[r, :] = Linear_last(act(Linear_0(dropout(normalize(src_{mods[r]}(idx[r / k]))))))  (+ act of the last layer)
+ *        = _get_modality_embeddings + _embed (algorithms/sgd_alg.py:1934-1978, 1865-1877) + PolyLinear
+ *        (modules/polylinear.py:50-76) without X0 / hidden activations ever reaching HBM; colstats (optional): rows of
+ *        partial column sums / sums of squares of z for the BatchNorm behind the chain (sbr_bn_finalize adds them in a
+ *        fixed order; sbr_mlp2_colstats_rows(n_rows) rows of 2 D floats).
+ *   bwd: from dy = dL/d(output behind the optional BatchNorm) and the saved z: dz (BatchNorm backward from the column sums
+ *        `sums` = [n_replicas, 2 D] of (dy, dy * xhat), then the last activation's derivative), the gradients of both
+ *        weights and biases (accumulated into grad_w / grad_b, fp32 [out, in] / [out]), d gamma / d beta, and
+ *        dx[r, :] = dL/dX0 (fp32, consumed by sbr_row_gather_bwd_segmented).  X0 and the hidden activation are recomputed.
+ * Weights: the bf16 shadows [out, ldw] (ldw % 8 == 0). */
+typedef struct {
+  const void* w_bf16;
+  int64_t ldw;
+  const float* bias; /* may be NULL */
+  int in_f, out_f;
+  int act; /* SBR_ACT_* applied to this layer's output */
+} sbr_mlp2_layer_t;
+
+typedef struct {
+  const sbr_modality_src_t* srcs; /* device array [n_mods] */
+  int n_mods;
+  const int64_t* idx;  /* [n_idx] entity indices */
+  const uint8_t* mods; /* [n_idx * k] modality of every row (NULL: modality 0) */
+  int64_t n_idx;
+  int k, C, normalize;
+  float p_drop;
+  uint64_t seed;
+  const int64_t* step_dev;
+  const uint8_t* keep_mask; /* optional explicit dropout mask uint8 [n_idx * k, C] */
+  int32_t* err_flag;
+  int n_layers; /* 1 or 2 */
+  sbr_mlp2_layer_t layers[2];
+} sbr_mlp2_desc_t;
+
+typedef struct {
+  const float* mean_invstd; /* [2 D] of the forward */
+  const float* gamma;
+  const float* sums; /* [n_replicas, 2 D]: column sums of dy and of dy * xhat */
+  int n_replicas;
+  float* dgamma; /* += */
+  float* dbeta;  /* += */
+} sbr_mlp2_bn_t;
+
+int sbr_mlp2_colstats_rows(int64_t n_rows);
+int sbr_mlp2_fwd(const sbr_mlp2_desc_t* desc, int64_t n_rows, int C, float* z, int64_t ldz, float* colstats,
+                 int colstats_rows, void* stream);
+int sbr_mlp2_bwd(const sbr_mlp2_desc_t* desc, int64_t n_rows, int C, const float* dy, int64_t lddy, const float* z,
+                 int64_t ldz, const sbr_mlp2_bn_t* bn, float* const* grad_w, float* const* grad_b, float* dx,
+                 int64_t lddx, void* stream);
 
 /* nn.EmbeddingBag(mode="mean", padding_idx=pad_id) of EVERY feature row as a dense fp32 table [n_rows, C]
  * (reference FeatureEmbedding for tag features, algorithms/sgd_alg.py:1279-1396; codes int32 [n_rows, max_tags]):

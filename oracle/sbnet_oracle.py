@@ -71,11 +71,12 @@ def bf16_round(x):
 class Bf16Emulation:
     """Mirrors the ROUNDING POINTS of the B200 path ('precision'): GEMM operands (weights, activations
     between fused stages, dz) are bf16; accumulation, BatchNorm, normalisation, losses and every reduction are
-    fp32/fp64; the CSR ('sparse interactions') route is fp32 end to end.  With it the oracle predicts the kernels'
-    results to ~1e-3 instead of the ~1e-2 that separates bf16 from the fp32 reference."""
+    fp32/fp64; the CSR ('sparse interactions') route gathers bf16 weight rows / bf16 dz rows with fp32 accumulation, i.e.
+    it has the rounding points of the dense route (multi-hot inputs are exact in bf16).  With it the oracle predicts the
+    kernels' results to ~1e-3 instead of the ~1e-2 that separates bf16 from the fp32 reference."""
 
     def __init__(self, csr_route=()):
-        self.csr_route = set(csr_route)  # prefixes of FeatureProj modules whose first layer runs as SpMM
+        self.csr_route = set()  # (kept for callers; no module runs an fp32-exact first layer any more)
 
     q = staticmethod(bf16_round)
 

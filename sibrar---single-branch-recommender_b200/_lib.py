@@ -36,6 +36,22 @@ class BnInline(C.Structure):
     _fields_ = [("z", c_vp), ("mean_invstd", c_vp), ("gamma", c_vp), ("beta", c_vp), ("sums", c_vp)]
 
 
+class Mlp2Layer(C.Structure):
+    _fields_ = [("w_bf16", c_vp), ("ldw", c_i64), ("bias", c_vp), ("in_f", C.c_int), ("out_f", C.c_int),
+                ("act", C.c_int)]
+
+
+class Mlp2Desc(C.Structure):
+    _fields_ = [("srcs", c_vp), ("n_mods", C.c_int), ("idx", c_vp), ("mods", c_vp), ("n_idx", c_i64), ("k", C.c_int),
+                ("C", C.c_int), ("normalize", C.c_int), ("p_drop", c_f32), ("seed", c_u64), ("step_dev", c_vp),
+                ("keep_mask", c_vp), ("err_flag", c_vp), ("n_layers", C.c_int), ("layers", Mlp2Layer * 2)]
+
+
+class Mlp2Bn(C.Structure):
+    _fields_ = [("mean_invstd", c_vp), ("gamma", c_vp), ("sums", c_vp), ("n_replicas", C.c_int), ("dgamma", c_vp),
+                ("dbeta", c_vp)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", c_vp), ("grad", c_vp), ("exp_avg", c_vp), ("exp_avg_sq", c_vp), ("shadow_bf16", c_vp),
                 ("numel", c_i64), ("cols", c_i64), ("shadow_ld", c_i64)]
@@ -51,7 +67,9 @@ _PROTOS = {
     "sbr_transpose_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "sbr_csr_to_dense_bf16": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp],
     "sbr_spmm_csr": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int, c_vp,
-                     c_i64, c_vp],
+                     c_i64, c_vp, C.c_int, c_vp],
+    "sbr_spmm_csr_bf16": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int,
+                          c_vp, c_i64, c_vp, c_vp, c_vp],
     "sbr_sample_modalities": [c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_u64, c_vp, c_vp],
     "sbr_tick": [c_vp, c_vp],
     "sbr_step_begin": [c_vp, c_vp, c_vp, c_i64, c_vp],
@@ -80,6 +98,10 @@ _PROTOS = {
                           c_vp, C.c_int, c_vp],
     "sbr_infonce": [c_vp, c_i64, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, C.c_int, c_vp, c_vp],
     "sbr_aggregate": [c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp],
+    "sbr_mlp2_colstats_rows": [c_i64],
+    "sbr_mlp2_fwd": [C.POINTER(Mlp2Desc), c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp],
+    "sbr_mlp2_bwd": [C.POINTER(Mlp2Desc), c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, C.POINTER(Mlp2Bn),
+                     C.POINTER(c_vp), C.POINTER(c_vp), c_vp, c_i64, c_vp],
     "sbr_adam_step": [c_vp, C.c_int, c_i64, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, C.c_int, c_vp, c_f32,
                       c_vp],
     "sbr_topk_workspace_bytes": [c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.POINTER(c_i64)],

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256)
 spmm_vec_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ vals,
                 int64_t rows, const float* __restrict__ dense, int64_t ld_dense, int C,
                 const float* __restrict__ bias, int act, float* __restrict__ out, int64_t ld_out, int accumulate,
-                bf16* __restrict__ out16, int64_t ld_out16) {
+                bf16* __restrict__ out16, int64_t ld_out16, const int32_t* __restrict__ row_map, int atomic) {
   SBR_PDL_ENTRY();
   extern __shared__ float s_tile[];  // TRANSPOSE: [C][33]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,8 +136,15 @@ spmm_vec_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
         s_tile[(4 * c4 + 2) * 33 + local] = v.z;
         s_tile[(4 * c4 + 3) * 33 + local] = v.w;
       } else if (row < rows) {
-        if (out != nullptr) {
-          float4* dst = reinterpret_cast<float4*>(out + row * ld_out) + c4;
+        if (out != nullptr && atomic) {
+          // segment mode (several CSR rows add into one output row, e.g. the chunks of one tag's row list)
+          const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : row;
+          const size_t a = __cvta_generic_to_global(out + orow * ld_out + 4 * c4);
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                       : "memory");
+        } else if (out != nullptr) {
+          const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : row;
+          float4* dst = reinterpret_cast<float4*>(out + orow * ld_out) + c4;
           if (accumulate) {
             const float4 o = *dst;
             v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -170,7 +177,7 @@ spmm_vec_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
 template <int NV4>
 int launch_vec(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows, const float* dense,
                int64_t ld_dense, int C, const float* bias, int act, float* out, int64_t ld_out, int transpose_out,
-               int accumulate, bf16* out16, int64_t ld_out16, cudaStream_t st) {
+               int accumulate, bf16* out16, int64_t ld_out16, const int32_t* row_map, int atomic, cudaStream_t st) {
   if (transpose_out) {
     const size_t smem = (size_t)C * 33 * sizeof(float);
     static size_t configured = 0;
@@ -180,22 +187,210 @@ int launch_vec(const int64_t* indptr, const int32_t* indices, const float* vals,
       configured = smem;
     }
     SBR_CHECK_CUDA(sbr_launch(spmm_vec_kernel<NV4, true>, dim3(cdiv(rows, 32)), dim3(256), smem, st, indptr, indices,
-                              vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16, ld_out16));
+                              vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16, ld_out16,
+                              row_map, atomic));
   } else {
     SBR_CHECK_CUDA(sbr_launch(spmm_vec_kernel<NV4, false>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, st, indptr,
                               indices, vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16,
-                              ld_out16));
+                              ld_out16, row_map, atomic));
+  }
+  return SBR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ bf16 dense operand
+// The 'interactions' projection of a sparse matrix with the rounding points of the dense tensor-core route: bf16 weight
+// rows (the transposed shadow W^T [d, pad8(C)]) / bf16 dz rows, fp32 accumulation.  Half the bytes of the fp32 kernel;
+// lane owns the 16-byte chunks lane + 32 i (8 columns each), four gathered rows in flight per warp.
+__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& u, float w) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __bfloat1622float2(h[t]);
+    acc[2 * t] += w * f.x;
+    acc[2 * t + 1] += w * f.y;
+  }
+}
+
+template <int NV8, bool TRANSPOSE>
+__global__ void __launch_bounds__(256)
+spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                 const float* __restrict__ vals, int64_t rows, const bf16* __restrict__ dense, int64_t ld_dense, int C,
+                 const float* __restrict__ bias, int act, float* __restrict__ out, int64_t ld_out, int accumulate,
+                 bf16* __restrict__ out16, int64_t ld_out16, const int32_t* __restrict__ row_list,
+                 const int32_t* __restrict__ n_rows_dev) {
+  SBR_PDL_ENTRY();
+  extern __shared__ float s_tile[];  // TRANSPOSE: [C][33]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ROWS_PER_WARP = TRANSPOSE ? 4 : 1;
+  const int64_t row_base = (int64_t)blockIdx.x * (8 * ROWS_PER_WARP);
+  if (n_rows_dev != nullptr) rows = min(rows, (int64_t)*n_rows_dev);  // device-side row count (referenced-rows route)
+  if (row_base >= rows) return;
+  const int C8 = (C + 7) >> 3;
+#pragma unroll 1
+  for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+    const int local = warp * ROWS_PER_WARP + rr;
+    const int64_t slot = row_base + local;
+    // row_list: the CSR rows to compute (and the output rows they go to); otherwise row = slot
+    const int64_t row = slot < rows ? (row_list ? (int64_t)__ldg(row_list + slot) : slot) : -1;
+    float acc[NV8][8];
+#pragma unroll
+    for (int i = 0; i < NV8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    if (row >= 0) {
+      const int64_t beg = indptr[row], end = indptr[row + 1];
+      for (int64_t p = beg; p < end; p += 32) {
+        const int32_t my = (p + lane < end) ? __ldg(indices + p + lane) : 0;
+        const float myv = (vals != nullptr && p + lane < end) ? __ldg(vals + p + lane) : 1.f;
+        const int cnt = (int)min((int64_t)32, end - p);
+        int t = 0;
+        for (; t + 4 <= cnt; t += 4) {
+          uint4 u[4][NV8];
+          float w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int32_t j = __shfl_sync(0xffffffffu, my, t + q);
+            w[q] = __shfl_sync(0xffffffffu, myv, t + q);
+            const uint4* d = reinterpret_cast<const uint4*>(dense + (int64_t)j * ld_dense);
+#pragma unroll
+            for (int i = 0; i < NV8; ++i) {
+              const int c8 = lane + 32 * i;
+              u[q][i] = c8 < C8 ? __ldg(d + c8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < NV8; ++i) fma8(acc[i], u[q][i], w[q]);
+        }
+        for (; t < cnt; ++t) {
+          const int32_t j = __shfl_sync(0xffffffffu, my, t);
+          const float w = __shfl_sync(0xffffffffu, myv, t);
+          const uint4* d = reinterpret_cast<const uint4*>(dense + (int64_t)j * ld_dense);
+#pragma unroll
+          for (int i = 0; i < NV8; ++i) {
+            const int c8 = lane + 32 * i;
+            if (c8 < C8) fma8(acc[i], __ldg(d + c8), w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) {
+      const int c8 = lane + 32 * i;
+      if (c8 >= C8) continue;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = 8 * c8 + j;
+        v[j] = act_fwd(act, acc[i][j] + ((bias != nullptr && c < C) ? __ldg(bias + c) : 0.f));
+      }
+      if (TRANSPOSE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (8 * c8 + j < C) s_tile[(8 * c8 + j) * 33 + local] = v[j];
+      } else if (row >= 0) {
+        if (out != nullptr) {
+          float* dst = out + row * ld_out + 8 * c8;
+          if (8 * c8 + 8 <= C && (ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
+            if (accumulate) {
+              const float4 oa = *reinterpret_cast<float4*>(dst), ob = *reinterpret_cast<float4*>(dst + 4);
+              a.x += oa.x; a.y += oa.y; a.z += oa.z; a.w += oa.w;
+              b.x += ob.x; b.y += ob.y; b.z += ob.z; b.w += ob.w;
+            }
+            *reinterpret_cast<float4*>(dst) = a;
+            *reinterpret_cast<float4*>(dst + 4) = b;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (8 * c8 + j < C) dst[j] = accumulate ? dst[j] + v[j] : v[j];
+          }
+        }
+        if (out16 != nullptr) {  // [rows, ld_out16 >= pad8(C)]: pad columns written as zero
+          uint4 o;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int t2 = 0; t2 < 4; ++t2)
+            h[t2] = __floats2bfloat162_rn(8 * c8 + 2 * t2 < C ? v[2 * t2] : 0.f, 8 * c8 + 2 * t2 + 1 < C ? v[2 * t2 + 1] : 0.f);
+          *reinterpret_cast<uint4*>(out16 + row * ld_out16 + 8 * c8) = o;
+        }
+      }
+    }
+  }
+  if (TRANSPOSE) {
+    __syncthreads();
+    const int64_t slot = row_base + lane;
+    if (slot < rows) {
+      const int64_t row = row_list ? (int64_t)__ldg(row_list + slot) : slot;
+      for (int c = warp; c < C; c += 8) {
+        float* dst = out + (int64_t)c * ld_out + row;
+        const float v = s_tile[c * 33 + lane];
+        *dst = accumulate ? *dst + v : v;
+      }
+    }
+  }
+}
+
+template <int NV8>
+int launch_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows, const bf16* dense,
+                int64_t ld_dense, int C, const float* bias, int act, float* out, int64_t ld_out, int transpose_out,
+                int accumulate, bf16* out16, int64_t ld_out16, const int32_t* row_list, const int32_t* n_rows_dev,
+                cudaStream_t st) {
+  if (transpose_out) {
+    const size_t smem = (size_t)C * 33 * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      SBR_CHECK_CUDA(cudaFuncSetAttribute(spmm_bf16_kernel<NV8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+      configured = smem;
+    }
+    SBR_CHECK_CUDA(sbr_launch(spmm_bf16_kernel<NV8, true>, dim3(cdiv(rows, 32)), dim3(256), smem, st, indptr, indices,
+                              vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16, ld_out16,
+                              row_list, n_rows_dev));
+  } else {
+    SBR_CHECK_CUDA(sbr_launch(spmm_bf16_kernel<NV8, false>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, st, indptr,
+                              indices, vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16,
+                              ld_out16, row_list, n_rows_dev));
   }
   return SBR_OK;
 }
 
 }  // namespace
 
+extern "C" int sbr_spmm_csr_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows,
+                                 const void* dense_bf16, int64_t ld_dense, int64_t C, const float* bias, int act,
+                                 float* out, int64_t ld_out, int transpose_out, int accumulate, void* out_bf16,
+                                 int64_t ld_bf16, const int32_t* row_list, const int32_t* n_rows_dev, void* stream) {
+  SBR_REQUIRE(indptr && indices && dense_bf16 && (out || out_bf16) && rows > 0, "sbr_spmm_csr_bf16: bad arguments");
+  SBR_REQUIRE(C > 0 && C <= 1024, "sbr_spmm_csr_bf16: C=%lld not in [1, 1024]", (long long)C);
+  SBR_REQUIRE(ld_dense % 8 == 0 && ld_dense >= ((C + 7) / 8) * 8 && (reinterpret_cast<uintptr_t>(dense_bf16) & 15) == 0,
+              "sbr_spmm_csr_bf16: dense rows must be 16-byte aligned and padded to 8 columns (ld=%lld)",
+              (long long)ld_dense);
+  SBR_REQUIRE(!(transpose_out && (out_bf16 || !out)), "sbr_spmm_csr_bf16: the transposed output is fp32 only");
+  SBR_REQUIRE(out_bf16 == nullptr || (ld_bf16 % 8 == 0 && ld_bf16 >= ((C + 7) / 8) * 8 &&
+                                      (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0),
+              "sbr_spmm_csr_bf16: bf16 output rows must be 16-byte aligned and padded to 8 columns");
+  const bf16* d = reinterpret_cast<const bf16*>(dense_bf16);
+  bf16* o16 = reinterpret_cast<bf16*>(out_bf16);
+  const int nv8 = (int)(((C + 7) / 8 + 31) / 32);
+  cudaStream_t st = S(stream);
+#define SBR_SPMM_BF16(N)                                                                                          \
+  return launch_bf16<N>(indptr, indices, vals, rows, d, ld_dense, (int)C, bias, act, out, ld_out, transpose_out, \
+                        accumulate, o16, ld_bf16, row_list, n_rows_dev, st)
+  if (nv8 <= 1) SBR_SPMM_BF16(1);
+  if (nv8 <= 2) SBR_SPMM_BF16(2);
+  SBR_SPMM_BF16(4);
+#undef SBR_SPMM_BF16
+}
+
 extern "C" int sbr_spmm_csr(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows,
                             const float* dense, int64_t ld_dense, int64_t C, const float* bias, int act, float* out,
                             int64_t ld_out, int transpose_out, int accumulate, void* out_bf16, int64_t ld_bf16,
-                            void* stream) {
+                            const int32_t* row_map, int atomic, void* stream) {
   SBR_REQUIRE(indptr && indices && dense && (out || out_bf16) && rows > 0, "sbr_spmm_csr: bad arguments");
+  SBR_REQUIRE(!(row_map || atomic) || (!transpose_out && out && !out_bf16 && C % 4 == 0),
+              "sbr_spmm_csr: row_map / atomic need the row-major fp32 output and C %% 4 == 0");
   SBR_REQUIRE(C > 0 && C <= 1024, "sbr_spmm_csr: C=%lld not in [1, 1024]", (long long)C);
   SBR_REQUIRE(!(transpose_out && (out_bf16 || !out)), "sbr_spmm_csr: the transposed output is fp32 only");
   bf16* o16 = reinterpret_cast<bf16*>(out_bf16);
@@ -208,14 +403,14 @@ extern "C" int sbr_spmm_csr(const int64_t* indptr, const int32_t* indices, const
     cudaStream_t st = S(stream);
 #define SBR_SPMM_VEC(N)                                                                                              \
   return launch_vec<N>(indptr, indices, vals, rows, dense, ld_dense, (int)C, bias, act, out, ld_out, transpose_out, \
-                       accumulate, o16, ld_bf16, st)
+                       accumulate, o16, ld_bf16, row_map, atomic, st)
     if (nv4 <= 1) SBR_SPMM_VEC(1);
     if (nv4 <= 2) SBR_SPMM_VEC(2);
     if (nv4 <= 4) SBR_SPMM_VEC(4);
     SBR_SPMM_VEC(8);
 #undef SBR_SPMM_VEC
   }
-  SBR_REQUIRE(o16 == nullptr, "sbr_spmm_csr: bf16 output needs C %% 4 == 0 and aligned operands");
+  SBR_REQUIRE(o16 == nullptr && !row_map && !atomic, "sbr_spmm_csr: bf16 output / row_map need C %% 4 == 0 and aligned operands");
   const int nv = (int)((C + 31) / 32);
 #define SBR_SPMM_GEN(N)                                                                                         \
   SBR_CHECK_CUDA(sbr_launch(spmm_kernel<N>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, S(stream), indptr, indices, \

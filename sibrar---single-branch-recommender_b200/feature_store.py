@@ -56,6 +56,25 @@ class DeviceFeature:
             self.pad_id = int(feature.dim)  # padding index == number of tags (data/Feature.py:254-255)
             self.n_cat = int(feature.dim) + 1
             self.dim = int(feature.dim)
+            # tag -> feature rows, cut into segments of <= 128 entries, with the EmbeddingBag(mean) weight 1 / #tags of
+            # the row: the backward of a LARGE tag vocabulary is a gather-sum per segment (sbr_spmm_csr, segment mode)
+            # instead of ~n_rows * tags_per_row contended atomics onto n_tags rows
+            rr, cc = np.nonzero(v != self.pad_id)
+            tags = v[rr, cc]
+            cnt = np.maximum((v != self.pad_id).sum(1), 1).astype(np.float32)
+            order = np.argsort(tags, kind="stable")
+            tags, rows_sorted = tags[order], rr[order].astype(np.int32)
+            starts = np.flatnonzero(np.r_[True, tags[1:] != tags[:-1]]) if tags.size else np.zeros(0, np.int64)
+            ends = np.r_[starts[1:], tags.size] if tags.size else np.zeros(0, np.int64)
+            seg_ptr, seg_tag = [0], []
+            for a, b in zip(starts.tolist(), ends.tolist()):
+                for lo in range(a, b, 128):
+                    seg_ptr.append(min(b, lo + 128))
+                    seg_tag.append(int(tags[a]))
+            self.tag_segments = (torch.from_numpy(np.asarray(seg_ptr, dtype=np.int64)).to(device),
+                                 torch.from_numpy(rows_sorted).to(device),
+                                 torch.from_numpy((1.0 / cnt[rows_sorted]).astype(np.float32)).to(device),
+                                 torch.from_numpy(np.asarray(seg_tag, dtype=np.int32)).to(device))
         elif sp.issparse(values):
             m = values.tocsr()
             m.sort_indices()

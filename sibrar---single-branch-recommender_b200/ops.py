@@ -6,7 +6,8 @@ import ctypes as C
 
 import torch
 
-from ._lib import ACT, LOSS, AdamTensor, BnInline, GemmEpilogue, ModalitySrc, call, ptr, stream_ptr
+from ._lib import (ACT, LOSS, AdamTensor, BnInline, GemmEpilogue, Mlp2Bn, Mlp2Desc, ModalitySrc, call, ptr,
+                   stream_ptr)
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -109,6 +110,15 @@ def cast_bf16(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:
     return dst
 
 
+def transpose_bf16(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [cols, pad8(rows)] (dst[c, r] = src[r, c]; pad columns must be pre-zeroed by the caller)"""
+    rows, cols = src.shape
+    if dst is None:
+        dst = torch.zeros((cols, pad8(rows)), dtype=BF16, device=src.device)
+    call("sbr_transpose_f32_to_bf16", ptr(src), src.stride(0), ptr(dst), dst.stride(0), rows, cols, stream_ptr())
+    return dst
+
+
 def transpose_f32(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:
     rows, cols = src.shape
     if dst is None:
@@ -126,12 +136,22 @@ def csr_to_dense_bf16(indptr, indices, rows, cols, vals=None) -> torch.Tensor:
 
 
 def spmm_csr(indptr, indices, rows, dense, C_, bias, act, out, transpose_out=False, vals=None, accumulate=False,
-             out_bf16=None):
+             out_bf16=None, row_map=None, atomic=False, row_list=None, n_rows_dev=None):
     """out[r] = act(sum_p vals[p] * dense[indices[p]] + bias); ``transpose_out``: out is [C, rows] (the wgrad through
-    the transposed CSR), ``accumulate``: out += result"""
+    the transposed CSR), ``accumulate``: out += result.  ``dense`` fp32 or bf16 (fp32 accumulation either way).
+    fp32 only: ``row_map`` / ``atomic`` (segment mode).  bf16 only: ``row_list`` / ``n_rows_dev`` (row subset)."""
+    if dense.dtype == BF16:
+        assert row_map is None and not atomic
+        call("sbr_spmm_csr_bf16", ptr(indptr), ptr(indices), ptr(vals), int(rows), ptr(dense), dense.stride(0),
+             int(C_), ptr(bias), _act(act), ptr(out), out.stride(0) if out is not None else 0, int(transpose_out),
+             int(bool(accumulate)), ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(row_list),
+             ptr(n_rows_dev), stream_ptr())
+        return
+    assert row_list is None and n_rows_dev is None
     call("sbr_spmm_csr", ptr(indptr), ptr(indices), ptr(vals), int(rows), ptr(dense), dense.stride(0), int(C_),
          ptr(bias), _act(act), ptr(out), out.stride(0) if out is not None else 0, int(transpose_out),
-         int(bool(accumulate)), ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, stream_ptr())
+         int(bool(accumulate)), ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(row_map),
+         int(bool(atomic)), stream_ptr())
 
 
 def sample_modalities(mods, n_rows, k, n_mods, central, seed, step_dev):
@@ -204,6 +224,51 @@ class GatherPlan:
         call("sbr_row_gather_bwd_segmented", ptr(srcs), int(n_mods), self.n_keys, ptr(self.offsets), ptr(self.perm),
              ptr(self.sorted_keys), self.N, int(C_), int(bool(normalize)), float(p_drop or 0.0), int(seed),
              ptr(step_dev), ptr(keep_mask), ptr(dx), dx.stride(0), self.rows_per_warp, ptr(keep_bits), stream_ptr())
+
+
+TAG_BAG_SMEM_FLOATS = 10240  # csrc/gather.cu SEG_SMEM_FLOATS: gradient matrices up to this size are privatised per block
+
+
+def mlp2_desc(srcs, n_mods, idx, mods, k, C_, normalize, p_drop, seed, step_dev, keep_mask, err_flag, layers):
+    """descriptor of the fused gather + single-branch MLP kernels; ``layers``: list (1 or 2) of
+    (w_bf16 [out, ldw], bias or None, in_f, out_f, activation applied to the layer's output)"""
+    d = Mlp2Desc()
+    d.srcs, d.n_mods, d.idx, d.mods = ptr(srcs), int(n_mods), ptr(idx), ptr(mods)
+    d.n_idx, d.k, d.C, d.normalize = idx.numel(), int(k), int(C_), int(bool(normalize))
+    d.p_drop, d.seed, d.step_dev = float(p_drop or 0.0), int(seed), ptr(step_dev)
+    d.keep_mask, d.err_flag, d.n_layers = ptr(keep_mask), ptr(err_flag), len(layers)
+    for i, (w16, bias, in_f, out_f, act) in enumerate(layers):
+        assert w16.dtype == BF16 and w16.stride(-1) == 1
+        y = d.layers[i]
+        y.w_bf16, y.ldw, y.bias = ptr(w16), w16.stride(0), ptr(bias)
+        y.in_f, y.out_f, y.act = int(in_f), int(out_f), _act(act)
+    d._keep = (srcs, idx, mods, step_dev, keep_mask, err_flag, [(w, b) for w, b, *_ in layers])  # keep-alive
+    return d
+
+
+def mlp2_colstats_rows(n_rows: int) -> int:
+    from ._lib import lib
+    return int(lib().sbr_mlp2_colstats_rows(int(n_rows)))
+
+
+def mlp2_fwd(desc, n_rows, C_, z, colstats=None, colstats_rows=0):
+    call("sbr_mlp2_fwd", C.byref(desc), int(n_rows), int(C_), ptr(z), z.stride(0), ptr(colstats), int(colstats_rows),
+         stream_ptr())
+
+
+def mlp2_bwd(desc, n_rows, C_, dy, z, bn, grad_w, grad_b, dx):
+    """bn: None or dict(mean_invstd, gamma, sums, n_replicas, dgamma, dbeta); grad_w / grad_b: per-layer fp32 tensors
+    (None entries are skipped)"""
+    b = None
+    if bn is not None:
+        b = Mlp2Bn()
+        b.mean_invstd, b.gamma, b.sums = ptr(bn["mean_invstd"]), ptr(bn["gamma"]), ptr(bn["sums"])
+        b.n_replicas, b.dgamma, b.dbeta = int(bn["n_replicas"]), ptr(bn.get("dgamma")), ptr(bn.get("dbeta"))
+    from ._lib import c_vp
+    gw = (c_vp * 2)(*[ptr(t) for t in (list(grad_w) + [None, None])[:2]])
+    gb = (c_vp * 2)(*[ptr(t) for t in (list(grad_b) + [None, None])[:2]])
+    call("sbr_mlp2_bwd", C.byref(desc), int(n_rows), int(C_), ptr(dy), dy.stride(0), ptr(z), z.stride(0),
+         C.byref(b) if b is not None else None, gw, gb, ptr(dx), dx.stride(0), stream_ptr())
 
 
 def tag_bag_fwd(codes, max_tags, pad_id, weight, out):

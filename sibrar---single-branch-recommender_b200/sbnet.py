@@ -95,12 +95,12 @@ class LinearStage:
         self.act2: Optional[str] = None
         self.in_f, self.out_f = linear.in_features, linear.out_features
         self.w16 = None     # bf16 [out, pad8(in)]: K-major B of the forward GEMM, MN-major B of the dgrad GEMM
-        self.wt32 = None    # fp32 [in, out] for the CSR route
+        self.wt16 = None    # bf16 [in, pad8(out)]: the transposed shadow, gathered row by row on the CSR route
         self._ver = -1
         # saved for backward
         self.x = self.y16 = self.y32 = self.a32 = self.mi = None
 
-    def refresh(self, need_wt32: bool):
+    def refresh(self, need_wt16: bool):
         w = self.linear.weight
         if self.w16 is None or self.w16.device != w.device:
             self.w16 = torch.zeros((self.out_f, ops.pad8(self.in_f)), dtype=BF16, device=w.device)
@@ -108,10 +108,10 @@ class LinearStage:
         if w._version != self._ver:
             ops.cast_bf16(w.detach(), self.w16)
             self._ver = w._version
-        if need_wt32:  # refreshed every forward: the fused optimizer only maintains the bf16 shadow
-            if self.wt32 is None or self.wt32.device != w.device:
-                self.wt32 = torch.empty((self.in_f, self.out_f), dtype=F32, device=w.device)
-            ops.transpose_f32(w.detach(), self.wt32)
+        if need_wt16:  # refreshed every forward: the fused optimizer only maintains the row-major bf16 shadow
+            if self.wt16 is None or self.wt16.device != w.device:
+                self.wt16 = torch.zeros((self.in_f, ops.pad8(self.out_f)), dtype=BF16, device=w.device)
+            ops.transpose_bf16(w.detach(), self.wt16)
 
 
 def build_stages(poly: PolyLinear, trailing_bn: Optional[nn.BatchNorm1d] = None):
@@ -223,17 +223,15 @@ class Chain:
             out_pad = ops.pad8(st.out_f)
             y16 = y32 = a32 = mi = None
             if st.bn is None:
-                if final or first_csr:
-                    y32 = out32 if (final and out32 is not None) else torch.empty((rows, st.out_f), dtype=F32,
-                                                                                  device=dev)
+                if final:
+                    y32 = out32 if out32 is not None else torch.empty((rows, st.out_f), dtype=F32, device=dev)
                 if not final:
                     y16 = torch.empty((rows, out_pad), dtype=BF16, device=dev)
                 if first_csr:
                     ip, ix = self.feature.csr
-                    ops.spmm_csr(ip, ix, rows, st.wt32, st.out_f, bias, st.act1, y32, vals=self.feature.csr_vals,
-                                 out_bf16=y16 if (y16 is not None and st.out_f % 8 == 0) else None)
-                    if y16 is not None and st.out_f % 8 != 0:
-                        ops.cast_bf16(y32, y16)
+                    # gather-sum of bf16 weight rows, fp32 accumulation: the rounding points of the dense route
+                    ops.spmm_csr(ip, ix, rows, st.wt16, st.out_f, bias, st.act1, y32, vals=self.feature.csr_vals,
+                                 out_bf16=y16)
                 else:
                     first_bits = si == 0 and self.bits_input
                     mm = (lambda *a, **k: ops.gemm_bits(self.feature.bits, *a[1:], **k)) if first_bits else ops.gemm
@@ -313,8 +311,9 @@ class Chain:
                 fused = None
             else:
                 y = st.y32 if st.y32 is not None else st.y16
-                dz16 = None if first_csr else torch.empty((rows, out_pad), dtype=BF16, device=dev)
-                dz32 = torch.empty((rows, st.out_f), dtype=F32, device=dev) if first_csr else None
+                dz16 = torch.zeros((rows, out_pad), dtype=BF16, device=dev) if (first_csr and out_pad != st.out_f) \
+                    else torch.empty((rows, out_pad), dtype=BF16, device=dev)
+                dz32 = None
                 if st.bn is None:
                     ops.actgrad_colsum(dy32, y, st.act1, rows, st.out_f, out_bf16=dz16, out_f32=dz32, colsum=g_b,
                                        zero_dy=zero_dy)
@@ -339,7 +338,7 @@ class Chain:
             if first_csr:
                 ip_t, ix_t = self.feature.csr_t
                 # accumulates like every other wgrad of the path (gradient accumulation over micro-batches)
-                ops.spmm_csr(ip_t, ix_t, st.in_f, dz32, st.out_f, None, None, g_w, transpose_out=True,
+                ops.spmm_csr(ip_t, ix_t, st.in_f, dz16, st.out_f, None, None, g_w, transpose_out=True,
                              vals=self.feature.csr_t_vals, accumulate=True)
             else:
                 x16 = st.x if si > 0 or self.feature is None else self.feature.x16
@@ -376,8 +375,10 @@ class Chain:
                 prev = self.stages[si - 1]
                 if prev.bn is None:
                     prev_csr = si - 1 == 0 and self.csr_input
-                    p16 = None if prev_csr else torch.empty((rows, ops.pad8(st.in_f)), dtype=BF16, device=dev)
-                    p32 = torch.empty((rows, st.in_f), dtype=F32, device=dev) if prev_csr else None
+                    pad_in = ops.pad8(st.in_f)
+                    p16 = torch.zeros((rows, pad_in), dtype=BF16, device=dev) if (prev_csr and pad_in != st.in_f) \
+                        else torch.empty((rows, pad_in), dtype=BF16, device=dev)
+                    p32 = None
                     g_pb = grads[id(prev.linear.bias)] if prev.linear.bias is not None else None
                     ops.gemm(dz16, st.w16, rows, st.in_f, st.out_f, b_mn=True, out_bf16=p16, out_f32=p32,
                              actgrad_y=prev.y16, actgrad_act=prev.act1, colstats=g_pb, colstats_sum_only=True)
@@ -734,10 +735,14 @@ class SingleBranchNetEntity(_EntityBase):
         srcs = self._src_blob(None)
         C_ = cfg.common_modality_dim
         N = n_idx * k
-        x0 = torch.empty((N, ops.pad8(C_)), dtype=BF16, device=dev)
         p_drop = cfg.single_branch_input_dropout if (training and cfg.single_branch_input_dropout) else 0.0
         seed = (int(cfg.sampling_seed) << 8) ^ (0x11 if self.entity_name == "user" else 0x22) ^ \
             (int(rt.seed_salt) << 24)
+        self._fused = None
+        if training and self._fused_mlp_ok():
+            self._ctx = (flat, mods, keep_mask, k, p_drop, seed, None)
+            return self._embed_fused(srcs, flat, mods, keep_mask, k, N, p_drop, seed, defer_final_bn and k == 1)
+        x0 = torch.empty((N, ops.pad8(C_)), dtype=BF16, device=dev)
         keep_bits = torch.empty((N, (C_ + 7) // 8), dtype=torch.uint8, device=dev) if (training and p_drop) else None
         ops.row_gather_fwd(srcs, len(self.mod_names), flat, mods, k, C_, cfg.normalize_single_branch_input, p_drop,
                            seed, rt.step_dev, keep_mask, out_bf16=x0, err_flag=rt.err_flag, keep_bits_out=keep_bits)
@@ -745,6 +750,94 @@ class SingleBranchNetEntity(_EntityBase):
                                   defer_final_bn=defer_final_bn and k == 1)
         self._ctx = (flat, mods, keep_mask, k, p_drop, seed, keep_bits)
         return E
+
+    # ---- fused gather + single-branch MLP (csrc/mlp_fused.cu): chains of 1 or 2 Linear layers, all widths <= 64
+    def _fused_mlp_ok(self):
+        if os.environ.get("SBR_FUSED_MLP", "1") == "0":
+            return False
+        st = self.sb_chain.stages
+        if len(st) not in (1, 2) or self.entity_config.common_modality_dim > 64 or len(self.mod_names) > 16:
+            return False
+        if any(s.in_f > 64 or s.out_f > 64 for s in st):
+            return False
+        if any(s.bn is not None or s.act2 is not None for s in st[:-1]) or st[-1].act2 is not None:
+            return False  # (BatchNorm between the layers needs all rows between two GEMMs: layer-by-layer path)
+        return True
+
+    def _embed_fused(self, srcs, flat, mods, keep_mask, k, N, p_drop, seed, defer_bn):
+        rt = self._rt()
+        cfg = self.entity_config
+        dev = self._device()
+        st = self.sb_chain.stages
+        last = st[-1]
+        C_, D = cfg.common_modality_dim, last.out_f
+        layers = []
+        for s_ in st:
+            s_.refresh(False)
+            layers.append((s_.w16, s_.linear.bias.detach() if s_.linear.bias is not None else None, s_.in_f, s_.out_f,
+                           s_.act1))
+        desc = ops.mlp2_desc(srcs, len(self.mod_names), flat, mods, k, C_, cfg.normalize_single_branch_input, p_drop,
+                             seed, rt.step_dev, keep_mask, rt.err_flag, layers)
+        z = torch.empty((N, D), dtype=F32, device=dev)
+        stats, n_part, mi = None, 0, None
+        if last.bn is not None:
+            n_part = ops.mlp2_colstats_rows(N)
+            stats = torch.empty((n_part, 2 * D), dtype=F32, device=dev)
+        ops.mlp2_fwd(desc, N, C_, z, stats, n_part)
+        E = z
+        self.sb_chain.deferred = None
+        if last.bn is not None:
+            bn = last.bn
+            mi = torch.empty(2 * D, dtype=F32, device=dev)
+            ops.bn_finalize(stats, N, D, mi, bn.running_mean, bn.running_var, bn.num_batches_tracked, eps=bn.eps,
+                            momentum=bn.momentum, n_partials=n_part)
+            if defer_bn:
+                self.sb_chain.deferred = dict(z=z, mean_invstd=mi, gamma=bn.weight.detach(), beta=bn.bias.detach())
+                E = None
+            else:
+                E = torch.empty((N, D), dtype=F32, device=dev)
+                ops.bn_apply(z, mi, bn.weight.detach(), bn.bias.detach(), None, N, D, out_f32=E)
+        self._fused = dict(desc=desc, z=z, mi=mi, N=N)
+        return E
+
+    def _backward_fused(self, dE, grads, final_bn_sums):
+        rt = self._rt()
+        f = self._fused
+        st = self.sb_chain.stages
+        last = st[-1]
+        C_, D, N = self.entity_config.common_modality_dim, last.out_f, f["N"]
+        bn = None
+        if last.bn is not None:
+            if final_bn_sums is not None:
+                sums, reps = final_bn_sums, ops.BN_SUM_REPLICAS  # produced by the fused score/loss kernel
+            else:
+                sums, reps = rt.arena.take(2 * D), 1
+                ops.bn_bwd_reduce(dE, None, None, f["z"], f["mi"], N, D, sums)
+            bn = dict(mean_invstd=f["mi"], gamma=last.bn.weight.detach(), sums=sums, n_replicas=reps,
+                      dgamma=grads[id(last.bn.weight)], dbeta=grads[id(last.bn.bias)])
+        gw = [grads[id(s_.linear.weight)] for s_ in st]
+        gb = [grads[id(s_.linear.bias)] if s_.linear.bias is not None else None for s_ in st]
+        if last.bn is not None and last.act1 is None:
+            gb[-1] = None  # the Linear bias in front of a BatchNorm has an exactly-zero gradient: not computed
+        dx0 = torch.empty((N, C_), dtype=F32, device=dE.device)
+        ops.mlp2_bwd(f["desc"], N, C_, dE, f["z"], bn, gw, gb, dx0)
+        return dx0
+
+    def dropout_keep_bits(self):
+        """debugging / parity tests: the dropout keep decisions of the last training forward (uint8 [N, ceil(C / 8)],
+        bit j of byte c / 8 = column c), regenerated from the counter-based hash (seed, step, row, column group)"""
+        rt = self._rt()
+        flat, mods, keep_mask, k, p_drop, seed, keep_bits = self._ctx
+        if keep_bits is not None:
+            return keep_bits
+        C_ = self.entity_config.common_modality_dim
+        N = flat.numel() * k
+        bits = torch.empty((N, (C_ + 7) // 8), dtype=torch.uint8, device=flat.device)
+        tmp = torch.empty((N, ops.pad8(C_)), dtype=BF16, device=flat.device)
+        ops.row_gather_fwd(self._src_blob(None), len(self.mod_names), flat, mods, k, C_,
+                           self.entity_config.normalize_single_branch_input, p_drop, seed, rt.step_dev, keep_mask,
+                           out_bf16=tmp, keep_bits_out=bits)
+        return bits
 
     def build_plan(self, idx, mods, k, grads):
         """sorted-run plan of the gather backward; depends only on (indices, sampled modalities), so the trainer
@@ -762,8 +855,11 @@ class SingleBranchNetEntity(_EntityBase):
         flat, mods, keep_mask, k, p_drop, seed, keep_bits = self._ctx
         C_ = cfg.common_modality_dim
         aux = self._aux_streams(max(1, len(self.tables) - 1))
-        dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena, final_bn_sums=final_bn_sums,
-                                     wgrad_stream=aux[0] if aux else None)
+        if getattr(self, "_fused", None) is not None:
+            dx0 = self._backward_fused(dE, grads, final_bn_sums)
+        else:
+            dx0 = self.sb_chain.backward(dE, grads, need_dx=True, arena=rt.arena, final_bn_sums=final_bn_sums,
+                                         wgrad_stream=aux[0] if aux else None)
         srcs = self._src_blob(grads)
         if getattr(self, "_plan_built", False):
             plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
@@ -778,8 +874,17 @@ class SingleBranchNetEntity(_EntityBase):
                   for n, c in self.proj.items()]
         for n in self.bags:
             df, w = self.dfeat[n], self.modality_modules[n].embedding_layer.weight
-            thunks.append(lambda n=n, df=df, w=w: ops.tag_bag_bwd(df.codes, df.max_tags, df.pad_id,
-                                                                  self.table_grads[n], grads[id(w)]))
+
+            def bag_bwd(n=n, df=df, w=w):
+                if w.numel() <= ops.TAG_BAG_SMEM_FLOATS or C_ % 4 != 0:
+                    # small vocabulary: block-private shared-memory copies of the whole gradient matrix
+                    ops.tag_bag_bwd(df.codes, df.max_tags, df.pad_id, self.table_grads[n], grads[id(w)])
+                else:
+                    seg_ptr, seg_rows, seg_vals, seg_tag = df.tag_segments
+                    ops.spmm_csr(seg_ptr, seg_rows, seg_tag.numel(), self.table_grads[n], C_, None, None, grads[id(w)],
+                                 vals=seg_vals, row_map=seg_tag, atomic=True)
+                    self.table_grads[n].zero_()  # (memset: the accumulator table is cleared by its consumer)
+            thunks.append(bag_bwd)
         run_branches(thunks, aux)
 
     def get_and_reset_other_loss(self) -> Dict:

@@ -64,7 +64,7 @@ def test_graph_step_at_bench_shape_matches_oracle(batch, batch_norm):
     mods = {"user": ent_u._ctx[1].cpu().numpy().astype(np.int64).reshape(batch, 1),
             "item": ent_i._ctx[1].cpu().numpy().astype(np.int64).reshape(batch, 1 + workloads.N_NEG, 1)}
     names = {"user": ent_u.mod_names, "item": ent_i.mod_names}
-    drop = {"item": _unpack_keep(ent_i._ctx[6], 64)}
+    drop = {"item": _unpack_keep(ent_i.dropout_keep_bits(), 64)}
     assert 0.75 < drop["item"].mean() < 0.85  # p = 0.2
     p64 = {k: v.astype(np.float64) if v.dtype.kind == "f" else v for k, v in before.items()}
     net = O.OracleSBNet(conf, train)

@@ -193,7 +193,9 @@ def test_reference_style_loop_matches_fused_step(name):
     for k, p in dict(model.named_parameters()).items():
         diff = (p.detach() - after[k]).abs()
         assert float(diff.max()) <= 2.1 * spec["lr"], k
-        solid = fused[k].abs() > max(1e-3 * float(fused[k].abs().max()), 1e-5)
+        # (entries an order of magnitude above the 2e-3 * max-abs agreement of the two gradients checked above: below that
+        # a flipped bf16 rounding of one dz element may flip the sign of an entry, i.e. move the update by 2 * lr)
+        solid = fused[k].abs() > max(2e-2 * float(fused[k].abs().max()), 1e-5)
         if bool(solid.any()) and ldiff < 1e-6:
             assert float(diff[solid].max()) <= 0.02 * spec["lr"], k
 
@@ -395,3 +397,66 @@ def test_metric_kernel_pinned_against_reference_metrics():
     for ki, k in enumerate(ks):
         for name in ("ndcg", "recall", "precision"):
             assert np.abs(m[USER_METRICS.index(name), ki] - g[f"{name}@{k}"]).max() < 2e-6, (name, k)
+
+
+@pytest.mark.parametrize("name", ["ml1m_small", "pairwise_bn2", "plain_user_ssm"])
+def test_csr_route_matches_dense_route(name, monkeypatch):
+    """the sparse ('CSR') route of the interactions modality -- gather-sums of bf16 weight rows / bf16 dz rows -- gives
+    the step of the dense tensor-core route (same rounding points; only the fp32 summation order differs), including
+    gradient ACCUMULATION over two micro-batches (apply_optimizer=False twice)"""
+    res = {}
+    for route, density in (("dense", "0.0"), ("csr", "2.0")):
+        monkeypatch.setenv("SBR_DENSE_MIN_DENSITY", density)
+        spec, g, corpus, model = _build(name)
+        model.to(DEV).train()
+        _load(model, state_dict_of(g, "sd0/"))
+        tr = _trainer(model, spec)
+        u, i, mods, keep = _translate(model, g, 0)
+        for _ in range(2):
+            _load(model, state_dict_of(g, "sd0/"))  # (BatchNorm running statistics back to the start)
+            tr.step(u, i, mods, keep, apply_optimizer=False)
+        torch.cuda.synchronize()
+        kinds = {n: d.kind for ent in (model.user_embedding_module, model.item_embedding_module)
+                 if isinstance(ent, SingleBranchNetEntity) for n, d in ent.dfeat.items() if n == "interactions"}
+        assert kinds and all(k == ("csr" if route == "csr" else k) for k in kinds.values())
+        if route == "csr":
+            assert set(kinds.values()) == {"csr"}
+        params = dict(model.named_parameters())
+        res[route] = (tr.logits.cpu().numpy().copy(), {k: tr.grads[id(p)].cpu().numpy().copy() for k, p in params.items()})
+    assert _maxrel(res["csr"][0], res["dense"][0]) < 2e-3
+    gscale = max(float(np.abs(v).max()) for v in res["dense"][1].values())
+    for k, want in res["dense"][1].items():
+        got = res["csr"][1][k]
+        assert np.abs(got - want).max() <= 1e-2 * np.abs(want).max() + 1e-4 * gscale, k
+
+
+@pytest.mark.parametrize("name", ["ml1m_small", "central_max_bce", "tanh_dropout_norm"])
+def test_fused_mlp_kernels_match_layer_by_layer_path(name, monkeypatch):
+    """sbr_mlp2_fwd / sbr_mlp2_bwd (gather + SB-MLP + BatchNorm backward + both wgrads in one persistent kernel per
+    direction) against the layer-by-layer kernels on the same inputs: logits, losses and every gradient"""
+    res = {}
+    for route in ("0", "1"):
+        monkeypatch.setenv("SBR_FUSED_MLP", route)
+        spec, g, corpus, model = _build(name)
+        model.to(DEV).train()
+        _load(model, state_dict_of(g, "sd0/"))
+        tr = _trainer(model, spec)
+        u, i, mods, keep = _translate(model, g, 0)
+        tr.step(u, i, mods, keep, apply_optimizer=False)
+        torch.cuda.synchronize()
+        model.check_errors()
+        used = [getattr(e, "_fused", None) is not None for e in (model.user_embedding_module, model.item_embedding_module)
+                if isinstance(e, SingleBranchNetEntity)]
+        assert any(used) if route == "1" else not any(used)
+        params = dict(model.named_parameters())
+        res[route] = (tr.logits.cpu().numpy().copy(), tr.read_losses()["train/loss"],
+                      {k: tr.grads[id(p)].cpu().numpy().copy() for k, p in params.items()},
+                      {k: v.cpu().numpy().copy() for k, v in model.state_dict().items() if "running" in k})
+    assert _maxrel(res["1"][0], res["0"][0]) < 2e-3
+    assert res["1"][1] == pytest.approx(res["0"][1], rel=5e-4)
+    gscale = max(float(np.abs(v).max()) for v in res["0"][2].values())
+    for k, want in res["0"][2].items():
+        got = res["1"][2][k]
+        assert np.abs(got - want).max() <= 1e-2 * np.abs(want).max() + 1e-4 * gscale, k
+    for k, want in res["0"][3].items():
+        assert np.abs(res["1"][3][k] - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), k

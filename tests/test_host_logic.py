@@ -104,9 +104,17 @@ def test_fused_step_and_eval_call_sequence(name, monkeypatch):
     seq = stub.calls
     assert seq[0] == "sbr_step_begin" and seq[-1] == "sbr_adam_step" and "sbr_tick" not in seq
     score = "sbr_score_loss_bn" if "sbr_score_loss_bn" in seq else "sbr_score_loss"
-    assert score in seq and "sbr_row_gather_fwd" in seq and "sbr_row_gather_bwd_segmented" in seq
+    # entities whose single-branch net is 1-2 Linear layers of width <= 64 run the fused gather + MLP kernels
+    fused = "sbr_mlp2_fwd" in seq
+    assert score in seq and ("sbr_row_gather_fwd" in seq or fused) and "sbr_row_gather_bwd_segmented" in seq
     assert seq.index("sbr_gather_plan") < seq.index("sbr_row_gather_bwd_segmented")
-    assert seq.count("sbr_gemm_bf16") >= 3  # forward, wgrad, dgrad GEMMs on the tensor cores
+    if fused:
+        assert seq.count("sbr_mlp2_fwd") == seq.count("sbr_mlp2_bwd")
+        assert seq.index("sbr_mlp2_fwd") < seq.index(score) < seq.index("sbr_mlp2_bwd")
+        last_bwd = len(seq) - 1 - seq[::-1].index("sbr_row_gather_bwd_segmented")
+        assert seq.index("sbr_mlp2_bwd") < last_bwd  # dX0 of the fused backward feeds the sorted-run gather backward
+    if "sbr_row_gather_fwd" in seq:
+        assert seq.count("sbr_gemm_bf16") >= 3  # forward, wgrad, dgrad GEMMs on the tensor cores
     assert ("sbr_infonce" in seq) == (model.user_embedding_module.reg_enabled or model.item_embedding_module.reg_enabled)
     assert seq.index(score) < seq.index("sbr_row_gather_bwd_segmented") < seq.index("sbr_adam_step")
     assert set(tr.read_losses()) >= {"train/loss", "train/rec_loss", "train/reg_loss"}

@@ -567,3 +567,101 @@ def test_device_batch_feeder_epoch_semantics():
     with pytest.raises(ValueError):
         train.negative_sampling_strategy = "popular"
         DeviceBatchFeeder(train, batch_size=10, device=DEV)
+
+
+@pytest.mark.parametrize("rows,d,C_", [(700, 900, 64), (333, 1500, 512), (260, 300, 20), (1000, 4000, 128)])
+def test_spmm_bf16_values_transpose_accumulate(rows, d, C_):
+    """sbr_spmm_csr_bf16 (the CSR 'interactions' route): stored values are used (counts > 1), bf16 dense rows, fp32
+    accumulation; the transposed output accumulates (wgrad); row subsets with a device-side count"""
+    import scipy.sparse as sp
+    m = sp.random(rows, d, density=0.03, format="csr", random_state=rows + C_)
+    m.data[:] = np.random.default_rng(1).integers(1, 4, size=m.nnz)
+    m.sort_indices()
+    Cp = ops.pad8(C_)
+    Wt = torch.zeros(d, Cp, device=DEV, dtype=torch.bfloat16)
+    Wt[:, :C_] = torch.randn(d, C_, device=DEV).to(torch.bfloat16)
+    b = torch.randn(C_, device=DEV)
+    ip = torch.from_numpy(m.indptr.astype(np.int64)).to(DEV)
+    ix = torch.from_numpy(m.indices.astype(np.int32)).to(DEV)
+    vals = torch.from_numpy(m.data.astype(np.float32)).to(DEV)
+    X = torch.from_numpy(m.toarray()).float().to(DEV)
+    out = torch.empty(rows, C_, device=DEV)
+    out16 = torch.full((rows, Cp), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.spmm_csr(ip, ix, rows, Wt, C_, b, "relu", out, vals=vals, out_bf16=out16)
+    ref = torch.relu(X @ Wt[:, :C_].float() + b)
+    assert _relerr(out, ref) < 1e-5
+    assert _relerr(out16[:, :C_].float(), ref) < 5e-3 and (out16[:, C_:] == 0).all()
+    # all-ones shortcut
+    ops.spmm_csr(ip, ix, rows, Wt, C_, None, None, out)
+    assert _relerr(out, (X > 0).float() @ Wt[:, :C_].float()) < 1e-5
+    # wgrad through the transposed matrix: dW[:, j] += sum_r X[r, j] dz[r, :], twice (accumulation)
+    mt = m.T.tocsr()
+    mt.sort_indices()
+    ipt = torch.from_numpy(mt.indptr.astype(np.int64)).to(DEV)
+    ixt = torch.from_numpy(mt.indices.astype(np.int32)).to(DEV)
+    valst = torch.from_numpy(mt.data.astype(np.float32)).to(DEV)
+    dz = torch.zeros(rows, Cp, device=DEV, dtype=torch.bfloat16)
+    dz[:, :C_] = torch.randn(rows, C_, device=DEV).to(torch.bfloat16)
+    gw = torch.zeros(C_, d, device=DEV)
+    for _ in range(2):
+        ops.spmm_csr(ipt, ixt, d, dz, C_, None, None, gw, transpose_out=True, vals=valst, accumulate=True)
+    assert _relerr(gw, 2 * (dz[:, :C_].float().T @ X)) < 1e-5
+    # row subset: only the listed rows are computed / written, the count lives on the device
+    sel = torch.randperm(rows, device=DEV)[:rows // 3].to(torch.int32)
+    lst = torch.cat([sel, torch.full((17,), -7, dtype=torch.int32, device=DEV)])  # tail beyond the count: ignored
+    n_dev = torch.tensor([sel.numel()], dtype=torch.int32, device=DEV)
+    sub = torch.full((rows, C_), -1.0, device=DEV)
+    ops.spmm_csr(ip, ix, lst.numel(), Wt, C_, b, "relu", sub, vals=vals, row_list=lst, n_rows_dev=n_dev)
+    mask = torch.zeros(rows, dtype=torch.bool, device=DEV)
+    mask[sel.long()] = True
+    assert _relerr(sub[mask], ref[mask]) < 1e-5 and (sub[~mask] == -1).all()
+
+
+@pytest.mark.parametrize("n_rows,n_tags,max_tags,C", [(5000, 853, 7, 512), (900, 60, 4, 64)])
+def test_tag_bag_bwd_segment_route(n_rows, n_tags, max_tags, C):
+    """EmbeddingBag(mean) weight gradient of a LARGE vocabulary as per-tag gather-sums over <= 128-row segments
+    (DeviceFeature.tag_segments + sbr_spmm_csr segment mode) == the per-row scatter kernel"""
+    from types import SimpleNamespace
+
+    from sibrar_b200.feature_store import DeviceFeature
+    rng = np.random.default_rng(n_rows)
+    codes = np.full((n_rows, max_tags), n_tags, dtype=np.int64)
+    for r in range(n_rows):
+        n = int(rng.integers(0, max_tags + 1))
+        codes[r, :n] = rng.permutation(n_tags)[:n]
+    codes[:300, 0] = 3  # one very frequent tag: several segments
+    feat = SimpleNamespace(feature_definition=SimpleNamespace(name="t", type="tag"), values=codes,
+                           _indices=np.arange(n_rows), dim=n_tags)
+    df = DeviceFeature("t", feat, n_rows, DEV)
+    seg_ptr, seg_rows, seg_vals, seg_tag = df.tag_segments
+    assert int((seg_ptr[1:] - seg_ptr[:-1]).max()) <= 128
+    dy = torch.randn(n_rows, C, device=DEV)
+    want = torch.zeros(n_tags + 1, C, device=DEV)
+    ops.tag_bag_bwd(df.codes, df.max_tags, df.pad_id, dy.clone(), want)
+    got = torch.zeros(n_tags + 1, C, device=DEV)
+    ops.spmm_csr(seg_ptr, seg_rows, seg_tag.numel(), dy, C, None, None, got, vals=seg_vals, row_map=seg_tag, atomic=True)
+    assert _relerr(got, want) < 1e-5 and (got[n_tags] == 0).all()
+
+
+def test_adagrad():
+    """sbr_adam_step mode 2 == torch.optim.Adagrad(lr, weight_decay) (train/trainer.py:62-68)"""
+    shapes = [(70, 33), (5000,), (3, 4097), (1,)]
+    ps = [torch.randn(*s, device=DEV) for s in shapes]
+    ref = [p.clone().requires_grad_() for p in ps]
+    opt = torch.optim.Adagrad(ref, lr=1e-2, weight_decay=0.1)
+    grads = [torch.zeros_like(p) for p in ps]
+    shadows = [torch.zeros((70, 40), dtype=torch.bfloat16, device=DEV), None, None, None]
+    plan = ops.AdamPlan([dict(param=p, grad=g, exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p), shadow=s)
+                         for p, g, s in zip(ps, grads, shadows)], DEV)
+    step = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for it in range(3):
+        ops.tick(step)
+        for g, r in zip(grads, ref):
+            g.copy_(torch.randn_like(g))
+            r.grad = g.clone()
+        opt.step()
+        plan.step(1e-2, 0.9, 0.999, 1e-10, 0.1, 2, step)
+        for p, r, g in zip(ps, ref, grads):
+            assert _relerr(p, r.detach()) < 1e-5
+            assert g.abs().max().item() == 0
+    assert torch.equal(shadows[0][:, :33], ps[0].to(torch.bfloat16))
