@@ -242,7 +242,7 @@ class CallProfiler:
             return (name, i(1), i(2), i(3))
         if name == "sbr_splitk_reduce":
             return (name, i(1), i(4), i(5))
-        if name == "sbr_spmm_csr":
+        if name in ("sbr_spmm_csr", "sbr_spmm_csr_bf16"):
             return (name, i(3), i(6))
         if name == "sbr_adam_step":
             return (name, i(2))
@@ -327,10 +327,11 @@ def algorithmic_work(key, nnz_hint=None):
     if n == "sbr_splitk_reduce":
         _, split, rows, cols = key
         return 0.0, rows * cols * (4.0 * split + 6)  # (the slices exist only because the GEMM was split)
-    if n == "sbr_spmm_csr":  # one weight row per stored entry (+ its index), output rows
+    if n in ("sbr_spmm_csr", "sbr_spmm_csr_bf16"):  # one dense row per stored entry (+ its index), output rows
         _, rows, C = key
         nnz = nnz_hint if nnz_hint else rows
-        return 2.0 * nnz * C, nnz * (4 + 4.0 * C) + rows * C * 4
+        eb = 2.0 if n.endswith("bf16") else 4.0
+        return 2.0 * nnz * C, nnz * (4 + eb * C) + rows * C * 4
     if n == "sbr_adam_step":  # p, g, m, v read; p, m, v, zeroed g written; bf16 shadow
         return 0.0, key[1] * 1024 * 34.0
     if n in ("sbr_tag_bag_fwd", "sbr_tag_bag_bwd"):

@@ -121,7 +121,12 @@ int sbr_spmm_csr(const int64_t* indptr, const int32_t* indices, const float* val
 int sbr_spmm_csr_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows,
                       const void* dense_bf16, int64_t ld_dense, int64_t C, const float* bias, int act, float* out,
                       int64_t ld_out, int transpose_out, int accumulate, void* out_bf16, int64_t ld_bf16,
-                      const int32_t* row_list, const int32_t* n_rows_dev, void* stream);
+                      const int32_t* row_list, const int32_t* n_rows_dev, const int32_t* seg_row,
+                      const int32_t* long_rows, int64_t n_long, void* stream);
+/* seg_row (optional): `indptr` holds SEGMENTS of at most 256 entries of the matrix rows (`rows` = number of segments), so
+ * that a popular item / a heavy user is not one warp's serial loop; seg_row[s] = output row | (row has several segments
+ * << 31).  Segments of such long rows are combined with atomics; for the row-major output the library clears the
+ * `n_long` rows listed in long_rows first and applies bias / activation (+ the bf16 copy) to them afterwards. */
 
 /* ------------------------------------------------------------------------------------------------ modality sampling
  * Per (row, slot) choose k distinct modalities out of n_mods (optionally slot 0 fixed to `central`), Philox keyed

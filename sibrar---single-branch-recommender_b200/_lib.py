@@ -69,7 +69,7 @@ _PROTOS = {
     "sbr_spmm_csr": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int, c_vp,
                      c_i64, c_vp, C.c_int, c_vp],
     "sbr_spmm_csr_bf16": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int,
-                          c_vp, c_i64, c_vp, c_vp, c_vp],
+                          c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "sbr_sample_modalities": [c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_u64, c_vp, c_vp],
     "sbr_tick": [c_vp, c_vp],
     "sbr_step_begin": [c_vp, c_vp, c_vp, c_i64, c_vp],

@@ -454,14 +454,24 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       if (lane == 0) mbar_arrive(df_empty);
     }
     if (p.colstats != nullptr) {
-      // this warp's private row of partial sums (added up in a fixed order by sbr_bn_finalize: deterministic statistics)
-      float* rowp = p.colstats + (size_t)(blockIdx.x * 4 + q) * 2 * p.D;
+      // one row of partial sums per CTA: the four lane quarters are added in a fixed order (deterministic statistics;
+      // sbr_bn_finalize adds the rows of all CTAs in a fixed order as well)
+      float* s_part = reinterpret_cast<float*>(sA1);  // (the hidden-activation tile is no longer needed)
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int col = 32 * i + lane;
-        if (col < p.D) {
-          rowp[col] = cs_acc[i];
-          rowp[p.D + col] = cq_acc[i];
+        s_part[q * 128 + 32 * i + lane] = cs_acc[i];
+        s_part[q * 128 + 64 + 32 * i + lane] = cq_acc[i];
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
+      if (q == 0) {
+        float* rowp = p.colstats + (size_t)blockIdx.x * 2 * p.D;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int col = 32 * i + lane;
+          if (col < p.D) {
+            rowp[col] = ((s_part[col] + s_part[128 + col]) + s_part[256 + col]) + s_part[384 + col];
+            rowp[p.D + col] = ((s_part[64 + col] + s_part[128 + 64 + col]) + s_part[256 + 64 + col]) + s_part[384 + 64 + col];
+          }
         }
       }
     }
@@ -929,7 +939,7 @@ int make_weight_maps(const sbr_mlp2_desc_t* d, CUtensorMap* tm) {
 
 }  // namespace
 
-extern "C" int sbr_mlp2_colstats_rows(int64_t n_rows) { return (int)(4 * mlp2_grid(n_rows)); }
+extern "C" int sbr_mlp2_colstats_rows(int64_t n_rows) { return (int)mlp2_grid(n_rows); }
 
 extern "C" int sbr_mlp2_fwd(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, float* z, int64_t ldz, float* colstats,
                             int colstats_rows, void* stream) {
@@ -946,8 +956,8 @@ extern "C" int sbr_mlp2_fwd(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, flo
   p.z = z; p.ldz = ldz; p.colstats = colstats;
   SBR_REQUIRE(ldz >= p.D, "sbr_mlp2_fwd: ldz < D");
   const int64_t grid = mlp2_grid(n_rows);
-  SBR_REQUIRE(colstats == nullptr || colstats_rows >= 4 * grid, "sbr_mlp2_fwd: colstats_rows=%d < %lld", colstats_rows,
-              (long long)(4 * grid));
+  SBR_REQUIRE(colstats == nullptr || colstats_rows >= grid, "sbr_mlp2_fwd: colstats_rows=%d < %lld", colstats_rows,
+              (long long)grid);
   CUtensorMap tm[2];
   rc = make_weight_maps(d, tm);
   if (rc) return rc;
@@ -959,9 +969,9 @@ extern "C" int sbr_mlp2_fwd(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, flo
     SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     configured = true;
   }
-  if (colstats != nullptr && colstats_rows > 4 * grid)  // rows no CTA writes must not hold garbage
-    SBR_CHECK_CUDA(cudaMemsetAsync(colstats + (size_t)4 * grid * 2 * p.D, 0,
-                                   (size_t)(colstats_rows - 4 * grid) * 2 * p.D * sizeof(float), S(stream)));
+  if (colstats != nullptr && colstats_rows > grid)  // rows no CTA writes must not hold garbage
+    SBR_CHECK_CUDA(cudaMemsetAsync(colstats + (size_t)grid * 2 * p.D, 0,
+                                   (size_t)(colstats_rows - grid) * 2 * p.D * sizeof(float), S(stream)));
   const bool poll = mlp2_poll();
   auto kern = d->n_layers == 1 ? (poll ? mlp2_fwd_kernel<1, true> : mlp2_fwd_kernel<1, false>)
                                : (poll ? mlp2_fwd_kernel<2, true> : mlp2_fwd_kernel<2, false>);

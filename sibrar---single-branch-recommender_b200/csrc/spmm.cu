@@ -217,7 +217,7 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
                  const float* __restrict__ vals, int64_t rows, const bf16* __restrict__ dense, int64_t ld_dense, int C,
                  const float* __restrict__ bias, int act, float* __restrict__ out, int64_t ld_out, int accumulate,
                  bf16* __restrict__ out16, int64_t ld_out16, const int32_t* __restrict__ row_list,
-                 const int32_t* __restrict__ n_rows_dev) {
+                 const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ seg_row) {
   SBR_PDL_ENTRY();
   extern __shared__ float s_tile[];  // TRANSPOSE: [C][33]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -230,8 +230,14 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
   for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
     const int local = warp * ROWS_PER_WARP + rr;
     const int64_t slot = row_base + local;
-    // row_list: the CSR rows to compute (and the output rows they go to); otherwise row = slot
+    // row_list: the CSR rows to compute (and the output rows they go to); otherwise row = slot.
+    // seg_row: `indptr` describes SEGMENTS (<= 256 entries) of the matrix rows -- long rows (a popular item, a heavy
+    // user) are cut so that no warp walks thousands of entries; seg_row[s] = output row, bit 31 = the row has several
+    // segments (their partial sums are combined with atomics; bias / activation are applied by the fix-up pass)
     const int64_t row = slot < rows ? (row_list ? (int64_t)__ldg(row_list + slot) : slot) : -1;
+    const int32_t sr = (seg_row != nullptr && row >= 0) ? __ldg(seg_row + row) : 0;
+    const bool multi = sr < 0;
+    const int64_t orow = seg_row != nullptr ? (int64_t)(sr & 0x7fffffff) : row;
     float acc[NV8][8];
 #pragma unroll
     for (int i = 0; i < NV8; ++i)
@@ -280,6 +286,15 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
       const int c8 = lane + 32 * i;
       if (c8 >= C8) continue;
       float v[8];
+      if (!TRANSPOSE && multi) {  // partial sum of one segment of a long row
+        if (row >= 0 && out != nullptr) {
+          float* dst = out + orow * ld_out + 8 * c8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (8 * c8 + j < C) atomicAdd(dst + j, acc[i][j]);
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = 8 * c8 + j;
@@ -291,7 +306,7 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
           if (8 * c8 + j < C) s_tile[(8 * c8 + j) * 33 + local] = v[j];
       } else if (row >= 0) {
         if (out != nullptr) {
-          float* dst = out + row * ld_out + 8 * c8;
+          float* dst = out + orow * ld_out + 8 * c8;
           if (8 * c8 + 8 <= C && (ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
             float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
             if (accumulate) {
@@ -313,7 +328,7 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2)
             h[t2] = __floats2bfloat162_rn(8 * c8 + 2 * t2 < C ? v[2 * t2] : 0.f, 8 * c8 + 2 * t2 + 1 < C ? v[2 * t2 + 1] : 0.f);
-          *reinterpret_cast<uint4*>(out16 + row * ld_out16 + 8 * c8) = o;
+          *reinterpret_cast<uint4*>(out16 + orow * ld_out16 + 8 * c8) = o;
         }
       }
     }
@@ -323,11 +338,34 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
     const int64_t slot = row_base + lane;
     if (slot < rows) {
       const int64_t row = row_list ? (int64_t)__ldg(row_list + slot) : slot;
+      const int32_t sr = seg_row != nullptr ? __ldg(seg_row + row) : 0;
+      const int64_t orow = seg_row != nullptr ? (int64_t)(sr & 0x7fffffff) : row;
       for (int c = warp; c < C; c += 8) {
-        float* dst = out + (int64_t)c * ld_out + row;
+        float* dst = out + (int64_t)c * ld_out + orow;
         const float v = s_tile[c * 33 + lane];
-        *dst = accumulate ? *dst + v : v;
+        if (sr < 0) atomicAdd(dst, v);  // (several segments of one row: the output must hold the running sum)
+        else *dst = accumulate ? *dst + v : v;
       }
+    }
+  }
+}
+
+// long rows of the segmented forward: cleared before the main pass, bias + activation (+ bf16 copy) afterwards
+__global__ void spmm_long_rows_kernel(const int32_t* __restrict__ long_rows, int n_long, float* __restrict__ out,
+                                      int64_t ld_out, int C, const float* __restrict__ bias, int act,
+                                      bf16* __restrict__ out16, int64_t ld_out16, int finish) {
+  SBR_PDL_ENTRY();
+  const int64_t total = (int64_t)n_long * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = __ldg(long_rows + i / C);
+    const int c = (int)(i % C);
+    float* p = out + r * ld_out + c;
+    if (!finish) {
+      *p = 0.f;
+    } else {
+      const float v = act_fwd(act, *p + (bias ? bias[c] : 0.f));
+      *p = v;
+      if (out16) out16[r * ld_out16 + c] = __float2bfloat16(v);
     }
   }
 }
@@ -336,7 +374,7 @@ template <int NV8>
 int launch_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows, const bf16* dense,
                 int64_t ld_dense, int C, const float* bias, int act, float* out, int64_t ld_out, int transpose_out,
                 int accumulate, bf16* out16, int64_t ld_out16, const int32_t* row_list, const int32_t* n_rows_dev,
-                cudaStream_t st) {
+                const int32_t* seg_row, cudaStream_t st) {
   if (transpose_out) {
     const size_t smem = (size_t)C * 33 * sizeof(float);
     static size_t configured = 0;
@@ -347,11 +385,11 @@ int launch_bf16(const int64_t* indptr, const int32_t* indices, const float* vals
     }
     SBR_CHECK_CUDA(sbr_launch(spmm_bf16_kernel<NV8, true>, dim3(cdiv(rows, 32)), dim3(256), smem, st, indptr, indices,
                               vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16, ld_out16,
-                              row_list, n_rows_dev));
+                              row_list, n_rows_dev, seg_row));
   } else {
     SBR_CHECK_CUDA(sbr_launch(spmm_bf16_kernel<NV8, false>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, st, indptr,
                               indices, vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16,
-                              ld_out16, row_list, n_rows_dev));
+                              ld_out16, row_list, n_rows_dev, seg_row));
   }
   return SBR_OK;
 }
@@ -361,7 +399,8 @@ int launch_bf16(const int64_t* indptr, const int32_t* indices, const float* vals
 extern "C" int sbr_spmm_csr_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows,
                                  const void* dense_bf16, int64_t ld_dense, int64_t C, const float* bias, int act,
                                  float* out, int64_t ld_out, int transpose_out, int accumulate, void* out_bf16,
-                                 int64_t ld_bf16, const int32_t* row_list, const int32_t* n_rows_dev, void* stream) {
+                                 int64_t ld_bf16, const int32_t* row_list, const int32_t* n_rows_dev,
+                                 const int32_t* seg_row, const int32_t* long_rows, int64_t n_long, void* stream) {
   SBR_REQUIRE(indptr && indices && dense_bf16 && (out || out_bf16) && rows > 0, "sbr_spmm_csr_bf16: bad arguments");
   SBR_REQUIRE(C > 0 && C <= 1024, "sbr_spmm_csr_bf16: C=%lld not in [1, 1024]", (long long)C);
   SBR_REQUIRE(ld_dense % 8 == 0 && ld_dense >= ((C + 7) / 8) * 8 && (reinterpret_cast<uintptr_t>(dense_bf16) & 15) == 0,
@@ -371,17 +410,31 @@ extern "C" int sbr_spmm_csr_bf16(const int64_t* indptr, const int32_t* indices, 
   SBR_REQUIRE(out_bf16 == nullptr || (ld_bf16 % 8 == 0 && ld_bf16 >= ((C + 7) / 8) * 8 &&
                                       (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0),
               "sbr_spmm_csr_bf16: bf16 output rows must be 16-byte aligned and padded to 8 columns");
+  SBR_REQUIRE(seg_row == nullptr || (n_long >= 0 && (n_long == 0 || long_rows) && (transpose_out || out)),
+              "sbr_spmm_csr_bf16: segmented rows need the fp32 output and the list of long rows");
+  SBR_REQUIRE(seg_row == nullptr || !transpose_out || accumulate,
+              "sbr_spmm_csr_bf16: the segmented transposed output accumulates (accumulate = 1)");
   const bf16* d = reinterpret_cast<const bf16*>(dense_bf16);
   bf16* o16 = reinterpret_cast<bf16*>(out_bf16);
   const int nv8 = (int)(((C + 7) / 8 + 31) / 32);
   cudaStream_t st = S(stream);
-#define SBR_SPMM_BF16(N)                                                                                          \
-  return launch_bf16<N>(indptr, indices, vals, rows, d, ld_dense, (int)C, bias, act, out, ld_out, transpose_out, \
-                        accumulate, o16, ld_bf16, row_list, n_rows_dev, st)
-  if (nv8 <= 1) SBR_SPMM_BF16(1);
-  if (nv8 <= 2) SBR_SPMM_BF16(2);
-  SBR_SPMM_BF16(4);
+  const bool fix = seg_row != nullptr && !transpose_out && n_long > 0;
+  if (fix)
+    SBR_CHECK_CUDA(sbr_launch(spmm_long_rows_kernel, dim3(cdiv(n_long * C, 256)), dim3(256), (size_t)0, st, long_rows,
+                              (int)n_long, out, ld_out, (int)C, bias, act, o16, ld_bf16, 0));
+  int rc;
+#define SBR_SPMM_BF16(N)                                                                                        \
+  rc = launch_bf16<N>(indptr, indices, vals, rows, d, ld_dense, (int)C, bias, act, out, ld_out, transpose_out, \
+                      accumulate, o16, ld_bf16, row_list, n_rows_dev, seg_row, st)
+  if (nv8 <= 1) { SBR_SPMM_BF16(1); }
+  else if (nv8 <= 2) { SBR_SPMM_BF16(2); }
+  else { SBR_SPMM_BF16(4); }
 #undef SBR_SPMM_BF16
+  if (rc) return rc;
+  if (fix)
+    SBR_CHECK_CUDA(sbr_launch(spmm_long_rows_kernel, dim3(cdiv(n_long * C, 256)), dim3(256), (size_t)0, st, long_rows,
+                              (int)n_long, out, ld_out, (int)C, bias, act, o16, ld_bf16, 1));
+  return SBR_OK;
 }
 
 extern "C" int sbr_spmm_csr(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows,

@@ -41,7 +41,7 @@ class DeviceFeature:
             remap[idx] = np.arange(len(idx), dtype=np.int32)
             self.remap = torch.from_numpy(remap).to(device)
         self.x16 = self.csr = self.csr_t = self.codes = self.bits = self.bits_t = None
-        self.csr_vals = self.csr_t_vals = None
+        self.csr_vals = self.csr_t_vals = self.csr_seg = self.csr_t_seg = None
         self.max_tags, self.pad_id, self.n_cat = 0, -1, 0
         if self.type == "categorical":
             self.kind = "categorical"
@@ -106,6 +106,8 @@ class DeviceFeature:
                               torch.from_numpy(mt.indices.astype(np.int32)).to(device))
                 self.csr_vals = vals
                 self.csr_t_vals = None if binary else torch.from_numpy(mt.data.astype(np.float32)).to(device)
+                self.csr_seg = csr_segments(m.indptr, device)
+                self.csr_t_seg = csr_segments(mt.indptr, device)
         else:
             self.kind = "dense"
             v = np.asarray(values, dtype=np.float32)
@@ -126,6 +128,30 @@ class DeviceFeature:
             if pair is not None:
                 n += sum(t.numel() * t.element_size() for t in pair)
         return n
+
+
+CSR_SEGMENT = 256  # entries per warp-sized unit of work of the sparse kernels
+
+
+def csr_segments(indptr: np.ndarray, device, seg: int = CSR_SEGMENT):
+    """rows of a CSR matrix cut into segments of at most ``seg`` entries (None when no row is longer): ``seg_ptr`` int64
+    [n_seg + 1] (a refinement of indptr), ``seg_row`` int32 [n_seg] = row | (row has several segments) << 31,
+    ``long_rows`` int32 -- see sbr_spmm_csr_bf16"""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    lens = np.diff(indptr)
+    if lens.size == 0 or int(lens.max()) <= seg:
+        return None
+    per_row = np.maximum(1, -(-lens // seg))
+    seg_row = np.repeat(np.arange(lens.size, dtype=np.int64), per_row)
+    first = np.cumsum(per_row) - per_row
+    k = np.arange(seg_row.size, dtype=np.int64) - first[seg_row]
+    seg_beg = indptr[seg_row] + k * seg
+    seg_ptr = np.concatenate([seg_beg, indptr[-1:]])
+    multi = per_row[seg_row] > 1
+    enc = (seg_row.astype(np.uint32) | (multi.astype(np.uint32) << np.uint32(31))).view(np.int32)
+    long_rows = np.flatnonzero(per_row > 1).astype(np.int32)
+    return (torch.from_numpy(seg_ptr).to(device), torch.from_numpy(enc).to(device),
+            torch.from_numpy(long_rows).to(device))
 
 
 def csr_to_device(m, device):

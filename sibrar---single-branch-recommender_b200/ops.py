@@ -136,17 +136,26 @@ def csr_to_dense_bf16(indptr, indices, rows, cols, vals=None) -> torch.Tensor:
 
 
 def spmm_csr(indptr, indices, rows, dense, C_, bias, act, out, transpose_out=False, vals=None, accumulate=False,
-             out_bf16=None, row_map=None, atomic=False, row_list=None, n_rows_dev=None):
+             out_bf16=None, row_map=None, atomic=False, row_list=None, n_rows_dev=None, segments=None):
     """out[r] = act(sum_p vals[p] * dense[indices[p]] + bias); ``transpose_out``: out is [C, rows] (the wgrad through
     the transposed CSR), ``accumulate``: out += result.  ``dense`` fp32 or bf16 (fp32 accumulation either way).
     fp32 only: ``row_map`` / ``atomic`` (segment mode).  bf16 only: ``row_list`` / ``n_rows_dev`` (row subset)."""
     if dense.dtype == BF16:
         assert row_map is None and not atomic
+        seg_ptr = seg_row = long_rows = None
+        if segments is not None:  # (seg_ptr int64 [n_seg + 1], seg_row int32 [n_seg], long_rows int32 [n_long])
+            seg_ptr, seg_row, long_rows = segments
+            indptr, rows = seg_ptr, seg_row.numel()
+            if not transpose_out and long_rows.numel() > 0:
+                from . import _lib
+                _lib._launches[0] += 2  # the clear / fix-up passes over the long rows
         call("sbr_spmm_csr_bf16", ptr(indptr), ptr(indices), ptr(vals), int(rows), ptr(dense), dense.stride(0),
              int(C_), ptr(bias), _act(act), ptr(out), out.stride(0) if out is not None else 0, int(transpose_out),
              int(bool(accumulate)), ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(row_list),
-             ptr(n_rows_dev), stream_ptr())
+             ptr(n_rows_dev), ptr(seg_row), ptr(long_rows), long_rows.numel() if long_rows is not None else 0,
+             stream_ptr())
         return
+    assert segments is None
     assert row_list is None and n_rows_dev is None
     call("sbr_spmm_csr", ptr(indptr), ptr(indices), ptr(vals), int(rows), ptr(dense), dense.stride(0), int(C_),
          ptr(bias), _act(act), ptr(out), out.stride(0) if out is not None else 0, int(transpose_out),

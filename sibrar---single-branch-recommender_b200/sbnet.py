@@ -230,8 +230,11 @@ class Chain:
                 if first_csr:
                     ip, ix = self.feature.csr
                     # gather-sum of bf16 weight rows, fp32 accumulation: the rounding points of the dense route
+                    seg = self.feature.csr_seg
+                    if seg is not None and y32 is None:  # (the partial sums of long rows need an fp32 home)
+                        y32 = torch.empty((rows, st.out_f), dtype=F32, device=dev)
                     ops.spmm_csr(ip, ix, rows, st.wt16, st.out_f, bias, st.act1, y32, vals=self.feature.csr_vals,
-                                 out_bf16=y16)
+                                 out_bf16=y16, segments=seg)
                 else:
                     first_bits = si == 0 and self.bits_input
                     mm = (lambda *a, **k: ops.gemm_bits(self.feature.bits, *a[1:], **k)) if first_bits else ops.gemm
@@ -339,7 +342,7 @@ class Chain:
                 ip_t, ix_t = self.feature.csr_t
                 # accumulates like every other wgrad of the path (gradient accumulation over micro-batches)
                 ops.spmm_csr(ip_t, ix_t, st.in_f, dz16, st.out_f, None, None, g_w, transpose_out=True,
-                             vals=self.feature.csr_t_vals, accumulate=True)
+                             vals=self.feature.csr_t_vals, accumulate=True, segments=self.feature.csr_t_seg)
             else:
                 x16 = st.x if si > 0 or self.feature is None else self.feature.x16
                 tiles = -(-st.in_f // 128) * -(-st.out_f // (64 if st.out_f <= 64 else 128 if st.out_f <= 128 else 256))

@@ -665,3 +665,42 @@ def test_adagrad():
             assert _relerr(p, r.detach()) < 1e-5
             assert g.abs().max().item() == 0
     assert torch.equal(shadows[0][:, :33], ps[0].to(torch.bfloat16))
+
+
+def test_spmm_bf16_segmented_long_rows():
+    """rows longer than 256 entries are cut into segments (feature_store.csr_segments): same results as the plain
+    kernel for the forward (bias + activation applied once per row, bf16 copy included) and the accumulating wgrad"""
+    import scipy.sparse as sp
+    from sibrar_b200.feature_store import csr_segments
+    rows, d, C_ = 400, 3000, 128
+    m = sp.random(rows, d, density=0.01, format="lil", random_state=5)
+    rng = np.random.default_rng(5)
+    for r, n in ((0, 2900), (7, 700), (399, 257)):  # a popular item, a heavy user, one entry over the limit
+        m[r, rng.choice(d, size=n, replace=False)] = 1
+    m = m.tocsr()
+    m.data[:] = 1
+    m.sort_indices()
+    seg = csr_segments(m.indptr, DEV)
+    assert seg is not None and seg[2].cpu().tolist() == [0, 7, 399]
+    assert int((seg[0][1:] - seg[0][:-1]).max()) <= 256
+    Wt = torch.randn(d, C_, device=DEV).to(torch.bfloat16)
+    b = torch.randn(C_, device=DEV)
+    ip = torch.from_numpy(m.indptr.astype(np.int64)).to(DEV)
+    ix = torch.from_numpy(m.indices.astype(np.int32)).to(DEV)
+    X = torch.from_numpy(m.toarray()).float().to(DEV)
+    ref = torch.relu(X @ Wt.float() + b)
+    out = torch.full((rows, C_), float("nan"), device=DEV)
+    out16 = torch.full((rows, C_), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.spmm_csr(ip, ix, rows, Wt, C_, b, "relu", out, out_bf16=out16, segments=seg)
+    assert _relerr(out, ref) < 1e-5 and _relerr(out16.float(), ref) < 5e-3
+    mt = m.T.tocsr()
+    mt.sort_indices()
+    segt = csr_segments(mt.indptr, DEV, seg=64)  # (short segments: many long rows on the transposed side too)
+    assert segt is not None
+    ipt = torch.from_numpy(mt.indptr.astype(np.int64)).to(DEV)
+    ixt = torch.from_numpy(mt.indices.astype(np.int32)).to(DEV)
+    dz = torch.randn(rows, C_, device=DEV).to(torch.bfloat16)
+    gw = torch.zeros(C_, d, device=DEV)
+    for _ in range(2):
+        ops.spmm_csr(ipt, ixt, d, dz, C_, None, None, gw, transpose_out=True, accumulate=True, segments=segt)
+    assert _relerr(gw, 2 * (dz.float().T @ X)) < 1e-5
