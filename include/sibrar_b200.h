@@ -122,11 +122,14 @@ int sbr_spmm_csr_bf16(const int64_t* indptr, const int32_t* indices, const float
                       const void* dense_bf16, int64_t ld_dense, int64_t C, const float* bias, int act, float* out,
                       int64_t ld_out, int transpose_out, int accumulate, void* out_bf16, int64_t ld_bf16,
                       const int32_t* row_list, const int32_t* n_rows_dev, const int32_t* seg_row,
-                      const int32_t* long_rows, int64_t n_long, void* stream);
+                      const int32_t* long_rows, int64_t n_long, const int32_t* out_pos, void* stream);
 /* seg_row (optional): `indptr` holds SEGMENTS of at most 256 entries of the matrix rows (`rows` = number of segments), so
  * that a popular item / a heavy user is not one warp's serial loop; seg_row[s] = output row | (row has several segments
  * << 31).  Segments of such long rows are combined with atomics; for the row-major output the library clears the
- * `n_long` rows listed in long_rows first and applies bias / activation (+ the bf16 copy) to them afterwards. */
+ * `n_long` rows listed in long_rows first and applies bias / activation (+ the bf16 copy) to them afterwards.
+ * out_pos (optional, row-major fp32 output only): matrix row -> output row (the compact positions of
+ * sbr_mark_referenced).  With it every unit ADDS its raw partial sum into the (caller-cleared) output row -- no bias,
+ * activation or bf16 copy; the caller finishes the rows (sbr_splitk_reduce with one slice). */
 
 /* ------------------------------------------------------------------------------------------------ modality sampling
  * Per (row, slot) choose k distinct modalities out of n_mods (optionally slot 0 fixed to `central`), Philox keyed
@@ -186,6 +189,40 @@ int sbr_row_gather_bwd_segmented(const sbr_modality_src_t* srcs_dev, int n_mods,
                                  int64_t n_rows, int C, int normalize, float p_drop, uint64_t seed,
                                  const int64_t* step_dev, const uint8_t* keep_mask, const float* dx, int64_t ld_dx,
                                  int rows_per_warp, const uint8_t* keep_bits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ referenced rows
+ * The per-step subset of feature rows a modality projection has to compute (the reference projects exactly the rows of the
+ * batch: algorithms/sgd_alg.py:1949-1974 + data/Feature.py:140-162).  One sbr_ref_table_t per modality of an entity
+ * (device array [n_mods]); stamp == NULL: the modality keeps the whole-table route.
+ *   stamp [n_rows] int32 (0-initialised once), pos [n_rows] int32: row -> compact position of this step,
+ *   list [capacity] int32: compact position -> row, count: device int32 cleared by the caller before the call;
+ *   seg_first (optional, int64 [n_rows + 1]): first segment of every row of a segmented CSR matrix -- then the row's
+ *   segments are appended to seg_list / seg_count as the units of work of the sparse kernels. */
+typedef struct {
+  int32_t* stamp;
+  int32_t* pos;
+  int32_t* list;
+  int32_t* count;
+  const int64_t* seg_first;
+  int32_t* seg_list;
+  int32_t* seg_count;
+} sbr_ref_table_t;
+
+/* every (entity, modality) slot of the step marks its feature row.  epoch_dev: int64 [2] owned by the caller, zero
+ * before the first call (the kernel advances the epoch itself: [0] = epoch, [1] = finished blocks) */
+int sbr_mark_referenced(const sbr_modality_src_t* srcs_dev, int n_mods, const int64_t* idx, const uint8_t* mods,
+                        int64_t n_idx, int k, int64_t* epoch_dev, const sbr_ref_table_t* tabs_dev, void* stream);
+/* dst[slot, :] = src[list[slot], :] for slot < *count_dev, zero rows up to `capacity` (bf16 rows, 16-byte aligned) */
+int sbr_gather_rows_bf16(const void* src, int64_t ld_src, const int32_t* list, const int32_t* count_dev,
+                         int64_t capacity, int64_t cols, void* dst, int64_t ld_dst, void* stream);
+/* wgrad of a sparse-input Linear over the listed units (rows, or segments with seg_row as in sbr_spmm_csr_bf16):
+ * gT[j, :] += vals[p] * dz[pos[row], :] for every stored entry (p, j) of the unit; gT is the TRANSPOSED gradient [d, C] */
+int sbr_spmm_scatter_wgrad(const int64_t* indptr, const int32_t* indices, const float* vals, const int32_t* unit_list,
+                           const int32_t* n_units_dev, int64_t max_units, const int32_t* seg_row, const int32_t* pos,
+                           const void* dz_bf16, int64_t ld_dz, int64_t C, float* gT, int64_t ld_gT, void* stream);
+/* dst[c, r] += src[r, c], src cleared */
+int sbr_transpose_add_f32(float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------ fused single-branch MLP
  * One persistent kernel per direction for an entity whose single-branch network is 1 or 2 Linear layers of width <= 64

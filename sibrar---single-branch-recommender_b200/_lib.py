@@ -52,6 +52,11 @@ class Mlp2Bn(C.Structure):
                 ("dbeta", c_vp)]
 
 
+class RefTable(C.Structure):
+    _fields_ = [("stamp", c_vp), ("pos", c_vp), ("list", c_vp), ("count", c_vp), ("seg_first", c_vp),
+                ("seg_list", c_vp), ("seg_count", c_vp)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", c_vp), ("grad", c_vp), ("exp_avg", c_vp), ("exp_avg_sq", c_vp), ("shadow_bf16", c_vp),
                 ("numel", c_i64), ("cols", c_i64), ("shadow_ld", c_i64)]
@@ -69,7 +74,11 @@ _PROTOS = {
     "sbr_spmm_csr": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int, c_vp,
                      c_i64, c_vp, C.c_int, c_vp],
     "sbr_spmm_csr_bf16": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp, c_i64, C.c_int, C.c_int,
-                          c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+                          c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "sbr_mark_referenced": [c_vp, C.c_int, c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp],
+    "sbr_gather_rows_bf16": [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp],
+    "sbr_spmm_scatter_wgrad": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp],
+    "sbr_transpose_add_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp],
     "sbr_sample_modalities": [c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_u64, c_vp, c_vp],
     "sbr_tick": [c_vp, c_vp],
     "sbr_step_begin": [c_vp, c_vp, c_vp, c_i64, c_vp],

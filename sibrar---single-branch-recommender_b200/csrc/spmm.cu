@@ -217,7 +217,8 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
                  const float* __restrict__ vals, int64_t rows, const bf16* __restrict__ dense, int64_t ld_dense, int C,
                  const float* __restrict__ bias, int act, float* __restrict__ out, int64_t ld_out, int accumulate,
                  bf16* __restrict__ out16, int64_t ld_out16, const int32_t* __restrict__ row_list,
-                 const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ seg_row) {
+                 const int32_t* __restrict__ n_rows_dev, const int32_t* __restrict__ seg_row,
+                 const int32_t* __restrict__ out_pos) {
   SBR_PDL_ENTRY();
   extern __shared__ float s_tile[];  // TRANSPOSE: [C][33]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -236,8 +237,11 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
     // segments (their partial sums are combined with atomics; bias / activation are applied by the fix-up pass)
     const int64_t row = slot < rows ? (row_list ? (int64_t)__ldg(row_list + slot) : slot) : -1;
     const int32_t sr = (seg_row != nullptr && row >= 0) ? __ldg(seg_row + row) : 0;
-    const bool multi = sr < 0;
-    const int64_t orow = seg_row != nullptr ? (int64_t)(sr & 0x7fffffff) : row;
+    // out_pos (compact output of the referenced-rows route): EVERY unit adds its raw partial sum into the (cleared)
+    // output row; bias / activation are applied by the caller's finishing pass
+    const bool multi = sr < 0 || (!TRANSPOSE && out_pos != nullptr);
+    int64_t orow = seg_row != nullptr ? (int64_t)(sr & 0x7fffffff) : row;
+    if (!TRANSPOSE && out_pos != nullptr && row >= 0) orow = (int64_t)__ldg(out_pos + orow);
     float acc[NV8][8];
 #pragma unroll
     for (int i = 0; i < NV8; ++i)
@@ -339,7 +343,8 @@ spmm_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
     if (slot < rows) {
       const int64_t row = row_list ? (int64_t)__ldg(row_list + slot) : slot;
       const int32_t sr = seg_row != nullptr ? __ldg(seg_row + row) : 0;
-      const int64_t orow = seg_row != nullptr ? (int64_t)(sr & 0x7fffffff) : row;
+      int64_t orow = seg_row != nullptr ? (int64_t)(sr & 0x7fffffff) : row;
+    if (!TRANSPOSE && out_pos != nullptr && row >= 0) orow = (int64_t)__ldg(out_pos + orow);
       for (int c = warp; c < C; c += 8) {
         float* dst = out + (int64_t)c * ld_out + orow;
         const float v = s_tile[c * 33 + lane];
@@ -374,7 +379,7 @@ template <int NV8>
 int launch_bf16(const int64_t* indptr, const int32_t* indices, const float* vals, int64_t rows, const bf16* dense,
                 int64_t ld_dense, int C, const float* bias, int act, float* out, int64_t ld_out, int transpose_out,
                 int accumulate, bf16* out16, int64_t ld_out16, const int32_t* row_list, const int32_t* n_rows_dev,
-                const int32_t* seg_row, cudaStream_t st) {
+                const int32_t* seg_row, const int32_t* out_pos, cudaStream_t st) {
   if (transpose_out) {
     const size_t smem = (size_t)C * 33 * sizeof(float);
     static size_t configured = 0;
@@ -385,11 +390,11 @@ int launch_bf16(const int64_t* indptr, const int32_t* indices, const float* vals
     }
     SBR_CHECK_CUDA(sbr_launch(spmm_bf16_kernel<NV8, true>, dim3(cdiv(rows, 32)), dim3(256), smem, st, indptr, indices,
                               vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16, ld_out16,
-                              row_list, n_rows_dev, seg_row));
+                              row_list, n_rows_dev, seg_row, out_pos));
   } else {
     SBR_CHECK_CUDA(sbr_launch(spmm_bf16_kernel<NV8, false>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, st, indptr,
                               indices, vals, rows, dense, ld_dense, C, bias, act, out, ld_out, accumulate, out16,
-                              ld_out16, row_list, n_rows_dev, seg_row));
+                              ld_out16, row_list, n_rows_dev, seg_row, out_pos));
   }
   return SBR_OK;
 }
@@ -400,7 +405,8 @@ extern "C" int sbr_spmm_csr_bf16(const int64_t* indptr, const int32_t* indices, 
                                  const void* dense_bf16, int64_t ld_dense, int64_t C, const float* bias, int act,
                                  float* out, int64_t ld_out, int transpose_out, int accumulate, void* out_bf16,
                                  int64_t ld_bf16, const int32_t* row_list, const int32_t* n_rows_dev,
-                                 const int32_t* seg_row, const int32_t* long_rows, int64_t n_long, void* stream) {
+                                 const int32_t* seg_row, const int32_t* long_rows, int64_t n_long,
+                                 const int32_t* out_pos, void* stream) {
   SBR_REQUIRE(indptr && indices && dense_bf16 && (out || out_bf16) && rows > 0, "sbr_spmm_csr_bf16: bad arguments");
   SBR_REQUIRE(C > 0 && C <= 1024, "sbr_spmm_csr_bf16: C=%lld not in [1, 1024]", (long long)C);
   SBR_REQUIRE(ld_dense % 8 == 0 && ld_dense >= ((C + 7) / 8) * 8 && (reinterpret_cast<uintptr_t>(dense_bf16) & 15) == 0,
@@ -418,14 +424,16 @@ extern "C" int sbr_spmm_csr_bf16(const int64_t* indptr, const int32_t* indices, 
   bf16* o16 = reinterpret_cast<bf16*>(out_bf16);
   const int nv8 = (int)(((C + 7) / 8 + 31) / 32);
   cudaStream_t st = S(stream);
-  const bool fix = seg_row != nullptr && !transpose_out && n_long > 0;
+  SBR_REQUIRE(out_pos == nullptr || (!transpose_out && out && !out_bf16 && !bias && act == SBR_ACT_NONE),
+              "sbr_spmm_csr_bf16: out_pos produces raw fp32 partial sums (no bias / activation / bf16 copy)");
+  const bool fix = seg_row != nullptr && !transpose_out && n_long > 0 && out_pos == nullptr;
   if (fix)
     SBR_CHECK_CUDA(sbr_launch(spmm_long_rows_kernel, dim3(cdiv(n_long * C, 256)), dim3(256), (size_t)0, st, long_rows,
                               (int)n_long, out, ld_out, (int)C, bias, act, o16, ld_bf16, 0));
   int rc;
 #define SBR_SPMM_BF16(N)                                                                                        \
   rc = launch_bf16<N>(indptr, indices, vals, rows, d, ld_dense, (int)C, bias, act, out, ld_out, transpose_out, \
-                      accumulate, o16, ld_bf16, row_list, n_rows_dev, seg_row, st)
+                      accumulate, o16, ld_bf16, row_list, n_rows_dev, seg_row, out_pos, st)
   if (nv8 <= 1) { SBR_SPMM_BF16(1); }
   else if (nv8 <= 2) { SBR_SPMM_BF16(2); }
   else { SBR_SPMM_BF16(4); }

@@ -136,7 +136,7 @@ CSR_SEGMENT = 256  # entries per warp-sized unit of work of the sparse kernels
 def csr_segments(indptr: np.ndarray, device, seg: int = CSR_SEGMENT):
     """rows of a CSR matrix cut into segments of at most ``seg`` entries (None when no row is longer): ``seg_ptr`` int64
     [n_seg + 1] (a refinement of indptr), ``seg_row`` int32 [n_seg] = row | (row has several segments) << 31,
-    ``long_rows`` int32 -- see sbr_spmm_csr_bf16"""
+    ``long_rows`` int32 -- see sbr_spmm_csr_bf16; ``seg_first`` int64 [n_rows + 1]: first segment of every row"""
     indptr = np.asarray(indptr, dtype=np.int64)
     lens = np.diff(indptr)
     if lens.size == 0 or int(lens.max()) <= seg:
@@ -150,8 +150,9 @@ def csr_segments(indptr: np.ndarray, device, seg: int = CSR_SEGMENT):
     multi = per_row[seg_row] > 1
     enc = (seg_row.astype(np.uint32) | (multi.astype(np.uint32) << np.uint32(31))).view(np.int32)
     long_rows = np.flatnonzero(per_row > 1).astype(np.int32)
+    seg_first = np.concatenate([[0], np.cumsum(per_row)]).astype(np.int64)  # row -> its first segment
     return (torch.from_numpy(seg_ptr).to(device), torch.from_numpy(enc).to(device),
-            torch.from_numpy(long_rows).to(device))
+            torch.from_numpy(long_rows).to(device), torch.from_numpy(seg_first).to(device))
 
 
 def csr_to_device(m, device):

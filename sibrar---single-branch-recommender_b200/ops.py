@@ -136,7 +136,7 @@ def csr_to_dense_bf16(indptr, indices, rows, cols, vals=None) -> torch.Tensor:
 
 
 def spmm_csr(indptr, indices, rows, dense, C_, bias, act, out, transpose_out=False, vals=None, accumulate=False,
-             out_bf16=None, row_map=None, atomic=False, row_list=None, n_rows_dev=None, segments=None):
+             out_bf16=None, row_map=None, atomic=False, row_list=None, n_rows_dev=None, segments=None, out_pos=None):
     """out[r] = act(sum_p vals[p] * dense[indices[p]] + bias); ``transpose_out``: out is [C, rows] (the wgrad through
     the transposed CSR), ``accumulate``: out += result.  ``dense`` fp32 or bf16 (fp32 accumulation either way).
     fp32 only: ``row_map`` / ``atomic`` (segment mode).  bf16 only: ``row_list`` / ``n_rows_dev`` (row subset)."""
@@ -144,16 +144,17 @@ def spmm_csr(indptr, indices, rows, dense, C_, bias, act, out, transpose_out=Fal
         assert row_map is None and not atomic
         seg_ptr = seg_row = long_rows = None
         if segments is not None:  # (seg_ptr int64 [n_seg + 1], seg_row int32 [n_seg], long_rows int32 [n_long])
-            seg_ptr, seg_row, long_rows = segments
-            indptr, rows = seg_ptr, seg_row.numel()
-            if not transpose_out and long_rows.numel() > 0:
+            seg_ptr, seg_row, long_rows = segments[:3]
+            indptr = seg_ptr
+            rows = seg_row.numel() if row_list is None else rows
+            if not transpose_out and long_rows.numel() > 0 and out_pos is None:
                 from . import _lib
                 _lib._launches[0] += 2  # the clear / fix-up passes over the long rows
         call("sbr_spmm_csr_bf16", ptr(indptr), ptr(indices), ptr(vals), int(rows), ptr(dense), dense.stride(0),
              int(C_), ptr(bias), _act(act), ptr(out), out.stride(0) if out is not None else 0, int(transpose_out),
              int(bool(accumulate)), ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(row_list),
              ptr(n_rows_dev), ptr(seg_row), ptr(long_rows), long_rows.numel() if long_rows is not None else 0,
-             stream_ptr())
+             ptr(out_pos), stream_ptr())
         return
     assert segments is None
     assert row_list is None and n_rows_dev is None
@@ -236,6 +237,44 @@ class GatherPlan:
 
 
 TAG_BAG_SMEM_FLOATS = 10240  # csrc/gather.cu SEG_SMEM_FLOATS: gradient matrices up to this size are privatised per block
+
+
+def make_ref_tables(entries, device) -> torch.Tensor:
+    """entries: per modality None (whole-table route) or dict(stamp, pos, list, count[, seg_first, seg_list, seg_count])
+    -> uint8 device blob of ``sbr_ref_table_t[n]``"""
+    from ._lib import RefTable
+    arr = (RefTable * len(entries))()
+    for i, e in enumerate(entries):
+        if e is None:
+            continue
+        arr[i].stamp, arr[i].pos, arr[i].list, arr[i].count = ptr(e["stamp"]), ptr(e["pos"]), ptr(e["list"]), ptr(e["count"])
+        arr[i].seg_first, arr[i].seg_list = ptr(e.get("seg_first")), ptr(e.get("seg_list"))
+        arr[i].seg_count = ptr(e.get("seg_count"))
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+
+def mark_referenced(srcs, n_mods, idx, mods, k, epoch_dev, tabs):
+    call("sbr_mark_referenced", ptr(srcs), int(n_mods), ptr(idx), ptr(mods), idx.numel(), int(k), ptr(epoch_dev),
+         ptr(tabs), stream_ptr())
+
+
+def gather_rows_bf16(src, lst, count_dev, capacity, dst):
+    """dst[slot] = src[lst[slot]] for slot < *count_dev, zero rows up to ``capacity``"""
+    assert src.dtype == BF16 and dst.dtype == BF16 and src.shape[1] == dst.shape[1]
+    call("sbr_gather_rows_bf16", ptr(src), src.stride(0), ptr(lst), ptr(count_dev), int(capacity), int(src.shape[1]),
+         ptr(dst), dst.stride(0), stream_ptr())
+
+
+def spmm_scatter_wgrad(indptr, indices, vals, unit_list, n_units_dev, max_units, seg_row, pos, dz16, C_, gT):
+    call("sbr_spmm_scatter_wgrad", ptr(indptr), ptr(indices), ptr(vals), ptr(unit_list), ptr(n_units_dev),
+         int(max_units), ptr(seg_row), ptr(pos), ptr(dz16), dz16.stride(0), int(C_), ptr(gT), gT.stride(0),
+         stream_ptr())
+
+
+def transpose_add_f32(src, dst):
+    """dst[c, r] += src[r, c]; src cleared"""
+    rows, cols = src.shape
+    call("sbr_transpose_add_f32", ptr(src), src.stride(0), ptr(dst), dst.stride(0), rows, cols, stream_ptr())
 
 
 def mlp2_desc(srcs, n_mods, idx, mods, k, C_, normalize, p_drop, seed, step_dev, keep_mask, err_flag, layers):

@@ -208,12 +208,16 @@ class Chain:
         return max(1, min(num_kb // 4, (2 * n_sms) // tiles))
 
     def forward(self, x16, rows, training, arena: ZeroArena, keep_for_backward=True, out32=None,
-                defer_final_bn=False):
+                defer_final_bn=False, ref=None):
         """``defer_final_bn``: when the chain ends in BatchNorm (no activation after it) the normalised output is not
         written; ``self.deferred`` = dict(z, mean_invstd, gamma, beta) lets the score/loss kernel apply it inline."""
         dev = self.stages[0].linear.weight.device
         self.rows = rows
         self.deferred = None
+        # ref: the "referenced rows" route -- the chain runs on the compact list of feature rows this step touches
+        # (dict(list, count, pos, units, n_units, max_units, gT)); x16 is then the gathered copy of those rows
+        self._ref = ref
+        self._first_x = x16 if ref is not None else None
         last = len(self.stages) - 1
         for si, st in enumerate(self.stages):
             final = si == last
@@ -231,10 +235,19 @@ class Chain:
                     ip, ix = self.feature.csr
                     # gather-sum of bf16 weight rows, fp32 accumulation: the rounding points of the dense route
                     seg = self.feature.csr_seg
-                    if seg is not None and y32 is None:  # (the partial sums of long rows need an fp32 home)
+                    if (seg is not None or ref is not None) and y32 is None:  # (partial sums need an fp32 home)
                         y32 = torch.empty((rows, st.out_f), dtype=F32, device=dev)
-                    ops.spmm_csr(ip, ix, rows, st.wt16, st.out_f, bias, st.act1, y32, vals=self.feature.csr_vals,
-                                 out_bf16=y16, segments=seg)
+                    if ref is None:
+                        ops.spmm_csr(ip, ix, rows, st.wt16, st.out_f, bias, st.act1, y32, vals=self.feature.csr_vals,
+                                     out_bf16=y16, segments=seg)
+                    else:
+                        # only the listed rows (or their segments): raw sums into the cleared compact rows, then one
+                        # pass applies bias + activation (+ the bf16 copy)
+                        y32.zero_()
+                        ops.spmm_csr(ip, ix, ref["max_units"], st.wt16, st.out_f, None, None, y32,
+                                     vals=self.feature.csr_vals, row_list=ref["units"], n_rows_dev=ref["n_units"],
+                                     segments=seg, out_pos=ref["pos"])
+                        ops.splitk_reduce(y32, 1, rows, st.out_f, bias=bias, act=st.act1, out_f32=y32, out_bf16=y16)
                 else:
                     first_bits = si == 0 and self.bits_input
                     mm = (lambda *a, **k: ops.gemm_bits(self.feature.bits, *a[1:], **k)) if first_bits else ops.gemm
@@ -338,13 +351,23 @@ class Chain:
                                          dz_f32=da32, dgamma=g_gamma, dbeta=g_beta, n_replicas=reps)
                         ops.actgrad_colsum(da32, st.a32, st.act1, rows, st.out_f, out_bf16=dz16, colsum=g_b)
             # ---- wgrad: dW[out, in] += dz^T x   (contraction over the rows)
-            if first_csr:
+            if first_csr and self._ref is not None:
+                # referenced rows only: every stored entry (r, j) adds dz[pos(r)] into row j of the transposed gradient,
+                # which is then added into dW [out, in] (and cleared)
+                ref = self._ref
+                ip, ix = self.feature.csr
+                seg = self.feature.csr_seg
+                ops.spmm_scatter_wgrad(seg[0] if seg is not None else ip, ix, self.feature.csr_vals, ref["units"],
+                                       ref["n_units"], ref["max_units"], seg[1] if seg is not None else None,
+                                       ref["pos"], dz16, st.out_f, ref["gT"])
+                ops.transpose_add_f32(ref["gT"], g_w)
+            elif first_csr:
                 ip_t, ix_t = self.feature.csr_t
                 # accumulates like every other wgrad of the path (gradient accumulation over micro-batches)
                 ops.spmm_csr(ip_t, ix_t, st.in_f, dz16, st.out_f, None, None, g_w, transpose_out=True,
                              vals=self.feature.csr_t_vals, accumulate=True, segments=self.feature.csr_t_seg)
             else:
-                x16 = st.x if si > 0 or self.feature is None else self.feature.x16
+                x16 = st.x if (si > 0 or self.feature is None or self._first_x is not None) else self.feature.x16
                 tiles = -(-st.in_f // 128) * -(-st.out_f // (64 if st.out_f <= 64 else 128 if st.out_f <= 128 else 256))
                 split = ops.effective_splits(rows, max(1, min(-(-rows // 64), (2 * n_sms) // max(1, tiles))))
                 # wgrad partitions accumulate with fp32 atomics (measured faster than private slices + a reduce pass at
@@ -650,19 +673,33 @@ class SingleBranchNetEntity(_EntityBase):
         self.table_grads = {n: torch.zeros((self.dfeat[n].n_rows, cfg.common_modality_dim), dtype=F32, device=dev)
                             for n in list(self.proj) + self.bags}
         self._srcs_cache = {}
+        # "referenced rows" route (csrc/refrows.cu): per modality projection, the per-step subset of feature rows
+        self._ref_state = {}    # name -> dict(stamp, pos, gT)
+        self._ref_bufs = {}     # (name, capacity) -> per-shape buffers
+        self._ref_epoch = torch.zeros(2, dtype=torch.int64, device=dev)  # [epoch, finished blocks] of the marking kernel
+        self._route = {}        # modality name -> buffers of the current call (empty: whole-table route everywhere)
         self._eval_ids = torch.tensor([self.mod_names.index(m) for m in sorted(self.eval_modalities)],
                                       dtype=torch.uint8, device=dev)
         self._dev_ready = dev
 
     def _src_blob(self, grads):
-        key = id(grads) if grads is not None else 0
+        route_sig = tuple(sorted((n, b["capacity"]) for n, b in self._route.items()))
+        key = (id(grads) if grads is not None else 0, route_sig)
         hit = self._srcs_cache.get(key)
         if hit is not None and hit[0] is grads:
+            self.n_keys = hit[3]
             return hit[1]
         entries, key_base = [], 0
         for name in self.mod_names:
             df, fe = self.dfeat[name], self.modality_modules[name]
-            if name in self.tables:
+            if name in self._route:
+                # projected rows of THIS step, addressed indirectly: feature row -> compact position (like a categorical
+                # source whose codes are the positions handed out by sbr_mark_referenced)
+                b = self._route[name]
+                entries.append(dict(kind=SRC_CATEGORICAL, remap=df.remap, table=b["T"], codes=b["pos"],
+                                    key_base=key_base, grad=b["G"] if grads is not None else None))
+                key_base += int(b["capacity"])
+            elif name in self.tables:
                 entries.append(dict(kind=SRC_TABLE, remap=df.remap, table=self.tables[name], key_base=key_base,
                                     grad=self.table_grads[name] if grads is not None else None))
                 key_base += int(df.n_rows)
@@ -676,8 +713,69 @@ class SingleBranchNetEntity(_EntityBase):
                 key_base += int(w.shape[0]) if kind == SRC_CATEGORICAL else int(df.n_rows)
         self.n_keys = key_base
         blob = ops.make_modality_srcs(entries, self._device())
-        self._srcs_cache[key] = (grads, blob, entries)
+        self._srcs_cache[key] = (grads, blob, entries, key_base)
         return blob
+
+    # ---- referenced-rows route
+    def _select_route(self, n_idx: int):
+        """which modality projections run on the rows this call references only (static in the call's shape): vector /
+        sparse features whose table has at least twice as many rows as the call has entities"""
+        self._route = {}
+        if os.environ.get("SBR_REF_ROWS", "1") == "0":
+            return
+        dev = self._device()
+        C_ = self.entity_config.common_modality_dim
+        for name, chain in self.proj.items():
+            df = self.dfeat[name]
+            if df.kind not in ("dense", "csr") or 2 * n_idx > df.n_rows:
+                continue
+            st = self._ref_state.get(name)
+            if st is None:
+                st = self._ref_state[name] = dict(
+                    stamp=torch.zeros(df.n_rows, dtype=torch.int32, device=dev),
+                    pos=torch.zeros(df.n_rows, dtype=torch.int32, device=dev),
+                    gT=torch.zeros((chain.stages[0].in_f, chain.stages[0].out_f), dtype=F32, device=dev)
+                    if df.kind == "csr" else None)
+            cap = int(n_idx)
+            b = self._ref_bufs.get((name, cap))
+            if b is None:
+                seg = df.csr_seg if df.kind == "csr" else None
+                extra = int(seg[1].numel() - df.n_rows) if seg is not None else 0
+                b = self._ref_bufs[(name, cap)] = dict(
+                    capacity=cap, pos=st["pos"], stamp=st["stamp"], gT=st["gT"],
+                    list=torch.zeros(cap, dtype=torch.int32, device=dev),
+                    T=torch.zeros((cap, C_), dtype=F32, device=dev), G=torch.zeros((cap, C_), dtype=F32, device=dev),
+                    X=torch.zeros((cap, df.x16.shape[1]), dtype=BF16, device=dev) if df.kind == "dense" else None,
+                    seg_first=seg[3] if seg is not None else None, max_units=cap + extra,
+                    seg_list=torch.zeros(cap + extra, dtype=torch.int32, device=dev) if seg is not None else None)
+            self._route[name] = b
+
+    def begin_call(self, flat, mods, k):
+        """route selection + row marking of one embed call.  The trainer issues it before it forks the side stream (the
+        gather plan of this entity is built there and needs the compact positions); ``embed`` does it otherwise."""
+        self._select_route(flat.numel())
+        self._mark_referenced(flat, mods, k)
+
+    def _mark_referenced(self, flat, mods, k):
+        """one pass over the call's (entity, modality) slots: row lists + compact positions of the routed modalities"""
+        if not self._route:
+            return
+        rt = self._rt()
+        entries = []
+        for name in self.mod_names:
+            b = self._route.get(name)
+            if b is None:
+                entries.append(None)
+                continue
+            cnt = rt.arena.take(2, torch.int32)  # [rows, segments] of this call (the arena is cleared per step)
+            b["count"], b["seg_count"] = cnt[0:1], cnt[1:2]
+            entries.append(dict(stamp=b["stamp"], pos=b["pos"], list=b["list"], count=b["count"],
+                                seg_first=b["seg_first"], seg_list=b["seg_list"], seg_count=b["seg_count"]))
+        sig = tuple(None if e is None else (e["list"].data_ptr(), e["count"].data_ptr()) for e in entries)
+        hit = self.__dict__.get("_ref_tabs")
+        if hit is None or hit[0] != sig:
+            self._ref_tabs = hit = (sig, ops.make_ref_tables(entries, self._device()), entries)
+        ops.mark_referenced(self._src_blob(None), len(self.mod_names), flat, mods, k, self._ref_epoch, hit[1])
 
     def _aux_streams(self, n):
         """side streams of this entity (None unless the trainer enabled branch parallelism on the runtime)"""
@@ -698,7 +796,16 @@ class SingleBranchNetEntity(_EntityBase):
                 ops.tag_bag_fwd(df.codes, df.max_tags, df.pad_id, w, self.tables[name])
                 return
             chain = self.proj[name]
-            chain.forward(df.x16, df.n_rows, training, arena, keep_for_backward=training, out32=self.tables[name])
+            b = self._route.get(name)
+            if b is None:
+                chain.forward(df.x16, df.n_rows, training, arena, keep_for_backward=training, out32=self.tables[name])
+                return
+            seg = b["seg_list"] is not None
+            ref = dict(list=b["list"], count=b["count"], pos=b["pos"], gT=b["gT"], max_units=b["max_units"],
+                       units=b["seg_list"] if seg else b["list"], n_units=b["seg_count"] if seg else b["count"])
+            if df.kind == "dense":
+                ops.gather_rows_bf16(df.x16, b["list"], b["count"], b["capacity"], b["X"])
+            chain.forward(b["X"], b["capacity"], training, arena, keep_for_backward=training, out32=b["T"], ref=ref)
         todo = [n for n in names if n in self.tables]
         run_branches([lambda n=n: one(n) for n in todo], self._aux_streams(len(todo) - 1) if training else None)
 
@@ -734,6 +841,8 @@ class SingleBranchNetEntity(_EntityBase):
             k = self.k_eval
             mods = self._eval_ids.repeat(n_idx)
             used = sorted(self.eval_modalities)
+        if not self.__dict__.pop("_premarked", False):
+            self.begin_call(flat, mods, k)
         self._project_tables(used, training, rt.arena)
         srcs = self._src_blob(None)
         C_ = cfg.common_modality_dim
@@ -846,6 +955,7 @@ class SingleBranchNetEntity(_EntityBase):
         """sorted-run plan of the gather backward; depends only on (indices, sampled modalities), so the trainer
         builds it on its side stream while the forward GEMMs run"""
         flat = idx.reshape(-1)
+        self._select_route(flat.numel())
         srcs = self._src_blob(grads)
         plan = _gather_plan(self, self.n_keys, flat.numel() * k, flat.device)
         plan.build(srcs, len(self.mod_names), flat, mods, k)
@@ -873,7 +983,8 @@ class SingleBranchNetEntity(_EntityBase):
                       keep_mask, dx0, keep_bits=keep_bits)
         # table-level backward, one independent branch per modality; the accumulator table is cleared by the kernel
         # that consumes it
-        thunks = [lambda n=n, c=c: c.backward(self.table_grads[n], grads, need_dx=False, arena=rt.arena, zero_dy=True)
+        thunks = [lambda n=n, c=c: c.backward(self._route[n]["G"] if n in self._route else self.table_grads[n], grads,
+                                              need_dx=False, arena=rt.arena, zero_dy=True)
                   for n, c in self.proj.items()]
         for n in self.bags:
             df, w = self.dfeat[n], self.modality_modules[n].embedding_layer.weight

@@ -151,6 +151,12 @@ class FusedTrainer:
             imods = mods.get("item")
             if imods is None and sb_i:
                 imods = self.item.sample_modalities(i_idxs.numel())
+            if sb_i:
+                # (the item-side gather plan is built on the side stream: its row keys need the compact positions of the
+                # referenced-rows route, so the marking pass runs here, before the fork)
+                self.item._materialize()
+                self.item.begin_call(i_idxs.reshape(-1).contiguous(), imods, ki)
+                self.item._premarked = True
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 Eu = self.user.embed(u_idxs, True, mods.get("user"), keep_masks.get("user"), defer_final_bn=fuse)

@@ -460,3 +460,51 @@ def test_fused_mlp_kernels_match_layer_by_layer_path(name, monkeypatch):
         assert np.abs(got - want).max() <= 1e-2 * np.abs(want).max() + 1e-4 * gscale, k
     for k, want in res["0"][3].items():
         assert np.abs(res["1"][3][k] - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), k
+
+
+@pytest.mark.parametrize("name,density", [("ml1m_small", "0.004"), ("ml1m_small", "2.0"), ("pairwise_bn2", "2.0"),
+                                          ("tanh_dropout_norm", "2.0"), ("plain_user_ssm", "2.0")])
+def test_referenced_rows_route_matches_table_route(name, density, monkeypatch):
+    """the "referenced rows" route (sbr_mark_referenced + gathered / listed projections over the rows a step touches
+    only -- what the reference computes, sgd_alg.py:1949-1974) gives the step of the whole-table route: logits, loss,
+    every gradient, on a batch small enough for the route to be selected (dense AND sparse modalities), and the same
+    representations for a subset of the items in evaluation mode"""
+    monkeypatch.setenv("SBR_DENSE_MIN_DENSITY", density)
+    res = {}
+    for route in ("0", "1"):
+        monkeypatch.setenv("SBR_REF_ROWS", route)
+        spec, g, corpus, model = _build(name)
+        model.to(DEV).train()
+        _load(model, state_dict_of(g, "sd0/"))
+        tr = _trainer(model, spec)
+        u, i, mods, keep = _translate(model, g, 0)
+        nb, n = 5, i.shape[1]
+        ents = {"user": model.user_embedding_module, "item": model.item_embedding_module}
+        sub_mods = {e: m.view(i.shape[0], -1)[:nb].reshape(-1).contiguous() for e, m in mods.items()}
+        sub_keep = {e: kk.view(i.shape[0], -1)[:nb].reshape(-1, kk.shape[1]).contiguous() for e, kk in keep.items()}
+        for _ in range(2):  # twice: stale stamps / positions of the first call must not leak into the second
+            _load(model, state_dict_of(g, "sd0/"))
+            for gr in tr.grads.values():
+                gr.zero_()
+            tr.read_losses()
+            tr.step(u[:nb].contiguous(), i[:nb].contiguous(), sub_mods, sub_keep, apply_optimizer=False)
+        torch.cuda.synchronize()
+        model.check_errors()
+        routed = {e: sorted(ent._route) for e, ent in ents.items() if isinstance(ent, SingleBranchNetEntity)}
+        if route == "0":
+            assert not any(routed.values())
+        else:
+            assert any(routed.values()), "the batch must be small enough for at least one routed modality"
+        params = dict(model.named_parameters())
+        model.eval()
+        items = torch.arange(0, corpus.n_items, 7, device=DEV)
+        rep = model.get_item_representations(items).cpu().numpy().copy()
+        res[route] = (tr.logits.cpu().numpy().copy(), tr.read_losses()["train/loss"],
+                      {k: tr.grads[id(p)].cpu().numpy().copy() for k, p in params.items()}, rep, routed)
+    assert _maxrel(res["1"][0], res["0"][0]) < 2e-3, res["1"][4]
+    assert res["1"][1] == pytest.approx(res["0"][1], rel=5e-4)
+    gscale = max(float(np.abs(v).max()) for v in res["0"][2].values())
+    for k, want in res["0"][2].items():
+        got = res["1"][2][k]
+        assert np.abs(got - want).max() <= 1e-2 * np.abs(want).max() + 1e-4 * gscale, (k, res["1"][4])
+    assert _maxrel(res["1"][3], res["0"][3]) < 2e-3
