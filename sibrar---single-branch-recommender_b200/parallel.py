@@ -58,7 +58,11 @@ def allreduce_mean_(flat: torch.Tensor, world: int):
 
 
 class DataParallelTrainer(FusedTrainer):
-    def __init__(self, model, learn, n_negative_samples, **kw):
+    """``sync_bn``: BatchNorm statistics (forward and backward) over the global batch -- an N-rank step then equals the
+    single-process step of the reference on the concatenated batch (2 small collectives per BatchNorm layer and step);
+    off by default, like ``DistributedDataParallel`` without ``SyncBatchNorm``."""
+
+    def __init__(self, model, learn, n_negative_samples, sync_bn: bool = False, **kw):
         self.world = dist.get_world_size()
         # identical initial weights on every rank
         for p in model.parameters():
@@ -69,6 +73,11 @@ class DataParallelTrainer(FusedTrainer):
         self._work = []
         # every rank draws its own modalities / dropout masks (the rank enters the Philox seeds)
         self.rt.seed_salt = dist.get_rank()
+        if sync_bn:
+            from .sbnet import BnSync, SingleBranchNetEntity
+            for ent in (self.user, self.item):
+                if isinstance(ent, SingleBranchNetEntity):
+                    ent.sb_chain.bn_sync = BnSync(self.world)
 
     def _after_item_backward(self):
         lo, mid, _ = self.bucket_bounds

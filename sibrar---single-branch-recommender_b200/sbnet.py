@@ -182,8 +182,31 @@ def run_branches(thunks, streams):
         cur.wait_stream(s)
 
 
+class BnSync:
+    """BatchNorm statistics over the GLOBAL batch under data parallelism (optional: ``DataParallelTrainer(sync_bn=True)``).
+    Forward: the per-CTA rows of partial column sums of every rank are all-gathered and added in a fixed order
+    (deterministic, identical on every rank) -- mean / variance / running statistics are those of the reference's single
+    process at the same global batch (``nn.BatchNorm1d`` over all rows, modules/polylinear.py:58-61).  Backward: the
+    column sums of (dy, dy * xhat) are all-reduced, pre-multiplied by 1 / world: the kernels divide by the LOCAL row
+    count, so that they see sum_global / N_global."""
+
+    def __init__(self, world: int):
+        self.world = int(world)
+
+    def gather_stats(self, stats: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        out = torch.empty((self.world * stats.shape[0], stats.shape[1]), dtype=stats.dtype, device=stats.device)
+        dist.all_gather_into_tensor(out, stats.contiguous())
+        return out
+
+    def reduce_sums(self, sums: torch.Tensor):
+        import torch.distributed as dist
+        dist.all_reduce(sums, op=dist._make_nccl_premul_sum(1.0 / self.world))
+
+
 class Chain:
     """A stack of LinearStages.  forward: bf16 rows (or a CSR feature) -> fp32 output; backward: hand-written."""
+    bn_sync: Optional[BnSync] = None
 
     def __init__(self, stages, feature: Optional[DeviceFeature] = None):
         self.stages = stages
@@ -278,7 +301,11 @@ class Chain:
                     ops.gemm(x16, st.w16, rows, st.out_f, st.in_f, bias=bias, act=st.act1, out_f32=a32,
                              colstats=stats, colstats_rows=n_part)
                 if training:
-                    ops.bn_finalize(stats, rows, st.out_f, mi, bn.running_mean, bn.running_var,
+                    rows_g = rows
+                    if self.bn_sync is not None:  # statistics of the global batch (equal rows per rank)
+                        stats, n_part, rows_g = self.bn_sync.gather_stats(stats), n_part * self.bn_sync.world, \
+                            rows * self.bn_sync.world
+                    ops.bn_finalize(stats, rows_g, st.out_f, mi, bn.running_mean, bn.running_var,
                                     bn.num_batches_tracked, eps=bn.eps, momentum=bn.momentum, n_partials=n_part)
                 else:
                     ops.bn_eval_coeffs(bn.running_mean, bn.running_var, st.out_f, mi, eps=bn.eps)
@@ -340,6 +367,8 @@ class Chain:
                     else:
                         sums, reps = arena.take(2 * st.out_f), 1
                         ops.bn_bwd_reduce(dy32, y, st.act2, st.a32, st.mi, rows, st.out_f, sums)
+                    if self.bn_sync is not None:
+                        self.bn_sync.reduce_sums(sums)
                     g_gamma, g_beta = grads[id(bn.weight)], grads[id(bn.bias)]
                     if st.act1 is None:
                         # the Linear bias in front of a BatchNorm has an exactly-zero gradient: not computed
@@ -901,7 +930,10 @@ class SingleBranchNetEntity(_EntityBase):
         if last.bn is not None:
             bn = last.bn
             mi = torch.empty(2 * D, dtype=F32, device=dev)
-            ops.bn_finalize(stats, N, D, mi, bn.running_mean, bn.running_var, bn.num_batches_tracked, eps=bn.eps,
+            rows_g, sync = N, self.sb_chain.bn_sync
+            if sync is not None:
+                stats, n_part, rows_g = sync.gather_stats(stats), n_part * sync.world, N * sync.world
+            ops.bn_finalize(stats, rows_g, D, mi, bn.running_mean, bn.running_var, bn.num_batches_tracked, eps=bn.eps,
                             momentum=bn.momentum, n_partials=n_part)
             if defer_bn:
                 self.sb_chain.deferred = dict(z=z, mean_invstd=mi, gamma=bn.weight.detach(), beta=bn.bias.detach())
@@ -925,6 +957,8 @@ class SingleBranchNetEntity(_EntityBase):
             else:
                 sums, reps = rt.arena.take(2 * D), 1
                 ops.bn_bwd_reduce(dE, None, None, f["z"], f["mi"], N, D, sums)
+            if self.sb_chain.bn_sync is not None:
+                self.sb_chain.bn_sync.reduce_sums(sums)
             bn = dict(mean_invstd=f["mi"], gamma=last.bn.weight.detach(), sums=sums, n_replicas=reps,
                       dgamma=grads[id(last.bn.weight)], dbeta=grads[id(last.bn.bias)])
         gw = [grads[id(s_.linear.weight)] for s_ in st]
