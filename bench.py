@@ -474,6 +474,7 @@ def run_train_workload(name, args, env, batch, steps, warmup, full, scale=1.0):
     res = dict(value=world * B * steps / (total_ms * 1e-3), unit=UNIT, ms_per_step=total_ms / steps, steps=steps,
                warmup=warmup, batch_per_gpu=B, global_batch=world * B, gpu_launches=launches,
                train_loss=losses.get("train/loss"), reg_loss=losses.get("train/reg_loss"), clocks=clk,
+               collective=getattr(tr, "collective", None),
                wall_ms_per_step_incl_flush=t_wall / steps * 1e3, workload=text,
                params=int(sum(p.numel() for p in model.parameters())))
 
@@ -640,6 +641,7 @@ def main():
                 dtype="bf16", data="synthetic",
                 config=dict(workload=head["workload"], name=args.config, batch_per_gpu=args.batch, n_neg=N_NEG,
                             global_batch=world * args.batch, parallelism=f"dp{world}", params=head["params"],
+                            collective=head.get("collective"),
                             l2="flushed between timed steps (256 MiB write)",
                             wall_ms_per_step_incl_flush=head["wall_ms_per_step_incl_flush"]),
                 clocks=head["clocks"], e2e=head["e2e"], gpu_launches=head["gpu_launches"],

@@ -79,9 +79,33 @@ class DataParallelTrainer(FusedTrainer):
                 if isinstance(ent, SingleBranchNetEntity):
                     ent.sb_chain.bn_sync = BnSync(self.world)
 
+    def _alloc_flat_grads(self, total: int, dev):
+        """the flat gradient buffer in SYMMETRIC memory (every rank maps every peer's buffer + the NVSwitch multicast
+        address): the gradient collective is then ONE in-switch all-reduce (`multimem.ld_reduce` of each rank's slice +
+        `multimem.st` of the sums, torch's symm_mem kernels) instead of two NCCL calls.  SBR_DP_COLLECTIVE=nccl keeps
+        the NCCL buckets (also the fallback when symmetric memory / multicast is not available)."""
+        import os
+        self._symm = None
+        if os.environ.get("SBR_DP_COLLECTIVE", "symm") != "nccl" and self.world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                t = symm_mem.empty(total, dtype=torch.float32, device=dev)
+                t.zero_()
+                hdl = symm_mem.rendezvous(t, dist.group.WORLD.group_name)
+                self._symm = (hdl, dist.group.WORLD.group_name,
+                              "multimem" if hdl.has_multicast_support() else "two_shot")
+                return t
+            except Exception as e:  # noqa: BLE001  (older drivers / no P2P): NCCL
+                self._symm_error = repr(e)
+        return torch.zeros(total, dtype=torch.float32, device=dev)
+
+    @property
+    def collective(self) -> str:
+        return f"symm_mem {self._symm[2]} all-reduce (1 call / step)" if self._symm else "nccl all-reduce (2 buckets / step)"
+
     def _after_item_backward(self):
         lo, mid, _ = self.bucket_bounds
-        if mid <= lo or not self._reduce_now:
+        if mid <= lo or not self._reduce_now or self._symm:
             return
         if torch.cuda.is_current_stream_capturing():
             # inside the step's CUDA graph the collective is captured in stream order (the buckets are a few MB:
@@ -92,6 +116,13 @@ class DataParallelTrainer(FusedTrainer):
 
     def _after_user_backward(self):
         _, mid, hi = self.bucket_bounds
+        if self._symm and self._reduce_now:
+            _, group, kind = self._symm
+            if kind == "multimem":
+                torch.ops.symm_mem.multimem_all_reduce_(self.flat_grads, "sum", group)
+            else:
+                torch.ops.symm_mem.two_shot_all_reduce_(self.flat_grads, "sum", group)
+            return
         if hi > mid and self._reduce_now:
             if torch.cuda.is_current_stream_capturing():
                 dist.all_reduce(self.flat_grads[mid:hi], op=dist.ReduceOp.SUM)

@@ -61,7 +61,7 @@ class FusedTrainer:
         for p in ordered:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
-        self.flat_grads = torch.zeros(total, dtype=F32, device=dev)
+        self.flat_grads = self._alloc_flat_grads(total, dev)
         n_item = len(list(self.item.parameters()))
         self.bucket_bounds = (0, offs[n_item] if n_item < len(offs) else total, total)  # [item | user]
         entries = []
@@ -216,6 +216,9 @@ class FusedTrainer:
         if apply_optimizer:
             self.optimizer_step(ticked=True)
         self.steps_accumulated += 1
+
+    def _alloc_flat_grads(self, total: int, dev):
+        return torch.zeros(total, dtype=F32, device=dev)
 
     def _side_stream(self, device):
         if self._side is None:

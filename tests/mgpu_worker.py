@@ -67,8 +67,12 @@ def main(out_path):
         # optimizer path: the ranks must end up with identical parameters
         tr.flat_grads.zero_()
         model.load_state_dict(sd0)
+        tr.snapshot_grads = True  # the all-reduced gradients the optimizer consumed (the trainer's own collective)
         tr.step(t(u[lo:hi]), t(i[lo:hi]), {"user": t(mods["user"][lo:hi].reshape(-1)), "item": t(mods["item"][lo:hi].reshape(-1))},
                 {"item": t(keep_i[lo * (1 + n_neg):hi * (1 + n_neg)])})
+        res[f"{tag}/collective"] = tr.collective
+        res[f"{tag}/collective_vs_nccl_max_err_rel"] = float(
+            np.abs(tr.grads_snapshot.cpu().numpy() / world - dp_grads).max() / np.abs(dp_grads).max())
         flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
         mx, mn = flat.clone(), flat.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)

@@ -27,6 +27,7 @@ def test_two_rank_step_and_sharded_eval_match_single_gpu(tmp_path):
     assert res["dp_no_bn/grad_max_err_rel"] < 2e-3
     assert abs(res["dp_no_bn/loss_rel_err"] - res["dp_no_bn/ref_loss"]) < 1e-5 * abs(res["dp_no_bn/ref_loss"]) + 1e-6
     assert res["dp_no_bn/param_spread_over_ranks"] == 0.0
+    assert res["dp_no_bn/collective_vs_nccl_max_err_rel"] < 1e-5  # the trainer's own collective == NCCL's sum
     # B. BatchNorm with global statistics
     assert res["dp_sync_bn/grad_max_err_rel"] < 5e-3
     assert abs(res["dp_sync_bn/loss_rel_err"] - res["dp_sync_bn/ref_loss"]) < 1e-4 * abs(res["dp_sync_bn/ref_loss"]) + 1e-6
