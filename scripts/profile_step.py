@@ -1,21 +1,24 @@
-"""Per-call CUDA-event breakdown of one fused train step (same workload as bench.py)."""
+"""Per-call CUDA-event breakdown of one fused train step of a BASELINE workload (same set-up as bench.py).
+
+    python scripts/profile_step.py [ml1m|onion18_huge|amazon_nouser] [batch]
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import sibrar_b200  # noqa
 import bench
-from sibrar_b200 import ops
+from sibrar_b200 import ops, workloads
 from sibrar_b200.sbnet import SingleBranchNet
-from sibrar_b200.synthetic import SynCorpus
 from sibrar_b200.trainer import FusedTrainer
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+name = sys.argv[1] if len(sys.argv) > 1 else "ml1m"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 dev = torch.device("cuda", 0)
-corpus = SynCorpus("ml1m", "cold_start_item", seed=42)
+corpus, conf, learn, _, _ = workloads.build(name)
 train = corpus.dataset("train")
 torch.manual_seed(1234)
-model = SingleBranchNet.build_from_conf(bench.ml1m_model_conf(), train).to(dev).train()
-tr = FusedTrainer(model, bench.LEARN, n_negative_samples=bench.N_NEG)
+model = SingleBranchNet.build_from_conf(conf, train).to(dev).train()
+tr = FusedTrainer(model, learn, n_negative_samples=bench.N_NEG)
 coo = train.interaction_matrix
 d = lambda a, t: torch.from_numpy(np.ascontiguousarray(a).astype(t)).to(dev)
 csr = train.user_sampling_matrix_train
@@ -31,16 +34,25 @@ for _ in range(5):
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
-for _ in range(20):
+for _ in range(10):
     tr.step(u, i)
 b.record()
 torch.cuda.synchronize()
-print(f"B={B}: {a.elapsed_time(b) / 20:.3f} ms/step unprofiled")
+print(f"{name} B={B}: {a.elapsed_time(b) / 10:.3f} ms/step unprofiled (graph replay, warm L2)")
+tr.cuda_graph, tr.branches = False, 0
+n_prof = 3
 with bench.CallProfiler(ops, torch) as prof:
-    for _ in range(5):
+    for _ in range(n_prof):
+        torch.cuda._sleep(20_000_000)
         tr.step(u, i)
 agg = prof.summary()
-tot = sum(v[0] for v in agg.values()) / 5
-print(f"sum of kernels {tot:.3f} ms/step, {sum(v[1] for v in agg.values()) / 5:.0f} calls/step")
+tot = sum(v[0] for v in agg.values()) / n_prof
+print(f"sum of kernels {tot:.3f} ms/step, {sum(v[1] for v in agg.values()) / n_prof:.0f} calls/step")
+nnz = float(train.user_sampling_matrix_train.nnz)
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-    print(f"{v[0] / 5 / tot * 100:5.1f}%  {v[0] / v[1] * 1e3:8.1f} us x {v[1] / 5:4.1f}  {k}")
+    us = v[0] / v[1] * 1e3
+    w = bench.algorithmic_work(k, nnz)
+    rate = ""
+    if w is not None and us > 0:
+        rate = f"{w[0] / us / 1e6:8.1f} TFLOP/s {w[1] / us / 1e3:8.1f} GB/s"
+    print(f"{v[0] / n_prof / tot * 100:5.1f}%  {us:8.1f} us x {v[1] / n_prof:4.1f}  {rate}  {k}")

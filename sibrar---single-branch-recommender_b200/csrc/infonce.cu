@@ -1,6 +1,8 @@
 // sibrar_b200 -- symmetric InfoNCE (CLIP-style) modality-alignment loss with hand-written backward.
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -105,6 +107,134 @@ __global__ void infonce_grad_kernel(const float* __restrict__ e, int64_t G, int6
   if (lane == 0 && loss_acc) atomicAdd(loss_acc, (double)((my_lse - l_ii) * inv_r * weight));
 }
 
+
+// ------------------------------------------------------------------------------------------------ small groups
+// Item side of the train step: G = B groups of n = 1 + n_neg rows (n <= 32).  ONE warp owns one group end to end: both
+// slots of the group are staged in shared memory once (coalesced 16-byte loads), the n x n logits are computed with
+// lane = (i, j) pair, row / column log-sum-exps with lane = row, the n x n gradient weights go back to shared memory
+// and both gradient blocks are produced with lane = 4 contiguous columns -- e is read once and de written once per
+// step (the two-pass kernels above read every row 2 (n + 1) times and issue one double-precision atomic per row).
+// Persistent blocks; the loss is reduced per block before its single atomic.
+constexpr int IG_MAX_N = 32;
+template <int DV>  // float4 chunks of a row per lane: D <= 128 * DV
+__global__ void __launch_bounds__(256)
+infonce_group_kernel(const float* __restrict__ e, int64_t G, int n, int D, float inv_t, float weight,
+                     double* __restrict__ loss_acc, float* __restrict__ de, int accumulate, int warps_per_block) {
+  SBR_PDL_ENTRY();
+  extern __shared__ float4 ig_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ldr = D + 4;                                   // padded row pitch (floats): rows land in different banks
+  const int per_warp = 2 * n * ldr + n * n + 2 * n + 2;    // e0 | e1 | L / W | lse_r | lse_c
+  float* base_s = reinterpret_cast<float*>(ig_smem) + (size_t)warp * ((per_warp + 3) & ~3);
+  float* s_e0 = base_s;  // slot `side` of the group: s_e0 + side * n * ldr
+  float* s_l = base_s + 2 * n * ldr;
+  float* s_lse_r = s_l + n * n;
+  float* s_lse_c = s_lse_r + n;
+  const int d4n = D >> 2;
+  const float inv_r = 1.f / (float)(G * n);
+  double loss_local = 0.0;
+  if (warp < warps_per_block) {
+    for (int64_t g = (int64_t)blockIdx.x * warps_per_block + warp; g < G; g += (int64_t)gridDim.x * warps_per_block) {
+      const float* src = e + g * n * 2 * D;
+      // ---- stage: global row (i, side) -> s_e[side][i]
+      for (int c = lane; c < 2 * n * d4n; c += 32) {
+        const int row = c / d4n, d4 = c - row * d4n;  // row = i * 2 + side
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)row * D) + d4);
+        *reinterpret_cast<float4*>(s_e0 + ((row & 1) * n + (row >> 1)) * ldr + 4 * d4) = v;
+      }
+      __syncwarp();
+      // ---- logits: lane = pair (i, j)
+      for (int pq = lane; pq < n * n; pq += 32) {
+        const int i = pq / n, j = pq - i * n;
+        const float4* a = reinterpret_cast<const float4*>(s_e0 + i * ldr);
+        const float4* b = reinterpret_cast<const float4*>(s_e0 + (n + j) * ldr);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        for (int t = 0; t < d4n; ++t) {
+          const float4 x = a[t], y = b[t];
+          d0 += x.x * y.x; d1 += x.y * y.y; d2 += x.z * y.z; d3 += x.w * y.w;
+        }
+        s_l[pq] = ((d0 + d1) + (d2 + d3)) * inv_t;
+      }
+      __syncwarp();
+      // ---- log-sum-exp of every row (lanes 0 .. n-1) and every column (the same lanes, second pass)
+      if (lane < n) {
+        float mx = -INFINITY, mc = -INFINITY;
+        for (int j = 0; j < n; ++j) {
+          mx = fmaxf(mx, s_l[lane * n + j]);
+          mc = fmaxf(mc, s_l[j * n + lane]);
+        }
+        float se = 0.f, sc = 0.f;
+        for (int j = 0; j < n; ++j) {
+          se += __expf(s_l[lane * n + j] - mx);
+          sc += __expf(s_l[j * n + lane] - mc);
+        }
+        const float lr = mx + logf(se), lc = mc + logf(sc);
+        s_lse_r[lane] = lr;
+        s_lse_c[lane] = lc;
+        const float lii = s_l[lane * n + lane];
+        loss_local += (double)(((lr - lii) + (lc - lii)) * inv_r * weight);
+      }
+      __syncwarp();
+      // ---- gradient weights W_ij (in place)
+      for (int pq = lane; pq < n * n; pq += 32) {
+        const int i = pq / n, j = pq - i * n;
+        const float l = s_l[pq];
+        s_l[pq] = (__expf(l - s_lse_r[i]) + __expf(l - s_lse_c[j]) - (i == j ? 2.f : 0.f)) * inv_r * inv_t * weight;
+      }
+      __syncwarp();
+      // ---- de0_i = sum_j W_ij e1_j,  de1_j = sum_i W_ij e0_i : lane = float4 column chunks
+      if (de != nullptr) {
+        float* dst = de + g * n * 2 * D;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const float* other = s_e0 + (1 - side) * n * ldr;
+          for (int i = 0; i < n; ++i) {
+            float4 acc[DV];
+#pragma unroll
+            for (int v = 0; v < DV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < n; ++j) {
+              const float w = side == 0 ? s_l[i * n + j] : s_l[j * n + i];
+#pragma unroll
+              for (int v = 0; v < DV; ++v) {
+                const int d4 = lane + 32 * v;
+                if (d4 < d4n) {
+                  const float4 o = *reinterpret_cast<const float4*>(other + j * ldr + 4 * d4);
+                  acc[v].x += w * o.x; acc[v].y += w * o.y; acc[v].z += w * o.z; acc[v].w += w * o.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int v = 0; v < DV; ++v) {
+              const int d4 = lane + 32 * v;
+              if (d4 < d4n) {
+                float4* q = reinterpret_cast<float4*>(dst + (size_t)(i * 2 + side) * D) + d4;
+                float4 r = acc[v];
+                if (accumulate) {
+                  const float4 old = *q;
+                  r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+                }
+                *q = r;
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // ---- loss: fixed-order sum over the block's lanes, one atomic per block
+  __shared__ double s_loss[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
+  if (lane == 0) s_loss[warp] = loss_local;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_acc != nullptr) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_loss[w];
+    atomicAdd(loss_acc, t);
+  }
+}
+
 }  // namespace
 
 extern "C" int sbr_infonce(const float* e, int64_t G, int64_t n, int D, float temperature, float weight,
@@ -112,6 +242,30 @@ extern "C" int sbr_infonce(const float* e, int64_t G, int64_t n, int D, float te
   SBR_REQUIRE(e && lse_ws && G > 0 && n > 0, "sbr_infonce: bad arguments");
   SBR_REQUIRE(D > 0 && D <= 512, "sbr_infonce: D=%d not in [1, 512]", D);
   SBR_REQUIRE(temperature > 0.f, "sbr_infonce: temperature must be positive");
+  // small groups (the item side: n = 1 + n_neg): one warp per group, everything staged in shared memory once
+  if (n <= IG_MAX_N && (D & 3) == 0 && (reinterpret_cast<uintptr_t>(e) & 15) == 0 &&
+      (de == nullptr || (reinterpret_cast<uintptr_t>(de) & 15) == 0) && getenv("SBR_INFONCE_TWO_PASS") == nullptr) {
+    const int per_warp = ((2 * (int)n * (D + 4) + (int)(n * n) + 2 * (int)n + 2) + 3) & ~3;
+    const size_t per_warp_bytes = (size_t)per_warp * sizeof(float);
+    int wpb = (int)std::min<size_t>(8, (100 * 1024) / per_warp_bytes);  // two blocks per SM when the groups are small
+    if (wpb >= 1) {
+      const size_t smem = per_warp_bytes * wpb;
+      int64_t blocks = (G + wpb - 1) / wpb;
+      const int64_t cap = (int64_t)sbr_num_sms() * 2;
+      if (blocks > cap) blocks = cap;
+      auto launch = [&](auto kern) -> int {
+        SBR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)));
+        SBR_CHECK_CUDA(sbr_launch(kern, dim3((unsigned)blocks), dim3(256), smem, S(stream), e, G, (int)n, D,
+                                  1.f / temperature, weight, loss_acc, de, accumulate, wpb));
+        return SBR_OK;
+      };
+      int rc = D <= 128 ? launch(infonce_group_kernel<1>) : (D <= 256 ? launch(infonce_group_kernel<2>)
+                                                                      : launch(infonce_group_kernel<4>));
+      if (rc) return rc;
+      SBR_LAUNCH_CHECK();
+      return SBR_OK;
+    }
+  }
   const int64_t warps = 2 * G * n;
   DISPATCH_NV(D, 32, {
     infonce_lse_kernel<NVv><<<cdiv(warps, 8), 256, 0, S(stream)>>>(e, G, n, D, 1.f / temperature, lse_ws);

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 namespace {
+constexpr int BNV_UNR = 4;  // rows in flight per thread in the vector kernels
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
@@ -270,6 +271,124 @@ actgrad_colsum_vec_kernel(float* __restrict__ dy, int64_t ld_dy, const float* __
   }
 }
 
+
+// ---- vector paths of bn_apply / bn_bwd_reduce and of bn_bwd_apply with an activation behind the BatchNorm (the wide
+// single-branch networks: BatchNorm -> ReLU every second layer, 360 448 x 512 rows per step): 4 columns per thread, the
+// loads of 4 rows in flight (the scalar kernels -- one 4-byte load per thread and row -- ran at 2.1 - 2.5 TB/s there)
+__device__ __forceinline__ float4 load_y4(const float* y_f32, const bf16* y_bf16, int64_t off) {
+  if (y_f32) return __ldcs(reinterpret_cast<const float4*>(y_f32 + off));
+  const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(y_bf16 + off));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store_bf16x4(bf16* dst, const float (&v)[4]) {
+  uint2 o;
+  *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[0], v[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(dst) = o;
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_vec_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean_invstd,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, int act, int64_t rows, int C,
+                    bf16* __restrict__ out_bf16, int64_t ld_bf16, float* __restrict__ out_f32, int64_t ld_f32) {
+  SBR_PDL_ENTRY();
+  const int c4n = C >> 2;
+  const int c = (threadIdx.x % c4n) * 4;
+  const int rpb = 256 / c4n;
+  const float4 mean = *reinterpret_cast<const float4*>(mean_invstd + c);
+  const float4 invstd = *reinterpret_cast<const float4*>(mean_invstd + C + c);
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+  const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+  const float m[4] = {mean.x, mean.y, mean.z, mean.w};
+  const float sc[4] = {gm.x * invstd.x, gm.y * invstd.y, gm.z * invstd.z, gm.w * invstd.w};
+  const float sh[4] = {bt.x, bt.y, bt.z, bt.w};
+  const int64_t stride = (int64_t)gridDim.x * rpb;
+  for (int64_t r0 = (int64_t)blockIdx.x * rpb + threadIdx.x / c4n; r0 < rows; r0 += stride * BNV_UNR) {
+    float4 zz[BNV_UNR];
+#pragma unroll
+    for (int u = 0; u < BNV_UNR; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < rows) zz[u] = __ldcs(reinterpret_cast<const float4*>(z + r * ld_z + c));
+    }
+#pragma unroll
+    for (int u = 0; u < BNV_UNR; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= rows) break;
+      const float zv[4] = {zz[u].x, zz[u].y, zz[u].z, zz[u].w};
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = act_fwd(act, (zv[j] - m[j]) * sc[j] + sh[j]);
+      if (out_bf16) store_bf16x4(out_bf16 + r * ld_bf16 + c, v);
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * ld_f32 + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_vec_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
+                         const bf16* __restrict__ y_bf16, int64_t ld_y, int act, const float* __restrict__ z,
+                         int64_t ld_z, const float* __restrict__ mean_invstd, int64_t rows, int C,
+                         float* __restrict__ sums) {
+  SBR_PDL_ENTRY();
+  const int c4n = C >> 2;
+  const int c = (threadIdx.x % c4n) * 4;
+  const int rpb = 256 / c4n;
+  const float4 mean = *reinterpret_cast<const float4*>(mean_invstd + c);
+  const float4 invstd = *reinterpret_cast<const float4*>(mean_invstd + C + c);
+  const float m[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
+  float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t stride = (int64_t)gridDim.x * rpb;
+  for (int64_t r0 = (int64_t)blockIdx.x * rpb + threadIdx.x / c4n; r0 < rows; r0 += stride * BNV_UNR) {
+    float4 g[BNV_UNR], zz[BNV_UNR], yv[BNV_UNR];
+#pragma unroll
+    for (int u = 0; u < BNV_UNR; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < rows) {
+        g[u] = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + c));  // (read again by bn_bwd_apply)
+        zz[u] = __ldg(reinterpret_cast<const float4*>(z + r * ld_z + c));
+        if (act != SBR_ACT_NONE) yv[u] = load_y4(y_f32, y_bf16, r * ld_y + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BNV_UNR; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= rows) break;
+      float gv[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      const float zv[4] = {zz[u].x, zz[u].y, zz[u].z, zz[u].w};
+      if (act != SBR_ACT_NONE) {
+        gv[0] *= act_grad_from_out(act, yv[u].x);
+        gv[1] *= act_grad_from_out(act, yv[u].y);
+        gv[2] *= act_grad_from_out(act, yv[u].z);
+        gv[3] *= act_grad_from_out(act, yv[u].w);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p0[j] += gv[j];
+        p1[j] += gv[j] * (zv[j] - m[j]) * is[j];
+      }
+    }
+  }
+  __shared__ float4 red[2][256];
+  red[0][threadIdx.x] = make_float4(p0[0], p0[1], p0[2], p0[3]);
+  red[1][threadIdx.x] = make_float4(p1[0], p1[1], p1[2], p1[3]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c4n; i += 256) {
+    const int which = i / c4n, t = i % c4n;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < rpb; ++k) {
+      const float4 b = red[which][k * c4n + t];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float* dst = sums + (size_t)which * C + 4 * t;
+    atomicAdd(dst, a.x);
+    atomicAdd(dst + 1, a.y);
+    atomicAdd(dst + 2, a.z);
+    atomicAdd(dst + 3, a.w);
+  }
+}
+
 extern "C" int sbr_actgrad_colsum(float* dy, int64_t ld_dy, const float* y_f32, const void* y_bf16, int64_t ld_y,
                                   int act, int64_t rows, int64_t cols, void* out_bf16, int64_t ld_out, float* out_f32,
                                   int64_t ld_out_f32, float* colsum, int zero_dy, void* stream) {
@@ -322,6 +441,25 @@ extern "C" int sbr_bn_apply(const float* z, int64_t ld_z, const float* mean_invs
                             const float* beta, int act, int64_t rows, int C, void* out_bf16, int64_t ld_bf16,
                             float* out_f32, int64_t ld_f32, void* stream) {
   SBR_REQUIRE(z && mean_invstd && gamma && beta && rows > 0 && C > 0, "sbr_bn_apply: bad arguments");
+  {
+    const auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+    const bool vec = (C & 3) == 0 && C <= 1024 && 256 % (C >> 2) == 0 && (ld_z & 3) == 0 && al(z, 16) &&
+                     al(mean_invstd, 16) && al(gamma, 16) && al(beta, 16) &&
+                     (!out_bf16 || ((ld_bf16 & 3) == 0 && al(out_bf16, 8))) &&
+                     (!out_f32 || ((ld_f32 & 3) == 0 && al(out_f32, 16))) && rows >= 1024 &&
+                     getenv("SBR_NORM_SCALAR") == nullptr;
+    if (vec) {
+      const int rpb = 256 / (C >> 2);
+      int64_t blocks = cdiv(rows, (int64_t)rpb * BNV_UNR);
+      const int64_t cap = (int64_t)sbr_num_sms() * 8;
+      if (blocks > cap) blocks = cap;
+      SBR_CHECK_CUDA(sbr_launch(bn_apply_vec_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), S(stream), z, ld_z,
+                                mean_invstd, gamma, beta, act, rows, C, reinterpret_cast<bf16*>(out_bf16), ld_bf16,
+                                out_f32, ld_f32));
+      SBR_LAUNCH_CHECK();
+      return SBR_OK;
+    }
+  }
   SBR_CHECK_CUDA(sbr_launch(bn_apply_kernel, dim3(tile_grid(rows, C)), dim3(256), (size_t)(0), S(stream), z, ld_z, mean_invstd, gamma, beta, act, rows, C,
                                                              reinterpret_cast<bf16*>(out_bf16), ld_bf16, out_f32,
                                                              ld_f32, rows_per_block(rows)));
@@ -334,6 +472,24 @@ extern "C" int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_
                                  float* sums, void* stream) {
   SBR_REQUIRE(dy && z && mean_invstd && sums && rows > 0 && C > 0, "sbr_bn_bwd_reduce: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_reduce: activation gradient needs the output y");
+  {
+    const auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+    const bool y_ok = act == SBR_ACT_NONE || ((ld_y & 3) == 0 && (y_f32 ? al(y_f32, 16) : al(y_bf16, 8)));
+    const bool vec = y_ok && (C & 3) == 0 && C <= 1024 && 256 % (C >> 2) == 0 && (ld_dy & 3) == 0 && (ld_z & 3) == 0 &&
+                     al(dy, 16) && al(z, 16) && al(mean_invstd, 16) && rows >= 1024 &&
+                     getenv("SBR_NORM_SCALAR") == nullptr;
+    if (vec) {
+      const int rpb = 256 / (C >> 2);
+      int64_t blocks = cdiv(rows, (int64_t)rpb * BNV_UNR);
+      const int64_t cap = (int64_t)sbr_num_sms() * 4;  // (one atomic per column and block)
+      if (blocks > cap) blocks = cap;
+      SBR_CHECK_CUDA(sbr_launch(bn_bwd_reduce_vec_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), S(stream), dy,
+                                ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, rows,
+                                C, sums));
+      SBR_LAUNCH_CHECK();
+      return SBR_OK;
+    }
+  }
   SBR_CHECK_CUDA(sbr_launch(bn_bwd_reduce_kernel, dim3(tile_grid(rows, C)), dim3(256), (size_t)(0), S(stream), 
       dy, ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, rows, C, sums,
       rows_per_block(rows)));
@@ -345,9 +501,9 @@ extern "C" int sbr_bn_bwd_reduce(const float* dy, int64_t ld_dy, const float* y_
 // rows, 256 % (C / 4) == 0): a thread owns 4 columns (its BatchNorm coefficients live in registers), grid-strides over
 // the rows and keeps the loads of UNR rows in flight -- the scalar kernel (one 4-byte load per thread and row, no
 // unrolling) ran at 2.4 TB/s.
-constexpr int BNV_UNR = 4;
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_vec_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ z, int64_t ld_z,
+bn_bwd_apply_vec_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ y_f32,
+                        const bf16* __restrict__ y_bf16, int64_t ld_y, int act, const float* __restrict__ z, int64_t ld_z,
                         const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
                         const float* __restrict__ sums, int n_replicas, int64_t rows, int C,
                         bf16* __restrict__ dz_bf16, int64_t ld_dz, float* __restrict__ dz_f32, int64_t ld_dz_f32,
@@ -384,20 +540,28 @@ bn_bwd_apply_vec_kernel(const float* __restrict__ dy, int64_t ld_dy, const float
   }
   const int64_t stride = (int64_t)gridDim.x * rpb;
   for (int64_t r0 = (int64_t)blockIdx.x * rpb + threadIdx.x / c4n; r0 < rows; r0 += stride * BNV_UNR) {
-    float4 g[BNV_UNR], zz[BNV_UNR];
+    float4 g[BNV_UNR], zz[BNV_UNR], yv[BNV_UNR];
 #pragma unroll
     for (int u = 0; u < BNV_UNR; ++u) {
       const int64_t r = r0 + u * stride;
       if (r < rows) {
         g[u] = __ldcs(reinterpret_cast<const float4*>(dy + r * ld_dy + c));  // read once: streaming
         zz[u] = __ldcs(reinterpret_cast<const float4*>(z + r * ld_z + c));
+        if (act != SBR_ACT_NONE) yv[u] = load_y4(y_f32, y_bf16, r * ld_y + c);
       }
     }
 #pragma unroll
     for (int u = 0; u < BNV_UNR; ++u) {
       const int64_t r = r0 + u * stride;
       if (r >= rows) break;
-      const float gv[4] = {g[u].x, g[u].y, g[u].z, g[u].w}, zv[4] = {zz[u].x, zz[u].y, zz[u].z, zz[u].w};
+      float gv[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      const float zv[4] = {zz[u].x, zz[u].y, zz[u].z, zz[u].w};
+      if (act != SBR_ACT_NONE) {
+        gv[0] *= act_grad_from_out(act, yv[u].x);
+        gv[1] *= act_grad_from_out(act, yv[u].y);
+        gv[2] *= act_grad_from_out(act, yv[u].z);
+        gv[3] *= act_grad_from_out(act, yv[u].w);
+      }
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -423,7 +587,8 @@ extern "C" int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f
               "sbr_bn_bwd_apply: bad arguments");
   SBR_REQUIRE(act == SBR_ACT_NONE || y_f32 || y_bf16, "sbr_bn_bwd_apply: activation gradient needs the output y");
   const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const bool vec = act == SBR_ACT_NONE && (C & 3) == 0 && C <= 1024 && 256 % (C >> 2) == 0 && (ld_dy & 3) == 0 &&
+  const bool y_ok = act == SBR_ACT_NONE || ((ld_y & 3) == 0 && (y_f32 ? al16(y_f32) : (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0));
+  const bool vec = y_ok && (C & 3) == 0 && C <= 1024 && 256 % (C >> 2) == 0 && (ld_dy & 3) == 0 &&
                    (ld_z & 3) == 0 && al16(dy) && al16(z) && al16(mean_invstd) && al16(gamma) && al16(sums) &&
                    (!dz_bf16 || ((ld_dz & 3) == 0 && (reinterpret_cast<uintptr_t>(dz_bf16) & 7) == 0)) &&
                    (!dz_f32 || ((ld_dz_f32 & 3) == 0 && al16(dz_f32))) && getenv("SBR_NORM_SCALAR") == nullptr;
@@ -433,7 +598,8 @@ extern "C" int sbr_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* y_f
     const int64_t cap = (int64_t)sbr_num_sms() * 8;
     if (blocks > cap) blocks = cap;
     SBR_CHECK_CUDA(sbr_launch(bn_bwd_apply_vec_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), S(stream), dy,
-                              ld_dy, z, ld_z, mean_invstd, gamma, sums, n_replicas, rows, C,
+                              ld_dy, y_f32, reinterpret_cast<const bf16*>(y_bf16), ld_y, act, z, ld_z, mean_invstd, gamma,
+                              sums, n_replicas, rows, C,
                               reinterpret_cast<bf16*>(dz_bf16), ld_dz, dz_f32, ld_dz_f32, dgamma, dbeta));
     SBR_LAUNCH_CHECK();
     return SBR_OK;

@@ -172,11 +172,12 @@ def test_reference_style_loop_matches_fused_step(name):
     gscale = max(float(v.abs().max()) for v in fused.values())
     for k, p in params.items():
         assert p.grad is not None, k
+        # entry-wise, mandatory (no direction-only escape): the forward is bit-reproducible; in the backward the fp32
+        # atomics of the BatchNorm-backward sums / split-K weight gradients arrive in a different order on every run, a
+        # bf16 rounding of a dz entry flips now and then, and a deep 512-wide stack turns that into ~3e-3 of a
+        # tensor's largest entry
         err = float((p.grad - fused[k]).abs().max())
-        if err > 2e-3 * float(fused[k].abs().max()) + 1e-5 * gscale:
-            a, b = p.grad.reshape(-1).double(), fused[k].reshape(-1).double()
-            cos = float(a @ b) / max(1e-30, float(a.norm() * b.norm()))
-            assert ldiff >= 1e-6 and cos >= 0.9, (k, err, cos)  # only a flipped rounding may move entries this much
+        assert err <= 1e-2 * float(fused[k].abs().max()) + 1e-5 * gscale, (k, err, float(fused[k].abs().max()))
     # torch.optim on the accumulated .grad moves the parameters like the fused AdamW
     opt = torch.optim.AdamW(model.parameters(), lr=spec["lr"], weight_decay=spec["wd"]) if spec["optimizer"] == "adamw" \
         else torch.optim.Adam(model.parameters(), lr=spec["lr"], weight_decay=spec["wd"])

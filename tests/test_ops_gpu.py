@@ -379,33 +379,43 @@ def test_gemm_partial_colstats_are_deterministic():
     assert _relerr(outs[0][N:], 1.0 / torch.sqrt(ref.var(0, unbiased=False) + 1e-5)) < 1e-4
 
 
-@pytest.mark.parametrize("act", [None, "relu"])
-def test_batchnorm_fwd_bwd(act):
-    rows, C_ = 1000, 40
+@pytest.mark.parametrize("act", [None, "relu", "tanh"])
+@pytest.mark.parametrize("rows,C_,y16", [(1000, 40, False), (4100, 512, True), (3000, 128, False), (2049, 256, True)])
+def test_batchnorm_fwd_bwd(act, rows, C_, y16):
+    """scalar kernels (C = 40) and the vector kernels (C = 128 / 256 / 512, y saved as bf16 or fp32, with and without
+    an activation behind the BatchNorm) against torch.nn.functional.batch_norm + autograd"""
     z = (torch.randn(rows, C_, device=DEV) * 2 + 1).requires_grad_()
     gamma = torch.randn(C_, device=DEV).requires_grad_()
     beta = torch.randn(C_, device=DEV).requires_grad_()
     rm, rv = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
     ref = torch.nn.functional.batch_norm(z, rm.clone(), rv.clone(), gamma, beta, True, 0.1, 1e-5)
-    ref = torch.relu(ref) if act else ref
+    ref = getattr(torch, act)(ref) if act else ref
     stats = torch.stack([z.detach().sum(0), (z.detach() ** 2).sum(0)]).reshape(-1).contiguous()
     mi = torch.empty(2 * C_, device=DEV)
     nbt = torch.zeros(1, dtype=torch.int64, device=DEV)
     ops.bn_finalize(stats, rows, C_, mi, rm, rv, nbt)
     y = torch.empty(rows, C_, device=DEV)
-    ops.bn_apply(z.detach(), mi, gamma.detach(), beta.detach(), act, rows, C_, out_f32=y)
+    y_b = torch.empty(rows, C_, device=DEV, dtype=torch.bfloat16)
+    ops.bn_apply(z.detach(), mi, gamma.detach(), beta.detach(), act, rows, C_, out_f32=y, out_bf16=y_b)
     assert _relerr(y, ref) < 1e-4
+    assert torch.equal(y_b, y.to(torch.bfloat16))
     rm2, rv2 = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
     torch.nn.functional.batch_norm(z.detach(), rm2, rv2, None, None, True, 0.1, 1e-5)
     assert _relerr(rm, rm2) < 1e-4 and _relerr(rv, rv2) < 1e-4 and nbt.item() == 1
     dy = torch.randn(rows, C_, device=DEV)
     ref.backward(dy)
+    ysaved = y_b if y16 else y
+    # (tanh' from a bf16 y is only as exact as the rounding of y: the fp32 copy is the tight check)
+    tol = 2e-4 if (not y16 or act != "tanh") else 2e-2
     sums = torch.zeros(2 * C_, device=DEV)
-    ops.bn_bwd_reduce(dy, y, act, z.detach(), mi, rows, C_, sums)
+    ops.bn_bwd_reduce(dy, ysaved, act, z.detach(), mi, rows, C_, sums)
     dz = torch.empty(rows, C_, device=DEV)
+    dz_b = torch.empty(rows, C_, device=DEV, dtype=torch.bfloat16)
     dg, db = torch.zeros(C_, device=DEV), torch.zeros(C_, device=DEV)
-    ops.bn_bwd_apply(dy, y, act, z.detach(), mi, gamma.detach(), sums, rows, C_, dz_f32=dz, dgamma=dg, dbeta=db)
-    assert _relerr(dz, z.grad) < 2e-4 and _relerr(dg, gamma.grad) < 1e-4 and _relerr(db, beta.grad) < 1e-4
+    ops.bn_bwd_apply(dy, ysaved, act, z.detach(), mi, gamma.detach(), sums, rows, C_, dz_f32=dz, dz_bf16=dz_b, dgamma=dg,
+                     dbeta=db)
+    assert _relerr(dz, z.grad) < tol and _relerr(dg, gamma.grad) < tol and _relerr(db, beta.grad) < tol
+    assert torch.equal(dz_b, dz.to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("loss,agg_u,agg_i,ku,ki,sum_", [("bpr", 0, 0, 1, 1, 0), ("bpr", 0, 1, 2, 2, 0),
@@ -467,17 +477,20 @@ def test_score_loss_bn_matches_unfused(loss, D, n, bn_user, bn_item):
         assert _relerr(got, ref) < 1e-4
 
 
-@pytest.mark.parametrize("G,n,D", [(9, 5, 24), (1, 70, 16), (300, 11, 64)])
-def test_infonce(G, n, D):
+@pytest.mark.parametrize("G,n,D,accumulate", [(9, 5, 24, 1), (1, 70, 16, 1), (300, 11, 64, 1), (2500, 11, 128, 0),
+                                              (700, 11, 512, 1), (333, 32, 256, 0), (40, 3, 8, 1), (1, 300, 128, 1)])
+def test_infonce(G, n, D, accumulate):
+    """one-warp-per-group kernel (n <= 32: the item side at its real widths) and the two-pass kernels (n > 32) against
+    the fp64 oracle (train/regularization_losses.py:28-43)"""
     from oracle import sbnet_oracle as O
-    e = torch.randn(G, n, 2, D, device=DEV) * 0.5
+    e = torch.randn(G, n, 2, D, device=DEV) * (2.0 / D ** 0.5)
     acc = torch.zeros(1, dtype=torch.float64, device=DEV)
     de = torch.ones_like(e)
-    ops.infonce(e, G, n, D, 0.7, 0.3, acc, de, accumulate=1)
+    ops.infonce(e, G, n, D, 0.7, 0.3, acc, de, accumulate=accumulate)
     en = e.double().cpu().numpy()
     loss, d0, d1 = O.info_nce(en[:, :, 0], en[:, :, 1], 0.7)
     assert abs(acc.item() - 0.3 * loss) < 1e-5 * max(1, abs(loss))
-    ref = 1.0 + 0.3 * np.stack([d0, d1], axis=2)
+    ref = (1.0 if accumulate else 0.0) + 0.3 * np.stack([d0, d1], axis=2)
     assert np.abs(de.cpu().numpy() - ref).max() < 1e-5
 
 
