@@ -175,8 +175,9 @@ int sbr_row_gather_bwd(const sbr_modality_src_t* srcs_dev, int n_mods, const int
                        void* stream);
 
 /* Low-contention backward of the row gather.  plan: counting sort of the N flat rows by segment key
- * (counts/cursor int32 [n_keys], offsets int32 [n_keys + 1], row_keys/perm/sorted_keys int32 [N]; all caller-owned
- * scratch).  reduce: persistent blocks; one lane group (row width / 8 lanes) per chunk of consecutive SORTED rows (the
+ * (counts/cursor int32 [n_keys], offsets int32 [n_keys + 1 + ceil(n_keys / 4096)] (the tail is the scan's per-chunk
+ * state), row_keys/perm/sorted_keys int32 [N]; all caller-owned scratch; `counts` must be ZERO on entry and is zero
+ * again on return -- allocate it cleared once, no memset per step).  reduce: persistent blocks; one lane group (row width / 8 lanes) per chunk of consecutive SORTED rows (the
  * library picks the chunk length: one equal-length chunk per resident group, at least 8 rows; `rows_per_warp` >= 1 is
  * accepted for ABI stability and otherwise ignored) sums runs of equal keys in registers
  * (dropout-scaled dx rows), applies the L2-normalise backward once per run and atomically adds the run into the

@@ -528,31 +528,56 @@ __device__ __forceinline__ int64_t row_key(const sbr_modality_src_t& s, int64_t 
   return s.key_base + feat_row;
 }
 
-__global__ void plan_count_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods,
-                                  const int64_t* __restrict__ idx, const uint8_t* __restrict__ mods, int64_t N, int k,
-                                  int32_t* __restrict__ counts, int32_t* __restrict__ row_keys) {
+// Plan = counting sort in three launches, no memsets: `counts` is zero on entry (allocation / the previous call's scan
+// clears it), the scan also seeds `cursor` with the segment starts, and the per-chunk scan state lives behind
+// offsets[n_keys] (cleared by the count kernel).  Same-key slots of a warp are combined before the atomic (a 2-row
+// gender table otherwise takes one same-address atomic per batch row).
+constexpr int SCAN_CHUNK = 4096;  // keys per block of the scan (1024 threads x 4)
+
+__global__ void __launch_bounds__(256)
+plan_count_kernel(const sbr_modality_src_t* __restrict__ srcs, int n_mods, const int64_t* __restrict__ idx,
+                  const uint8_t* __restrict__ mods, int64_t N, int k, int32_t* __restrict__ counts,
+                  int32_t* __restrict__ row_keys, int32_t* __restrict__ scan_state, int n_state) {
   SBR_PDL_ENTRY();
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= N) return;
-  const sbr_modality_src_t& s = srcs[min(mods ? (int)mods[r] : 0, n_mods - 1)];
-  const int64_t e = idx[r / k];
-  const int64_t feat_row = s.remap ? (int64_t)__ldg(s.remap + e) : e;
-  const int64_t key = row_key(s, feat_row);
-  row_keys[r] = (int32_t)key;
-  if (key >= 0) atomicAdd(counts + key, 1);
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r < n_state) scan_state[r] = 0;
+  int32_t key = -1;
+  if (r < N) {
+    const sbr_modality_src_t& s = srcs[min(mods ? (int)mods[r] : 0, n_mods - 1)];
+    const int64_t e = idx[r / k];
+    const int64_t feat_row = s.remap ? (int64_t)__ldg(s.remap + e) : e;
+    key = (int32_t)row_key(s, feat_row);
+    row_keys[r] = key;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + key, __popc(peers));
 }
 
-// exclusive scan by one block of 1024 threads: thread t owns the contiguous slice [t * per, (t + 1) * per) -- one
-// serial pass for the slice sums, one block scan of the 1024 sums, one serial pass to write the offsets
+// exclusive scan of counts[0, n) -> offsets[0, n] and cursor[0, n); counts is cleared.  One block per chunk of 4096
+// keys; a block publishes its chunk total (bit 31 = valid) and adds up the totals of the chunks in front of it
+// (in-order block dispatch: those blocks are running or done).
 __global__ void __launch_bounds__(1024)
-plan_scan_kernel(const int32_t* __restrict__ counts, int64_t n, int32_t* __restrict__ offsets) {
+plan_scan_kernel(int32_t* __restrict__ counts, int64_t n, int32_t* __restrict__ offsets, int32_t* __restrict__ cursor,
+                 volatile int32_t* __restrict__ scan_state) {
   SBR_PDL_ENTRY();
   __shared__ int32_t warp_sums[32];
+  __shared__ int32_t s_prefix;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
-  const int64_t beg = min(n, (int64_t)threadIdx.x * per), end = min(n, beg + per);
-  int32_t local = 0;
-  for (int64_t i = beg; i < end; ++i) local += counts[i];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + 4 * threadIdx.x;
+  int32_t c[4] = {0, 0, 0, 0};
+  if (base + 4 <= n && (reinterpret_cast<uintptr_t>(counts) & 15) == 0) {
+    const int4 v = *reinterpret_cast<const int4*>(counts + base);
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    *reinterpret_cast<int4*>(counts + base) = make_int4(0, 0, 0, 0);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (base + j < n) {
+        c[j] = counts[base + j];
+        counts[base + j] = 0;
+      }
+  }
+  const int32_t local = c[0] + c[1] + c[2] + c[3];
   int32_t x = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -569,25 +594,48 @@ plan_scan_kernel(const int32_t* __restrict__ counts, int64_t n, int32_t* __restr
       if (lane >= o) w += y;
     }
     warp_sums[lane] = w;  // inclusive
+    if (lane == 31) {
+      __threadfence();
+      scan_state[blockIdx.x] = (int32_t)(0x80000000u | (uint32_t)w);  // this chunk's total
+    }
+    // totals of the chunks in front (lanes stride over them)
+    int32_t pre = 0;
+    for (int b = lane; b < (int)blockIdx.x; b += 32) {
+      int32_t v;
+      do { v = scan_state[b]; } while (v >= 0);
+      pre += (int32_t)((uint32_t)v & 0x7fffffffu);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+    if (lane == 0) s_prefix = pre;
   }
   __syncthreads();
-  int32_t run = (warp > 0 ? warp_sums[warp - 1] : 0) + x - local;  // exclusive prefix of this thread's slice
-  for (int64_t i = beg; i < end; ++i) {
-    offsets[i] = run;
-    run += counts[i];
+  int32_t run = s_prefix + (warp > 0 ? warp_sums[warp - 1] : 0) + x - local;  // exclusive prefix of this thread's 4 keys
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (base + j < n) {
+      offsets[base + j] = run;
+      cursor[base + j] = run;
+    }
+    run += c[j];
+    if (base + j == n - 1) offsets[n] = run;
   }
-  if (threadIdx.x == blockDim.x - 1) offsets[n] = warp_sums[31];
 }
 
-__global__ void plan_fill_kernel(const int32_t* __restrict__ row_keys, int64_t N, const int32_t* __restrict__ offsets,
-                                 int32_t* __restrict__ cursor, int32_t* __restrict__ perm,
-                                 int32_t* __restrict__ sorted_keys) {
+__global__ void __launch_bounds__(256)
+plan_fill_kernel(const int32_t* __restrict__ row_keys, int64_t N, int32_t* __restrict__ cursor,
+                 int32_t* __restrict__ perm, int32_t* __restrict__ sorted_keys) {
   SBR_PDL_ENTRY();
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= N) return;
-  const int32_t key = row_keys[r];
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int32_t key = r < N ? row_keys[r] : -1;
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  const int leader = __ffs(peers) - 1;
+  int32_t first = 0;
+  if (key >= 0 && lane == leader) first = atomicAdd(cursor + key, __popc(peers));
+  first = __shfl_sync(0xffffffffu, first, leader);
   if (key < 0) return;
-  const int32_t pos = offsets[key] + atomicAdd(cursor + key, 1);
+  const int32_t pos = first + __popc(peers & ((1u << lane) - 1u));
   perm[pos] = (int32_t)r;
   sorted_keys[pos] = key;
 }
@@ -640,13 +688,14 @@ extern "C" int sbr_gather_plan(const sbr_modality_src_t* srcs_dev, int n_mods, c
   SBR_REQUIRE(n_idx > 0 && k >= 1 && n_keys > 0 && n_keys < (1ll << 31), "sbr_gather_plan: bad sizes");
   const int64_t N = n_idx * k;
   SBR_REQUIRE(N < (1ll << 31), "sbr_gather_plan: too many rows");
-  SBR_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_keys, S(stream)));
-  SBR_CHECK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n_keys, S(stream)));
-  SBR_CHECK_CUDA(sbr_launch(plan_count_kernel, dim3(cdiv(N, 256)), dim3(256), 0, S(stream), srcs_dev, n_mods, idx, mods,
-                            N, k, counts, row_keys));
-  SBR_CHECK_CUDA(sbr_launch(plan_scan_kernel, dim3(1), dim3(1024), 0, S(stream), (const int32_t*)counts, n_keys, offsets));
+  const int n_state = (int)((n_keys + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  int32_t* scan_state = offsets + n_keys + 1;
+  SBR_CHECK_CUDA(sbr_launch(plan_count_kernel, dim3(cdiv(N > n_state ? N : n_state, 256)), dim3(256), 0, S(stream),
+                            srcs_dev, n_mods, idx, mods, N, k, counts, row_keys, scan_state, n_state));
+  SBR_CHECK_CUDA(sbr_launch(plan_scan_kernel, dim3((unsigned)n_state), dim3(1024), 0, S(stream), counts, n_keys, offsets,
+                            cursor, (volatile int32_t*)scan_state));
   SBR_CHECK_CUDA(sbr_launch(plan_fill_kernel, dim3(cdiv(N, 256)), dim3(256), 0, S(stream), (const int32_t*)row_keys, N,
-                            (const int32_t*)offsets, cursor, perm, sorted_keys));
+                            cursor, perm, sorted_keys));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

@@ -155,13 +155,56 @@ __global__ void score_loss_kernel(const float* __restrict__ eu, const float* __r
   }
 }
 
-// Fast path (one modality slot per entity, D in {16, 32, 64, 128}): LPR = D / 4 lanes hold one row as float4, so one
-// load instruction covers 32 / LPR item rows; the block's loss goes out with one atomic.
+// Fast path (D in {16, 32, 64, 128}; any number of modality slots per entity): LPR = D / 4 lanes hold one row as
+// float4, so one load instruction covers 32 / LPR item rows; the k slots of a row are aggregated (mean / max) in
+// registers and re-read (L1 / L2 hits) for the gradient; the block's loss goes out with one atomic.
+__device__ __forceinline__ float4 agg_slots4(const float4* __restrict__ row, int k, int stride4, int agg_max) {
+  float4 a = __ldg(row);
+  for (int s = 1; s < k; ++s) {
+    const float4 b = __ldg(row + (size_t)s * stride4);
+    if (agg_max) {
+      a.x = b.x > a.x ? b.x : a.x; a.y = b.y > a.y ? b.y : a.y; a.z = b.z > a.z ? b.z : a.z; a.w = b.w > a.w ? b.w : a.w;
+    } else {
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+  }
+  if (!agg_max && k > 1) {
+    a.x = a.x / (float)k; a.y = a.y / (float)k; a.z = a.z / (float)k; a.w = a.w / (float)k;  // (like the scalar kernel)
+  }
+  return a;
+}
+// gradient g (w.r.t. the aggregated row) -> the k slots: mean: g / k everywhere; max: g at the FIRST slot holding the
+// maximum of each element (strict > in the forward scan), 0 elsewhere
+__device__ __forceinline__ void scatter_slots4(float4* __restrict__ drow, const float4* __restrict__ row, int k, int stride4,
+                                               int agg_max, const float4 g) {
+  if (k == 1) {
+    *drow = g;
+    return;
+  }
+  if (!agg_max) {
+    const float4 q = make_float4(g.x / (float)k, g.y / (float)k, g.z / (float)k, g.w / (float)k);
+    for (int s = 0; s < k; ++s) drow[(size_t)s * stride4] = q;
+    return;
+  }
+  float4 best = __ldg(row);
+  int ax = 0, ay = 0, az = 0, aw = 0;
+  for (int s = 1; s < k; ++s) {
+    const float4 b = __ldg(row + (size_t)s * stride4);
+    if (b.x > best.x) { best.x = b.x; ax = s; }
+    if (b.y > best.y) { best.y = b.y; ay = s; }
+    if (b.z > best.z) { best.z = b.z; az = s; }
+    if (b.w > best.w) { best.w = b.w; aw = s; }
+  }
+  for (int s = 0; s < k; ++s)
+    drow[(size_t)s * stride4] = make_float4(s == ax ? g.x : 0.f, s == ay ? g.y : 0.f, s == az ? g.z : 0.f, s == aw ? g.w : 0.f);
+}
+
 template <int LPR>
 __global__ void __launch_bounds__(256)
-score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ ei, int64_t B, int n, int loss_kind,
-                       float inv_cnt, float ssm_shift, float* __restrict__ logits, double* __restrict__ loss_acc,
-                       float* __restrict__ deu, float* __restrict__ dei) {
+score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ ei, int64_t B, int n, int ku, int ki,
+                       int agg_max_user, int agg_max_item, int loss_kind, float inv_cnt, float ssm_shift,
+                       float* __restrict__ logits, double* __restrict__ loss_acc, float* __restrict__ deu,
+                       float* __restrict__ dei, const float* __restrict__ dlogits_in) {
   SBR_PDL_ENTRY();
   constexpr int D = 4 * LPR;
   constexpr int RPP = 32 / LPR;  // item rows per pass
@@ -174,13 +217,14 @@ score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ e
   const int sub = lane / LPR, li = lane % LPR;
   float lsum = 0.f;
   if (b < B) {
-    const float4 u4 = __ldg(reinterpret_cast<const float4*>(eu + b * D) + li);
-    const float4* items = reinterpret_cast<const float4*>(ei + b * n * D);
+    const float4* urow = reinterpret_cast<const float4*>(eu + b * ku * D) + li;
+    const float4 u4 = agg_slots4(urow, ku, LPR, agg_max_user);
+    const float4* items = reinterpret_cast<const float4*>(ei + b * n * ki * D);
     for (int j0 = 0; j0 < n; j0 += RPP) {
       const int j = j0 + sub;
       float dot = 0.f;
       if (j < n) {
-        const float4 v = __ldg(items + (size_t)j * LPR + li);
+        const float4 v = agg_slots4(items + (size_t)j * ki * LPR + li, ki, LPR, agg_max_item);
         dot = u4.x * v.x + u4.y * v.y + u4.z * v.z + u4.w * v.w;
       }
 #pragma unroll
@@ -188,7 +232,9 @@ score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ e
       if (li == 0 && j < n) sc[j] = dot;
     }
     __syncwarp();
-    if (loss_kind == SBR_LOSS_BPR) {
+    if (dlogits_in != nullptr) {  // gradients of an externally computed loss (autograd path): d loss / d score given
+      for (int j = lane; j < n; j += 32) gr[j] = dlogits_in[b * n + j];
+    } else if (loss_kind == SBR_LOSS_BPR) {
       float s0 = sc[0], g0 = 0.f;
       for (int j = 1 + lane; j < n; j += 32) {
         float d = s0 - sc[j];
@@ -226,14 +272,16 @@ score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ e
     __syncwarp();
     if (deu != nullptr && dei != nullptr) {
       float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4* dit = reinterpret_cast<float4*>(dei + b * n * D);
+      float4* dit = reinterpret_cast<float4*>(dei + b * n * ki * D);
       for (int j0 = 0; j0 < n; j0 += RPP) {
         const int j = j0 + sub;
         if (j < n) {
           const float g = gr[j];
-          const float4 v = __ldg(items + (size_t)j * LPR + li);
+          const float4* irow = items + (size_t)j * ki * LPR + li;
+          const float4 v = agg_slots4(irow, ki, LPR, agg_max_item);
           du.x += g * v.x; du.y += g * v.y; du.z += g * v.z; du.w += g * v.w;
-          dit[(size_t)j * LPR + li] = make_float4(g * u4.x, g * u4.y, g * u4.z, g * u4.w);
+          scatter_slots4(dit + (size_t)j * ki * LPR + li, irow, ki, LPR, agg_max_item,
+                         make_float4(g * u4.x, g * u4.y, g * u4.z, g * u4.w));
         }
       }
 #pragma unroll
@@ -243,7 +291,7 @@ score_loss_fast_kernel(const float* __restrict__ eu, const float* __restrict__ e
         du.z += __shfl_xor_sync(0xffffffffu, du.z, o);
         du.w += __shfl_xor_sync(0xffffffffu, du.w, o);
       }
-      if (sub == 0) reinterpret_cast<float4*>(deu + b * D)[li] = du;
+      if (sub == 0) scatter_slots4(reinterpret_cast<float4*>(deu + b * ku * D) + li, urow, ku, LPR, agg_max_user, du);
     }
   }
   if (lane == 0) s_loss[wib] = lsum;
@@ -482,7 +530,7 @@ extern "C" int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n
   if (!aggregator_sum)
     cnt = loss_kind == SBR_LOSS_BPR ? (double)B * (n - 1) : (loss_kind == SBR_LOSS_BCE ? (double)B * n : (double)B);
   const float inv = (float)(1.0 / cnt);
-  if (ku == 1 && ki == 1 && u_agg == nullptr && i_agg == nullptr && (D == 16 || D == 32 || D == 64 || D == 128) &&
+  if (u_agg == nullptr && i_agg == nullptr && (D == 16 || D == 32 || D == 64 || D == 128) &&
       (reinterpret_cast<uintptr_t>(eu) & 15) == 0 && (reinterpret_cast<uintptr_t>(ei) & 15) == 0 &&
       (deu == nullptr || (reinterpret_cast<uintptr_t>(deu) & 15) == 0) &&
       (dei == nullptr || (reinterpret_cast<uintptr_t>(dei) & 15) == 0)) {
@@ -491,7 +539,8 @@ extern "C" int sbr_score_loss(const float* eu, const float* ei, int64_t B, int n
     const unsigned blocks = cdiv(B, nw);
 #define SBR_FAST(LPR_)                                                                                              \
   SBR_CHECK_CUDA(sbr_launch(score_loss_fast_kernel<LPR_>, dim3(blocks), dim3(nw * 32), sm, S(stream), eu, ei, B, n,  \
-                            loss_kind, inv, ssm_shift, logits, loss_acc, deu, dei))
+                            ku, ki, agg_max_user, agg_max_item, loss_kind, inv, ssm_shift, logits, loss_acc, deu, dei, \
+                            (const float*)nullptr))
     if (D == 16) SBR_FAST(4);
     else if (D == 32) SBR_FAST(8);
     else if (D == 64) SBR_FAST(16);
@@ -515,6 +564,24 @@ extern "C" int sbr_score_bwd(const float* eu, const float* ei, int64_t B, int n,
   SBR_REQUIRE(eu && ei && dlogits && deu && dei && B > 0 && n >= 1 && ku >= 1 && ki >= 1,
               "sbr_score_bwd: bad arguments");
   SBR_REQUIRE(D > 0 && D <= 512 && n <= 1024, "sbr_score_bwd: D=%d / n=%d out of range", D, n);
+  if ((D == 16 || D == 32 || D == 64 || D == 128) && (reinterpret_cast<uintptr_t>(eu) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(ei) & 15) == 0 && (reinterpret_cast<uintptr_t>(deu) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dei) & 15) == 0) {
+    const int nw = 8;
+    const size_t sm = ((size_t)nw * 2 * n + nw) * sizeof(float);
+    const unsigned blocks = cdiv(B, nw);
+#define SBR_FASTB(LPR_)                                                                                             \
+  SBR_CHECK_CUDA(sbr_launch(score_loss_fast_kernel<LPR_>, dim3(blocks), dim3(nw * 32), sm, S(stream), eu, ei, B, n,  \
+                            ku, ki, agg_max_user, agg_max_item, (int)SBR_LOSS_BCE, 1.f, 0.f, (float*)nullptr,        \
+                            (double*)nullptr, deu, dei, dlogits))
+    if (D == 16) SBR_FASTB(4);
+    else if (D == 32) SBR_FASTB(8);
+    else if (D == 64) SBR_FASTB(16);
+    else SBR_FASTB(32);
+#undef SBR_FASTB
+    SBR_LAUNCH_CHECK();
+    return SBR_OK;
+  }
   const int wpb = 4;
   size_t shmem = (size_t)wpb * 2 * n * sizeof(float);
   DISPATCH_NV(D, 32, score_loss_kernel<NVv><<<cdiv(B, wpb), wpb * 32, shmem, S(stream)>>>(

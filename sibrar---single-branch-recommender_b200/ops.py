@@ -218,7 +218,8 @@ class GatherPlan:
         self.n_keys, self.N = int(n_keys), int(N)
         self.counts = torch.zeros(n_keys, dtype=i32, device=device)
         self.cursor = torch.zeros(n_keys, dtype=i32, device=device)
-        self.offsets = torch.zeros(n_keys + 1, dtype=i32, device=device)
+        # counts: zero on entry, cleared again by the plan's scan; offsets: + the scan's per-chunk state (include/sibrar_b200.h)
+        self.offsets = torch.zeros(n_keys + 1 + (n_keys + 4095) // 4096, dtype=i32, device=device)
         self.row_keys = torch.empty(N, dtype=i32, device=device)
         self.perm = torch.empty(N, dtype=i32, device=device)
         self.sorted_keys = torch.empty(N, dtype=i32, device=device)

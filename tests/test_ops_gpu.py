@@ -418,11 +418,13 @@ def test_batchnorm_fwd_bwd(act, rows, C_, y16):
     assert torch.equal(dz_b, dz.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("D", [24, 64, 128])  # 24: scalar kernel; 64 / 128: the float4 fast path (any slot count)
 @pytest.mark.parametrize("loss,agg_u,agg_i,ku,ki,sum_", [("bpr", 0, 0, 1, 1, 0), ("bpr", 0, 1, 2, 2, 0),
-                                                         ("bce", 1, 0, 2, 1, 1), ("sampled_softmax", 0, 0, 1, 2, 0)])
-def test_score_loss(loss, agg_u, agg_i, ku, ki, sum_):
+                                                         ("bce", 1, 0, 2, 1, 1), ("sampled_softmax", 0, 0, 1, 2, 0),
+                                                         ("bpr", 1, 1, 3, 3, 0)])
+def test_score_loss(loss, agg_u, agg_i, ku, ki, sum_, D):
     from oracle import sbnet_oracle as O
-    B, n, D = 37, 6, 24
+    B, n = 37, 6
     eu = torch.randn(B, ku, D, device=DEV).requires_grad_()
     ei = torch.randn(B, n, ki, D, device=DEV).requires_grad_()
     logits = torch.empty(B, n, device=DEV)
@@ -439,6 +441,11 @@ def test_score_loss(loss, agg_u, agg_i, ku, ki, sum_):
     assert _relerr(logits, ref_logits) < 1e-5
     assert abs(acc.item() - rl) < 1e-5 * max(1, abs(rl))
     assert _relerr(deu, eu.grad) < 1e-4 and _relerr(dei, ei.grad) < 1e-4
+    # the gradient-only entry (autograd glue): same gradients from the externally computed d loss / d logits
+    deu2, dei2 = torch.empty_like(eu), torch.empty_like(ei)
+    ops.score_bwd(eu.detach(), ei.detach(), B, n, ku, ki, D, agg_u, agg_i, torch.from_numpy(dlog).float().to(DEV), deu2,
+                  dei2)
+    assert _relerr(deu2, eu.grad) < 1e-4 and _relerr(dei2, ei.grad) < 1e-4
 
 
 @pytest.mark.parametrize("loss,D,n,bn_user,bn_item", [("bpr", 64, 11, True, True), ("bce", 32, 4, False, True),
