@@ -379,6 +379,31 @@ int sbr_adam_step(const sbr_adam_tensor_t* tensors_dev, int n_tensors, int64_t t
                                                       2 = Adagrad (torch.optim.Adagrad defaults; exp_avg_sq holds the
                                                       running sum of squares, exp_avg is left untouched) */
 
+/* Data-parallel optimizer step (the gradient all-reduce of the data-parallel train step; the
+ * reference is single-process): the SUM of the flat gradient buffers of all ranks is formed inside the NVSwitch
+ * (multimem.ld_reduce on the multicast mapping of the buffer), broadcast (multimem.st) into every rank's `sum` buffer
+ * and consumed by the same Adam / AdamW / Adagrad update as sbr_adam_step -- ONE kernel per rank and step, no NCCL
+ * call.  All buffers are symmetric allocations (same size on every rank, mapped by every rank, multicast-bound). */
+typedef struct {
+  const float* flat_grads;        /* local address of this rank's flat gradient buffer [total]                       */
+  const float* mc_grads;          /* multicast address of the same buffer (reads reduce over the ranks)              */
+  float* sum_local;               /* local address of the summed-gradient buffer [total]                             */
+  float* sum_mc;                  /* multicast address of it (stores reach every rank)                               */
+  int64_t total;                  /* floats; a multiple of 4 * world                                                 */
+  int32_t* const* peer_flags_dev; /* device array [world]: address of every rank's flag words int32 [2 * world]      */
+  int32_t* flags_local;           /* this rank's flag words (zero at allocation, only ever grow)                     */
+  int64_t* state;                 /* local int64 [4], zero at allocation: epoch, 2 release words, grid arrivals      */
+  int world, rank;
+} sbr_mc_comm_t;
+int sbr_adam_step_mc(const sbr_adam_tensor_t* tensors_dev, int n_tensors, int64_t total_chunks,
+                     const int32_t* chunk_to_tensor_dev, const int64_t* chunk_offset_dev, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int decoupled, const int64_t* step_dev,
+                     float grad_scale, int apply_adam, const sbr_mc_comm_t* comm, int grid_blocks, void* stream);
+/* every adam tensor's `grad` must point into flat_grads; grid_blocks: the same value on every call that shares
+ * `state` (<= 2 x SM count: the blocks of the grid wait for each other); apply_adam = 0: all-reduce only (the sums
+ * are left in sum_local). */
+
+
 /* ------------------------------------------------------------------------------------------------ evaluation
  * Fused  scores = U * I^T  (bf16 tcgen05 GEMM, fp32 accumulate)  ->  seen-item mask (-inf)  ->  per-user top-k.
  * The [U, I] score matrix never reaches HBM.  Replaces eval/eval.py:216-220 + the topk inside rmet.calculate

@@ -62,6 +62,12 @@ class AdamTensor(C.Structure):
                 ("numel", c_i64), ("cols", c_i64), ("shadow_ld", c_i64)]
 
 
+class McComm(C.Structure):
+    """sbr_mc_comm_t (include/sibrar_b200.h): symmetric buffers of the fused all-reduce + optimizer kernel"""
+    _fields_ = [("flat_grads", c_vp), ("mc_grads", c_vp), ("sum_local", c_vp), ("sum_mc", c_vp), ("total", c_i64),
+                ("peer_flags_dev", c_vp), ("flags_local", c_vp), ("state", c_vp), ("world", C.c_int), ("rank", C.c_int)]
+
+
 _PROTOS = {
     "sbr_gemm_bf16": [c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, c_i64, c_i64, c_i64, C.POINTER(GemmEpilogue), c_vp],
     "sbr_gemm_bits_bf16": [c_vp, c_i64, c_vp, c_i64, C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp],
@@ -113,6 +119,8 @@ _PROTOS = {
                      C.POINTER(c_vp), C.POINTER(c_vp), c_vp, c_i64, c_vp],
     "sbr_adam_step": [c_vp, C.c_int, c_i64, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, C.c_int, c_vp, c_f32,
                       c_vp],
+    "sbr_adam_step_mc": [c_vp, C.c_int, c_i64, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, C.c_int, c_vp, c_f32,
+                         C.c_int, C.POINTER(McComm), C.c_int, c_vp],
     "sbr_topk_workspace_bytes": [c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.POINTER(c_i64)],
     "sbr_topk_scores_masked": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_i32,
                                c_vp, c_vp, c_i64, c_vp],

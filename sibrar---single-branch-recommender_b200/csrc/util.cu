@@ -127,31 +127,19 @@ __device__ __forceinline__ void adam_update(float& p, float& g, float& m, float&
   p -= step_size * m / (sqrtf(v) / bc2_sqrt + eps);
 }
 
-__global__ void __launch_bounds__(256)
-adam_kernel(const sbr_adam_tensor_t* __restrict__ tensors, const int32_t* __restrict__ chunk_to_tensor,
-            const int64_t* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps, float wd,
-            int decoupled, const int64_t* __restrict__ step_dev, float grad_scale) {
-  SBR_PDL_ENTRY();
-  // bias corrections: double-precision pow once per block (every thread doing it cost more than the update itself)
-  __shared__ float s_bc[2];
-  if (threadIdx.x == 0) {
-    const double step = (double)*step_dev;
-    s_bc[0] = (float)(1.0 - pow((double)beta1, step));
-    s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, step));
-  }
-  const sbr_adam_tensor_t t = tensors[chunk_to_tensor[blockIdx.x]];
-  const int64_t off = chunk_offset[blockIdx.x];
+// one chunk [off, off + ADAM_CHUNK) of tensor t; g_src = where the gradient is READ (t.grad, or the all-reduced copy of
+// the data-parallel step); t.grad itself is cleared either way (zero_grad)
+__device__ __forceinline__ void adam_chunk(const sbr_adam_tensor_t& t, int64_t off, const float* __restrict__ g_src,
+                                           float lr, float beta1, float beta2, float eps, float wd, int decoupled,
+                                           float grad_scale, float step_size, float bc2_sqrt) {
   const int64_t end = min(off + (int64_t)ADAM_CHUNK, t.numel);
-  __syncthreads();
-  const float bc2_sqrt = s_bc[1];
-  const float step_size = lr / s_bc[0];
   const auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
-  const bool vec = (t.numel & 3) == 0 && (off & 3) == 0 && al(t.param, 16) && al(t.grad, 16) && al(t.exp_avg, 16) &&
-                   al(t.exp_avg_sq, 16) &&
+  const bool vec = (t.numel & 3) == 0 && (off & 3) == 0 && al(t.param, 16) && al(t.grad, 16) && al(g_src, 16) &&
+                   al(t.exp_avg, 16) && al(t.exp_avg_sq, 16) &&
                    (t.shadow_bf16 == nullptr || ((t.cols & 3) == 0 && (t.shadow_ld & 3) == 0 && al(t.shadow_bf16, 8)));
   if (vec) {
     for (int64_t i = off + 4 * (int64_t)threadIdx.x; i < end; i += 4 * (int64_t)blockDim.x) {
-      float4 p4 = *reinterpret_cast<const float4*>(t.param + i), g4 = *reinterpret_cast<const float4*>(t.grad + i);
+      float4 p4 = *reinterpret_cast<const float4*>(t.param + i), g4 = *reinterpret_cast<const float4*>(g_src + i);
       float4 m4 = *reinterpret_cast<const float4*>(t.exp_avg + i), v4 = *reinterpret_cast<const float4*>(t.exp_avg_sq + i);
       adam_update(p4.x, g4.x, m4.x, v4.x, grad_scale, lr, wd, decoupled, beta1, beta2, step_size, bc2_sqrt, eps);
       adam_update(p4.y, g4.y, m4.y, v4.y, grad_scale, lr, wd, decoupled, beta1, beta2, step_size, bc2_sqrt, eps);
@@ -172,7 +160,7 @@ adam_kernel(const sbr_adam_tensor_t* __restrict__ tensors, const int32_t* __rest
     return;
   }
   for (int64_t i = off + threadIdx.x; i < end; i += blockDim.x) {
-    float p = t.param[i], g = t.grad[i], m = t.exp_avg[i], v = t.exp_avg_sq[i];
+    float p = t.param[i], g = g_src[i], m = t.exp_avg[i], v = t.exp_avg_sq[i];
     adam_update(p, g, m, v, grad_scale, lr, wd, decoupled, beta1, beta2, step_size, bc2_sqrt, eps);
     t.param[i] = p;
     t.exp_avg[i] = m;
@@ -182,6 +170,140 @@ adam_kernel(const sbr_adam_tensor_t* __restrict__ tensors, const int32_t* __rest
       int64_t r = i / t.cols, c = i - r * t.cols;
       reinterpret_cast<bf16*>(t.shadow_bf16)[r * t.shadow_ld + c] = __float2bfloat16(p);
     }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(const sbr_adam_tensor_t* __restrict__ tensors, const int32_t* __restrict__ chunk_to_tensor,
+            const int64_t* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps, float wd,
+            int decoupled, const int64_t* __restrict__ step_dev, float grad_scale) {
+  SBR_PDL_ENTRY();
+  // bias corrections: double-precision pow once per block (every thread doing it cost more than the update itself)
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double step = (double)*step_dev;
+    s_bc[0] = (float)(1.0 - pow((double)beta1, step));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, step));
+  }
+  const sbr_adam_tensor_t t = tensors[chunk_to_tensor[blockIdx.x]];
+  const int64_t off = chunk_offset[blockIdx.x];
+  __syncthreads();
+  adam_chunk(t, off, t.grad, lr, beta1, beta2, eps, wd, decoupled, grad_scale, lr / s_bc[0], s_bc[1]);
+}
+
+// ------------------------------------------------------------------------------------------------ data-parallel Adam
+// Gradient all-reduce + optimizer in ONE kernel over NVSwitch multicast memory (replaces the NCCL all-reduce nodes in
+// front of the optimizer of the data-parallel step).  Every rank runs the same persistent grid:
+//   barrier A  (all ranks' gradients are complete)
+//   phase 1    rank r sums slice r of the flat gradient buffer over all ranks INSIDE the switch
+//              (multimem.ld_reduce on the multicast address) and broadcasts the sums into every rank's `sum` buffer
+//              (multimem.st) -- each NVLink carries the buffer once in each direction
+//   barrier B  (every slice has landed everywhere)
+//   phase 2    multi-tensor Adam / AdamW / Adagrad on the local replica, reading the summed gradients, clearing the
+//              local accumulators, refreshing the bf16 shadows.
+// Cross-GPU barriers are epoch flags in symmetric memory (rank r writes epoch e into word [slot][r] of every peer and
+// waits until its own words [slot][*] reach e; flags only grow, so CUDA-graph replays need no reset); block 0 talks to
+// the peers, the other blocks of the grid follow a local release word.
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu64(int64_t* p, int64_t v) {
+  asm volatile("st.release.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int64_t ld_acquire_gpu64(const int64_t* p) {
+  int64_t v;
+  asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// a peer that never arrives (crashed rank) must not hang the GPU: after ~10 s of polling the kernel traps
+struct spin_guard {
+  long long t0 = -1;
+  unsigned n = 0;
+  __device__ __forceinline__ void poll() {
+#ifdef __CUDA_ARCH__
+    if ((++n & 0x3ffu) == 0) {
+      const long long now = clock64();
+      if (t0 < 0) t0 = now;
+      if (now - t0 > 20000000000ll) asm volatile("trap;");
+    }
+#endif
+  }
+};
+
+// block 0: handshake with every peer on `slot`, then release the local grid; other blocks: wait for the release
+__device__ __forceinline__ void mc_barrier(const sbr_mc_comm_t& c, int slot, int32_t epoch) {
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < c.world) {
+      __threadfence_system();
+      st_release_sys(c.peer_flags_dev[threadIdx.x] + slot * c.world + c.rank, epoch);
+      spin_guard sg;
+      while (ld_acquire_sys(c.flags_local + slot * c.world + threadIdx.x) - epoch < 0) sg.poll();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu64(c.state + 1 + slot, (int64_t)epoch);
+  } else {
+    if (threadIdx.x == 0) {
+      spin_guard sg;
+      while (ld_acquire_gpu64(c.state + 1 + slot) - (int64_t)epoch < 0) sg.poll();
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_mc_kernel(const sbr_adam_tensor_t* __restrict__ tensors, int64_t total_chunks,
+               const int32_t* __restrict__ chunk_to_tensor, const int64_t* __restrict__ chunk_offset, float lr,
+               float beta1, float beta2, float eps, float wd, int decoupled, const int64_t* __restrict__ step_dev,
+               float grad_scale, int apply_adam, sbr_mc_comm_t c) {
+  SBR_PDL_ENTRY();
+  __shared__ float s_bc[2];
+  const int32_t epoch = (int32_t)(ld_acquire_gpu64(c.state) + 1);  // (read by every block before the grid barrier below)
+  if (threadIdx.x == 0) {
+    const double step = (double)*step_dev;
+    s_bc[0] = (float)(1.0 - pow((double)beta1, step));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, step));
+  }
+  mc_barrier(c, 0, epoch);
+  // ---- phase 1: my slice, reduced in the switch, broadcast to every rank
+  const int64_t slice = c.total / c.world;  // floats, a multiple of 4
+  const int64_t lo = slice * c.rank;
+  for (int64_t i = 4 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x); i < slice; i += 4 * (int64_t)gridDim.x * blockDim.x) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(c.mc_grads + lo + i)
+                 : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c.sum_mc + lo + i), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+  // ---- grid barrier (all of this rank's stores issued), then barrier B over the ranks
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    atomicAdd(reinterpret_cast<unsigned long long*>(c.state + 3), 1ull);
+    if (blockIdx.x == 0) {
+      const int64_t want = (int64_t)epoch * gridDim.x;  // (the grid size is fixed for the lifetime of `state`)
+      spin_guard sg;
+      while (ld_acquire_gpu64(c.state + 3) - want < 0) sg.poll();
+      st_release_gpu64(c.state, (int64_t)epoch);  // every block has read the previous epoch by now
+    }
+  }
+  __syncthreads();
+  mc_barrier(c, 1, epoch);
+  if (!apply_adam) return;
+  // ---- phase 2: the optimizer on the summed gradients (grad_scale carries 1 / world)
+  const float bc2_sqrt = s_bc[1], step_size = lr / s_bc[0];
+  for (int64_t ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+    const sbr_adam_tensor_t t = tensors[chunk_to_tensor[ch]];
+    const float* g_src = c.sum_local + (t.grad - c.flat_grads);
+    adam_chunk(t, chunk_offset[ch], g_src, lr, beta1, beta2, eps, wd, decoupled, grad_scale, step_size, bc2_sqrt);
   }
 }
 
@@ -441,6 +563,28 @@ extern "C" int sbr_adam_step(const sbr_adam_tensor_t* tensors_dev, int n_tensors
   SBR_CHECK_CUDA(sbr_launch(adam_kernel, dim3((unsigned)total_chunks), dim3(256), (size_t)(0), S(stream), tensors_dev, chunk_to_tensor_dev, chunk_offset_dev, lr,
                                                              beta1, beta2, eps, weight_decay, decoupled, step_dev,
                                                              grad_scale));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_adam_step_mc(const sbr_adam_tensor_t* tensors_dev, int n_tensors, int64_t total_chunks,
+                                const int32_t* chunk_to_tensor_dev, const int64_t* chunk_offset_dev, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                                const int64_t* step_dev, float grad_scale, int apply_adam, const sbr_mc_comm_t* comm,
+                                int grid_blocks, void* stream) {
+  SBR_REQUIRE(tensors_dev && chunk_to_tensor_dev && chunk_offset_dev && step_dev && n_tensors > 0 && total_chunks > 0,
+              "sbr_adam_step_mc: bad arguments");
+  SBR_REQUIRE(comm && comm->flat_grads && comm->mc_grads && comm->sum_local && comm->sum_mc && comm->peer_flags_dev &&
+                  comm->flags_local && comm->state && comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world,
+              "sbr_adam_step_mc: bad communicator");
+  SBR_REQUIRE(comm->world <= 256 && comm->total > 0 && comm->total % (4 * (int64_t)comm->world) == 0,
+              "sbr_adam_step_mc: total=%lld must be a multiple of 4 * world", (long long)comm->total);
+  // persistent grid, every block resident (the blocks wait for each other): at most 2 per SM
+  SBR_REQUIRE(grid_blocks >= 1 && grid_blocks <= 2 * sbr_num_sms(), "sbr_adam_step_mc: grid_blocks=%d not in [1, %d]",
+              grid_blocks, 2 * sbr_num_sms());
+  SBR_CHECK_CUDA(sbr_launch(adam_mc_kernel, dim3((unsigned)grid_blocks), dim3(256), (size_t)0, S(stream), tensors_dev,
+                            total_chunks, chunk_to_tensor_dev, chunk_offset_dev, lr, beta1, beta2, eps, weight_decay,
+                            decoupled, step_dev, grad_scale, apply_adam, *comm));
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

@@ -453,6 +453,14 @@ class AdamPlan:
              ptr(self.chunk_offset), float(lr), float(beta1), float(beta2), float(eps), float(wd), int(decoupled),
              ptr(step_dev), float(grad_scale), stream_ptr())
 
+    def step_mc(self, comm, grid_blocks, lr, beta1, beta2, eps, wd, decoupled, step_dev, grad_scale=1.0,
+                apply_adam=True):
+        """data parallel: in-switch all-reduce of the flat gradient buffer + the update, one kernel (sbr_adam_step_mc);
+        ``comm`` is a ``_lib.McComm``"""
+        call("sbr_adam_step_mc", ptr(self.tensors), self.n_tensors, self.total_chunks, ptr(self.chunk_to_tensor),
+             ptr(self.chunk_offset), float(lr), float(beta1), float(beta2), float(eps), float(wd), int(decoupled),
+             ptr(step_dev), float(grad_scale), int(bool(apply_adam)), C.byref(comm), int(grid_blocks), stream_ptr())
+
 
 def topk_n_splits(U: int, I: int, D: int, k: int, n_sms: int = 148) -> int:
     nu = 256 if D <= 256 else 128

@@ -80,32 +80,65 @@ class DataParallelTrainer(FusedTrainer):
                     ent.sb_chain.bn_sync = BnSync(self.world)
 
     def _alloc_flat_grads(self, total: int, dev):
-        """the flat gradient buffer in SYMMETRIC memory (every rank maps every peer's buffer + the NVSwitch multicast
-        address): the gradient collective is then ONE in-switch all-reduce (`multimem.ld_reduce` of each rank's slice +
-        `multimem.st` of the sums, torch's symm_mem kernels) instead of two NCCL calls.  SBR_DP_COLLECTIVE=nccl keeps
-        the NCCL buckets (also the fallback when symmetric memory / multicast is not available)."""
+        """the flat gradient buffer in SYMMETRIC memory (CUDA VMM allocations mapped by every rank and bound to an
+        NVSwitch multicast object; ``torch.distributed._symmetric_memory`` does the allocation and the handle exchange --
+        plumbing).  The gradient collective is then part of the optimizer kernel (``sbr_adam_step_mc``: in-switch
+        reduction with ``multimem.ld_reduce``, broadcast with ``multimem.st``, Adam on the sums): no NCCL node in the
+        step.  SBR_DP_COLLECTIVE=nccl keeps the two NCCL all-reduce buckets (also the fallback when multicast memory
+        is not available: no NVSwitch, older driver)."""
         import os
-        self._symm = None
-        if os.environ.get("SBR_DP_COLLECTIVE", "symm") != "nccl" and self.world > 1:
+        self._mc = None
+        self._mc_error = None
+        if os.environ.get("SBR_DP_COLLECTIVE", "multimem") != "nccl" and self.world > 1:
             try:
-                import torch.distributed._symmetric_memory as symm_mem
-                t = symm_mem.empty(total, dtype=torch.float32, device=dev)
-                t.zero_()
-                hdl = symm_mem.rendezvous(t, dist.group.WORLD.group_name)
-                self._symm = (hdl, dist.group.WORLD.group_name,
-                              "multimem" if hdl.has_multicast_support() else "two_shot")
-                return t
-            except Exception as e:  # noqa: BLE001  (older drivers / no P2P): NCCL
-                self._symm_error = repr(e)
+                self._mc = self._setup_multicast(total, dev)
+                return self._mc["grads"][:total]
+            except Exception as e:  # noqa: BLE001
+                self._mc, self._mc_error = None, repr(e)
         return torch.zeros(total, dtype=torch.float32, device=dev)
+
+    def _setup_multicast(self, total: int, dev):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from ._lib import McComm
+        world, rank = self.world, dist.get_rank()
+        group = dist.group.WORLD.group_name
+        padded = -(-total // (4 * world)) * 4 * world
+        bufs = {}
+        for name, shape, dtype in (("grads", padded, torch.float32), ("sums", padded, torch.float32),
+                                   ("flags", max(64, 2 * world), torch.int32)):
+            t = symm_mem.empty(shape, dtype=dtype, device=dev)
+            t.zero_()
+            bufs[name] = t
+            bufs[name + "_hdl"] = symm_mem.rendezvous(t, group)
+        torch.cuda.synchronize()
+        dist.barrier()  # every rank's buffers are zero before anybody signals
+        hg, hs, hf = bufs["grads_hdl"], bufs["sums_hdl"], bufs["flags_hdl"]
+        if not int(hg.multicast_ptr) or not int(hs.multicast_ptr):
+            raise RuntimeError("symmetric memory without a multicast mapping (no NVSwitch multicast on this system)")
+        state = torch.zeros(4, dtype=torch.int64, device=dev)
+        peer_flags = torch.tensor([int(p) for p in hf.buffer_ptrs], dtype=torch.int64, device=dev)
+        comm = McComm()
+        comm.flat_grads, comm.mc_grads = bufs["grads"].data_ptr(), int(hg.multicast_ptr)
+        comm.sum_local, comm.sum_mc = bufs["sums"].data_ptr(), int(hs.multicast_ptr)
+        comm.total = padded
+        comm.peer_flags_dev, comm.flags_local, comm.state = peer_flags.data_ptr(), bufs["flags"].data_ptr(), state.data_ptr()
+        comm.world, comm.rank = world, rank
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        bufs.update(comm=comm, state=state, peer_flags=peer_flags, total=total,
+                    grid=2 * n_sms)  # persistent, all blocks resident (they wait for each other)
+        return bufs
 
     @property
     def collective(self) -> str:
-        return f"symm_mem {self._symm[2]} all-reduce (1 call / step)" if self._symm else "nccl all-reduce (2 buckets / step)"
+        if self._mc is not None:
+            return ("in-switch all-reduce (multimem.ld_reduce / multimem.st over NVSwitch multicast memory) fused into "
+                    "the optimizer kernel sbr_adam_step_mc (1 launch / step, no NCCL)")
+        return "nccl all-reduce (2 buckets / step)" + (f" [multicast unavailable: {self._mc_error}]" if self._mc_error else "")
 
     def _after_item_backward(self):
         lo, mid, _ = self.bucket_bounds
-        if mid <= lo or not self._reduce_now or self._symm:
+        if mid <= lo or not self._reduce_now or self._mc is not None:
             return
         if torch.cuda.is_current_stream_capturing():
             # inside the step's CUDA graph the collective is captured in stream order (the buckets are a few MB:
@@ -116,13 +149,8 @@ class DataParallelTrainer(FusedTrainer):
 
     def _after_user_backward(self):
         _, mid, hi = self.bucket_bounds
-        if self._symm and self._reduce_now:
-            _, group, kind = self._symm
-            if kind == "multimem":
-                torch.ops.symm_mem.multimem_all_reduce_(self.flat_grads, "sum", group)
-            else:
-                torch.ops.symm_mem.two_shot_all_reduce_(self.flat_grads, "sum", group)
-            return
+        if self._mc is not None:
+            return  # (the collective is the prologue of the optimizer kernel)
         if hi > mid and self._reduce_now:
             if torch.cuda.is_current_stream_capturing():
                 dist.all_reduce(self.flat_grads[mid:hi], op=dist.ReduceOp.SUM)
@@ -132,11 +160,23 @@ class DataParallelTrainer(FusedTrainer):
             w.wait()  # stream-level wait: no host synchronisation
         self._work.clear()
 
-
     def optimizer_step(self, ticked: bool = False):
-        if not ticked:  # called on its own after accumulation steps: their rank-local sums are reduced here, once
-            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
-        super().optimizer_step(ticked)
+        if self._mc is None:
+            if not ticked:  # called on its own after accumulation steps: their rank-local sums are reduced here, once
+                dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
+            return super().optimizer_step(ticked)
+        b1, b2 = self.betas
+        if not ticked:
+            ops.tick(self.opt_step_dev)
+        mode = {"adam": 0, "adamw": 1, "adagrad": 2}[self.learn.optimizer]
+        eps = 1e-10 if mode == 2 and self.eps == 1e-8 else self.eps
+        mc = self._mc
+        self.adam.step_mc(mc["comm"], mc["grid"], self.learn.lr, b1, b2, eps, self.learn.wd, mode, self.opt_step_dev,
+                          self.grad_scale)
+        if self.snapshot_grads:  # the summed gradients the update consumed
+            if self.grads_snapshot is None:
+                self.grads_snapshot = torch.empty_like(self.flat_grads)
+            self.grads_snapshot.copy_(mc["sums"][:mc["total"]])
 
 
 class ShardedEvaluator(FullEvaluator):

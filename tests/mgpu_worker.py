@@ -73,6 +73,13 @@ def main(out_path):
         res[f"{tag}/collective"] = tr.collective
         res[f"{tag}/collective_vs_nccl_max_err_rel"] = float(
             np.abs(tr.grads_snapshot.cpu().numpy() / world - dp_grads).max() / np.abs(dp_grads).max())
+        if os.environ.get("SBR_MGPU_DEBUG"):
+            snap = tr.grads_snapshot.cpu().numpy() / world
+            for k, prm in model.named_parameters():
+                o, nel, _ = tr.grad_offsets[id(prm)]
+                e = np.abs(snap[o:o + nel] - dp_grads[o:o + nel]).max()
+                print(rank, tag, k, o, nel, "err", e, "max", np.abs(dp_grads[o:o + nel]).max(),
+                      "snap max", np.abs(snap[o:o + nel]).max(), flush=True)
         flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
         mx, mn = flat.clone(), flat.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
