@@ -45,10 +45,18 @@ def _fixture_shapes():
                    "lyrics_mpnet": (VECTOR, 96)})
     amazon = Shape(137, 260, 3000, {},
                    {"title_mpnet": (VECTOR, 768), "description_mpnet": (VECTOR, 64), "image_resnet": (VECTOR, 64)})
-    return onion, amazon
+    # users with a vector, a categorical and a TAG feature: the three forms of a plain (non single-branch) entity
+    plain = Shape(90, 140, 2200,
+                  {"country": (CATEGORICAL, 9), "mpnet": (VECTOR, 40), "languages": (TAG, 7)},
+                  {"genres": (TAG, 11), "plot_mpnet": (VECTOR, 24)})
+    return onion, amazon, plain
 
 
-ONION_FIXTURE_SHAPE, AMAZON_FIXTURE_SHAPE = _fixture_shapes()
+ONION_FIXTURE_SHAPE, AMAZON_FIXTURE_SHAPE, PLAIN_FIXTURE_SHAPE = _fixture_shapes()
+
+
+def _plain_item():
+    return entity([("interactions", []), ("genres", []), ("plot_mpnet", [])], [16], 16, single_branch_input_dropout=0.1)
 
 # name -> dict(corpus kwargs, model conf, loss, optimizer, ...)
 CASES = {
@@ -95,6 +103,29 @@ CASES = {
                                eval_modalities=["title_mpnet", "image_resnet"],
                                embedding_regularization_type="pairwise_single", regularization_weight=0.1)),
         rec_loss="sampled_softmax", optimizer="adamw", lr=1e-3, wd=1e-2, batch=12, n_neg=5, steps=2),
+    # ---- plain (non single-branch) USER entities on other than ID features (FeatureEmbedding as the entity module,
+    # sgd_alg.py:1279-1396, 2043-2046): vector feature with pre- and post-embedding layers, categorical feature + post
+    # layers, tag feature (EmbeddingBag) + post layers
+    "plain_user_vector": dict(
+        corpus=dict(shape=PLAIN_FIXTURE_SHAPE, split_type="random", seed=31, scale=1.0),
+        model=dict(shared_common_dim=12,
+                   user=dict(feature_name="mpnet", embedding_dim=20, pre_embedding_layers=[24],
+                             post_embedding_layers=[16, 12], activation_fn="relu"),
+                   item=_plain_item()),
+        rec_loss="bpr", optimizer="adamw", lr=2e-3, wd=1e-4, batch=20, n_neg=3, steps=2),
+    "plain_user_categorical_post": dict(
+        corpus=dict(shape=PLAIN_FIXTURE_SHAPE, split_type="random", seed=33, scale=1.0),
+        model=dict(shared_common_dim=12,
+                   user=dict(feature_name="country", embedding_dim=10, post_embedding_layers=[12],
+                             activation_fn="tanh"),
+                   item=_plain_item()),
+        rec_loss="bpr", optimizer="adam", lr=2e-3, wd=0.0, batch=20, n_neg=3, steps=2),
+    "plain_user_tag_post": dict(
+        corpus=dict(shape=PLAIN_FIXTURE_SHAPE, split_type="random", seed=35, scale=1.0),
+        model=dict(shared_common_dim=12,
+                   user=dict(feature_name="languages", embedding_dim=8, post_embedding_layers=[12]),
+                   item=_plain_item()),
+        rec_loss="bpr", optimizer="adamw", lr=2e-3, wd=1e-4, batch=20, n_neg=3, steps=2),
     # tanh everywhere (activation + activation-gradient epilogues other than ReLU), input dropout AND L2 normalisation on
     # both entities, a hidden layer inside a modality projection, an Embedding modality next to tags, Adam without decay
     "tanh_dropout_norm": dict(

@@ -201,8 +201,18 @@ class FeatureProj:
             v = v.reshape(len(rows), 1)
         return v
 
-    def forward(self, ent_idx, p):
+    def forward(self, ent_idx, p, emu=None):
+        """``emu`` (a plain, non single-branch entity on the B200 path): the table of ALL feature rows is computed once
+        with the kernels' rounding points and the batch gathers rows of it; the backward sums the row gradients per
+        feature row before they enter the chain (same result in exact arithmetic)."""
         rows = self.rows(ent_idx)
+        if emu is None or (self.type == "categorical" and self.post_ops is None):
+            return self._forward_rows(rows, p, None)
+        n = self.f.values.shape[0]
+        T, cache = self._forward_rows(np.arange(n), p, emu)
+        return T[rows], {"rows": rows, "table": cache, "n": n, "emu": emu}
+
+    def _forward_rows(self, rows, p, emu):
         x = self.raw(rows)
         cache = {"rows": rows}
         if self.type == "categorical":
@@ -220,9 +230,11 @@ class FeatureProj:
         else:
             y = x.astype(F64)
             if self.pre_ops is not None:
-                y, cache["pre"] = poly_forward(y, p, self.prefix + ".pre_embedding_layers.layers", self.pre_ops, True)
+                y, cache["pre"] = poly_forward(y, p, self.prefix + ".pre_embedding_layers.layers", self.pre_ops, True,
+                                               emu=emu)
         if self.post_ops is not None:
-            y, cache["post"] = poly_forward(y, p, self.prefix + ".post_embedding_layers.layers", self.post_ops, True)
+            y, cache["post"] = poly_forward(y, p, self.prefix + ".post_embedding_layers.layers", self.post_ops, True,
+                                            emu=emu)
         return y, cache
 
     # -- table mode (what the B200 path does): project ALL rows once, gather afterwards; the backward sums the
@@ -242,9 +254,14 @@ class FeatureProj:
                       exact_first=csr)
 
     def backward(self, dy, cache, p, grads):
+        emu = None
+        if "table" in cache:  # table mode: row gradients summed per feature row first
+            dT = np.zeros((cache["n"], dy.shape[-1]), F64)
+            np.add.at(dT, cache["rows"], dy)
+            dy, emu, cache = dT, cache["emu"], cache["table"]
         if self.post_ops is not None:
             dy = poly_backward(dy, p, self.prefix + ".post_embedding_layers.layers", self.post_ops, cache["post"],
-                               grads)
+                               grads, emu=emu)
         k = self.prefix + ".embedding_layer.weight"
         if self.type == "categorical":
             g = grads.get(k)
@@ -261,7 +278,8 @@ class FeatureProj:
             g[-1] = 0.  # padding row never receives gradient
             grads[k] = g
         elif self.pre_ops is not None:
-            poly_backward(dy, p, self.prefix + ".pre_embedding_layers.layers", self.pre_ops, cache["pre"], grads)
+            poly_backward(dy, p, self.prefix + ".pre_embedding_layers.layers", self.pre_ops, cache["pre"], grads,
+                          emu=emu)
 
 
 # ------------------------------------------------------------------------------------------------ losses
@@ -467,7 +485,7 @@ class OracleSBNet:
     def represent(self, name, idx, p, training, mods=None, mod_names=None, drop_keep=None, new_stats=None, emu=None):
         e = self.ent[name]
         if isinstance(e, FeatureProj):
-            y, cache = e.forward(idx.reshape(-1), p)
+            y, cache = e.forward(idx.reshape(-1), p, emu)
             self._plain_cache = getattr(self, "_plain_cache", {})
             self._plain_cache[name] = cache
             return y.reshape(idx.shape + (-1,)), 0.

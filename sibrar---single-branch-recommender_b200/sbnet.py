@@ -534,45 +534,107 @@ def _gather_plan(ent, n_keys: int, N: int, device) -> "ops.GatherPlan":
 
 class PlainEntity(_EntityBase):
     """Entity that is a single FeatureEmbedding (reference: ``FeatureEmbedding`` used directly as
-    ``{user,item}_embedding_module`` when the config parses as FeatureModuleConfig, sgd_alg.py:2043-2046)."""
+    ``{user,item}_embedding_module`` when the config parses as FeatureModuleConfig, sgd_alg.py:2043-2046; forward
+    sgd_alg.py:1373-1389): any feature type, optional ``pre_embedding_layers`` (vector-like features) and
+    ``post_embedding_layers``.
+
+    A categorical feature without post layers (the shipped configs: ``user_embedding``) is gathered directly.  Every
+    other form is a function of the FEATURE ROW alone, so each step computes the table of all rows once
+    (``T = post(embed | pre(x))``: the entity-table projection of the single-branch entities) and the batch gathers rows
+    of it; the table gradient flows back through the same chain."""
 
     def __init__(self, feature, config: FeatureModuleConfig, n_entities: int):
         nn.Module.__init__(self)
         fe = FeatureEmbedding.build_from_conf(config, feature)
-        if fe._feature_type != "categorical" or fe.post_embedding_layers is not None:
-            raise NotImplementedError("plain (non single-branch) entities are supported for categorical features "
-                                      "(ID embeddings) only on the B200 path")
-        # flatten: the reference's state_dict keys are '<entity>_embedding_module.embedding_layer.weight'
+        # flatten: the reference's state_dict keys are '<entity>_embedding_module.embedding_layer.weight',
+        # '<entity>_embedding_module.{pre,post}_embedding_layers.layers.linear_{i}.{weight,bias}'
         self.embedding_layer = fe.embedding_layer
-        self.pre_embedding_layers = None
-        self.post_embedding_layers = None
+        self.pre_embedding_layers = fe.pre_embedding_layers
+        self.post_embedding_layers = fe.post_embedding_layers
         self._feature = feature
+        self._feature_type = fe._feature_type
         self.output_dim = fe.output_dim
         self.k_train = self.k_eval = 1
         self.agg_max = 0
         self.reg_enabled = False
+        self.direct = self._feature_type == "categorical" and self.post_embedding_layers is None
         self._init_runtime(n_entities)
 
     def _materialize(self):
         dev = self._device()
         if self._dev_ready == dev:
             return
-        self.df = DeviceFeature("plain", self._feature, self.n_entities, dev)
+        self.df = DeviceFeature("plain", self._feature, self.n_entities, dev,
+                                dense_min_density=float(os.environ.get("SBR_DENSE_MIN_DENSITY", 0.004)))
         self._dev_ready = dev
         self._srcs = self._srcs_grad = None
+        if self.direct:
+            return
+        df = self.df
+        stages = []
+        if self.pre_embedding_layers is not None:
+            stages += build_stages(self.pre_embedding_layers)
+        if self.post_embedding_layers is not None:
+            stages += build_stages(self.post_embedding_layers)
+        vector = self._feature_type not in ("categorical", "tag")
+        self.chain = Chain(stages, feature=df if vector else None) if stages else None
+        self.emb_dim = self.embedding_layer.weight.shape[1] if self.embedding_layer is not None else None
+        self.table = torch.zeros((df.n_rows, self.output_dim), dtype=F32, device=dev)
+        self.table_grad = torch.zeros((df.n_rows, self.output_dim), dtype=F32, device=dev)
+        self._rows = torch.arange(df.n_rows, dtype=torch.int64, device=dev)
+        if not vector and self.chain is not None:
+            self._x32 = torch.zeros((df.n_rows, self.emb_dim), dtype=F32, device=dev)
+            self._x16 = torch.zeros((df.n_rows, ops.pad8(self.emb_dim)), dtype=BF16, device=dev)
+        self._emb_srcs = {}
 
+    # ---- descriptors
     def _src_blob(self, grads):
-        w = self.embedding_layer.weight
-        g = grads[id(w)] if grads is not None else None
-        self.n_keys = int(w.shape[0])
-        return ops.make_modality_srcs([dict(kind=SRC_CATEGORICAL, remap=self.df.remap, table=w.detach(), grad=g,
-                                            codes=self.df.codes, key_base=0)], w.device)
+        if self.direct:
+            w = self.embedding_layer.weight
+            g = grads[id(w)] if grads is not None else None
+            self.n_keys = int(w.shape[0])
+            return ops.make_modality_srcs([dict(kind=SRC_CATEGORICAL, remap=self.df.remap, table=w.detach(), grad=g,
+                                                codes=self.df.codes, key_base=0)], w.device)
+        self.n_keys = int(self.df.n_rows)
+        return ops.make_modality_srcs([dict(kind=SRC_TABLE, remap=self.df.remap, table=self.table, key_base=0,
+                                            grad=self.table_grad if grads is not None else None)], self._device())
+
+    def _embedding_src(self, grads):
+        """the categorical Embedding addressed by FEATURE ROW (identity remap): the input of the post layers"""
+        key = id(grads) if grads is not None else 0
+        hit = self._emb_srcs.get(key)
+        if hit is None or hit[0] is not grads:
+            w = self.embedding_layer.weight
+            blob = ops.make_modality_srcs([dict(kind=SRC_CATEGORICAL, remap=None, table=w.detach(), codes=self.df.codes,
+                                                grad=grads[id(w)] if grads is not None else None, key_base=0)],
+                                          w.device)
+            self._emb_srcs[key] = hit = (grads, blob)
+        return hit[1]
+
+    # ---- the per-step table of all feature rows
+    def _build_table(self, training):
+        rt, df = self._rt(), self.df
+        if self._feature_type == "tag":
+            w = self.embedding_layer.weight.detach()
+            bag = self._x32 if self.chain is not None else self.table
+            ops.tag_bag_fwd(df.codes, df.max_tags, df.pad_id, w, bag)
+            if self.chain is not None:
+                ops.cast_bf16(bag, self._x16)
+                self.chain.forward(self._x16, df.n_rows, training, rt.arena, keep_for_backward=training, out32=self.table)
+        elif self._feature_type == "categorical":
+            ops.row_gather_fwd(self._embedding_src(None), 1, self._rows, None, 1, self.emb_dim, False, 0.0, 0,
+                               rt.step_dev, None, out_bf16=self._x16, err_flag=rt.err_flag)
+            self.chain.forward(self._x16, df.n_rows, training, rt.arena, keep_for_backward=training, out32=self.table)
+        else:
+            self.chain.forward(df.x16, df.n_rows, training, rt.arena, keep_for_backward=training, out32=self.table)
 
     def embed(self, idx, training, mods=None, keep_mask=None, defer_final_bn=False):
         self._materialize()
         rt = self._rt()
         flat = idx.reshape(-1).contiguous()
         D = self.output_dim
+        if not self.direct:
+            self._build_table(training)
         out = torch.empty((flat.numel(), D), dtype=F32, device=flat.device)
         if self._srcs is None:
             self._srcs = self._src_blob(None)
@@ -580,6 +642,13 @@ class PlainEntity(_EntityBase):
                            err_flag=rt.err_flag)
         self._ctx = (flat,)
         return out
+
+    def build_plan(self, idx, mods, k, grads):
+        pass  # (single source: the plan is built in backward)
+
+    def chains(self):
+        self._materialize()
+        return [] if self.direct or self.chain is None else [self.chain]
 
     def backward(self, dE, grads, final_bn_sums=None):
         rt = self._rt()
@@ -589,6 +658,35 @@ class PlainEntity(_EntityBase):
         plan = _gather_plan(self, self.n_keys, flat.numel(), flat.device)
         plan.build(self._srcs_grad[1], 1, flat, None, 1)
         plan.backward(self._srcs_grad[1], 1, self.output_dim, False, 0.0, 0, rt.step_dev, None, dE)
+        if self.direct:
+            return
+        # table-level backward: G = d loss / d T  (the consumers clear it)
+        df = self.df
+        if self.chain is None:  # tag feature without post layers: T is the bag table itself
+            self._tag_backward(self.table_grad, grads)
+            return
+        vector = self._feature_type not in ("categorical", "tag")
+        dx = self.chain.backward(self.table_grad, grads, need_dx=not vector, arena=rt.arena, zero_dy=True)
+        if vector:
+            return
+        if self._feature_type == "tag":
+            self._tag_backward(dx, grads)
+        else:
+            p2 = _gather_plan(self, int(self.embedding_layer.weight.shape[0]), df.n_rows, dx.device)
+            src = self._embedding_src(grads)
+            p2.build(src, 1, self._rows, None, 1)
+            p2.backward(src, 1, self.emb_dim, False, 0.0, 0, rt.step_dev, None, dx)
+
+    def _tag_backward(self, bag_grad, grads):
+        df, w = self.df, self.embedding_layer.weight
+        C_ = int(w.shape[1])
+        if w.numel() <= ops.TAG_BAG_SMEM_FLOATS or C_ % 4 != 0:
+            ops.tag_bag_bwd(df.codes, df.max_tags, df.pad_id, bag_grad, grads[id(w)])
+        else:
+            seg_ptr, seg_rows, seg_vals, seg_tag = df.tag_segments
+            ops.spmm_csr(seg_ptr, seg_rows, seg_tag.numel(), bag_grad, C_, None, None, grads[id(w)], vals=seg_vals,
+                         row_map=seg_tag, atomic=True)
+            bag_grad.zero_()
 
 
 class SingleBranchNetEntity(_EntityBase):
@@ -1035,6 +1133,11 @@ class SingleBranchNetEntity(_EntityBase):
             thunks.append(bag_bwd)
         run_branches(thunks, aux)
 
+    def chains(self):
+        """every Linear chain of the entity (bf16 weight shadows are maintained per stage)"""
+        self._materialize()
+        return list(self.proj.values()) + [self.sb_chain]
+
     def get_and_reset_other_loss(self) -> Dict:
         loss = self.regularization_loss
         if loss is None:
@@ -1088,7 +1191,12 @@ class SingleBranchNet(nn.Module):
             return SingleBranchNetEntity(name, features, conf, D, interactions_available, n_entities)
         if conf.embedding_dim == -1:
             conf.embedding_dim = D
-        return PlainEntity(features[conf.feature_name], conf, n_entities)
+        ent = PlainEntity(features[conf.feature_name], conf, n_entities)
+        if ent.output_dim != D:
+            # (the reference fails later, inside the einsum of combine_user_item_representations, sgd_alg.py:2109-2114)
+            raise ValueError(f'plain "{name}" entity produces {ent.output_dim}-d representations, the model\'s '
+                             f'shared_common_dim is {D}')
+        return ent
 
     @staticmethod
     def build_from_conf(conf: dict, dataset):
@@ -1112,11 +1220,9 @@ class SingleBranchNet(nn.Module):
         """bring the bf16 weight shadows up to date with the fp32 masters (host-side version check, cast kernels only
         for weights that changed); CUDA-graph replays of the evaluation call this first"""
         for ent in (self.user_embedding_module, self.item_embedding_module):
-            if isinstance(ent, SingleBranchNetEntity):
-                ent._materialize()
-                for chain in list(ent.proj.values()) + [ent.sb_chain]:
-                    for st in chain.stages:
-                        st.refresh(False)
+            for chain in ent.chains():
+                for st in chain.stages:
+                    st.refresh(False)
 
     def check_errors(self):
         """raises KeyError like ``Feature.__getitem__`` (data/Feature.py:146) if a kernel met an entity index

@@ -48,11 +48,10 @@ class FusedTrainer:
         self.grads: Dict[int, torch.Tensor] = {}
         shadows = {}
         for ent in (self.user, self.item):
-            if isinstance(ent, SingleBranchNetEntity):
-                for chain in list(ent.proj.values()) + [ent.sb_chain]:
-                    for st in chain.stages:
-                        st.refresh(False)
-                        shadows[id(st.linear.weight)] = st.w16
+            for chain in ent.chains():
+                for st in chain.stages:
+                    st.refresh(False)
+                    shadows[id(st.linear.weight)] = st.w16
         # one flat fp32 gradient buffer, item-entity parameters first (they finish first in the backward pass, so a
         # data-parallel run can all-reduce that bucket while the user entity is still back-propagating)
         ordered = list(self.item.parameters()) + list(self.user.parameters())
