@@ -354,6 +354,14 @@ int sbr_score_loss_bn(const float* eu, const sbr_bn_inline_t* bn_u, const float*
 int sbr_infonce(const float* e, int64_t G, int64_t n, int D, float temperature, float weight, double* loss_acc,
                 float* de, int accumulate, float* lse_ws, void* stream);
 
+/* Bias terms of the matrix-factorisation siblings (SGDMatrixFactorization.combine_user_item_representations,
+ * algorithms/sgd_alg.py:175-195): logits[b, j] += user_bias[u[b]] + item_bias[i[b, j]] + global_bias[0] (each optional)
+ * and the matching gradient accumulation from d loss / d logits. */
+int sbr_logit_bias_fwd(float* logits, int64_t B, int n, const int64_t* u_idx, const int64_t* i_idx,
+                       const float* user_bias, const float* item_bias, const float* global_bias, void* stream);
+int sbr_logit_bias_bwd(const float* dlogits, int64_t B, int n, const int64_t* u_idx, const int64_t* i_idx,
+                       float* d_user_bias, float* d_item_bias, float* d_global_bias, void* stream);
+
 /* aggregation only (eval path): out[r, :] = mean | max over k of e[r, k, :] */
 int sbr_aggregate(const float* e, int64_t rows, int k, int D, int agg_max, float* out_f32, void* out_bf16,
                   int64_t ld_bf16, void* stream);
@@ -445,6 +453,20 @@ int sbr_sample_epoch_batch(const int32_t* coo_user, const int32_t* coo_item, int
                            int64_t offset, const int64_t* train_indptr, const int32_t* train_indices,
                            const int32_t* items_in_split, int64_t n_items_in_split, int64_t B, int n_neg, uint64_t seed,
                            const int64_t* step_dev, int64_t* out_u, int64_t* out_i, void* stream);
+
+/* both strategies of the reference behind one entry (data/dataset.py:361-375, data/sampling.py): `order` NULL = a random
+ * train interaction per slot (sbr_sample_batch), else slot b = interaction order[offset + b].
+ *   SBR_NEG_UNIFORM_RECBOLE  with replacement over items_in_split, re-drawn while a train positive (data/sampling.py:35-67)
+ *   SBR_NEG_UNIFORM          n_neg DISTINCT non-positive items of the split (negative_sample_uniform +
+ *                            neg_samp_vectorized_bsearch, data/sampling.py:7-32); item_pos int32 [n_items] = position of
+ *                            an item inside the sorted items_in_split (NULL when the split holds every item: identity).
+ * The caller checks n_choices - n_pos >= n_neg per user like the reference (ValueError). */
+enum { SBR_NEG_UNIFORM_RECBOLE = 0, SBR_NEG_UNIFORM = 1 };
+int sbr_sample_negatives(const int32_t* coo_user, const int32_t* coo_item, int64_t nnz, const int64_t* order,
+                         int64_t offset, const int64_t* train_indptr, const int32_t* train_indices,
+                         const int32_t* items_in_split, int64_t n_items_in_split, const int32_t* item_pos, int64_t B,
+                         int n_neg, int strategy, uint64_t seed, const int64_t* step_dev, int64_t* out_u,
+                         int64_t* out_i, void* stream);
 
 #ifdef __cplusplus
 }

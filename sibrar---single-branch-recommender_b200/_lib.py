@@ -112,6 +112,8 @@ _PROTOS = {
     "sbr_score_loss_bn": [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp,
                           c_vp, C.c_int, c_vp],
     "sbr_infonce": [c_vp, c_i64, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, C.c_int, c_vp, c_vp],
+    "sbr_logit_bias_fwd": [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "sbr_logit_bias_bwd": [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "sbr_aggregate": [c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp],
     "sbr_mlp2_colstats_rows": [c_i64],
     "sbr_mlp2_fwd": [C.POINTER(Mlp2Desc), c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp],
@@ -127,6 +129,8 @@ _PROTOS = {
     "sbr_topk_merge": [c_vp, C.c_int, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp],
     "sbr_metrics_at_k": [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_i64, c_vp],
     "sbr_sample_batch": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_u64, c_vp, c_vp, c_vp, c_vp],
+    "sbr_sample_negatives": [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, C.c_int, c_u64,
+                             c_vp, c_vp, c_vp, c_vp],
     "sbr_sample_epoch_batch": [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_u64, c_vp,
                                c_vp, c_vp, c_vp],
 }

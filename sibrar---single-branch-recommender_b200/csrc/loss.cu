@@ -641,6 +641,70 @@ extern "C" int sbr_score_loss_bn(const float* eu, const sbr_bn_inline_t* bn_u, c
   return SBR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ MF bias terms
+// logits[b, j] += user_bias[u[b]] + item_bias[i[b, j]] + global_bias   (SGDMatrixFactorization, sgd_alg.py:187-195;
+// any of the three may be absent) and its backward: d item_bias[i[b, j]] += dl[b, j], d user_bias[u[b]] += sum_j dl[b, j],
+// d global_bias += sum dl.
+namespace {
+__global__ void logit_bias_fwd_kernel(float* __restrict__ logits, int64_t B, int n, const int64_t* __restrict__ u_idx,
+                                      const int64_t* __restrict__ i_idx, const float* __restrict__ user_bias,
+                                      const float* __restrict__ item_bias, const float* __restrict__ global_bias) {
+  SBR_PDL_ENTRY();
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= B * n) return;
+  float v = logits[t];
+  if (user_bias) v += user_bias[u_idx[t / n]];
+  if (item_bias) v += item_bias[i_idx[t]];
+  if (global_bias) v += global_bias[0];
+  logits[t] = v;
+}
+__global__ void __launch_bounds__(256)
+logit_bias_bwd_kernel(const float* __restrict__ dlogits, int64_t B, int n, const int64_t* __restrict__ u_idx,
+                      const int64_t* __restrict__ i_idx, float* __restrict__ d_user_bias,
+                      float* __restrict__ d_item_bias, float* __restrict__ d_global_bias) {
+  SBR_PDL_ENTRY();
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float v = 0.f;
+  if (t < B * n) {
+    v = dlogits[t];
+    if (d_item_bias) atomicAdd(d_item_bias + i_idx[t], v);
+    if (d_user_bias) atomicAdd(d_user_bias + u_idx[t / n], v);
+  }
+  if (d_global_bias) {
+    __shared__ float red[8];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s_ = 0.f;
+      for (int w = 0; w < 8; ++w) s_ += red[w];
+      atomicAdd(d_global_bias, s_);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int sbr_logit_bias_fwd(float* logits, int64_t B, int n, const int64_t* u_idx, const int64_t* i_idx,
+                                  const float* user_bias, const float* item_bias, const float* global_bias,
+                                  void* stream) {
+  SBR_REQUIRE(logits && B > 0 && n >= 1 && (!user_bias || u_idx) && (!item_bias || i_idx),
+              "sbr_logit_bias_fwd: bad arguments");
+  SBR_CHECK_CUDA(sbr_launch(logit_bias_fwd_kernel, dim3(cdiv(B * n, 256)), dim3(256), (size_t)0, S(stream), logits, B, n,
+                            u_idx, i_idx, user_bias, item_bias, global_bias));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_logit_bias_bwd(const float* dlogits, int64_t B, int n, const int64_t* u_idx, const int64_t* i_idx,
+                                  float* d_user_bias, float* d_item_bias, float* d_global_bias, void* stream) {
+  SBR_REQUIRE(dlogits && B > 0 && n >= 1 && (!d_user_bias || u_idx) && (!d_item_bias || i_idx),
+              "sbr_logit_bias_bwd: bad arguments");
+  SBR_CHECK_CUDA(sbr_launch(logit_bias_bwd_kernel, dim3(cdiv(B * n, 256)), dim3(256), (size_t)0, S(stream), dlogits, B, n,
+                            u_idx, i_idx, d_user_bias, d_item_bias, d_global_bias));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
 extern "C" int sbr_aggregate(const float* e, int64_t rows, int k, int D, int agg_max, float* out_f32, void* out_bf16,
                              int64_t ld_bf16, void* stream) {
   SBR_REQUIRE(e && rows > 0 && k >= 1 && D > 0 && (out_f32 || out_bf16), "sbr_aggregate: bad arguments");

@@ -313,7 +313,8 @@ __global__ void sample_batch_kernel(const int32_t* __restrict__ coo_user, const 
                                     const int32_t* __restrict__ indices, const int32_t* __restrict__ items_in_split,
                                     int64_t n_items_in_split, int64_t B, int n_neg, uint64_t seed,
                                     const int64_t* __restrict__ step_dev, int64_t* __restrict__ out_u,
-                                    int64_t* __restrict__ out_i, const int64_t* __restrict__ order, int64_t offset) {
+                                    int64_t* __restrict__ out_i, const int64_t* __restrict__ order, int64_t offset,
+                                    int strategy, const int32_t* __restrict__ item_pos) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= B * (n_neg + 1)) return;
   const int64_t b = t / (n_neg + 1);
@@ -336,6 +337,37 @@ __global__ void sample_batch_kernel(const int32_t* __restrict__ coo_user, const 
     return;
   }
   const int64_t beg = indptr[u], end = indptr[u + 1];
+  if (strategy == 1) {
+    // 'uniform' (data/sampling.py:7-32): n_neg DISTINCT items of the split that are not train positives of the user --
+    // raw = n_neg distinct draws from [0, M), M = n_choices - n_pos (np.random.choice(..., replace=False)), shifted past
+    // the positives: neg = raw + #{j : pos_j - j <= raw} with pos_j the sorted positions of the positives among the
+    // choices (searchsorted(pos - arange, raw, 'right')).  Thread j == 1 draws the whole slot (Floyd's subset sampling:
+    // a uniformly random n_neg-subset; the order inside the row does not enter any loss).
+    if (j != 1) return;
+    const int64_t M = n_items_in_split - (end - beg);
+    int64_t chosen[64];
+    const int nn = n_neg < 64 ? n_neg : 64;
+    for (int i = 0; i < nn; ++i) {
+      const int64_t hi = M - nn + i;  // draw from [0, hi]
+      uint4 r = philox4x32(make_uint4((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)step, 0x40000000u + i), key);
+      int64_t v = (int64_t)__umul64hi(((uint64_t)r.x << 32) | r.y, (uint64_t)(hi + 1));
+      bool dup = false;
+      for (int q = 0; q < i; ++q) dup |= chosen[q] == v;
+      chosen[i] = dup ? hi : v;
+    }
+    for (int i = 0; i < nn; ++i) {
+      const int64_t raw = chosen[i];
+      int64_t lo = 0, hi = end - beg;  // first positive with (position - rank) > raw
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int64_t pj = (item_pos ? (int64_t)item_pos[indices[beg + mid]] : (int64_t)indices[beg + mid]) - mid;
+        if (pj <= raw) lo = mid + 1;
+        else hi = mid;
+      }
+      out_i[b * (n_neg + 1) + 1 + i] = items_in_split[raw + lo];
+    }
+    return;
+  }
   int32_t cand = 0;
   int64_t pos = 0;
   bool found = false;
@@ -599,7 +631,8 @@ extern "C" int sbr_sample_batch(const int32_t* coo_user, const int32_t* coo_item
   sample_batch_kernel<<<cdiv(B * (n_neg + 1), 256), 256, 0, S(stream)>>>(coo_user, coo_item, nnz, train_indptr,
                                                                         train_indices, items_in_split, n_items_in_split,
                                                                         B, n_neg, seed, step_dev, out_u, out_i,
-                                                                        (const int64_t*)nullptr, 0);
+                                                                        (const int64_t*)nullptr, 0, 0,
+                                                                        (const int32_t*)nullptr);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }
@@ -618,7 +651,28 @@ extern "C" int sbr_sample_epoch_batch(const int32_t* coo_user, const int32_t* co
   sample_batch_kernel<<<cdiv(B * (n_neg + 1), 256), 256, 0, S(stream)>>>(coo_user, coo_item, nnz, train_indptr,
                                                                         train_indices, items_in_split, n_items_in_split,
                                                                         B, n_neg, seed, step_dev, out_u, out_i, order,
-                                                                        offset);
+                                                                        offset, 0, (const int32_t*)nullptr);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_sample_negatives(const int32_t* coo_user, const int32_t* coo_item, int64_t nnz, const int64_t* order,
+                                    int64_t offset, const int64_t* train_indptr, const int32_t* train_indices,
+                                    const int32_t* items_in_split, int64_t n_items_in_split, const int32_t* item_pos,
+                                    int64_t B, int n_neg, int strategy, uint64_t seed, const int64_t* step_dev,
+                                    int64_t* out_u, int64_t* out_i, void* stream) {
+  SBR_REQUIRE(coo_user && coo_item && train_indptr && train_indices && items_in_split && out_u && out_i && step_dev,
+              "sbr_sample_negatives: null argument");
+  SBR_REQUIRE(nnz > 0 && n_items_in_split > 0 && B > 0 && n_neg >= 0 && offset >= 0 &&
+                  (order == nullptr || offset + B <= nnz),
+              "sbr_sample_negatives: bad sizes");
+  SBR_REQUIRE(strategy == SBR_NEG_UNIFORM_RECBOLE || strategy == SBR_NEG_UNIFORM,
+              "sbr_sample_negatives: Sampling strategy %d not yet supported.", strategy);
+  SBR_REQUIRE(strategy != SBR_NEG_UNIFORM || n_neg <= 64, "sbr_sample_negatives: 'uniform' draws at most 64 negatives");
+  sample_batch_kernel<<<cdiv(B * (n_neg + 1), 256), 256, 0, S(stream)>>>(coo_user, coo_item, nnz, train_indptr,
+                                                                        train_indices, items_in_split, n_items_in_split,
+                                                                        B, n_neg, seed, step_dev, out_u, out_i, order,
+                                                                        offset, strategy, item_pos);
   SBR_LAUNCH_CHECK();
   return SBR_OK;
 }

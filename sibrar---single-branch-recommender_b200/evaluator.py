@@ -85,8 +85,13 @@ class FullEvaluator:
         def device_part():
             was_training = model.training
             model.eval()
-            i_repr = model.get_item_representations(d["items"])
-            u_repr = model.get_user_representations(d["users"])
+            if hasattr(model, "eval_factors"):
+                # models whose score is not a plain dot product of the two representations (bias terms, slot means:
+                # sibling.py) hand over factor matrices whose dot product IS the score
+                u_repr, i_repr = model.eval_factors(d["users"], d["items"])
+            else:
+                i_repr = model.get_item_representations(d["items"])
+                u_repr = model.get_user_representations(d["users"])
             if was_training:
                 model.train()
             return self._device_eval(u_repr, i_repr, d["seen"], d["tgt"], ks, n_items)

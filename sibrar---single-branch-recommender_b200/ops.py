@@ -530,3 +530,29 @@ def sample_epoch_batch(coo_user, coo_item, order, offset, train_indptr, train_in
     call("sbr_sample_epoch_batch", ptr(coo_user), ptr(coo_item), coo_user.numel(), ptr(order), int(offset),
          ptr(train_indptr), ptr(train_indices), ptr(items_in_split), items_in_split.numel(), int(B), int(n_neg),
          int(seed), ptr(step_dev), ptr(out_u), ptr(out_i), stream_ptr())
+
+
+NEG_STRATEGY = {"uniform_recbole": 0, "uniform": 1}
+
+
+def sample_negatives(coo_user, coo_item, order, offset, train_indptr, train_indices, items_in_split, item_pos, B, n_neg,
+                     strategy, seed, step_dev, out_u, out_i):
+    """positives (a random train interaction per slot when ``order`` is None, else ``order[offset + b]``) + ``n_neg``
+    negatives per slot by ``strategy`` ('uniform_recbole' | 'uniform': data/sampling.py)"""
+    if strategy not in NEG_STRATEGY:
+        raise ValueError(f'Sampling strategy "{strategy}" not yet supported.')  # data/dataset.py:375
+    call("sbr_sample_negatives", ptr(coo_user), ptr(coo_item), coo_user.numel(), ptr(order), int(offset),
+         ptr(train_indptr), ptr(train_indices), ptr(items_in_split), items_in_split.numel(), ptr(item_pos), int(B),
+         int(n_neg), NEG_STRATEGY[strategy], int(seed), ptr(step_dev), ptr(out_u), ptr(out_i), stream_ptr())
+
+
+def logit_bias_fwd(logits, u_idx, i_idx, user_bias=None, item_bias=None, global_bias=None):
+    B, n = logits.shape
+    call("sbr_logit_bias_fwd", ptr(logits), int(B), int(n), ptr(u_idx), ptr(i_idx), ptr(user_bias), ptr(item_bias),
+         ptr(global_bias), stream_ptr())
+
+
+def logit_bias_bwd(dlogits, u_idx, i_idx, d_user_bias=None, d_item_bias=None, d_global_bias=None):
+    B, n = dlogits.shape
+    call("sbr_logit_bias_bwd", ptr(dlogits), int(B), int(n), ptr(u_idx), ptr(i_idx), ptr(d_user_bias), ptr(d_item_bias),
+         ptr(d_global_bias), stream_ptr())

@@ -543,9 +543,12 @@ class PlainEntity(_EntityBase):
     (``T = post(embed | pre(x))``: the entity-table projection of the single-branch entities) and the batch gathers rows
     of it; the table gradient flows back through the same chain."""
 
-    def __init__(self, feature, config: FeatureModuleConfig, n_entities: int):
+    def __init__(self, feature, config: FeatureModuleConfig, n_entities: int, fe: "FeatureEmbedding" = None):
+        """``fe``: an existing FeatureEmbedding (parameter holder) to run instead of building one from ``config`` -- the
+        sibling models keep it registered under the reference's own attribute names and run this engine unregistered"""
         nn.Module.__init__(self)
-        fe = FeatureEmbedding.build_from_conf(config, feature)
+        if fe is None:
+            fe = FeatureEmbedding.build_from_conf(config, feature)
         # flatten: the reference's state_dict keys are '<entity>_embedding_module.embedding_layer.weight',
         # '<entity>_embedding_module.{pre,post}_embedding_layers.layers.linear_{i}.{weight,bias}'
         self.embedding_layer = fe.embedding_layer
@@ -628,14 +631,16 @@ class PlainEntity(_EntityBase):
         else:
             self.chain.forward(df.x16, df.n_rows, training, rt.arena, keep_for_backward=training, out32=self.table)
 
-    def embed(self, idx, training, mods=None, keep_mask=None, defer_final_bn=False):
+    def embed(self, idx, training, mods=None, keep_mask=None, defer_final_bn=False, out=None):
+        """``out``: optional fp32 [numel, D] destination (may be a column block of a wider buffer: row pitch = stride)"""
         self._materialize()
         rt = self._rt()
         flat = idx.reshape(-1).contiguous()
         D = self.output_dim
         if not self.direct:
             self._build_table(training)
-        out = torch.empty((flat.numel(), D), dtype=F32, device=flat.device)
+        if out is None:
+            out = torch.empty((flat.numel(), D), dtype=F32, device=flat.device)
         if self._srcs is None:
             self._srcs = self._src_blob(None)
         ops.row_gather_fwd(self._srcs, 1, flat, None, 1, D, False, 0.0, 0, rt.step_dev, None, out_f32=out,

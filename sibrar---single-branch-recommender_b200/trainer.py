@@ -274,8 +274,11 @@ class DeviceBatchFeeder:
                  n_negative_samples: Optional[int] = None):
         import numpy as np
         strategy = getattr(dataset, "negative_sampling_strategy", "uniform_recbole")
-        if strategy not in {"uniform_recbole"}:
+        # 'uniform_recbole' is the dataloader-level sampler (data/dataloader.py:145-147); 'uniform' is the reference's
+        # dataset-level sampler (use_dataset_negative_sampler, data/dataset.py:361-375, data/sampling.py:7-32)
+        if strategy not in {"uniform_recbole", "uniform"}:
             raise ValueError(f"sampling strategy {strategy} not supported for dataloader sampling!")
+        self.strategy = strategy
         self.device = torch.device(device)
         self.batch_size, self.shuffle, self.seed = int(batch_size), shuffle, int(seed)
         self.n_neg = int(dataset.n_negative_samples if n_negative_samples is None else n_negative_samples)
@@ -289,6 +292,13 @@ class DeviceBatchFeeder:
         self.coo_u, self.coo_i = dev(coo.row, np.int32), dev(coo.col, np.int32)
         self.indptr, self.indices = dev(csr.indptr, np.int64), dev(csr.indices, np.int32)
         self.items = dev(dataset.items_in_split, np.int32)
+        self.item_pos = None
+        if strategy == "uniform":
+            if n_choices - int(row_len.max(initial=0)) < self.n_neg:
+                raise ValueError(f'Not enough values in the range to sample "{self.n_neg}" unique values.')
+            pos = np.full(csr.shape[1], -1, dtype=np.int32)
+            pos[np.asarray(dataset.items_in_split)] = np.arange(n_choices, dtype=np.int32)
+            self.item_pos = dev(pos, np.int32)
         self.nnz = int(coo.nnz)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.gen = torch.Generator(device=self.device).manual_seed(self.seed)
@@ -305,7 +315,7 @@ class DeviceBatchFeeder:
             u = torch.empty(b, dtype=torch.int64, device=self.device)
             i = torch.empty((b, 1 + self.n_neg), dtype=torch.int64, device=self.device)
             ops.tick(self.step_dev)
-            ops.sample_epoch_batch(self.coo_u, self.coo_i, order, off, self.indptr, self.indices, self.items, b,
-                                   self.n_neg, self.seed, self.step_dev, u, i)
+            ops.sample_negatives(self.coo_u, self.coo_i, order, off, self.indptr, self.indices, self.items, self.item_pos,
+                                 b, self.n_neg, self.strategy, self.seed, self.step_dev, u, i)
             yield u, i
         self.epochs_done += 1

@@ -589,6 +589,39 @@ def test_device_batch_feeder_epoch_semantics():
         DeviceBatchFeeder(train, batch_size=10, device=DEV)
 
 
+def test_uniform_sampler_matches_reference_semantics():
+    """'uniform' (data/sampling.py:7-32): n_neg DISTINCT items of the split, never a train positive, every eligible item
+    equally likely; on a tiny split the empirical distribution is compared with the reference's own sampler
+    (numpy statement of negative_sample_uniform) by a chi-square bound"""
+    from sibrar_b200.synthetic import SynCorpus
+    from sibrar_b200.trainer import DeviceBatchFeeder
+    train = SynCorpus("ml1m", "cold_start_item", seed=4, scale=0.02).dataset("train")
+    train.negative_sampling_strategy = "uniform"
+    n_neg = 7
+    feeder = DeviceBatchFeeder(train, batch_size=4096, device=DEV, seed=5, n_negative_samples=n_neg)
+    csr = train.user_sampling_matrix.tocsr()
+    in_split = np.zeros(train.n_items, dtype=bool)
+    in_split[train.items_in_split] = True
+    us, negs = [], []
+    for _ in range(6):
+        for u, i in feeder.epoch():
+            us.append(u.cpu().numpy())
+            negs.append(i.cpu().numpy()[:, 1:])
+    u, neg = np.concatenate(us), np.concatenate(negs)
+    assert in_split[neg].all()
+    assert not np.asarray(csr[np.repeat(u, n_neg), neg.reshape(-1)]).any()
+    srt = np.sort(neg, axis=1)
+    assert (srt[:, 1:] != srt[:, :-1]).all()  # distinct inside a slot (np.random.choice(replace=False))
+    # the busiest user: every eligible item about equally often
+    busy = np.bincount(u).argmax()
+    rows = neg[u == busy].reshape(-1)
+    eligible = np.setdiff1d(train.items_in_split, csr[busy].indices)
+    cnt = np.bincount(rows, minlength=train.n_items)[eligible]
+    expected = rows.size / len(eligible)
+    chi2 = ((cnt - expected) ** 2 / expected).sum()
+    assert chi2 < len(eligible) + 6 * np.sqrt(2 * len(eligible)), (chi2, len(eligible))
+
+
 @pytest.mark.parametrize("rows,d,C_", [(700, 900, 64), (333, 1500, 512), (260, 300, 20), (1000, 4000, 128)])
 def test_spmm_bf16_values_transpose_accumulate(rows, d, C_):
     """sbr_spmm_csr_bf16 (the CSR 'interactions' route): stored values are used (counts > 1), bf16 dense rows, fp32
