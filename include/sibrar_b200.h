@@ -277,6 +277,9 @@ int sbr_mlp2_fwd(const sbr_mlp2_desc_t* desc, int64_t n_rows, int C, float* z, i
 int sbr_mlp2_bwd(const sbr_mlp2_desc_t* desc, int64_t n_rows, int C, const float* dy, int64_t lddy, const float* z,
                  int64_t ldz, const sbr_mlp2_bn_t* bn, float* const* grad_w, float* const* grad_b, float* dx,
                  int64_t lddx, void* stream);
+/* profiling only: with SBR_MLP2_DEBUG bit 16 block 0 of sbr_mlp2_bwd stamps %globaltimer at its phase boundaries;
+ * returns the NUMBER of (time_ns << 8 | event id) words copied to host_out and clears the buffer */
+int sbr_mlp2_trace_read(unsigned long long* host_out, int max_events);
 
 /* nn.EmbeddingBag(mode="mean", padding_idx=pad_id) of EVERY feature row as a dense fp32 table [n_rows, C]
  * (reference FeatureEmbedding for tag features, algorithms/sgd_alg.py:1279-1396; codes int32 [n_rows, max_tags]):

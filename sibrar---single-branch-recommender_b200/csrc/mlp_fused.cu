@@ -81,6 +81,19 @@ struct BwdParams {
   int D;
 };
 
+// Profiling only (SBR_MLP2_DEBUG bit 16): block 0 stamps %globaltimer at the phase boundaries of its roles into a device
+// buffer read back by sbr_mlp2_trace_read (scripts/trace_mlp2.py prints the per-tile timeline).
+__device__ unsigned long long g_trace[4096];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_ev(int debug, int id) {
+  if ((debug & 16) && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned i = atomicAdd(&g_trace_n, 1u);
+    if (i < 4096) g_trace[i] = (t << 8) | (unsigned long long)(id & 0xff);
+  }
+}
+
 // Barrier wait of the latency-bound role hand-offs of these kernels: `mbarrier.test_wait` polling (no suspension).
 // `try_wait` may park the thread for a system-dependent time; the hand-off chain of one tile (producer -> MMA -> epilogue ->
 // MMA -> ...) pays that latency 6-8 times per tile with nothing else to overlap it.
@@ -592,13 +605,17 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
+      if (warp == 0) trace_ev(p.debug, 1);   // tile start
       resolve_rows(p.g, s_src, tile, s_ptr, threadIdx.x);
       producer_sync();
+      if (warp == 0) trace_ev(p.debug, 2);   // rows resolved
       wait_bar<POLL>(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1));
+      if (warp == 0) trace_ev(p.debug, 3);   // stage free
       gather_tile(p.g, s_ptr, tile, sX + s * TILE_BYTES, threadIdx.x, step, (p.debug & 2) != 0);
       fence_proxy_async_smem();
       producer_sync();
       if (threadIdx.x == 0) mbar_arrive(&x_full[s]);
+      if (warp == 0) trace_ev(p.debug, 4);   // X0 published
       // dz of the tile (16 rows per pass, 2 passes in flight): the global loads are issued before the wait for the
       // previous tile's wgrad MMAs (the last readers of DZ)
 #pragma unroll 1
@@ -630,7 +647,11 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             for (int j = 0; j < 8; ++j) gy[u][j] = zz[u][j] = 0.f;
           }
         }
-        if (pass == 0) wait_bar<POLL>(w_done, (uint32_t)((it & 1) ^ 1));
+        if (pass == 0) {
+          if (warp == 0) trace_ev(p.debug, 5);  // first dz loads issued
+          wait_bar<POLL>(w_done, (uint32_t)((it & 1) ^ 1));
+          if (warp == 0) trace_ev(p.debug, 6);  // DZ buffer free
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int row = (pass + u) * 16 + grp;
@@ -650,6 +671,7 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       fence_proxy_async_smem();
       producer_sync();
       if (threadIdx.x == 0) mbar_arrive(dz_full);
+      if (warp == 0) trace_ev(p.debug, 7);   // dz published
     }
     if (p.gb[L - 1] != nullptr && my_tiles > 0) {
 #pragma unroll
@@ -678,8 +700,11 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       const uint32_t ph = (uint32_t)(it & 1);
       const int s = it & 1;
       const uint32_t aXs = aX + s * TILE_BYTES;
+      trace_ev(p.debug, 16);
       wait_bar<POLL>(da_free, ph ^ 1);  // dX0 of the previous tile has been read out
+      trace_ev(p.debug, 17);
       wait_bar<POLL>(&x_full[s], (uint32_t)((it >> 1) & 1));
+      trace_ev(p.debug, 18);
       if (L == 2) {
         tc_fence_after();
         if (elect_one()) {
@@ -689,7 +714,9 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         }
         __syncwarp();
         wait_bar<POLL>(y1_full, ph);   // Y1 in shared memory, accumulator free again
+        trace_ev(p.debug, 19);
         wait_bar<POLL>(dz_full, ph);
+        trace_ev(p.debug, 20);
         tc_fence_after();
         if (elect_one()) {        // dz W1  (contraction over out_1)
 #pragma unroll
@@ -698,6 +725,7 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         }
         __syncwarp();
         wait_bar<POLL>(dy1_full, ph);
+        trace_ev(p.debug, 21);
         tc_fence_after();
         if (elect_one()) {        // dX0 = dY1 W0
 #pragma unroll
@@ -727,6 +755,7 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         umma_commit(w_done);
       }
       __syncwarp();
+      trace_ev(p.debug, 22);
     }
   } else {
     // ---------------------------------------------------------------- epilogue: thread = row of the tile
@@ -741,7 +770,9 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       const int64_t row = tile * TILE_ROWS + row_in_tile;
       const bool row_ok = row < p.g.N;
       if (L == 2) {
+        if (warp == 5) trace_ev(p.debug, 32);
         wait_bar<POLL>(da_full, da_ph);
+        if (warp == 5) trace_ev(p.debug, 33);
         da_ph ^= 1;
         tc_fence_after();
 #pragma unroll
@@ -765,8 +796,10 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(y1_full);
+        if (warp == 5) trace_ev(p.debug, 34);
         // dY1 = (dz W1) * act'(Y1)
         wait_bar<POLL>(da_full, da_ph);
+        if (warp == 5) trace_ev(p.debug, 35);
         da_ph ^= 1;
         tc_fence_after();
 #pragma unroll
@@ -803,9 +836,11 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(dy1_full);
+        if (warp == 5) trace_ev(p.debug, 36);
       }
       // dX0 -> global (fp32, consumed by the sorted-run gather backward)
       wait_bar<POLL>(da_full, da_ph);
+      if (warp == 5) trace_ev(p.debug, 37);
       da_ph ^= 1;
       tc_fence_after();
 #pragma unroll
@@ -831,6 +866,7 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(da_free);
+      if (warp == 5) trace_ev(p.debug, 38);
     }
     // ---- flush the gradient accumulators
     if (my_tiles > 0) {
@@ -938,6 +974,18 @@ int make_weight_maps(const sbr_mlp2_desc_t* d, CUtensorMap* tm) {
 }
 
 }  // namespace
+
+extern "C" int sbr_mlp2_trace_read(unsigned long long* host_out, int max_events) {
+  unsigned int n = 0;
+  SBR_CHECK_CUDA(cudaDeviceSynchronize());
+  SBR_CHECK_CUDA(cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n)));
+  if (n > 4096u) n = 4096u;
+  if ((int)n > max_events) n = (unsigned)max_events;
+  if (n > 0) SBR_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * n));
+  const unsigned int zero = 0;
+  SBR_CHECK_CUDA(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));
+  return (int)n;  // (number of events, not a status)
+}
 
 extern "C" int sbr_mlp2_colstats_rows(int64_t n_rows) { return (int)mlp2_grid(n_rows); }
 
