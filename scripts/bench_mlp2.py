@@ -1,6 +1,6 @@
 """Isolated timings of the fused gather + SB-MLP kernels (sbr_mlp2_fwd / sbr_mlp2_bwd) on the arguments the real ML-1M
 step passes (item side: 180 224 rows, user side: 16 384 rows), with the SBR_MLP2_DEBUG attribution switches
-(1 = no gradient flush, 2 = no gather loads, 4 = no dy / z loads, 8 = no output stores)."""
+(1 = no gradient flush, 2 = no gather loads, 4 = no dy / z loads, 8 = no output stores, 32 = no L2 prefetch)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -55,15 +55,12 @@ def timeit(key, label, reps=10):
     t = sorted(x.elapsed_time(y) * 1e3 for x, y in ev)
     print(f"{label:60s} median {t[len(t) // 2]:7.1f} us  min {t[0]:7.1f} us", flush=True)
 
-for poll in ("0", "1"):
-    os.environ["SBR_MLP2_POLL"] = poll
-    os.environ["SBR_MLP2_DEBUG"] = "0"
-    for key in sorted(calls):
-        timeit(key, f"{key[0]} rows={key[1]} poll={poll}")
-os.environ["SBR_MLP2_POLL"] = os.environ.get("POLL", "1")
+os.environ["SBR_MLP2_DEBUG"] = "0"
+for key in sorted(calls):
+    timeit(key, f"{key[0]} rows={key[1]}")
 only = os.environ.get("ONLY")  # e.g. "sbr_mlp2_bwd:180224:0" = one call, one debug mask (ncu captures)
 for key in sorted(calls):
-    for dbg in (0, 1, 2, 4, 8, 15):
+    for dbg in (0, 1, 2, 4, 8, 15, 32):
         if only and only != f"{key[0]}:{key[1]}:{dbg}":
             continue
         os.environ["SBR_MLP2_DEBUG"] = str(dbg)

@@ -18,6 +18,25 @@ __device__ __forceinline__ uint4 philox_group(int64_t r, int c8, uint64_t seed, 
   const uint32_t x = ((uint32_t)r * 0x9E3779B1u) ^ ((uint32_t)(r >> 32) * 0x7FEB352Du) ^ ((uint32_t)c8 * 0x846CA68Bu) ^ k0;
   return make_uint4(fmix32(x), fmix32(x + 0x68E31DA4u), fmix32(x + 0xB5297A4Du), fmix32(x + 0x1B56C4E9u));
 }
+// per-launch part of the counter (hoisted out of the row loops by the callers that care)
+__device__ __forceinline__ uint32_t philox_key0(uint64_t seed, uint64_t step) {
+  return fmix32((uint32_t)seed ^ ((uint32_t)step * 0x9E3779B1u)) ^ (uint32_t)(seed >> 32);
+}
+__device__ __forceinline__ uint4 philox_group_k(int64_t r, int c8, uint32_t k0) {
+  const uint32_t x = ((uint32_t)r * 0x9E3779B1u) ^ ((uint32_t)(r >> 32) * 0x7FEB352Du) ^ ((uint32_t)c8 * 0x846CA68Bu) ^ k0;
+  return make_uint4(fmix32(x), fmix32(x + 0x68E31DA4u), fmix32(x + 0xB5297A4Du), fmix32(x + 0x1B56C4E9u));
+}
+// x[j] = keep(j) ? x[j] * sc : 0 for the 8 columns of one dropout block: the same decisions as philox_lane16(blk, j) >=
+// thr, taken as two unsigned compares per word (low half: (w << 16) >= thr << 16, high half: w >= thr << 16) whose
+// predicates feed the selects directly.  thr_hi = drop_threshold(p) << 16 (p < 1).
+__device__ __forceinline__ void dropout8_hash(float (&x)[8], const uint4& blk, uint32_t thr_hi, float sc) {
+  const uint32_t w[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    x[2 * t] = ((w[t] << 16) >= thr_hi) ? x[2 * t] * sc : 0.f;
+    x[2 * t + 1] = (w[t] >= thr_hi) ? x[2 * t + 1] * sc : 0.f;
+  }
+}
 __device__ __forceinline__ uint32_t philox_lane16(const uint4& blk, int j) {  // j in [0, 8)
   const uint32_t w = (j >> 1) == 0 ? blk.x : ((j >> 1) == 1 ? blk.y : ((j >> 1) == 2 ? blk.z : blk.w));
   return (j & 1) ? (w >> 16) : (w & 0xFFFFu);

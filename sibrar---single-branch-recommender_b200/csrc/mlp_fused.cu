@@ -59,7 +59,7 @@ struct FwdParams {
 };
 struct BwdParams {
   int debug;  // SBR_MLP2_DEBUG bit mask (profiling only): 1 = no gradient flush, 2 = no gather loads, 4 = no dy / z loads,
-              // 8 = no dX0 stores
+              // 8 = no dX0 stores, 16 = wait-cycle profile of block 0, 32 = no L2 prefetch of dy / z
   GatherArgs g;
   LayerArgs l[2];
   int n_layers;
@@ -81,38 +81,39 @@ struct BwdParams {
   int D;
 };
 
-// Profiling only (SBR_MLP2_DEBUG bit 16): block 0 stamps %globaltimer at the phase boundaries of its roles into a device
-// buffer read back by sbr_mlp2_trace_read (scripts/trace_mlp2.py prints the per-tile timeline).
-__device__ unsigned long long g_trace[4096];
-__device__ unsigned int g_trace_n;
-__device__ __forceinline__ void trace_ev(int debug, int id) {
-  if ((debug & 16) && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    const unsigned i = atomicAdd(&g_trace_n, 1u);
-    if (i < 4096) g_trace[i] = (t << 8) | (unsigned long long)(id & 0xff);
+// Profiling only (SBR_MLP2_DEBUG bit 16 selects the PROF instantiation): warp 0 (producers), the MMA warp and the first
+// epilogue warp of block 0 accumulate the SM cycles they spend inside every barrier wait; slot 0 of a role is the length of
+// its tile loop.  Read back by sbr_mlp2_trace_read (scripts/trace_mlp2.py): loop - sum(waits) = the role's own work.
+constexpr int PROF_SLOTS = 16;  // 1-7: waits, 8-15: sections of the role's own work
+__device__ unsigned long long g_prof[4 * PROF_SLOTS];
+
+template <bool PROF>
+__device__ __forceinline__ void lap(uint32_t (&acc)[PROF_SLOTS], uint32_t& tmark, int work_slot) {
+  if (PROF) {
+    const uint32_t now = (uint32_t)clock();
+    acc[work_slot] += now - tmark;
+    tmark = now;
   }
 }
-
-// Barrier wait of the latency-bound role hand-offs of these kernels: `mbarrier.test_wait` polling (no suspension).
-// `try_wait` may park the thread for a system-dependent time; the hand-off chain of one tile (producer -> MMA -> epilogue ->
-// MMA -> ...) pays that latency 6-8 times per tile with nothing else to overlap it.
-template <bool POLL>
-__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
-  if (!POLL) {
+// barrier wait; PROF: the time since the last lap goes to `work_slot`, the wait itself to `wait_slot`
+template <bool PROF>
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, uint32_t (&acc)[PROF_SLOTS], uint32_t& tmark,
+                                         int wait_slot, int work_slot) {
+  if (PROF) {
+    lap<PROF>(acc, tmark, work_slot);
     mbar_wait(bar, parity);
-    return;
+    lap<PROF>(acc, tmark, wait_slot);
+  } else {
+    mbar_wait(bar, parity);
   }
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
+}
+template <bool PROF>
+__device__ __forceinline__ void prof_flush(int role, uint32_t t_loop, const uint32_t (&acc)[PROF_SLOTS]) {
+  if (PROF && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    g_prof[role * PROF_SLOTS] = (uint32_t)clock() - t_loop;
+#pragma unroll
+    for (int i = 1; i < PROF_SLOTS; ++i) g_prof[role * PROF_SLOTS + i] = acc[i];
+  }
 }
 
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {  // byte offset of 16-byte chunk `chunk` of line `row`
@@ -140,6 +141,21 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// 16 values per lane: on return lanes 2m and 2m+1 hold the sum over the warp's lanes of v[m]
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      float send = upper ? v[i] : v[i + n];
+      float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 // activation / activation gradient with the (warp-uniform) switch hoisted out of the element loop
@@ -287,7 +303,7 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, int k16, uint32_t lbo
 // ================================================================================================ forward
 constexpr int FWD_SMEM = 2 * W_BYTES + 3 * TILE_BYTES + 3072 + 1024;
 
-template <int L, bool POLL>
+template <int L, bool PROF>
 __global__ void __launch_bounds__(N_THREADS, 2)
 mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, FwdParams p) {
   SBR_PDL_LAUNCH();
@@ -339,6 +355,9 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     s_bias[l * 64 + c] = (l < L && p.l[l].bias != nullptr && c < p.l[l].out_f) ? p.l[l].bias[c] : 0.f;
   }
   __syncthreads();
+  uint32_t wacc[PROF_SLOTS] = {};  // (PROF only; dead otherwise)
+  const uint32_t t_loop = (uint32_t)clock();
+  uint32_t tmark = t_loop;
 
   if (warp < N_PRODUCER_WARPS) {
     // ---------------------------------------------------------------- producers: gather + normalise + dropout -> X0
@@ -348,11 +367,12 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       const int s = it & 1;
       resolve_rows(p.g, s_src, tile, s_ptr, threadIdx.x);
       producer_sync();
-      wait_bar<POLL>(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1));
+      wait_bar<PROF>(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1), wacc, tmark, 1, 8);
       gather_tile(p.g, s_ptr, tile, sX + s * TILE_BYTES, threadIdx.x, step, (p.debug & 2) != 0);
       fence_proxy_async_smem();
       producer_sync();  // (also: s_ptr may be overwritten by the next tile)
       if (lane == 0) mbar_arrive(&x_full[s]);
+      lap<PROF>(wacc, tmark, 9);
     }
   } else if (warp == MMA_WARP) {
     // ---------------------------------------------------------------- MMA issuer (converged warp, elected issue)
@@ -362,14 +382,14 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       if (L == 2) tma_load_2d(sW1, &tmW1, w_full, 0, 0);
     }
     __syncwarp();
-    wait_bar<POLL>(w_full, 0);
+    wait_bar<PROF>(w_full, 0, wacc, tmark, 7, 15);
     const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
     const uint32_t aX = smem_u32(sX), aA1 = smem_u32(sA1), aW0 = smem_u32(sW0), aW1 = smem_u32(sW1);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
-      wait_bar<POLL>(&x_full[s], (uint32_t)((it >> 1) & 1));
-      if (L == 1) wait_bar<POLL>(df_empty, (uint32_t)((it & 1) ^ 1));
+      wait_bar<PROF>(&x_full[s], (uint32_t)((it >> 1) & 1), wacc, tmark, 1, 8);
+      if (L == 1) wait_bar<PROF>(df_empty, (uint32_t)((it & 1) ^ 1), wacc, tmark, 2, 8);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -380,8 +400,8 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       }
       __syncwarp();
       if (L == 2) {
-        wait_bar<POLL>(a1_full, (uint32_t)(it & 1));
-        wait_bar<POLL>(df_empty, (uint32_t)((it & 1) ^ 1));
+        wait_bar<PROF>(a1_full, (uint32_t)(it & 1), wacc, tmark, 3, 8);
+        wait_bar<PROF>(df_empty, (uint32_t)((it & 1) ^ 1), wacc, tmark, 2, 8);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -403,7 +423,7 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       const int64_t row = tile * TILE_ROWS + row_in_tile;
       const bool row_ok = row < p.g.N;
       if (L == 2) {
-        wait_bar<POLL>(dh_full, (uint32_t)(it & 1));
+        wait_bar<PROF>(dh_full, (uint32_t)(it & 1), wacc, tmark, 1, 8);
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -427,7 +447,7 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(a1_full);
       }
-      wait_bar<POLL>(df_full, (uint32_t)(it & 1));
+      wait_bar<PROF>(df_full, (uint32_t)(it & 1), wacc, tmark, 2, 9);
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -465,6 +485,7 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(df_empty);
+      lap<PROF>(wacc, tmark, 10);
     }
     if (p.colstats != nullptr) {
       // one row of partial sums per CTA: the four lane quarters are added in a fixed order (deterministic statistics;
@@ -490,6 +511,8 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     }
   }
 
+  if (PROF && (warp == 0 || warp == MMA_WARP || warp == FIRST_EPI_WARP))
+    prof_flush<PROF>(warp == 0 ? 0 : (warp == MMA_WARP ? 1 : 2), t_loop, wacc);
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
@@ -499,13 +522,43 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
 }
 
 // ================================================================================================ backward
-// shared memory: W0 | W1 | DZ | DY1 | Y1 | X0[0] | X0[1].  Stacked operands of the wgrad MMA: A = [DZ ; DY1] (second
-// 64-element block one tile further), B = [Y1 | X0[s]] (second block one or two tiles further: the descriptor's leading
-// byte offset selects the X0 stage), L == 1: B = X0[s] alone.
-constexpr int BWD_SMEM = 2 * W_BYTES + 5 * TILE_BYTES + 3072 + 1024;
+// Warp roles (13 warps, two CTAs per SM): 0-3 epilogue (warp = TMEM lane quarter, thread = row of the tile), 4-7 X0
+// gather, 8-11 dz producers (+ the fp32 bias-gradient sums), 12 MMA issuer.  Every role runs at one warp per scheduler, so
+// the tile time is the longest role, not their sum: the gather of tile t+1, the dz of tile t+1 (its buffer is released
+// by the commit behind  dz W1  +  the layer-1 weight gradient, both issued as soon as dz and Y1 exist) and X0(t+1) W0^T
+// (own accumulator) all run while the epilogue warps walk Y1 -> dY1 -> dX0 of tile t.
+// shared memory: W0 | W1 | DZ | DY1 | Y1 | X0[0] | X0[1].  The weight-gradient MMAs take A = [DZ ; DY1] stacked on M (second
+// 64-row block one tile further) against B = Y1 (-> accumulator columns 0-63, lanes 0-63 = layer 1) and B = X0[s]
+// (-> columns 64-127, lanes 64-127 = layer 0); the other two quadrants hold cross terms nobody reads.
+constexpr int BWD_THREADS = 13 * 32;
+constexpr int BW_PG0 = 4, BW_PZ0 = 8, BW_MMA = 12;
+constexpr int BWD_MISC = 4096;
+constexpr int BWD_SMEM = 2 * W_BYTES + 5 * TILE_BYTES + BWD_MISC + 1024;
 
-template <int L, bool POLL>
-__global__ void __launch_bounds__(N_THREADS, 2)
+// rows of a tile owned by gather / dz warp w (4 lane groups of 8 lanes, 8 passes): 16 i + 4 w + j  (i < 8, j < 4)
+__device__ __forceinline__ int warp_row(int w, int lane) { return 16 * (lane >> 2) + 4 * w + (lane & 3); }
+
+template <bool GENERIC, int NE>
+__device__ __forceinline__ void act_t(int act, float (&v)[NE]) {
+  if (GENERIC) {
+    act_n<NE>(act, v);
+  } else if (act == SBR_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NE; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+}
+template <bool GENERIC, int NE>
+__device__ __forceinline__ void actgrad_t(int act, float (&v)[NE], const float (&y)[NE]) {
+  if (GENERIC) {
+    actgrad_n<NE>(act, v, y);
+  } else if (act == SBR_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NE; ++j) v[j] = y[j] > 0.f ? v[j] : 0.f;
+  }
+}
+
+template <int L, bool PROF, bool GENERIC>
+__global__ void __launch_bounds__(512, 2)  // 13 warps are allocated as 16: 64 registers per thread for two CTAs per SM
 mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, BwdParams p) {
   SBR_PDL_LAUNCH();
   extern __shared__ uint8_t smem_raw[];
@@ -517,163 +570,297 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
   uint8_t* sY1 = sDY1 + TILE_BYTES;
   uint8_t* sX = sY1 + TILE_BYTES;  // 2 stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * TILE_BYTES);
-  uint64_t* w_full = bars;        // weights landed
-  uint64_t* x_full = bars + 1;    // [2] X0 gathered
-  uint64_t* x_empty = bars + 3;   // [2] every MMA that reads the stage has completed
-  uint64_t* dz_full = bars + 5;   // dz written
-  uint64_t* da_full = bars + 6;   // the 64-column accumulator holds a result (used 1 or 3 times per tile)
-  uint64_t* y1_full = bars + 7;   // Y1 written (and the accumulator read)
-  uint64_t* dy1_full = bars + 8;  // dY1 written (and the accumulator read)
-  uint64_t* da_free = bars + 9;   // dX0 read out of the accumulator
-  uint64_t* w_done = bars + 10;   // the wgrad MMAs of the tile have read DZ / DY1 / Y1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-  sbr_modality_src_t* s_src = reinterpret_cast<sbr_modality_src_t*>(bars + 12);
-  const float** s_ptr = reinterpret_cast<const float**>(s_src + MAX_SRC);
-  float* s_bias = reinterpret_cast<float*>(s_ptr + TILE_ROWS);  // [2][64], zero beyond the widths
+  uint64_t* w_full = bars;         // weights landed
+  uint64_t* x_full = bars + 1;     // [2] X0 gathered (4 gather warps)
+  uint64_t* x_empty = bars + 3;    // [2] the last MMA reading the stage has completed
+  uint64_t* y_full = bars + 5;     // X0 W0^T in its accumulator
+  uint64_t* y1_full = bars + 6;    // Y1 written (4 epilogue warps)
+  uint64_t* dz_full = bars + 7;    // dz written (4 dz warps)
+  uint64_t* dz_free = bars + 8;    // dz W1 and the layer-1 weight gradient have completed
+  uint64_t* a_full = bars + 9;     // the shared accumulator holds dz W1 / dY1 W0 (two completions per tile, L == 2)
+  uint64_t* dy1_full = bars + 10;  // dY1 written (4 epilogue warps)
+  uint64_t* dy1_free = bars + 11;  // the dz warps have added dY1 into the layer-0 bias gradient (4 warps)
+  uint64_t* da_free = bars + 12;   // L == 1: dX0 read out of the accumulator (4 epilogue warps)
+  uint64_t* w_done = bars + 13;    // every MMA of this CTA has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  sbr_modality_src_t* s_src = reinterpret_cast<sbr_modality_src_t*>(bars + 16);
+  const float** s_ptr = reinterpret_cast<const float**>(s_src + MAX_SRC);  // [128] source row of every tile row
+  float* s_bias = reinterpret_cast<float*>(s_ptr + TILE_ROWS);                 // [2][64], zero beyond the widths
+  float* s_coef = s_bias + 128;                                                // [4][64] BatchNorm-backward coefficients
+  static_assert(16 * 8 + MAX_SRC * sizeof(sbr_modality_src_t) + TILE_ROWS * 8 + 128 * 4 + 256 * 4 <= BWD_MISC, "misc");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t num_tiles = (p.g.N + TILE_ROWS - 1) / TILE_ROWS;
-  if (warp == MMA_WARP && lane == 0) {
+  if (warp == BW_MMA && lane == 0) {
     tma_prefetch_desc(&tmW0);
     if (L == 2) tma_prefetch_desc(&tmW1);
     mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&x_full[s], 1);
+      mbar_init(&x_full[s], 4);
       mbar_init(&x_empty[s], 1);
     }
-    mbar_init(dz_full, 1);
-    mbar_init(da_full, 1);
+    mbar_init(y_full, 1);
     mbar_init(y1_full, 4);
+    mbar_init(dz_full, 4);
+    mbar_init(dz_free, 1);
+    mbar_init(a_full, 1);
     mbar_init(dy1_full, 4);
+    mbar_init(dy1_free, 4);
     mbar_init(da_free, 4);
     mbar_init(w_done, 1);
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 256);
+  if (warp == BW_MMA) tmem_alloc(tmem_slot, 256);
   if (L == 1)  // a defined second block of the stacked A operand (its accumulator lanes are never read)
-    for (int i = threadIdx.x; i < TILE_BYTES / 16; i += N_THREADS)
+    for (int i = threadIdx.x; i < TILE_BYTES / 16; i += BWD_THREADS)
       reinterpret_cast<uint4*>(sDY1)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_a = tmem_base, tmem_w = tmem_base + 64;
+  const uint32_t tmem_a = tmem_base, tmem_y = tmem_base + 64, tmem_w = tmem_base + 128;
   SBR_PDL_WAIT();
   if (threadIdx.x < p.g.n_mods) s_src[threadIdx.x] = p.g.srcs[threadIdx.x];
   if (threadIdx.x >= 128 && threadIdx.x < 256) {
     const int l = (threadIdx.x - 128) >> 6, c = threadIdx.x & 63;
     s_bias[l * 64 + c] = (l < L && p.l[l].bias != nullptr && c < p.l[l].out_f) ? p.l[l].bias[c] : 0.f;
   }
-  __syncthreads();
-  const int my_tiles = blockIdx.x < num_tiles ? (int)((num_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
-
-  if (warp < N_PRODUCER_WARPS) {
-    // ---------------------------------------------------------------- producers: X0 (re-gathered, one tile ahead) and dz
-    const uint64_t step = p.g.step_dev ? (uint64_t)*p.g.step_dev : 0;
-    const int grp = threadIdx.x >> 3, li = threadIdx.x & 7;
-    const int c0 = 8 * li;
-    const int act_last = p.l[L - 1].act;
-    // per-column coefficients of this lane's 8 columns: dz = A dy + B (z - mean) + C0  (BatchNorm backward), A = 1 else
-    float cA[8], cB[8], cM[8], c0v[8], bsum[8];
-    const bool bn = p.mean_invstd != nullptr;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      cA[j] = 1.f; cB[j] = 0.f; cM[j] = 0.f; c0v[j] = 0.f; bsum[j] = 0.f;
-      if (bn && c < p.D) {
-        float s0 = 0.f, s1 = 0.f;
-        for (int r = 0; r < p.n_replicas; ++r) {
-          s0 += p.sums[(size_t)r * 2 * p.D + c];
-          s1 += p.sums[(size_t)r * 2 * p.D + p.D + c];
-        }
-        const float inv_n = 1.f / (float)p.g.N;
-        const float istd = p.mean_invstd[p.D + c];
-        const float gi = p.gamma[c] * istd;
-        cM[j] = p.mean_invstd[c];
-        cA[j] = gi;
-        cB[j] = -gi * istd * (s1 * inv_n);
-        c0v[j] = -gi * (s0 * inv_n);
-        if (blockIdx.x == 0 && grp == 0) {  // d gamma / d beta come with the sums
-          if (p.dbeta) p.dbeta[c] += s0;
-          if (p.dgamma) p.dgamma[c] += s1;
-        }
+  if (threadIdx.x >= 256 && threadIdx.x < 320) {
+    // per-column coefficients  dz = A dy + B (z - mean) + C0  (BatchNorm backward; A = 1, B = C0 = 0 without one)
+    const int c = threadIdx.x - 256;
+    float cA = 1.f, cB = 0.f, cM = 0.f, c0v = 0.f;
+    if (p.mean_invstd != nullptr && c < p.D) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int r = 0; r < p.n_replicas; ++r) {
+        s0 += p.sums[(size_t)r * 2 * p.D + c];
+        s1 += p.sums[(size_t)r * 2 * p.D + p.D + c];
+      }
+      const float inv_n = 1.f / (float)p.g.N;
+      const float istd = p.mean_invstd[p.D + c];
+      const float gi = p.gamma[c] * istd;
+      cM = p.mean_invstd[c];
+      cA = gi;
+      cB = -gi * istd * (s1 * inv_n);
+      c0v = -gi * (s0 * inv_n);
+      if (blockIdx.x == 0) {  // d gamma / d beta come with the sums
+        if (p.dbeta) p.dbeta[c] += s0;
+        if (p.dgamma) p.dgamma[c] += s1;
       }
     }
-    const bool vec_ok = (p.lddy & 3) == 0 && (p.ldz & 3) == 0 && (p.D & 7) == 0;
-    const bool no_dz_loads = (p.debug & 4) != 0;
+    s_coef[c] = cA; s_coef[64 + c] = cB; s_coef[128 + c] = cM; s_coef[192 + c] = c0v;
+  }
+  __syncthreads();
+  const int my_tiles = blockIdx.x < num_tiles ? (int)((num_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  uint32_t wacc[PROF_SLOTS] = {};  // (PROF only; dead otherwise)
+  const uint32_t t_loop = (uint32_t)clock();
+  uint32_t tmark = t_loop;
+
+  if (warp >= BW_PG0 && warp < BW_PZ0) {
+    // ---------------------------------------------------------------- X0 gather (one tile ahead of the MMAs)
+    // A warp resolves the 32 rows it gathers itself (no CTA-level barrier); the dependent index loads of tile t+1
+    // (entity index -> feature row -> category) are issued between the gather passes of tile t.
+    const uint64_t step = p.g.step_dev ? (uint64_t)*p.g.step_dev : 0;
+    const int w = warp - BW_PG0;
+    const int grp = 4 * w + (lane >> 3), li = lane & 7;
+    const int my_row = warp_row(w, lane);
+    const float sc = p.g.p_drop > 0.f ? 1.f / (1.f - p.g.p_drop) : 1.f;
+    const bool vec_ok = (p.g.C & 3) == 0;
+    const bool no_loads = (p.debug & 2) != 0;
+    const bool hash_drop = p.g.p_drop > 0.f && p.g.keep_mask == nullptr;
+    const uint32_t key0 = philox_key0(p.g.seed, step);
+    const uint32_t thr_hi = min(drop_threshold(p.g.p_drop), 0xFFFFu) << 16;
+    const uint32_t base_off = tile_off(grp, li);  // this thread's chunk of row `grp`; row 16 i + grp is 2048 i further
+    // resolver state of the NEXT tile's row `my_row`
+    int64_t r_e = 0, r_feat = -1, r_src = 0;
+    int r_m = 0;
+    bool r_ok = false;
+    auto stage1 = [&](int64_t tile) {
+      const int64_t gr = tile * TILE_ROWS + my_row;
+      r_ok = tile < num_tiles && gr < p.g.N;
+      if (r_ok) {
+        r_m = p.g.mods ? min((int)__ldg(p.g.mods + gr), p.g.n_mods - 1) : 0;
+        r_e = __ldg(p.g.idx + (p.g.k == 1 ? gr : gr / p.g.k));
+      }
+    };
+    auto stage2 = [&]() {
+      if (r_ok) {
+        const sbr_modality_src_t& s = s_src[r_m];
+        r_feat = s.remap ? (int64_t)__ldg(s.remap + r_e) : r_e;
+      }
+    };
+    auto stage3 = [&]() {
+      if (r_ok && r_feat >= 0)
+        r_src = (s_src[r_m].kind == SBR_SRC_CATEGORICAL) ? (int64_t)__ldg(s_src[r_m].codes + r_feat) : r_feat;
+    };
+    auto publish = [&]() {  // -> s_ptr[my_row]
+      const float* ptr = nullptr;
+      if (r_ok) {
+        if (r_feat < 0) {
+          if (p.g.err_flag) atomicExch(p.g.err_flag, 1);
+        } else {
+          ptr = s_src[r_m].table + r_src * p.g.C;
+        }
+      }
+      s_ptr[my_row] = ptr;
+    };
+    stage1(blockIdx.x);
+    stage2();
+    stage3();
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
-      if (warp == 0) trace_ev(p.debug, 1);   // tile start
-      resolve_rows(p.g, s_src, tile, s_ptr, threadIdx.x);
-      producer_sync();
-      if (warp == 0) trace_ev(p.debug, 2);   // rows resolved
-      wait_bar<POLL>(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1));
-      if (warp == 0) trace_ev(p.debug, 3);   // stage free
-      gather_tile(p.g, s_ptr, tile, sX + s * TILE_BYTES, threadIdx.x, step, (p.debug & 2) != 0);
-      fence_proxy_async_smem();
-      producer_sync();
-      if (threadIdx.x == 0) mbar_arrive(&x_full[s]);
-      if (warp == 0) trace_ev(p.debug, 4);   // X0 published
-      // dz of the tile (16 rows per pass, 2 passes in flight): the global loads are issued before the wait for the
-      // previous tile's wgrad MMAs (the last readers of DZ)
+      uint8_t* dst = sX + s * TILE_BYTES;
+      publish();
+      __syncwarp();
+      stage1(tile + gridDim.x);
+      wait_bar<PROF>(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1), wacc, tmark, 1, 8);
 #pragma unroll 1
-      for (int pass = 0; pass < 8; pass += 2) {
-        float gy[2][8], zz[2][8];
+      for (int pass = 0; pass < 8; pass += 4) {
+        float x[4][8];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int row = (pass + u) * 16 + grp;
-          const int64_t gr = tile * TILE_ROWS + row;
-          if (gr < p.g.N && c0 < p.D && !no_dz_loads) {
-            const float* dyp = p.dy + gr * p.lddy + c0;
-            const float* zp = p.z + gr * p.ldz + c0;
-            if (vec_ok) {
-              const float4 a = __ldcs(reinterpret_cast<const float4*>(dyp)), b = __ldcs(reinterpret_cast<const float4*>(dyp + 4));
-              const float4 c = __ldcs(reinterpret_cast<const float4*>(zp)), d = __ldcs(reinterpret_cast<const float4*>(zp + 4));
-              gy[u][0] = a.x; gy[u][1] = a.y; gy[u][2] = a.z; gy[u][3] = a.w;
-              gy[u][4] = b.x; gy[u][5] = b.y; gy[u][6] = b.z; gy[u][7] = b.w;
-              zz[u][0] = c.x; zz[u][1] = c.y; zz[u][2] = c.z; zz[u][3] = c.w;
-              zz[u][4] = d.x; zz[u][5] = d.y; zz[u][6] = d.z; zz[u][7] = d.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                gy[u][j] = c0 + j < p.D ? dyp[j] : 0.f;
-                zz[u][j] = c0 + j < p.D ? zp[j] : 0.f;
-              }
-            }
+        for (int u = 0; u < 4; ++u) {
+          const float* ptr = s_ptr[(pass + u) * 16 + grp];
+          if (ptr != nullptr && !no_loads) {
+            load8(ptr, 8 * li, p.g.C, vec_ok, x[u]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gy[u][j] = zz[u][j] = 0.f;
+            for (int j = 0; j < 8; ++j) x[u][j] = 0.f;
           }
         }
-        if (pass == 0) {
-          if (warp == 0) trace_ev(p.debug, 5);  // first dz loads issued
-          wait_bar<POLL>(w_done, (uint32_t)((it & 1) ^ 1));
-          if (warp == 0) trace_ev(p.debug, 6);  // DZ buffer free
-        }
+        if (pass == 0) stage2(); else stage3();
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
           const int row = (pass + u) * 16 + grp;
-          const bool ok = tile * TILE_ROWS + row < p.g.N;
-          float v[8];
+          const int64_t gr = tile * TILE_ROWS + row;
+          if (p.g.normalize) {
+            float ss = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = cA[j] * gy[u][j] + cB[j] * (zz[u][j] - cM[j]) + c0v[j];  // (A = 1, B = C0 = 0 without BN)
-          actgrad_n<8>(act_last, v, zz[u]);
+            for (int j = 0; j < 8; ++j) ss += x[u][j] * x[u][j];
+            ss = group_sum<LPR>(ss);
+            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[j] = (ok && c0 + j < p.D) ? v[j] : 0.f;
-            bsum[j] += v[j];  // bias gradient of the last layer: fp32 column sums BEFORE the bf16 rounding
+            for (int j = 0; j < 8; ++j) x[u][j] *= inv;
           }
-          *reinterpret_cast<uint4*>(sDZ + tile_off(row, li)) = pack8(v);
+          // (rows beyond N were loaded as zeros)
+          if (hash_drop) {
+            dropout8_hash(x[u], philox_group_k(gr, li, key0), thr_hi, sc);
+          } else if (p.g.p_drop > 0.f) {
+            const uint32_t km = gr < p.g.N ? keep8(p.g.keep_mask, gr, p.g.C, 8 * li, p.g.p_drop, p.g.seed, step) : 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[u][j] = ((km >> j) & 1u) ? x[u][j] * sc : 0.f;
+          }
+          *reinterpret_cast<uint4*>(dst + base_off + (pass + u) * 2048) = pack8(x[u]);
         }
       }
       fence_proxy_async_smem();
-      producer_sync();
-      if (threadIdx.x == 0) mbar_arrive(dz_full);
-      if (warp == 0) trace_ev(p.debug, 7);   // dz published
+      __syncwarp();  // (also: every lane has read s_ptr before the next publish)
+      if (lane == 0) mbar_arrive(&x_full[s]);
+      lap<PROF>(wacc, tmark, 9);
     }
-    if (p.gb[L - 1] != nullptr && my_tiles > 0) {
+  } else if (warp >= BW_PZ0 && warp < BW_MMA) {
+    // ---------------------------------------------------------------- dz producers + bias-gradient sums
+    const int w = warp - BW_PZ0;
+    const int grp = 4 * w + (lane >> 3), li = lane & 7;
+    const int c0 = 8 * li;
+    const int act_last = p.l[L - 1].act;
+    float bsum[8];  // fp32 column sums of dz (the last layer's bias gradient)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+    const bool vec_ok = (p.lddy & 3) == 0 && (p.ldz & 3) == 0 && (p.D & 7) == 0;
+    const bool no_dz_loads = (p.debug & 4) != 0;
+    const bool want_gb = p.gb[L - 1] != nullptr;
+    const uint32_t base_off = tile_off(grp, li);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      // 16 rows per pass, 2 passes in flight; the first loads are issued before the wait for the buffer.  Full tiles of
+      // full-width rows (all but the last tile) take the path without per-element predicates.
+      const int64_t r0 = tile * TILE_ROWS + grp;
+      const bool full = vec_ok && p.D == 64 && tile * TILE_ROWS + TILE_ROWS <= p.g.N && !no_dz_loads;
+      if (!(p.debug & 32)) {
+        // dy / z of this CTA's NEXT tile -> L2 (thread = row, one prefetch per 128-byte line): the loads of the next
+        // iteration see L2 latency, and a whole tile of DRAM requests is in flight without registers or shared memory
+        const int64_t nr = (tile + gridDim.x) * TILE_ROWS + (threadIdx.x - BW_PZ0 * 32);
+        if (nr < p.g.N && !no_dz_loads) {
+          const char* a = reinterpret_cast<const char*>(p.dy + nr * p.lddy);
+          const char* b = reinterpret_cast<const char*>(p.z + nr * p.ldz);
+          for (int o = 0; o < p.D * 4; o += 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+          }
+        }
+      }
+      const float* dyp = p.dy + r0 * p.lddy + c0;
+      const float* zp = p.z + r0 * p.ldz + c0;
+#pragma unroll 1
+      for (int pass = 0; pass < 8; pass += 2) {
+        float gy[2][8], zz[2][8];
+        if (full) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(dyp + (int64_t)u * 16 * p.lddy));
+            const float4 b = __ldcs(reinterpret_cast<const float4*>(dyp + (int64_t)u * 16 * p.lddy + 4));
+            const float4 c = __ldcs(reinterpret_cast<const float4*>(zp + (int64_t)u * 16 * p.ldz));
+            const float4 d = __ldcs(reinterpret_cast<const float4*>(zp + (int64_t)u * 16 * p.ldz + 4));
+            gy[u][0] = a.x; gy[u][1] = a.y; gy[u][2] = a.z; gy[u][3] = a.w;
+            gy[u][4] = b.x; gy[u][5] = b.y; gy[u][6] = b.z; gy[u][7] = b.w;
+            zz[u][0] = c.x; zz[u][1] = c.y; zz[u][2] = c.z; zz[u][3] = c.w;
+            zz[u][4] = d.x; zz[u][5] = d.y; zz[u][6] = d.z; zz[u][7] = d.w;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int64_t gr = r0 + (pass + u) * 16;
+            const float* dq = dyp + (int64_t)u * 16 * p.lddy;
+            const float* zq = zp + (int64_t)u * 16 * p.ldz;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool in = gr < p.g.N && c0 + j < p.D && !no_dz_loads;
+              gy[u][j] = in ? dq[j] : 0.f;
+              zz[u][j] = in ? zq[j] : 0.f;
+            }
+          }
+        }
+        dyp += (int64_t)32 * p.lddy;
+        zp += (int64_t)32 * p.ldz;
+        if (pass == 0) wait_bar<PROF>(dz_free, (uint32_t)((it & 1) ^ 1), wacc, tmark, 1, 8);
+        // dz in place of dy, four columns at a time (the coefficients are broadcast reads of shared memory)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 a = *reinterpret_cast<const float4*>(s_coef + c0 + 4 * h);
+          const float4 b = *reinterpret_cast<const float4*>(s_coef + 64 + c0 + 4 * h);
+          const float4 m = *reinterpret_cast<const float4*>(s_coef + 128 + c0 + 4 * h);
+          const float4 c = *reinterpret_cast<const float4*>(s_coef + 192 + c0 + 4 * h);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            gy[u][4 * h] = a.x * gy[u][4 * h] + b.x * (zz[u][4 * h] - m.x) + c.x;
+            gy[u][4 * h + 1] = a.y * gy[u][4 * h + 1] + b.y * (zz[u][4 * h + 1] - m.y) + c.y;
+            gy[u][4 * h + 2] = a.z * gy[u][4 * h + 2] + b.z * (zz[u][4 * h + 2] - m.z) + c.z;
+            gy[u][4 * h + 3] = a.w * gy[u][4 * h + 3] + b.w * (zz[u][4 * h + 3] - m.w) + c.w;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float (&v)[8] = gy[u];
+          actgrad_t<GENERIC, 8>(act_last, v, zz[u]);
+          if (!full) {  // rows beyond N / columns beyond D contribute nothing (the BatchNorm constant is not zero there)
+            const bool ok = r0 + (pass + u) * 16 < p.g.N;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (ok && c0 + j < p.D) ? v[j] : 0.f;
+          }
+          if (want_gb) {  // bias gradient of the last layer: fp32 column sums BEFORE the bf16 rounding
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bsum[j] += v[j];
+          }
+          *reinterpret_cast<uint4*>(sDZ + base_off + (pass + u) * 2048) = pack8(v);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dz_full);
+      lap<PROF>(wacc, tmark, 9);
+    }
+    if (my_tiles > 0 && want_gb) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float v = bsum[j];
@@ -682,7 +869,7 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         if (lane < 8 && c0 + j < p.D) atomicAdd(p.gb[L - 1] + c0 + j, v);
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == BW_MMA) {
     // ---------------------------------------------------------------- MMA issuer
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, (L == 2 ? 2 : 1) * W_BYTES);
@@ -690,128 +877,146 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       if (L == 2) tma_load_2d(sW1, &tmW1, w_full, 0, 0);
     }
     __syncwarp();
-    wait_bar<POLL>(w_full, 0);
-    const uint32_t id_fwd = umma_idesc_bf16(128, 64, 0, 0);    // A K-major, B K-major   (forward)
-    const uint32_t id_dg = umma_idesc_bf16(128, 64, 0, 1);     // A K-major, B MN-major  (dgrad: B = weight^T view)
-    const uint32_t id_wg = umma_idesc_bf16(128, L == 2 ? 128 : 64, 1, 1);  // both MN-major (contraction over the rows)
+    wait_bar<PROF>(w_full, 0, wacc, tmark, 7, 15);
+    const uint32_t id_fwd = umma_idesc_bf16(128, 64, 0, 0);   // A K-major, B K-major   (forward)
+    const uint32_t id_dg = umma_idesc_bf16(128, 64, 0, 1);    // A K-major, B MN-major  (dgrad: B = weight^T view)
+    const uint32_t id_wg = umma_idesc_bf16(128, 64, 1, 1);    // both MN-major (contraction over the rows of the tile)
     const uint32_t aX = smem_u32(sX), aY1 = smem_u32(sY1), aDZ = smem_u32(sDZ), aDY1 = smem_u32(sDY1),
                    aW0 = smem_u32(sW0), aW1 = smem_u32(sW1);
+    if (L == 2 && my_tiles > 0) {  // X0(0) W0^T
+      wait_bar<PROF>(&x_full[0], 0u, wacc, tmark, 2, 8);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, desc_k(aX, k), desc_k(aW0, k), id_fwd, k > 0 ? 1u : 0u);
+        umma_commit(y_full);
+      }
+      __syncwarp();
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       const int s = it & 1;
       const uint32_t aXs = aX + s * TILE_BYTES;
-      trace_ev(p.debug, 16);
-      wait_bar<POLL>(da_free, ph ^ 1);  // dX0 of the previous tile has been read out
-      trace_ev(p.debug, 17);
-      wait_bar<POLL>(&x_full[s], (uint32_t)((it >> 1) & 1));
-      trace_ev(p.debug, 18);
       if (L == 2) {
+        wait_bar<PROF>(y1_full, ph, wacc, tmark, 3, 8);  // Y1 in shared memory; dX0 of the previous tile read out
+        wait_bar<PROF>(dz_full, ph, wacc, tmark, 4, 8);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_a, desc_k(aXs, k), desc_k(aW0, k), id_fwd, k > 0 ? 1u : 0u);
-          umma_commit(da_full);
-        }
-        __syncwarp();
-        wait_bar<POLL>(y1_full, ph);   // Y1 in shared memory, accumulator free again
-        trace_ev(p.debug, 19);
-        wait_bar<POLL>(dz_full, ph);
-        trace_ev(p.debug, 20);
-        tc_fence_after();
-        if (elect_one()) {        // dz W1  (contraction over out_1)
+          for (int k = 0; k < 4; ++k)  // dz W1  (contraction over out_1)
+            umma_bf16(tmem_a, desc_k(aDZ, k), desc_mn(aW1, k, W_BYTES), id_dg, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_a, desc_k(aDZ, k), desc_mn(aW1, k, W_BYTES), id_dg, k > 0 ? 1u : 0u);
-          umma_commit(da_full);
+          for (int k = 0; k < 8; ++k)  // [dz ; .]^T Y1 -> columns 0-63
+            umma_bf16(tmem_w, desc_mn(aDZ, k, TILE_BYTES), desc_mn(aY1, k, TILE_BYTES), id_wg, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(a_full);
+          umma_commit(dz_free);
         }
         __syncwarp();
-        wait_bar<POLL>(dy1_full, ph);
-        trace_ev(p.debug, 21);
+        wait_bar<PROF>(dy1_full, ph, wacc, tmark, 5, 8);
         tc_fence_after();
-        if (elect_one()) {        // dX0 = dY1 W0
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_a, desc_k(aDY1, k), desc_mn(aW0, k, W_BYTES), id_dg, k > 0 ? 1u : 0u);
-          umma_commit(da_full);
+          for (int k = 0; k < 4; ++k)  // dX0 = dY1 W0
+            umma_bf16(tmem_a, desc_k(aDY1, k), desc_mn(aW0, k, W_BYTES), id_dg, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // [. ; dY1]^T X0 -> columns 64-127
+            umma_bf16(tmem_w + 64, desc_mn(aDZ, k, TILE_BYTES), desc_mn(aXs, k, TILE_BYTES), id_wg, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(a_full);
+          umma_commit(&x_empty[s]);
         }
         __syncwarp();
+        if (it + 1 < my_tiles) {  // X0(t+1) W0^T into its own accumulator (read out by the epilogue before y1_full(t))
+          wait_bar<PROF>(&x_full[s ^ 1], (uint32_t)(((it + 1) >> 1) & 1), wacc, tmark, 2, 8);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_y, desc_k(aX + (s ^ 1) * TILE_BYTES, k), desc_k(aW0, k), id_fwd, k > 0 ? 1u : 0u);
+            umma_commit(y_full);
+          }
+          __syncwarp();
+        }
       } else {
-        wait_bar<POLL>(dz_full, ph);
+        wait_bar<PROF>(da_free, ph ^ 1, wacc, tmark, 1, 8);  // dX0 of the previous tile has been read out
+        wait_bar<PROF>(&x_full[s], (uint32_t)((it >> 1) & 1), wacc, tmark, 2, 8);
+        wait_bar<PROF>(dz_full, ph, wacc, tmark, 4, 8);
         tc_fence_after();
-        if (elect_one()) {        // dX0 = dz W0
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_a, desc_k(aDZ, k), desc_mn(aW0, k, W_BYTES), id_dg, k > 0 ? 1u : 0u);
-          umma_commit(da_full);
+          for (int k = 0; k < 4; ++k)  // dX0 = dz W0
+            umma_bf16(tmem_a, desc_k(aDZ, k), desc_mn(aW0, k, W_BYTES), id_dg, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // [dz ; 0]^T X0 -> columns 0-63
+            umma_bf16(tmem_w, desc_mn(aDZ, k, TILE_BYTES), desc_mn(aXs, k, TILE_BYTES), id_wg, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(a_full);
+          umma_commit(&x_empty[s]);
+          umma_commit(dz_free);
         }
         __syncwarp();
       }
-      // weight gradients: [dz ; dY1]^T (M = 128) x [Y1 | X0] (N = 128) or x X0 (N = 64), K = the 128 rows of the tile,
-      // accumulated in TMEM over every tile of this CTA
-      if (elect_one()) {
-        const uint32_t b_addr = (L == 2) ? aY1 : aXs;
-        const uint32_t b_lbo = (L == 2) ? (uint32_t)((1 + s) * TILE_BYTES) : (uint32_t)TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_w, desc_mn(aDZ, k, TILE_BYTES), desc_mn(b_addr, k, b_lbo), id_wg, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&x_empty[s]);
-        umma_commit(w_done);
-      }
-      __syncwarp();
-      trace_ev(p.debug, 22);
     }
+    if (elect_one()) umma_commit(w_done);
+    __syncwarp();
   } else {
     // ---------------------------------------------------------------- epilogue: thread = row of the tile
-    const int q = warp & 3;
+    const int q = warp;
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint32_t da_ph = 0;  // parity of the next completion of da_full
+    uint32_t a_ph = 0;  // parity of the next completion of a_full
     const int act0 = p.l[0].act;
-    float cb_acc[2] = {0.f, 0.f};  // bias gradient of layer 0 (L == 2): lane l owns column 32 i + l
+    const bool want_gb0 = L == 2 && p.gb[0] != nullptr;
+    const uint32_t e_row = (uint32_t)((row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128), e_r7 = (uint32_t)(row_in_tile & 7);
+    auto e_off = [&](int chunk) { return e_row + (((uint32_t)chunk ^ e_r7) << 4); };  // = tile_off(row_in_tile, chunk)
+    float cb_acc[4] = {0.f, 0.f, 0.f, 0.f};  // bias gradient of layer 0: lanes 2m, 2m+1 hold column 16 i + m
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int64_t row = tile * TILE_ROWS + row_in_tile;
       const bool row_ok = row < p.g.N;
       if (L == 2) {
-        if (warp == 5) trace_ev(p.debug, 32);
-        wait_bar<POLL>(da_full, da_ph);
-        if (warp == 5) trace_ev(p.debug, 33);
-        da_ph ^= 1;
+        // Y1 = act(X0 W0^T + b0) -> shared memory (bf16)
+        wait_bar<PROF>(y_full, (uint32_t)(it & 1), wacc, tmark, 1, 8);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_a + lane_off + c0, r);
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_y + lane_off + c0, r);
           tmem_ld_wait();
-          float v[32];
-          add_bias32(v, r, s_bias + c0);
-          act32(act0, v);
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+            v[j] = __uint_as_float(r[j]) + b.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+          }
+          act_t<GENERIC, 16>(act0, v);
+          // (columns beyond the layer's width hold act(0): the next weight's K columns there are zero)
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
             float w8[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) w8[t] = v[j + t];
-            const uint4 u = pack8(w8);
-            *reinterpret_cast<uint4*>(sY1 + tile_off(row_in_tile, (c0 + j) >> 3)) = u;
+            *reinterpret_cast<uint4*>(sY1 + e_off((c0 + j) >> 3)) = pack8(w8);
           }
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(y1_full);
-        if (warp == 5) trace_ev(p.debug, 34);
         // dY1 = (dz W1) * act'(Y1)
-        wait_bar<POLL>(da_full, da_ph);
-        if (warp == 5) trace_ev(p.debug, 35);
-        da_ph ^= 1;
+        wait_bar<PROF>(a_full, a_ph, wacc, tmark, 2, 9);
+        a_ph ^= 1;
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_a + lane_off + c0, r);
-          tmem_ld_wait();
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_a + lane_off + c0, r);
           // (rows beyond N have dz = 0, columns beyond the width meet zero weight columns: no masks needed)
-          float v[32], yv[32];
+          float v[16], yv[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {  // Y1 of this row back from its shared-memory tile (bf16)
-            const uint4 u = *reinterpret_cast<const uint4*>(sY1 + tile_off(row_in_tile, (c0 + j) >> 3));
+          for (int j = 0; j < 16; j += 8) {  // Y1 of this row back from its shared-memory tile (bf16)
+            const uint4 u = *reinterpret_cast<const uint4*>(sY1 + e_off((c0 + j) >> 3));
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -820,64 +1025,63 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
               yv[j + 2 * t + 1] = y.y;
             }
           }
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          actgrad_n<32>(act0, v, yv);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          actgrad_t<GENERIC, 16>(act0, v, yv);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < 16; j += 8) {
             float w8[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) w8[t] = v[j + t];
-            *reinterpret_cast<uint4*>(sDY1 + tile_off(row_in_tile, (c0 + j) >> 3)) = pack8(w8);
+            *reinterpret_cast<uint4*>(sDY1 + e_off((c0 + j) >> 3)) = pack8(w8);
           }
-          if (p.gb[0] != nullptr && c0 < p.l[0].out_f) cb_acc[c0 >> 5] += warp_colsum32(v, lane);  // fp32, pre-rounding
+          if (want_gb0) cb_acc[c0 >> 4] += warp_colsum16(v, lane);  // fp32, before the bf16 rounding
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(dy1_full);
-        if (warp == 5) trace_ev(p.debug, 36);
       }
       // dX0 -> global (fp32, consumed by the sorted-run gather backward)
-      wait_bar<POLL>(da_full, da_ph);
-      if (warp == 5) trace_ev(p.debug, 37);
-      da_ph ^= 1;
+      wait_bar<PROF>(a_full, a_ph, wacc, tmark, 3, 10);
+      a_ph ^= 1;
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+      for (int c0 = 0; c0 < 64; c0 += 16) {
         if (c0 >= p.g.C) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_a + lane_off + c0, r);
+        uint32_t r[16];
+        tmem_ld16(tmem_a + lane_off + c0, r);
         tmem_ld_wait();
         if (row_ok && !(p.debug & 8)) {
           float* dst = p.dx + row * p.lddx + c0;
-          if (c0 + 32 <= p.g.C && (p.lddx & 3) == 0) {
+          if (c0 + 16 <= p.g.C && (p.lddx & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
+            for (int j = 0; j < 16; j += 4)
               *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < 16; ++j)
               if (c0 + j < p.g.C) dst[j] = __uint_as_float(r[j]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(da_free);
-      if (warp == 5) trace_ev(p.debug, 38);
+      if (L == 1 && lane == 0) mbar_arrive(da_free);
+      lap<PROF>(wacc, tmark, 11);
     }
-    // ---- flush the gradient accumulators
+    // ---- flush the weight-gradient accumulators
     if (my_tiles > 0) {
-      if (L == 2 && p.gb[0] != nullptr) {
+      if (want_gb0 && !(lane & 1)) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int col = 32 * i + lane;
+        for (int i = 0; i < 4; ++i) {
+          const int col = 16 * i + (lane >> 1);
           if (col < p.l[0].out_f) atomicAdd(p.gb[0] + col, cb_acc[i]);
         }
       }
-      wait_bar<POLL>(w_done, (uint32_t)((my_tiles - 1) & 1));
+      wait_bar<PROF>(w_done, 0u, wacc, tmark, 5, 12);
       tc_fence_after();
       // lane = output feature of the stacked A operand.  L == 2: lanes 0-63 = dz (layer 1, x Y1 = columns 0-63), lanes
       // 64-127 = dY1 (layer 0, x X0 = columns 64-127).  L == 1: lanes 0-63 = dz (layer 0, x X0 = columns 0-63).
@@ -890,16 +1094,16 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         float* gw = p.gw[layer];
         const int col_base = (L == 2 && half == 1) ? 64 : 0;
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = 0; c0 < 64; c0 += 16) {
           if (c0 >= la.in_f) break;
-          uint32_t r[32];
-          tmem_ld32(tmem_w + lane_off + col_base + c0, r);
+          uint32_t r[16];
+          tmem_ld16(tmem_w + lane_off + col_base + c0, r);
           tmem_ld_wait();
           if (o < la.out_f && gw != nullptr) {
             float* dst = gw + (int64_t)o * la.in_f + c0;
-            if (c0 + 32 <= la.in_f && (la.in_f & 3) == 0 && (reinterpret_cast<uintptr_t>(gw) & 15) == 0) {
+            if (c0 + 16 <= la.in_f && (la.in_f & 3) == 0 && (reinterpret_cast<uintptr_t>(gw) & 15) == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
+              for (int j = 0; j < 16; j += 4) {
                 const size_t a = __cvta_generic_to_global(dst + j);
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(__uint_as_float(r[j])),
                              "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
@@ -908,7 +1112,7 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < 16; ++j)
                 if (c0 + j < la.in_f) atomicAdd(dst + j, __uint_as_float(r[j]));
             }
           }
@@ -917,9 +1121,11 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     }
   }
 
+  if (PROF && (lane == 0) && (warp == 0 || warp == BW_PG0 || warp == BW_PZ0 || warp == BW_MMA))
+    prof_flush<PROF>(warp == BW_PG0 ? 0 : (warp == BW_MMA ? 1 : (warp == 0 ? 2 : 3)), t_loop, wacc);
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == BW_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -930,11 +1136,6 @@ inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int mlp2_debug() {
   const char* e = getenv("SBR_MLP2_DEBUG");
   return e ? atoi(e) : 0;
-}
-
-inline bool mlp2_poll() {
-  const char* e = getenv("SBR_MLP2_POLL");
-  return e ? atoi(e) != 0 : false;  // (measured: test_wait polling is 4 % slower than try_wait here)
 }
 
 inline int64_t mlp2_grid(int64_t N) {
@@ -976,15 +1177,10 @@ int make_weight_maps(const sbr_mlp2_desc_t* d, CUtensorMap* tm) {
 }  // namespace
 
 extern "C" int sbr_mlp2_trace_read(unsigned long long* host_out, int max_events) {
-  unsigned int n = 0;
   SBR_CHECK_CUDA(cudaDeviceSynchronize());
-  SBR_CHECK_CUDA(cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n)));
-  if (n > 4096u) n = 4096u;
-  if ((int)n > max_events) n = (unsigned)max_events;
-  if (n > 0) SBR_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * n));
-  const unsigned int zero = 0;
-  SBR_CHECK_CUDA(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));
-  return (int)n;  // (number of events, not a status)
+  const int n = max_events < 4 * PROF_SLOTS ? max_events : 4 * PROF_SLOTS;
+  if (n > 0) SBR_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * n));
+  return n;  // (number of words, not a status)
 }
 
 extern "C" int sbr_mlp2_colstats_rows(int64_t n_rows) { return (int)mlp2_grid(n_rows); }
@@ -1020,9 +1216,9 @@ extern "C" int sbr_mlp2_fwd(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, flo
   if (colstats != nullptr && colstats_rows > grid)  // rows no CTA writes must not hold garbage
     SBR_CHECK_CUDA(cudaMemsetAsync(colstats + (size_t)grid * 2 * p.D, 0,
                                    (size_t)(colstats_rows - grid) * 2 * p.D * sizeof(float), S(stream)));
-  const bool poll = mlp2_poll();
-  auto kern = d->n_layers == 1 ? (poll ? mlp2_fwd_kernel<1, true> : mlp2_fwd_kernel<1, false>)
-                               : (poll ? mlp2_fwd_kernel<2, true> : mlp2_fwd_kernel<2, false>);
+  const bool prof = (p.debug & 16) != 0;
+  auto kern = d->n_layers == 1 ? (prof ? mlp2_fwd_kernel<1, true> : mlp2_fwd_kernel<1, false>)
+                               : (prof ? mlp2_fwd_kernel<2, true> : mlp2_fwd_kernel<2, false>);
   SBR_CHECK_CUDA(sbr_launch(kern, dim3((unsigned)grid), dim3(N_THREADS), (size_t)FWD_SMEM, S(stream), tm[0], tm[1], p));
   return SBR_OK;
 }
@@ -1054,18 +1250,22 @@ extern "C" int sbr_mlp2_bwd(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, con
   CUtensorMap tm[2];
   rc = make_weight_maps(d, tm);
   if (rc) return rc;
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, BwdParams);
+  static const Kern kerns[8] = {mlp2_bwd_kernel<1, false, false>, mlp2_bwd_kernel<1, false, true>,
+                                mlp2_bwd_kernel<1, true, false>,  mlp2_bwd_kernel<1, true, true>,
+                                mlp2_bwd_kernel<2, false, false>, mlp2_bwd_kernel<2, false, true>,
+                                mlp2_bwd_kernel<2, true, false>,  mlp2_bwd_kernel<2, true, true>};
   static bool configured = false;
   if (!configured) {
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_bwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_bwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_bwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_bwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    for (int i = 0; i < 8; ++i)
+      SBR_CHECK_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     configured = true;
   }
   const int64_t grid = mlp2_grid(n_rows);
-  const bool poll = mlp2_poll();
-  auto kern = d->n_layers == 1 ? (poll ? mlp2_bwd_kernel<1, true> : mlp2_bwd_kernel<1, false>)
-                               : (poll ? mlp2_bwd_kernel<2, true> : mlp2_bwd_kernel<2, false>);
-  SBR_CHECK_CUDA(sbr_launch(kern, dim3((unsigned)grid), dim3(N_THREADS), (size_t)BWD_SMEM, S(stream), tm[0], tm[1], p));
+  const bool prof = (p.debug & 16) != 0;
+  bool generic = false;  // activations other than none / ReLU take the instantiation with the full switch
+  for (int l = 0; l < d->n_layers; ++l) generic |= d->layers[l].act != SBR_ACT_NONE && d->layers[l].act != SBR_ACT_RELU;
+  const Kern kern = kerns[(d->n_layers == 2 ? 4 : 0) + (prof ? 2 : 0) + (generic ? 1 : 0)];
+  SBR_CHECK_CUDA(sbr_launch(kern, dim3((unsigned)grid), dim3(BWD_THREADS), (size_t)BWD_SMEM, S(stream), tm[0], tm[1], p));
   return SBR_OK;
 }
