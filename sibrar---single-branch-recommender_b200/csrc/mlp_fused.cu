@@ -28,7 +28,6 @@ constexpr int TILE_BYTES = TILE_ROWS * 128;  // 16 KiB
 constexpr int W_BYTES = 64 * 128;            // 8 KiB
 constexpr int LPR = 8;                       // lanes per gathered row (8 columns each)
 constexpr int MAX_SRC = 16;
-constexpr int N_PRODUCER_WARPS = 4, MMA_WARP = 4, FIRST_EPI_WARP = 5, N_THREADS = 9 * 32;
 
 struct GatherArgs {
   const sbr_modality_src_t* srcs;
@@ -220,74 +219,6 @@ __device__ __forceinline__ void add_bias32(float (&v)[32], const uint32_t (&r)[3
   }
 }
 
-// Producer, phase A (thread = row of the tile): entity index -> modality source -> feature row -> address of the fp32
-// source row (nullptr: no row).  128 independent dependent-load chains in flight per CTA.
-__device__ __forceinline__ void resolve_rows(const GatherArgs& g, const sbr_modality_src_t* s_src, int64_t tile,
-                                             const float** s_ptr, int tid) {
-  const int64_t gr = tile * TILE_ROWS + tid;
-  const float* ptr = nullptr;
-  if (gr < g.N) {
-    int m = g.mods ? (int)__ldg(g.mods + gr) : 0;
-    m = min(m, g.n_mods - 1);
-    const sbr_modality_src_t& s = s_src[m];
-    const int64_t e = __ldg(g.idx + gr / g.k);
-    const int64_t feat = s.remap ? (int64_t)__ldg(s.remap + e) : e;
-    if (feat < 0) {
-      if (g.err_flag) atomicExch(g.err_flag, 1);
-    } else {
-      const int64_t src_row = (s.kind == SBR_SRC_CATEGORICAL) ? (int64_t)__ldg(s.codes + feat) : feat;
-      ptr = s.table + src_row * g.C;
-    }
-  }
-  s_ptr[tid] = ptr;
-}
-
-// Producer, phase B: groups of 8 lanes load the rows (4 rows per group in flight), normalise, drop, convert and store
-// them into `dst` (the SWIZZLE_128B image).  TAG sources are not handled here (entities present them as tables).
-__device__ __forceinline__ void gather_tile(const GatherArgs& g, const float* const* s_ptr, int64_t tile, uint8_t* dst,
-                                            int tid, uint64_t step, bool no_loads) {
-  const int grp = tid >> 3, li = tid & 7;
-  const float sc = g.p_drop > 0.f ? 1.f / (1.f - g.p_drop) : 1.f;
-  const bool vec_ok = (g.C & 3) == 0;
-#pragma unroll 1
-  for (int pass = 0; pass < 8; pass += 4) {
-    float x[4][8];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float* ptr = s_ptr[(pass + u) * 16 + grp];
-      if (ptr != nullptr && !no_loads) {
-        load8(ptr, 8 * li, g.C, vec_ok, x[u]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[u][j] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int row = (pass + u) * 16 + grp;
-      const int64_t gr = tile * TILE_ROWS + row;
-      if (g.normalize) {
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss += x[u][j] * x[u][j];
-        ss = group_sum<LPR>(ss);
-        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[u][j] *= inv;
-      }
-      const uint32_t km = gr < g.N ? keep8(g.keep_mask, gr, g.C, 8 * li, g.p_drop, g.seed, step) : 0u;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = ((km >> j) & 1u) ? x[u][j] * sc : 0.f;
-      *reinterpret_cast<uint4*>(dst + tile_off(row, li)) = pack8(v);
-    }
-  }
-}
-
-__device__ __forceinline__ void producer_sync() {  // the 128 producer threads only
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-}
-
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
@@ -300,11 +231,144 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, int k16, uint32_t lbo
   return umma_smem_desc(addr + k16 * 2048, lbo, 1024);
 }
 
+// rows of a tile owned by gather / dz warp w (4 lane groups of 8 lanes, 8 passes): 16 i + 4 w + j  (i < 8, j < 4)
+__device__ __forceinline__ int warp_row(int w, int lane) { return 16 * (lane >> 2) + 4 * w + (lane & 3); }
+
+// X0 producer loop of one gather warp (w = 0..3 of the 4 gather warps): X0 = dropout(normalise(gather)) of every tile of
+// this CTA -> the SWIZZLE_128B stage (it & 1).  A warp resolves the 32 rows it gathers itself (no CTA-level barrier), and
+// the dependent index loads of tile t+1 (entity index -> feature row -> category) are issued between the gather passes of
+// tile t.  x_full[s] expects one arrival per gather warp; x_empty[s] completes when the stage may be overwritten.
+template <bool PROF>
+__device__ __forceinline__ void gather_producer(const GatherArgs& g, const sbr_modality_src_t* s_src, const float** s_ptr,
+                                                uint8_t* sX, uint64_t* x_full, uint64_t* x_empty, int w, int lane,
+                                                int64_t num_tiles, bool no_loads, uint32_t (&wacc)[PROF_SLOTS],
+                                                uint32_t& tmark) {
+  const uint64_t step = g.step_dev ? (uint64_t)*g.step_dev : 0;
+  const int grp = 4 * w + (lane >> 3), li = lane & 7;
+  const int my_row = warp_row(w, lane);
+  const float sc = g.p_drop > 0.f ? 1.f / (1.f - g.p_drop) : 1.f;
+  const bool vec_ok = (g.C & 3) == 0;
+  const bool hash_drop = g.p_drop > 0.f && g.keep_mask == nullptr;
+  const uint32_t key0 = philox_key0(g.seed, step);
+  const uint32_t thr_hi = min(drop_threshold(g.p_drop), 0xFFFFu) << 16;
+  const uint32_t base_off = tile_off(grp, li);  // this thread's chunk of row `grp`; row 16 i + grp is 2048 i further
+  // resolver state of the NEXT tile's row `my_row`
+  int64_t r_e = 0, r_feat = -1, r_src = 0;
+  int r_m = 0;
+  bool r_ok = false;
+  auto stage1 = [&](int64_t tile) {
+    const int64_t gr = tile * TILE_ROWS + my_row;
+    r_ok = tile < num_tiles && gr < g.N;
+    if (r_ok) {
+      r_m = g.mods ? min((int)__ldg(g.mods + gr), g.n_mods - 1) : 0;
+      r_e = __ldg(g.idx + (g.k == 1 ? gr : gr / g.k));
+    }
+  };
+  auto stage2 = [&]() {
+    if (r_ok) {
+      const sbr_modality_src_t& s = s_src[r_m];
+      r_feat = s.remap ? (int64_t)__ldg(s.remap + r_e) : r_e;
+    }
+  };
+  auto stage3 = [&]() {
+    if (r_ok && r_feat >= 0)
+      r_src = (s_src[r_m].kind == SBR_SRC_CATEGORICAL) ? (int64_t)__ldg(s_src[r_m].codes + r_feat) : r_feat;
+  };
+  auto publish = [&]() {  // -> s_ptr[my_row]
+    const float* ptr = nullptr;
+    if (r_ok) {
+      if (r_feat < 0) {
+        if (g.err_flag) atomicExch(g.err_flag, 1);
+      } else {
+        ptr = s_src[r_m].table + r_src * g.C;
+      }
+    }
+    s_ptr[my_row] = ptr;
+  };
+  stage1(blockIdx.x);
+  stage2();
+  stage3();
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    uint8_t* dst = sX + s * TILE_BYTES;
+    publish();
+    __syncwarp();
+    stage1(tile + gridDim.x);
+    wait_bar<PROF>(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1), wacc, tmark, 1, 8);
+#pragma unroll 1
+    for (int pass = 0; pass < 8; pass += 4) {
+      float x[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* ptr = s_ptr[(pass + u) * 16 + grp];
+        if (ptr != nullptr && !no_loads) {
+          load8(ptr, 8 * li, g.C, vec_ok, x[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[u][j] = 0.f;
+        }
+      }
+      if (pass == 0) stage2(); else stage3();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = (pass + u) * 16 + grp;
+        const int64_t gr = tile * TILE_ROWS + row;
+        if (g.normalize) {
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ss += x[u][j] * x[u][j];
+          ss = group_sum<LPR>(ss);
+          const float inv = rsqrtf(fmaxf(ss, 1e-24f));  // = 1 / max(||x||, 1e-12)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[u][j] *= inv;
+        }
+        // (rows beyond N were loaded as zeros)
+        if (hash_drop) {
+          dropout8_hash(x[u], philox_group_k(gr, li, key0), thr_hi, sc);
+        } else if (g.p_drop > 0.f) {
+          const uint32_t km = gr < g.N ? keep8(g.keep_mask, gr, g.C, 8 * li, g.p_drop, g.seed, step) : 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[u][j] = ((km >> j) & 1u) ? x[u][j] * sc : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dst + base_off + (pass + u) * 2048) = pack8(x[u]);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();  // (also: every lane has read s_ptr before the next publish)
+    if (lane == 0) mbar_arrive(&x_full[s]);
+    lap<PROF>(wacc, tmark, 9);
+  }
+}
+
+template <bool GENERIC, int NE>
+__device__ __forceinline__ void act_t(int act, float (&v)[NE]) {
+  if (GENERIC) {
+    act_n<NE>(act, v);
+  } else if (act == SBR_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NE; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+}
+template <bool GENERIC, int NE>
+__device__ __forceinline__ void actgrad_t(int act, float (&v)[NE], const float (&y)[NE]) {
+  if (GENERIC) {
+    actgrad_n<NE>(act, v, y);
+  } else if (act == SBR_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NE; ++j) v[j] = y[j] > 0.f ? v[j] : 0.f;
+  }
+}
+
 // ================================================================================================ forward
+// Warp roles (13 warps, two CTAs per SM): 0-7 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = 32-column half of the
+// row), 8-11 X0 gather, 12 MMA issuer.
+constexpr int FWD_THREADS = 13 * 32;
+constexpr int FW_P0 = 8, FW_MMA = 12;
 constexpr int FWD_SMEM = 2 * W_BYTES + 3 * TILE_BYTES + 3072 + 1024;
 
-template <int L, bool PROF>
-__global__ void __launch_bounds__(N_THREADS, 2)
+template <int L, bool PROF, bool GENERIC>
+__global__ void __launch_bounds__(512, 2)  // 13 warps are allocated as 16: 64 registers per thread for two CTAs per SM
 mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, FwdParams p) {
   SBR_PDL_LAUNCH();
   extern __shared__ uint8_t smem_raw[];
@@ -315,12 +379,12 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
   uint8_t* sA1 = sX + 2 * TILE_BYTES;      // hidden activation (L == 2)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA1 + TILE_BYTES);
   uint64_t* w_full = bars;          // weights landed
-  uint64_t* x_full = bars + 1;      // [2]
+  uint64_t* x_full = bars + 1;      // [2] (4 gather warps)
   uint64_t* x_empty = bars + 3;     // [2]
   uint64_t* dh_full = bars + 5;     // hidden accumulator ready
-  uint64_t* a1_full = bars + 6;     // hidden activation written
+  uint64_t* a1_full = bars + 6;     // hidden activation written (8 epilogue warps)
   uint64_t* df_full = bars + 7;     // final accumulator ready
-  uint64_t* df_empty = bars + 8;    // final accumulator drained
+  uint64_t* df_empty = bars + 8;    // final accumulator drained (8 epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   sbr_modality_src_t* s_src = reinterpret_cast<sbr_modality_src_t*>(bars + 12);
   const float** s_ptr = reinterpret_cast<const float**>(s_src + MAX_SRC);  // [128] source row of every tile row
@@ -328,21 +392,21 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t num_tiles = (p.g.N + TILE_ROWS - 1) / TILE_ROWS;
-  if (warp == MMA_WARP && lane == 0) {
+  if (warp == FW_MMA && lane == 0) {
     tma_prefetch_desc(&tmW0);
     if (L == 2) tma_prefetch_desc(&tmW1);
     mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&x_full[s], N_PRODUCER_WARPS);
+      mbar_init(&x_full[s], 4);
       mbar_init(&x_empty[s], 1);
     }
     mbar_init(dh_full, 1);
-    mbar_init(a1_full, 4);
+    mbar_init(a1_full, 8);
     mbar_init(df_full, 1);
-    mbar_init(df_empty, 4);
+    mbar_init(df_empty, 8);
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 128);
+  if (warp == FW_MMA) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -359,22 +423,11 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
   const uint32_t t_loop = (uint32_t)clock();
   uint32_t tmark = t_loop;
 
-  if (warp < N_PRODUCER_WARPS) {
+  if (warp >= FW_P0 && warp < FW_MMA) {
     // ---------------------------------------------------------------- producers: gather + normalise + dropout -> X0
-    const uint64_t step = p.g.step_dev ? (uint64_t)*p.g.step_dev : 0;
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int s = it & 1;
-      resolve_rows(p.g, s_src, tile, s_ptr, threadIdx.x);
-      producer_sync();
-      wait_bar<PROF>(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1), wacc, tmark, 1, 8);
-      gather_tile(p.g, s_ptr, tile, sX + s * TILE_BYTES, threadIdx.x, step, (p.debug & 2) != 0);
-      fence_proxy_async_smem();
-      producer_sync();  // (also: s_ptr may be overwritten by the next tile)
-      if (lane == 0) mbar_arrive(&x_full[s]);
-      lap<PROF>(wacc, tmark, 9);
-    }
-  } else if (warp == MMA_WARP) {
+    gather_producer<PROF>(p.g, s_src, s_ptr, sX, x_full, x_empty, warp - FW_P0, lane, num_tiles, (p.debug & 2) != 0, wacc,
+                          tmark);
+  } else if (warp == FW_MMA) {
     // ---------------------------------------------------------------- MMA issuer (converged warp, elected issue)
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, (L == 2 ? 2 : 1) * W_BYTES);
@@ -412,12 +465,14 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue: thread = row of the tile
-    const int q = warp & 3;
+    // ---------------------------------------------------------------- epilogue: thread = row, 32 of its 64 columns
+    const int q = warp & 3, half = warp >> 2;
+    const int cb = 32 * half;
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int act0 = p.l[0].act, act_last = p.l[L - 1].act;
-    float cs_acc[2] = {0.f, 0.f}, cq_acc[2] = {0.f, 0.f};
+    const uint32_t e_row = (uint32_t)((row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128), e_r7 = (uint32_t)(row_in_tile & 7);
+    float cs_acc[2] = {0.f, 0.f}, cq_acc[2] = {0.f, 0.f};  // lanes 2m, 2m+1: column cb + 16 i + m
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int64_t row = tile * TILE_ROWS + row_in_tile;
@@ -426,20 +481,27 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         wait_bar<PROF>(dh_full, (uint32_t)(it & 1), wacc, tmark, 1, 8);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_h + lane_off + c0, r);
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_h + lane_off + cb + c0, r);
           tmem_ld_wait();
-          float v[32];
-          add_bias32(v, r, s_bias + c0);
-          act32(act0, v);
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + cb + c0 + j);
+            v[j] = __uint_as_float(r[j]) + b.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+          }
+          act_t<GENERIC, 16>(act0, v);
           // (columns beyond the layer's width hold act(0): the next weight's K columns there are zero)
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < 16; j += 8) {
             float w8[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) w8[t] = v[j + t];
-            *reinterpret_cast<uint4*>(sA1 + tile_off(row_in_tile, (c0 + j) >> 3)) = pack8(w8);
+            *reinterpret_cast<uint4*>(sA1 + e_row + ((((uint32_t)(cb + c0 + j) >> 3) ^ e_r7) << 4)) = pack8(w8);
           }
         }
         tc_fence_before();
@@ -450,36 +512,43 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       wait_bar<PROF>(df_full, (uint32_t)(it & 1), wacc, tmark, 2, 9);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        if (c0 >= p.D) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_f + lane_off + c0, r);
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        if (cb + c0 >= p.D) break;  // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(tmem_f + lane_off + cb + c0, r);
         tmem_ld_wait();
-        float v[32];
-        add_bias32(v, r, s_bias + (L - 1) * 64 + c0);
-        act32(act_last, v);
-        if (p.colstats != nullptr) {
-          float s1[32], s2[32];
+        float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(s_bias + (L - 1) * 64 + cb + c0 + j);
+          v[j] = __uint_as_float(r[j]) + b.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+        }
+        act_t<GENERIC, 16>(act_last, v);
+        if (row_ok && !(p.debug & 8)) {
+          float* dst = p.z + row * p.ldz + cb + c0;
+          if (cb + c0 + 16 <= p.D && (p.ldz & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cb + c0 + j < p.D) dst[j] = v[j];
+          }
+        }
+        if (p.colstats != nullptr) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
             const float x = row_ok ? v[j] : 0.f;
             s1[j] = x;
             s2[j] = x * x;
           }
-          cs_acc[c0 >> 5] += warp_colsum32(s1, lane);
-          cq_acc[c0 >> 5] += warp_colsum32(s2, lane);
-        }
-        if (row_ok && !(p.debug & 8)) {
-          float* dst = p.z + row * p.ldz + c0;
-          if (c0 + 32 <= p.D && (p.ldz & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.D) dst[j] = v[j];
-          }
+          cs_acc[c0 >> 4] += warp_colsum16(s1, lane);
+          cq_acc[c0 >> 4] += warp_colsum16(s2, lane);
         }
       }
       tc_fence_before();
@@ -491,31 +560,30 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
       // one row of partial sums per CTA: the four lane quarters are added in a fixed order (deterministic statistics;
       // sbr_bn_finalize adds the rows of all CTAs in a fixed order as well)
       float* s_part = reinterpret_cast<float*>(sA1);  // (the hidden-activation tile is no longer needed)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        s_part[q * 128 + 32 * i + lane] = cs_acc[i];
-        s_part[q * 128 + 64 + 32 * i + lane] = cq_acc[i];
-      }
-      asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
-      if (q == 0) {
-        float* rowp = p.colstats + (size_t)blockIdx.x * 2 * p.D;
+      if (!(lane & 1)) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const int col = 32 * i + lane;
-          if (col < p.D) {
-            rowp[col] = ((s_part[col] + s_part[128 + col]) + s_part[256 + col]) + s_part[384 + col];
-            rowp[p.D + col] = ((s_part[64 + col] + s_part[128 + 64 + col]) + s_part[256 + 64 + col]) + s_part[384 + 64 + col];
-          }
+          s_part[q * 128 + cb + 16 * i + (lane >> 1)] = cs_acc[i];
+          s_part[q * 128 + 64 + cb + 16 * i + (lane >> 1)] = cq_acc[i];
+        }
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the eight epilogue warps
+      if (q == 0) {
+        float* rowp = p.colstats + (size_t)blockIdx.x * 2 * p.D;
+        const int col = cb + lane;
+        if (col < p.D) {
+          rowp[col] = ((s_part[col] + s_part[128 + col]) + s_part[256 + col]) + s_part[384 + col];
+          rowp[p.D + col] = ((s_part[64 + col] + s_part[128 + 64 + col]) + s_part[256 + 64 + col]) + s_part[384 + 64 + col];
         }
       }
     }
   }
 
-  if (PROF && (warp == 0 || warp == MMA_WARP || warp == FIRST_EPI_WARP))
-    prof_flush<PROF>(warp == 0 ? 0 : (warp == MMA_WARP ? 1 : 2), t_loop, wacc);
+  if (PROF && (lane == 0) && (warp == 0 || warp == FW_P0 || warp == FW_MMA))
+    prof_flush<PROF>(warp == FW_P0 ? 0 : (warp == FW_MMA ? 1 : 2), t_loop, wacc);
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == FW_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 128);
   }
@@ -534,28 +602,6 @@ constexpr int BWD_THREADS = 13 * 32;
 constexpr int BW_PG0 = 4, BW_PZ0 = 8, BW_MMA = 12;
 constexpr int BWD_MISC = 4096;
 constexpr int BWD_SMEM = 2 * W_BYTES + 5 * TILE_BYTES + BWD_MISC + 1024;
-
-// rows of a tile owned by gather / dz warp w (4 lane groups of 8 lanes, 8 passes): 16 i + 4 w + j  (i < 8, j < 4)
-__device__ __forceinline__ int warp_row(int w, int lane) { return 16 * (lane >> 2) + 4 * w + (lane & 3); }
-
-template <bool GENERIC, int NE>
-__device__ __forceinline__ void act_t(int act, float (&v)[NE]) {
-  if (GENERIC) {
-    act_n<NE>(act, v);
-  } else if (act == SBR_ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < NE; ++j) v[j] = fmaxf(v[j], 0.f);
-  }
-}
-template <bool GENERIC, int NE>
-__device__ __forceinline__ void actgrad_t(int act, float (&v)[NE], const float (&y)[NE]) {
-  if (GENERIC) {
-    actgrad_n<NE>(act, v, y);
-  } else if (act == SBR_ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < NE; ++j) v[j] = y[j] > 0.f ? v[j] : 0.f;
-  }
-}
 
 template <int L, bool PROF, bool GENERIC>
 __global__ void __launch_bounds__(512, 2)  // 13 warps are allocated as 16: 64 registers per thread for two CTAs per SM
@@ -658,106 +704,8 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
 
   if (warp >= BW_PG0 && warp < BW_PZ0) {
     // ---------------------------------------------------------------- X0 gather (one tile ahead of the MMAs)
-    // A warp resolves the 32 rows it gathers itself (no CTA-level barrier); the dependent index loads of tile t+1
-    // (entity index -> feature row -> category) are issued between the gather passes of tile t.
-    const uint64_t step = p.g.step_dev ? (uint64_t)*p.g.step_dev : 0;
-    const int w = warp - BW_PG0;
-    const int grp = 4 * w + (lane >> 3), li = lane & 7;
-    const int my_row = warp_row(w, lane);
-    const float sc = p.g.p_drop > 0.f ? 1.f / (1.f - p.g.p_drop) : 1.f;
-    const bool vec_ok = (p.g.C & 3) == 0;
-    const bool no_loads = (p.debug & 2) != 0;
-    const bool hash_drop = p.g.p_drop > 0.f && p.g.keep_mask == nullptr;
-    const uint32_t key0 = philox_key0(p.g.seed, step);
-    const uint32_t thr_hi = min(drop_threshold(p.g.p_drop), 0xFFFFu) << 16;
-    const uint32_t base_off = tile_off(grp, li);  // this thread's chunk of row `grp`; row 16 i + grp is 2048 i further
-    // resolver state of the NEXT tile's row `my_row`
-    int64_t r_e = 0, r_feat = -1, r_src = 0;
-    int r_m = 0;
-    bool r_ok = false;
-    auto stage1 = [&](int64_t tile) {
-      const int64_t gr = tile * TILE_ROWS + my_row;
-      r_ok = tile < num_tiles && gr < p.g.N;
-      if (r_ok) {
-        r_m = p.g.mods ? min((int)__ldg(p.g.mods + gr), p.g.n_mods - 1) : 0;
-        r_e = __ldg(p.g.idx + (p.g.k == 1 ? gr : gr / p.g.k));
-      }
-    };
-    auto stage2 = [&]() {
-      if (r_ok) {
-        const sbr_modality_src_t& s = s_src[r_m];
-        r_feat = s.remap ? (int64_t)__ldg(s.remap + r_e) : r_e;
-      }
-    };
-    auto stage3 = [&]() {
-      if (r_ok && r_feat >= 0)
-        r_src = (s_src[r_m].kind == SBR_SRC_CATEGORICAL) ? (int64_t)__ldg(s_src[r_m].codes + r_feat) : r_feat;
-    };
-    auto publish = [&]() {  // -> s_ptr[my_row]
-      const float* ptr = nullptr;
-      if (r_ok) {
-        if (r_feat < 0) {
-          if (p.g.err_flag) atomicExch(p.g.err_flag, 1);
-        } else {
-          ptr = s_src[r_m].table + r_src * p.g.C;
-        }
-      }
-      s_ptr[my_row] = ptr;
-    };
-    stage1(blockIdx.x);
-    stage2();
-    stage3();
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int s = it & 1;
-      uint8_t* dst = sX + s * TILE_BYTES;
-      publish();
-      __syncwarp();
-      stage1(tile + gridDim.x);
-      wait_bar<PROF>(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1), wacc, tmark, 1, 8);
-#pragma unroll 1
-      for (int pass = 0; pass < 8; pass += 4) {
-        float x[4][8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float* ptr = s_ptr[(pass + u) * 16 + grp];
-          if (ptr != nullptr && !no_loads) {
-            load8(ptr, 8 * li, p.g.C, vec_ok, x[u]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[u][j] = 0.f;
-          }
-        }
-        if (pass == 0) stage2(); else stage3();
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int row = (pass + u) * 16 + grp;
-          const int64_t gr = tile * TILE_ROWS + row;
-          if (p.g.normalize) {
-            float ss = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ss += x[u][j] * x[u][j];
-            ss = group_sum<LPR>(ss);
-            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[u][j] *= inv;
-          }
-          // (rows beyond N were loaded as zeros)
-          if (hash_drop) {
-            dropout8_hash(x[u], philox_group_k(gr, li, key0), thr_hi, sc);
-          } else if (p.g.p_drop > 0.f) {
-            const uint32_t km = gr < p.g.N ? keep8(p.g.keep_mask, gr, p.g.C, 8 * li, p.g.p_drop, p.g.seed, step) : 0u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[u][j] = ((km >> j) & 1u) ? x[u][j] * sc : 0.f;
-          }
-          *reinterpret_cast<uint4*>(dst + base_off + (pass + u) * 2048) = pack8(x[u]);
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();  // (also: every lane has read s_ptr before the next publish)
-      if (lane == 0) mbar_arrive(&x_full[s]);
-      lap<PROF>(wacc, tmark, 9);
-    }
+    gather_producer<PROF>(p.g, s_src, s_ptr, sX, x_full, x_empty, warp - BW_PG0, lane, num_tiles, (p.debug & 2) != 0, wacc,
+                          tmark);
   } else if (warp >= BW_PZ0 && warp < BW_MMA) {
     // ---------------------------------------------------------------- dz producers + bias-gradient sums
     const int w = warp - BW_PZ0;
@@ -1205,21 +1153,25 @@ extern "C" int sbr_mlp2_fwd(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, flo
   CUtensorMap tm[2];
   rc = make_weight_maps(d, tm);
   if (rc) return rc;
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, FwdParams);
+  static const Kern kerns[8] = {mlp2_fwd_kernel<1, false, false>, mlp2_fwd_kernel<1, false, true>,
+                                mlp2_fwd_kernel<1, true, false>,  mlp2_fwd_kernel<1, true, true>,
+                                mlp2_fwd_kernel<2, false, false>, mlp2_fwd_kernel<2, false, true>,
+                                mlp2_fwd_kernel<2, true, false>,  mlp2_fwd_kernel<2, true, true>};
   static bool configured = false;
   if (!configured) {
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    SBR_CHECK_CUDA(cudaFuncSetAttribute(mlp2_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    for (int i = 0; i < 8; ++i)
+      SBR_CHECK_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     configured = true;
   }
   if (colstats != nullptr && colstats_rows > grid)  // rows no CTA writes must not hold garbage
     SBR_CHECK_CUDA(cudaMemsetAsync(colstats + (size_t)grid * 2 * p.D, 0,
                                    (size_t)(colstats_rows - grid) * 2 * p.D * sizeof(float), S(stream)));
   const bool prof = (p.debug & 16) != 0;
-  auto kern = d->n_layers == 1 ? (prof ? mlp2_fwd_kernel<1, true> : mlp2_fwd_kernel<1, false>)
-                               : (prof ? mlp2_fwd_kernel<2, true> : mlp2_fwd_kernel<2, false>);
-  SBR_CHECK_CUDA(sbr_launch(kern, dim3((unsigned)grid), dim3(N_THREADS), (size_t)FWD_SMEM, S(stream), tm[0], tm[1], p));
+  bool generic = false;  // activations other than none / ReLU take the instantiation with the full switch
+  for (int l = 0; l < d->n_layers; ++l) generic |= d->layers[l].act != SBR_ACT_NONE && d->layers[l].act != SBR_ACT_RELU;
+  const Kern kern = kerns[(d->n_layers == 2 ? 4 : 0) + (prof ? 2 : 0) + (generic ? 1 : 0)];
+  SBR_CHECK_CUDA(sbr_launch(kern, dim3((unsigned)grid), dim3(FWD_THREADS), (size_t)FWD_SMEM, S(stream), tm[0], tm[1], p));
   return SBR_OK;
 }
 
