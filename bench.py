@@ -214,8 +214,8 @@ class CallProfiler:
         if name == "sbr_gemm_bits_bf16":
             ep = args[8]._obj
             return (name, i(5), i(6), i(7), bool(ep.out_bf16), bool(ep.out_f32), False)
-        if name == "sbr_mlp2_fwd":
-            return (name, i(1), i(2))
+        if name in ("sbr_mlp2_fwd", "sbr_mlp2_fwd_bn"):  # (_bn: the same kernel + the in-kernel BatchNorm finalize)
+            return ("sbr_mlp2_fwd", i(1), i(2))
         if name == "sbr_mlp2_bwd":
             return (name, i(1), i(2))
         if name == "sbr_row_gather_fwd":

@@ -274,11 +274,27 @@ typedef struct {
 int sbr_mlp2_colstats_rows(int64_t n_rows);
 int sbr_mlp2_fwd(const sbr_mlp2_desc_t* desc, int64_t n_rows, int C, float* z, int64_t ldz, float* colstats,
                  int colstats_rows, void* stream);
+/* Same forward with the BatchNorm statistics finalised inside the kernel (nn.BatchNorm1d training forward,
+ * modules/polylinear.py:58-62): the CTA that finishes last adds the rows of `colstats` in a fixed order and writes
+ * mean_invstd [2 D] (mean | 1 / sqrt(biased var + eps)), updates the running statistics (unbiased variance) and
+ * num_batches_tracked -- no separate sbr_bn_finalize launch between the chain and the scoring kernel.
+ * counter: one uint32 in device memory, zero on entry, zero again on return. */
+typedef struct {
+  unsigned int* counter;
+  float eps, momentum;
+  float* mean_invstd;
+  float* running_mean;          /* may be NULL */
+  float* running_var;           /* may be NULL */
+  int64_t* num_batches_tracked; /* may be NULL */
+} sbr_mlp2_bn_tail_t;
+int sbr_mlp2_fwd_bn(const sbr_mlp2_desc_t* desc, int64_t n_rows, int C, float* z, int64_t ldz, float* colstats,
+                    int colstats_rows, const sbr_mlp2_bn_tail_t* tail, void* stream);
 int sbr_mlp2_bwd(const sbr_mlp2_desc_t* desc, int64_t n_rows, int C, const float* dy, int64_t lddy, const float* z,
                  int64_t ldz, const sbr_mlp2_bn_t* bn, float* const* grad_w, float* const* grad_b, float* dx,
                  int64_t lddx, void* stream);
-/* profiling only: with SBR_MLP2_DEBUG bit 16 block 0 of sbr_mlp2_bwd stamps %globaltimer at its phase boundaries;
- * returns the NUMBER of (time_ns << 8 | event id) words copied to host_out and clears the buffer */
+/* profiling only: with SBR_MLP2_DEBUG bit 16 the roles of block 0 of sbr_mlp2_fwd / sbr_mlp2_bwd accumulate the SM
+ * cycles of every barrier wait and of the sections of their own work (16 words per role: gather, MMA, epilogue, dz);
+ * returns the NUMBER of words copied to host_out (scripts/trace_mlp2.py prints them) */
 int sbr_mlp2_trace_read(unsigned long long* host_out, int max_events);
 
 /* nn.EmbeddingBag(mode="mean", padding_idx=pad_id) of EVERY feature row as a dense fp32 table [n_rows, C]

@@ -32,7 +32,7 @@ torch.cuda.synchronize()
 calls = {}
 orig_call = ops.call
 def spy(name, *a):
-    if name in ("sbr_mlp2_fwd", "sbr_mlp2_bwd"):
+    if name in ("sbr_mlp2_fwd", "sbr_mlp2_fwd_bn", "sbr_mlp2_bwd"):
         calls[(name, int(a[1]))] = a
     return orig_call(name, *a)
 ops.call = spy

@@ -36,7 +36,7 @@ for key in sorted(calls):
     per_cta = -(-tiles // min(tiles, 296))
     print(f"{key[0]} rows={key[1]} debug={16 | extra} (block 0: {per_cta} tiles), cycles per tile (~1900 cycles = 1 us)")
     for r, role in enumerate("PMEZ"):
-        if role not in SITES[key[0]]:
+        if role not in SITES[key[0].replace("_bn", "")]:
             continue
         v = [int(buf[r * 16 + i]) for i in range(16)]
-        print(f"  {role}: loop {v[0] / per_cta:8.0f}   " + "   ".join(f"{name} {v[i] / per_cta:.0f}" for i, name in SITES[key[0]][role].items()))
+        print(f"  {role}: loop {v[0] / per_cta:8.0f}   " + "   ".join(f"{name} {v[i] / per_cta:.0f}" for i, name in SITES[key[0].replace("_bn", "")][role].items()))

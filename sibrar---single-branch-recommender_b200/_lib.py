@@ -47,6 +47,11 @@ class Mlp2Desc(C.Structure):
                 ("keep_mask", c_vp), ("err_flag", c_vp), ("n_layers", C.c_int), ("layers", Mlp2Layer * 2)]
 
 
+class Mlp2BnTail(C.Structure):
+    _fields_ = [("counter", c_vp), ("eps", c_f32), ("momentum", c_f32), ("mean_invstd", c_vp), ("running_mean", c_vp),
+                ("running_var", c_vp), ("num_batches_tracked", c_vp)]
+
+
 class Mlp2Bn(C.Structure):
     _fields_ = [("mean_invstd", c_vp), ("gamma", c_vp), ("sums", c_vp), ("n_replicas", C.c_int), ("dgamma", c_vp),
                 ("dbeta", c_vp)]
@@ -117,6 +122,7 @@ _PROTOS = {
     "sbr_aggregate": [c_vp, c_i64, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp],
     "sbr_mlp2_colstats_rows": [c_i64],
     "sbr_mlp2_fwd": [C.POINTER(Mlp2Desc), c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp],
+    "sbr_mlp2_fwd_bn": [C.POINTER(Mlp2Desc), c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, C.POINTER(Mlp2BnTail), c_vp],
     "sbr_mlp2_bwd": [C.POINTER(Mlp2Desc), c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, C.POINTER(Mlp2Bn),
                      C.POINTER(c_vp), C.POINTER(c_vp), c_vp, c_i64, c_vp],
     "sbr_mlp2_trace_read": [c_vp, C.c_int],

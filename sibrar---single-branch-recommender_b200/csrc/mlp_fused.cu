@@ -55,6 +55,13 @@ struct FwdParams {
   int64_t ldz;
   float* colstats;  // [colstats_rows, 2 D] partial column sums / sums of squares (deterministic), or nullptr
   int D;
+  // BatchNorm statistics finalised by the CTA that finishes last (counter == nullptr: not done here)
+  unsigned int* bn_counter;
+  float bn_eps, bn_momentum;
+  float* bn_mean_invstd;
+  float* bn_running_mean;
+  float* bn_running_var;
+  int64_t* bn_nbt;
 };
 struct BwdParams {
   int debug;  // SBR_MLP2_DEBUG bit mask (profiling only): 1 = no gradient flush, 2 = no gather loads, 4 = no dy / z loads,
@@ -319,7 +326,7 @@ __device__ __forceinline__ void gather_producer(const GatherArgs& g, const sbr_m
 #pragma unroll
           for (int j = 0; j < 8; ++j) ss += x[u][j] * x[u][j];
           ss = group_sum<LPR>(ss);
-          const float inv = rsqrtf(fmaxf(ss, 1e-24f));  // = 1 / max(||x||, 1e-12)
+          const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[u][j] *= inv;
         }
@@ -582,10 +589,64 @@ mlp2_fwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
   if (PROF && (lane == 0) && (warp == 0 || warp == FW_P0 || warp == FW_MMA))
     prof_flush<PROF>(warp == FW_P0 ? 0 : (warp == FW_MMA ? 1 : 2), t_loop, wacc);
   tc_fence_before();
+  if (p.bn_counter != nullptr) __threadfence();  // this CTA's row of partial sums is visible before its ticket is taken
   __syncthreads();
   if (warp == FW_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 128);
+  }
+  if (p.bn_counter == nullptr) return;
+  // ---- BatchNorm statistics: the CTA that takes the last ticket adds the rows of every CTA in a fixed order (13 row lanes
+  // of 32 float4 column groups, then the lanes in order): the result does not depend on which CTA does it
+  __shared__ unsigned int s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(p.bn_counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  float* s_red = reinterpret_cast<float*>(sX);  // [13][128]
+  const int W2 = 2 * p.D;                       // floats per row (D <= 64)
+  const int g4 = lane * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g4 < W2 && (W2 & 3) == 0) {
+#pragma unroll 4
+    for (int r = warp; r < (int)gridDim.x; r += 13) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.colstats + (size_t)r * W2 + g4));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  } else if (g4 < W2) {
+    for (int r = warp; r < (int)gridDim.x; r += 13) {
+      const float* row = p.colstats + (size_t)r * W2 + g4;
+      acc.x += __ldcg(row);
+      if (g4 + 1 < W2) acc.y += __ldcg(row + 1);
+      if (g4 + 2 < W2) acc.z += __ldcg(row + 2);
+      if (g4 + 3 < W2) acc.w += __ldcg(row + 3);
+    }
+  }
+  *reinterpret_cast<float4*>(s_red + warp * 128 + g4) = acc;
+  __syncthreads();
+  if (threadIdx.x < p.D) {
+    const int c = threadIdx.x;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 13; ++wv) {
+      a += s_red[wv * 128 + c];
+      b += s_red[wv * 128 + p.D + c];
+    }
+    const double n = (double)p.g.N;
+    const double mean = (double)a / n;
+    double var = (double)b / n - mean * mean;
+    if (var < 0.) var = 0.;
+    p.bn_mean_invstd[c] = (float)mean;
+    p.bn_mean_invstd[p.D + c] = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+    if (p.bn_running_mean) p.bn_running_mean[c] = (1.f - p.bn_momentum) * p.bn_running_mean[c] + p.bn_momentum * (float)mean;
+    if (p.bn_running_var) {
+      const double unbiased = n > 1. ? var * n / (n - 1.) : var;
+      p.bn_running_var[c] = (1.f - p.bn_momentum) * p.bn_running_var[c] + p.bn_momentum * (float)unbiased;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (p.bn_nbt) *p.bn_nbt += 1;
+    *p.bn_counter = 0u;
   }
 }
 
@@ -1135,6 +1196,11 @@ extern "C" int sbr_mlp2_colstats_rows(int64_t n_rows) { return (int)mlp2_grid(n_
 
 extern "C" int sbr_mlp2_fwd(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, float* z, int64_t ldz, float* colstats,
                             int colstats_rows, void* stream) {
+  return sbr_mlp2_fwd_bn(d, n_rows, C, z, ldz, colstats, colstats_rows, nullptr, stream);
+}
+
+extern "C" int sbr_mlp2_fwd_bn(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, float* z, int64_t ldz, float* colstats,
+                               int colstats_rows, const sbr_mlp2_bn_tail_t* tail, void* stream) {
   int rc = check_desc(d, "sbr_mlp2_fwd");
   if (rc) return rc;
   SBR_REQUIRE(z && n_rows == d->n_idx * d->k && C == d->C, "sbr_mlp2_fwd: bad output arguments");
@@ -1147,6 +1213,12 @@ extern "C" int sbr_mlp2_fwd(const sbr_mlp2_desc_t* d, int64_t n_rows, int C, flo
   p.D = d->layers[d->n_layers - 1].out_f;
   p.z = z; p.ldz = ldz; p.colstats = colstats;
   SBR_REQUIRE(ldz >= p.D, "sbr_mlp2_fwd: ldz < D");
+  if (tail != nullptr) {
+    SBR_REQUIRE(colstats && tail->counter && tail->mean_invstd, "sbr_mlp2_fwd_bn: colstats, counter and mean_invstd needed");
+    p.bn_counter = tail->counter; p.bn_eps = tail->eps; p.bn_momentum = tail->momentum;
+    p.bn_mean_invstd = tail->mean_invstd; p.bn_running_mean = tail->running_mean; p.bn_running_var = tail->running_var;
+    p.bn_nbt = tail->num_batches_tracked;
+  }
   const int64_t grid = mlp2_grid(n_rows);
   SBR_REQUIRE(colstats == nullptr || colstats_rows >= grid, "sbr_mlp2_fwd: colstats_rows=%d < %lld", colstats_rows,
               (long long)grid);

@@ -300,9 +300,20 @@ def mlp2_colstats_rows(n_rows: int) -> int:
     return int(lib().sbr_mlp2_colstats_rows(int(n_rows)))
 
 
-def mlp2_fwd(desc, n_rows, C_, z, colstats=None, colstats_rows=0):
-    call("sbr_mlp2_fwd", C.byref(desc), int(n_rows), int(C_), ptr(z), z.stride(0), ptr(colstats), int(colstats_rows),
-         stream_ptr())
+def mlp2_fwd(desc, n_rows, C_, z, colstats=None, colstats_rows=0, bn_tail=None):
+    """bn_tail: None or dict(counter (uint32 [1], zero), eps, momentum, mean_invstd, running_mean, running_var,
+    num_batches_tracked): the BatchNorm statistics are finalised by the last CTA of the kernel"""
+    if bn_tail is None:
+        call("sbr_mlp2_fwd", C.byref(desc), int(n_rows), int(C_), ptr(z), z.stride(0), ptr(colstats),
+             int(colstats_rows), stream_ptr())
+        return
+    from ._lib import Mlp2BnTail
+    t = Mlp2BnTail()
+    t.counter, t.eps, t.momentum = ptr(bn_tail["counter"]), float(bn_tail["eps"]), float(bn_tail["momentum"])
+    t.mean_invstd, t.running_mean = ptr(bn_tail["mean_invstd"]), ptr(bn_tail.get("running_mean"))
+    t.running_var, t.num_batches_tracked = ptr(bn_tail.get("running_var")), ptr(bn_tail.get("num_batches_tracked"))
+    call("sbr_mlp2_fwd_bn", C.byref(desc), int(n_rows), int(C_), ptr(z), z.stride(0), ptr(colstats),
+         int(colstats_rows), C.byref(t), stream_ptr())
 
 
 def mlp2_bwd(desc, n_rows, C_, dy, z, bn, grad_w, grad_b, dx):

@@ -1027,17 +1027,30 @@ class SingleBranchNetEntity(_EntityBase):
         if last.bn is not None:
             n_part = ops.mlp2_colstats_rows(N)
             stats = torch.empty((n_part, 2 * D), dtype=F32, device=dev)
-        ops.mlp2_fwd(desc, N, C_, z, stats, n_part)
+        sync = self.sb_chain.bn_sync if last.bn is not None else None
+        tail = None
+        if last.bn is not None and sync is None and os.environ.get("SBR_MLP2_BN_TAIL", "0") == "1":
+            # BatchNorm statistics finalised by the last CTA of the forward kernel (no sbr_bn_finalize launch).  Opt-in:
+            # measured on the ML-1M step the serial tail of the last CTA (4 us) costs what the PDL-overlapped finalize
+            # launch did (0.295-0.299 ms with it, 0.293 ms without)
+            if getattr(self, "_bn_ticket", None) is None or self._bn_ticket.device != dev:
+                self._bn_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+            mi = torch.empty(2 * D, dtype=F32, device=dev)
+            tail = dict(counter=self._bn_ticket, eps=last.bn.eps, momentum=last.bn.momentum, mean_invstd=mi,
+                        running_mean=last.bn.running_mean, running_var=last.bn.running_var,
+                        num_batches_tracked=last.bn.num_batches_tracked)
+        ops.mlp2_fwd(desc, N, C_, z, stats, n_part, bn_tail=tail)
         E = z
         self.sb_chain.deferred = None
         if last.bn is not None:
             bn = last.bn
-            mi = torch.empty(2 * D, dtype=F32, device=dev)
-            rows_g, sync = N, self.sb_chain.bn_sync
-            if sync is not None:
-                stats, n_part, rows_g = sync.gather_stats(stats), n_part * sync.world, N * sync.world
-            ops.bn_finalize(stats, rows_g, D, mi, bn.running_mean, bn.running_var, bn.num_batches_tracked, eps=bn.eps,
-                            momentum=bn.momentum, n_partials=n_part)
+            if tail is None:
+                mi = torch.empty(2 * D, dtype=F32, device=dev)
+                rows_g = N
+                if sync is not None:
+                    stats, n_part, rows_g = sync.gather_stats(stats), n_part * sync.world, N * sync.world
+                ops.bn_finalize(stats, rows_g, D, mi, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                eps=bn.eps, momentum=bn.momentum, n_partials=n_part)
             if defer_bn:
                 self.sb_chain.deferred = dict(z=z, mean_invstd=mi, gamma=bn.weight.detach(), beta=bn.bias.detach())
                 E = None

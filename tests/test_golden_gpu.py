@@ -436,8 +436,9 @@ def test_fused_mlp_kernels_match_layer_by_layer_path(name, monkeypatch):
     """sbr_mlp2_fwd / sbr_mlp2_bwd (gather + SB-MLP + BatchNorm backward + both wgrads in one persistent kernel per
     direction) against the layer-by-layer kernels on the same inputs: logits, losses and every gradient"""
     res = {}
-    for route in ("0", "1"):
-        monkeypatch.setenv("SBR_FUSED_MLP", route)
+    for route in ("0", "1", "tail"):  # "tail": BatchNorm statistics finalised inside the forward kernel (sbr_mlp2_fwd_bn)
+        monkeypatch.setenv("SBR_FUSED_MLP", "0" if route == "0" else "1")
+        monkeypatch.setenv("SBR_MLP2_BN_TAIL", "1" if route == "tail" else "0")
         spec, g, corpus, model = _build(name)
         model.to(DEV).train()
         _load(model, state_dict_of(g, "sd0/"))
@@ -448,19 +449,20 @@ def test_fused_mlp_kernels_match_layer_by_layer_path(name, monkeypatch):
         model.check_errors()
         used = [getattr(e, "_fused", None) is not None for e in (model.user_embedding_module, model.item_embedding_module)
                 if isinstance(e, SingleBranchNetEntity)]
-        assert any(used) if route == "1" else not any(used)
+        assert any(used) if route != "0" else not any(used)
         params = dict(model.named_parameters())
         res[route] = (tr.logits.cpu().numpy().copy(), tr.read_losses()["train/loss"],
                       {k: tr.grads[id(p)].cpu().numpy().copy() for k, p in params.items()},
                       {k: v.cpu().numpy().copy() for k, v in model.state_dict().items() if "running" in k})
-    assert _maxrel(res["1"][0], res["0"][0]) < 2e-3
-    assert res["1"][1] == pytest.approx(res["0"][1], rel=5e-4)
-    gscale = max(float(np.abs(v).max()) for v in res["0"][2].values())
-    for k, want in res["0"][2].items():
-        got = res["1"][2][k]
-        assert np.abs(got - want).max() <= 1e-2 * np.abs(want).max() + 1e-4 * gscale, k
-    for k, want in res["0"][3].items():
-        assert np.abs(res["1"][3][k] - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), k
+    for route in ("1", "tail"):
+        assert _maxrel(res[route][0], res["0"][0]) < 2e-3
+        assert res[route][1] == pytest.approx(res["0"][1], rel=5e-4)
+        gscale = max(float(np.abs(v).max()) for v in res["0"][2].values())
+        for k, want in res["0"][2].items():
+            got = res[route][2][k]
+            assert np.abs(got - want).max() <= 1e-2 * np.abs(want).max() + 1e-4 * gscale, (route, k)
+        for k, want in res["0"][3].items():
+            assert np.abs(res[route][3][k] - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (route, k)
 
 
 @pytest.mark.parametrize("name,density", [("ml1m_small", "0.004"), ("ml1m_small", "2.0"), ("pairwise_bn2", "2.0"),

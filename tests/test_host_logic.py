@@ -105,6 +105,7 @@ def test_fused_step_and_eval_call_sequence(name, monkeypatch):
     assert seq[0] == "sbr_step_begin" and seq[-1] == "sbr_adam_step" and "sbr_tick" not in seq
     score = "sbr_score_loss_bn" if "sbr_score_loss_bn" in seq else "sbr_score_loss"
     # entities whose single-branch net is 1-2 Linear layers of width <= 64 run the fused gather + MLP kernels
+    seq = ["sbr_mlp2_fwd" if c == "sbr_mlp2_fwd_bn" else c for c in seq]  # (= the forward + in-kernel BatchNorm finalize)
     fused = "sbr_mlp2_fwd" in seq
     assert score in seq and ("sbr_row_gather_fwd" in seq or fused) and "sbr_row_gather_bwd_segmented" in seq
     assert seq.index("sbr_gather_plan") < seq.index("sbr_row_gather_bwd_segmented")
