@@ -381,6 +381,11 @@ int sbr_logit_bias_fwd(float* logits, int64_t B, int n, const int64_t* u_idx, co
 int sbr_logit_bias_bwd(const float* dlogits, int64_t B, int n, const int64_t* u_idx, const int64_t* i_idx,
                        float* d_user_bias, float* d_item_bias, float* d_global_bias, void* stream);
 
+/* Lower clamp of the scores of DeepMatrixFactorization (`sim[sim < mu] = mu`, algorithms/sgd_alg.py:1238-1242), in
+ * place; `clamped` (optional, uint8 [n]) records where, for the backward (no gradient through a clamped score). */
+int sbr_clamp_min_fwd(float* x, int64_t n, float lo, uint8_t* clamped, void* stream);
+int sbr_clamp_min_bwd(float* dx, int64_t n, const uint8_t* clamped, void* stream);
+
 /* aggregation only (eval path): out[r, :] = mean | max over k of e[r, k, :] */
 int sbr_aggregate(const float* e, int64_t rows, int k, int D, int agg_max, float* out_f32, void* out_bf16,
                   int64_t ld_bf16, void* stream);

@@ -705,6 +705,34 @@ extern "C" int sbr_logit_bias_bwd(const float* dlogits, int64_t B, int n, const 
   return SBR_OK;
 }
 
+// x[i] < lo ? lo : x[i]  (in place);  backward: dx[i] = 0 where the forward input was below lo
+__global__ void clamp_min_fwd_kernel(float* __restrict__ x, int64_t n, float lo, uint8_t* __restrict__ clamped) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const bool c = v < lo;
+  if (clamped) clamped[i] = c ? 1 : 0;
+  if (c) x[i] = lo;
+}
+__global__ void clamp_min_bwd_kernel(float* __restrict__ dx, int64_t n, const uint8_t* __restrict__ clamped) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && clamped[i]) dx[i] = 0.f;
+}
+
+extern "C" int sbr_clamp_min_fwd(float* x, int64_t n, float lo, uint8_t* clamped, void* stream) {
+  SBR_REQUIRE(x && n > 0, "sbr_clamp_min_fwd: bad arguments");
+  clamp_min_fwd_kernel<<<cdiv(n, 256), 256, 0, S(stream)>>>(x, n, lo, clamped);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_clamp_min_bwd(float* dx, int64_t n, const uint8_t* clamped, void* stream) {
+  SBR_REQUIRE(dx && clamped && n > 0, "sbr_clamp_min_bwd: bad arguments");
+  clamp_min_bwd_kernel<<<cdiv(n, 256), 256, 0, S(stream)>>>(dx, n, clamped);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
 extern "C" int sbr_aggregate(const float* e, int64_t rows, int k, int D, int agg_max, float* out_f32, void* out_bf16,
                              int64_t ld_bf16, void* stream) {
   SBR_REQUIRE(e && rows > 0 && k >= 1 && D > 0 && (out_f32 || out_bf16), "sbr_aggregate: bad arguments");

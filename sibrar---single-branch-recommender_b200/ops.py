@@ -563,6 +563,15 @@ def logit_bias_fwd(logits, u_idx, i_idx, user_bias=None, item_bias=None, global_
          ptr(global_bias), stream_ptr())
 
 
+def clamp_min_fwd(x, lo, clamped=None):
+    """x = max(x, lo) in place (contiguous fp32); ``clamped`` uint8 like x records where"""
+    call("sbr_clamp_min_fwd", ptr(x), x.numel(), float(lo), ptr(clamped), stream_ptr())
+
+
+def clamp_min_bwd(dx, clamped):
+    call("sbr_clamp_min_bwd", ptr(dx), dx.numel(), ptr(clamped), stream_ptr())
+
+
 def logit_bias_bwd(dlogits, u_idx, i_idx, d_user_bias=None, d_item_bias=None, d_global_bias=None):
     B, n = dlogits.shape
     call("sbr_logit_bias_bwd", ptr(dlogits), int(B), int(n), ptr(u_idx), ptr(i_idx), ptr(d_user_bias), ptr(d_item_bias),

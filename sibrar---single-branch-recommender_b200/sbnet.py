@@ -561,6 +561,7 @@ class PlainEntity(_EntityBase):
         self.agg_max = 0
         self.reg_enabled = False
         self.direct = self._feature_type == "categorical" and self.post_embedding_layers is None
+        self.normalize_output = False  # L2-normalise the gathered rows (DeepMatrixFactorization's cosine scores)
         self._init_runtime(n_entities)
 
     def _materialize(self):
@@ -643,8 +644,8 @@ class PlainEntity(_EntityBase):
             out = torch.empty((flat.numel(), D), dtype=F32, device=flat.device)
         if self._srcs is None:
             self._srcs = self._src_blob(None)
-        ops.row_gather_fwd(self._srcs, 1, flat, None, 1, D, False, 0.0, 0, rt.step_dev, None, out_f32=out,
-                           err_flag=rt.err_flag)
+        ops.row_gather_fwd(self._srcs, 1, flat, None, 1, D, self.normalize_output, 0.0, 0, rt.step_dev, None,
+                           out_f32=out, err_flag=rt.err_flag)
         self._ctx = (flat,)
         return out
 
@@ -662,7 +663,7 @@ class PlainEntity(_EntityBase):
             self._srcs_grad = (grads, self._src_blob(grads))
         plan = _gather_plan(self, self.n_keys, flat.numel(), flat.device)
         plan.build(self._srcs_grad[1], 1, flat, None, 1)
-        plan.backward(self._srcs_grad[1], 1, self.output_dim, False, 0.0, 0, rt.step_dev, None, dE)
+        plan.backward(self._srcs_grad[1], 1, self.output_dim, self.normalize_output, 0.0, 0, rt.step_dev, None, dE)
         if self.direct:
             return
         # table-level backward: G = d loss / d T  (the consumers clear it)
