@@ -2,9 +2,11 @@
 
 The reference is single-device (no collective anywhere); this is the B200 addition:
   * training: data parallel.  Every rank runs the fused step on its own B interactions; the flat fp32 gradient buffer
-    is all-reduced in two buckets -- the item-entity bucket is launched as soon as the item backward has been
-    enqueued, so the collective overlaps the user-entity backward -- and the multi-tensor Adam kernel divides by the
-    world size.  BatchNorm statistics and the user-side in-batch InfoNCE stay rank-local.
+    lives in NVSwitch multicast (symmetric) memory and the all-reduce is the prologue of the optimizer kernel
+    (``sbr_adam_step_mc``: ``multimem.ld_reduce`` / ``multimem.st``, flag barriers over peer memory, 1/world folded into
+    the update) -- no collective node in the step.  Fallback (``SBR_DP_COLLECTIVE=nccl`` or no multicast): two NCCL
+    all-reduce buckets, the item-entity bucket overlapping the user-entity backward.  BatchNorm statistics are rank-local
+    unless ``sync_bn=True``; the user-side in-batch InfoNCE stays rank-local.
   * evaluation: the item catalogue is sharded; each rank computes its items' representations and an exact local
     top-k (packed keys with GLOBAL positions), the [U, k] key lists are all-gathered and merged by
     ``sbr_topk_merge`` -- the only exchange step of the path.
