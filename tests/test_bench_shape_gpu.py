@@ -35,7 +35,9 @@ def _unpack_keep(bits: torch.Tensor, C: int) -> np.ndarray:
     return np.unpackbits(b, axis=1, bitorder="little")[:, :C].astype(np.float32)
 
 
-@pytest.mark.parametrize("batch,batch_norm", [(256, True), (16384, True), (16384, False)])
+# (300, 1000: row counts that are NOT multiples of the fused kernels' 128-row tiles -- a partial last tile behind full ones,
+# on the user side (300 / 1000 rows) and on the item side (3 300 / 11 000 rows))
+@pytest.mark.parametrize("batch,batch_norm", [(256, True), (300, True), (1000, False), (16384, True), (16384, False)])
 def test_graph_step_at_bench_shape_matches_oracle(batch, batch_norm):
     corpus = _corpus()
     train = corpus.dataset("train")
