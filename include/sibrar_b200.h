@@ -372,6 +372,19 @@ int sbr_score_loss_bn(const float* eu, const sbr_bn_inline_t* bn_u, const float*
  * loss_acc[0] += weight * loss; de (+)= weight * dloss/de (accumulate=1 adds to existing gradients). */
 int sbr_infonce(const float* e, int64_t G, int64_t n, int D, float temperature, float weight, double* loss_acc,
                 float* de, int accumulate, float* lse_ws, void* stream);
+/* Large groups (the user side: ONE group of n = B in-batch rows): the n x n logits and both gradient products are
+ * tcgen05 GEMMs (sbr_gemm_bf16) and these are the memory-bound passes between them (train/regularization_losses.py:28-43
+ * evaluated as  L = E0 E1^T / T,  CE over rows + CE over columns):
+ *   split:   e fp32 [n, 2, D] -> bf16 [n, 3 pad8(D)] triples  A3 = [hi0 | lo0 | hi0], B3 = [hi1 | hi1 | lo1]; one GEMM over
+ *            K = 3 pad8(D) then gives the logits to ~2^-16 relative
+ *   lse:     lse_r[i], lse_c[j] of L fp32 [n, n] (n % 4 == 0; partial_ws: 2 * n_chunks * n floats) and
+ *            loss_acc += scale * (sum_i (lse_r[i] - L_ii) + sum_j (lse_c[j] - L_jj))
+ *   weights: W_ij = exp(L_ij - lse_r[i]) + exp(L_ij - lse_c[j]) - 2 delta_ij as bf16 [n, n]:
+ *            dE0 = alpha W E1,  dE1 = alpha W^T E0  with alpha = weight / (n T)  (ops.infonce_gemm) */
+int sbr_infonce_split(const float* e, int64_t n, int D, void* a3, void* b3, void* stream);
+int sbr_infonce_lse(const float* L, int64_t n, float scale, float* lse_r, float* lse_c, float* partial_ws, int n_chunks,
+                    double* loss_acc, void* stream);
+int sbr_infonce_weights(const float* L, int64_t n, const float* lse_r, const float* lse_c, void* W, void* stream);
 
 /* Bias terms of the matrix-factorisation siblings (SGDMatrixFactorization.combine_user_item_representations,
  * algorithms/sgd_alg.py:175-195): logits[b, j] += user_bias[u[b]] + item_bias[i[b, j]] + global_bias[0] (each optional)

@@ -117,6 +117,9 @@ _PROTOS = {
     "sbr_score_loss_bn": [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp,
                           c_vp, C.c_int, c_vp],
     "sbr_infonce": [c_vp, c_i64, c_i64, C.c_int, c_f32, c_f32, c_vp, c_vp, C.c_int, c_vp, c_vp],
+    "sbr_infonce_split": [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp],
+    "sbr_infonce_lse": [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp],
+    "sbr_infonce_weights": [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "sbr_clamp_min_fwd": [c_vp, c_i64, c_f32, c_vp, c_vp],
     "sbr_clamp_min_bwd": [c_vp, c_i64, c_vp, c_vp],
     "sbr_logit_bias_fwd": [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],

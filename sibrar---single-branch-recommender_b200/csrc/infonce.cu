@@ -235,7 +235,183 @@ infonce_group_kernel(const float* __restrict__ e, int64_t G, int n, int D, float
   }
 }
 
+// ------------------------------------------------------------------------------------------------ large groups
+// User side of the train step: ONE group of n = B rows (in-batch negatives).  The n x n logits, the two gradient products
+// and nothing else are GEMMs (sbr_gemm_bf16, tcgen05); the kernels below are the memory-bound passes between them:
+//   split   e (fp32) -> bf16 triples  A3 = [hi0 | lo0 | hi0],  B3 = [hi1 | hi1 | lo1]  so that ONE GEMM with K = 3 D gives
+//           hi0 hi1 + lo0 hi1 + hi0 lo1 = the fp32 logits to ~2^-16 (single bf16 operands would move a logit of a
+//           128-d unit-variance pair by ~0.04 / T)
+//   lse     row / column log-sum-exp of L (online max / sum), the loss terms, then
+//   weights W_ij = exp(L_ij - lse_r[i]) + exp(L_ij - lse_c[j]) - 2 delta_ij  as bf16, the A operand of  dE0 = W E1  and
+//           (MN-major)  dE1 = W^T E0  (scale 1 / (R T) * weight folded into the GEMMs' alpha).
+__global__ void infonce_split_kernel(const float* __restrict__ e, int64_t n, int D, int D8, bf16* __restrict__ a3,
+                                     bf16* __restrict__ b3) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n * D8) return;
+  const int64_t i = t / D8;
+  const int d = (int)(t - i * D8);
+  const float x0 = d < D ? e[(i * 2 + 0) * D + d] : 0.f, x1 = d < D ? e[(i * 2 + 1) * D + d] : 0.f;
+  const bf16 h0 = __float2bfloat16(x0), h1 = __float2bfloat16(x1);
+  const bf16 l0 = __float2bfloat16(x0 - __bfloat162float(h0)), l1 = __float2bfloat16(x1 - __bfloat162float(h1));
+  bf16* a = a3 + i * 3 * D8 + d;
+  bf16* b = b3 + i * 3 * D8 + d;
+  a[0] = h0; a[D8] = l0; a[2 * D8] = h0;
+  b[0] = h1; b[D8] = h1; b[2 * D8] = l1;
+}
+
+__device__ __forceinline__ void online_add(float& m, float& s, float v) {
+  if (v > m) {
+    s = s * __expf(m - v) + 1.f;
+    m = v;
+  } else {
+    s += __expf(v - m);
+  }
+}
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+  const float mm = fmaxf(m, m2);
+  s = (m == -INFINITY ? 0.f : s * __expf(m - mm)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mm));
+  m = mm;
+}
+
+// one warp per row of L [n, n]: lse_r[i]; loss += (lse_r[i] - L_ii) * scale
+__global__ void __launch_bounds__(256)
+infonce_row_lse_kernel(const float* __restrict__ L, int64_t n, float* __restrict__ lse_r, float scale,
+                       double* __restrict__ loss_acc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + warp;
+  double part = 0.0;
+  if (i < n) {
+    const float4* row = reinterpret_cast<const float4*>(L + i * n);
+    float m = -INFINITY, s = 0.f;
+    for (int64_t j = lane; j < n / 4; j += 32) {
+      const float4 v = __ldcs(row + j);
+      online_add(m, s, v.x); online_add(m, s, v.y); online_add(m, s, v.z); online_add(m, s, v.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      online_merge(m, s, m2, s2);
+    }
+    const float lse = m + logf(s);
+    if (lane == 0) {
+      lse_r[i] = lse;
+      part = (double)((lse - L[i * n + i]) * scale);
+    }
+  }
+  __shared__ double s_part[8];
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_acc != nullptr) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+    atomicAdd(loss_acc, t);
+  }
+}
+
+// column pass, step 1: block (x = 32-column group, y = row chunk) -> partial (max, sum) of its columns over its rows
+__global__ void __launch_bounds__(256)
+infonce_col_partial_kernel(const float* __restrict__ L, int64_t n, int64_t rows_per_chunk, float2* __restrict__ partial) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(n, r0 + rows_per_chunk);
+  float m = -INFINITY, s = 0.f;
+  if (c < n)
+    for (int64_t r = r0 + warp; r < r1; r += 8) online_add(m, s, __ldcs(L + r * n + c));
+  __shared__ float sm[8][32], ss[8][32];
+  sm[warp][lane] = m;
+  ss[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < n) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) online_merge(m, s, sm[w][lane], ss[w][lane]);
+    partial[(int64_t)blockIdx.y * n + c] = make_float2(m, s);
+  }
+}
+// step 2: one thread per column merges the chunk partials -> lse_c[j]; loss += (lse_c[j] - L_jj) * scale
+__global__ void __launch_bounds__(256)
+infonce_col_finish_kernel(const float2* __restrict__ partial, int n_chunks, const float* __restrict__ L, int64_t n,
+                          float* __restrict__ lse_c, float scale, double* __restrict__ loss_acc) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double part = 0.0;
+  if (j < n) {
+    float m = -INFINITY, s = 0.f;
+    for (int q = 0; q < n_chunks; ++q) {
+      const float2 p = partial[(int64_t)q * n + j];
+      online_merge(m, s, p.x, p.y);
+    }
+    const float lse = m + logf(s);
+    lse_c[j] = lse;
+    part = (double)((lse - L[j * n + j]) * scale);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  __shared__ double s_part[8];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_acc != nullptr) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+    atomicAdd(loss_acc, t);
+  }
+}
+
+// W = exp(L - lse_r[i]) + exp(L - lse_c[j]) - 2 delta_ij  (bf16), four columns per thread
+__global__ void __launch_bounds__(256)
+infonce_weights_kernel(const float* __restrict__ L, int64_t n, const float* __restrict__ lse_r,
+                       const float* __restrict__ lse_c, bf16* __restrict__ W) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // float4 index
+  const int64_t per_row = n / 4;
+  if (q >= n * per_row) return;
+  const int64_t i = q / per_row, j = (q - i * per_row) * 4;
+  const float4 l = __ldcs(reinterpret_cast<const float4*>(L) + q);
+  const float4 lc = *reinterpret_cast<const float4*>(lse_c + j);
+  const float lr = lse_r[i];
+  float w[4] = {__expf(l.x - lr) + __expf(l.x - lc.x), __expf(l.y - lr) + __expf(l.y - lc.y),
+                __expf(l.z - lr) + __expf(l.z - lc.z), __expf(l.w - lr) + __expf(l.w - lc.w)};
+  if (i >= j && i < j + 4) w[i - j] -= 2.f;
+  uint2 o;
+  *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(w[0], w[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(w[2], w[3]);
+  *reinterpret_cast<uint2*>(W + i * n + j) = o;
+}
+
 }  // namespace
+
+extern "C" int sbr_infonce_split(const float* e, int64_t n, int D, void* a3, void* b3, void* stream) {
+  SBR_REQUIRE(e && a3 && b3 && n > 0 && D > 0, "sbr_infonce_split: bad arguments");
+  const int D8 = (D + 7) & ~7;
+  infonce_split_kernel<<<cdiv(n * D8, 256), 256, 0, S(stream)>>>(e, n, D, D8, reinterpret_cast<bf16*>(a3),
+                                                                  reinterpret_cast<bf16*>(b3));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_infonce_lse(const float* L, int64_t n, float scale, float* lse_r, float* lse_c, float* partial_ws,
+                               int n_chunks, double* loss_acc, void* stream) {
+  SBR_REQUIRE(L && lse_r && lse_c && partial_ws && n > 0 && (n & 3) == 0 && n_chunks >= 1 && n_chunks <= 65535,
+              "sbr_infonce_lse: bad arguments (n must be a multiple of 4)");
+  SBR_REQUIRE((reinterpret_cast<uintptr_t>(L) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial_ws) & 7) == 0,
+              "sbr_infonce_lse: unaligned buffers");
+  infonce_row_lse_kernel<<<cdiv(n, 8), 256, 0, S(stream)>>>(L, n, lse_r, scale, loss_acc);
+  const int64_t rpc = (n + n_chunks - 1) / n_chunks;
+  infonce_col_partial_kernel<<<dim3(cdiv(n, 32), (unsigned)n_chunks), 256, 0, S(stream)>>>(
+      L, n, rpc, reinterpret_cast<float2*>(partial_ws));
+  infonce_col_finish_kernel<<<cdiv(n, 256), 256, 0, S(stream)>>>(reinterpret_cast<const float2*>(partial_ws), n_chunks, L,
+                                                                 n, lse_c, scale, loss_acc);
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
+
+extern "C" int sbr_infonce_weights(const float* L, int64_t n, const float* lse_r, const float* lse_c, void* W,
+                                   void* stream) {
+  SBR_REQUIRE(L && lse_r && lse_c && W && n > 0 && (n & 3) == 0, "sbr_infonce_weights: bad arguments");
+  SBR_REQUIRE((reinterpret_cast<uintptr_t>(L) & 15) == 0 && (reinterpret_cast<uintptr_t>(lse_c) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(W) & 7) == 0,
+              "sbr_infonce_weights: unaligned buffers");
+  infonce_weights_kernel<<<cdiv(n * (n / 4), 256), 256, 0, S(stream)>>>(L, n, lse_r, lse_c, reinterpret_cast<bf16*>(W));
+  SBR_LAUNCH_CHECK();
+  return SBR_OK;
+}
 
 extern "C" int sbr_infonce(const float* e, int64_t G, int64_t n, int D, float temperature, float weight,
                            double* loss_acc, float* de, int accumulate, float* lse_ws, void* stream) {

@@ -418,7 +418,43 @@ def score_loss_bn(eu, bn_u, ei, bn_i, B, n, D, loss_kind, aggregator_sum, ssm_sh
          stream_ptr())
 
 
+INFONCE_GEMM_MIN_N = 1024          # one group of at least this many rows takes the tensor-core route
+INFONCE_GEMM_MAX_BYTES = 24 << 30  # n x n logits (fp32) + weights (bf16)
+
+
+def infonce_gemm(e, n, D, temperature, weight, loss_acc, de, accumulate):
+    """symmetric InfoNCE of ONE group of n rows (e fp32 [n, 2, D]) with the n x n logits and both gradient products on
+    the tensor cores: split-bf16 logits GEMM (K = 3 D) -> row / column log-sum-exp + loss -> softmax-weight matrix ->
+    dE0 = W E1, dE1 = W^T E0 (written / accumulated into ``de`` [n, 2, D])"""
+    dev = e.device
+    D8 = pad8(D)
+    a3 = torch.empty((n, 3 * D8), dtype=BF16, device=dev)
+    b3 = torch.empty((n, 3 * D8), dtype=BF16, device=dev)
+    call("sbr_infonce_split", ptr(e), int(n), int(D), ptr(a3), ptr(b3), stream_ptr())
+    L = torch.empty((n, n), dtype=F32, device=dev)
+    gemm(a3, b3, n, n, 3 * D8, out_f32=L, alpha=1.0 / float(temperature))
+    lse = torch.empty((2, n), dtype=F32, device=dev)
+    n_chunks = max(1, min(64, n // 256))
+    part = torch.empty((n_chunks, n, 2), dtype=F32, device=dev)
+    call("sbr_infonce_lse", ptr(L), int(n), float(weight) / float(n), ptr(lse[0]), ptr(lse[1]), ptr(part), int(n_chunks),
+         ptr(loss_acc), stream_ptr())
+    if de is None:
+        return
+    W = torch.empty((n, n), dtype=BF16, device=dev)
+    call("sbr_infonce_weights", ptr(L), int(n), ptr(lse[0]), ptr(lse[1]), ptr(W), stream_ptr())
+    alpha = float(weight) / (float(n) * float(temperature))
+    d3 = de.view(n, 2, D)
+    # dE0 = alpha W E1 (B = the hi part of E1, [K = n, N = D] MN-major);  dE1 = alpha W^T E0 (A = W read MN-major)
+    gemm(W, b3, n, D, n, b_mn=True, ldb=3 * D8, out_f32=d3[:, 0, :], alpha=alpha, atomic_out=bool(accumulate))
+    gemm(W, a3, n, D, n, a_mn=True, b_mn=True, lda=n, ldb=3 * D8, out_f32=d3[:, 1, :], alpha=alpha,
+         atomic_out=bool(accumulate))
+
+
 def infonce(e, G, n, D, temperature, weight, loss_acc, de, accumulate, lse_ws=None):
+    import os
+    if (G == 1 and n >= INFONCE_GEMM_MIN_N and n % 8 == 0 and D % 8 == 0 and 6 * n * n <= INFONCE_GEMM_MAX_BYTES
+            and os.environ.get("SBR_INFONCE_GEMM", "1") != "0"):
+        return infonce_gemm(e, n, D, temperature, weight, loss_acc, de, accumulate)
     if lse_ws is None:
         lse_ws = torch.empty(2 * G * n, dtype=F32, device=e.device)
     call("sbr_infonce", ptr(e), int(G), int(n), int(D), float(temperature), float(weight), ptr(loss_acc), ptr(de),

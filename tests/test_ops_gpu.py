@@ -501,6 +501,34 @@ def test_infonce(G, n, D, accumulate):
     assert np.abs(de.cpu().numpy() - ref).max() < 1e-5
 
 
+@pytest.mark.parametrize("n,D,scale,temp,accumulate", [(1024, 64, 1.0, 0.5, False), (2048, 128, 1.0, 0.1, True),
+                                                       (1536, 40, 0.3, 1.0, True)])
+def test_infonce_tensor_core_route(n, D, scale, temp, accumulate, monkeypatch):
+    """one large group (the user side: in-batch negatives): logits / gradient products as tcgen05 GEMMs with split-bf16
+    operands (ops.infonce_gemm) against the fp64 oracle (train/regularization_losses.py:28-43) at post-BatchNorm
+    magnitudes (unit-variance elements: |logit| up to ~40 / T), and against the CUDA-core kernels on the same input"""
+    from oracle import sbnet_oracle as O
+    torch.manual_seed(5)
+    e = torch.randn(1, n, 2, D, device=DEV) * scale
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    de = torch.ones_like(e)
+    assert n >= ops.INFONCE_GEMM_MIN_N
+    ops.infonce(e, 1, n, D, temp, 0.3, acc, de, accumulate=accumulate)
+    en = e.double().cpu().numpy()
+    loss, d0, d1 = O.info_nce(en[:, :, 0], en[:, :, 1], temp)
+    assert abs(acc.item() - 0.3 * loss) < 2e-4 * max(1, abs(loss))
+    ref = (1.0 if accumulate else 0.0) + 0.3 * np.stack([d0, d1], axis=2)
+    got = de.cpu().numpy()
+    gmax = np.abs(0.3 * np.stack([d0, d1], axis=2)).max()
+    assert np.abs(got - ref).max() < 1e-2 * gmax  # (bf16 softmax weights and gradient operands; fp32-grade logits)
+    monkeypatch.setenv("SBR_INFONCE_GEMM", "0")
+    acc2 = torch.zeros(1, dtype=torch.float64, device=DEV)
+    de2 = torch.ones_like(e)
+    ops.infonce(e, 1, n, D, temp, 0.3, acc2, de2, accumulate=accumulate)
+    assert abs(acc2.item() - acc.item()) < 2e-4 * max(1, abs(acc2.item()))
+    assert (de2 - de).abs().max().item() < 1e-2 * gmax
+
+
 @pytest.mark.parametrize("decoupled", [0, 1])
 def test_adam(decoupled):
     shapes = [(70, 33), (5000,), (3, 4097), (1,)]
