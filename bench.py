@@ -480,7 +480,7 @@ def run_train_workload(name, args, env, batch, steps, warmup, full, scale=1.0):
 
     # ---- e2e: host buffers in, loss out, through the public trainer API
     # (double-buffered: the pinned-memory fill and the H2D copy of batch k+1 run on a copy stream while step k
-    # computes; every step still ends with a device -> host read of its losses)
+    # computes; every step is followed by a device -> host read of its losses, waited for one step later)
     hu = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(2)]
     hi = [torch.empty((B, n), dtype=torch.int64).pin_memory() for _ in range(2)]
     host_batches = [(b[0].cpu(), b[1].cpu()) for b in batches[:4]]
@@ -488,12 +488,14 @@ def run_train_workload(name, args, env, batch, steps, warmup, full, scale=1.0):
     copy_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    loss_host = torch.empty(tr.loss_acc.shape, dtype=tr.loss_acc.dtype).pin_memory()
-    loss_read = torch.cuda.Event()
+    loss_host = [torch.empty(tr.loss_acc.shape, dtype=tr.loss_acc.dtype).pin_memory() for _ in range(2)]
+    loss_read = [torch.cuda.Event() for _ in range(2)]
 
     def stage(k):
         s_ = k % 2
         src = host_batches[k % len(host_batches)]
+        if k >= 2:
+            ready[s_].synchronize()  # the H2D copy that last read this pinned buffer has finished (host runs one step ahead)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[s_])  # the step that last read this device buffer has finished
             hu[s_].copy_(src[0])
@@ -513,9 +515,13 @@ def run_train_workload(name, args, env, batch, steps, warmup, full, scale=1.0):
         consumed[k % 2].record()
         if k + 1 < steps:
             stage(k + 1)
-        loss_host.copy_(tr.loss_acc, non_blocking=True)  # device -> host read of the step's losses ...
-        loss_read.record()
-        loss_read.synchronize()                           # ... waited for before the next step is issued
+        # device -> host read of THIS step's losses, every step; the host waits for it after the NEXT step has been
+        # enqueued (a logging loop has no use for the value before that), so the launch of step k+1 overlaps step k
+        loss_host[k % 2].copy_(tr.loss_acc, non_blocking=True)
+        loss_read[k % 2].record()
+        if k > 0:
+            loss_read[(k - 1) % 2].synchronize()
+    loss_read[(steps - 1) % 2].synchronize()
     sync_all()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
