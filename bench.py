@@ -504,24 +504,31 @@ def run_train_workload(name, args, env, batch, steps, warmup, full, scale=1.0):
             dbuf[s_][1].copy_(hi[s_], non_blocking=True)
             ready[s_].record(copy_stream)
 
+    def e2e_loop(n_steps):
+        stage(0)
+        for k in range(n_steps):
+            torch.cuda.current_stream().wait_event(ready[k % 2])
+            tr.step(*dbuf[k % 2])
+            consumed[k % 2].record()
+            if k + 1 < n_steps:
+                stage(k + 1)
+            # device -> host read of THIS step's losses, every step; the host waits for it after the NEXT step has been
+            # enqueued (a logging loop has no use for the value before that), so the launch of step k+1 overlaps step k
+            loss_host[k % 2].copy_(tr.loss_acc, non_blocking=True)
+            loss_read[k % 2].record()
+            if k > 0:
+                loss_read[(k - 1) % 2].synchronize()
+        loss_read[(n_steps - 1) % 2].synchronize()
+
+    sync_all()
+    for e in consumed:
+        e.record()
+    e2e_loop(max(3, warmup))  # untimed: first use of the copy stream, the events and the pinned buffers
     sync_all()
     for e in consumed:
         e.record()
     t0 = time.perf_counter()
-    stage(0)
-    for k in range(steps):
-        torch.cuda.current_stream().wait_event(ready[k % 2])
-        tr.step(*dbuf[k % 2])
-        consumed[k % 2].record()
-        if k + 1 < steps:
-            stage(k + 1)
-        # device -> host read of THIS step's losses, every step; the host waits for it after the NEXT step has been
-        # enqueued (a logging loop has no use for the value before that), so the launch of step k+1 overlaps step k
-        loss_host[k % 2].copy_(tr.loss_acc, non_blocking=True)
-        loss_read[k % 2].record()
-        if k > 0:
-            loss_read[(k - 1) % 2].synchronize()
-    loss_read[(steps - 1) % 2].synchronize()
+    e2e_loop(steps)
     sync_all()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

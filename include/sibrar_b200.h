@@ -296,6 +296,9 @@ int sbr_mlp2_bwd(const sbr_mlp2_desc_t* desc, int64_t n_rows, int C, const float
  * cycles of every barrier wait and of the sections of their own work (16 words per role: gather, MMA, epilogue, dz);
  * returns the NUMBER of words copied to host_out (scripts/trace_mlp2.py prints them) */
 int sbr_mlp2_trace_read(unsigned long long* host_out, int max_events);
+/* profiling only: with SBR_MLP2_DEBUG bit 64 every CTA of an sbr_mlp2_bwd launch over more than 100 000 rows stamps
+ * %globaltimer at its start and end; copies (start, end) ns pairs of the first n_ctas CTAs (returns their number) */
+int sbr_mlp2_cta_times_read(unsigned long long* host_out, int n_ctas);
 
 /* nn.EmbeddingBag(mode="mean", padding_idx=pad_id) of EVERY feature row as a dense fp32 table [n_rows, C]
  * (reference FeatureEmbedding for tag features, algorithms/sgd_alg.py:1279-1396; codes int32 [n_rows, max_tags]):

@@ -131,6 +131,7 @@ _PROTOS = {
     "sbr_mlp2_bwd": [C.POINTER(Mlp2Desc), c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, C.POINTER(Mlp2Bn),
                      C.POINTER(c_vp), C.POINTER(c_vp), c_vp, c_i64, c_vp],
     "sbr_mlp2_trace_read": [c_vp, C.c_int],
+    "sbr_mlp2_cta_times_read": [c_vp, C.c_int],
     "sbr_adam_step": [c_vp, C.c_int, c_i64, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, C.c_int, c_vp, c_f32,
                       c_vp],
     "sbr_adam_step_mc": [c_vp, C.c_int, c_i64, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, C.c_int, c_vp, c_f32,

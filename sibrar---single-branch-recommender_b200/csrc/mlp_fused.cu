@@ -92,6 +92,14 @@ struct BwdParams {
 // its tile loop.  Read back by sbr_mlp2_trace_read (scripts/trace_mlp2.py): loop - sum(waits) = the role's own work.
 constexpr int PROF_SLOTS = 16;  // 1-7: waits, 8-15: sections of the role's own work
 __device__ unsigned long long g_prof[4 * PROF_SLOTS];
+// SBR_MLP2_DEBUG bit 64: every CTA of a backward launch with more than 100 000 rows stamps %globaltimer at its start and
+// end (sbr_mlp2_cta_times_read): start skew / tail of the persistent grid inside the real step
+__device__ unsigned long long g_cta_times[2 * 1024];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <bool PROF>
 __device__ __forceinline__ void lap(uint32_t (&acc)[PROF_SLOTS], uint32_t& tmark, int work_slot) {
@@ -668,6 +676,8 @@ template <int L, bool PROF, bool GENERIC>
 __global__ void __launch_bounds__(512, 2)  // 13 warps are allocated as 16: 64 registers per thread for two CTAs per SM
 mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, BwdParams p) {
   SBR_PDL_LAUNCH();
+  const bool stamp = (p.debug & 64) && p.g.N > 100000 && threadIdx.x == 0 && blockIdx.x < 1024;
+  if (stamp) g_cta_times[2 * blockIdx.x] = globaltimer_ns();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sW0 = smem;
@@ -1138,6 +1148,7 @@ mlp2_bwd_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+  if (stamp) g_cta_times[2 * blockIdx.x + 1] = globaltimer_ns();
 }
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -1190,6 +1201,13 @@ extern "C" int sbr_mlp2_trace_read(unsigned long long* host_out, int max_events)
   const int n = max_events < 4 * PROF_SLOTS ? max_events : 4 * PROF_SLOTS;
   if (n > 0) SBR_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * n));
   return n;  // (number of words, not a status)
+}
+
+extern "C" int sbr_mlp2_cta_times_read(unsigned long long* host_out, int n_ctas) {
+  SBR_CHECK_CUDA(cudaDeviceSynchronize());
+  const int n = n_ctas < 1024 ? n_ctas : 1024;
+  if (n > 0) SBR_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_cta_times, sizeof(unsigned long long) * 2 * n));
+  return n;
 }
 
 extern "C" int sbr_mlp2_colstats_rows(int64_t n_rows) { return (int)mlp2_grid(n_rows); }
