@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import sibrar_b200  # noqa
-import bench
+from sibrar_b200 import workloads
 from sibrar_b200 import ops
 from sibrar_b200.sbnet import SingleBranchNet
 from sibrar_b200.synthetic import SynCorpus
@@ -12,11 +12,11 @@ from sibrar_b200.trainer import FusedTrainer
 
 B = 16384
 dev = torch.device("cuda", 0)
-corpus = SynCorpus("ml1m", "cold_start_item", seed=42)
+corpus, _conf, _learn, _, _ = workloads.build("ml1m")
 train = corpus.dataset("train")
 torch.manual_seed(1234)
-model = SingleBranchNet.build_from_conf(bench.ml1m_model_conf(), train).to(dev).train()
-tr = FusedTrainer(model, bench.LEARN, n_negative_samples=bench.N_NEG)
+model = SingleBranchNet.build_from_conf(_conf, train).to(dev).train()
+tr = FusedTrainer(model, _learn, n_negative_samples=workloads.N_NEG)
 coo = train.interaction_matrix
 d = lambda a, t: torch.from_numpy(np.ascontiguousarray(a).astype(t)).to(dev)
 csr = train.user_sampling_matrix_train
