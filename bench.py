@@ -797,7 +797,8 @@ def bench_eval_split(torch, model, corpus, FullEvaluator, env, graph=True):
 
 
 SWEEP = ((100_000, 100_000, 64, 10), (100_000, 1_000_000, 64, 10), (100_000, 1_000_000, 128, 50),
-         (100_000, 1_000_000, 256, 10), (100_000, 1_000_000, 512, 10), (100_000, 10_000_000, 64, 10))
+         (100_000, 1_000_000, 256, 10), (100_000, 1_000_000, 512, 10), (100_000, 10_000_000, 64, 10),
+         (100_000, 10_000_000, 256, 50))  # (the largest point: 5 GB of item embeddings, ~0.5 s on one GPU)
 
 
 def bench_eval_sweep(torch, ops, env):
