@@ -14,6 +14,8 @@ HBM layout per feature (row = position in the feature's value table, NOT the ent
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -87,7 +89,6 @@ class DeviceFeature:
             # the reference feeds the stored values (``csr[rows].toarray().float()``, data/Feature.py:147-150): duplicate
             # history rows are counts > 1 in its sampling matrices.  None = all ones (the bit-packed route needs that).
             vals = None if binary else torch.from_numpy(m.data.astype(np.float32)).to(device)
-            import os
             if (density >= dense_min_density and binary and m.shape[0] * m.shape[1] // 4 <= dense_max_bytes
                     and os.environ.get("SBR_BITS", "1") != "0"):
                 # bit-packed multi-hot rows (and the transposed matrix for the wgrad), 1 bit per element in HBM:
