@@ -11,7 +11,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libsibrar_b200.so")
+# SBR_LIB_PATH: another build of the same library (the timeline build `make -C csrc stamps`: scripts/step_timeline.py)
+LIB_PATH = os.environ.get("SBR_LIB_PATH") or os.path.join(CSRC, "libsibrar_b200.so")
 
 ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "selu": 4}
 SRC_TABLE, SRC_CATEGORICAL, SRC_TAG = 0, 1, 2

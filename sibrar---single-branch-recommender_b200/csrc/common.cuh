@@ -50,16 +50,62 @@ typedef __nv_bfloat16 bf16;
 // of the stream be scheduled as soon as all CTAs of this one are running (its prologue / block dispatch overlaps our
 // tail) and then waits until the PREVIOUS kernel has completed and flushed its memory.  Nothing before the wait may
 // touch global memory.  Without the launch attribute (plain <<<>>> launches) both instructions are no-ops.
+// Timeline build only (-DSBR_STAMPS, `make stamps` -> libsibrar_b200_stamps.so, scripts/step_timeline.py): thread 0 of
+// block 0 of every kernel records %globaltimer right behind its griddepcontrol.wait -- the moment its inputs are ready
+// inside the replayed graph -- tagged with (hash of the source file, line of the macro).  The production library
+// contains none of this.
+#ifdef SBR_STAMPS
+static __device__ unsigned long long* g_sbr_stamps;  // [0] = count, then (time ns, tag) pairs; one copy per translation unit
+__host__ __device__ constexpr unsigned sbr_fid(const char* s) {
+  unsigned h = 2166136261u;
+  for (; *s; ++s) h = (h ^ (unsigned)*s) * 16777619u;
+  return h & 0xffffu;
+}
+__device__ __forceinline__ void sbr_stamp(unsigned fid, int line) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
+    unsigned long long* b = g_sbr_stamps;
+    if (b != nullptr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      const unsigned long long i = atomicAdd(b, 1ull);
+      if (i < 4000) {
+        b[1 + 2 * i] = t;
+        b[2 + 2 * i] = ((unsigned long long)(gridDim.x * gridDim.y * gridDim.z) << 32) | ((unsigned long long)fid << 16) |
+                       (unsigned long long)(line & 0xffff);
+      }
+    }
+  }
+}
+void sbr_register_tu(int (*setter)(unsigned long long*));  // util.cu
+static int sbr_tu_set_stamps(unsigned long long* p) {
+  return (int)cudaMemcpyToSymbol(g_sbr_stamps, &p, sizeof(p));
+}
+namespace {
+struct SbrTuReg {
+  SbrTuReg() { sbr_register_tu(sbr_tu_set_stamps); }
+};
+static SbrTuReg sbr_tu_reg;
+}  // namespace
+#define SBR_STAMP() sbr_stamp(sbr_fid(__FILE__), __LINE__)
+#else
+#define SBR_STAMP() ((void)0)
+#endif
+
 #define SBR_PDL_ENTRY()                                                   \
   do {                                                                    \
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");       \
     asm volatile("griddepcontrol.wait;" ::: "memory");                    \
+    SBR_STAMP();                                                          \
   } while (0)
 
 // the two halves, for kernels with a real prologue (barrier / TMEM set-up, shared-memory clears): the prologue runs
 // while the previous kernel drains; only what follows SBR_PDL_WAIT() may touch memory the previous kernel wrote
 #define SBR_PDL_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
-#define SBR_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define SBR_PDL_WAIT()                                                    \
+  do {                                                                    \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                    \
+    SBR_STAMP();                                                          \
+  } while (0)
 
 static inline int sbr_pdl_enabled() {
   static int v = -1;

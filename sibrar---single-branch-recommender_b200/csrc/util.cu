@@ -677,3 +677,18 @@ extern "C" int sbr_sample_negatives(const int32_t* coo_user, const int32_t* coo_
   return SBR_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ timeline build
+#ifdef SBR_STAMPS
+static int (*g_tu_setters[32])(unsigned long long*);
+static int g_n_tu = 0;
+void sbr_register_tu(int (*setter)(unsigned long long*)) {
+  if (g_n_tu < 32) g_tu_setters[g_n_tu++] = setter;
+}
+// buf: device uint64 [1 + 2 * 4000] (word 0 = number of stamps, zeroed by the caller), or NULL to switch stamping off
+extern "C" int sbr_debug_stamps(unsigned long long* buf) {
+  for (int i = 0; i < g_n_tu; ++i)
+    if (g_tu_setters[i](buf) != 0) return 1;
+  return 0;
+}
+#endif

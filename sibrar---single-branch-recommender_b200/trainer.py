@@ -142,7 +142,7 @@ class FusedTrainer:
         # The user and the item side of a step only meet in the score/loss kernel and in Adam.  Their kernels are small
         # (tens of CTAs for the table projections, one CTA for the BatchNorm finalisers), so the user side runs on a
         # side stream -- a parallel branch of the captured graph -- next to the (longer) item side.
-        side = self._side_stream(u_idxs.device) if (self.branches and u_idxs.is_cuda) else None
+        side = self._side_stream(u_idxs.device, small_batch=B * n <= 16384) if (self.branches and u_idxs.is_cuda) else None
         rt.branches = side is not None and self.branches >= 2
         main = torch.cuda.current_stream() if side is not None else None
         sb_u, sb_i = isinstance(self.user, SingleBranchNetEntity), isinstance(self.item, SingleBranchNetEntity)
@@ -219,7 +219,14 @@ class FusedTrainer:
     def _alloc_flat_grads(self, total: int, dev):
         return torch.zeros(total, dtype=F32, device=dev)
 
-    def _side_stream(self, device):
+    def _side_stream(self, device, small_batch: bool = False):
+        """the user branch's stream.  Small batches (fixed-cost kernels everywhere): high priority, so the short user chain
+        is never queued behind the item chain's table projections (0.167 vs 0.187 ms per step at B = 256; at B = 16 384 the
+        same priority costs 14 %, so large batches keep the default)"""
+        if small_batch and os.environ.get("SBR_SIDE_PRIORITY", "auto") != "0":
+            if getattr(self, "_side_hi", None) is None:
+                self._side_hi = torch.cuda.Stream(device=device, priority=-1)
+            return self._side_hi
         if self._side is None:
             self._side = torch.cuda.Stream(device=device)
         return self._side
