@@ -164,6 +164,17 @@ class ZeroArena:
         return self.buf[start:start + size].view(dtype)
 
 
+# CTAs per SM a split-K projection / wgrad GEMM aims at.  2 fills the machine with one GEMM; under the two-branch step
+# (FusedTrainer sets 1) the user-side and the item-side GEMM are launched together, and two 145-CTA grids that run SIDE BY
+# SIDE (23 us) beat two 290-CTA grids that run one after the other (2 x 16 us): scripts/step_timeline.py
+SPLITK_FILL = 2
+
+
+def splitk_fill() -> int:
+    e = os.environ.get("SBR_SPLITK_FILL")
+    return int(e) if e else SPLITK_FILL
+
+
 def run_branches(thunks, streams):
     """fork/join: ``thunks[0]`` runs on the current stream, ``thunks[j]`` on ``streams[j - 1]``, all of them after
     what the current stream holds so far; the current stream continues after all of them.  Under CUDA-graph capture
@@ -228,7 +239,7 @@ class Chain:
         num_kb = -(-st.in_f // 64)
         if tiles * 2 > n_sms or num_kb < 16:
             return 1
-        return max(1, min(num_kb // 4, (2 * n_sms) // tiles))
+        return max(1, min(num_kb // 4, (splitk_fill() * n_sms) // tiles))
 
     def forward(self, x16, rows, training, arena: ZeroArena, keep_for_backward=True, out32=None,
                 defer_final_bn=False, ref=None):
@@ -398,7 +409,7 @@ class Chain:
             else:
                 x16 = st.x if (si > 0 or self.feature is None or self._first_x is not None) else self.feature.x16
                 tiles = -(-st.in_f // 128) * -(-st.out_f // (64 if st.out_f <= 64 else 128 if st.out_f <= 128 else 256))
-                split = ops.effective_splits(rows, max(1, min(-(-rows // 64), (2 * n_sms) // max(1, tiles))))
+                split = ops.effective_splits(rows, max(1, min(-(-rows // 64), (splitk_fill() * n_sms) // max(1, tiles))))
                 # wgrad partitions accumulate with fp32 atomics (measured faster than private slices + a reduce pass at
                 # every shape of the ML-1M step; SBR_SLICED_MIN_SPLIT selects the deterministic sliced variant)
                 sliced = split >= int(os.environ.get("SBR_SLICED_MIN_SPLIT", 1 << 30)) and \

@@ -85,6 +85,9 @@ class FusedTrainer:
         # user side / item side of the step on two streams (SBR_BRANCHES=0: one stream)
         # 2 (default): + weight-gradient GEMMs and per-modality table chains on further streams
         self.branches = int(os.environ.get("SBR_BRANCHES", "2"))
+        if self.branches:
+            from . import sbnet as _sbnet
+            _sbnet.SPLITK_FILL = 1  # the two entities' split-K GEMMs run side by side (sbnet.SPLITK_FILL)
         self._side = None
         # debugging / parity tests: a copy of the flat gradient buffer taken inside the step right before the optimizer
         # consumes (and clears) it -- also inside the captured graph
