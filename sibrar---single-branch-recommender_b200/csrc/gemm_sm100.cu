@@ -30,7 +30,8 @@ template <int BN>
 struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int B_STAGE_BYTES = BN * 128;
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;  // + barriers + align slack
+  static constexpr int LUT_BYTES = 4096;  // byte -> eight bf16 table of the bit-packed A operand
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + LUT_BYTES + 1024;  // + barriers + align slack
 };
 
 // butterfly transpose-reduce: on return lane l holds sum over the warp's 32 lanes of v[l]
@@ -121,14 +122,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + C::STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint2* s_lut = reinterpret_cast<uint2*>(tmem_slot + 2);  // A_BITS: nibble -> four bf16 (0.0 | 1.0)
+  // A_BITS: byte -> eight bf16 (0.0 | 1.0) = one 16-byte chunk of the K-major stage per lookup
+  uint4* s_lut = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (A_BITS && threadIdx.x < 16) {
+  if (A_BITS && threadIdx.x < 256) {
     const uint32_t t = threadIdx.x;
-    s_lut[t] = make_uint2(((t & 1u) ? 0x3F80u : 0u) | ((t & 2u) ? 0x3F800000u : 0u),
-                          ((t & 4u) ? 0x3F80u : 0u) | ((t & 8u) ? 0x3F800000u : 0u));
+    const auto pair = [t](int b) { return ((t >> b) & 1u ? 0x3F80u : 0u) | ((t >> (b + 1)) & 1u ? 0x3F800000u : 0u); };
+    s_lut[t] = make_uint4(pair(0), pair(2), pair(4), pair(6));
   }
   // persistent over the M tiles: CTA x handles tiles x, x + gridDim.x, ...; the two TMEM accumulators let the MMA of
   // tile t+1 run while the epilogue warps drain tile t (skinny layers are bound by the epilogue's HBM traffic)
@@ -257,8 +259,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (uint32_t c = 0; c < 8; ++c) {  // chunk c = K elements 8c .. 8c+7 -> 16 bytes at the swizzled position
               const uint32_t byte = ((c < 4 ? w.x : w.y) >> ((c & 3) * 8)) & 0xFFu;
-              const uint2 lo = s_lut[byte & 15u], hi = s_lut[byte >> 4];
-              *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+              *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = s_lut[byte];
             }
             fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
