@@ -83,8 +83,8 @@ int sbr_splitk_reduce(const float* partials, int n_splits, int64_t split_stride,
 
 /* Same GEMM with a BIT-PACKED 0/1 A operand (K-major): bit k of row m = A_bits[m * ld_words + k / 32] >> (k % 32).
  * The multi-hot 'interactions' rows (data/Feature.py:147-150: csr.toarray() per batch in the reference) stay packed in
- * HBM (1 bit per element) and are expanded to bf16 in shared memory inside the kernel.  ld_words is even and covers
- * whole 64-bit K blocks; bits at k >= K are zero.  Used for the forward projection (A = the entity's interaction
+ * HBM (1 bit per element) and are expanded to bf16 in shared memory inside the kernel (the bit words arrive there by TMA).  ld_words is a multiple
+ * of 4 (16-byte rows, A_bits 16-byte aligned) and covers whole 64-bit K blocks; bits at k >= K are zero.  Used for the forward projection (A = the entity's interaction
  * matrix) and for its wgrad (A = the transposed matrix, output written transposed). */
 int sbr_gemm_bits_bf16(const uint32_t* A_bits, int64_t ld_words, const void* B, int64_t ldb, int b_mn_major, int64_t M,
                        int64_t N, int64_t K, const sbr_gemm_epilogue_t* ep, void* stream);

@@ -26,12 +26,19 @@ struct GemmParams {
   sbr_gemm_epilogue_t ep;
 };
 
+constexpr int BITS_GROUP = 4;  // K blocks per TMA load of the bit-packed A operand (32 bytes per row)
+
 template <int BN>
 struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int LUT_BYTES = 4096;  // byte -> eight bf16 table of the bit-packed A operand
+  // bit-packed A operand: ring of TMA-loaded groups of BITS_GROUP K blocks ([BM rows] x [8 bytes per K block])
+  static constexpr int BITS_SLOTS = 2;
+  static constexpr int BITS_SLOT_BYTES = BM * 8 * BITS_GROUP;
   static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + LUT_BYTES + 1024;  // + barriers + align slack
+  // (BN = 64: 111 872 bytes, so that two CTAs -- the user- and the item-side projection -- still share an SM)
+  static constexpr int SMEM_BYTES_BITS = SMEM_BYTES + BITS_SLOTS * BITS_SLOT_BYTES;
 };
 
 // butterfly transpose-reduce: on return lane l holds sum over the warp's 32 lanes of v[l]
@@ -102,6 +109,24 @@ __device__ __forceinline__ void apply_actgrad32(int act, float (&v)[32], const f
 // tensor cores see ordinary bf16 operands; the TMA producer then only loads B.
 // epilogue warps: 4 (one per TMEM lane quarter) next to the bit converters, else 8 -- two warps per lane quarter, each
 // draining every other 32-column chunk: skinny layers (K = N = 64) are bound by the epilogue's instruction stream
+// timing diagnostics of the bit-packed GEMM (scripts/gemm_bits_variants.sh): each switch removes one part of the kernel
+// (results are then wrong); the product build leaves all of them on
+#ifndef SBR_GB_LOAD
+#define SBR_GB_LOAD 1
+#endif
+#ifndef SBR_GB_STS
+#define SBR_GB_STS 1
+#endif
+#ifndef SBR_GB_FENCE
+#define SBR_GB_FENCE 1
+#endif
+#ifndef SBR_GB_TMA
+#define SBR_GB_TMA 1
+#endif
+#ifndef SBR_GB_EPI
+#define SBR_GB_EPI 1
+#endif
+
 template <bool A_BITS>
 struct Warps {
   static constexpr int EPI = A_BITS ? 4 : 8;
@@ -117,13 +142,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + C::STAGES * C::B_STAGE_BYTES);
+  // A_BITS: [BITS_SLOTS][BM][8 * BITS_GROUP] bit words behind the operand ring (1024-byte aligned TMA destination)
+  uint8_t* s_bits = sB + C::STAGES * C::B_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bits + (A_BITS ? C::BITS_SLOTS * C::BITS_SLOT_BYTES : 0));
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   // A_BITS: byte -> eight bf16 (0.0 | 1.0) = one 16-byte chunk of the K-major stage per lookup
   uint4* s_lut = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+  uint64_t* bits_full = reinterpret_cast<uint64_t*>(tmem_slot + 2);    // [BITS_SLOTS] group landed (TMA)
+  uint64_t* bits_empty = bits_full + C::BITS_SLOTS;                    // [BITS_SLOTS] group read by the 4 converter warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,6 +179,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], Warps<A_BITS>::EPI);
     }
+    if (A_BITS) {
+      for (int b = 0; b < C::BITS_SLOTS; ++b) {
+        mbar_init(&bits_full[b], 1);
+        mbar_init(&bits_empty[b], 4);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN);
@@ -163,12 +198,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
     int s = 0;
     uint32_t ph = 0;
+    // A_BITS: the bit words of tile rows x BITS_GROUP K blocks arrive by TMA, one group ahead of the group whose B
+    // tiles are being issued (sequence number bq over all (tile, group) pairs of this CTA; slot = bq % BITS_SLOTS).
+    // The slot's previous group was read into registers by the converters before they filled the A stages this warp
+    // has just seen released, so the wait below does not block.
+    // (a TMA box has to start on a 16-byte boundary of the row: groups are counted from the even K block kb_al)
+    const int kb_al = kb_begin & ~1;
+    const int n_groups = (kb_end - kb_al + BITS_GROUP - 1) / BITS_GROUP;
+    int bq = 0, b_tile = blockIdx.x, b_g = 0;
+    auto issue_bits = [&]() {
+      if (!SBR_GB_LOAD || b_tile >= num_m_tiles) return;
+      const int slot = bq % C::BITS_SLOTS;
+      mbar_wait(&bits_empty[slot], (uint32_t)(((bq / C::BITS_SLOTS) & 1) ^ 1));
+      mbar_arrive_expect_tx(&bits_full[slot], C::BITS_SLOT_BYTES);
+      tma_load_2d(s_bits + slot * C::BITS_SLOT_BYTES, &tmA, &bits_full[slot], (kb_al + b_g * BITS_GROUP) * 8,
+                  b_tile * BM);
+      ++bq;
+      if (++b_g == n_groups) { b_g = 0; b_tile += gridDim.x; }
+    };
+    if (A_BITS && elect_one()) issue_bits();
+    __syncwarp();
     for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
       const int m0 = tile * BM;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[s], (A_BITS ? 0 : A_STAGE_BYTES) + C::B_STAGE_BYTES);
+          if (A_BITS && (kb == kb_begin || (kb - kb_al) % BITS_GROUP == 0)) issue_bits();
+          mbar_arrive_expect_tx(&full_bar[s], (A_BITS ? 0 : A_STAGE_BYTES) + (SBR_GB_TMA ? C::B_STAGE_BYTES : 0));
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           uint8_t* b_dst = sB + s * C::B_STAGE_BYTES;
           if (A_BITS) {
@@ -179,7 +235,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full_bar[s], m0 + j * 64, kb * BK);
           }
-          if (!p.b_mn) {
+          if (!SBR_GB_TMA) {
+          } else if (!p.b_mn) {
             tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
           } else {
 #pragma unroll
@@ -233,35 +290,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t row_off = (uint32_t)((row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128);
     int s = 0;
     uint32_t ph = 0;
+    int bq = 0;  // (tile, group) sequence number, as in the producer
+    const uint4* my_bits = reinterpret_cast<const uint4*>(s_bits + row_in_tile * (8 * BITS_GROUP));
     for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
-      const int64_t row = (int64_t)tile * BM + row_in_tile;
-      const uint2* bits = reinterpret_cast<const uint2*>(p.a_bits + (row < p.M ? row : 0) * p.ld_words);
-      // the row's bit words are fetched 8 K blocks at a time, one batch ahead of the batch being expanded: a thread's
-      // 8-byte loads are strided by the row pitch (one 32-byte sector per row), so their latency has to be overlapped
-      constexpr int NB = 8;
-      uint2 nxt[NB];
+      for (int kb0 = kb_begin & ~1; kb0 < kb_end; kb0 += BITS_GROUP, ++bq) {
+        // this row's bit words of BITS_GROUP K blocks (rows past M and K blocks past the row pitch arrive as zeros)
+        uint2 curw[BITS_GROUP];
+        if (SBR_GB_LOAD) {
+          const int slot = bq % C::BITS_SLOTS;
+          mbar_wait(&bits_full[slot], (uint32_t)((bq / C::BITS_SLOTS) & 1));
+          const uint4* src = my_bits + slot * (C::BITS_SLOT_BYTES / 16);
 #pragma unroll
-      for (int q = 0; q < NB; ++q)
-        nxt[q] = (row < p.M && kb_begin + q < kb_end) ? __ldg(bits + kb_begin + q) : make_uint2(0u, 0u);
-      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += NB) {
-        uint2 curw[NB];
+          for (int q = 0; q < BITS_GROUP; q += 2) {
+            const uint4 v = src[q / 2];
+            curw[q] = make_uint2(v.x, v.y);
+            curw[q + 1] = make_uint2(v.z, v.w);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bits_empty[slot]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < NB; ++q) curw[q] = nxt[q];
+          for (int q = 0; q < BITS_GROUP; ++q) curw[q] = make_uint2(0u, 0u);
+        }
 #pragma unroll
-        for (int q = 0; q < NB; ++q)
-          nxt[q] = (row < p.M && kb0 + NB + q < kb_end) ? __ldg(bits + kb0 + NB + q) : make_uint2(0u, 0u);
-#pragma unroll
-        for (int q = 0; q < NB; ++q) {
-          if (kb0 + q < kb_end) {  // 64 bits = one K block of this row
+        for (int q = 0; q < BITS_GROUP; ++q) {
+          if (kb0 + q >= kb_begin && kb0 + q < kb_end) {  // 64 bits = one K block of this row
             const uint2 w = curw[q];
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* dst = sA + s * A_STAGE_BYTES + row_off;
 #pragma unroll
-            for (uint32_t c = 0; c < 8; ++c) {  // chunk c = K elements 8c .. 8c+7 -> 16 bytes at the swizzled position
+            for (uint32_t c = 0; c < (SBR_GB_STS ? 8u : 0u); ++c) {  // chunk c = K elements 8c .. 8c+7 -> 16 bytes at the swizzled position
               const uint32_t byte = ((c < 4 ? w.x : w.y) >> ((c & 3) * 8)) & 0xFFu;
               *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = s_lut[byte];
             }
-            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+            if (SBR_GB_FENCE) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
             if (++s == C::STAGES) { s = 0; ph ^= 1; }
@@ -285,7 +347,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
     const int acc = it & 1;
     const int64_t row = (int64_t)tile * BM + row_in_tile;
-    const bool row_ok = row < p.M;
+    const bool row_ok = SBR_GB_EPI && row < p.M;
     mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
     tc_fence_after();
 #pragma unroll 1
@@ -443,7 +505,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   static bool configured = false;
   if (!configured) {
     SBR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg<BN>::SMEM_BYTES));
+                                        A_BITS ? Cfg<BN>::SMEM_BYTES_BITS : Cfg<BN>::SMEM_BYTES));
     configured = true;
   }
   const int64_t n_tiles = (p.N + BN - 1) / BN;
@@ -451,7 +513,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   SBR_REQUIRE(p.ep.colstats == nullptr || p.ep.colstats_rows == 0 || p.ep.colstats_rows >= 4 * gx,
               "sbr_gemm: colstats_rows=%d < %lld partial rows", p.ep.colstats_rows, (long long)(4 * gx));
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);
-  SBR_CHECK_CUDA(sbr_launch(gemm_bf16_kernel<BN, A_BITS>, grid, dim3(Warps<A_BITS>::THREADS), (size_t)Cfg<BN>::SMEM_BYTES, st,
+  SBR_CHECK_CUDA(sbr_launch(gemm_bf16_kernel<BN, A_BITS>, grid, dim3(Warps<A_BITS>::THREADS),
+                            (size_t)(A_BITS ? Cfg<BN>::SMEM_BYTES_BITS : Cfg<BN>::SMEM_BYTES), st,
                             tmA, tmB, p));
   return SBR_OK;
 }
@@ -491,6 +554,23 @@ int sbr_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, ui
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SBR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu)",
               (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems);
+  return SBR_OK;
+}
+
+// bit-packed A operand as a byte matrix [M, ld_bytes]: box = BM rows x (8 bytes per K block x BITS_GROUP), no swizzle,
+// rows / bytes outside the matrix arrive as zeros
+static int sbr_make_tmap_bits_2d(CUtensorMap* out, const void* base, uint64_t ld_bytes, uint64_t rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  SBR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t dims[2] = {ld_bytes, rows};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {8 * BITS_GROUP, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SBR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (bit matrix) failed with CUresult %d (rows=%llu ld_bytes=%llu)",
+              (int)r, (unsigned long long)rows, (unsigned long long)ld_bytes);
   return SBR_OK;
 }
 
@@ -546,9 +626,10 @@ extern "C" int sbr_gemm_bits_bf16(const uint32_t* A_bits, int64_t ld_words, cons
   SBR_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31),
               "sbr_gemm_bits_bf16: bad problem M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   const int num_kb = (int)((K + BK - 1) / BK);
-  SBR_REQUIRE(ld_words % 2 == 0 && ld_words >= 2 * (int64_t)num_kb &&
-                  (reinterpret_cast<uintptr_t>(A_bits) & 7) == 0,
-              "sbr_gemm_bits_bf16: rows must be 8-byte aligned and padded to whole 64-bit K blocks (ld_words=%lld)",
+  // (the bit words reach shared memory by TMA: 16-byte aligned rows)
+  SBR_REQUIRE(ld_words % 4 == 0 && ld_words >= 2 * (int64_t)num_kb &&
+                  (reinterpret_cast<uintptr_t>(A_bits) & 15) == 0,
+              "sbr_gemm_bits_bf16: rows must be 16-byte aligned and padded to whole 64-bit K blocks (ld_words=%lld)",
               (long long)ld_words);
   SBR_REQUIRE(ep->out_bf16 || ep->out_f32 || ep->colstats, "sbr_gemm_bits_bf16: no output requested");
   SBR_REQUIRE(!(ep->transpose_out && ep->out_bf16), "sbr_gemm_bits_bf16: transposed output is fp32 only");
@@ -558,8 +639,9 @@ extern "C" int sbr_gemm_bits_bf16(const uint32_t* A_bits, int64_t ld_words, cons
                               !ep->bias && ep->act == SBR_ACT_NONE && !ep->actgrad_y),
               "sbr_gemm_bits_bf16: split_k > 1 needs a pure fp32 epilogue (atomic, or one slice per partition)");
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  CUtensorMap tmB;
-  int rc;
+  CUtensorMap tmBits, tmB;
+  int rc = sbr_make_tmap_bits_2d(&tmBits, A_bits, (uint64_t)ld_words * 4, (uint64_t)M);
+  if (rc) return rc;
   if (!b_mn_major) rc = sbr_make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)BN);
   else rc = sbr_make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
   if (rc) return rc;
@@ -576,8 +658,8 @@ extern "C" int sbr_gemm_bits_bf16(const uint32_t* A_bits, int64_t ld_words, cons
   if (p.ep.alpha == 0.f) p.ep.alpha = 1.f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (BN) {
-    case 64: return launch_gemm<64, true>(tmB, tmB, p, splits, st);
-    case 128: return launch_gemm<128, true>(tmB, tmB, p, splits, st);
-    default: return launch_gemm<256, true>(tmB, tmB, p, splits, st);
+    case 64: return launch_gemm<64, true>(tmBits, tmB, p, splits, st);
+    case 128: return launch_gemm<128, true>(tmBits, tmB, p, splits, st);
+    default: return launch_gemm<256, true>(tmBits, tmB, p, splits, st);
   }
 }

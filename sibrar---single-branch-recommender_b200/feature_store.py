@@ -7,7 +7,7 @@ HBM layout per feature (row = position in the feature's value table, NOT the ent
   * ``remap``  int32 [n_entities]  entity index -> row (-1: entity has no row; identity maps are dropped)
   * dense (VECTOR / CONTINUOUS / DISCRETE, and 'interactions' when dense enough):
         ``x16`` bf16 [n_rows, pad8(d)]  row-major -- read K-major by the forward GEMM and MN-major by the wgrad GEMM
-  * bits ('interactions', density >= 0.4 %): ``bits`` int32 [n_rows, 2*ceil(d/64)] and ``bits_t`` of the transposed
+  * bits ('interactions', density >= 0.4 %): ``bits`` int32 [n_rows, 4*ceil(d/128)] and ``bits_t`` of the transposed
         matrix -- 1 bit per element; expanded to bf16 in shared memory by the GEMM (sbr_gemm_bits_bf16)
   * csr ('interactions', sparse route): ``indptr`` int64 / ``indices`` int32 of the matrix and of its transpose
   * CATEGORICAL: ``codes`` int32 [n_rows];  TAG: ``codes`` int32 [n_rows, max_tags] padded with ``pad_id``

@@ -91,10 +91,10 @@ def effective_splits(K: int, split_k: int) -> int:
 
 
 def pack_bits(csr, device) -> torch.Tensor:
-    """scipy CSR 0/1 matrix -> int32 [rows, ld_words] bit matrix (ld_words even, whole 64-bit K blocks, zero padded)"""
+    """scipy CSR 0/1 matrix -> int32 [rows, ld_words] bit matrix (16-byte rows, whole 64-bit K blocks, zero padded)"""
     import numpy as np
     rows, cols = csr.shape
-    ld_words = 2 * ((cols + 63) // 64)
+    ld_words = 4 * ((cols + 127) // 128)  # 16-byte row pitch: the kernel fetches the bit words by TMA
     out = np.zeros((rows, ld_words), dtype=np.uint32)
     coo = csr.tocoo()
     np.bitwise_or.at(out, (coo.row, coo.col // 32), (np.uint32(1) << (coo.col % 32).astype(np.uint32)))
