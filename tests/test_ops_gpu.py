@@ -79,7 +79,7 @@ def test_gemm_dgrad_b_mn_major_actgrad(rows, din, dout):
 
 
 @pytest.mark.parametrize("rows,d,out,density", [(300, 200, 64, 0.05), (1000, 6040, 64, 0.04), (257, 130, 24, 0.3),
-                                                  (3706, 777, 128, 0.02), (40000, 300, 64, 0.03)])
+                                                  (3706, 777, 128, 0.02), (40000, 300, 64, 0.03), (500, 300, 192, 0.05)])
 def test_gemm_bits_matches_dense(rows, d, out, density):
     """bit-packed multi-hot A operand == the same GEMM on the dense bf16 matrix (forward and wgrad forms)"""
     import scipy.sparse as sp
