@@ -32,7 +32,7 @@ template <int BN>
 struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int B_STAGE_BYTES = BN * 128;
-  static constexpr int LUT_BYTES = 4096;  // byte -> eight bf16 table of the bit-packed A operand
+  static constexpr int LUT_BYTES = 4096;  // (comparison build -DSBR_GB_LUT=1: byte -> eight bf16 table in shared memory)
   // bit-packed A operand: ring of TMA-loaded groups of BITS_GROUP K blocks ([BM rows] x [8 bytes per K block])
   static constexpr int BITS_SLOTS = 2;
   static constexpr int BITS_SLOT_BYTES = BM * 8 * BITS_GROUP;
@@ -117,6 +117,9 @@ __device__ __forceinline__ void apply_actgrad32(int act, float (&v)[32], const f
 #ifndef SBR_GB_STS
 #define SBR_GB_STS 1
 #endif
+#ifndef SBR_GB_LUT
+#define SBR_GB_LUT 0
+#endif
 #ifndef SBR_GB_FENCE
 #define SBR_GB_FENCE 1
 #endif
@@ -125,6 +128,17 @@ __device__ __forceinline__ void apply_actgrad32(int act, float (&v)[32], const f
 #endif
 #ifndef SBR_GB_EPI
 #define SBR_GB_EPI 1
+#endif
+
+// per-CTA phase trace of the bit-packed GEMM (-DSBR_GB_TRACE, scripts/gemm_bits_trace.py): clock64 relative to the
+// kernel entry at a handful of points, %globaltimer at entry and exit
+#ifdef SBR_GB_TRACE
+__device__ unsigned long long g_gb_trace[1024 * 16];
+#define GB_T(slot) do { if (A_BITS && lane == 0 && cta_lin < 1024) g_gb_trace[cta_lin * 16 + (slot)] = (unsigned long long)(clock64() - t_entry); } while (0)
+#define GB_T1(slot, cond) do { if (cond) GB_T(slot); } while (0)
+#else
+#define GB_T(slot) do { } while (0)
+#define GB_T1(slot, cond) do { } while (0)
 #endif
 
 template <bool A_BITS>
@@ -137,6 +151,15 @@ template <int BN, bool A_BITS>
 __global__ void __launch_bounds__(Warps<A_BITS>::THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   SBR_PDL_LAUNCH();  // (the wait follows the barrier / TMEM set-up: the prologue overlaps the previous kernel's tail)
+#ifdef SBR_GB_TRACE
+  const long long t_entry = clock64();
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (A_BITS && threadIdx.x == 0 && cta_lin < 1024) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_gb_trace[cta_lin * 16 + 0] = gt;
+  }
+#endif
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -149,14 +172,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + C::STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  // A_BITS: byte -> eight bf16 (0.0 | 1.0) = one 16-byte chunk of the K-major stage per lookup
   uint4* s_lut = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
   uint64_t* bits_full = reinterpret_cast<uint64_t*>(tmem_slot + 2);    // [BITS_SLOTS] group landed (TMA)
   uint64_t* bits_empty = bits_full + C::BITS_SLOTS;                    // [BITS_SLOTS] group read by the 4 converter warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (A_BITS && threadIdx.x < 256) {
+  if (A_BITS && SBR_GB_LUT && threadIdx.x < 256) {
     const uint32_t t = threadIdx.x;
     const auto pair = [t](int b) { return ((t >> b) & 1u ? 0x3F80u : 0u) | ((t >> (b + 1)) & 1u ? 0x3F800000u : 0u); };
     s_lut[t] = make_uint4(pair(0), pair(2), pair(4), pair(6));
@@ -192,7 +214,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GB_T1(1, warp == 0);
   SBR_PDL_WAIT();  // nothing above reads or writes global memory
+  GB_T1(2, warp == 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
@@ -238,6 +262,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!SBR_GB_TMA) {
           } else if (!p.b_mn) {
             tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+            GB_T1(11, kb == kb_begin);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
@@ -262,6 +287,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[s], ph);
+        GB_T1(3, kb == kb_begin);
+        GB_T1(4, kb == kb_begin + 4);
+        GB_T1(13, kb == kb_begin + 8);
+        GB_T1(14, kb == kb_begin + 12);
         tc_fence_after();
         const uint32_t a_addr = sA_addr + (uint32_t)(s * A_STAGE_BYTES);
         const uint32_t b_addr = sB_addr + (uint32_t)(s * C::B_STAGE_BYTES);
@@ -281,6 +310,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
       if (elect_one()) umma_commit(&tfull_bar[acc]);
+      GB_T(5);
       __syncwarp();
     }
   } else if (A_BITS && warp >= 6) {
@@ -299,6 +329,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (SBR_GB_LOAD) {
           const int slot = bq % C::BITS_SLOTS;
           mbar_wait(&bits_full[slot], (uint32_t)((bq / C::BITS_SLOTS) & 1));
+          GB_T1(9, bq == 0 && warp == 6);
           const uint4* src = my_bits + slot * (C::BITS_SLOT_BYTES / 16);
 #pragma unroll
           for (int q = 0; q < BITS_GROUP; q += 2) {
@@ -321,11 +352,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (uint32_t c = 0; c < (SBR_GB_STS ? 8u : 0u); ++c) {  // chunk c = K elements 8c .. 8c+7 -> 16 bytes at the swizzled position
               const uint32_t byte = ((c < 4 ? w.x : w.y) >> ((c & 3) * 8)) & 0xFFu;
-              *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = s_lut[byte];
+              if (SBR_GB_LUT) {
+                *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = s_lut[byte];
+              } else {
+                // two bits -> two bf16 (0.0 | 1.0) in one word, in registers: bit 0 -> bit 7, bit 1 -> bit 23 (the two
+                // shifted copies of the byte do not overlap, so the product has no carries), then x 0x7F turns each
+                // single bit into the seven mantissa / exponent bits of 0x3F80.  The shared-memory pipe (table reads
+                // with bank conflicts + stage stores + the tensor core's operand reads) bounded this kernel at
+                // ~1000 cycles per K block (scripts/gemm_bits_trace.py).
+                const auto two = [](uint32_t t) { return ((t * 0x00400080u) & 0x00800080u) * 0x7Fu; };
+                *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) =
+                    make_uint4(two(byte), two(byte >> 2), two(byte >> 4), two(byte >> 6));
+              }
             }
             if (SBR_GB_FENCE) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
+            GB_T1(10, kb0 + q == kb_begin && warp == 6);
             if (++s == C::STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -349,6 +392,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int64_t row = (int64_t)tile * BM + row_in_tile;
     const bool row_ok = SBR_GB_EPI && row < p.M;
     mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
+    GB_T1(6, warp == 2);
     tc_fence_after();
 #pragma unroll 1
     for (int c0 = 32 * half; c0 < BN; c0 += 32 * NH) {
@@ -458,6 +502,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+    GB_T1(7, warp == 2);
     // this warp is done with the accumulator
     tc_fence_before();
     __syncwarp();
@@ -486,6 +531,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  GB_T1(8, warp == 0);
+#ifdef SBR_GB_TRACE
+  if (A_BITS && threadIdx.x == 0 && cta_lin < 1024) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_gb_trace[cta_lin * 16 + 12] = gt;
+  }
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN < 32 ? 32 : 2 * BN);
@@ -617,6 +670,12 @@ extern "C" int sbr_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const v
     default: return launch_gemm<256, false>(tmA, tmB, p, splits, st);
   }
 }
+
+#ifdef SBR_GB_TRACE
+extern "C" int sbr_debug_gemm_bits_trace(unsigned long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, g_gb_trace, sizeof(g_gb_trace));
+}
+#endif
 
 extern "C" int sbr_gemm_colstats_rows(int64_t M, int64_t N) { return (int)(4 * gemm_grid_x(M, N, 1)); }
 
