@@ -351,7 +351,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* dst = sA + s * A_STAGE_BYTES + row_off;
 #pragma unroll
             for (uint32_t c = 0; c < (SBR_GB_STS ? 8u : 0u); ++c) {  // chunk c = K elements 8c .. 8c+7 -> 16 bytes at the swizzled position
-              const uint32_t byte = ((c < 4 ? w.x : w.y) >> ((c & 3) * 8)) & 0xFFu;
+              const uint32_t byte = __byte_perm(c < 4 ? w.x : w.y, 0u, 0x4440u | (c & 3u));
               if (SBR_GB_LUT) {
                 *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = s_lut[byte];
               } else {
@@ -360,9 +360,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // single bit into the seven mantissa / exponent bits of 0x3F80.  The shared-memory pipe (table reads
                 // with bank conflicts + stage stores + the tensor core's operand reads) bounded this kernel at
                 // ~1000 cycles per K block (scripts/gemm_bits_trace.py).
-                const auto two = [](uint32_t t) { return ((t * 0x00400080u) & 0x00800080u) * 0x7Fu; };
-                *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) =
-                    make_uint4(two(byte), two(byte >> 2), two(byte >> 4), two(byte >> 6));
+                // (one multiply spreads all eight bits of the byte: bit j -> bits j + 7 and j + 22)
+                const uint32_t y = byte * 0x00400080u;
+                const auto two = [y](int i) { return ((y >> (2 * i)) & 0x00800080u) * 0x7Fu; };
+                *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(two(0), two(1), two(2), two(3));
               }
             }
             if (SBR_GB_FENCE) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
