@@ -127,3 +127,21 @@ def test_fused_step_and_eval_call_sequence(name, monkeypatch):
                          "ndcg@5", "ndcg@5_std", "recall@1", "recall@1_std", "recall@3", "recall@3_std", "recall@5",
                          "recall@5_std"]
     assert model.training  # evaluate() restores the mode it found
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 1), (7, 64), (9, 130), (33, 6040)])
+def test_pack_bits_layout(rows, cols):
+    """host layout of the bit-packed multi-hot operand (`include/sibrar_b200.h`, sbr_gemm_bits_bf16): bit k of row m =
+    word k // 32, bit k % 32; 16-byte row pitch (the kernel fetches the words by TMA), whole 64-bit K blocks, zero
+    padding -- the dense matrix the reference builds per batch (data/Feature.py:147-150) is recovered bit for bit"""
+    import scipy.sparse as sp
+    m = sp.random(rows, cols, density=0.3, format="csr", random_state=rows * 1000 + cols)
+    m.data[:] = 1
+    bits = ops.pack_bits(m, "cpu")
+    assert bits.dtype == torch.int32 and bits.shape[0] == rows
+    ld_words = bits.shape[1]
+    assert ld_words % 4 == 0 and ld_words * 32 >= 64 * ((cols + 63) // 64) and bits.stride(0) == ld_words
+    words = bits.numpy().view(np.uint32)
+    dense = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(rows, ld_words * 32)
+    assert np.array_equal(dense[:, :cols], m.toarray().astype(np.uint32))
+    assert not dense[:, cols:].any()
