@@ -105,8 +105,8 @@ __device__ __forceinline__ void apply_actgrad32(int act, float (&v)[32], const f
 
 // A_BITS: the A operand is a bit-packed 0/1 matrix (multi-hot 'interactions' rows, data/Feature.py:147-150).  Four extra
 // warps expand it into the bf16 SWIZZLE_128B K-major stage in shared memory (thread = tile row, 64 bits -> eight
-// 16-byte chunks per K block through a 16-entry nibble table), so HBM sees 1 bit per element instead of 16 and the
-// tensor cores see ordinary bf16 operands; the TMA producer then only loads B.
+// 16-byte chunks per K block, expanded in registers), so HBM sees 1 bit per element instead of 16 and the tensor cores
+// see ordinary bf16 operands; the TMA producer loads B and, as 32-byte row segments, the bit words.
 // epilogue warps: 4 (one per TMEM lane quarter) next to the bit converters, else 8 -- two warps per lane quarter, each
 // draining every other 32-column chunk: skinny layers (K = N = 64) are bound by the epilogue's instruction stream
 // timing diagnostics of the bit-packed GEMM (scripts/gemm_bits_variants.sh): each switch removes one part of the kernel
